@@ -1,0 +1,15 @@
+// Internal helpers shared by the translation units of libffvc_sm100.so.
+#pragma once
+#include "../../include/ffvc.h"
+
+namespace ffvc {
+int set_error(int code, const char* msg);
+void count_launch(int n = 1);
+}  // namespace ffvc
+
+#define FFVC_CHECK_LAUNCH()                                                        \
+  do {                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess) return ffvc::set_error(FFVC_ERR_CUDA, cudaGetErrorString(e__)); \
+    ffvc::count_launch();                                                          \
+  } while (0)

@@ -1,0 +1,576 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a — the tensor-core workhorse of the train step.
+//
+//   D[b][m][n] (+)= alpha * sum_k A[m][k] * B[n][k]      (bf16 operands, fp32 accumulate in TMEM)
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor -> 4-stage smem ring, 128B swizzle)
+//   warp 1      : MMA issuer    (one thread issues tcgen05.mma, M=128, N=BLOCK_N, K=16 x 4 per stage)
+//   warps 2..5  : epilogue      (tcgen05.ld 32x32b -> registers -> bias/activation/residual -> global)
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+//
+// Operand modes (runtime, resolved by the producer / descriptor builder only):
+//   K-major   : operand stored [rows][K] with K contiguous        (fwd Linear:  X[M,K], W[N,K])
+//   MN-major  : operand stored [K][rows] with rows contiguous     (dgrad: W as B; wgrad: dY, X)
+//   CONV3X3   : A is an NHWC image; the 9 taps x Cin/64 channel chunks form the K loop, each
+//               A tile is one 4-D TMA box (zero fill outside the image = padding 1)
+// Replaces, on the reference's path, every nn.Linear / Conv1d(k=1) of the mappers
+// (mlp_mixer_pytorch.py:16-23,32; vitgan.py:31-33,64-67), taming's Conv2d 3x3 / 1x1 in the VQGAN decoder
+// (call site main.py:142), and the CLIP ViT linears (cloob.py:188-196,224,249).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "ffvc_internal.h"
+#include "ptx.cuh"
+
+namespace ffvc {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;
+static constexpr int kStages = 4;
+static constexpr int kStageABytes = kBlockM * kBlockK * 2;  // 16 KB
+static constexpr int kStageBBytes = 256 * kBlockK * 2;      // 32 KB (max BLOCK_N)
+static constexpr int kStageBytes = kStageABytes + kStageBBytes;
+static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int kNumThreads = 192;
+static constexpr int kTmemCols = 512;
+
+struct GemmDev {
+  int M, N;
+  int batch;            // output batches
+  int block_n;          // 32 / 64 / 128 / 256
+  int a_mode, b_mode;   // FFVC_OP_*
+  int kb_per_seg;       // ceil(K / 64)
+  int k_segs;           // contraction additionally runs over this many "segments" (dim2 of the maps)
+  int a_c2_out, a_c2_seg, b_c2_out, b_c2_seg;  // dim2 coordinate = out_batch*x_out + seg*x_seg
+  int splits;           // split-K factor (atomic fp32 accumulation)
+  int conv_h, conv_w, conv_cblocks, conv_tile_w, conv_dil;
+  // epilogue
+  void* out;
+  void* pre_out;
+  const __nv_bfloat16* aux;
+  const __nv_bfloat16* res;
+  const float* bias;
+  long long ldc;
+  long long out_bs;
+  int out_fp32;
+  int atomic;
+  int bias_mode;  // 0 none, 1 per column, 2 per row
+  int act;        // FFVC_ACT_*
+  int mul_mode;   // multiply by act'(aux): FFVC_ACT_*
+  float alpha;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == FFVC_ACT_GELU) return gelu_f(v);
+  if (act == FFVC_ACT_QUICKGELU) return quick_gelu_f(v);
+  if (act == FFVC_ACT_SWISH) return swish_f(v);
+  return v;
+}
+__device__ __forceinline__ float apply_act_grad(float x, int act) {
+  if (act == FFVC_ACT_GELU) return gelu_grad_f(x);
+  if (act == FFVC_ACT_QUICKGELU) return quick_gelu_grad_f(x);
+  if (act == FFVC_ACT_SWISH) return swish_grad_f(x);
+  return 1.0f;
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by the 128B swizzle atoms.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;
+  // barrier layout (8 bytes each): full[4], empty[4], tmem_full[2], tmem_empty[2], then tmem ptr slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_m = (p.M + kBlockM - 1) / kBlockM;
+  const int tiles_n = (p.N + p.block_n - 1) / p.block_n;
+  const int tiles_per_batch = tiles_m * tiles_n;
+  const int total_kb = p.kb_per_seg * p.k_segs;
+  const long long total_tiles = (long long)tiles_per_batch * p.batch * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = (int)(t / ((long long)tiles_per_batch * p.batch));
+        const int rem = (int)(t % ((long long)tiles_per_batch * p.batch));
+        const int bi = rem / tiles_per_batch;
+        const int tm = (rem % tiles_per_batch) / tiles_n;
+        const int tn = rem % tiles_n;
+        const int m0 = tm * kBlockM, n0 = tn * p.block_n;
+        const int kb_begin = (int)((long long)total_kb * split / p.splits);
+        const int kb_end = (int)((long long)total_kb * (split + 1) / p.splits);
+        // conv: decompose the flattened pixel index of the tile origin
+        int cimg = 0, cy0 = 0, cx0 = 0;
+        if (p.a_mode == FFVC_OP_CONV3X3) {
+          const int hw = p.conv_h * p.conv_w;
+          cimg = m0 / hw;
+          const int r = m0 % hw;
+          cy0 = r / p.conv_w;
+          cx0 = r % p.conv_w;
+        }
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kStageABytes;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, (uint32_t)kStageABytes + b_bytes);
+          const int seg = kb / p.kb_per_seg;
+          const int k0 = (kb % p.kb_per_seg) * kBlockK;
+          // ---- A
+          if (p.a_mode == FFVC_OP_KMAJOR) {
+            tma_load_3d(sa, &tmap_a, fb, k0, m0, bi * p.a_c2_out + seg * p.a_c2_seg);
+          } else if (p.a_mode == FFVC_OP_MNMAJOR) {
+            const int c2 = bi * p.a_c2_out + seg * p.a_c2_seg;
+            tma_load_3d(sa, &tmap_a, fb, m0, k0, c2);
+            tma_load_3d(sa + 64 * kBlockK * 2, &tmap_a, fb, m0 + 64, k0, c2);
+          } else {
+            const int kk = kb % p.kb_per_seg;
+            const int tap = kk / p.conv_cblocks;
+            const int c0 = (kk % p.conv_cblocks) * kBlockK;
+            const int dy = (tap / 3 - 1) * p.conv_dil, dx = (tap % 3 - 1) * p.conv_dil;
+            tma_load_4d(sa, &tmap_a, fb, c0, cx0 + dx, cy0 + dy, cimg);
+          }
+          // ---- B
+          if (p.b_mode == FFVC_OP_KMAJOR) {
+            tma_load_3d(sb, &tmap_b, fb, k0, n0, bi * p.b_c2_out + seg * p.b_c2_seg);
+          } else {
+            const int c2 = bi * p.b_c2_out + seg * p.b_c2_seg;
+            for (int j = 0; j < p.block_n / 64; ++j)
+              tma_load_3d(sb + j * 64 * kBlockK * 2, &tmap_b, fb, n0 + 64 * j, k0, c2);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(p.block_n, p.a_mode == FFVC_OP_MNMAJOR, p.b_mode == FFVC_OP_MNMAJOR);
+      // K-major : 8-row groups 1024 B apart (SBO), one swizzle atom along K (LBO unused), K step = 32 B
+      // MN-major: 64-wide MN chunks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), K step = 2048 B
+      const uint32_t a_lbo = (p.a_mode == FFVC_OP_MNMAJOR) ? 64u * kBlockK * 2u : 16u;
+      const uint32_t b_lbo = (p.b_mode == FFVC_OP_MNMAJOR) ? 64u * kBlockK * 2u : 16u;
+      const uint32_t a_kstep = (p.a_mode == FFVC_OP_MNMAJOR) ? 2048u : 32u;
+      const uint32_t b_kstep = (p.b_mode == FFVC_OP_MNMAJOR) ? 2048u : 32u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = (int)(t / ((long long)tiles_per_batch * p.batch));
+        const int kb_begin = (int)((long long)total_kb * split / p.splits);
+        const int kb_end = (int)((long long)total_kb * (split + 1) / p.splits);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sb = sa + kStageABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
+            const uint64_t db = umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ld_ok = (p.ldc % 8 == 0) && (p.out_bs % 8 == 0);
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int rem = (int)(t % ((long long)tiles_per_batch * p.batch));
+      const int bi = rem / tiles_per_batch;
+      const int tm = (rem % tiles_per_batch) / tiles_n;
+      const int tn = rem % tiles_n;
+      const int gm = tm * kBlockM + row;
+      const int n0 = tn * p.block_n;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const long long row_off = (long long)bi * p.out_bs + (long long)gm * p.ldc;
+      const float rbias = (p.bias_mode == 2 && gm < p.M) ? p.bias[gm] : 0.0f;
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * 256 + c) + ((uint32_t)(q * 32) << 16);
+        tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        if (c + 32 >= p.block_n) {
+          // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        const int gn0 = n0 + c;
+        if (gm < p.M && gn0 < p.N) {
+        const int ncols = min(32, p.N - gn0);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+        if (p.bias_mode == 1) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < ncols) v[i] += p.bias[gn0 + i];
+        } else if (p.bias_mode == 2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] += rbias;
+        }
+        const long long off = row_off + gn0;
+        const bool full_vec = vec_ld_ok && (ncols == 32);
+        if (p.pre_out != nullptr) {
+          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(p.pre_out) + off;
+          if (full_vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i + 0], v[i + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(po + i) = pk;
+            }
+          } else {
+            for (int i = 0; i < ncols; ++i) po[i] = __float2bfloat16(v[i]);
+          }
+        }
+        if (p.act != FFVC_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+        }
+        if (p.mul_mode != FFVC_ACT_NONE) {
+          const __nv_bfloat16* ax = p.aux + off;
+          if (full_vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(ax + i);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h[j]);
+                v[i + 2 * j] *= apply_act_grad(f.x, p.mul_mode);
+                v[i + 2 * j + 1] *= apply_act_grad(f.y, p.mul_mode);
+              }
+            }
+          } else {
+            for (int i = 0; i < ncols; ++i) v[i] *= apply_act_grad(__bfloat162float(ax[i]), p.mul_mode);
+          }
+        }
+        if (p.res != nullptr) {
+          const __nv_bfloat16* rs = p.res + off;
+          if (full_vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(rs + i);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(h[j]);
+                v[i + 2 * j] += f.x;
+                v[i + 2 * j + 1] += f.y;
+              }
+            }
+          } else {
+            for (int i = 0; i < ncols; ++i) v[i] += __bfloat162float(rs[i]);
+          }
+        }
+        if (p.out_fp32) {
+          float* o = reinterpret_cast<float*>(p.out) + off;
+          if (p.atomic) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < ncols) atomicAdd(o + i, v[i]);
+          } else if (ncols == 32 && (p.ldc % 4 == 0) && (p.out_bs % 4 == 0)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+            for (int i = 0; i < ncols; ++i) o[i] = v[i];
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+          if (full_vec) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              uint4 pk;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i + 0], v[i + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(o + i) = pk;
+            }
+          } else {
+            for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(v[i]);
+          }
+        }
+        }  // active row / column chunk
+        __syncwarp();
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// dims/strides in elements (bf16); rank 3 or 4; dim0 contiguous.
+static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                     const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return set_error(FFVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 1; i < rank; ++i) {
+    gstr[i - 1] = strides_elems[i] * 2ull;
+    if (gstr[i - 1] % 16 != 0) return set_error(FFVC_ERR_ARG, "gemm: operand stride not a multiple of 16 bytes");
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return set_error(FFVC_ERR_ARG, "gemm: operand not 16B aligned");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf),
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+             (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0,
+             rank > 3 ? box[3] : 0);
+    return set_error(FFVC_ERR_CUDA, buf);
+  }
+  return FFVC_OK;
+}
+
+static int g_num_sms = 0;
+static bool g_attr_set = false;
+
+}  // namespace ffvc
+
+using namespace ffvc;
+
+extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  if (!g || !g->a || !g->b || !g->out) return set_error(FFVC_ERR_ARG, "gemm: null pointer");
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return set_error(FFVC_ERR_ARG, "gemm: non-positive dimension");
+  const int batch = g->batch > 0 ? g->batch : 1;
+  const int k_segs = g->k_segs > 0 ? g->k_segs : 1;
+  int splits = g->splits > 0 ? g->splits : 1;
+  if (splits > 1 && !(g->out_fp32 && g->atomic)) return set_error(FFVC_ERR_ARG, "gemm: split-K needs fp32 atomic output");
+  if (g->b_mode == FFVC_OP_CONV3X3) return set_error(FFVC_ERR_ARG, "gemm: conv mode is for operand A only");
+
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) return set_error(FFVC_ERR_CUDA, "gemm: no CUDA device");
+  }
+  if (!g_attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+    g_attr_set = true;
+  }
+
+  // ---- tile N
+  int block_n = g->block_n;
+  if (block_n <= 0) {
+    if (g->N > 128) block_n = 256;
+    else if (g->N > 64) block_n = 128;
+    else if (g->N > 32) block_n = 64;
+    else block_n = 32;
+    // prefer more tiles when the problem is small: fill the SMs
+    const long long tm = (g->M + kBlockM - 1) / kBlockM;
+    while (block_n > 64 && tm * ((g->N + block_n - 1) / block_n) * batch * splits < g_num_sms) block_n >>= 1;
+  }
+  if (block_n != 32 && block_n != 64 && block_n != 128 && block_n != 256)
+    return set_error(FFVC_ERR_ARG, "gemm: block_n must be 32/64/128/256");
+  if (g->b_mode == FFVC_OP_MNMAJOR && block_n < 64) block_n = 64;
+
+  GemmDev p;
+  memset(&p, 0, sizeof(p));
+  p.M = g->M;
+  p.N = g->N;
+  p.batch = batch;
+  p.block_n = block_n;
+  p.a_mode = g->a_mode;
+  p.b_mode = g->b_mode;
+  p.k_segs = k_segs;
+  p.splits = splits;
+  p.a_c2_out = (g->a_batch_role == FFVC_ROLE_OUT_BATCH);
+  p.a_c2_seg = (g->a_batch_role == FFVC_ROLE_K_SEGMENT);
+  p.b_c2_out = (g->b_batch_role == FFVC_ROLE_OUT_BATCH);
+  p.b_c2_seg = (g->b_batch_role == FFVC_ROLE_K_SEGMENT);
+
+  CUtensorMap ta, tb;
+  int rc;
+  // ---- operand A
+  if (g->a_mode == FFVC_OP_CONV3X3) {
+    const int H = g->conv_h, W = g->conv_w, C = g->conv_c;
+    if (H <= 0 || W <= 0 || C <= 0 || C % 64 != 0) return set_error(FFVC_ERR_ARG, "conv: Cin must be a multiple of 64");
+    const int tile_w = W < 128 ? W : 128;
+    if (128 % tile_w != 0 || W % tile_w != 0) return set_error(FFVC_ERR_ARG, "conv: W must divide or be a multiple of 128");
+    const int tile_h = 128 / tile_w;
+    if (H % tile_h != 0) return set_error(FFVC_ERR_ARG, "conv: H*W must tile by 128 pixels");
+    const long long npix = (long long)g->conv_n * H * W;
+    if (npix != g->M) return set_error(FFVC_ERR_ARG, "conv: M must equal N_img*H*W");
+    if (g->K != 9 * C) return set_error(FFVC_ERR_ARG, "conv: K must equal 9*Cin");
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)g->conv_n};
+    uint64_t str[4] = {1, (uint64_t)C, (uint64_t)W * C, (uint64_t)H * W * C};
+    uint32_t box[4] = {64, (uint32_t)tile_w, (uint32_t)tile_h, 1};
+    if ((rc = make_tmap(&ta, g->a, 4, dims, str, box)) != FFVC_OK) return rc;
+    p.conv_h = H;
+    p.conv_w = W;
+    p.conv_cblocks = C / 64;
+    p.conv_tile_w = tile_w;
+    p.conv_dil = 1;
+    p.kb_per_seg = 9 * (C / 64);
+  } else {
+    p.kb_per_seg = (g->K + kBlockK - 1) / kBlockK;
+    const uint64_t nb = (g->a_batch_role == FFVC_ROLE_OUT_BATCH) ? batch : (g->a_batch_role == FFVC_ROLE_K_SEGMENT ? k_segs : 1);
+    const uint64_t bs = nb > 1 ? (uint64_t)g->a_batch_stride : (uint64_t)g->a_ld * 8;  // any valid stride for size-1 dim
+    if (g->a_mode == FFVC_OP_KMAJOR) {
+      uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->M, nb};
+      uint64_t str[3] = {1, (uint64_t)g->a_ld, bs};
+      uint32_t box[3] = {64, 128, 1};
+      if ((rc = make_tmap(&ta, g->a, 3, dims, str, box)) != FFVC_OK) return rc;
+    } else {
+      uint64_t dims[3] = {(uint64_t)g->M, (uint64_t)g->K, nb};
+      uint64_t str[3] = {1, (uint64_t)g->a_ld, bs};
+      uint32_t box[3] = {64, 64, 1};
+      if ((rc = make_tmap(&ta, g->a, 3, dims, str, box)) != FFVC_OK) return rc;
+    }
+  }
+  // ---- operand B
+  {
+    const uint64_t nb = (g->b_batch_role == FFVC_ROLE_OUT_BATCH) ? batch : (g->b_batch_role == FFVC_ROLE_K_SEGMENT ? k_segs : 1);
+    const uint64_t bs = nb > 1 ? (uint64_t)g->b_batch_stride : (uint64_t)g->b_ld * 8;
+    if (g->b_mode == FFVC_OP_KMAJOR) {
+      uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->N, nb};
+      uint64_t str[3] = {1, (uint64_t)g->b_ld, bs};
+      uint32_t box[3] = {64, (uint32_t)block_n, 1};
+      if ((rc = make_tmap(&tb, g->b, 3, dims, str, box)) != FFVC_OK) return rc;
+    } else {
+      uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)g->K, nb};
+      uint64_t str[3] = {1, (uint64_t)g->b_ld, bs};
+      uint32_t box[3] = {64, 64, 1};
+      if ((rc = make_tmap(&tb, g->b, 3, dims, str, box)) != FFVC_OK) return rc;
+    }
+  }
+  if (splits > p.kb_per_seg * k_segs) splits = p.splits = p.kb_per_seg * k_segs;
+
+  p.out = g->out;
+  p.pre_out = g->pre_out;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(g->aux);
+  p.res = reinterpret_cast<const __nv_bfloat16*>(g->res);
+  p.bias = g->bias;
+  p.ldc = g->ldc;
+  p.out_bs = g->out_batch_stride;
+  p.out_fp32 = g->out_fp32;
+  p.atomic = g->atomic;
+  p.bias_mode = g->bias ? g->bias_mode : 0;
+  p.act = g->act;
+  p.mul_mode = g->aux ? g->mul_mode : 0;
+  p.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
+
+  const long long tiles = (long long)((g->M + kBlockM - 1) / kBlockM) * ((g->N + block_n - 1) / block_n) * batch * splits;
+  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+  gemm_tcgen05_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return FFVC_OK;
+}
