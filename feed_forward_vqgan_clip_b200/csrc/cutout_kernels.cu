@@ -1,0 +1,402 @@
+// MakeCutouts (main.py:154-229) + CLIP normalisation (main.py:797) as gather/scatter HBM kernels.
+//   pool      : (AdaptiveAvgPool2d + AdaptiveMaxPool2d) / 2                     main.py:218
+//   warp      : bilinear homography resample, border or zero padding            kornia RandomAffine / RandomPerspective
+//   final     : perspective warp + hue/saturation jitter + erase + noise + (x-mean)/std, written PATCH-MAJOR in bf16
+//               so that the ViT patch embedding (cloob.py:224,237) is a plain GEMM      main.py:171-190,223-225,797
+// Images are NHWC fp32 with 3 channels.  All randomness arrives as explicit tensors (host-side sampling policy).
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cfloat>
+
+#include "ffvc_internal.h"
+
+namespace ffvc {
+
+#define TWO_PI_F 6.283185307179586f
+
+static inline unsigned grid_for_c(long long n, int threads, int cap = 148 * 16) {
+  long long g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  return (unsigned)(g < cap ? g : cap);
+}
+
+// ------------------------------------------------------------------------------ adaptive (avg+max)/2 pooling
+__device__ __forceinline__ int win_start(int i, int in, int out) { return (int)(((long long)i * in) / out); }
+__device__ __forceinline__ int win_end(int i, int in, int out) { return (int)((((long long)(i + 1)) * in + out - 1) / out); }
+
+__global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int P) {
+  const long long total = (long long)B * P * P * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 3);
+    long long p = i / 3;
+    const int ox = (int)(p % P);
+    p /= P;
+    const int oy = (int)(p % P);
+    const int b = (int)(p / P);
+    const int y0 = win_start(oy, H, P), y1 = win_end(oy, H, P), x0 = win_start(ox, W, P), x1 = win_end(ox, W, P);
+    float s = 0.f, m = -FLT_MAX;
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) {
+        const float v = x[(((long long)b * H + yy) * W + xx) * 3 + c];
+        s += v;
+        m = fmaxf(m, v);
+      }
+    y[i] = 0.5f * (s / ((y1 - y0) * (x1 - x0)) + m);
+  }
+}
+// gather form: each input pixel collects from every pooled output whose window contains it
+__global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H,
+                                int W, int P) {
+  const long long total = (long long)B * H * W * 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 3);
+    long long p = i / 3;
+    const int ix = (int)(p % W);
+    p /= W;
+    const int iy = (int)(p % H);
+    const int b = (int)(p / H);
+    float acc = 0.f;
+    const int oy_lo = max(0, (int)(((long long)iy * P) / H) - 1), oy_hi = min(P - 1, (int)((((long long)(iy + 1)) * P + H - 1) / H));
+    const int ox_lo = max(0, (int)(((long long)ix * P) / W) - 1), ox_hi = min(P - 1, (int)((((long long)(ix + 1)) * P + W - 1) / W));
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const int y0 = win_start(oy, H, P), y1 = win_end(oy, H, P);
+      if (iy < y0 || iy >= y1) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const int x0 = win_start(ox, W, P), x1 = win_end(ox, W, P);
+        if (ix < x0 || ix >= x1) continue;
+        const float g = dy[(((long long)b * P + oy) * P + ox) * 3 + c];
+        acc += 0.5f * g / ((y1 - y0) * (x1 - x0));
+        // arg max of the window (first maximum in row-major order, like ATen's adaptive_max_pool2d)
+        float m = -FLT_MAX;
+        int my = y0, mx = x0;
+        for (int yy = y0; yy < y1; ++yy)
+          for (int xx = x0; xx < x1; ++xx) {
+            const float v = x[(((long long)b * H + yy) * W + xx) * 3 + c];
+            if (v > m) {
+              m = v;
+              my = yy;
+              mx = xx;
+            }
+          }
+        if (my == iy && mx == ix) acc += 0.5f * g;
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------ bilinear homography sampling
+struct Taps {
+  int x0, y0, x1, y1;
+  float w00, w01, w10, w11;  // weights for (y0,x0), (y0,x1), (y1,x0), (y1,x1); zero if tap is outside (zeros mode)
+};
+__device__ __forceinline__ Taps make_taps(const float* __restrict__ hm, int ox, int oy, int P, int border) {
+  const float fx = (float)ox, fy = (float)oy;
+  const float den = hm[6] * fx + hm[7] * fy + hm[8];
+  float sx = (hm[0] * fx + hm[1] * fy + hm[2]) / den;
+  float sy = (hm[3] * fx + hm[4] * fy + hm[5]) / den;
+  if (border) {
+    sx = fminf(fmaxf(sx, 0.f), (float)(P - 1));
+    sy = fminf(fmaxf(sy, 0.f), (float)(P - 1));
+  }
+  const float flx = floorf(sx), fly = floorf(sy);
+  const float ax = sx - flx, ay = sy - fly;
+  Taps t;
+  // keep the integer conversion safe for wild coordinates
+  const float cl = 4.0f * P;
+  t.x0 = (int)fminf(fmaxf(flx, -cl), cl);
+  t.y0 = (int)fminf(fmaxf(fly, -cl), cl);
+  t.x1 = t.x0 + 1;
+  t.y1 = t.y0 + 1;
+  t.w00 = (1.f - ax) * (1.f - ay);
+  t.w01 = ax * (1.f - ay);
+  t.w10 = (1.f - ax) * ay;
+  t.w11 = ax * ay;
+  const bool vx0 = t.x0 >= 0 && t.x0 < P, vx1 = t.x1 >= 0 && t.x1 < P;
+  const bool vy0 = t.y0 >= 0 && t.y0 < P, vy1 = t.y1 >= 0 && t.y1 < P;
+  if (!(vx0 && vy0)) t.w00 = 0.f;
+  if (!(vx1 && vy0)) t.w01 = 0.f;
+  if (!(vx0 && vy1)) t.w10 = 0.f;
+  if (!(vx1 && vy1)) t.w11 = 0.f;
+  t.x0 = min(max(t.x0, 0), P - 1);
+  t.x1 = min(max(t.x1, 0), P - 1);
+  t.y0 = min(max(t.y0, 0), P - 1);
+  t.y1 = min(max(t.y1, 0), P - 1);
+  return t;
+}
+__device__ __forceinline__ void sample3(const float* __restrict__ img, const Taps& t, int P, float (&o)[3]) {
+  const float* a = img + ((long long)t.y0 * P + t.x0) * 3;
+  const float* b = img + ((long long)t.y0 * P + t.x1) * 3;
+  const float* c = img + ((long long)t.y1 * P + t.x0) * 3;
+  const float* d = img + ((long long)t.y1 * P + t.x1) * 3;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) o[ch] = t.w00 * a[ch] + t.w01 * b[ch] + t.w10 * c[ch] + t.w11 * d[ch];
+}
+__device__ __forceinline__ void scatter3(float* __restrict__ img, const Taps& t, int P, const float (&g)[3]) {
+  float* a = img + ((long long)t.y0 * P + t.x0) * 3;
+  float* b = img + ((long long)t.y0 * P + t.x1) * 3;
+  float* c = img + ((long long)t.y1 * P + t.x0) * 3;
+  float* d = img + ((long long)t.y1 * P + t.x1) * 3;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    if (t.w00 != 0.f) atomicAdd(a + ch, t.w00 * g[ch]);
+    if (t.w01 != 0.f) atomicAdd(b + ch, t.w01 * g[ch]);
+    if (t.w10 != 0.f) atomicAdd(c + ch, t.w10 * g[ch]);
+    if (t.w11 != 0.f) atomicAdd(d + ch, t.w11 * g[ch]);
+  }
+}
+
+// out[n] = warp(in[n % n_src], hinv[n])
+__global__ void warp_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hinv, float* __restrict__ out, int N,
+                                int n_src, int P, int border) {
+  const long long total = (long long)N * P * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % P);
+    const int oy = (int)((i / P) % P);
+    const int n = (int)(i / ((long long)P * P));
+    const Taps t = make_taps(hinv + n * 9, ox, oy, P, border);
+    float o[3];
+    sample3(in + (long long)(n % n_src) * P * P * 3, t, P, o);
+    out[i * 3 + 0] = o[0];
+    out[i * 3 + 1] = o[1];
+    out[i * 3 + 2] = o[2];
+  }
+}
+// din[n % n_src] += warp^T(dout[n])   (din must be zeroed by the caller)
+__global__ void warp_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ hinv, float* __restrict__ din, int N,
+                                int n_src, int P, int border) {
+  const long long total = (long long)N * P * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % P);
+    const int oy = (int)((i / P) % P);
+    const int n = (int)(i / ((long long)P * P));
+    const Taps t = make_taps(hinv + n * 9, ox, oy, P, border);
+    const float g[3] = {dout[i * 3], dout[i * 3 + 1], dout[i * 3 + 2]};
+    scatter3(din + (long long)(n % n_src) * P * P * 3, t, P, g);
+  }
+}
+
+// ------------------------------------------------------------------------------ hue / saturation jitter with forward-mode
+// derivatives (value + d/d(r,g,b)) so the backward kernel gets the exact 3x3 Jacobian of the HSV round trip.
+struct D3 {
+  float v, d0, d1, d2;
+};
+__device__ __forceinline__ D3 dconst(float c) { return {c, 0.f, 0.f, 0.f}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.v + b.v, a.d0 + b.d0, a.d1 + b.d1, a.d2 + b.d2}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.v - b.v, a.d0 - b.d0, a.d1 - b.d1, a.d2 - b.d2}; }
+__device__ __forceinline__ D3 operator*(D3 a, D3 b) {
+  return {a.v * b.v, a.d0 * b.v + a.v * b.d0, a.d1 * b.v + a.v * b.d1, a.d2 * b.v + a.v * b.d2};
+}
+__device__ __forceinline__ D3 operator/(D3 a, D3 b) {
+  const float inv = 1.0f / b.v;
+  const float q = a.v * inv;
+  return {q, (a.d0 - q * b.d0) * inv, (a.d1 - q * b.d1) * inv, (a.d2 - q * b.d2) * inv};
+}
+__device__ __forceinline__ D3 operator*(float s, D3 a) { return {s * a.v, s * a.d0, s * a.d1, s * a.d2}; }
+__device__ __forceinline__ D3 shift(D3 a, float c) { return {a.v + c, a.d0, a.d1, a.d2}; }
+
+__device__ __forceinline__ void jitter(D3 r, D3 g, D3 b, float sat, float hue, D3& ro, D3& go, D3& bo) {
+  // rgb -> hsv (kornia.color.rgb_to_hsv)
+  int am = 0;
+  D3 maxc = r;
+  if (g.v > maxc.v) {
+    maxc = g;
+    am = 1;
+  }
+  if (b.v > maxc.v) {
+    maxc = b;
+    am = 2;
+  }
+  D3 minc = r;
+  if (g.v < minc.v) minc = g;
+  if (b.v < minc.v) minc = b;
+  const D3 v = maxc;
+  D3 deltac = maxc - minc;
+  D3 s = deltac / shift(v, 1e-6f);
+  if (deltac.v == 0.f) deltac = dconst(1.f);
+  const D3 rc = maxc - r, gc = maxc - g, bc = maxc - b;
+  D3 h;
+  if (am == 0) h = bc - gc;
+  else if (am == 1) h = 2.f * deltac + rc - bc;
+  else h = 4.f * deltac + gc - rc;
+  h = h / deltac;
+  h = (1.0f / 6.0f) * h;
+  h = shift(h, -floorf(h.v));  // python-style % 1.0
+  h = TWO_PI_F * h;
+  // jitter
+  s = sat * s;
+  if (s.v < 0.f) s = dconst(0.f);
+  else if (s.v > 1.f) s = dconst(1.f);
+  h = shift(h, hue + TWO_PI_F);
+  h = shift(h, -TWO_PI_F * truncf(h.v / TWO_PI_F));  // fmod(h, 2pi), h >= 0
+  // hsv -> rgb (kornia.color.hsv_to_rgb)
+  D3 h6 = (6.0f / TWO_PI_F) * h;
+  const float fl = floorf(h6.v);
+  int hi = ((int)fl) % 6;
+  if (hi < 0) hi += 6;
+  const float m6 = h6.v - 6.0f * floorf(h6.v / 6.0f);  // h6 % 6
+  D3 f = shift(h6, (m6 - (float)hi) - h6.v);
+  const D3 one = dconst(1.f);
+  const D3 p = v * (one - s);
+  const D3 q = v * (one - f * s);
+  const D3 t = v * (one - (one - f) * s);
+  switch (hi) {
+    case 0: ro = v; go = t; bo = p; break;
+    case 1: ro = q; go = v; bo = p; break;
+    case 2: ro = p; go = v; bo = t; break;
+    case 3: ro = p; go = q; bo = v; break;
+    case 4: ro = t; go = p; bo = v; break;
+    default: ro = v; go = p; bo = q; break;
+  }
+}
+
+struct FinalParams {
+  const float* cut1;    // [N][P][P][3] image after the affine warp
+  const float* hinv;    // [N][9] perspective inverse homographies
+  const float* sat;     // [N]
+  const float* hue;     // [N]
+  const float* noise;   // [N][3][P][P]  (standard normal, NCHW like randn_like(batch))
+  const float* facs;    // [N]           (U(0, noise_fac))
+  int ex0, ey0, ex1, ey1;  // erase rectangle (empty if ex1 <= ex0)
+  float mean[3], istd[3];
+  int N, P, patch, grid;   // grid = P / patch
+};
+
+// forward: -> patches [N][grid*grid][3*patch*patch] bf16   (k = c*patch^2 + py*patch + px)
+__global__ void cutout_final_fwd_kernel(FinalParams fp, __nv_bfloat16* __restrict__ patches, float* __restrict__ img_out) {
+  const int P = fp.P;
+  const long long total = (long long)fp.N * P * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % P);
+    const int oy = (int)((i / P) % P);
+    const int n = (int)(i / ((long long)P * P));
+    const Taps t = make_taps(fp.hinv + n * 9, ox, oy, P, 0);
+    float c[3];
+    sample3(fp.cut1 + (long long)n * P * P * 3, t, P, c);
+    D3 ro, go, bo;
+    jitter({c[0], 1, 0, 0}, {c[1], 0, 1, 0}, {c[2], 0, 0, 1}, fp.sat[n], fp.hue[n], ro, go, bo);
+    float o[3] = {ro.v, go.v, bo.v};
+    const bool erased = ox >= fp.ex0 && ox < fp.ex1 && oy >= fp.ey0 && oy < fp.ey1;
+    const float fac = fp.facs[n];
+    const int pp = fp.patch * fp.patch;
+    const int pidx = (oy / fp.patch) * fp.grid + ox / fp.patch;
+    const int kin = (oy % fp.patch) * fp.patch + ox % fp.patch;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float val = erased ? 0.f : o[ch];
+      val += fac * fp.noise[(((long long)n * 3 + ch) * P + oy) * P + ox];
+      val = (val - fp.mean[ch]) * fp.istd[ch];
+      patches[((long long)n * fp.grid * fp.grid + pidx) * (3 * pp) + ch * pp + kin] = __float2bfloat16(val);
+      if (img_out) img_out[(((long long)n * 3 + ch) * P + oy) * P + ox] = val;
+    }
+  }
+}
+// backward: dpatches (bf16, same layout) -> dcut1 (atomics, zeroed by caller)
+__global__ void cutout_final_bwd_kernel(FinalParams fp, const __nv_bfloat16* __restrict__ dpatches, float* __restrict__ dcut1) {
+  const int P = fp.P;
+  const long long total = (long long)fp.N * P * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % P);
+    const int oy = (int)((i / P) % P);
+    const int n = (int)(i / ((long long)P * P));
+    const bool erased = ox >= fp.ex0 && ox < fp.ex1 && oy >= fp.ey0 && oy < fp.ey1;
+    if (erased) continue;
+    const Taps t = make_taps(fp.hinv + n * 9, ox, oy, P, 0);
+    float c[3];
+    sample3(fp.cut1 + (long long)n * P * P * 3, t, P, c);
+    D3 ro, go, bo;
+    jitter({c[0], 1, 0, 0}, {c[1], 0, 1, 0}, {c[2], 0, 0, 1}, fp.sat[n], fp.hue[n], ro, go, bo);
+    const int pp = fp.patch * fp.patch;
+    const int pidx = (oy / fp.patch) * fp.grid + ox / fp.patch;
+    const int kin = (oy % fp.patch) * fp.patch + ox % fp.patch;
+    float go_[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      go_[ch] = __bfloat162float(dpatches[((long long)n * fp.grid * fp.grid + pidx) * (3 * pp) + ch * pp + kin]) * fp.istd[ch];
+    float gi[3];
+    gi[0] = go_[0] * ro.d0 + go_[1] * go.d0 + go_[2] * bo.d0;
+    gi[1] = go_[0] * ro.d1 + go_[1] * go.d1 + go_[2] * bo.d1;
+    gi[2] = go_[0] * ro.d2 + go_[1] * go.d2 + go_[2] * bo.d2;
+    scatter3(dcut1 + (long long)n * P * P * 3, t, P, gi);
+  }
+}
+
+}  // namespace ffvc
+
+using namespace ffvc;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int ffvc_cutout_pool_fwd(const float* x, float* y, int B, int H, int W, int P, void* stream) {
+  pool_fwd_kernel<<<grid_for_c((long long)B * P * P * 3, 256), 256, 0, ST(stream)>>>(x, y, B, H, W, P);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_cutout_pool_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int P, void* stream) {
+  pool_bwd_kernel<<<grid_for_c((long long)B * H * W * 3, 256), 256, 0, ST(stream)>>>(x, dy, dx, B, H, W, P);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_cutout_warp_fwd(const float* in, const float* hinv, float* out, int N, int n_src, int P, int border,
+                                    void* stream) {
+  warp_fwd_kernel<<<grid_for_c((long long)N * P * P, 256), 256, 0, ST(stream)>>>(in, hinv, out, N, n_src, P, border);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_cutout_warp_bwd(const float* dout, const float* hinv, float* din, int N, int n_src, int P, int border,
+                                    void* stream) {
+  cudaMemsetAsync(din, 0, sizeof(float) * (size_t)n_src * P * P * 3, ST(stream));
+  warp_bwd_kernel<<<grid_for_c((long long)N * P * P, 256), 256, 0, ST(stream)>>>(dout, hinv, din, N, n_src, P, border);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+static int fill_final(FinalParams& fp, const float* cut1, const float* hinv, const float* sat, const float* hue,
+                      const float* noise, const float* facs, const int* erase, const float* mean, const float* std_, int N,
+                      int P, int patch) {
+  if (P % patch) return set_error(FFVC_ERR_ARG, "cutout_final: cut size must be a multiple of the patch size");
+  fp.cut1 = cut1;
+  fp.hinv = hinv;
+  fp.sat = sat;
+  fp.hue = hue;
+  fp.noise = noise;
+  fp.facs = facs;
+  fp.ex0 = erase[0];
+  fp.ey0 = erase[1];
+  fp.ex1 = erase[2];
+  fp.ey1 = erase[3];
+  for (int i = 0; i < 3; ++i) {
+    fp.mean[i] = mean[i];
+    fp.istd[i] = 1.0f / std_[i];
+  }
+  fp.N = N;
+  fp.P = P;
+  fp.patch = patch;
+  fp.grid = P / patch;
+  return FFVC_OK;
+}
+// erase / mean / std are HOST pointers (4 ints, 3 floats, 3 floats).  img_out (optional, [N][3][P][P] fp32) receives the
+// normalised cutouts in the reference's NCHW layout (for parity tests / callers that want the tensor).
+extern "C" int ffvc_cutout_final_fwd(const float* cut1, const float* hinv, const float* sat, const float* hue,
+                                     const float* noise, const float* facs, const int* erase, const float* mean,
+                                     const float* std_, void* patches, float* img_out, int N, int P, int patch, void* stream) {
+  FinalParams fp;
+  int rc = fill_final(fp, cut1, hinv, sat, hue, noise, facs, erase, mean, std_, N, P, patch);
+  if (rc) return rc;
+  cutout_final_fwd_kernel<<<grid_for_c((long long)N * P * P, 256), 256, 0, ST(stream)>>>(
+      fp, reinterpret_cast<__nv_bfloat16*>(patches), img_out);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_cutout_final_bwd(const float* cut1, const float* hinv, const float* sat, const float* hue,
+                                     const int* erase, const float* mean, const float* std_, const void* dpatches,
+                                     float* dcut1, int N, int P, int patch, void* stream) {
+  FinalParams fp;
+  int rc = fill_final(fp, cut1, hinv, sat, hue, nullptr, nullptr, erase, mean, std_, N, P, patch);
+  if (rc) return rc;
+  cudaMemsetAsync(dcut1, 0, sizeof(float) * (size_t)N * P * P * 3, ST(stream));
+  cutout_final_bwd_kernel<<<grid_for_c((long long)N * P * P, 256), 256, 0, ST(stream)>>>(
+      fp, reinterpret_cast<const __nv_bfloat16*>(dpatches), dcut1);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}

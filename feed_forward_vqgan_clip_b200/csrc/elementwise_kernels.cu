@@ -1,0 +1,525 @@
+// Coalesced / vectorised HBM-bound kernels of the train step that are not normalisations:
+// nearest-2x upsample, batched transpose, row softmax, bias-gradient reductions, casts, ClampWithGrad,
+// VQ nearest-code search, image post-processing, the tiny-Cin 3x3 conv (dgrad of conv_out) and fused Adam.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cfloat>
+
+#include "ffvc_internal.h"
+#include "ptx.cuh"
+
+namespace ffvc {
+
+static inline unsigned grid_for(long long n, int threads, int cap = 148 * 16) {
+  long long g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  return (unsigned)(g < cap ? g : cap);
+}
+
+// ---------------------------------------------------------------- nearest 2x upsample (taming Upsample)
+__global__ void upsample2x_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W, int CV) {
+  const long long total = (long long)N * 2 * H * 2 * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV);
+    long long p = i / CV;
+    const int ox = (int)(p % (2 * W));
+    p /= (2 * W);
+    const int oy = (int)(p % (2 * H));
+    const int n = (int)(p / (2 * H));
+    y[i] = x[(((long long)n * H + (oy >> 1)) * W + (ox >> 1)) * CV + c];
+  }
+}
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int H,
+                                      int W, int C) {
+  const int CV = C >> 3;
+  const long long total = (long long)N * H * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % CV);
+    long long p = i / CV;
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H);
+    const int n = (int)(p / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dy_ = 0; dy_ < 2; ++dy_)
+#pragma unroll
+      for (int dx_ = 0; dx_ < 2; ++dx_) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(
+            dy + ((((long long)n * 2 * H + 2 * y + dy_) * 2 * W + 2 * x + dx_) * C + c * 8));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+    uint4 o;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&h0);
+    o.y = *reinterpret_cast<uint32_t*>(&h1);
+    o.z = *reinterpret_cast<uint32_t*>(&h2);
+    o.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(dx + i * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------- batched 2-D transpose  in[b][R][Cc] -> out[b][Cc][R]
+template <typename Tin, typename Tout>
+__global__ void transpose_kernel(const Tin* __restrict__ in, Tout* __restrict__ out, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const Tin* ib = in + (long long)b * R * Cc;
+  Tout* ob = out + (long long)b * R * Cc;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < R && c < Cc) tile[j][threadIdx.x] = (float)ib[(long long)r * Cc + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) ob[(long long)c * R + r] = (Tout)tile[threadIdx.x][j];
+  }
+}
+
+// ---------------------------------------------------------------- row softmax (VQGAN AttnBlock, fp32 scores -> bf16 probs)
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p,
+                                                          long long rows, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const float* sr = s + row * n;
+  float mx = -FLT_MAX;
+  for (int i = lane; i < n; i += 32) mx = fmaxf(mx, sr[i]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < n; i += 32) sum += __expf(sr[i] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int i = lane; i < n; i += 32) p[row * n + i] = __float2bfloat16(__expf(sr[i] - mx) * inv);
+}
+// ds = p * (dp - sum(p*dp)) * scale   (dp fp32 from the dO.V^T GEMM; ds bf16 feeds the dQ/dK GEMMs)
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp,
+                                                          __nv_bfloat16* __restrict__ ds, long long rows, int n, float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int i = lane; i < n; i += 32) dot += __bfloat162float(p[row * n + i]) * dp[row * n + i];
+  dot = warp_sum(dot);
+  for (int i = lane; i < n; i += 32)
+    ds[row * n + i] = __float2bfloat16(__bfloat162float(p[row * n + i]) * (dp[row * n + i] - dot) * scale);
+}
+
+// ---------------------------------------------------------------- bias gradients
+// db[n] += sum_rows dy[row][n]
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
+                                                     long long rows, int n, int rows_per_cta) {
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += __bfloat162float(dy[r * n + c]);
+  atomicAdd(&db[c], acc);
+}
+// db[j] += sum_{b,d} dy[b][j][d]   (row-bias of the token-mixing Conv1d)
+__global__ void __launch_bounds__(256) rowsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, int B,
+                                                     int J, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;  // over B*J
+  if (row >= (long long)B * J) return;
+  const __nv_bfloat16* r = dy + row * D;
+  float acc = 0.f;
+  for (int i = lane; i < D; i += 32) acc += __bfloat162float(r[i]);
+  acc = warp_sum(acc);
+  if (lane == 0) atomicAdd(&db[row % J], acc);
+}
+
+// ---------------------------------------------------------------- casts / adds
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
+// ---------------------------------------------------------------- VQ: clamp -> nearest code -> gather (main.py:763,134-138)
+// fp32 SIMT distance search (argmin is discontinuous: no bf16 here):
+//   d(row, code) = |c|^2 - 2 x.c        (|x|^2 is constant per row and dropped)
+// CTA = 64 latent vectors x all codes; the clamped x tile lives in smem transposed [C][64]; codes stream through
+// smem in [32 k][64 codes] chunks read from a pre-transposed codebook codeT[C][ncodes] (frozen -> transposed once).
+// Thread micro-tile 4 rows x 4 codes, float4 LDS.  Ties resolve to the lowest index like torch.argmin.
+template <int C>
+__global__ void __launch_bounds__(256) vq_nearest_kernel(const float* __restrict__ z, const float* __restrict__ codebook,
+                                                         const float* __restrict__ codeT, const float* __restrict__ cnorm,
+                                                         int* __restrict__ idx_out, __nv_bfloat16* __restrict__ zq_bf16,
+                                                         float* __restrict__ zq_f32, float* __restrict__ zc_out,
+                                                         long long P, int ncodes, float lo, float hi) {
+  extern __shared__ float vq_smem[];
+  float* xs = vq_smem;                 // [C][64]
+  float* cs = vq_smem + C * 64;        // [32][64]
+  float* red_d = cs + 32 * 64;         // [64][16]
+  int* red_i = reinterpret_cast<int*>(red_d + 64 * 16);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long row0 = (long long)blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 64 * C; i += 256) {
+    const int r = i / C, c = i % C;
+    float v = 0.f;
+    if (row0 + r < P) {
+      v = z[(row0 + r) * C + c];
+      v = fminf(fmaxf(v, lo), hi);     // clamp_with_grad forward (main.py:763)
+      if (zc_out) zc_out[(row0 + r) * C + c] = v;
+    }
+    xs[c * 64 + r] = v;
+  }
+  float best[4];
+  int besti[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    best[i] = FLT_MAX;
+    besti[i] = 0;
+  }
+  for (int c0 = 0; c0 < ncodes; c0 += 64) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < C; k0 += 32) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+        const int k = i >> 4, c4 = i & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + c4 * 4 + 3 < ncodes) v = *reinterpret_cast<const float4*>(codeT + (long long)(k0 + k) * ncodes + c0 + c4 * 4);
+        else {
+          float t[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < 4; ++j)
+            if (c0 + c4 * 4 + j < ncodes) t[j] = codeT[(long long)(k0 + k) * ncodes + c0 + c4 * 4 + j];
+          v = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        *reinterpret_cast<float4*>(cs + k * 64 + c4 * 4) = v;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + (k0 + k) * 64 + ty * 4);
+        const float4 cv = *reinterpret_cast<const float4*>(cs + k * 64 + tx * 4);
+        const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float cr[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], cr[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int code = c0 + tx * 4 + j;
+      if (code < ncodes) {
+        const float cn = cnorm[code];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float d = cn - 2.0f * acc[i][j];
+          if (d < best[i]) {
+            best[i] = d;
+            besti[i] = code;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red_d[(ty * 4 + i) * 16 + tx] = best[i];
+    red_i[(ty * 4 + i) * 16 + tx] = besti[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int r = threadIdx.x;
+    float b = red_d[r * 16];
+    int bi = red_i[r * 16];
+    for (int t = 1; t < 16; ++t) {
+      const float d = red_d[r * 16 + t];
+      const int di = red_i[r * 16 + t];
+      if (d < b || (d == b && di < bi)) {
+        b = d;
+        bi = di;
+      }
+    }
+    red_i[r * 16] = bi;
+    if (row0 + r < P) idx_out[row0 + r] = bi;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * C; i += 256) {
+    const int r = i / C, c = i % C;
+    if (row0 + r < P) {
+      const float v = codebook[(long long)red_i[r * 16] * C + c];
+      if (zq_bf16) zq_bf16[(row0 + r) * C + c] = __float2bfloat16(v);
+      if (zq_f32) zq_f32[(row0 + r) * C + c] = v;
+    }
+  }
+}
+__global__ void rownorm2_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int i = lane; i < C; i += 32) s += x[(long long)row * C + i] * x[(long long)row * C + i];
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+
+// ClampWithGrad.backward (main.py:126-129): pass g iff g * (x - clamp(x)) >= 0
+__global__ void clamp_bwd_kernel(const float* __restrict__ g, const float* __restrict__ x, float* __restrict__ gx,
+                                 long long n, float lo, float hi) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float xv = x[i], gv = g[i];
+    const float d = xv - fminf(fmaxf(xv, lo), hi);
+    gx[i] = (gv * d >= 0.f) ? gv : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------- image post: xr = clamp_with_grad((d+1)/2, 0, 1)  (main.py:142)
+__global__ void image_post_fwd_kernel(const float* __restrict__ d, float* __restrict__ xr, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    xr[i] = fminf(fmaxf((d[i] + 1.0f) * 0.5f, 0.f), 1.f);
+}
+__global__ void image_post_bwd_kernel(const float* __restrict__ g, const float* __restrict__ d, float* __restrict__ gd,
+                                      long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float u = (d[i] + 1.0f) * 0.5f;
+    const float diff = u - fminf(fmaxf(u, 0.f), 1.f);
+    const float gv = g[i];
+    gd[i] = (gv * diff >= 0.f) ? 0.5f * gv : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------- 3x3 conv with tiny Cin (dgrad of conv_out: 3 -> 128 ch)
+// x: [N][H][W][CIN] fp32, w: [COUT][9][CIN] fp32 (already flipped/transposed for dgrad), y: NHWC bf16.  pad 1.
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_smallcin_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ y, int N, int H, int W, int COUT) {
+  extern __shared__ float ws[];  // [COUT][9*CIN]
+  for (int i = threadIdx.x; i < COUT * 9 * CIN; i += blockDim.x) ws[i] = w[i];
+  __syncthreads();
+  const int cv = COUT >> 3;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    long long p = i / cv;
+    const int px = (int)(p % W);
+    p /= W;
+    const int py = (int)(p % H);
+    const int n = (int)(p / H);
+    float in[9 * CIN];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) in[t * CIN + c] = ok ? x[(((long long)n * H + yy) * W + xx) * CIN + c] : 0.f;
+    }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float* wr = ws + (c8 * 8 + j) * 9 * CIN;
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < 9 * CIN; ++k) a = fmaf(in[k], wr[k], a);
+      acc[j] = a;
+    }
+    uint4 o;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+    o.x = *reinterpret_cast<uint32_t*>(&h0);
+    o.y = *reinterpret_cast<uint32_t*>(&h1);
+    o.z = *reinterpret_cast<uint32_t*>(&h2);
+    o.w = *reinterpret_cast<uint32_t*>(&h3);
+    *reinterpret_cast<uint4*>(y + i * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------- fused Adam (torch.optim.Adam defaults, main.py:591,835)
+// p,g,m,v fp32 flat arenas; also refreshes the bf16 shadow the GEMMs read.  grad_scale folds the DP average.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n,
+                                                   float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
+                                                   float grad_scale, float wd) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gv = g[i] * grad_scale;
+    const float pv = p[i];
+    if (wd != 0.f) gv += wd * pv;
+    const float mv = b1 * m[i] + (1.f - b1) * gv;
+    const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    const float np = pv - (lr / bc1) * (mv / denom);
+    p[i] = np;
+    if (shadow) shadow[i] = __float2bfloat16(np);
+  }
+}
+
+__global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc += x[i] * x[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+}  // namespace ffvc
+
+using namespace ffvc;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" int ffvc_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  if (C % 8) return set_error(FFVC_ERR_ARG, "upsample: C % 8 != 0");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  upsample2x_fwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const uint4*>(x),
+                                                                     reinterpret_cast<uint4*>(y), N, H, W, C / 8);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
+  if (C % 8) return set_error(FFVC_ERR_ARG, "upsample: C % 8 != 0");
+  const long long total = (long long)N * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(CBF(dy), BF(dx), N, H, W, C);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+// in[b][R][Cc] -> out[b][Cc][R]; dtype codes: 0 = bf16, 1 = fp32
+extern "C" int ffvc_transpose(const void* in, void* out, int B, int R, int Cc, int in_fp32, int out_fp32, void* stream) {
+  dim3 grid((Cc + 31) / 32, (R + 31) / 32, B), block(32, 8);
+  if (!in_fp32 && !out_fp32)
+    transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, ST(stream)>>>(CBF(in), BF(out), R, Cc);
+  else if (in_fp32 && !out_fp32)
+    transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const float*>(in), BF(out), R, Cc);
+  else if (!in_fp32 && out_fp32)
+    transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, ST(stream)>>>(CBF(in), reinterpret_cast<float*>(out), R, Cc);
+  else
+    transpose_kernel<float, float><<<grid, block, 0, ST(stream)>>>(reinterpret_cast<const float*>(in),
+                                                                  reinterpret_cast<float*>(out), R, Cc);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_softmax_fwd(const float* s, void* p, long long rows, int n, void* stream) {
+  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(s, BF(p), rows, n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_softmax_bwd(const void* p, const float* dp, void* ds, long long rows, int n, float scale, void* stream) {
+  softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(CBF(p), dp, BF(ds), rows, n, scale);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_colsum(const void* dy, float* db, long long rows, int n, void* stream) {
+  const int rows_per_cta = 512;
+  dim3 grid((n + 255) / 256, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
+  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(CBF(dy), db, rows, n, rows_per_cta);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_rowsum(const void* dy, float* db, int B, int J, int D, void* stream) {
+  const long long rows = (long long)B * J;
+  rowsum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(CBF(dy), db, B, J, D);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_cast_f32_bf16(const float* x, void* y, long long n, void* stream) {
+  cast_f32_bf16_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(x, BF(y), n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_cast_bf16_f32(const void* x, float* y, long long n, void* stream) {
+  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(CBF(x), y, n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_add_bf16(const void* a, const void* b, void* y, long long n, void* stream) {
+  add_bf16_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), BF(y), n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_rownorm2(const float* x, float* out, int rows, int C, void* stream) {
+  rownorm2_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>(x, out, rows, C);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+// z: [P][C] fp32 (token-major latent), clamp to [lo,hi], nearest code; outputs: idx int32 [P], zq (bf16 and/or fp32),
+// zc (clamped z, optional).  codeT = codebook transposed [C][ncodes] (ffvc_transpose), cnorm = |code|^2 (ffvc_rownorm2).
+extern "C" int ffvc_vq_nearest(const float* z, const float* codebook, const float* codeT, const float* cnorm, int* idx,
+                               void* zq_bf16, float* zq_f32, float* zc, long long P, int C, int ncodes, float lo, float hi,
+                               void* stream) {
+  if (ncodes % 4) return set_error(FFVC_ERR_ARG, "vq_nearest: ncodes must be a multiple of 4");
+  const unsigned grid = (unsigned)((P + 63) / 64);
+  const size_t smem = (size_t)(C * 64 + 32 * 64 + 64 * 16) * sizeof(float) + 64 * 16 * sizeof(int);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(vq_nearest_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(vq_nearest_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_done = true;
+  }
+  if (C == 256)
+    vq_nearest_kernel<256><<<grid, 256, smem, ST(stream)>>>(z, codebook, codeT, cnorm, idx, BF(zq_bf16), zq_f32, zc, P, ncodes, lo, hi);
+  else if (C == 64)
+    vq_nearest_kernel<64><<<grid, 256, smem, ST(stream)>>>(z, codebook, codeT, cnorm, idx, BF(zq_bf16), zq_f32, zc, P, ncodes, lo, hi);
+  else
+    return set_error(FFVC_ERR_UNSUPPORTED, "vq_nearest: embed dim must be 64 or 256");
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_clamp_bwd(const float* g, const float* x, float* gx, long long n, float lo, float hi, void* stream) {
+  clamp_bwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(g, x, gx, n, lo, hi);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_image_post_fwd(const float* d, float* xr, long long n, void* stream) {
+  image_post_fwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(d, xr, n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_image_post_bwd(const float* g, const float* d, float* gd, long long n, void* stream) {
+  image_post_bwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(g, d, gd, n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_conv3x3_cin3(const float* x, const float* w, void* y, int N, int H, int W, int COUT, void* stream) {
+  if (COUT % 8 || COUT > 512) return set_error(FFVC_ERR_ARG, "conv3x3_cin3: COUT % 8 != 0 or too large");
+  const long long total = (long long)N * H * W * (COUT / 8);
+  conv3x3_smallcin_kernel<3><<<grid_for(total, 256), 256, COUT * 27 * sizeof(float), ST(stream)>>>(x, w, BF(y), N, H, W, COUT);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr,
+                              float beta1, float beta2, float eps, int step, float grad_scale, float weight_decay,
+                              void* stream) {
+  if (step < 1) return set_error(FFVC_ERR_ARG, "adam: step must be >= 1");
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = 1.0f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(p, g, m, v, BF(shadow_bf16), n, lr, beta1, beta2, eps, bc1,
+                                                                 sqrtf(bc2), grad_scale, weight_decay);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_sumsq(const float* x, float* out, long long n, void* stream) {
+  cudaMemsetAsync(out, 0, sizeof(float), ST(stream));
+  sumsq_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, ST(stream)>>>(x, out, n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}

@@ -1,0 +1,75 @@
+// Spherical-distance loss between the normalised image embedding and the normalised target embedding,
+// forward and backward fused in one pass (main.py:801-811):
+//   H = normalize(out_feats.repeat(cutn,1)); e = normalize(embed); loss = coef * mean(2 * asin(|H - e| / 2)^2)
+// One warp per embedding row; produces d(loss)/d(embed) directly.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "ffvc_internal.h"
+#include "ptx.cuh"
+
+namespace ffvc {
+
+// embed: [N][D] fp32, target: [B][D] fp32 (row n uses target[n % B]).  loss_out: one float (accumulated, zeroed by caller).
+__global__ void __launch_bounds__(256) spherical_loss_kernel(const float* __restrict__ embed, const float* __restrict__ target,
+                                                             float* __restrict__ loss_out, float* __restrict__ dembed,
+                                                             __nv_bfloat16* __restrict__ dembed_bf16, int N, int B, int D,
+                                                             float coef) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (n >= N) return;
+  const float* e = embed + (long long)n * D;
+  const float* t = target + (long long)(n % B) * D;
+  float se = 0.f, st = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    se += e[i] * e[i];
+    st += t[i] * t[i];
+  }
+  se = warp_sum(se);
+  st = warp_sum(st);
+  const float ne = fmaxf(sqrtf(se), 1e-12f), nt = fmaxf(sqrtf(st), 1e-12f);  // F.normalize eps
+  const float ie = 1.0f / ne, it = 1.0f / nt;
+  float d2 = 0.f, dot_eh_g = 0.f;
+  for (int i = lane; i < D; i += 32) {
+    const float diff = t[i] * it - e[i] * ie;
+    d2 += diff * diff;
+  }
+  d2 = warp_sum(d2);
+  const float d = sqrtf(d2);
+  const float half = fminf(0.5f * d, 1.0f);
+  const float a = asinf(half);
+  const float l = 2.0f * a * a;
+  if (lane == 0) atomicAdd(loss_out, coef * l / N);
+  // dl/dd = 2 * a / sqrt(1 - d^2/4);  dl/d(ehat) = dl/dd * (ehat - Hhat) / d
+  const float dl_dd = (d > 0.f) ? 2.0f * a * rsqrtf(fmaxf(1.0f - half * half, 1e-12f)) : 0.f;
+  const float s = (d > 0.f) ? (coef / N) * dl_dd / d : 0.f;
+  // g = s * (ehat - Hhat);  de = (g - ehat * <g, ehat>) / |e|
+  for (int i = lane; i < D; i += 32) {
+    const float eh = e[i] * ie;
+    const float g = s * (eh - t[i] * it);
+    dot_eh_g += g * eh;
+  }
+  dot_eh_g = warp_sum(dot_eh_g);
+  for (int i = lane; i < D; i += 32) {
+    const float eh = e[i] * ie;
+    const float g = s * (eh - t[i] * it);
+    const float de = (g - eh * dot_eh_g) * ie;
+    if (dembed) dembed[(long long)n * D + i] = de;
+    if (dembed_bf16) dembed_bf16[(long long)n * D + i] = __float2bfloat16(de);
+  }
+}
+
+}  // namespace ffvc
+
+using namespace ffvc;
+
+extern "C" int ffvc_spherical_loss(const float* embed, const float* target, float* loss_out, float* dembed,
+                                   void* dembed_bf16, int N, int B, int D, float coef, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(loss_out, 0, sizeof(float), st);
+  spherical_loss_kernel<<<(N + 7) / 8, 256, 0, st>>>(embed, target, loss_out, dembed,
+                                                    reinterpret_cast<__nv_bfloat16*>(dembed_bf16), N, B, D, coef);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}

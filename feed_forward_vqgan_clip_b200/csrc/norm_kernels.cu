@@ -1,0 +1,486 @@
+// LayerNorm (mapper + CLIP ViT) and GroupNorm(32)+swish (VQGAN decoder) — HBM-bound, vectorised,
+// warp-shuffle reductions.  bf16 activations, fp32 statistics.
+//   LayerNorm : mlp_mixer_pytorch.py:11,37 (nn.LayerNorm), cloob.py:170-176,244,250 (fp32 LayerNorm)
+//   GroupNorm : taming Normalize = GroupNorm(32, C, eps=1e-6, affine) followed by x*sigmoid(x)
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "ffvc_internal.h"
+#include "ptx.cuh"
+
+namespace ffvc {
+
+__device__ __forceinline__ void unpack8(const uint4& pk, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 pk;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
+  __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
+  __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
+  pk.x = *reinterpret_cast<uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  pk.z = *reinterpret_cast<uint32_t*>(&h2);
+  pk.w = *reinterpret_cast<uint32_t*>(&h3);
+  return pk;
+}
+
+// ------------------------------------------------------------------------------------ LayerNorm forward
+// One warp per row; D % 8 == 0, D <= 32*8*kMaxV.
+template <int kMaxV>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta,
+                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                                                            float* __restrict__ rstd, long long rows, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int nvec = D >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+  float v[kMaxV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      unpack8(xr[c], v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  s = warp_sum(s);
+  const float mu = s / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mu;
+        q += d * d;
+      }
+    }
+  }
+  q = warp_sum(q);
+  const float rs = rsqrtf(q / D + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+  uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+#pragma unroll
+  for (int i = 0; i < kMaxV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      float o[8];
+      const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
+      const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * c], b1 = reinterpret_cast<const float4*>(beta)[2 * c + 1];
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * gg[j] + bb[j];
+      yr[c] = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ LayerNorm backward
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  optional dx += add (residual path);
+// optional dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (fp32 atomics, one per column per CTA).
+template <int kMaxV>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                            const __nv_bfloat16* __restrict__ x,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd,
+                                                            const __nv_bfloat16* __restrict__ add,
+                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, long long rows, int D) {
+  extern __shared__ float sm[];  // [2][D] when dgamma != nullptr
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  const bool wgrad = dgamma != nullptr;
+  float accg[kMaxV][8], accb[kMaxV][8];
+  if (wgrad) {
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) accg[i][j] = accb[i][j] = 0.f;
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+  }
+  for (long long row = (long long)blockIdx.x * nwarps + warp; row < rows; row += (long long)gridDim.x * nwarps) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+    const uint4* dr = reinterpret_cast<const uint4*>(dy + row * D);
+    const float mu = mean[row], rs = rstd[row];
+    float xh[kMaxV][8], g[kMaxV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float xv[8], dv[8];
+        unpack8(xr[c], xv);
+        unpack8(dr[c], dv);
+        const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          g[i][j] = dv[j] * gg[j];
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+          if (wgrad) {
+            accg[i][j] += dv[j] * xh[i][j];
+            accb[i][j] += dv[j];
+          }
+        }
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+    uint4* ox = reinterpret_cast<uint4*>(dx + row * D);
+    const uint4* ar = add ? reinterpret_cast<const uint4*>(add + row * D) : nullptr;
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+        if (ar) {
+          float av[8];
+          unpack8(ar[c], av);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += av[j];
+        }
+        ox[c] = pack8(o);
+      }
+    }
+  }
+  if (wgrad) {
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&sm[c * 8 + j], accg[i][j]);
+          atomicAdd(&sm[D + c * 8 + j], accb[i][j]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      atomicAdd(&dgamma[i], sm[i]);
+      atomicAdd(&dbeta[i], sm[D + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ GroupNorm
+// x: NHWC bf16, G groups of cpg = C/G consecutive channels.  Statistics per (n, g) over HW*cpg elements.
+// Pass 1: partial (sum, sumsq) per CTA -> double atomics into ws[N*G*2].  C % 8 == 0.
+// Each thread owns one 8-channel vector column (fixed group set) and strides over pixels.
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              double* __restrict__ ws, int HW, int C, int G,
+                                                              int pix_per_cta) {
+  extern __shared__ float sm[];  // [2][G]
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  const int vec_per_pix = C >> 3;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  // thread -> (vector column vc, pixel lane pl); blockDim.x is a multiple of vec_per_pix or vice versa handled by stride
+  const int vc = threadIdx.x % vec_per_pix;
+  const int pl = threadIdx.x / vec_per_pix;
+  const int pstride = blockDim.x / vec_per_pix;
+  if (pstride > 0) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const __nv_bfloat16* base = x + (long long)n * HW * C;
+    for (int p = p0 + pl; p < p1; p += pstride) {
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + (long long)p * C + vc * 8), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] += v[j] * v[j];
+      }
+    }
+    if (pl < pstride) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = (vc * 8 + j) / cpg;
+        atomicAdd(&sm[g], s[j]);
+        atomicAdd(&sm[G + g], q[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    atomicAdd(&ws[((long long)n * G + i) * 2 + 0], (double)sm[i]);
+    atomicAdd(&ws[((long long)n * G + i) * 2 + 1], (double)sm[G + i]);
+  }
+}
+
+__global__ void groupnorm_finalize_kernel(const double* __restrict__ ws, float* __restrict__ mean,
+                                          float* __restrict__ rstd, int NG, double count, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NG) return;
+  const double m = ws[2 * i] / count;
+  double var = ws[2 * i + 1] / count - m * m;
+  if (var < 0) var = 0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// y = act((x - mean) * rstd * gamma + beta), act = swish or identity
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta,
+                                                              __nv_bfloat16* __restrict__ y, long long total_vec,
+                                                              int HW, int C, int G, int swish) {
+  const int cpg = C / G;
+  const int vec_per_pix = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vc = (int)(i % vec_per_pix);
+    const long long pix = i / vec_per_pix;
+    const int n = (int)(pix / HW);
+    float v[8], o[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[i], v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = vc * 8 + j;
+      const int g = n * G + c / cpg;
+      const float u = (v[j] - mean[g]) * rstd[g] * gamma[c] + beta[c];
+      o[j] = swish ? swish_f(u) : u;
+    }
+    reinterpret_cast<uint4*>(y)[i] = pack8(o);
+  }
+}
+
+// backward pass 1: per (n,g) sums of g = dy*act'(u)*gamma and g*xhat  (double atomics into ws)
+__global__ void __launch_bounds__(256) groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                  const __nv_bfloat16* __restrict__ x,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta,
+                                                                  double* __restrict__ ws, int HW, int C, int G,
+                                                                  int pix_per_cta, int swish) {
+  extern __shared__ float sm[];  // [2][G]
+  const int n = blockIdx.y;
+  const int cpg = C / G;
+  const int vec_per_pix = C >> 3;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int vc = threadIdx.x % vec_per_pix;
+  const int pl = threadIdx.x / vec_per_pix;
+  const int pstride = blockDim.x / vec_per_pix;
+  if (pstride > 0 && pl < pstride) {
+    float s[8], q[8], gm[8], bt[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = vc * 8 + j;
+      s[j] = q[j] = 0.f;
+      gm[j] = gamma[c];
+      bt[j] = beta[c];
+      mu[j] = mean[n * G + c / cpg];
+      rs[j] = rstd[n * G + c / cpg];
+    }
+    const long long base = (long long)n * HW * C;
+    for (int p = p0 + pl; p < p1; p += pstride) {
+      float v[8], d[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + base + (long long)p * C + vc * 8), v);
+      unpack8(*reinterpret_cast<const uint4*>(dy + base + (long long)p * C + vc * 8), d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (v[j] - mu[j]) * rs[j];
+        const float u = xh * gm[j] + bt[j];
+        const float g = d[j] * (swish ? swish_grad_f(u) : 1.0f) * gm[j];
+        s[j] += g;
+        q[j] += g * xh;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (vc * 8 + j) / cpg;
+      atomicAdd(&sm[g], s[j]);
+      atomicAdd(&sm[G + g], q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    atomicAdd(&ws[((long long)n * G + i) * 2 + 0], (double)sm[i]);
+    atomicAdd(&ws[((long long)n * G + i) * 2 + 1], (double)sm[G + i]);
+  }
+}
+
+// backward pass 2: dx = rstd * (g - S1/cnt - xhat * S2/cnt) (+ add)
+__global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                  const __nv_bfloat16* __restrict__ x,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd,
+                                                                  const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta,
+                                                                  const double* __restrict__ ws,
+                                                                  const __nv_bfloat16* __restrict__ add,
+                                                                  __nv_bfloat16* __restrict__ dx, long long total_vec,
+                                                                  int HW, int C, int G, float inv_count, int swish) {
+  const int cpg = C / G;
+  const int vec_per_pix = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vc = (int)(i % vec_per_pix);
+    const long long pix = i / vec_per_pix;
+    const int n = (int)(pix / HW);
+    float v[8], d[8], o[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[i], v);
+    unpack8(reinterpret_cast<const uint4*>(dy)[i], d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = vc * 8 + j;
+      const int gi = n * G + c / cpg;
+      const float rs = rstd[gi];
+      const float xh = (v[j] - mean[gi]) * rs;
+      const float u = xh * gamma[c] + beta[c];
+      const float g = d[j] * (swish ? swish_grad_f(u) : 1.0f) * gamma[c];
+      const float s1 = (float)ws[2 * gi] * inv_count, s2 = (float)ws[2 * gi + 1] * inv_count;
+      o[j] = rs * (g - s1 - xh * s2);
+    }
+    if (add) {
+      float a[8];
+      unpack8(reinterpret_cast<const uint4*>(add)[i], a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    }
+    reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+  }
+}
+
+}  // namespace ffvc
+
+using namespace ffvc;
+
+extern "C" int ffvc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                                  float* rstd, long long rows, int D, float eps, void* stream) {
+  if (D % 8 != 0 || D > 2048) return set_error(FFVC_ERR_ARG, "layernorm: D must be a multiple of 8 and <= 2048");
+  if (rows <= 0) return FFVC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y);
+  if (D <= 1024)
+    layernorm_fwd_kernel<4><<<grid, wpb * 32, 0, st>>>(xb, gamma, beta, yb, mean, rstd, rows, D, eps);
+  else
+    layernorm_fwd_kernel<8><<<grid, wpb * 32, 0, st>>>(xb, gamma, beta, yb, mean, rstd, rows, D, eps);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean,
+                                  const float* rstd, const void* add, void* dx, float* dgamma, float* dbeta,
+                                  long long rows, int D, void* stream) {
+  if (D % 8 != 0 || D > 2048) return set_error(FFVC_ERR_ARG, "layernorm: D must be a multiple of 8 and <= 2048");
+  if (rows <= 0) return FFVC_OK;
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return set_error(FFVC_ERR_ARG, "layernorm_bwd: dgamma/dbeta both or none");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  long long want = (rows + wpb - 1) / wpb;
+  const unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4);
+  const size_t smem = dgamma ? 2 * D * sizeof(float) : 0;
+  auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto ab = reinterpret_cast<const __nv_bfloat16*>(add);
+  auto dxb = reinterpret_cast<__nv_bfloat16*>(dx);
+  if (D <= 1024)
+    layernorm_bwd_kernel<4><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
+  else
+    layernorm_bwd_kernel<8><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+static int gn_check(int C, int G) {
+  if (C % 8 != 0 || G <= 0 || C % G != 0 || C / 8 > 256 || 256 % (C / 8) != 0)
+    return set_error(FFVC_ERR_ARG, "groupnorm: C must be a multiple of 8, divisible by G, C/8 must divide 256");
+  return FFVC_OK;
+}
+
+// ws: N*G*2 doubles (zeroed here).  Produces mean/rstd [N*G].
+extern "C" int ffvc_groupnorm_stats(const void* x, double* ws, float* mean, float* rstd, int N, int HW, int C, int G,
+                                    float eps, void* stream) {
+  int rc = gn_check(C, G);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st);
+  const int pix_per_cta = 1024;
+  dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
+  groupnorm_stats_kernel<<<grid, 256, 2 * G * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ws, HW, C, G,
+                                                                  pix_per_cta);
+  FFVC_CHECK_LAUNCH();
+  groupnorm_finalize_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(ws, mean, rstd, N * G, (double)HW * (C / G), eps);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+extern "C" int ffvc_groupnorm_apply(const void* x, const float* mean, const float* rstd, const float* gamma,
+                                    const float* beta, void* y, int N, int HW, int C, int G, int swish, void* stream) {
+  int rc = gn_check(C, G);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long total_vec = (long long)N * HW * (C / 8);
+  long long want = (total_vec + 255) / 256;
+  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  groupnorm_apply_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta,
+                                               reinterpret_cast<__nv_bfloat16*>(y), total_vec, HW, C, G, swish);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+// dx = d/dx [ act(GN(x)) ] . dy  (+ add).  ws: N*G*2 doubles scratch.
+extern "C" int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                                  const float* gamma, const float* beta, double* ws, const void* add, void* dx, int N,
+                                  int HW, int C, int G, int swish, void* stream) {
+  int rc = gn_check(C, G);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st);
+  const int pix_per_cta = 1024;
+  dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
+  auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  groupnorm_bwd_stats_kernel<<<grid, 256, 2 * G * sizeof(float), st>>>(dyb, xb, mean, rstd, gamma, beta, ws, HW, C, G,
+                                                                      pix_per_cta, swish);
+  FFVC_CHECK_LAUNCH();
+  const long long total_vec = (long long)N * HW * (C / 8);
+  long long want = (total_vec + 255) / 256;
+  const unsigned g2 = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  groupnorm_bwd_apply_kernel<<<g2, 256, 0, st>>>(dyb, xb, mean, rstd, gamma, beta, ws,
+                                                 reinterpret_cast<const __nv_bfloat16*>(add),
+                                                 reinterpret_cast<__nv_bfloat16*>(dx), total_vec, HW, C, G,
+                                                 1.0f / ((float)HW * (C / G)), swish);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
