@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py — prompts/s for one train step of the feed-forward VQGAN-CLIP pipeline (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched per rank by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): MLP-Mixer 32x1024 mapper, VQGAN f16/16384 decoder, 8 cutouts, CLIP ViT-B/32,
+256x256, bf16 compute, batch 64 prompts per GPU, synthetic text embeddings, seeded random-init weights.
+A step = mapper fwd -> clamp -> VQ -> decode -> cutouts -> CLIP -> loss -> full backward -> (NCCL grad all-reduce)
+-> Adam.  Nothing is skipped inside the timed region.
+
+`value`   : whole-job prompts/s, inputs resident in HBM, CUDA-graph replay, CUDA events, max over ranks.
+`e2e`     : same metric through the public API with HOST inputs: per step a pinned-host -> device copy of the
+            embeddings + augmentation parameters and a device -> host read of the loss.
+`roofline`: the tcgen05 GEMM kernel (dominant), algorithmic FLOPs / CUDA-event time of its launches in one step.
+`cpu_baseline` / `--impl reference`: the reference's CPU path (oracle restatement, torch fp32, all host threads)
+            on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MIXER = dict(input_dim=512, image_size=16, channels=256, patch_size=1, dim=1024, depth=32)
+CUTN = 8
+CLIP_DIM = 512
+METRIC = "prompts/sec per train step (256x256, ViT-B/32)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def flops_per_prompt():
+    """SURVEY App. B formulas, config #2 (S=16, D=1024, L=32, cutn=8)."""
+    T, C, D, L = 256, 256, 1024, 32
+    mixer_fwd = 2 * 512 * T * C + 2 * T * C * D + L * (4 * T * 4 * T * D + 4 * T * D * 4 * D) + 2 * T * D * C
+    vit = 2 * 49 * 3072 * 768 + 12 * (2 * 50 * 768 * 2304 + 4 * 50 * 50 * 768 + 2 * 50 * 768 * 768 + 16 * 50 * 768 * 768) + 2 * 768 * 512
+    return dict(mapper=3 * mixer_fwd, decoder=506.0e9, vq=2.15e9, clip=CUTN * 2 * vit, total=3 * mixer_fwd + 506.0e9 + 2.15e9 + CUTN * 2 * vit)
+
+
+# ------------------------------------------------------------------------------------------------ model construction
+def build_b200(device, batch, world, pg, seed=0):
+    from feed_forward_vqgan_clip_b200.clip_vit import CLIP
+    from feed_forward_vqgan_clip_b200.mixer import Mixer
+    from feed_forward_vqgan_clip_b200.train_step import TrainStep
+    from feed_forward_vqgan_clip_b200.vqgan import VQModel
+    torch.manual_seed(seed)                       # same seed on every rank = identical replicas (main.py:628)
+    net = Mixer(**MIXER)
+    vq = VQModel()
+    with torch.no_grad():
+        vq.quantize.embedding.weight.normal_(0, 1)   # N(0,1) codebook (taming's U(+-1/n) makes ties)
+    clip = CLIP()
+    net, vq, clip = net.to(device), vq.to(device).eval().requires_grad_(False), clip.to(device).eval().requires_grad_(False)
+    return TrainStep(net, vq, clip, cutn=CUTN, lr=1e-3, world_size=world, process_group=pg, seed=seed + 17)
+
+
+def synthetic_embeddings(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(n, CLIP_DIM, generator=g) * 0.45).float()     # |x| ~ 10 like raw CLIP text embeddings
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(steps, warmup, sample_batch):
+    import oracle.clip_vit as oclip
+    import oracle.mixer as omix
+    import oracle.vqgan as ovq
+    from oracle.train_step import OracleTrainer
+    from feed_forward_vqgan_clip_b200.cutouts import sample_params
+    cores = torch.get_num_threads()
+    sd_m = omix.init_mixer_state_dict(CLIP_DIM, MIXER["image_size"], MIXER["channels"], MIXER["dim"], MIXER["depth"], seed=0)
+    sd_v = ovq.init_vqgan_state_dict(seed=1)
+    sd_c = oclip.init_clip_state_dict(seed=2)
+    tr = OracleTrainer(sd_m, sd_v, sd_c, MIXER["image_size"], MIXER["channels"], cutn=CUTN)
+    g = torch.Generator().manual_seed(3)
+    times = []
+    for i in range(warmup + steps):
+        x = synthetic_embeddings(sample_batch, 100 + i)
+        prm = sample_params(CUTN * sample_batch, 224, g)
+        t0 = time.perf_counter()
+        tr.step(x, x, prm)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return dict(value=sample_batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
+                sample="%d step(s) of %d prompt(s) (config #2 nets, fp32, torch CPU, %d threads) after %d warm-up"
+                       % (len(times), sample_batch, cores, warmup))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="prompts per GPU")
+    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "config#2: MLP-Mixer 32x1024 -> VQGAN f16/16384 decode -> 8 cutouts -> CLIP ViT-B/32, 256x256",
+              "per_gpu_batch": args.batch, "global_batch": args.batch * world, "cutn": CUTN,
+              "parallelism": "dp%d" % world, "l2": "inputs larger than L2 (tens of GB of activations per step)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        K, W = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+        r = cpu_reference(K, W, args.cpu_sample_batch)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "prompts/s", "n_gpus": args.gpus,
+                          "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": r["value"], "unit": "prompts/s", "cores": r["cores"], "kind": "port",
+                                           "sample": r["sample"]},
+                          "e2e": {"value": r["value"], "unit": "prompts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    from feed_forward_vqgan_clip_b200 import ops
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+
+    B = args.batch
+    ts = build_b200(dev, B, world, pg)
+    x_host = [synthetic_embeddings(B, 1000 + 7919 * rank + i).pin_memory() for i in range(4)]
+
+    ops.reset_launch_count()
+    if not args.no_graph:
+        ts.capture(B, CLIP_DIM)
+        launches_per_step = ops.launch_count() // 2          # capture() runs the body twice (warm-up + capture)
+        run = lambda i: ts.replay(x_host[i % 4], None, None)               # noqa: E731
+        ts.static["inp"].copy_(x_host[0])
+        run_dev = lambda i: ts.graph.replay()                              # noqa: E731 (inputs already in HBM)
+    else:
+        xd = [x.to(dev) for x in x_host]
+        ts.step(xd[0])
+        launches_per_step = ops.launch_count()
+        run = lambda i: ts.step(x_host[i % 4].to(dev, non_blocking=True))  # noqa: E731
+        run_dev = lambda i: ts.step(xd[i % 4])                             # noqa: E731
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value)
+    for i in range(args.warmup):
+        run_dev(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_dev(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    total_ms = ms.item()
+    ms_per_step = total_ms / args.steps
+    value = B * world / (ms_per_step / 1e3)
+
+    # ---------------- end-to-end through the public API with host inputs (e2e)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss = run(i)
+        loss_host = loss.item()                                    # D2H read of the step's loss
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_s, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / e2e_s.item()
+    N = CUTN * B
+    h2d = B * CLIP_DIM * 4 * 2 + N * (9 + 9 + 1 + 1) * 4 + 16
+
+    # ---------------- roofline of the dominant kernel: instrumented eager step, CUDA events around every GEMM launch
+    roof = None
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        ev, fl = [], []
+        real_gemm = ops.gemm
+
+        def timed_gemm(a, b, out, M, Nn, K, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = real_gemm(a, b, out, M, Nn, K, **kw)
+            e.record()
+            ev.append((s, e))
+            fl.append(2.0 * M * Nn * K * kw.get("batch", 1) * kw.get("k_segs", 1))
+            return r
+
+        ops.gemm = timed_gemm
+        import feed_forward_vqgan_clip_b200.ops as _o
+        _o.gemm = timed_gemm
+        xd0 = x_host[0].to(dev)
+        if world == 1:
+            s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_all.record()
+            ts.step(xd0)
+            e_all.record()
+            torch.cuda.synchronize()
+            gemm_ms = sum(s.elapsed_time(e) for s, e in ev)
+            gemm_flops = sum(fl)
+            achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+            peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+            roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " (sustained cuBLAS bf16)",
+                    "launches_per_step": len(ev), "gemm_ms_per_step": gemm_ms, "eager_step_ms": s_all.elapsed_time(e_all),
+                    "gemm_share_of_step": gemm_ms / s_all.elapsed_time(e_all),
+                    "flops_per_step_executed": gemm_flops}
+        ops.gemm = real_gemm
+        _o.gemm = real_gemm
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    fp = flops_per_prompt()
+    peaks, peak_src = load_peaks()
+    line = {"metric": METRIC, "value": value, "unit": "prompts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "prompts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches_per_step) * args.steps * 2,
+            "launches_per_step": int(launches_per_step), "cuda_graph": not args.no_graph, "last_loss": loss_host,
+            "algorithmic_tflop_per_prompt": fp["total"] / 1e12,
+            "step_tflops_achieved": fp["total"] * value / world / 1e12,
+            "step_frac_of_bf16_peak": fp["total"] * value / world / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
+    if roof is not None:
+        line["roofline"] = roof
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(1, 1, args.cpu_sample_batch)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "prompts/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,11 +1,14 @@
-"""ctypes binding of libffvc_sm100.so (include/ffvc.h).  Fails loudly when the library is absent:
-there is no CPU or PyTorch fallback for the hot path."""
+"""ctypes binding of libffvc_sm100.so.  Argument types are derived from include/ffvc.h itself, so the binding
+cannot drift from the C ABI.  Fails loudly when the library is absent: there is no CPU / PyTorch fallback."""
 import ctypes as C
 import os
+import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libffvc_sm100.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "ffvc.h")
 _lib = None
+_decls = None
 
 
 class GemmParams(C.Structure):
@@ -26,6 +29,46 @@ class GemmParams(C.Structure):
     ]
 
 
+def _ctype(t):
+    t = t.strip()
+    if t == "const char*":
+        return C.c_char_p
+    if t.endswith("*"):
+        return C.c_void_p
+    if t == "int":
+        return C.c_int
+    if t == "long long":
+        return C.c_longlong
+    if t == "float":
+        return C.c_float
+    if t == "void":
+        return None
+    raise ValueError("unmapped C type in ffvc.h: %r" % t)
+
+
+def header_declarations():
+    """{name: (restype, [argtypes])} for every function declared in include/ffvc.h."""
+    global _decls
+    if _decls is not None:
+        return _decls
+    src = open(HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"typedef struct \{.*?\} \w+;", " ", src, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"(const char\*|long long|int|void)\s+(ffvc_\w+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        argtypes = []
+        for a in [x.strip() for x in args.split(",")]:
+            if a in ("void", ""):
+                continue
+            a = re.sub(r"\s+", " ", a)
+            mm = re.match(r"^(.*?)(\w+)$", a)           # strip the parameter name
+            argtypes.append(_ctype(mm.group(1).strip().replace(" *", "*")))
+        decls[name] = (_ctype(ret), argtypes)
+    _decls = decls
+    return decls
+
+
 def load():
     global _lib
     if _lib is not None:
@@ -35,10 +78,10 @@ def load():
             "libffvc_sm100.so not found at %s — build it with `python -m feed_forward_vqgan_clip_b200.build` "
             "(or __graft_entry__.build()).  There is no fallback path." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
-    lib.ffvc_last_error.restype = C.c_char_p
-    lib.ffvc_launch_count.restype = C.c_longlong
-    lib.ffvc_sizeof.restype = C.c_int
-    lib.ffvc_sizeof.argtypes = [C.c_char_p]
+    for name, (ret, argtypes) in header_declarations().items():
+        fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+        fn.restype = ret
+        fn.argtypes = argtypes
     _lib = lib
     return lib
 

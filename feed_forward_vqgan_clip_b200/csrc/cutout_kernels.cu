@@ -258,7 +258,7 @@ struct FinalParams {
   const float* hue;     // [N]
   const float* noise;   // [N][3][P][P]  (standard normal, NCHW like randn_like(batch))
   const float* facs;    // [N]           (U(0, noise_fac))
-  int ex0, ey0, ex1, ey1;  // erase rectangle (empty if ex1 <= ex0)
+  const int* erase;     // DEVICE int[4]: x0, y0, x1, y1 (empty if x1 <= x0)
   float mean[3], istd[3];
   int N, P, patch, grid;   // grid = P / patch
 };
@@ -277,7 +277,7 @@ __global__ void cutout_final_fwd_kernel(FinalParams fp, __nv_bfloat16* __restric
     D3 ro, go, bo;
     jitter({c[0], 1, 0, 0}, {c[1], 0, 1, 0}, {c[2], 0, 0, 1}, fp.sat[n], fp.hue[n], ro, go, bo);
     float o[3] = {ro.v, go.v, bo.v};
-    const bool erased = ox >= fp.ex0 && ox < fp.ex1 && oy >= fp.ey0 && oy < fp.ey1;
+    const bool erased = ox >= fp.erase[0] && ox < fp.erase[2] && oy >= fp.erase[1] && oy < fp.erase[3];
     const float fac = fp.facs[n];
     const int pp = fp.patch * fp.patch;
     const int pidx = (oy / fp.patch) * fp.grid + ox / fp.patch;
@@ -300,7 +300,7 @@ __global__ void cutout_final_bwd_kernel(FinalParams fp, const __nv_bfloat16* __r
     const int ox = (int)(i % P);
     const int oy = (int)((i / P) % P);
     const int n = (int)(i / ((long long)P * P));
-    const bool erased = ox >= fp.ex0 && ox < fp.ex1 && oy >= fp.ey0 && oy < fp.ey1;
+    const bool erased = ox >= fp.erase[0] && ox < fp.erase[2] && oy >= fp.erase[1] && oy < fp.erase[3];
     if (erased) continue;
     const Taps t = make_taps(fp.hinv + n * 9, ox, oy, P, 0);
     float c[3];
@@ -361,10 +361,7 @@ static int fill_final(FinalParams& fp, const float* cut1, const float* hinv, con
   fp.hue = hue;
   fp.noise = noise;
   fp.facs = facs;
-  fp.ex0 = erase[0];
-  fp.ey0 = erase[1];
-  fp.ex1 = erase[2];
-  fp.ey1 = erase[3];
+  fp.erase = erase;
   for (int i = 0; i < 3; ++i) {
     fp.mean[i] = mean[i];
     fp.istd[i] = 1.0f / std_[i];
@@ -375,7 +372,7 @@ static int fill_final(FinalParams& fp, const float* cut1, const float* hinv, con
   fp.grid = P / patch;
   return FFVC_OK;
 }
-// erase / mean / std are HOST pointers (4 ints, 3 floats, 3 floats).  img_out (optional, [N][3][P][P] fp32) receives the
+// erase is a DEVICE int[4]; mean / std are HOST pointers (3 floats each).  img_out (optional, [N][3][P][P] fp32) receives the
 // normalised cutouts in the reference's NCHW layout (for parity tests / callers that want the tensor).
 extern "C" int ffvc_cutout_final_fwd(const float* cut1, const float* hinv, const float* sat, const float* hue,
                                      const float* noise, const float* facs, const int* erase, const float* mean,

@@ -356,8 +356,12 @@ __global__ void __launch_bounds__(256) conv3x3_smallcin_kernel(const float* __re
 // p,g,m,v fp32 flat arenas; also refreshes the bf16 shadow the GEMMs read.  grad_scale folds the DP average.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n,
-                                                   float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                                                   float grad_scale, float wd) {
+                                                   const float* __restrict__ hyper) {
+  // hyper (device, so a captured CUDA graph sees per-step values): lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t),
+  // grad_scale, weight_decay
+  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], bc1 = hyper[4], bc2_sqrt = hyper[5];
+  const float grad_scale = hyper[6], wd = hyper[7];
+  const float step_size = lr / bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float gv = g[i] * grad_scale;
     const float pv = p[i];
@@ -367,9 +371,19 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     m[i] = mv;
     v[i] = vv;
     const float denom = sqrtf(vv) / bc2_sqrt + eps;
-    const float np = pv - (lr / bc1) * (mv / denom);
+    const float np = pv - step_size * (mv / denom);
     p[i] = np;
     if (shadow) shadow[i] = __float2bfloat16(np);
+  }
+}
+
+// advance Adam's step counter on the device and refresh the bias corrections (graph-capturable, no host staging)
+__global__ void adam_tick_kernel(float* __restrict__ hyper) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float t = hyper[8] + 1.0f;
+    hyper[8] = t;
+    hyper[4] = 1.0f - powf(hyper[1], t);
+    hyper[5] = sqrtf(1.0f - powf(hyper[2], t));
   }
 }
 
@@ -379,6 +393,31 @@ __global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ ou
     acc += x[i] * x[i];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+
+// ---------------------------------------------------------------- CLIP ViT token assembly (cloob.py:240-243)
+// x[n][0] = cls + pos[0];  x[n][1+p] = pe[n][p] + pos[1+p]        (bf16 activations, fp32 cls/pos)
+__global__ void clip_assemble_kernel(const __nv_bfloat16* __restrict__ pe, const float* __restrict__ cls,
+                                     const float* __restrict__ pos, __nv_bfloat16* __restrict__ x, int N, int T, int W) {
+  const long long total = (long long)N * T * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    const int t = (int)((i / W) % T);
+    const long long n = i / ((long long)W * T);
+    const float v = (t == 0) ? cls[w] : __bfloat162float(pe[(n * (T - 1) + (t - 1)) * W + w]);
+    x[i] = __float2bfloat16(v + pos[t * W + w]);
+  }
+}
+// generic strided row copy (bf16): dst[r*dst_stride + c] = src[r*src_stride + c]
+__global__ void copy_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int D,
+                                 long long src_stride, long long dst_stride) {
+  const long long total = rows * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D;
+    const int c = (int)(i % D);
+    dst[r * dst_stride + c] = src[r * src_stride + c];
+  }
 }
 
 }  // namespace ffvc
@@ -506,20 +545,33 @@ extern "C" int ffvc_conv3x3_cin3(const float* x, const float* w, void* y, int N,
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
-extern "C" int ffvc_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, float lr,
-                              float beta1, float beta2, float eps, int step, float grad_scale, float weight_decay,
-                              void* stream) {
-  if (step < 1) return set_error(FFVC_ERR_ARG, "adam: step must be >= 1");
-  const float bc1 = 1.0f - powf(beta1, (float)step);
-  const float bc2 = 1.0f - powf(beta2, (float)step);
-  adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(p, g, m, v, BF(shadow_bf16), n, lr, beta1, beta2, eps, bc1,
-                                                                 sqrtf(bc2), grad_scale, weight_decay);
+extern "C" int ffvc_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
+                              const float* hyper_dev, void* stream) {
+  if (!hyper_dev) return set_error(FFVC_ERR_ARG, "adam: hyper-parameter block is null");
+  adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(p, g, m, v, BF(shadow_bf16), n, hyper_dev);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_adam_tick(float* hyper_dev, void* stream) {
+  adam_tick_kernel<<<1, 32, 0, ST(stream)>>>(hyper_dev);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
 extern "C" int ffvc_sumsq(const float* x, float* out, long long n, void* stream) {
   cudaMemsetAsync(out, 0, sizeof(float), ST(stream));
   sumsq_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, ST(stream)>>>(x, out, n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+extern "C" int ffvc_clip_assemble(const void* pe, const float* cls, const float* pos, void* x, int N, int T, int W, void* stream) {
+  clip_assemble_kernel<<<grid_for((long long)N * T * W, 256), 256, 0, ST(stream)>>>(CBF(pe), cls, pos, BF(x), N, T, W);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_copy_rows(const void* src, void* dst, long long rows, int D, long long src_stride, long long dst_stride,
+                              void* stream) {
+  copy_rows_kernel<<<grid_for(rows * D, 256), 256, 0, ST(stream)>>>(CBF(src), BF(dst), rows, D, src_stride, dst_stride);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

@@ -1,5 +1,5 @@
 """Thin Python wrappers over the C ABI (include/ffvc.h).  Tensors are torch CUDA tensors used purely as
-device-memory handles; every computation happens in libffvc_sm100.so."""
+device-memory handles; every computation happens in libffvc_sm100.so.  No fallback path exists."""
 import ctypes as C
 
 import torch
@@ -11,25 +11,45 @@ KMAJOR, MNMAJOR, CONV3X3 = 0, 1, 2
 ROLE_BCAST, ROLE_OUT, ROLE_SEG = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_SWISH = 0, 1, 2, 3
 
+BF16 = torch.bfloat16
+F32 = torch.float32
+
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch.cuda.current_stream().cuda_stream
 
 
-def _ptr(t):
-    if t is None:
-        return None
-    assert t.is_cuda, "ffvc ops need CUDA tensors (no CPU fallback)"
-    return C.c_void_p(t.data_ptr())
+def _arg(a):
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda:
+            raise RuntimeError("ffvc ops need CUDA tensors (there is no CPU fallback)")
+        return a.data_ptr()
+    return a
+
+
+def call(name, *args):
+    """Call `int ffvc_<name>(..., void* stream)`; tensors become device pointers, the stream is appended."""
+    fn = getattr(_lib.load(), "ffvc_" + name)
+    check(fn(*[_arg(a) for a in args], _stream()))
+
+
+def launch_count():
+    return int(_lib.load().ffvc_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().ffvc_reset_launch_count()
 
 
 def gemm(a, b, out, M, N, K, *, a_mode=KMAJOR, b_mode=KMAJOR, a_ld=None, b_ld=None,
          a_role=ROLE_BCAST, b_role=ROLE_BCAST, a_bs=0, b_bs=0, batch=1, k_segs=1, splits=1, block_n=0,
          conv=None, pre_out=None, aux=None, res=None, bias=None, ldc=None, out_bs=0, atomic=False,
-         bias_mode=1, act=ACT_NONE, mul_mode=ACT_NONE, alpha=1.0):
-    """out[b,m,n] (+)= epilogue(alpha * sum_k A[m,k] B[n,k]); see include/ffvc.h:ffvc_gemm."""
+         bias_mode=1, act=ACT_NONE, mul_mode=ACT_NONE, alpha=1.0, a_off=0, out_off=0):
+    """out[b,m,n] (+)= epilogue(alpha * sum_k A[m,k] B[n,k]); see include/ffvc.h:ffvc_gemm.
+    a_off / out_off: element offsets added to the base pointers."""
     p = GemmParams()
-    p.a, p.b = _ptr(a), _ptr(b)
+    p.a = a.data_ptr() + a_off * a.element_size()
+    p.b = b.data_ptr()
     p.a_mode, p.b_mode = a_mode, b_mode
     if a_ld is None:
         a_ld = K if a_mode == KMAJOR else M
@@ -42,12 +62,42 @@ def gemm(a, b, out, M, N, K, *, a_mode=KMAJOR, b_mode=KMAJOR, a_ld=None, b_ld=No
     p.batch, p.k_segs, p.splits, p.block_n = batch, k_segs, splits, block_n
     if conv is not None:
         p.conv_n, p.conv_h, p.conv_w, p.conv_c = conv
-    p.out, p.pre_out, p.aux, p.res, p.bias = _ptr(out), _ptr(pre_out), _ptr(aux), _ptr(res), _ptr(bias)
+    p.out = out.data_ptr() + out_off * out.element_size()
+    p.pre_out = None if pre_out is None else pre_out.data_ptr()
+    p.aux = None if aux is None else aux.data_ptr()
+    p.res = None if res is None else res.data_ptr()
+    p.bias = None if bias is None else bias.data_ptr()
     p.ldc = N if ldc is None else ldc
     p.out_batch_stride = out_bs
-    p.out_fp32 = 1 if out.dtype == torch.float32 else 0
-    assert out.dtype in (torch.float32, torch.bfloat16)
+    assert out.dtype in (F32, BF16)
+    p.out_fp32 = 1 if out.dtype == F32 else 0
     p.atomic = 1 if atomic else 0
     p.bias_mode, p.act, p.mul_mode, p.alpha = bias_mode, act, mul_mode, alpha
     check(_lib.load().ffvc_gemm(C.byref(p), _stream()))
     return out
+
+
+# ------------------------------------------------------------------ convenience forms used by the model code
+def linear_fwd(x, w, bias, out, M, N, K, **kw):
+    """out[M,N] = x[M,K] @ w[N,K]^T + bias"""
+    return gemm(x, w, out, M, N, K, bias=bias, **kw)
+
+
+def linear_dgrad(dy, w, dx, M, N, K, **kw):
+    """dx[M,K] = dy[M,N] @ w[N,K]  (w read MN-major straight from its forward layout)"""
+    return gemm(dy, w, dx, M, K, N, b_mode=MNMAJOR, b_ld=K, **kw)
+
+
+def linear_wgrad(dy, x, dw, M, N, K, splits=1):
+    """dw[N,K] += dy[M,N]^T @ x[M,K]   (fp32 atomic accumulation)"""
+    return gemm(dy, x, dw, N, K, M, a_mode=MNMAJOR, b_mode=MNMAJOR, a_ld=N, b_ld=K, atomic=True, splits=splits)
+
+
+def auto_splits(M, N, K, sms=148):
+    """split-K factor so that a wgrad GEMM with few output tiles still fills the SMs."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    kb = (K + 63) // 64
+    s = 1
+    while tiles * s * 2 <= sms and s * 2 <= kb:
+        s *= 2
+    return s

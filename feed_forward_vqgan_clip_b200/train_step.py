@@ -1,0 +1,176 @@
+"""One B200-native train step of the feed-forward VQGAN-CLIP pipeline — the body of the reference's hot loop
+(main.py:729-837) with every device computation in libffvc_sm100.so:
+
+    z = net(inp_feats)                       main.py:754          MixerEngine.forward
+    z = clamp_with_grad(z, z_min, z_max)     main.py:763          ffvc_vq_nearest (fused clamp)
+    xr = synth(vq, z)                        main.py:767,140-143  ffvc_vq_nearest + DecoderEngine.forward
+    x = (make_cutouts(xr) - mean) / std      main.py:796-797      CutoutEngine.forward
+    embed = perceptor.encode_image(x)        main.py:799          ClipEngine.forward
+    dists = spherical distance loss          main.py:801-811      ffvc_spherical_loss (fwd + bwd fused)
+    loss.backward()                          main.py:832          the engines' explicit backward passes
+    opt.step()                               main.py:835          ffvc_adam_step (fused, flat arena)
+    Horovod gradient averaging               main.py:627          one NCCL all-reduce of the flat gradient arena
+
+The step can be captured into a CUDA graph (static shapes): `TrainStep.capture()`; inputs then travel through
+static device buffers and one graph launch replaces ~2000 kernel launches.
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import BF16, F32, call
+from .cutouts import CutoutEngine, sample_params
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics (lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) on the mapper's flat arena."""
+
+    def __init__(self, engine, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.eng = engine
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(engine.arena)
+        self.v = torch.zeros_like(engine.arena)
+        self.t = 0
+        b1, b2 = betas
+        self.hyper = torch.tensor([lr, b1, b2, eps, 1.0, 1.0, 1.0, weight_decay, 0.0, 0, 0, 0, 0, 0, 0, 0], dtype=F32).to(engine.dev)
+
+    def set_lr(self, lr):
+        self.lr = lr
+        self.hyper[0:1].fill_(lr)
+
+    def set_grad_scale(self, s):
+        self.hyper[6:7].fill_(s)
+
+    def apply(self):
+        """tick the device-side step counter (bias corrections) and update parameters + bf16 shadow in one pass."""
+        e = self.eng
+        self.t += 1
+        call("adam_tick", self.hyper)
+        call("adam_step", e.arena, e.grad, self.m, self.v, e.shadow, e.total, self.hyper)
+        e.ext_shadow_fresh = True
+
+
+class TrainStep:
+    def __init__(self, net, vq, perceptor, cutn=8, lr=1e-3, cut_size=224, target_loss_coef=1.0, world_size=1,
+                 process_group=None, seed=0):
+        self.net, self.vq, self.perceptor = net, vq, perceptor
+        self.mix = net.engine()
+        self.dec = vq.engine()
+        self.clip = perceptor.visual.engine()
+        self.dev = self.mix.dev
+        self.cutn, self.cut_size = cutn, cut_size
+        self.cut = CutoutEngine(cut_size, cutn, self.clip.patch, self.dev)
+        self.coef = target_loss_coef
+        self.opt = FusedAdam(self.mix, lr=lr)
+        self.world, self.pg = world_size, process_group
+        self.opt.set_grad_scale(1.0 / world_size)
+        cb = self.dec.codebook
+        self.z_lo, self.z_hi = float(cb.min()), float(cb.max())          # main.py:645-646,763 (global scalars)
+        self.gen = torch.Generator().manual_seed(seed)
+        self.loss = torch.zeros(1, device=self.dev, dtype=F32)
+        self.graph = None
+        self.static = None
+        self.last_indices = None
+
+    # ------------------------------------------------------------------ one step on device-resident inputs
+    def _device_step(self, inp, out_feats, prm):
+        mix, dec, clip, cut = self.mix, self.dec, self.clip, self.cut
+        B = inp.shape[0]
+        S, C = mix.S, mix.C
+        N = self.cutn * B
+        z, sv_m = mix.forward(inp)                                       # [B*T, C] fp32
+        zq, idx, zc = dec.quantize(z, self.z_lo, self.z_hi)
+        self.last_indices = idx
+        img, tape = dec.forward(zq.view(B, S, S, C))                     # [B, H, W, 3] fp32 in [0, 1]
+        patches, sv_c, _ = cut.forward(img, prm)
+        emb, sv_e = clip.forward(patches)
+        demb = torch.empty(N, clip.E, device=self.dev, dtype=F32)
+        call("spherical_loss", emb, out_feats, self.loss, demb, None, N, B, clip.E, self.coef)
+        # ---- backward
+        dpatch = clip.backward(sv_e, demb)
+        del sv_e
+        dimg = cut.backward(sv_c, dpatch)
+        del sv_c, dpatch
+        dzq = dec.backward(tape, dimg)                                   # [B*T, C] bf16 (straight-through to z)
+        del tape
+        dzq32 = torch.empty(B * S * S, C, device=self.dev, dtype=F32)
+        call("cast_bf16_f32", dzq, dzq32, dzq.numel())
+        dz = torch.empty_like(dzq32)
+        call("clamp_bwd", dzq32, z, dz, dz.numel(), self.z_lo, self.z_hi)
+        mix.zero_grad_arena()
+        mix.backward(sv_m, dz)
+        del sv_m
+        if self.world > 1:
+            torch.distributed.all_reduce(mix.grad, group=self.pg)       # one NCCL all-reduce over NVLink (main.py:627)
+        self.opt.apply()
+        return self.loss
+
+    def new_params(self, B):
+        prm = sample_params(self.cutn * B, self.cut_size, self.gen, with_noise=False)
+        return prm
+
+    def _stage_params(self, prm, B):
+        N = self.cutn * B
+        dev = self.dev
+        out = {}
+        for k in ("affine_inv", "persp_inv", "sat", "hue"):
+            out[k] = prm[k].to(dev, non_blocking=True)
+        out["erase"] = torch.tensor([int(t) for t in prm["erase"]], dtype=torch.int32).to(dev, non_blocking=True)
+        if "noise_raw" in prm:
+            out["noise_raw"] = prm["noise_raw"].to(dev)
+            out["facs"] = prm["facs"].to(dev)
+        else:   # main.py:223-225: facs ~ U(0, noise_fac), noise ~ N(0,1), drawn on the device
+            out["facs"] = torch.rand(N, device=dev) * 0.1
+            out["noise_raw"] = torch.randn(N, 3, self.cut_size, self.cut_size, device=dev)
+        return out
+
+    def step(self, inp, out_feats=None, prm=None):
+        """Eager step.  inp / out_feats: (B, clip_dim) fp32 CUDA tensors; prm: explicit cutout parameters or None."""
+        if out_feats is None:
+            out_feats = inp
+        B = inp.shape[0]
+        prm = self._stage_params(prm if prm is not None else self.new_params(B), B)
+        return self._device_step(inp.contiguous().float(), out_feats.contiguous().float(), prm)
+
+    # ------------------------------------------------------------------ CUDA-graph path
+    def capture(self, B, clip_dim):
+        dev = self.dev
+        N = self.cutn * B
+        st = dict(inp=torch.zeros(B, clip_dim, device=dev), out=torch.zeros(B, clip_dim, device=dev),
+                  affine_inv=torch.eye(3, device=dev).repeat(N, 1, 1).contiguous(),
+                  persp_inv=torch.eye(3, device=dev).repeat(N, 1, 1).contiguous(),
+                  sat=torch.ones(N, device=dev), hue=torch.zeros(N, device=dev),
+                  erase=torch.zeros(4, device=dev, dtype=torch.int32))
+        self.static = st
+
+        def body():
+            prm = dict(affine_inv=st["affine_inv"], persp_inv=st["persp_inv"], sat=st["sat"], hue=st["hue"], erase=st["erase"],
+                       facs=torch.rand(N, device=dev) * 0.1,
+                       noise_raw=torch.randn(N, 3, self.cut_size, self.cut_size, device=dev))
+            self._device_step(st["inp"], st["out"], prm)
+
+        # warm-up on a side stream (allocator + lazy init), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+        return self
+
+    def replay(self, inp, out_feats=None, prm=None):
+        """inp may be a pinned host tensor (H2D copy on the current stream) or a device tensor."""
+        st = self.static
+        B = st["inp"].shape[0]
+        st["inp"].copy_(inp, non_blocking=True)
+        st["out"].copy_(inp if out_feats is None else out_feats, non_blocking=True)
+        prm = prm if prm is not None else self.new_params(B)
+        for k in ("affine_inv", "persp_inv", "sat", "hue"):
+            st[k].copy_(prm[k], non_blocking=True)
+        st["erase"].copy_(torch.tensor([int(t) for t in prm["erase"]], dtype=torch.int32), non_blocking=True)
+        self.graph.replay()
+        return self.loss

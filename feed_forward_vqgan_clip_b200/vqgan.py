@@ -1,0 +1,421 @@
+"""VQGAN f16 decoder + the reference's VQ glue, B200-native.
+
+Drop-in for what `load_vqgan_model(...)` returns (main.py:84-103) as far as train() uses it:
+`.quantize.embedding.weight`, `.decode(z_q)`, `.eval()`, `.requires_grad_(False)`, `.to(device)`, and a
+`state_dict` with taming's key names so `vqgan_imagenet_f16_16384.ckpt` loads (`init_from_ckpt`).
+`clamp_with_grad`, `vector_quantize`, `synth` mirror main.py:118-143.
+
+All arithmetic is in libffvc_sm100.so: 3x3 / 1x1 convolutions are tcgen05 implicit GEMMs on NHWC bf16 (TMA box
+per filter tap, zero fill = padding), GroupNorm+swish and nearest-2x upsample are vectorised HBM kernels, the
+single-head attention is batched tcgen05 GEMMs + a row softmax, VQ is an fp32 distance search.  The decoder is
+frozen: backward is dgrad only (flipped/transposed filter packs are prepared once).
+Architecture restated from taming-transformers — see oracle/vqgan.py for the CPU restatement.
+"""
+import math
+
+import torch
+from torch import nn
+
+from . import ops
+from .ops import BF16, F32, call
+
+F16_16384 = dict(ch=128, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, attn_resolutions=(16,), resolution=256,
+                 z_channels=256, out_ch=3, embed_dim=256, n_embed=16384)
+
+
+def _decoder_layout(cfg):
+    ch, ch_mult, nrb = cfg["ch"], cfg["ch_mult"], cfg["num_res_blocks"]
+    nres = len(ch_mult)
+    block_in = ch * ch_mult[-1]
+    curr = cfg["resolution"] // 2 ** (nres - 1)
+    levels = []
+    for i_level in reversed(range(nres)):
+        block_out = ch * ch_mult[i_level]
+        blocks = []
+        for _ in range(nrb + 1):
+            blocks.append((block_in, block_out))
+            block_in = block_out
+        levels.append((i_level, blocks, curr in cfg["attn_resolutions"], i_level != 0))
+        if i_level != 0:
+            curr *= 2
+    return levels
+
+
+# ---- parameter containers with taming's module / key names
+class _Res(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(32, cin, eps=1e-6)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.norm2 = nn.GroupNorm(32, cout, eps=1e-6)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.nin_shortcut = nn.Conv2d(cin, cout, 1)
+
+
+class _Attn(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.norm = nn.GroupNorm(32, c, eps=1e-6)
+        self.q, self.k, self.v, self.proj_out = (nn.Conv2d(c, c, 1) for _ in range(4))
+
+
+class _Up(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+
+class _DecoderParams(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        block_in = cfg["ch"] * cfg["ch_mult"][-1]
+        self.conv_in = nn.Conv2d(cfg["z_channels"], block_in, 3, padding=1)
+        self.mid = nn.Module()
+        self.mid.block_1 = _Res(block_in, block_in)
+        self.mid.attn_1 = _Attn(block_in)
+        self.mid.block_2 = _Res(block_in, block_in)
+        ups = {}
+        last = block_in
+        for i_level, blocks, has_attn, has_up in _decoder_layout(cfg):
+            up = nn.Module()
+            up.block = nn.ModuleList([_Res(a, b) for a, b in blocks])
+            up.attn = nn.ModuleList([_Attn(b) for _, b in blocks] if has_attn else [])
+            last = blocks[-1][1]
+            if has_up:
+                up.upsample = _Up(last)
+            ups[i_level] = up
+        self.up = nn.ModuleList([ups[i] for i in range(len(cfg["ch_mult"]))])
+        self.norm_out = nn.GroupNorm(32, last, eps=1e-6)
+        self.conv_out = nn.Conv2d(last, cfg["out_ch"], 3, padding=1)
+
+
+class VQModel(nn.Module):
+    """Decoder half of taming's VQModel (the encoder / loss are never used by the train step; main.py:102)."""
+
+    def __init__(self, cfg=F16_16384):
+        super().__init__()
+        self.cfg = dict(cfg)
+        self.quantize = nn.Module()
+        self.quantize.embedding = nn.Embedding(cfg["n_embed"], cfg["embed_dim"])
+        self.post_quant_conv = nn.Conv2d(cfg["embed_dim"], cfg["z_channels"], 1)
+        self.decoder = _DecoderParams(cfg)
+        self.loss = None
+        self._engine = None
+
+    def init_from_ckpt(self, path):
+        sd = torch.load(path, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+        own = self.state_dict()
+        self.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
+        self._engine = None
+
+    def engine(self):
+        if self._engine is None or not self._engine.valid():
+            self._engine = DecoderEngine(self)
+        return self._engine
+
+    def decode(self, z_q):
+        """z_q (B, embed_dim, S, S) fp32 -> (B, 3, 16S, 16S) fp32 in ~[-1, 1]; differentiable w.r.t. z_q."""
+        return _DecodeFn.apply(self, z_q)
+
+
+class _DecodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, z_q):
+        eng = model.engine()
+        B, C, S, _ = z_q.shape
+        zq = z_q.permute(0, 2, 3, 1).contiguous().to(BF16)
+        img, tape = eng.forward(zq, post=False)
+        ctx.eng, ctx.tape, ctx.shape = eng, tape, (B, C, S)
+        H = img.shape[1]
+        return img.view(B, H, H, 3).permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, S = ctx.shape
+        gd = g.permute(0, 2, 3, 1).contiguous().float()
+        dzq = ctx.eng.backward(ctx.tape, gd, post=False)
+        return None, dzq.view(B, S, S, C).permute(0, 3, 1, 2).float()
+
+
+class DecoderEngine:
+    """Explicit forward / backward over NHWC bf16 activations with a tape of backward closures."""
+
+    def __init__(self, model):
+        self.model = model
+        self.cfg = model.cfg
+        self.dev = model.post_quant_conv.weight.device
+        if self.dev.type != "cuda":
+            raise RuntimeError("the VQGAN decoder runs on CUDA only (no CPU fallback)")
+        self._ptr = model.post_quant_conv.weight.data_ptr()
+        self.layout = _decoder_layout(self.cfg)
+        self.pk = {}
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        for k, v in sd.items():
+            if k.endswith(".weight") and v.dim() == 4:
+                name = k[:-7]
+                co, ci, kh, kw = v.shape
+                if kh == 3 and ci % 64 == 0:
+                    self.pk[name + ".w"] = v.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous().to(BF16)
+                    if co % 64 == 0:   # dgrad pack: [ci][flipped tap][co]
+                        self.pk[name + ".wT"] = v.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous().to(BF16)
+                    else:              # conv_out: dgrad runs on the tiny-Cin SIMT kernel, fp32 [ci][flipped tap][co]
+                        self.pk[name + ".wT32"] = v.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous().float()
+                elif kh == 1:
+                    self.pk[name + ".w"] = v.reshape(co, ci).contiguous().to(BF16)
+                self.pk[name + ".b"] = sd[name + ".bias"].float().contiguous()
+            elif k.endswith(".weight") and v.dim() == 1:
+                name = k[:-7]
+                self.pk[name + ".g"] = v.float().contiguous()
+                self.pk[name + ".be"] = sd[name + ".bias"].float().contiguous()
+        cb = sd["quantize.embedding.weight"].float().contiguous()
+        self.codebook = cb
+        self.codeT = cb.t().contiguous()
+        self.cnorm = torch.empty(cb.shape[0], device=self.dev, dtype=F32)
+        call("rownorm2", cb, self.cnorm, cb.shape[0], cb.shape[1])
+        self._ws = None
+
+    def valid(self):
+        return self.model.post_quant_conv.weight.data_ptr() == self._ptr
+
+    def _new(self, *shape, dtype=BF16):
+        return torch.empty(*shape, device=self.dev, dtype=dtype)
+
+    def _gn_ws(self, n):
+        if self._ws is None or self._ws.numel() < n:
+            self._ws = torch.empty(max(n, 4096), device=self.dev, dtype=torch.float64)
+        return self._ws
+
+    # ---------------------------------------------------------------- primitive ops (forward + backward closure)
+    def conv3(self, x, name, N, H, W, cin, cout, res=None, out_f32=False):
+        out = self._new(N * H * W, cout, dtype=F32 if out_f32 else BF16)
+        ops.gemm(x, self.pk[name + ".w"], out, N * H * W, cout, 9 * cin, a_mode=ops.CONV3X3, conv=(N, H, W, cin),
+                 bias=self.pk[name + ".b"], res=res)
+        return out
+
+    def conv3_dgrad(self, dy, name, N, H, W, cin, cout, res=None):
+        dx = self._new(N * H * W, cin)
+        ops.gemm(dy, self.pk[name + ".wT"], dx, N * H * W, cin, 9 * cout, a_mode=ops.CONV3X3, conv=(N, H, W, cout), res=res)
+        return dx
+
+    def conv1(self, x, name, M, cin, cout, res=None):
+        out = self._new(M, cout)
+        ops.gemm(x, self.pk[name + ".w"], out, M, cout, cin, bias=self.pk[name + ".b"], res=res)
+        return out
+
+    def conv1_dgrad(self, dy, name, M, cin, cout, res=None):
+        dx = self._new(M, cin)
+        ops.linear_dgrad(dy, self.pk[name + ".w"], dx, M, cout, cin, res=res)
+        return dx
+
+    def gn(self, x, name, N, HW, C, swish):
+        mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
+        call("groupnorm_stats", x, self._gn_ws(N * 64), mean, rstd, N, HW, C, 32, 1e-6)
+        y = self._new(N * HW, C)
+        call("groupnorm_apply", x, mean, rstd, self.pk[name + ".g"], self.pk[name + ".be"], y, N, HW, C, 32, int(swish))
+        return y, (mean, rstd)
+
+    def gn_bwd(self, dy, x, stats, name, N, HW, C, swish, add=None):
+        dx = self._new(N * HW, C)
+        call("groupnorm_bwd", dy, x, stats[0], stats[1], self.pk[name + ".g"], self.pk[name + ".be"], self._gn_ws(N * 64),
+             add, dx, N, HW, C, 32, int(swish))
+        return dx
+
+    def resblock(self, x, name, N, H, W, cin, cout, tape):
+        HW = H * W
+        a1, st1 = self.gn(x, name + ".norm1", N, HW, cin, True)
+        h1 = self.conv3(a1, name + ".conv1", N, H, W, cin, cout)
+        del a1
+        a2, st2 = self.gn(h1, name + ".norm2", N, HW, cout, True)
+        short = x if cin == cout else self.conv1(x, name + ".nin_shortcut", N * HW, cin, cout)
+        out = self.conv3(a2, name + ".conv2", N, H, W, cout, cout, res=short)
+        del a2, short
+
+        def bwd(d):
+            d2 = self.conv3_dgrad(d, name + ".conv2", N, H, W, cout, cout)
+            dh1 = self.gn_bwd(d2, h1, st2, name + ".norm2", N, HW, cout, True)
+            d1 = self.conv3_dgrad(dh1, name + ".conv1", N, H, W, cin, cout)
+            ds = d if cin == cout else self.conv1_dgrad(d, name + ".nin_shortcut", N * HW, cin, cout)
+            return self.gn_bwd(d1, x, st1, name + ".norm1", N, HW, cin, True, add=ds)
+
+        tape.append(bwd)
+        return out
+
+    def attn(self, x, name, N, H, W, C, tape):
+        HW = H * W
+        M = N * HW
+        scale = float(C) ** -0.5
+        hn, st = self.gn(x, name + ".norm", N, HW, C, False)
+        q = self.conv1(hn, name + ".q", M, C, C)
+        k = self.conv1(hn, name + ".k", M, C, C)
+        v = self.conv1(hn, name + ".v", M, C, C)
+        del hn
+        S = self._new(N, HW, HW, dtype=F32)
+        ops.gemm(q, k, S, HW, HW, C, a_role=ops.ROLE_OUT, a_bs=HW * C, b_role=ops.ROLE_OUT, b_bs=HW * C, batch=N,
+                 out_bs=HW * HW, alpha=scale)
+        P = self._new(N, HW, HW)
+        call("softmax_fwd", S, P, N * HW, HW)
+        del S
+        O = self._new(M, C)
+        ops.gemm(P, v, O, HW, C, HW, a_role=ops.ROLE_OUT, a_bs=HW * HW, b_mode=ops.MNMAJOR, b_ld=C, b_role=ops.ROLE_OUT,
+                 b_bs=HW * C, batch=N, out_bs=HW * C)
+        out = self.conv1(O, name + ".proj_out", M, C, C, res=x)
+        del O
+
+        def bwd(d):
+            dO = self.conv1_dgrad(d, name + ".proj_out", M, C, C)
+            dP = self._new(N, HW, HW, dtype=F32)
+            ops.gemm(dO, v, dP, HW, HW, C, a_role=ops.ROLE_OUT, a_bs=HW * C, b_role=ops.ROLE_OUT, b_bs=HW * C, batch=N,
+                     out_bs=HW * HW)
+            dV = self._new(M, C)   # dV[j,c] = sum_i P[i,j] dO[i,c]
+            ops.gemm(P, dO, dV, HW, C, HW, a_mode=ops.MNMAJOR, a_ld=HW, a_role=ops.ROLE_OUT, a_bs=HW * HW,
+                     b_mode=ops.MNMAJOR, b_ld=C, b_role=ops.ROLE_OUT, b_bs=HW * C, batch=N, out_bs=HW * C)
+            dS = self._new(N, HW, HW)
+            call("softmax_bwd", P, dP, dS, N * HW, HW, scale)
+            del dP
+            dQ = self._new(M, C)   # dQ[i,c] = sum_j dS[i,j] k[j,c]
+            ops.gemm(dS, k, dQ, HW, C, HW, a_role=ops.ROLE_OUT, a_bs=HW * HW, b_mode=ops.MNMAJOR, b_ld=C,
+                     b_role=ops.ROLE_OUT, b_bs=HW * C, batch=N, out_bs=HW * C)
+            dK = self._new(M, C)   # dK[j,c] = sum_i dS[i,j] q[i,c]
+            ops.gemm(dS, q, dK, HW, C, HW, a_mode=ops.MNMAJOR, a_ld=HW, a_role=ops.ROLE_OUT, a_bs=HW * HW,
+                     b_mode=ops.MNMAJOR, b_ld=C, b_role=ops.ROLE_OUT, b_bs=HW * C, batch=N, out_bs=HW * C)
+            dh = self.conv1_dgrad(dQ, name + ".q", M, C, C)
+            dh = self.conv1_dgrad(dK, name + ".k", M, C, C, res=dh)
+            dh = self.conv1_dgrad(dV, name + ".v", M, C, C, res=dh)
+            return self.gn_bwd(dh, x, st, name + ".norm", N, HW, C, False, add=d)
+
+        tape.append(bwd)
+        return out
+
+    # ---------------------------------------------------------------- whole decoder
+    def forward(self, zq, post=True):
+        """zq: [B, S, S, embed_dim] bf16 NHWC.  Returns (image [B, 16S, 16S, 3] fp32 NHWC, tape).
+        post=True applies (x+1)/2 and clamp_with_grad(0,1) (main.py:142)."""
+        cfg = self.cfg
+        N, S = zq.shape[0], zq.shape[1]
+        tape = []
+        H = W = S
+        E, Z = cfg["embed_dim"], cfg["z_channels"]
+        block_in = cfg["ch"] * cfg["ch_mult"][-1]
+        h = self.conv1(zq.reshape(N * H * W, E), "post_quant_conv", N * H * W, E, Z)
+        tape.append(lambda d, M=N * H * W: self.conv1_dgrad(d, "post_quant_conv", M, E, Z))
+        h = self.conv3(h, "decoder.conv_in", N, H, W, Z, block_in)
+        tape.append(lambda d, H=H, W=W: self.conv3_dgrad(d, "decoder.conv_in", N, H, W, Z, block_in))
+        h = self.resblock(h, "decoder.mid.block_1", N, H, W, block_in, block_in, tape)
+        h = self.attn(h, "decoder.mid.attn_1", N, H, W, block_in, tape)
+        h = self.resblock(h, "decoder.mid.block_2", N, H, W, block_in, block_in, tape)
+        c = block_in
+        for i_level, blocks, has_attn, has_up in self.layout:
+            for j, (cin, cout) in enumerate(blocks):
+                h = self.resblock(h, "decoder.up.%d.block.%d" % (i_level, j), N, H, W, cin, cout, tape)
+                if has_attn:
+                    h = self.attn(h, "decoder.up.%d.attn.%d" % (i_level, j), N, H, W, cout, tape)
+                c = cout
+            if has_up:
+                up = self._new(N * 4 * H * W, c)
+                call("upsample2x_fwd", h, up, N, H, W, c)
+                name = "decoder.up.%d.upsample.conv" % i_level
+                H2, W2 = 2 * H, 2 * W
+                h = self.conv3(up, name, N, H2, W2, c, c)
+                del up
+
+                def up_bwd(d, name=name, H=H, W=W, c=c):
+                    du = self.conv3_dgrad(d, name, N, 2 * H, 2 * W, c, c)
+                    dx = self._new(N * H * W, c)
+                    call("upsample2x_bwd", du, dx, N, H, W, c)
+                    return dx
+
+                tape.append(up_bwd)
+                H, W = H2, W2
+        HW = H * W
+        x_last = h
+        a, st = self.gn(h, "decoder.norm_out", N, HW, c, True)
+        dimg = self.conv3(a, "decoder.conv_out", N, H, W, c, cfg["out_ch"], out_f32=True)   # [N*HW, 3] fp32
+        del a
+        if post:
+            img = self._new(N * HW, 3, dtype=F32)
+            call("image_post_fwd", dimg, img, N * HW * 3)
+        else:
+            img = dimg
+
+        def out_bwd(g, H=H, W=W, c=c):
+            # g: [N*HW, 3] fp32 gradient w.r.t. the returned image
+            if post:
+                gd = self._new(N * HW, 3, dtype=F32)
+                call("image_post_bwd", g, dimg, gd, N * HW * 3)
+            else:
+                gd = g
+            da = self._new(N * HW, c)
+            call("conv3x3_cin3", gd, self.pk["decoder.conv_out.wT32"], da, N, H, W, c)
+            return self.gn_bwd(da, x_last, st, "decoder.norm_out", N, HW, c, True)
+
+        tape.append(out_bwd)
+        return img.view(N, H, W, 3), tape
+
+    def backward(self, tape, g, post=True):
+        """g: gradient w.r.t. the image [B, H, W, 3] fp32 -> gradient w.r.t. zq [B*S*S, embed_dim] bf16."""
+        d = g.reshape(-1, 3)
+        for fn in reversed(tape):
+            d = fn(d)
+        return d
+
+    # ---------------------------------------------------------------- VQ (clamp + nearest code), main.py:763,134-138
+    def quantize(self, z_tok, lo, hi):
+        """z_tok: [P, C] fp32 token-major latent.  Returns (zq bf16 [P,C], idx int32 [P], z_clamped fp32)."""
+        P, C = z_tok.shape
+        idx = self._new(P, dtype=torch.int32)
+        zq = self._new(P, C)
+        zc = self._new(P, C, dtype=F32)
+        call("vq_nearest", z_tok, self.codebook, self.codeT, self.cnorm, idx, zq, None, zc, P, C, self.codebook.shape[0],
+             float(lo), float(hi))
+        return zq, idx, zc
+
+
+# -------------------------------------------------------------------------------- reference glue (main.py:105-143)
+class _ClampWithGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lo, hi):
+        ctx.lo, ctx.hi = float(lo), float(hi)
+        ctx.save_for_backward(x)
+        return x.clamp(ctx.lo, ctx.hi)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        gx = torch.empty_like(x, dtype=F32)
+        call("clamp_bwd", g.contiguous().float(), x.contiguous().float(), gx, x.numel(), ctx.lo, ctx.hi)
+        return gx.view_as(x), None, None
+
+
+clamp_with_grad = _ClampWithGrad.apply
+
+
+class _VQFn(torch.autograd.Function):
+    """vector_quantize with the straight-through gradient of ReplaceGrad (main.py:105-116,134-138)."""
+
+    @staticmethod
+    def forward(ctx, x, model):
+        eng = model.engine()
+        shp = x.shape
+        zf = x.reshape(-1, shp[-1]).contiguous().float()
+        P, C = zf.shape
+        idx = torch.empty(P, device=x.device, dtype=torch.int32)
+        zq = torch.empty(P, C, device=x.device, dtype=F32)
+        call("vq_nearest", zf, eng.codebook, eng.codeT, eng.cnorm, idx, None, zq, None, P, C, eng.codebook.shape[0],
+             -3.0e38, 3.0e38)
+        ctx.mark_non_differentiable(idx)
+        return zq.view(shp), idx.view(shp[:-1])
+
+    @staticmethod
+    def backward(ctx, g, _gi):
+        return g, None
+
+
+def vector_quantize(x, model):
+    return _VQFn.apply(x, model)[0]
+
+
+def synth(model, z):
+    z_q = vector_quantize(z.movedim(1, 3), model).movedim(3, 1)
+    return clamp_with_grad(model.decode(z_q).add(1).div(2), 0, 1)

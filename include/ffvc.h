@@ -89,6 +89,94 @@ typedef struct {
 
 int ffvc_gemm(const ffvc_gemm_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm over the last dim (bf16 in/out, fp32 stats).  mlp_mixer_pytorch.py:11,37; cloob.py:170-176.
+ * bwd: dx = LN'(dy) (+ add, the residual-path gradient); dgamma/dbeta (fp32, accumulated) optional.   */
+int ffvc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                       long long rows, int D, float eps, void* stream);
+int ffvc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                       const void* add, void* dx, float* dgamma, float* dbeta, long long rows, int D, void* stream);
+
+/* GroupNorm(G groups, eps) [+ swish] on NHWC bf16 — taming Normalize + nonlinearity.
+ * ws: N*G*2 doubles of scratch.  bwd gives dx only (frozen affine), optionally + add.                 */
+int ffvc_groupnorm_stats(const void* x, double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps,
+                         void* stream);
+int ffvc_groupnorm_apply(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                         void* y, int N, int HW, int C, int G, int swish, void* stream);
+int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                       const float* beta, double* ws, const void* add, void* dx, int N, int HW, int C, int G, int swish,
+                       void* stream);
+
+/* nearest-neighbour 2x upsample, NHWC bf16 (taming Upsample); bwd sums the 2x2 block. */
+int ffvc_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int ffvc_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+
+/* batched transpose in[b][R][Cc] -> out[b][Cc][R] (Rearrange 'b c h w -> b (h w) c', mlp_mixer_pytorch.py:31). */
+int ffvc_transpose(const void* in, void* out, int B, int R, int Cc, int in_fp32, int out_fp32, void* stream);
+
+/* row softmax (fp32 scores -> bf16 probabilities) and its backward, VQGAN AttnBlock. */
+int ffvc_softmax_fwd(const float* s, void* p, long long rows, int n, void* stream);
+int ffvc_softmax_bwd(const void* p, const float* dp, void* ds, long long rows, int n, float scale, void* stream);
+
+/* bias gradients: db[n] += sum_rows dy[row][n];  db[j] += sum_{b,d} dy[b][j][d]. */
+int ffvc_colsum(const void* dy, float* db, long long rows, int n, void* stream);
+int ffvc_rowsum(const void* dy, float* db, int B, int J, int D, void* stream);
+
+int ffvc_cast_f32_bf16(const float* x, void* y, long long n, void* stream);
+int ffvc_cast_bf16_f32(const void* x, float* y, long long n, void* stream);
+int ffvc_add_bf16(const void* a, const void* b, void* y, long long n, void* stream);
+int ffvc_rownorm2(const float* x, float* out, int rows, int C, void* stream);
+int ffvc_sumsq(const float* x, float* out, long long n, void* stream);
+
+/* clamp_with_grad(z, lo, hi) + vector_quantize (main.py:763,134-138), fp32: idx = argmin_c |z - c|^2, zq = codebook[idx].
+ * codeT = codebook transposed [C][ncodes]; cnorm = |code|^2.  zc (optional) = clamped z. */
+int ffvc_vq_nearest(const float* z, const float* codebook, const float* codeT, const float* cnorm, int* idx, void* zq_bf16,
+                    float* zq_f32, float* zc, long long P, int C, int ncodes, float lo, float hi, void* stream);
+/* ClampWithGrad.backward (main.py:126-129). */
+int ffvc_clamp_bwd(const float* g, const float* x, float* gx, long long n, float lo, float hi, void* stream);
+/* xr = clamp_with_grad((d + 1) / 2, 0, 1) and its backward (main.py:142). */
+int ffvc_image_post_fwd(const float* d, float* xr, long long n, void* stream);
+int ffvc_image_post_bwd(const float* g, const float* d, float* gd, long long n, void* stream);
+/* 3x3 conv, Cin = 3 (fp32 NHWC in, [COUT][9][3] fp32 weights, bf16 NHWC out): dgrad of the decoder's conv_out. */
+int ffvc_conv3x3_cin3(const float* x, const float* w, void* y, int N, int H, int W, int COUT, void* stream);
+
+/* fused Adam (torch.optim.Adam semantics, main.py:591,835) over a flat fp32 arena; refreshes the bf16 shadow. */
+/* hyper_dev: DEVICE float[16] = {lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale, weight_decay, t, ...}
+ * (device-resident so a captured CUDA graph sees each step's values).  ffvc_adam_tick increments t and refreshes
+ * the two bias-correction slots on the device. */
+int ffvc_adam_tick(float* hyper_dev, void* stream);
+int ffvc_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, const float* hyper_dev,
+                   void* stream);
+
+/* CLIP ViT multi-head attention for short sequences (T <= 64, head_dim 64); qkv [N][T][3W] bf16 (cloob.py:198-200). */
+int ffvc_mha_small_fwd(const void* qkv, void* out, int N, int T, int heads, int head_dim, float scale, void* stream);
+int ffvc_mha_small_bwd(const void* qkv, const void* dout, void* dqkv, int N, int T, int heads, int head_dim, float scale,
+                       void* stream);
+
+/* CLIP ViT token assembly: x[n][0] = cls + pos[0], x[n][1+p] = pe[n][p] + pos[1+p] (cloob.py:240-243); strided row copy. */
+int ffvc_clip_assemble(const void* pe, const float* cls, const float* pos, void* x, int N, int T, int W, void* stream);
+int ffvc_copy_rows(const void* src, void* dst, long long rows, int D, long long src_stride, long long dst_stride, void* stream);
+
+/* MakeCutouts (main.py:212-229) on NHWC fp32 3-channel images, explicit augmentation parameters. */
+int ffvc_cutout_pool_fwd(const float* x, float* y, int B, int H, int W, int P, void* stream);
+int ffvc_cutout_pool_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int P, void* stream);
+int ffvc_cutout_warp_fwd(const float* in, const float* hinv, float* out, int N, int n_src, int P, int border, void* stream);
+int ffvc_cutout_warp_bwd(const float* dout, const float* hinv, float* din, int N, int n_src, int P, int border, void* stream);
+/* erase: DEVICE int[4] (x0,y0,x1,y1); mean, std (3 floats each) are HOST pointers. patches: [N][(P/patch)^2][3*patch^2] bf16. */
+int ffvc_cutout_final_fwd(const float* cut1, const float* hinv, const float* sat, const float* hue, const float* noise,
+                          const float* facs, const int* erase, const float* mean, const float* std_, void* patches,
+                          float* img_out, int N, int P, int patch, void* stream);
+int ffvc_cutout_final_bwd(const float* cut1, const float* hinv, const float* sat, const float* hue, const int* erase,
+                          const float* mean, const float* std_, const void* dpatches, float* dcut1, int N, int P, int patch,
+                          void* stream);
+
+/* spherical distance loss fwd+bwd (main.py:801-811): loss_out (1 float), dembed fp32 and/or bf16 [N][D]. */
+int ffvc_spherical_loss(const float* embed, const float* target, float* loss_out, float* dembed, void* dembed_bf16, int N,
+                        int B, int D, float coef, void* stream);
+
+/* sizeof() of the ABI structs, for binding self-checks. */
+int ffvc_sizeof(const char* name);
+
 #ifdef __cplusplus
 }
 #endif

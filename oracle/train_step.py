@@ -1,0 +1,40 @@
+"""ORACLE (test infrastructure, not product): the reference's train-step body (main.py:729-837) restated on the
+CPU in fp32 from the oracle pieces — mapper (oracle/mixer.py) -> clamp_with_grad -> synth (oracle/vqgan.py) ->
+MakeCutouts + normalise (oracle/cutouts.py) -> encode_image (oracle/clip_vit.py) -> spherical loss (oracle/loss.py)
+-> backward -> Adam on the mapper parameters only (main.py:591).
+Used by tests/ (parity of the CUDA step) and by bench.py's cpu_baseline / --impl reference legs (timing of the
+reference's CPU path).  Never imported by the product package."""
+import torch
+
+from . import clip_vit as oclip
+from . import cutouts as ocut
+from . import loss as oloss
+from . import mixer as omix
+from . import vqgan as ovq
+
+
+class OracleTrainer:
+    def __init__(self, sd_mixer, sd_vq, sd_clip, image_size, channels, vq_cfg=ovq.F16_16384, clip_cfg=oclip.VIT_B32,
+                 cutn=8, cut_size=224, lr=1e-3, act="quick_gelu"):
+        self.params = {k: v.clone().requires_grad_(True) for k, v in sd_mixer.items()}
+        self.sd_vq, self.sd_clip = sd_vq, sd_clip
+        self.S, self.C = image_size, channels
+        self.vq_cfg, self.clip_cfg, self.cutn, self.cut_size, self.act = vq_cfg, clip_cfg, cutn, cut_size, act
+        self.opt = torch.optim.Adam(list(self.params.values()), lr=lr)       # main.py:591
+        cb = sd_vq["quantize.embedding.weight"]
+        self.z_lo, self.z_hi = float(cb.min()), float(cb.max())              # main.py:645-646,763
+        self.last_indices = None
+
+    def step(self, inp_feats, out_feats, prm):
+        z = omix.mixer_forward(self.params, inp_feats, self.S, self.C).contiguous()          # main.py:754-757
+        z = ovq.clamp_with_grad(z, self.z_lo, self.z_hi)                                     # main.py:763
+        xr, idx = ovq.synth(self.sd_vq, z, self.vq_cfg, return_indices=True)                 # main.py:767
+        self.last_indices = idx
+        x = ocut.make_cutouts(xr, self.cutn, prm, self.cut_size, normalize=True)             # main.py:796-797
+        embed = oclip.encode_image(self.sd_clip, x, self.clip_cfg, act=self.act).float()     # main.py:799
+        loss = oloss.spherical_dist_loss(embed, out_feats, self.cutn)                        # main.py:801-811
+        self.opt.zero_grad()                                                                 # main.py:825
+        loss.backward()                                                                      # main.py:832
+        self.grads = {k: p.grad.clone() for k, p in self.params.items()}
+        self.opt.step()                                                                      # main.py:835
+        return loss.item()

@@ -1,0 +1,266 @@
+"""Per-kernel parity of the HBM-bound ops (through the C ABI) against plain PyTorch fp32 on the same inputs.
+bf16 tensors are compared against fp32 math on the bf16-rounded inputs; tolerance 2e-2 of the reference's max
+magnitude unless stated (bf16 has 8 mantissa bits: one rounding of the output is 4e-3 relative)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from feed_forward_vqgan_clip_b200 import ops
+from feed_forward_vqgan_clip_b200.ops import call
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF, F32 = torch.bfloat16, torch.float32
+
+
+def rnd(*shape, seed=0, dtype=BF, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+def close(out, ref, tol=2e-2):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, "max err %g vs scale %g" % (err, scale)
+
+
+@pytest.mark.parametrize("rows,D", [(1000, 1024), (77, 768), (4096, 128)])
+def test_layernorm_fwd_bwd(rows, D):
+    x, dy = rnd(rows, D, seed=1), rnd(rows, D, seed=2)
+    add = rnd(rows, D, seed=3)
+    gamma = 1 + 0.1 * torch.randn(D, device=DEV)
+    beta = 0.1 * torch.randn(D, device=DEV)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    call("layernorm_fwd", x, gamma, beta, y, mean, rstd, rows, D, 1e-5)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (D,), gr, br, 1e-5)
+    close(y, yr)
+    yr.backward(dy.float())
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    call("layernorm_bwd", dy, x, gamma, mean, rstd, add, dx, dg, db, rows, D)
+    close(dx, xr.grad + add.float())
+    close(dg, gr.grad, 1e-2)
+    close(db, br.grad, 1e-2)
+    dx2 = torch.empty_like(x)
+    call("layernorm_bwd", dy, x, gamma, mean, rstd, None, dx2, None, None, rows, D)
+    close(dx2, xr.grad)
+
+
+@pytest.mark.parametrize("N,HW,C,swish", [(2, 256, 512, 1), (3, 1024, 128, 1), (1, 4096, 64, 0), (2, 16384, 128, 1)])
+def test_groupnorm_fwd_bwd(N, HW, C, swish):
+    x, dy, add = rnd(N, HW, C, seed=1), rnd(N, HW, C, seed=2), rnd(N, HW, C, seed=3)
+    gamma = 1 + 0.1 * torch.randn(C, device=DEV)
+    beta = 0.1 * torch.randn(C, device=DEV)
+    ws = torch.empty(N * 64, device=DEV, dtype=torch.float64)
+    mean, rstd = torch.empty(N * 32, device=DEV), torch.empty(N * 32, device=DEV)
+    call("groupnorm_stats", x, ws, mean, rstd, N, HW, C, 32, 1e-6)
+    y = torch.empty_like(x)
+    call("groupnorm_apply", x, mean, rstd, gamma, beta, y, N, HW, C, 32, swish)
+    xr = x.float().permute(0, 2, 1).contiguous().requires_grad_(True)       # (N, C, HW)
+    u = F.group_norm(xr, 32, gamma, beta, eps=1e-6)
+    yr = u * torch.sigmoid(u) if swish else u
+    close(y, yr.permute(0, 2, 1))
+    yr.backward(dy.float().permute(0, 2, 1))
+    dx = torch.empty_like(x)
+    call("groupnorm_bwd", dy, x, mean, rstd, gamma, beta, ws, add, dx, N, HW, C, 32, swish)
+    close(dx, xr.grad.permute(0, 2, 1) + add.float())
+
+
+def test_upsample_and_transpose():
+    x = rnd(2, 8, 8, 64, seed=1)
+    y = torch.empty(2, 16, 16, 64, device=DEV, dtype=BF)
+    call("upsample2x_fwd", x, y, 2, 8, 8, 64)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    close(y, ref, 1e-6)
+    dy = rnd(2, 16, 16, 64, seed=2)
+    dx = torch.empty_like(x)
+    call("upsample2x_bwd", dy, dx, 2, 8, 8, 64)
+    close(dx, dy.float().view(2, 8, 2, 8, 2, 64).sum(dim=(2, 4)))
+    a = rnd(3, 50, 70, seed=3)
+    b = torch.empty(3, 70, 50, device=DEV, dtype=BF)
+    call("transpose", a, b, 3, 50, 70, 0, 0)
+    assert torch.equal(b, a.transpose(1, 2).contiguous())
+    c = torch.empty(3, 70, 50, device=DEV, dtype=F32)
+    call("transpose", a.float(), c, 3, 50, 70, 1, 1)
+    assert torch.equal(c, a.float().transpose(1, 2).contiguous())
+
+
+def test_softmax_fwd_bwd():
+    rows, n = 512, 256
+    s = rnd(rows, n, seed=1, dtype=F32, scale=3.0)
+    p = torch.empty(rows, n, device=DEV, dtype=BF)
+    call("softmax_fwd", s, p, rows, n)
+    close(p, torch.softmax(s, -1))
+    dp = rnd(rows, n, seed=2, dtype=F32)
+    ds = torch.empty(rows, n, device=DEV, dtype=BF)
+    call("softmax_bwd", p, dp, ds, rows, n, 0.5)
+    pf = p.float()
+    close(ds, 0.5 * pf * (dp - (pf * dp).sum(-1, keepdim=True)))
+
+
+def test_bias_grads_and_casts():
+    dy = rnd(3000, 520, seed=1)
+    db = torch.zeros(520, device=DEV)
+    call("colsum", dy, db, 3000, 520)
+    close(db, dy.float().sum(0), 1e-3)
+    d3 = rnd(4, 96, 128, seed=2)
+    dj = torch.zeros(96, device=DEV)
+    call("rowsum", d3, dj, 4, 96, 128)
+    close(dj, d3.float().sum(dim=(0, 2)), 1e-3)
+    x = rnd(1000, seed=3, dtype=F32)
+    y = torch.empty(1000, device=DEV, dtype=BF)
+    call("cast_f32_bf16", x, y, 1000)
+    assert torch.equal(y, x.to(BF))
+    z = torch.empty(1000, device=DEV, dtype=F32)
+    call("cast_bf16_f32", y, z, 1000)
+    assert torch.equal(z, y.float())
+
+
+@pytest.mark.parametrize("C,ncodes,P", [(256, 16384, 512), (64, 512, 300)])
+def test_vq_nearest_matches_reference_argmin(C, ncodes, P):
+    g = torch.Generator().manual_seed(0)
+    cb = torch.randn(ncodes, C, generator=g).to(DEV)
+    z = (torch.randn(P, C, generator=g) * 1.5).to(DEV)
+    lo, hi = float(cb.min()), float(cb.max())
+    cbT = cb.t().contiguous()
+    cn = torch.empty(ncodes, device=DEV)
+    call("rownorm2", cb, cn, ncodes, C)
+    idx = torch.empty(P, device=DEV, dtype=torch.int32)
+    zq = torch.empty(P, C, device=DEV, dtype=BF)
+    zq32 = torch.empty(P, C, device=DEV, dtype=F32)
+    zc = torch.empty(P, C, device=DEV, dtype=F32)
+    call("vq_nearest", z, cb, cbT, cn, idx, zq, zq32, zc, P, C, ncodes, lo, hi)
+    zcl = z.clamp(lo, hi)
+    assert torch.equal(zc, zcl)
+    # the reference expression (main.py:135-136), evaluated in float64 to be the arbiter of near ties
+    d = (zcl.double().pow(2).sum(-1, keepdim=True) + cb.double().pow(2).sum(1) - 2 * zcl.double() @ cb.double().T)
+    ref = d.argmin(-1)
+    agree = (idx.long() == ref).float().mean().item()
+    assert agree >= 0.999, agree
+    # where they differ the chosen code must be a numerical tie
+    bad = (idx.long() != ref).nonzero().flatten()
+    for r in bad.tolist():
+        assert abs(d[r, idx[r]].item() - d[r, ref[r]].item()) < 1e-3
+    assert torch.equal(zq32, cb[idx.long()])
+    assert torch.equal(zq, cb[idx.long()].to(BF))
+
+
+def test_clamp_bwd_truth_table():
+    # SURVEY §8 a4 [probe]: x=-1,g=+1 -> 0; x=2,g=+1 -> 1 (passes); g=-1 passes at x=-1, blocked at x=2; inside passes
+    x = torch.tensor([-1.0, 2.0, -1.0, 2.0, 0.5, 0.5], device=DEV)
+    g = torch.tensor([1.0, 1.0, -1.0, -1.0, 1.0, -1.0], device=DEV)
+    gx = torch.empty_like(x)
+    call("clamp_bwd", g, x, gx, 6, 0.0, 1.0)
+    assert gx.tolist() == [0.0, 1.0, -1.0, 0.0, 1.0, -1.0]
+
+
+def test_image_post_and_conv_cin3():
+    d = rnd(4096, 3, seed=1, dtype=F32, scale=1.5)
+    xr = torch.empty_like(d)
+    call("image_post_fwd", d, xr, d.numel())
+    assert torch.allclose(xr, ((d + 1) / 2).clamp(0, 1))
+    g = rnd(4096, 3, seed=2, dtype=F32)
+    gd = torch.empty_like(d)
+    call("image_post_bwd", g, d, gd, d.numel())
+    u = (d + 1) / 2
+    ref = torch.where(g * (u - u.clamp(0, 1)) >= 0, 0.5 * g, torch.zeros_like(g))
+    assert torch.allclose(gd, ref)
+    # dgrad of a 128 -> 3 conv == conv of the 3-channel gradient with flipped, transposed filters
+    N, H, W, CO = 2, 32, 32, 128
+    w = rnd(3, CO, 3, 3, seed=3, dtype=F32, scale=0.1)        # forward conv_out weight [3][128][3][3]
+    gy = rnd(N, H, W, 3, seed=4, dtype=F32)
+    wT = w.flip(2, 3).permute(1, 2, 3, 0).reshape(CO, 27).contiguous()
+    out = torch.empty(N, H, W, CO, device=DEV, dtype=BF)
+    call("conv3x3_cin3", gy, wT, out, N, H, W, CO)
+    ref = F.conv_transpose2d(gy.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+    close(out, ref)
+
+
+def test_adam_matches_torch():
+    n = 10007
+    p0 = rnd(n, seed=1, dtype=F32)
+    p = p0.clone()
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    shadow = torch.empty(n, device=DEV, dtype=BF)
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 1, 1, 0.5, 0, 0, 0, 0, 0, 0, 0, 0, 0], device=DEV, dtype=F32)
+    for step in range(1, 4):
+        g = rnd(n, seed=10 + step, dtype=F32)
+        ref.grad = 0.5 * g
+        opt.step()
+        call("adam_tick", hyper)
+        call("adam_step", p, g, m, v, shadow, n, hyper)
+        assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.equal(shadow, p.to(BF))
+
+
+def test_mha_small_fwd_bwd():
+    N, T, Hh, dh = 6, 50, 12, 64
+    W = Hh * dh
+    qkv = rnd(N, T, 3 * W, seed=1, scale=0.7)
+    out = torch.empty(N, T, W, device=DEV, dtype=BF)
+    call("mha_small_fwd", qkv, out, N, T, Hh, dh, dh ** -0.5)
+    x = qkv.float().requires_grad_(True)
+    q, k, v = x.split(W, dim=-1)
+    q = q.reshape(N, T, Hh, dh).transpose(1, 2)
+    k = k.reshape(N, T, Hh, dh).transpose(1, 2)
+    v = v.reshape(N, T, Hh, dh).transpose(1, 2)
+    a = torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1)
+    o = (a @ v).transpose(1, 2).reshape(N, T, W)
+    close(out, o)
+    do = rnd(N, T, W, seed=2)
+    o.backward(do.float())
+    dqkv = torch.empty_like(qkv)
+    call("mha_small_bwd", qkv, do, dqkv, N, T, Hh, dh, dh ** -0.5)
+    close(dqkv, x.grad)
+
+
+def test_spherical_loss():
+    import oracle.loss as ol
+    N, B, D = 24, 3, 512
+    emb = rnd(N, D, seed=1, dtype=F32)
+    tgt = rnd(B, D, seed=2, dtype=F32, scale=0.45)
+    loss = torch.zeros(1, device=DEV)
+    demb = torch.empty(N, D, device=DEV)
+    call("spherical_loss", emb, tgt, loss, demb, None, N, B, D, 1.0)
+    e = emb.cpu().requires_grad_(True)
+    ref = ol.spherical_dist_loss(e, tgt.cpu(), N // B)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    close(demb.cpu(), e.grad, 1e-3)
+
+
+def test_cutouts_fwd_bwd_vs_oracle():
+    import oracle.cutouts as oc
+    from feed_forward_vqgan_clip_b200.cutouts import CutoutEngine, sample_params, params_to_device
+    B, H, cutn, P = 2, 256, 4, 224
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(B, 3, H, H, generator=g)
+    prm = sample_params(cutn * B, P, g)
+    # make sure every augmentation is exercised at least once
+    assert (prm["affine_inv"] != torch.eye(3)).any() and (prm["persp_inv"] != torch.eye(3)).any()
+    xr = x.clone().requires_grad_(True)
+    ref = oc.make_cutouts(xr, cutn, prm, P, normalize=True)
+    eng = CutoutEngine(P, cutn, 32, torch.device(DEV))
+    img = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    patches, saved, out = eng.forward(img, params_to_device(prm, DEV), want_image=True)
+    # a handful of pixels sit exactly on a hue-sector / floor boundary and may flip: compare robustly
+    diff = (out.cpu() - ref.detach()).abs()
+    assert (diff > 2e-3).float().mean().item() < 1e-4, diff.max()
+    N = cutn * B
+    pm = patches.float().cpu().view(N, 7, 7, 3, 32, 32).permute(0, 3, 1, 4, 2, 5).reshape(N, 3, P, P)
+    assert (pm - ref.detach()).abs().max().item() < 0.05      # bf16 rounding of values up to ~3
+    gy = torch.randn(N, 3, P, P, generator=g)
+    ref.backward(gy)
+    dp = gy.view(N, 3, 7, 32, 7, 32).permute(0, 2, 4, 1, 3, 5).reshape(N, 49, 3072).contiguous().to(DEV).to(BF)
+    dimg = eng.backward(saved, dp).cpu().permute(0, 3, 1, 2)
+    err = (dimg - xr.grad).abs()
+    scale = xr.grad.abs().max().item()
+    assert (err > 3e-2 * scale).float().mean().item() < 1e-3, (err.max().item(), scale)
