@@ -1,0 +1,87 @@
+"""The reference's Python call surface for the train-step path, backed by the B200 engines.
+
+    build_model(config)                      main.py:448-502   (model_type mlp_mixer; others raise -> SURVEY §8f next)
+    load_vqgan_model(config_path, ckpt)      main.py:84-103
+    load_clip_model(name, path)              main.py:1308-1333 (OpenAI ViT-B/32 and OpenCLIP ViT-B-32 architectures)
+    MakeCutouts / synth / clamp_with_grad / vector_quantize      main.py:105-229
+    train_step(net, vq, perceptor, ...)      the body of main.py:729-837 as one fused object (TrainStep)
+
+`config` may be any mapping / attribute object with the keys of configs/example.yaml (an OmegaConf DictConfig or a
+plain dict both work); unknown keys are ignored, optional keys defaulted exactly like main.py:450-457,466,496-498.
+"""
+import os
+
+import torch
+
+from .clip_vit import CLIP, VIT_B32
+from .cutouts import MakeCutouts, sample_params  # noqa: F401
+from .mixer import Mixer
+from .train_step import FusedAdam, TrainStep  # noqa: F401
+from .vqgan import F16_16384, VQModel, clamp_with_grad, synth, vector_quantize  # noqa: F401
+
+CLIP_SIZE = {"ViT-B/32": 224, "ViT-B-32": 224, "ViT-B-32-quickgelu": 224}       # main.py:53-66 (ViT-B/32 family)
+CLIP_DIM = {"ViT-B/32": 512, "ViT-B-32": 512, "ViT-B-32-quickgelu": 512}        # main.py:67-80
+
+
+def _get(cfg, key, default=None):
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    if hasattr(cfg, "get"):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+def load_config(path):
+    """YAML -> dict (stands in for OmegaConf.load, main.py:506; omegaconf is not a dependency here)."""
+    import yaml
+    with open(path) as f:
+        return yaml.safe_load(f)
+
+
+def build_model(config, vq_channels=256):
+    clip_model = _get(config, "clip_model", "ViT-B/32")
+    clip_dim = _get(config, "clip_dim", CLIP_DIM.get(clip_model.split(":")[-1] if ":" in clip_model else clip_model, 512))
+    vq_image_size = _get(config, "vq_image_size", 16)
+    noise_dim = _get(config, "noise_dim", 0) or 0
+    model_type = _get(config, "model_type", "mlp_mixer")
+    if model_type == "mlp_mixer":
+        return Mixer(input_dim=clip_dim + noise_dim, image_size=vq_image_size, channels=vq_channels, patch_size=1,
+                     dim=_get(config, "dim"), depth=_get(config, "depth"), dropout=_get(config, "dropout", 0))
+    raise NotImplementedError("model_type %r: vitgan / simple_vitgan / xtransformer mappers are SURVEY §8 rows a2/a3 "
+                              "(scheduled after the Mixer path)" % model_type)
+
+
+def load_vqgan_model(config_path=None, checkpoint_path=None):
+    """VQModel branch of main.py:84-103 (the only branch BASELINE's configs use).  The architecture of
+    vqgan_imagenet_f16_16384.yaml is built in; the checkpoint is optional (random init without it)."""
+    model = VQModel(F16_16384)
+    model.eval().requires_grad_(False)
+    if checkpoint_path and os.path.exists(checkpoint_path):
+        model.init_from_ckpt(checkpoint_path)
+    return model
+
+
+def load_clip_model(model_type="ViT-B/32", path=None):
+    if model_type.startswith("open_clip:"):
+        arch = model_type.split(":")[1]
+        act = "quick_gelu" if "quickgelu" in arch else "gelu"       # OpenCLIP ViT-B-32 = exact GELU
+        if not arch.startswith("ViT-B-32"):
+            raise NotImplementedError(arch)
+    elif model_type == "ViT-B/32":
+        act = "quick_gelu"
+    else:
+        raise NotImplementedError("perceptor %r (only the ViT-B/32 family is on the benchmark path)" % model_type)
+    model = CLIP(VIT_B32, act=act)
+    if path and os.path.exists(path):
+        sd = torch.load(path, map_location="cpu")
+        sd = sd.get("state_dict", sd)
+        vis = {k[len("visual."):]: v.float() for k, v in sd.items() if k.startswith("visual.")}
+        model.visual.load_state_dict(vis)
+    return model.eval().requires_grad_(False)
+
+
+def train_step(net, vq, perceptor, config=None, **kw):
+    """Build the fused step object for `net` (Mixer), `vq` (VQModel) and `perceptor` (CLIP), all on the same GPU."""
+    cfg = config or {}
+    return TrainStep(net, vq, perceptor, cutn=_get(cfg, "cutn", 8), lr=_get(cfg, "lr", 1e-3),
+                     target_loss_coef=_get(cfg, "target_loss_coef", 1.0), **kw)

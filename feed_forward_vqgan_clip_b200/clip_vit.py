@@ -140,6 +140,47 @@ class ClipEngine:
         call("layernorm_bwd", dy, x, self.sd32[name + ".weight"], st[0], st[1], add, dx, None, None, rows, self.W)
         return dx
 
+    # ---- multi-head attention on the tensor cores: per (sequence, head) GEMMs batched through 4-D tensor maps
+    # (inner batch = head: 64-element column slice of the fused qkv rows; outer batch = sequence), T padded to 64.
+    TP = 64
+
+    def _attn_fwd(self, qkv, N):
+        W, T, Hh, TP = self.W, self.T, self.Hh, self.TP
+        S = self._new(N, Hh, T, TP, dtype=F32)
+        ops.gemm(qkv, qkv, S, T, T, 64, a_ld=3 * W, b_ld=3 * W, b_off=W, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT,
+                 batch=N * Hh, batch_inner=Hh, a_bs=T * 3 * W, b_bs=T * 3 * W, a_bs_in=64, b_bs_in=64, ldc=TP,
+                 out_bs=Hh * T * TP, out_bs_in=T * TP, alpha=0.125, block_n=64)
+        P = self._new(N, Hh, T, TP)
+        call("softmax_fwd", S, P, N * Hh * T, T, TP)
+        a = self._new(N * T, W)
+        # O[n,i,h,:] = sum_j P[n,h,i,j] V[n,j,h,:]
+        ops.gemm(P, qkv, a, T, 64, T, a_ld=TP, b_mode=ops.MNMAJOR, b_ld=3 * W, b_off=2 * W, a_role=ops.ROLE_OUT,
+                 b_role=ops.ROLE_OUT, batch=N * Hh, batch_inner=Hh, a_bs=Hh * T * TP, a_bs_in=T * TP, b_bs=T * 3 * W,
+                 b_bs_in=64, ldc=W, out_bs=T * W, out_bs_in=64, block_n=64)
+        return a, P
+
+    def _attn_bwd(self, qkv, P, da, N):
+        W, T, Hh, TP = self.W, self.T, self.Hh, self.TP
+        kw = dict(batch=N * Hh, batch_inner=Hh, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT, block_n=64)
+        dP = self._new(N, Hh, T, TP, dtype=F32)            # dP[i,j] = sum_d dO[i,d] V[j,d]
+        ops.gemm(da, qkv, dP, T, T, 64, a_ld=W, b_ld=3 * W, b_off=2 * W, a_bs=T * W, a_bs_in=64, b_bs=T * 3 * W, b_bs_in=64,
+                 ldc=TP, out_bs=Hh * T * TP, out_bs_in=T * TP, **kw)
+        dS = self._new(N, Hh, T, TP)
+        call("softmax_bwd", P, dP, dS, N * Hh * T, T, TP, 0.125)
+        del dP
+        dqkv = self._new(N * T, 3 * W)
+        ob = dict(ldc=3 * W, out_bs=T * 3 * W, out_bs_in=64)
+        # dV[j,d] = sum_i P[i,j] dO[i,d]
+        ops.gemm(P, da, dqkv, T, 64, T, a_mode=ops.MNMAJOR, a_ld=TP, b_mode=ops.MNMAJOR, b_ld=W, a_bs=Hh * T * TP,
+                 a_bs_in=T * TP, b_bs=T * W, b_bs_in=64, out_off=2 * W, **ob, **kw)
+        # dQ[i,d] = sum_j dS[i,j] K[j,d]
+        ops.gemm(dS, qkv, dqkv, T, 64, T, a_ld=TP, b_mode=ops.MNMAJOR, b_ld=3 * W, b_off=W, a_bs=Hh * T * TP, a_bs_in=T * TP,
+                 b_bs=T * 3 * W, b_bs_in=64, out_off=0, **ob, **kw)
+        # dK[j,d] = sum_i dS[i,j] Q[i,d]
+        ops.gemm(dS, qkv, dqkv, T, 64, T, a_mode=ops.MNMAJOR, a_ld=TP, b_mode=ops.MNMAJOR, b_ld=3 * W, b_off=0,
+                 a_bs=Hh * T * TP, a_bs_in=T * TP, b_bs=T * 3 * W, b_bs_in=64, out_off=W, **ob, **kw)
+        return dqkv
+
     def forward(self, patches):
         """patches: [N][G*G][3*patch*patch] bf16 -> (embed [N][E] fp32, saved)."""
         N = patches.shape[0]
@@ -159,8 +200,7 @@ class ClipEngine:
             qkv = self._new(M, 3 * W)
             ops.gemm(n1, self.w[p + "in"], qkv, M, 3 * W, W, bias=self.sd32[p + "attn.in_proj_bias"])
             del n1
-            a = self._new(M, W)
-            call("mha_small_fwd", qkv, a, N, T, Hh, 64, 0.125)
+            a, P = self._attn_fwd(qkv, N)
             h2 = self._new(M, W)
             ops.gemm(a, self.w[p + "out"], h2, M, W, W, bias=self.sd32[p + "attn.out_proj.bias"], res=h)
             del a
@@ -171,7 +211,7 @@ class ClipEngine:
             h3 = self._new(M, W)
             ops.gemm(gact, self.w[p + "pj"], h3, M, W, 4 * W, bias=self.sd32[p + "mlp.c_proj.bias"], res=h2)
             del gact
-            saved["layers"].append(dict(h=h, st1=st1, qkv=qkv, h2=h2, st2=st2, u=u))
+            saved["layers"].append(dict(h=h, st1=st1, qkv=qkv, P=P, h2=h2, st2=st2, u=u))
             h = h3
         xc = self._new(N, W)
         call("copy_rows", h, xc, N, W, T * W, W)                     # class-token rows
@@ -205,8 +245,7 @@ class ClipEngine:
             dh2 = self._ln_bwd(dn2, lv["h2"], lv["st2"], p + "ln_2", M, add=dh)
             da = self._new(M, W)
             ops.linear_dgrad(dh2, self.w[p + "out"], da, M, W, W)
-            dqkv = self._new(M, 3 * W)
-            call("mha_small_bwd", lv["qkv"], da, dqkv, N, T, Hh, 64, 0.125)
+            dqkv = self._attn_bwd(lv["qkv"], lv["P"], da, N)
             dn1 = self._new(M, W)
             ops.linear_dgrad(dqkv, self.w[p + "in"], dn1, M, 3 * W, W)
             del dqkv

@@ -86,13 +86,14 @@ __global__ void transpose_kernel(const Tin* __restrict__ in, Tout* __restrict__ 
   }
 }
 
-// ---------------------------------------------------------------- row softmax (VQGAN AttnBlock, fp32 scores -> bf16 probs)
+// ---------------------------------------------------------------- row softmax (attention: fp32 scores -> bf16 probs)
+// rows are `ld` elements apart, the first n are valid; the padding [n, ld) of the output is zero-filled.
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p,
-                                                          long long rows, int n) {
+                                                          long long rows, int n, int ld) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
-  const float* sr = s + row * n;
+  const float* sr = s + row * ld;
   float mx = -FLT_MAX;
   for (int i = lane; i < n; i += 32) mx = fmaxf(mx, sr[i]);
   mx = warp_max(mx);
@@ -100,19 +101,20 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
   for (int i = lane; i < n; i += 32) sum += __expf(sr[i] - mx);
   sum = warp_sum(sum);
   const float inv = 1.0f / sum;
-  for (int i = lane; i < n; i += 32) p[row * n + i] = __float2bfloat16(__expf(sr[i] - mx) * inv);
+  for (int i = lane; i < ld; i += 32) p[row * ld + i] = __float2bfloat16(i < n ? __expf(sr[i] - mx) * inv : 0.f);
 }
 // ds = p * (dp - sum(p*dp)) * scale   (dp fp32 from the dO.V^T GEMM; ds bf16 feeds the dQ/dK GEMMs)
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ p, const float* __restrict__ dp,
-                                                          __nv_bfloat16* __restrict__ ds, long long rows, int n, float scale) {
+                                                          __nv_bfloat16* __restrict__ ds, long long rows, int n, int ld,
+                                                          float scale) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
   float dot = 0.f;
-  for (int i = lane; i < n; i += 32) dot += __bfloat162float(p[row * n + i]) * dp[row * n + i];
+  for (int i = lane; i < n; i += 32) dot += __bfloat162float(p[row * ld + i]) * dp[row * ld + i];
   dot = warp_sum(dot);
-  for (int i = lane; i < n; i += 32)
-    ds[row * n + i] = __float2bfloat16(__bfloat162float(p[row * n + i]) * (dp[row * n + i] - dot) * scale);
+  for (int i = lane; i < ld; i += 32)
+    ds[row * ld + i] = __float2bfloat16(i < n ? __bfloat162float(p[row * ld + i]) * (dp[row * ld + i] - dot) * scale : 0.f);
 }
 
 // ---------------------------------------------------------------- bias gradients
@@ -457,13 +459,16 @@ extern "C" int ffvc_transpose(const void* in, void* out, int B, int R, int Cc, i
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
-extern "C" int ffvc_softmax_fwd(const float* s, void* p, long long rows, int n, void* stream) {
-  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(s, BF(p), rows, n);
+extern "C" int ffvc_softmax_fwd(const float* s, void* p, long long rows, int n, int ld, void* stream) {
+  if (ld < n) return set_error(FFVC_ERR_ARG, "softmax: ld < n");
+  softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(s, BF(p), rows, n, ld);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
-extern "C" int ffvc_softmax_bwd(const void* p, const float* dp, void* ds, long long rows, int n, float scale, void* stream) {
-  softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(CBF(p), dp, BF(ds), rows, n, scale);
+extern "C" int ffvc_softmax_bwd(const void* p, const float* dp, void* ds, long long rows, int n, int ld, float scale,
+                                void* stream) {
+  if (ld < n) return set_error(FFVC_ERR_ARG, "softmax: ld < n");
+  softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(CBF(p), dp, BF(ds), rows, n, ld, scale);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

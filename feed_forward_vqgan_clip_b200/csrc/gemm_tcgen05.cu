@@ -2,18 +2,22 @@
 //
 //   D[b][m][n] (+)= alpha * sum_k A[m][k] * B[n][k]      (bf16 operands, fp32 accumulate in TMEM)
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor -> 4-stage smem ring, 128B swizzle)
-//   warp 1      : MMA issuer    (one thread issues tcgen05.mma, M=128, N=BLOCK_N, K=16 x 4 per stage)
-//   warps 2..5  : epilogue      (tcgen05.ld 32x32b -> registers -> bias/activation/residual -> global)
-// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the
-// main loop of tile i+1.
+//   warp 1      : MMA issuer    (one thread issues tcgen05.mma M=128, N=BLOCK_N, K=16; 4 (x2) per stage)
+//   warps 2..9  : epilogue      (tcgen05.ld 32x32b -> registers -> bias/activation/residual -> global); two warps per
+//                 TMEM lane quarter so the fused epilogue math never paces the tensor pipe
+// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the main loop of
+// tile i+1.  Two tile shapes: 128 x {32..256} (one MMA per k-step) and 256 x {32..128} (two MMAs sharing the B
+// tile: for N <= 128 the 128-row tile is shared-memory-bandwidth bound, the 256-row tile halves B traffic per FLOP).
 //
 // Operand modes (runtime, resolved by the producer / descriptor builder only):
 //   K-major   : operand stored [rows][K] with K contiguous        (fwd Linear:  X[M,K], W[N,K])
 //   MN-major  : operand stored [K][rows] with rows contiguous     (dgrad: W as B; wgrad: dY, X)
 //   CONV3X3   : A is an NHWC image; the 9 taps x Cin/64 channel chunks form the K loop, each
 //               A tile is one 4-D TMA box (zero fill outside the image = padding 1)
+// Batching: output batch index b = (b_outer, b_inner); operands are 4-D tensor maps (inner, rows, b_inner, b_outer)
+// so attention heads ([N][T][heads*64] slices) and per-sample token-mixing are plain strides.
 // Replaces, on the reference's path, every nn.Linear / Conv1d(k=1) of the mappers
 // (mlp_mixer_pytorch.py:16-23,32; vitgan.py:31-33,64-67), taming's Conv2d 3x3 / 1x1 in the VQGAN decoder
 // (call site main.py:142), and the CLIP ViT linears (cloob.py:188-196,224,249).
@@ -29,26 +33,27 @@
 
 namespace ffvc {
 
-static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;
 static constexpr int kStages = 4;
-static constexpr int kStageABytes = kBlockM * kBlockK * 2;  // 16 KB
-static constexpr int kStageBBytes = 256 * kBlockK * 2;      // 32 KB (max BLOCK_N)
-static constexpr int kStageBytes = kStageABytes + kStageBBytes;
+static constexpr int kStageABytes = 256 * kBlockK * 2;      // up to 256 rows of A  (32 KB)
+static constexpr int kStageBytes = 48 * 1024;               // A (16|32 KB) + B (32|16 KB)
 static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-static constexpr int kNumThreads = 192;
+static constexpr int kNumThreads = 320;
+static constexpr int kNumEpiWarps = 8;
 static constexpr int kTmemCols = 512;
 
 struct GemmDev {
   int M, N;
-  int batch;            // output batches
-  int block_n;          // 32 / 64 / 128 / 256
+  int batch;            // output batches (outer * inner)
+  int batch_inner;      // inner batch count (>= 1)
+  int tile_m;           // 128 or 256
+  int block_n;          // 32 / 64 / 128 / 256 (<= 128 when tile_m == 256)
   int a_mode, b_mode;   // FFVC_OP_*
   int kb_per_seg;       // ceil(K / 64)
-  int k_segs;           // contraction additionally runs over this many "segments" (dim2 of the maps)
-  int a_c2_out, a_c2_seg, b_c2_out, b_c2_seg;  // dim2 coordinate = out_batch*x_out + seg*x_seg
+  int k_segs;           // contraction additionally runs over this many "segments" (dim3 of the maps)
+  int a_role, b_role;   // FFVC_ROLE_*
   int splits;           // split-K factor (atomic fp32 accumulation)
-  int conv_h, conv_w, conv_cblocks, conv_tile_w, conv_dil;
+  int conv_h, conv_w, conv_cblocks;
   // epilogue
   void* out;
   void* pre_out;
@@ -56,7 +61,8 @@ struct GemmDev {
   const __nv_bfloat16* res;
   const float* bias;
   long long ldc;
-  long long out_bs;
+  long long out_bs;        // outer batch stride
+  long long out_bs_inner;  // inner batch stride
   int out_fp32;
   int atomic;
   int bias_mode;  // 0 none, 1 per column, 2 per row
@@ -76,6 +82,117 @@ __device__ __forceinline__ float apply_act_grad(float x, int act) {
   if (act == FFVC_ACT_QUICKGELU) return quick_gelu_grad_f(x);
   if (act == FFVC_ACT_SWISH) return swish_grad_f(x);
   return 1.0f;
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
+  uint4 pk;
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]);
+  __nv_bfloat162 h3 = __floats2bfloat162_rn(v[6], v[7]);
+  pk.x = *reinterpret_cast<uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  pk.z = *reinterpret_cast<uint32_t*>(&h2);
+  pk.w = *reinterpret_cast<uint32_t*>(&h3);
+  return pk;
+}
+
+// fused epilogue on 32 consecutive columns of one output row
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[32], int gn0, long long off, float rbias,
+                                               bool vec_ok) {
+  const int ncols = min(32, p.N - gn0);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  if (p.bias_mode == 1) {
+    if (ncols == 32) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(p.bias + gn0 + i);
+        v[i] += b4.x;
+        v[i + 1] += b4.y;
+        v[i + 2] += b4.z;
+        v[i + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) v[i] += p.bias[gn0 + i];
+    }
+  } else if (p.bias_mode == 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += rbias;
+  }
+  const bool full_vec = vec_ok && (ncols == 32);
+  if (p.pre_out != nullptr) {
+    __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(p.pre_out) + off;
+    if (full_vec) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(po + i) = pack_bf16x8(v + i);
+    } else {
+      for (int i = 0; i < ncols; ++i) po[i] = __float2bfloat16(v[i]);
+    }
+  }
+  if (p.act != FFVC_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
+  }
+  if (p.mul_mode != FFVC_ACT_NONE) {
+    const __nv_bfloat16* ax = p.aux + off;
+    if (full_vec) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(ax + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          v[i + 2 * j] *= apply_act_grad(f.x, p.mul_mode);
+          v[i + 2 * j + 1] *= apply_act_grad(f.y, p.mul_mode);
+        }
+      }
+    } else {
+      for (int i = 0; i < ncols; ++i) v[i] *= apply_act_grad(__bfloat162float(ax[i]), p.mul_mode);
+    }
+  }
+  if (p.res != nullptr) {
+    const __nv_bfloat16* rs = p.res + off;
+    if (full_vec) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(rs + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          v[i + 2 * j] += f.x;
+          v[i + 2 * j + 1] += f.y;
+        }
+      }
+    } else {
+      for (int i = 0; i < ncols; ++i) v[i] += __bfloat162float(rs[i]);
+    }
+  }
+  if (p.out_fp32) {
+    float* o = reinterpret_cast<float*>(p.out) + off;
+    if (p.atomic) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < ncols) atomicAdd(o + i, v[i]);
+    } else if (ncols == 32 && (p.ldc % 4 == 0) && (p.out_bs % 4 == 0) && (p.out_bs_inner % 4 == 0)) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+      for (int i = 0; i < ncols; ++i) o[i] = v[i];
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+    if (full_vec) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(o + i) = pack_bf16x8(v + i);
+    } else {
+      for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(v[i]);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kNumThreads, 1)
@@ -104,7 +221,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), kNumEpiWarps);
     }
     fence_mbar_init();
   }
@@ -118,11 +235,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int tiles_m = (p.M + kBlockM - 1) / kBlockM;
+  const int tiles_m = (p.M + p.tile_m - 1) / p.tile_m;
   const int tiles_n = (p.N + p.block_n - 1) / p.block_n;
   const int tiles_per_batch = tiles_m * tiles_n;
   const int total_kb = p.kb_per_seg * p.k_segs;
-  const long long total_tiles = (long long)tiles_per_batch * p.batch * p.splits;
+  const long long tiles_all_batches = (long long)tiles_per_batch * p.batch;
+  const long long total_tiles = tiles_all_batches * p.splits;
+  const uint32_t a_bytes = (uint32_t)p.tile_m * kBlockK * 2;
+  const uint32_t b_off = a_bytes;  // B follows A inside a stage
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -131,12 +251,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int split = (int)(t / ((long long)tiles_per_batch * p.batch));
-        const int rem = (int)(t % ((long long)tiles_per_batch * p.batch));
+        const int split = (int)(t / tiles_all_batches);
+        const int rem = (int)(t % tiles_all_batches);
         const int bi = rem / tiles_per_batch;
         const int tm = (rem % tiles_per_batch) / tiles_n;
         const int tn = rem % tiles_n;
-        const int m0 = tm * kBlockM, n0 = tn * p.block_n;
+        const int m0 = tm * p.tile_m, n0 = tn * p.block_n;
+        const int bi_in = bi % p.batch_inner, bi_out = bi / p.batch_inner;
         const int kb_begin = (int)((long long)total_kb * split / p.splits);
         const int kb_end = (int)((long long)total_kb * (split + 1) / p.splits);
         // conv: decompose the flattened pixel index of the tile origin
@@ -151,32 +272,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * kStageBytes;
-          const uint32_t sb = sa + kStageABytes;
+          const uint32_t sb = sa + b_off;
           const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, (uint32_t)kStageABytes + b_bytes);
+          mbar_expect_tx(fb, a_bytes + b_bytes);
           const int seg = kb / p.kb_per_seg;
-          const int k0 = (kb % p.kb_per_seg) * kBlockK;
+          const int kk = kb % p.kb_per_seg;
+          const int k0 = kk * kBlockK;
           // ---- A
-          if (p.a_mode == FFVC_OP_KMAJOR) {
-            tma_load_3d(sa, &tmap_a, fb, k0, m0, bi * p.a_c2_out + seg * p.a_c2_seg);
-          } else if (p.a_mode == FFVC_OP_MNMAJOR) {
-            const int c2 = bi * p.a_c2_out + seg * p.a_c2_seg;
-            tma_load_3d(sa, &tmap_a, fb, m0, k0, c2);
-            tma_load_3d(sa + 64 * kBlockK * 2, &tmap_a, fb, m0 + 64, k0, c2);
-          } else {
-            const int kk = kb % p.kb_per_seg;
+          if (p.a_mode == FFVC_OP_CONV3X3) {
             const int tap = kk / p.conv_cblocks;
             const int c0 = (kk % p.conv_cblocks) * kBlockK;
-            const int dy = (tap / 3 - 1) * p.conv_dil, dx = (tap % 3 - 1) * p.conv_dil;
-            tma_load_4d(sa, &tmap_a, fb, c0, cx0 + dx, cy0 + dy, cimg);
+            tma_load_4d(sa, &tmap_a, fb, c0, cx0 + (tap % 3 - 1), cy0 + (tap / 3 - 1), cimg);
+          } else {
+            const int c2 = (p.a_role == FFVC_ROLE_OUT_BATCH) ? bi_in : 0;
+            const int c3 = (p.a_role == FFVC_ROLE_OUT_BATCH) ? bi_out : (p.a_role == FFVC_ROLE_K_SEGMENT ? seg : 0);
+            if (p.a_mode == FFVC_OP_KMAJOR) {
+              tma_load_4d(sa, &tmap_a, fb, k0, m0, c2, c3);
+            } else {
+              for (int j = 0; j < p.tile_m / 64; ++j) tma_load_4d(sa + j * 8192, &tmap_a, fb, m0 + 64 * j, k0, c2, c3);
+            }
           }
           // ---- B
-          if (p.b_mode == FFVC_OP_KMAJOR) {
-            tma_load_3d(sb, &tmap_b, fb, k0, n0, bi * p.b_c2_out + seg * p.b_c2_seg);
-          } else {
-            const int c2 = bi * p.b_c2_out + seg * p.b_c2_seg;
-            for (int j = 0; j < p.block_n / 64; ++j)
-              tma_load_3d(sb + j * 64 * kBlockK * 2, &tmap_b, fb, n0 + 64 * j, k0, c2);
+          {
+            const int c2 = (p.b_role == FFVC_ROLE_OUT_BATCH) ? bi_in : 0;
+            const int c3 = (p.b_role == FFVC_ROLE_OUT_BATCH) ? bi_out : (p.b_role == FFVC_ROLE_K_SEGMENT ? seg : 0);
+            if (p.b_mode == FFVC_OP_KMAJOR) {
+              tma_load_4d(sb, &tmap_b, fb, k0, n0, c2, c3);
+            } else {
+              for (int j = 0; j < p.block_n / 64; ++j) tma_load_4d(sb + j * 8192, &tmap_b, fb, n0 + 64 * j, k0, c2, c3);
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -191,16 +315,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t idesc = umma_idesc_bf16(p.block_n, p.a_mode == FFVC_OP_MNMAJOR, p.b_mode == FFVC_OP_MNMAJOR);
       // K-major : 8-row groups 1024 B apart (SBO), one swizzle atom along K (LBO unused), K step = 32 B
       // MN-major: 64-wide MN chunks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), K step = 2048 B
-      const uint32_t a_lbo = (p.a_mode == FFVC_OP_MNMAJOR) ? 64u * kBlockK * 2u : 16u;
-      const uint32_t b_lbo = (p.b_mode == FFVC_OP_MNMAJOR) ? 64u * kBlockK * 2u : 16u;
+      const uint32_t a_lbo = (p.a_mode == FFVC_OP_MNMAJOR) ? 8192u : 16u;
+      const uint32_t b_lbo = (p.b_mode == FFVC_OP_MNMAJOR) ? 8192u : 16u;
       const uint32_t a_kstep = (p.a_mode == FFVC_OP_MNMAJOR) ? 2048u : 32u;
       const uint32_t b_kstep = (p.b_mode == FFVC_OP_MNMAJOR) ? 2048u : 32u;
+      const int subs = p.tile_m / 128;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int split = (int)(t / ((long long)tiles_per_batch * p.batch));
+        const int split = (int)(t / tiles_all_batches);
         const int kb_begin = (int)((long long)total_kb * split / p.splits);
         const int kb_end = (int)((long long)total_kb * (split + 1) / p.splits);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -210,12 +335,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * kStageBytes;
-          const uint32_t sb = sa + kStageABytes;
+          const uint32_t sb = sa + b_off;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u);
             const uint64_t db = umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
-            umma_bf16(tmem_d, da, db, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+            const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
+            for (int sub = 0; sub < subs; ++sub) {
+              const uint64_t da = umma_smem_desc_sw128(sa + sub * 16384 + k * a_kstep, a_lbo, 1024u);
+              umma_bf16(tmem_d + sub * 128, da, db, idesc, accum);
+            }
           }
           umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
           if (++stage == kStages) {
@@ -231,146 +359,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // 0 / 1: column half (tile_m 128) or row sub-tile (tile_m 256)
+    const int row_in_tile = (p.tile_m == 256 ? half * 128 : 0) + q * 32 + lane;
+    // columns this warp covers inside the tile
+    int c_begin, c_end, tmem_col0;
+    if (p.tile_m == 256) {
+      c_begin = 0;
+      c_end = p.block_n;
+      tmem_col0 = half * 128;
+    } else {
+      const int hcols = (p.block_n >= 64) ? p.block_n / 2 : p.block_n;
+      c_begin = half * hcols;
+      c_end = (p.block_n >= 64) ? c_begin + hcols : (half == 0 ? p.block_n : 0);
+      tmem_col0 = 0;
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ld_ok = (p.ldc % 8 == 0) && (p.out_bs % 8 == 0);
+    const bool vec_ok = (p.ldc % 8 == 0) && (p.out_bs % 8 == 0) && (p.out_bs_inner % 8 == 0);
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int rem = (int)(t % ((long long)tiles_per_batch * p.batch));
+      const int rem = (int)(t % tiles_all_batches);
       const int bi = rem / tiles_per_batch;
       const int tm = (rem % tiles_per_batch) / tiles_n;
       const int tn = rem % tiles_n;
-      const int gm = tm * kBlockM + row;
+      const int gm = tm * p.tile_m + row_in_tile;
       const int n0 = tn * p.block_n;
+      const int bi_in = bi % p.batch_inner, bi_out = bi / p.batch_inner;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const long long row_off = (long long)bi * p.out_bs + (long long)gm * p.ldc;
+      const long long row_off = (long long)bi_out * p.out_bs + (long long)bi_in * p.out_bs_inner + (long long)gm * p.ldc;
       const float rbias = (p.bias_mode == 2 && gm < p.M) ? p.bias[gm] : 0.0f;
-      for (int c = 0; c < p.block_n; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_base + (uint32_t)(acc * 256 + c) + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * 256 + tmem_col0 + c) + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
-        if (c + 32 >= p.block_n) {
-          // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
         const int gn0 = n0 + c;
-        if (gm < p.M && gn0 < p.N) {
-        const int ncols = min(32, p.N - gn0);
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-        if (p.bias_mode == 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i < ncols) v[i] += p.bias[gn0 + i];
-        } else if (p.bias_mode == 2) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] += rbias;
-        }
-        const long long off = row_off + gn0;
-        const bool full_vec = vec_ld_ok && (ncols == 32);
-        if (p.pre_out != nullptr) {
-          __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(p.pre_out) + off;
-          if (full_vec) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 pk;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i + 0], v[i + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(po + i) = pk;
-            }
-          } else {
-            for (int i = 0; i < ncols; ++i) po[i] = __float2bfloat16(v[i]);
-          }
-        }
-        if (p.act != FFVC_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-        }
-        if (p.mul_mode != FFVC_ACT_NONE) {
-          const __nv_bfloat16* ax = p.aux + off;
-          if (full_vec) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(ax + i);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(h[j]);
-                v[i + 2 * j] *= apply_act_grad(f.x, p.mul_mode);
-                v[i + 2 * j + 1] *= apply_act_grad(f.y, p.mul_mode);
-              }
-            }
-          } else {
-            for (int i = 0; i < ncols; ++i) v[i] *= apply_act_grad(__bfloat162float(ax[i]), p.mul_mode);
-          }
-        }
-        if (p.res != nullptr) {
-          const __nv_bfloat16* rs = p.res + off;
-          if (full_vec) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(rs + i);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(h[j]);
-                v[i + 2 * j] += f.x;
-                v[i + 2 * j + 1] += f.y;
-              }
-            }
-          } else {
-            for (int i = 0; i < ncols; ++i) v[i] += __bfloat162float(rs[i]);
-          }
-        }
-        if (p.out_fp32) {
-          float* o = reinterpret_cast<float*>(p.out) + off;
-          if (p.atomic) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < ncols) atomicAdd(o + i, v[i]);
-          } else if (ncols == 32 && (p.ldc % 4 == 0) && (p.out_bs % 4 == 0)) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-            for (int i = 0; i < ncols; ++i) o[i] = v[i];
-          }
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-          if (full_vec) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              uint4 pk;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i + 0], v[i + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(o + i) = pk;
-            }
-          } else {
-            for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(v[i]);
-          }
-        }
-        }  // active row / column chunk
+        if (gm < p.M && gn0 < p.N) epilogue_chunk(p, r, gn0, row_off + gn0, rbias, vec_ok);
         __syncwarp();
       }
+      // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -402,7 +434,7 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// dims/strides in elements (bf16); rank 3 or 4; dim0 contiguous.
+// dims/strides in elements (bf16); rank 4; dim0 contiguous.
 static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                      const uint32_t* box) {
   PFN_encodeTiled fn = get_encode_fn();
@@ -448,6 +480,9 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   if (!g || !g->a || !g->b || !g->out) return set_error(FFVC_ERR_ARG, "gemm: null pointer");
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return set_error(FFVC_ERR_ARG, "gemm: non-positive dimension");
   const int batch = g->batch > 0 ? g->batch : 1;
+  const int batch_inner = g->batch_inner > 0 ? g->batch_inner : 1;
+  if (batch % batch_inner) return set_error(FFVC_ERR_ARG, "gemm: batch must be a multiple of batch_inner");
+  const int batch_outer = batch / batch_inner;
   const int k_segs = g->k_segs > 0 ? g->k_segs : 1;
   int splits = g->splits > 0 ? g->splits : 1;
   if (splits > 1 && !(g->out_fp32 && g->atomic)) return set_error(FFVC_ERR_ARG, "gemm: split-K needs fp32 atomic output");
@@ -465,35 +500,45 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     g_attr_set = true;
   }
 
-  // ---- tile N
+  // ---- tile shape
   int block_n = g->block_n;
+  int tile_m = g->tile_m;
   if (block_n <= 0) {
     if (g->N > 128) block_n = 256;
     else if (g->N > 64) block_n = 128;
     else if (g->N > 32) block_n = 64;
     else block_n = 32;
-    // prefer more tiles when the problem is small: fill the SMs
-    const long long tm = (g->M + kBlockM - 1) / kBlockM;
-    while (block_n > 64 && tm * ((g->N + block_n - 1) / block_n) * batch * splits < g_num_sms) block_n >>= 1;
+    if (tile_m <= 0) {
+      // prefer more tiles when the problem is small: fill the SMs
+      const long long tm = (g->M + 127) / 128;
+      while (block_n > 64 && tm * ((g->N + block_n - 1) / block_n) * batch * splits < g_num_sms) block_n >>= 1;
+    }
   }
   if (block_n != 32 && block_n != 64 && block_n != 128 && block_n != 256)
     return set_error(FFVC_ERR_ARG, "gemm: block_n must be 32/64/128/256");
   if (g->b_mode == FFVC_OP_MNMAJOR && block_n < 64) block_n = 64;
+  if (tile_m <= 0) {
+    // 256-row tiles share one B tile between two MMAs: worthwhile whenever N <= 128 and there is enough M to go round
+    const long long t256 = (long long)((g->M + 255) / 256) * ((g->N + block_n - 1) / block_n) * batch * splits;
+    tile_m = (block_n <= 128 && g->M >= 256 && t256 >= g_num_sms) ? 256 : 128;
+  }
+  if (tile_m != 128 && tile_m != 256) return set_error(FFVC_ERR_ARG, "gemm: tile_m must be 128 or 256");
+  if (tile_m == 256 && block_n > 128) return set_error(FFVC_ERR_ARG, "gemm: tile_m 256 needs block_n <= 128");
 
   GemmDev p;
   memset(&p, 0, sizeof(p));
   p.M = g->M;
   p.N = g->N;
   p.batch = batch;
+  p.batch_inner = batch_inner;
+  p.tile_m = tile_m;
   p.block_n = block_n;
   p.a_mode = g->a_mode;
   p.b_mode = g->b_mode;
   p.k_segs = k_segs;
   p.splits = splits;
-  p.a_c2_out = (g->a_batch_role == FFVC_ROLE_OUT_BATCH);
-  p.a_c2_seg = (g->a_batch_role == FFVC_ROLE_K_SEGMENT);
-  p.b_c2_out = (g->b_batch_role == FFVC_ROLE_OUT_BATCH);
-  p.b_c2_seg = (g->b_batch_role == FFVC_ROLE_K_SEGMENT);
+  p.a_role = g->a_batch_role;
+  p.b_role = g->b_batch_role;
 
   CUtensorMap ta, tb;
   int rc;
@@ -501,10 +546,11 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   if (g->a_mode == FFVC_OP_CONV3X3) {
     const int H = g->conv_h, W = g->conv_w, C = g->conv_c;
     if (H <= 0 || W <= 0 || C <= 0 || C % 64 != 0) return set_error(FFVC_ERR_ARG, "conv: Cin must be a multiple of 64");
-    const int tile_w = W < 128 ? W : 128;
-    if (128 % tile_w != 0 || W % tile_w != 0) return set_error(FFVC_ERR_ARG, "conv: W must divide or be a multiple of 128");
-    const int tile_h = 128 / tile_w;
-    if (H % tile_h != 0) return set_error(FFVC_ERR_ARG, "conv: H*W must tile by 128 pixels");
+    if (tile_m == 256 && ((long long)H * W) % 256 != 0) tile_m = p.tile_m = 128;
+    const int tile_w = W < tile_m ? W : tile_m;
+    if (tile_m % tile_w != 0 || W % tile_w != 0) return set_error(FFVC_ERR_ARG, "conv: W must divide or be a multiple of the pixel tile");
+    const int tile_h = tile_m / tile_w;
+    if (H % tile_h != 0) return set_error(FFVC_ERR_ARG, "conv: H*W must tile by the pixel tile");
     const long long npix = (long long)g->conv_n * H * W;
     if (npix != g->M) return set_error(FFVC_ERR_ARG, "conv: M must equal N_img*H*W");
     if (g->K != 9 * C) return set_error(FFVC_ERR_ARG, "conv: K must equal 9*Cin");
@@ -515,39 +561,53 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     p.conv_h = H;
     p.conv_w = W;
     p.conv_cblocks = C / 64;
-    p.conv_tile_w = tile_w;
-    p.conv_dil = 1;
     p.kb_per_seg = 9 * (C / 64);
   } else {
     p.kb_per_seg = (g->K + kBlockK - 1) / kBlockK;
-    const uint64_t nb = (g->a_batch_role == FFVC_ROLE_OUT_BATCH) ? batch : (g->a_batch_role == FFVC_ROLE_K_SEGMENT ? k_segs : 1);
-    const uint64_t bs = nb > 1 ? (uint64_t)g->a_batch_stride : (uint64_t)g->a_ld * 8;  // any valid stride for size-1 dim
+    uint64_t n_in = 1, n_out = 1, s_in = (uint64_t)g->a_ld * 8, s_out = (uint64_t)g->a_ld * 8;  // any valid stride for size-1 dims
+    if (g->a_batch_role == FFVC_ROLE_OUT_BATCH) {
+      n_in = batch_inner;
+      n_out = batch_outer;
+      if (n_in > 1) s_in = (uint64_t)g->a_batch_stride_inner;
+      if (n_out > 1) s_out = (uint64_t)g->a_batch_stride;
+    } else if (g->a_batch_role == FFVC_ROLE_K_SEGMENT) {
+      n_out = k_segs;
+      if (n_out > 1) s_out = (uint64_t)g->a_batch_stride;
+    }
     if (g->a_mode == FFVC_OP_KMAJOR) {
-      uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->M, nb};
-      uint64_t str[3] = {1, (uint64_t)g->a_ld, bs};
-      uint32_t box[3] = {64, 128, 1};
-      if ((rc = make_tmap(&ta, g->a, 3, dims, str, box)) != FFVC_OK) return rc;
+      uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->M, n_in, n_out};
+      uint64_t str[4] = {1, (uint64_t)g->a_ld, s_in, s_out};
+      uint32_t box[4] = {64, (uint32_t)tile_m, 1, 1};
+      if ((rc = make_tmap(&ta, g->a, 4, dims, str, box)) != FFVC_OK) return rc;
     } else {
-      uint64_t dims[3] = {(uint64_t)g->M, (uint64_t)g->K, nb};
-      uint64_t str[3] = {1, (uint64_t)g->a_ld, bs};
-      uint32_t box[3] = {64, 64, 1};
-      if ((rc = make_tmap(&ta, g->a, 3, dims, str, box)) != FFVC_OK) return rc;
+      uint64_t dims[4] = {(uint64_t)g->M, (uint64_t)g->K, n_in, n_out};
+      uint64_t str[4] = {1, (uint64_t)g->a_ld, s_in, s_out};
+      uint32_t box[4] = {64, 64, 1, 1};
+      if ((rc = make_tmap(&ta, g->a, 4, dims, str, box)) != FFVC_OK) return rc;
     }
   }
   // ---- operand B
   {
-    const uint64_t nb = (g->b_batch_role == FFVC_ROLE_OUT_BATCH) ? batch : (g->b_batch_role == FFVC_ROLE_K_SEGMENT ? k_segs : 1);
-    const uint64_t bs = nb > 1 ? (uint64_t)g->b_batch_stride : (uint64_t)g->b_ld * 8;
+    uint64_t n_in = 1, n_out = 1, s_in = (uint64_t)g->b_ld * 8, s_out = (uint64_t)g->b_ld * 8;
+    if (g->b_batch_role == FFVC_ROLE_OUT_BATCH) {
+      n_in = batch_inner;
+      n_out = batch_outer;
+      if (n_in > 1) s_in = (uint64_t)g->b_batch_stride_inner;
+      if (n_out > 1) s_out = (uint64_t)g->b_batch_stride;
+    } else if (g->b_batch_role == FFVC_ROLE_K_SEGMENT) {
+      n_out = k_segs;
+      if (n_out > 1) s_out = (uint64_t)g->b_batch_stride;
+    }
     if (g->b_mode == FFVC_OP_KMAJOR) {
-      uint64_t dims[3] = {(uint64_t)g->K, (uint64_t)g->N, nb};
-      uint64_t str[3] = {1, (uint64_t)g->b_ld, bs};
-      uint32_t box[3] = {64, (uint32_t)block_n, 1};
-      if ((rc = make_tmap(&tb, g->b, 3, dims, str, box)) != FFVC_OK) return rc;
+      uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->N, n_in, n_out};
+      uint64_t str[4] = {1, (uint64_t)g->b_ld, s_in, s_out};
+      uint32_t box[4] = {64, (uint32_t)block_n, 1, 1};
+      if ((rc = make_tmap(&tb, g->b, 4, dims, str, box)) != FFVC_OK) return rc;
     } else {
-      uint64_t dims[3] = {(uint64_t)g->N, (uint64_t)g->K, nb};
-      uint64_t str[3] = {1, (uint64_t)g->b_ld, bs};
-      uint32_t box[3] = {64, 64, 1};
-      if ((rc = make_tmap(&tb, g->b, 3, dims, str, box)) != FFVC_OK) return rc;
+      uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->K, n_in, n_out};
+      uint64_t str[4] = {1, (uint64_t)g->b_ld, s_in, s_out};
+      uint32_t box[4] = {64, 64, 1, 1};
+      if ((rc = make_tmap(&tb, g->b, 4, dims, str, box)) != FFVC_OK) return rc;
     }
   }
   if (splits > p.kb_per_seg * k_segs) splits = p.splits = p.kb_per_seg * k_segs;
@@ -559,14 +619,17 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   p.bias = g->bias;
   p.ldc = g->ldc;
   p.out_bs = g->out_batch_stride;
+  p.out_bs_inner = g->out_batch_stride_inner;
   p.out_fp32 = g->out_fp32;
   p.atomic = g->atomic;
   p.bias_mode = g->bias ? g->bias_mode : 0;
   p.act = g->act;
   p.mul_mode = g->aux ? g->mul_mode : 0;
   p.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
+  if (p.bias_mode == 1 && (reinterpret_cast<uintptr_t>(g->bias) % 16 != 0))
+    return set_error(FFVC_ERR_ARG, "gemm: column bias must be 16-byte aligned");
 
-  const long long tiles = (long long)((g->M + kBlockM - 1) / kBlockM) * ((g->N + block_n - 1) / block_n) * batch * splits;
+  const long long tiles = (long long)((g->M + tile_m - 1) / tile_m) * ((g->N + block_n - 1) / block_n) * batch * splits;
   const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
   gemm_tcgen05_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, p);
   cudaError_t e = cudaGetLastError();

@@ -249,31 +249,42 @@ __global__ void groupnorm_finalize_kernel(const double* __restrict__ ws, float* 
   rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
-// y = act((x - mean) * rstd * gamma + beta), act = swish or identity
+// y = act((x - mean) * rstd * gamma + beta), act = swish or identity.
+// grid (pixel chunks, N); each thread owns one 8-channel vector column (its affine + statistics live in registers)
+// and strides over the pixels of the chunk: no per-element index arithmetic, 16-byte coalesced loads/stores.
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ x,
                                                               const float* __restrict__ mean,
                                                               const float* __restrict__ rstd,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta,
-                                                              __nv_bfloat16* __restrict__ y, long long total_vec,
-                                                              int HW, int C, int G, int swish) {
+                                                              __nv_bfloat16* __restrict__ y, int HW, int C, int G,
+                                                              int pix_per_cta, int swish) {
+  const int n = blockIdx.y;
   const int cpg = C / G;
   const int vec_per_pix = C >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int vc = (int)(i % vec_per_pix);
-    const long long pix = i / vec_per_pix;
-    const int n = (int)(pix / HW);
+  const int vc = threadIdx.x % vec_per_pix;
+  const int pl = threadIdx.x / vec_per_pix;
+  const int pstride = blockDim.x / vec_per_pix;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = vc * 8 + j;
+    const int g = n * G + c / cpg;
+    sc[j] = rstd[g] * gamma[c];
+    sh[j] = beta[c] - mean[g] * sc[j];
+  }
+  const long long base = (long long)n * HW * C + vc * 8;
+  for (int p = p0 + pl; p < p1; p += pstride) {
     float v[8], o[8];
-    unpack8(reinterpret_cast<const uint4*>(x)[i], v);
+    unpack8(*reinterpret_cast<const uint4*>(x + base + (long long)p * C), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = vc * 8 + j;
-      const int g = n * G + c / cpg;
-      const float u = (v[j] - mean[g]) * rstd[g] * gamma[c] + beta[c];
+      const float u = fmaf(v[j], sc[j], sh[j]);
       o[j] = swish ? swish_f(u) : u;
     }
-    reinterpret_cast<uint4*>(y)[i] = pack8(o);
+    *reinterpret_cast<uint4*>(y + base + (long long)p * C) = pack8(o);
   }
 }
 
@@ -336,7 +347,7 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_stats_kernel(const __nv_bfl
   }
 }
 
-// backward pass 2: dx = rstd * (g - S1/cnt - xhat * S2/cnt) (+ add)
+// backward pass 2: dx = rstd * (g - S1/cnt - xhat * S2/cnt) (+ add); same thread mapping as the apply kernel
 __global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                   const __nv_bfloat16* __restrict__ x,
                                                                   const float* __restrict__ mean,
@@ -345,36 +356,48 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfl
                                                                   const float* __restrict__ beta,
                                                                   const double* __restrict__ ws,
                                                                   const __nv_bfloat16* __restrict__ add,
-                                                                  __nv_bfloat16* __restrict__ dx, long long total_vec,
-                                                                  int HW, int C, int G, float inv_count, int swish) {
+                                                                  __nv_bfloat16* __restrict__ dx, int HW, int C, int G,
+                                                                  int pix_per_cta, float inv_count, int swish) {
+  const int n = blockIdx.y;
   const int cpg = C / G;
   const int vec_per_pix = C >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int vc = (int)(i % vec_per_pix);
-    const long long pix = i / vec_per_pix;
-    const int n = (int)(pix / HW);
+  const int vc = threadIdx.x % vec_per_pix;
+  const int pl = threadIdx.x / vec_per_pix;
+  const int pstride = blockDim.x / vec_per_pix;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  float mu[8], rs[8], gm[8], bt[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = vc * 8 + j;
+    const int g = n * G + c / cpg;
+    mu[j] = mean[g];
+    rs[j] = rstd[g];
+    gm[j] = gamma[c];
+    bt[j] = beta[c];
+    s1[j] = (float)ws[2 * g] * inv_count;
+    s2[j] = (float)ws[2 * g + 1] * inv_count;
+  }
+  const long long base = (long long)n * HW * C + vc * 8;
+  for (int p = p0 + pl; p < p1; p += pstride) {
+    const long long off = base + (long long)p * C;
     float v[8], d[8], o[8];
-    unpack8(reinterpret_cast<const uint4*>(x)[i], v);
-    unpack8(reinterpret_cast<const uint4*>(dy)[i], d);
+    unpack8(*reinterpret_cast<const uint4*>(x + off), v);
+    unpack8(*reinterpret_cast<const uint4*>(dy + off), d);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = vc * 8 + j;
-      const int gi = n * G + c / cpg;
-      const float rs = rstd[gi];
-      const float xh = (v[j] - mean[gi]) * rs;
-      const float u = xh * gamma[c] + beta[c];
-      const float g = d[j] * (swish ? swish_grad_f(u) : 1.0f) * gamma[c];
-      const float s1 = (float)ws[2 * gi] * inv_count, s2 = (float)ws[2 * gi + 1] * inv_count;
-      o[j] = rs * (g - s1 - xh * s2);
+      const float xh = (v[j] - mu[j]) * rs[j];
+      const float u = fmaf(xh, gm[j], bt[j]);
+      const float g = d[j] * (swish ? swish_grad_f(u) : 1.0f) * gm[j];
+      o[j] = rs[j] * (g - s1[j] - xh * s2[j]);
     }
     if (add) {
       float a[8];
-      unpack8(reinterpret_cast<const uint4*>(add)[i], a);
+      unpack8(*reinterpret_cast<const uint4*>(add + off), a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] += a[j];
     }
-    reinterpret_cast<uint4*>(dx)[i] = pack8(o);
+    *reinterpret_cast<uint4*>(dx + off) = pack8(o);
   }
 }
 
@@ -422,6 +445,12 @@ extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* ga
   return FFVC_OK;
 }
 
+// pixels per CTA: aim for >= 8 CTAs per SM worth of work, at least 64 pixels each
+static int gn_pix_per_cta(int N, int HW) {
+  int ppc = 1024;
+  while (ppc > 64 && (long long)N * ((HW + ppc - 1) / ppc) < 148 * 8) ppc >>= 1;
+  return ppc;
+}
 static int gn_check(int C, int G) {
   if (C % 8 != 0 || G <= 0 || C % G != 0 || C / 8 > 256 || 256 % (C / 8) != 0)
     return set_error(FFVC_ERR_ARG, "groupnorm: C must be a multiple of 8, divisible by G, C/8 must divide 256");
@@ -435,7 +464,7 @@ extern "C" int ffvc_groupnorm_stats(const void* x, double* ws, float* mean, floa
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st);
-  const int pix_per_cta = 1024;
+  const int pix_per_cta = gn_pix_per_cta(N, HW);
   dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
   groupnorm_stats_kernel<<<grid, 256, 2 * G * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ws, HW, C, G,
                                                                   pix_per_cta);
@@ -450,11 +479,10 @@ extern "C" int ffvc_groupnorm_apply(const void* x, const float* mean, const floa
   int rc = gn_check(C, G);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long total_vec = (long long)N * HW * (C / 8);
-  long long want = (total_vec + 255) / 256;
-  const unsigned grid = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  const int pix_per_cta = gn_pix_per_cta(N, HW);
+  dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
   groupnorm_apply_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta,
-                                               reinterpret_cast<__nv_bfloat16*>(y), total_vec, HW, C, G, swish);
+                                               reinterpret_cast<__nv_bfloat16*>(y), HW, C, G, pix_per_cta, swish);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
@@ -467,19 +495,18 @@ extern "C" int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* me
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st);
-  const int pix_per_cta = 1024;
+  const int pix_per_cta = gn_pix_per_cta(N, HW);
   dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
   auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   groupnorm_bwd_stats_kernel<<<grid, 256, 2 * G * sizeof(float), st>>>(dyb, xb, mean, rstd, gamma, beta, ws, HW, C, G,
                                                                       pix_per_cta, swish);
   FFVC_CHECK_LAUNCH();
-  const long long total_vec = (long long)N * HW * (C / 8);
-  long long want = (total_vec + 255) / 256;
-  const unsigned g2 = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  const int ppc2 = gn_pix_per_cta(N, HW);
+  dim3 g2((HW + ppc2 - 1) / ppc2, N);
   groupnorm_bwd_apply_kernel<<<g2, 256, 0, st>>>(dyb, xb, mean, rstd, gamma, beta, ws,
                                                  reinterpret_cast<const __nv_bfloat16*>(add),
-                                                 reinterpret_cast<__nv_bfloat16*>(dx), total_vec, HW, C, G,
+                                                 reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, ppc2,
                                                  1.0f / ((float)HW * (C / G)), swish);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;

@@ -145,11 +145,28 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU() default) evaluated with the Abramowitz-Stegun 7.1.26 rational form of erf
+// (|abs err| <= 1.5e-7, far below the bf16 output rounding): one MUFU.RCP, one MUFU.EX2 and ~10 FMAs instead of erff's
+// long dependent chain.  cdf = Phi(x), pdf = phi(x) share the single exponential.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float e = __expf(-z * z);
+  const float poly =
+      t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  const float tail = 0.5f * poly * e;  // = 0.5 * erfc(|x| / sqrt(2))
+  cdf = (x >= 0.f) ? 1.0f - tail : tail;
+  pdf = 0.39894228040143268f * e;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float c, d;
+  gelu_parts(x, c, d);
+  return x * c;
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float c, d;
+  gelu_parts(x, c, d);
+  return fmaf(x, d, c);
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float quick_gelu_f(float x) { return x * sigmoid_f(1.702f * x); }

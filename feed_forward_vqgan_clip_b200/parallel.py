@@ -1,0 +1,54 @@
+"""Data-parallel plumbing of the train step (replaces the Horovod calls of main.py:528-531,627-629,668-674,838-842).
+
+One process per GPU (torchrun), full replicas, the prompt batch is sharded across ranks, and ONE all-reduce of the
+mapper's flat gradient arena per step; the 1/world average is folded into the fused Adam's grad_scale.  The process
+group is NCCL on the GPU box; the same functions run over gloo on CPU for the host-logic tests."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment (torch.distributed.run)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            kw["device_id"] = torch.device("cuda", local_rank)
+        dist.init_process_group(backend, **kw)
+    return rank, local_rank, world
+
+
+def shard_range(n_total, rank, world):
+    """Contiguous shard [lo, hi) of a global batch, like DistributedSampler with drop_last (main.py:668-674)."""
+    per = n_total // world
+    return rank * per, (rank + 1) * per
+
+
+def allreduce_flat_grads(flat_grad, world, group=None):
+    """Sum-all-reduce the flat gradient arena in place; returns the scale Adam must apply (1/world)."""
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+def broadcast_flat(flat, src=0, group=None):
+    """hvd.broadcast_parameters / broadcast_optimizer_state equivalent on a flat arena (main.py:628-629)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat, src=src, group=group)
+    return flat
+
+
+def allreduce_scalars(values, world, group=None):
+    """The 4 logging scalars of main.py:838-842 in ONE all-reduce (average)."""
+    t = torch.stack([v.reshape(()) for v in values]).clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t /= world
+    return t

@@ -255,7 +255,7 @@ class DecoderEngine:
         ops.gemm(q, k, S, HW, HW, C, a_role=ops.ROLE_OUT, a_bs=HW * C, b_role=ops.ROLE_OUT, b_bs=HW * C, batch=N,
                  out_bs=HW * HW, alpha=scale)
         P = self._new(N, HW, HW)
-        call("softmax_fwd", S, P, N * HW, HW)
+        call("softmax_fwd", S, P, N * HW, HW, HW)
         del S
         O = self._new(M, C)
         ops.gemm(P, v, O, HW, C, HW, a_role=ops.ROLE_OUT, a_bs=HW * HW, b_mode=ops.MNMAJOR, b_ld=C, b_role=ops.ROLE_OUT,
@@ -272,7 +272,7 @@ class DecoderEngine:
             ops.gemm(P, dO, dV, HW, C, HW, a_mode=ops.MNMAJOR, a_ld=HW, a_role=ops.ROLE_OUT, a_bs=HW * HW,
                      b_mode=ops.MNMAJOR, b_ld=C, b_role=ops.ROLE_OUT, b_bs=HW * C, batch=N, out_bs=HW * C)
             dS = self._new(N, HW, HW)
-            call("softmax_bwd", P, dP, dS, N * HW, HW, scale)
+            call("softmax_bwd", P, dP, dS, N * HW, HW, HW, scale)
             del dP
             dQ = self._new(M, C)   # dQ[i,c] = sum_j dS[i,j] k[j,c]
             ops.gemm(dS, k, dQ, HW, C, HW, a_role=ops.ROLE_OUT, a_bs=HW * HW, b_mode=ops.MNMAJOR, b_ld=C,
@@ -383,9 +383,9 @@ class _ClampWithGrad(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, = ctx.saved_tensors
-        gx = torch.empty_like(x, dtype=F32)
+        gx = torch.empty(x.shape, device=x.device, dtype=F32)        # contiguous: x may carry permuted strides
         call("clamp_bwd", g.contiguous().float(), x.contiguous().float(), gx, x.numel(), ctx.lo, ctx.hi)
-        return gx.view_as(x), None, None
+        return gx, None, None
 
 
 clamp_with_grad = _ClampWithGrad.apply

@@ -63,12 +63,15 @@ typedef struct {
   int a_mode, b_mode;      /* FFVC_OP_* (CONV3X3 only for A) */
   int64_t a_ld, b_ld;      /* elements between consecutive rows (K-major: rows of M/N; MN-major: rows of K) */
   int a_batch_role, b_batch_role; /* FFVC_ROLE_* */
-  int64_t a_batch_stride, b_batch_stride; /* elements */
+  int64_t a_batch_stride, b_batch_stride; /* elements (outer batch / k-segment stride) */
+  int64_t a_batch_stride_inner, b_batch_stride_inner; /* elements (inner batch stride; used when batch_inner > 1) */
   int M, N, K;             /* K = contraction length per segment */
-  int batch;               /* output batches (>=1) */
+  int batch;               /* output batches (>=1) = outer * inner */
+  int batch_inner;         /* inner batch count (0/1 = none): b = b_outer * batch_inner + b_inner */
   int k_segs;              /* extra contraction over operand dim 2 (>=1) */
   int splits;              /* split-K (requires out_fp32 && atomic) */
   int block_n;             /* 0 = auto, else 32/64/128/256 */
+  int tile_m;              /* 0 = auto, else 128/256 (256 needs block_n <= 128) */
   /* CONV3X3 (A is NHWC [conv_n][conv_h][conv_w][conv_c], pad 1, stride 1; M = n*h*w; K = 9*c) */
   int conv_n, conv_h, conv_w, conv_c;
   /* epilogue */
@@ -79,6 +82,7 @@ typedef struct {
   const float* bias;       /* optional fp32 */
   int64_t ldc;
   int64_t out_batch_stride;
+  int64_t out_batch_stride_inner;
   int out_fp32;
   int atomic;
   int bias_mode;           /* 1 = per column (n), 2 = per row (m) */
@@ -114,9 +118,10 @@ int ffvc_upsample2x_bwd(const void* dy, void* dx, int N, int H, int W, int C, vo
 /* batched transpose in[b][R][Cc] -> out[b][Cc][R] (Rearrange 'b c h w -> b (h w) c', mlp_mixer_pytorch.py:31). */
 int ffvc_transpose(const void* in, void* out, int B, int R, int Cc, int in_fp32, int out_fp32, void* stream);
 
-/* row softmax (fp32 scores -> bf16 probabilities) and its backward, VQGAN AttnBlock. */
-int ffvc_softmax_fwd(const float* s, void* p, long long rows, int n, void* stream);
-int ffvc_softmax_bwd(const void* p, const float* dp, void* ds, long long rows, int n, float scale, void* stream);
+/* row softmax (fp32 scores -> bf16 probabilities) and its backward (VQGAN AttnBlock, CLIP attention).
+ * rows are ld elements apart, n valid columns; output padding [n, ld) is zero-filled. */
+int ffvc_softmax_fwd(const float* s, void* p, long long rows, int n, int ld, void* stream);
+int ffvc_softmax_bwd(const void* p, const float* dp, void* ds, long long rows, int n, int ld, float scale, void* stream);
 
 /* bias gradients: db[n] += sum_rows dy[row][n];  db[j] += sum_{b,d} dy[b][j][d]. */
 int ffvc_colsum(const void* dy, float* db, long long rows, int n, void* stream);

@@ -113,3 +113,77 @@ def test_epilogue_residual_mulgrad_alpha():
     s = torch.sigmoid(1.702 * x)
     ref = (0.5 * (a.float() @ b.float().t()) + bias) * (s + 1.702 * x * s * (1 - s)) + res.float()
     _check(out, ref, 2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 128, 256), (512, 64, 192), (300, 100, 64)])
+def test_tile_m_256_kmajor(M, N, K):
+    a, b = _rand(M, K, seed=21), _rand(N, K, seed=22)
+    bias = torch.randn(N, device=DEV)
+    res = _rand(M, N, seed=23)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, b, out, M, N, K, tile_m=256, block_n=128 if N > 64 else 64, bias=bias, res=res, act=ops.ACT_GELU)
+    _check(out, F.gelu(a.float() @ b.float().t() + bias) + res.float(), 2e-2)
+
+
+def test_tile_m_256_mn_major_wgrad():
+    M, N, K = 640, 512, 128        # dW[n,k] = sum_m dY[m,n] X[m,k]  -> out (N x K), contraction M
+    dy, x = _rand(M, N, seed=24), _rand(M, K, seed=25)
+    out = torch.zeros(N, K, device=DEV, dtype=torch.float32)
+    ops.gemm(dy, x, out, N, K, M, a_mode=ops.MNMAJOR, b_mode=ops.MNMAJOR, a_ld=N, b_ld=K, tile_m=256, block_n=128, atomic=True)
+    _check(out, dy.float().t() @ x.float(), 1e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 128, 128), (1, 256, 256, 64, 64), (2, 64, 64, 64, 128)])
+def test_conv3x3_tile_m_256(n, h, w, cin, cout):
+    x = _rand(n, h, w, cin, seed=26)
+    wt = (_rand(cout, cin, 3, 3, seed=27).float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(cout, device=DEV)
+    res = _rand(n, h, w, cout, seed=28)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    out = torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, wp, out, n * h * w, cout, 9 * cin, a_mode=ops.CONV3X3, conv=(n, h, w, cin), bias=bias, res=res, tile_m=256,
+             block_n=min(cout, 128))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    _check(out, ref, 2e-2)
+
+
+def test_gelu_epilogue_matches_exact_erf_gelu():
+    M, N, K = 256, 512, 64
+    a, b = _rand(M, K, seed=29), (_rand(N, K, seed=30).float() * 0.5).to(torch.bfloat16)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(a, b, out, M, N, K, act=ops.ACT_GELU)
+    ref = F.gelu(a.float() @ b.float().t())                 # exact (erf) GELU, nn.GELU() default
+    assert (out - ref).abs().max().item() < 5e-5
+    aux = _rand(M, N, seed=31)
+    out2 = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(a, b, out2, M, N, K, aux=aux, mul_mode=ops.ACT_GELU)
+    x = aux.float()
+    gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * 3.141592653589793) ** 0.5
+    assert ((out2 - (a.float() @ b.float().t()) * gp).abs().max().item()) < 5e-4
+
+
+def test_batch_inner_attention_heads():
+    # scores[n,h,i,j] = sum_d Q[n,i,h,d] K[n,j,h,d] over a fused [N][T][3W] qkv tensor (CLIP ViT attention layout)
+    Nn, T, Hh, dh = 5, 50, 12, 64
+    W = Hh * dh
+    qkv = _rand(Nn, T, 3 * W, seed=32)
+    S = torch.zeros(Nn, Hh, T, 64, device=DEV, dtype=torch.float32)
+    ops.gemm(qkv, qkv, S, T, T, dh, a_ld=3 * W, b_ld=3 * W, b_off=W, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT,
+             batch=Nn * Hh, batch_inner=Hh, a_bs=T * 3 * W, b_bs=T * 3 * W, a_bs_in=dh, b_bs_in=dh, ldc=64,
+             out_bs=Hh * T * 64, out_bs_in=T * 64, alpha=0.125, block_n=64)
+    q = qkv[..., :W].float().reshape(Nn, T, Hh, dh).transpose(1, 2)
+    k = qkv[..., W:2 * W].float().reshape(Nn, T, Hh, dh).transpose(1, 2)
+    ref = 0.125 * q @ k.transpose(-1, -2)
+    _check(S[..., :T], ref, 1e-3)
+    assert float(S[..., T:].abs().max()) == 0.0
+    # O[n,i,h,:] = sum_j P[n,h,i,j] V[n,j,h,:]  (B read MN-major from the same fused tensor, K = 50 zero-extended to 64)
+    P = torch.softmax(ref, -1)
+    Pp = torch.zeros(Nn, Hh, T, 64, device=DEV, dtype=torch.bfloat16)
+    Pp[..., :T] = P.to(torch.bfloat16)
+    O = torch.empty(Nn, T, W, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(Pp, qkv, O, T, dh, T, a_ld=64, b_mode=ops.MNMAJOR, b_ld=3 * W, b_off=2 * W, a_role=ops.ROLE_OUT,
+             b_role=ops.ROLE_OUT, batch=Nn * Hh, batch_inner=Hh, a_bs=Hh * T * 64, a_bs_in=T * 64, b_bs=T * 3 * W, b_bs_in=dh,
+             ldc=W, out_bs=T * W, out_bs_in=dh, block_n=64)
+    v = qkv[..., 2 * W:].float().reshape(Nn, T, Hh, dh).transpose(1, 2)
+    refo = (Pp[..., :T].float() @ v).transpose(1, 2).reshape(Nn, T, W)
+    _check(O, refo, 2e-2)

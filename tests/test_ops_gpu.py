@@ -95,11 +95,11 @@ def test_softmax_fwd_bwd():
     rows, n = 512, 256
     s = rnd(rows, n, seed=1, dtype=F32, scale=3.0)
     p = torch.empty(rows, n, device=DEV, dtype=BF)
-    call("softmax_fwd", s, p, rows, n)
+    call("softmax_fwd", s, p, rows, n, n)
     close(p, torch.softmax(s, -1))
     dp = rnd(rows, n, seed=2, dtype=F32)
     ds = torch.empty(rows, n, device=DEV, dtype=BF)
-    call("softmax_bwd", p, dp, ds, rows, n, 0.5)
+    call("softmax_bwd", p, dp, ds, rows, n, n, 0.5)
     pf = p.float()
     close(ds, 0.5 * pf * (dp - (pf * dp).sum(-1, keepdim=True)))
 
