@@ -129,7 +129,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
 #pragma unroll
       for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(po + i) = pack_bf16x8(v + i);
     } else {
-      for (int i = 0; i < ncols; ++i) po[i] = __float2bfloat16(v[i]);
+      _Pragma("unroll") for (int i = 0; i < 32; ++i)
+        if (i < ncols) po[i] = __float2bfloat16(v[i]);
     }
   }
   if (p.act != FFVC_ACT_NONE) {
@@ -151,7 +152,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
         }
       }
     } else {
-      for (int i = 0; i < ncols; ++i) v[i] *= apply_act_grad(__bfloat162float(ax[i]), p.mul_mode);
+      _Pragma("unroll") for (int i = 0; i < 32; ++i)
+        if (i < ncols) v[i] *= apply_act_grad(__bfloat162float(ax[i]), p.mul_mode);
     }
   }
   if (p.res != nullptr) {
@@ -169,7 +171,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
         }
       }
     } else {
-      for (int i = 0; i < ncols; ++i) v[i] += __bfloat162float(rs[i]);
+      _Pragma("unroll") for (int i = 0; i < 32; ++i)
+        if (i < ncols) v[i] += __bfloat162float(rs[i]);
     }
   }
   if (p.out_fp32) {
@@ -182,7 +185,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
 #pragma unroll
       for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     } else {
-      for (int i = 0; i < ncols; ++i) o[i] = v[i];
+      _Pragma("unroll") for (int i = 0; i < 32; ++i)
+        if (i < ncols) o[i] = v[i];
     }
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
@@ -190,7 +194,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
 #pragma unroll
       for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(o + i) = pack_bf16x8(v + i);
     } else {
-      for (int i = 0; i < ncols; ++i) o[i] = __float2bfloat16(v[i]);
+      _Pragma("unroll") for (int i = 0; i < 32; ++i)
+        if (i < ncols) o[i] = __float2bfloat16(v[i]);
     }
   }
 }

@@ -98,14 +98,14 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  optional dx += add (residual path);
 // optional dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (fp32 atomics, one per column per CTA).
 template <int kMaxV>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                            const __nv_bfloat16* __restrict__ x,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ mean,
-                                                            const float* __restrict__ rstd,
-                                                            const __nv_bfloat16* __restrict__ add,
-                                                            __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, long long rows, int D) {
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                               const __nv_bfloat16* __restrict__ x,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const __nv_bfloat16* __restrict__ add,
+                                                               __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                               float* __restrict__ dbeta, long long rows, int D) {
   extern __shared__ float sm[];  // [2][D] when dgamma != nullptr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
@@ -124,25 +124,34 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
     const uint4* dr = reinterpret_cast<const uint4*>(dy + row * D);
     const float mu = mean[row], rs = rstd[row];
-    float xh[kMaxV][8], g[kMaxV][8];
+    // the row stays packed (bf16) in registers between the two passes: 8 registers per 16 values instead of 16
+    uint4 xp[kMaxV], dp[kMaxV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
+        xp[i] = xr[c];
+        dp[i] = dr[c];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
         float xv[8], dv[8];
-        unpack8(xr[c], xv);
-        unpack8(dr[c], dv);
+        unpack8(xp[i], xv);
+        unpack8(dp[i], dv);
         const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mu) * rs;
-          g[i][j] = dv[j] * gg[j];
-          s1 += g[i][j];
-          s2 += g[i][j] * xh[i][j];
+          const float xh = (xv[j] - mu) * rs;
+          const float g = dv[j] * gg[j];
+          s1 += g;
+          s2 += g * xh;
           if (wgrad) {
-            accg[i][j] += dv[j] * xh[i][j];
+            accg[i][j] += dv[j] * xh;
             accb[i][j] += dv[j];
           }
         }
@@ -156,9 +165,16 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     for (int i = 0; i < kMaxV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
-        float o[8];
+        float xv[8], dv[8], o[8];
+        unpack8(xp[i], xv);
+        unpack8(dp[i], dv);
+        const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xv[j] - mu) * rs;
+          o[j] = rs * (dv[j] * gg[j] - s1 - xh * s2);
+        }
         if (ar) {
           float av[8];
           unpack8(ar[c], av);
@@ -431,7 +447,7 @@ extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* ga
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int wpb = 8;
   long long want = (rows + wpb - 1) / wpb;
-  const unsigned grid = (unsigned)(want < 148 * 4 ? want : 148 * 4);
+  const unsigned grid = (unsigned)(want < 148 * 2 ? want : 148 * 2);
   const size_t smem = dgamma ? 2 * D * sizeof(float) : 0;
   auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);

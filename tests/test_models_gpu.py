@@ -71,6 +71,12 @@ def test_mixer_forward_backward_vs_oracle(cfg, B):
     (yr * w).sum().backward()
     bad = []
     for n, p in net.named_parameters():
+        if n.endswith(".0.fn.3.bias"):
+            # d(loss)/d(token-mix output bias) is analytically ZERO: the bias adds a per-token constant over the
+            # channel axis, and every consumer of the residual stream starts with a LayerNorm over that axis.  The
+            # oracle gives ~1e-5 (fp32 noise); the bf16 path gives rounding noise of the summed gradient.  Bound it.
+            assert p.grad.abs().max().item() < 1.0, (n, p.grad.abs().max().item())
+            continue
         c = cos(p.grad, sd_ref[n].grad)
         ref_g = sd_ref[n].grad
         err = (p.grad.detach().float().cpu() - ref_g).abs().max().item()
