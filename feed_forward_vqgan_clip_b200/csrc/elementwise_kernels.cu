@@ -375,6 +375,41 @@ __global__ void __launch_bounds__(256) conv3x3_smallcin_kernel(const float* __re
   }
 }
 
+// ---------------------------------------------------------------- im2col for a 3-channel 3x3 conv (dgrad of conv_out on tensor cores)
+// x: [N][H][W][3] fp32 -> col: [N*H*W][32] bf16, col[p][tap*3 + c] = x[pixel p shifted by tap][c] (zero outside / for k >= 27)
+__global__ void __launch_bounds__(256) im2col3x3_cin3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int N,
+                                                             int H, int W) {
+  const long long total = (long long)N * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % W);
+    const int py = (int)((i / W) % H);
+    const int n = (int)(i / ((long long)W * H));
+    float v[32];
+#pragma unroll
+    for (int k = 27; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = py + t / 3 - 1, xx = px + t % 3 - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const float* src = x + (((long long)n * H + yy) * W + xx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[t * 3 + c] = ok ? src[c] : 0.f;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(col + i * 32);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 o;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]), h1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]), h3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
+      o.x = *reinterpret_cast<uint32_t*>(&h0);
+      o.y = *reinterpret_cast<uint32_t*>(&h1);
+      o.z = *reinterpret_cast<uint32_t*>(&h2);
+      o.w = *reinterpret_cast<uint32_t*>(&h3);
+      dst[q] = o;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- fused Adam (torch.optim.Adam defaults, main.py:591,835)
 // p,g,m,v fp32 flat arenas; also refreshes the bf16 shadow the GEMMs read.  grad_scale folds the DP average.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -584,6 +619,11 @@ extern "C" int ffvc_adam_step(float* p, const float* g, float* m, float* v, void
                               const float* hyper_dev, void* stream) {
   if (!hyper_dev) return set_error(FFVC_ERR_ARG, "adam: hyper-parameter block is null");
   adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(p, g, m, v, BF(shadow_bf16), n, hyper_dev);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_im2col3x3_cin3(const float* x, void* col, int N, int H, int W, void* stream) {
+  im2col3x3_cin3_kernel<<<grid_for((long long)N * H * W, 256), 256, 0, ST(stream)>>>(x, BF(col), N, H, W);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

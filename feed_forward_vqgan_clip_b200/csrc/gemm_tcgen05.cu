@@ -37,7 +37,7 @@ static constexpr int kBlockK = 64;
 static constexpr int kStages = 4;
 static constexpr int kStageABytes = 256 * kBlockK * 2;      // up to 256 rows of A  (32 KB)
 static constexpr int kStageBytes = 48 * 1024;               // A (16|32 KB) + B (32|16 KB)
-static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/ + 2048 /*bias*/;
 static constexpr int kNumThreads = 320;
 static constexpr int kNumEpiWarps = 8;
 static constexpr int kTmemCols = 512;
@@ -96,84 +96,107 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
   return pk;
 }
 
-// fused epilogue on 32 consecutive columns of one output row
+// activation / activation-gradient on a 32-wide register chunk; the switch is hoisted out of the element loop so each
+// case is straight-line code (a per-element runtime branch costs more than the math)
+__device__ __forceinline__ void act_chunk(float (&v)[32], int act) {
+  if (act == FFVC_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+  } else if (act == FFVC_ACT_QUICKGELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = quick_gelu_f(v[i]);
+  } else if (act == FFVC_ACT_SWISH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = swish_f(v[i]);
+  }
+}
+__device__ __forceinline__ void mulgrad_chunk(float (&v)[32], const float (&x)[32], int act) {
+  if (act == FFVC_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(x[i]);
+  } else if (act == FFVC_ACT_QUICKGELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= quick_gelu_grad_f(x[i]);
+  } else if (act == FFVC_ACT_SWISH) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= swish_grad_f(x[i]);
+  }
+}
+__device__ __forceinline__ void unpack_bf16x32(const uint4 (&pk)[4], float (&f)[32]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[q]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __bfloat1622float2(h[j]);
+      f[q * 8 + 2 * j] = t.x;
+      f[q * 8 + 2 * j + 1] = t.y;
+    }
+  }
+}
+
+// fused epilogue on 32 consecutive columns of one output row.
+//   sbias : column bias of this tile staged in shared memory (already offset to this chunk), or nullptr
+//   pf_aux / pf_res : aux / residual of this chunk prefetched into registers (valid when `vec` is true)
 __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[32], int gn0, long long off, float rbias,
-                                               bool vec_ok) {
+                                               bool vec, const float* sbias, const uint4 (&pf_aux)[4],
+                                               const uint4 (&pf_res)[4]) {
   const int ncols = min(32, p.N - gn0);
   float v[32];
+  if (p.alpha != 1.0f) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  }
   if (p.bias_mode == 1) {
-    if (ncols == 32) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        const float4 b4 = *reinterpret_cast<const float4*>(p.bias + gn0 + i);
-        v[i] += b4.x;
-        v[i + 1] += b4.y;
-        v[i + 2] += b4.z;
-        v[i + 3] += b4.w;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < ncols) v[i] += p.bias[gn0 + i];
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + i);   // smem broadcast; zero beyond N
+      v[i] += b4.x;
+      v[i + 1] += b4.y;
+      v[i + 2] += b4.z;
+      v[i + 3] += b4.w;
     }
   } else if (p.bias_mode == 2) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += rbias;
   }
-  const bool full_vec = vec_ok && (ncols == 32);
   if (p.pre_out != nullptr) {
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(p.pre_out) + off;
-    if (full_vec) {
+    if (vec) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(po + i) = pack_bf16x8(v + i);
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i)
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
         if (i < ncols) po[i] = __float2bfloat16(v[i]);
     }
   }
-  if (p.act != FFVC_ACT_NONE) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = apply_act(v[i], p.act);
-  }
+  act_chunk(v, p.act);
   if (p.mul_mode != FFVC_ACT_NONE) {
-    const __nv_bfloat16* ax = p.aux + off;
-    if (full_vec) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(ax + i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          v[i + 2 * j] *= apply_act_grad(f.x, p.mul_mode);
-          v[i + 2 * j + 1] *= apply_act_grad(f.y, p.mul_mode);
-        }
-      }
+    float x[32];
+    if (vec) {
+      unpack_bf16x32(pf_aux, x);
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i)
-        if (i < ncols) v[i] *= apply_act_grad(__bfloat162float(ax[i]), p.mul_mode);
+      const __nv_bfloat16* ax = p.aux + off;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = (i < ncols) ? __bfloat162float(ax[i]) : 0.f;
     }
+    mulgrad_chunk(v, x, p.mul_mode);
   }
   if (p.res != nullptr) {
-    const __nv_bfloat16* rs = p.res + off;
-    if (full_vec) {
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(rs + i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __bfloat1622float2(h[j]);
-          v[i + 2 * j] += f.x;
-          v[i + 2 * j + 1] += f.y;
-        }
-      }
+    float x[32];
+    if (vec) {
+      unpack_bf16x32(pf_res, x);
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i)
-        if (i < ncols) v[i] += __bfloat162float(rs[i]);
+      const __nv_bfloat16* rs = p.res + off;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = (i < ncols) ? __bfloat162float(rs[i]) : 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += x[i];
   }
   if (p.out_fp32) {
     float* o = reinterpret_cast<float*>(p.out) + off;
@@ -185,16 +208,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
 #pragma unroll
       for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i)
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
         if (i < ncols) o[i] = v[i];
     }
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-    if (full_vec) {
+    if (vec) {
 #pragma unroll
       for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(o + i) = pack_bf16x8(v + i);
     } else {
-      _Pragma("unroll") for (int i = 0; i < 32; ++i)
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
         if (i < ncols) o[i] = __float2bfloat16(v[i]);
     }
   }
@@ -213,6 +238,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+  const uint32_t bias_smem = bar_base + 128u;   // [2][256] floats, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -367,6 +393,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;       // 0 / 1: column half (tile_m 128) or row sub-tile (tile_m 256)
+    const int etid = threadIdx.x - 64;      // 0..255 among the epilogue threads
     const int row_in_tile = (p.tile_m == 256 ? half * 128 : 0) + q * 32 + lane;
     // columns this warp covers inside the tile
     int c_begin, c_end, tmem_col0;
@@ -380,9 +407,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       c_end = (p.block_n >= 64) ? c_begin + hcols : (half == 0 ? p.block_n : 0);
       tmem_col0 = 0;
     }
+    float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));  // [2][256] floats
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 8 == 0) && (p.out_bs % 8 == 0) && (p.out_bs_inner % 8 == 0);
+    const bool want_aux = p.mul_mode != FFVC_ACT_NONE, want_res = p.res != nullptr;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int rem = (int)(t % tiles_all_batches);
       const int bi = rem / tiles_per_batch;
@@ -391,17 +420,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int gm = tm * p.tile_m + row_in_tile;
       const int n0 = tn * p.block_n;
       const int bi_in = bi % p.batch_inner, bi_out = bi / p.batch_inner;
+      const long long row_off = (long long)bi_out * p.out_bs + (long long)bi_in * p.out_bs_inner + (long long)gm * p.ldc;
+      const bool row_ok = gm < p.M;
+      float* sbias = sbias_all + acc * 256;
+      // stage this tile's column bias in shared memory (double-buffered with the accumulator stage) and prefetch the first
+      // chunk's aux / residual: all of it overlaps the wait for the MMA warp
+      if (p.bias_mode == 1) {
+        if (etid < p.block_n) sbias[etid] = (n0 + etid < p.N) ? p.bias[n0 + etid] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      const float rbias = (p.bias_mode == 2 && row_ok) ? p.bias[gm] : 0.0f;
+      uint4 pf_aux[4], pf_res[4];
+      auto prefetch = [&](int c) {
+        const int gn0 = n0 + c;
+        if (row_ok && vec_ok && gn0 + 32 <= p.N) {
+          if (want_aux) {
+            const uint4* ax = reinterpret_cast<const uint4*>(p.aux + row_off + gn0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pf_aux[j] = ax[j];
+          }
+          if (want_res) {
+            const uint4* rs = reinterpret_cast<const uint4*>(p.res + row_off + gn0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pf_res[j] = rs[j];
+          }
+        }
+      };
+      if (c_begin < c_end) prefetch(c_begin);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const long long row_off = (long long)bi_out * p.out_bs + (long long)bi_in * p.out_bs_inner + (long long)gm * p.ldc;
-      const float rbias = (p.bias_mode == 2 && gm < p.M) ? p.bias[gm] : 0.0f;
       for (int c = c_begin; c < c_end; c += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + (uint32_t)(acc * 256 + tmem_col0 + c) + ((uint32_t)(q * 32) << 16);
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
         const int gn0 = n0 + c;
-        if (gm < p.M && gn0 < p.N) epilogue_chunk(p, r, gn0, row_off + gn0, rbias, vec_ok);
+        uint4 cur_aux[4], cur_res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          cur_aux[j] = pf_aux[j];
+          cur_res[j] = pf_res[j];
+        }
+        if (c + 32 < c_end) prefetch(c + 32);
+        if (row_ok && gn0 < p.N)
+          epilogue_chunk(p, r, gn0, row_off + gn0, rbias, vec_ok && (gn0 + 32 <= p.N), sbias + c, cur_aux, cur_res);
         __syncwarp();
       }
       // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp
@@ -631,8 +693,6 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   p.act = g->act;
   p.mul_mode = g->aux ? g->mul_mode : 0;
   p.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
-  if (p.bias_mode == 1 && (reinterpret_cast<uintptr_t>(g->bias) % 16 != 0))
-    return set_error(FFVC_ERR_ARG, "gemm: column bias must be 16-byte aligned");
 
   const long long tiles = (long long)((g->M + tile_m - 1) / tile_m) * ((g->N + block_n - 1) / block_n) * batch * splits;
   const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);

@@ -161,7 +161,11 @@ class DecoderEngine:
                     if co % 64 == 0:   # dgrad pack: [ci][flipped tap][co]
                         self.pk[name + ".wT"] = v.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous().to(BF16)
                     else:              # conv_out: dgrad runs on the tiny-Cin SIMT kernel, fp32 [ci][flipped tap][co]
-                        self.pk[name + ".wT32"] = v.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous().float()
+                        wt = v.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous().float()
+                        self.pk[name + ".wT32"] = wt
+                        wp = torch.zeros(ci, 32, device=wt.device, dtype=F32)      # K padded 27 -> 32 for the GEMM form
+                        wp[:, :9 * co] = wt
+                        self.pk[name + ".wTp"] = wp.to(BF16)
                 elif kh == 1:
                     self.pk[name + ".w"] = v.reshape(co, ci).contiguous().to(BF16)
                 self.pk[name + ".b"] = sd[name + ".bias"].float().contiguous()
@@ -346,8 +350,10 @@ class DecoderEngine:
                 call("image_post_bwd", g, dimg, gd, N * HW * 3)
             else:
                 gd = g
+            col = self._new(N * HW, 32)
+            call("im2col3x3_cin3", gd, col, N, H, W)
             da = self._new(N * HW, c)
-            call("conv3x3_cin3", gd, self.pk["decoder.conv_out.wT32"], da, N, H, W, c)
+            ops.gemm(col, self.pk["decoder.conv_out.wTp"], da, N * HW, c, 32)
             return self.gn_bwd(da, x_last, st, "decoder.norm_out", N, HW, c, True)
 
         tape.append(out_bwd)

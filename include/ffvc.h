@@ -145,6 +145,10 @@ int ffvc_image_post_bwd(const float* g, const float* d, float* gd, long long n, 
 /* 3x3 conv, Cin = 3 (fp32 NHWC in, [COUT][9][3] fp32 weights, bf16 NHWC out): dgrad of the decoder's conv_out. */
 int ffvc_conv3x3_cin3(const float* x, const float* w, void* y, int N, int H, int W, int COUT, void* stream);
 
+/* im2col of a 3-channel NHWC fp32 image for a 3x3 / pad-1 conv: col[p][tap*3+c], 32 bf16 per pixel (k >= 27 zero), so the
+ * dgrad of conv_out runs as a tcgen05 GEMM with K = 32. */
+int ffvc_im2col3x3_cin3(const float* x, void* col, int N, int H, int W, void* stream);
+
 /* fused Adam (torch.optim.Adam semantics, main.py:591,835) over a flat fp32 arena; refreshes the bf16 shadow. */
 /* hyper_dev: DEVICE float[16] = {lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale, weight_decay, t, ...}
  * (device-resident so a captured CUDA graph sees each step's values).  ffvc_adam_tick increments t and refreshes

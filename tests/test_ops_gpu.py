@@ -180,6 +180,14 @@ def test_image_post_and_conv_cin3():
     call("conv3x3_cin3", gy, wT, out, N, H, W, CO)
     ref = F.conv_transpose2d(gy.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
     close(out, ref)
+    # the same dgrad as im2col (K = 27 padded to 32) + tcgen05 GEMM — the form the decoder uses
+    col = torch.empty(N * H * W, 32, device=DEV, dtype=BF)
+    call("im2col3x3_cin3", gy, col, N, H, W)
+    wp = torch.zeros(CO, 32, device=DEV)
+    wp[:, :27] = wT
+    out2 = torch.empty(N * H * W, CO, device=DEV, dtype=BF)
+    ops.gemm(col, wp.to(BF), out2, N * H * W, CO, 32)
+    close(out2.view(N, H, W, CO), ref)
 
 
 def test_adam_matches_torch():

@@ -13,3 +13,12 @@ if [ "$1" == "ncu" ]; then
      python bench.py --no-graph --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_ncu.json 2> gpurun_out/bench_ncu.err
   echo "== ncu rc=$? lines=$(wc -l < gpurun_out/launches.csv)"
 fi
+if [ "$2" == "full" ]; then
+  # one --set full capture of 4 consecutive mixer-layer GEMMs (token-mix 1/2, channel-mix 1/2) + a decoder conv later
+  timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 42 -c 4 -o gpurun_out/prof_gemm_mixer \
+     python bench.py --no-graph --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/prof1.log 2>&1
+  echo "== ncu full mixer rc=$?"
+  timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 190 -c 3 -o gpurun_out/prof_gemm_conv \
+     python bench.py --no-graph --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/prof2.log 2>&1
+  echo "== ncu full conv rc=$?"
+fi
