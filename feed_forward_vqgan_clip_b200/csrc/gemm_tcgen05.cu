@@ -37,7 +37,7 @@ static constexpr int kBlockK = 64;
 static constexpr int kStages = 4;
 static constexpr int kStageABytes = 256 * kBlockK * 2;      // up to 256 rows of A  (32 KB)
 static constexpr int kStageBytes = 48 * 1024;               // A (16|32 KB) + B (32|16 KB)
-static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 128 /*barriers*/ + 2048 /*bias*/;
+static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/;
 static constexpr int kNumThreads = 320;
 static constexpr int kNumEpiWarps = 8;
 static constexpr int kTmemCols = 512;
@@ -225,43 +225,57 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
   }
 }
 
+// kTwoCta = false: one CTA per tile (128 or 256 rows).
+// kTwoCta = true : a CTA PAIR (cluster of 2, cta_group::2) per 256-row tile — each CTA stages its own 128 rows of A and
+//   HALF of the B tile; the leader CTA issues tcgen05.mma M=256 that reads both CTAs' shared memory, so every SM
+//   reads / is written only (A + B/2) per k-step instead of (A + B): the 1-CTA kernel is shared-memory-bandwidth
+//   bound (128 B/clk/SM) at ~55-65 % of the tensor pipe, the pair removes a third of that traffic.  6-stage ring.
+template <bool kTwoCta>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmDev p) {
+  constexpr int kStagesT = kTwoCta ? 6 : kStages;
+  constexpr int kStageBytesT = kTwoCta ? 32 * 1024 : kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * kStageBytes;
-  // barrier layout (8 bytes each): full[4], empty[4], tmem_full[2], tmem_empty[2], then tmem ptr slot
+  const uint32_t bar_base = smem_base + kStages * kStageBytes;   // same offset for both variants (6*32 KB == 4*48 KB)
+  // barrier layout (8 bytes each): full[6], empty[6], tmem_full[2], tmem_empty[2], then tmem ptr slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
-  const uint32_t bias_smem = bar_base + 128u;   // [2][256] floats, 16-byte aligned
+  auto empty_bar = [&](int s) { return bar_base + 8u * (6 + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (12 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (14 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * 16;
+  const uint32_t bias_smem = bar_base + 256u;   // [2][256] floats, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = kTwoCta ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kStagesT; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kNumEpiWarps);
+      mbar_init(tempty_bar(a), kTwoCta ? 2 * kNumEpiWarps : kNumEpiWarps);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (kTwoCta) {
+      tmem_alloc_2sm(tmem_slot, kTmemCols);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kTwoCta) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -272,7 +286,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int total_kb = p.kb_per_seg * p.k_segs;
   const long long tiles_all_batches = (long long)tiles_per_batch * p.batch;
   const long long total_tiles = tiles_all_batches * p.splits;
-  const uint32_t a_bytes = (uint32_t)p.tile_m * kBlockK * 2;
+  const long long tile_first = kTwoCta ? (blockIdx.x >> 1) : blockIdx.x;
+  const long long tile_step = kTwoCta ? (gridDim.x >> 1) : gridDim.x;
+  const int rows_cta = kTwoCta ? 128 : p.tile_m;             // rows of A this CTA stages
+  const int bn_cta = kTwoCta ? (p.block_n >> 1) : p.block_n;  // rows of B this CTA stages
+  const uint32_t a_bytes = (uint32_t)rows_cta * kBlockK * 2;
   const uint32_t b_off = a_bytes;  // B follows A inside a stage
 
   if (warp == 0) {
@@ -280,14 +298,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const uint32_t b_bytes = (uint32_t)bn_cta * kBlockK * 2;
+      auto tma4 = [&](uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2, int c3) {
+        if (kTwoCta) tma_load_4d_2sm(dst, desc, bar, c0, c1, c2, c3);
+        else tma_load_4d(dst, desc, bar, c0, c1, c2, c3);
+      };
+      for (long long t = tile_first; t < total_tiles; t += tile_step) {
         const int split = (int)(t / tiles_all_batches);
         const int rem = (int)(t % tiles_all_batches);
         const int bi = rem / tiles_per_batch;
         const int tm = (rem % tiles_per_batch) / tiles_n;
         const int tn = rem % tiles_n;
-        const int m0 = tm * p.tile_m, n0 = tn * p.block_n;
+        const int m0 = tm * p.tile_m + (kTwoCta ? (int)rank * 128 : 0);
+        const int n0 = tn * p.block_n + (kTwoCta ? (int)rank * bn_cta : 0);
         const int bi_in = bi % p.batch_inner, bi_out = bi / p.batch_inner;
         const int kb_begin = (int)((long long)total_kb * split / p.splits);
         const int kb_end = (int)((long long)total_kb * (split + 1) / p.splits);
@@ -302,10 +325,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sa = smem_base + stage * kStageBytesT;
           const uint32_t sb = sa + b_off;
           const uint32_t fb = full_bar(stage);
-          mbar_expect_tx(fb, a_bytes + b_bytes);
+          if (!kTwoCta) mbar_expect_tx(fb, a_bytes + b_bytes);
+          else if (rank == 0) mbar_expect_tx(fb, 2u * (a_bytes + b_bytes));   // both CTAs' loads land on the leader's barrier
           const int seg = kb / p.kb_per_seg;
           const int kk = kb % p.kb_per_seg;
           const int k0 = kk * kBlockK;
@@ -313,14 +337,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           if (p.a_mode == FFVC_OP_CONV3X3) {
             const int tap = kk / p.conv_cblocks;
             const int c0 = (kk % p.conv_cblocks) * kBlockK;
-            tma_load_4d(sa, &tmap_a, fb, c0, cx0 + (tap % 3 - 1), cy0 + (tap / 3 - 1), cimg);
+            tma4(sa, &tmap_a, fb, c0, cx0 + (tap % 3 - 1), cy0 + (tap / 3 - 1), cimg);
           } else {
             const int c2 = (p.a_role == FFVC_ROLE_OUT_BATCH) ? bi_in : 0;
             const int c3 = (p.a_role == FFVC_ROLE_OUT_BATCH) ? bi_out : (p.a_role == FFVC_ROLE_K_SEGMENT ? seg : 0);
             if (p.a_mode == FFVC_OP_KMAJOR) {
-              tma_load_4d(sa, &tmap_a, fb, k0, m0, c2, c3);
+              tma4(sa, &tmap_a, fb, k0, m0, c2, c3);
             } else {
-              for (int j = 0; j < p.tile_m / 64; ++j) tma_load_4d(sa + j * 8192, &tmap_a, fb, m0 + 64 * j, k0, c2, c3);
+              for (int j = 0; j < rows_cta / 64; ++j) tma4(sa + j * 8192, &tmap_a, fb, m0 + 64 * j, k0, c2, c3);
             }
           }
           // ---- B
@@ -328,12 +352,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int c2 = (p.b_role == FFVC_ROLE_OUT_BATCH) ? bi_in : 0;
             const int c3 = (p.b_role == FFVC_ROLE_OUT_BATCH) ? bi_out : (p.b_role == FFVC_ROLE_K_SEGMENT ? seg : 0);
             if (p.b_mode == FFVC_OP_KMAJOR) {
-              tma_load_4d(sb, &tmap_b, fb, k0, n0, c2, c3);
+              tma4(sb, &tmap_b, fb, k0, n0, c2, c3);
             } else {
-              for (int j = 0; j < p.block_n / 64; ++j) tma_load_4d(sb + j * 8192, &tmap_b, fb, n0 + 64 * j, k0, c2, c3);
+              for (int j = 0; j < bn_cta / 64; ++j) tma4(sb + j * 8192, &tmap_b, fb, n0 + 64 * j, k0, c2, c3);
             }
           }
-          if (++stage == kStages) {
+          if (++stage == kStagesT) {
             stage = 0;
             phase ^= 1u;
           }
@@ -341,21 +365,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(p.block_n, p.a_mode == FFVC_OP_MNMAJOR, p.b_mode == FFVC_OP_MNMAJOR);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only in 2-CTA mode)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16_m(kTwoCta ? 256 : 128, p.block_n, p.a_mode == FFVC_OP_MNMAJOR,
+                                               p.b_mode == FFVC_OP_MNMAJOR);
       // K-major : 8-row groups 1024 B apart (SBO), one swizzle atom along K (LBO unused), K step = 32 B
       // MN-major: 64-wide MN chunks 8192 B apart (LBO), 8-k-row groups 1024 B apart (SBO), K step = 2048 B
       const uint32_t a_lbo = (p.a_mode == FFVC_OP_MNMAJOR) ? 8192u : 16u;
       const uint32_t b_lbo = (p.b_mode == FFVC_OP_MNMAJOR) ? 8192u : 16u;
       const uint32_t a_kstep = (p.a_mode == FFVC_OP_MNMAJOR) ? 2048u : 32u;
       const uint32_t b_kstep = (p.b_mode == FFVC_OP_MNMAJOR) ? 2048u : 32u;
-      const int subs = p.tile_m / 128;
+      const int subs = kTwoCta ? 1 : p.tile_m / 128;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (long long t = tile_first; t < total_tiles; t += tile_step) {
         const int split = (int)(t / tiles_all_batches);
         const int kb_begin = (int)((long long)total_kb * split / p.splits);
         const int kb_end = (int)((long long)total_kb * (split + 1) / p.splits);
@@ -365,24 +390,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * kStageBytes;
+          const uint32_t sa = smem_base + stage * kStageBytesT;
           const uint32_t sb = sa + b_off;
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t db = umma_smem_desc_sw128(sb + k * b_kstep, b_lbo, 1024u);
             const uint32_t accum = (kb > kb_begin || k > 0) ? 1u : 0u;
-            for (int sub = 0; sub < subs; ++sub) {
-              const uint64_t da = umma_smem_desc_sw128(sa + sub * 16384 + k * a_kstep, a_lbo, 1024u);
-              umma_bf16(tmem_d + sub * 128, da, db, idesc, accum);
+            if (kTwoCta) {
+              umma_bf16_2sm(tmem_d, umma_smem_desc_sw128(sa + k * a_kstep, a_lbo, 1024u), db, idesc, accum);
+            } else {
+              for (int sub = 0; sub < subs; ++sub) {
+                const uint64_t da = umma_smem_desc_sw128(sa + sub * 16384 + k * a_kstep, a_lbo, 1024u);
+                umma_bf16(tmem_d + sub * 128, da, db, idesc, accum);
+              }
             }
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-          if (++stage == kStages) {
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if (kTwoCta) umma_commit_2sm(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+          if (++stage == kStagesT) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if (kTwoCta) umma_commit_2sm(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -392,12 +423,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // 0 / 1: column half (tile_m 128) or row sub-tile (tile_m 256)
+    const int half = (warp - 2) >> 2;       // 0 / 1: column half (128-row CTA tile) or row sub-tile (256-row 1-CTA tile)
     const int etid = threadIdx.x - 64;      // 0..255 among the epilogue threads
-    const int row_in_tile = (p.tile_m == 256 ? half * 128 : 0) + q * 32 + lane;
+    const bool two_sub = !kTwoCta && p.tile_m == 256;
+    const int row_in_tile = (kTwoCta ? (int)rank * 128 : 0) + (two_sub ? half * 128 : 0) + q * 32 + lane;
     // columns this warp covers inside the tile
     int c_begin, c_end, tmem_col0;
-    if (p.tile_m == 256) {
+    if (two_sub) {
       c_begin = 0;
       c_end = p.block_n;
       tmem_col0 = half * 128;
@@ -412,7 +444,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 8 == 0) && (p.out_bs % 8 == 0) && (p.out_bs_inner % 8 == 0);
     const bool want_aux = p.mul_mode != FFVC_ACT_NONE, want_res = p.res != nullptr;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (long long t = tile_first; t < total_tiles; t += tile_step) {
       const int rem = (int)(t % tiles_all_batches);
       const int bi = rem / tiles_per_batch;
       const int tm = (rem % tiles_per_batch) / tiles_n;
@@ -466,10 +498,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           epilogue_chunk(p, r, gn0, row_off + gn0, rbias, vec_ok && (gn0 + 32 <= p.N), sbias + c, cur_aux, cur_res);
         __syncwarp();
       }
-      // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp
+      // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp (of the leader CTA)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (kTwoCta) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -478,10 +512,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kTwoCta) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kTwoCta) tmem_dealloc_2sm(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -562,7 +596,9 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     if (g_num_sms <= 0) return set_error(FFVC_ERR_CUDA, "gemm: no CUDA device");
   }
   if (!g_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
     g_attr_set = true;
   }
@@ -589,8 +625,23 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     const long long t256 = (long long)((g->M + 255) / 256) * ((g->N + block_n - 1) / block_n) * batch * splits;
     tile_m = (block_n <= 128 && g->M >= 256 && t256 >= g_num_sms) ? 256 : 128;
   }
+  // ---- CTA-pair (cta_group::2) variant: 256-row pair tiles, block_n 128 / 256; auto-selected for large problems
+  int two_cta = g->two_cta;   // 0 auto, 1 force, -1 never
+  if (two_cta == 0) {
+    const int bn2 = g->N > 128 ? 256 : 128;
+    const long long pair_tiles = (long long)((g->M + 255) / 256) * ((g->N + bn2 - 1) / bn2) * batch * splits;
+    const bool conv_ok = g->a_mode != FFVC_OP_CONV3X3 || (((long long)g->conv_h * g->conv_w) % 256 == 0);
+    two_cta = (g->block_n <= 0 && g->tile_m <= 0 && g->M >= 256 && g->N >= 128 && conv_ok && pair_tiles >= g_num_sms / 2) ? 1 : -1;
+  }
+  if (two_cta == 1) {
+    if (g->block_n <= 0) block_n = g->N > 128 ? 256 : 128;
+    if (block_n != 128 && block_n != 256) return set_error(FFVC_ERR_ARG, "gemm: the CTA-pair kernel needs block_n 128 or 256");
+    tile_m = 256;
+  }
   if (tile_m != 128 && tile_m != 256) return set_error(FFVC_ERR_ARG, "gemm: tile_m must be 128 or 256");
-  if (tile_m == 256 && block_n > 128) return set_error(FFVC_ERR_ARG, "gemm: tile_m 256 needs block_n <= 128");
+  if (two_cta != 1 && tile_m == 256 && block_n > 128) return set_error(FFVC_ERR_ARG, "gemm: tile_m 256 needs block_n <= 128");
+  const int rows_cta = (two_cta == 1) ? 128 : tile_m;          // A rows staged per CTA
+  const int bn_cta = (two_cta == 1) ? block_n / 2 : block_n;   // B rows staged per CTA
 
   GemmDev p;
   memset(&p, 0, sizeof(p));
@@ -613,10 +664,14 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   if (g->a_mode == FFVC_OP_CONV3X3) {
     const int H = g->conv_h, W = g->conv_w, C = g->conv_c;
     if (H <= 0 || W <= 0 || C <= 0 || C % 64 != 0) return set_error(FFVC_ERR_ARG, "conv: Cin must be a multiple of 64");
-    if (tile_m == 256 && ((long long)H * W) % 256 != 0) tile_m = p.tile_m = 128;
-    const int tile_w = W < tile_m ? W : tile_m;
-    if (tile_m % tile_w != 0 || W % tile_w != 0) return set_error(FFVC_ERR_ARG, "conv: W must divide or be a multiple of the pixel tile");
-    const int tile_h = tile_m / tile_w;
+    if (tile_m == 256 && ((long long)H * W) % 256 != 0) {
+      if (two_cta == 1) return set_error(FFVC_ERR_ARG, "conv: the CTA-pair kernel needs H*W % 256 == 0");
+      tile_m = p.tile_m = 128;
+    }
+    const int ptile = (two_cta == 1) ? 128 : tile_m;           // pixels staged per CTA
+    const int tile_w = W < ptile ? W : ptile;
+    if (ptile % tile_w != 0 || W % tile_w != 0) return set_error(FFVC_ERR_ARG, "conv: W must divide or be a multiple of the pixel tile");
+    const int tile_h = ptile / tile_w;
     if (H % tile_h != 0) return set_error(FFVC_ERR_ARG, "conv: H*W must tile by the pixel tile");
     const long long npix = (long long)g->conv_n * H * W;
     if (npix != g->M) return set_error(FFVC_ERR_ARG, "conv: M must equal N_img*H*W");
@@ -644,7 +699,7 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     if (g->a_mode == FFVC_OP_KMAJOR) {
       uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->M, n_in, n_out};
       uint64_t str[4] = {1, (uint64_t)g->a_ld, s_in, s_out};
-      uint32_t box[4] = {64, (uint32_t)tile_m, 1, 1};
+      uint32_t box[4] = {64, (uint32_t)rows_cta, 1, 1};
       if ((rc = make_tmap(&ta, g->a, 4, dims, str, box)) != FFVC_OK) return rc;
     } else {
       uint64_t dims[4] = {(uint64_t)g->M, (uint64_t)g->K, n_in, n_out};
@@ -668,7 +723,7 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     if (g->b_mode == FFVC_OP_KMAJOR) {
       uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->N, n_in, n_out};
       uint64_t str[4] = {1, (uint64_t)g->b_ld, s_in, s_out};
-      uint32_t box[4] = {64, (uint32_t)block_n, 1, 1};
+      uint32_t box[4] = {64, (uint32_t)bn_cta, 1, 1};
       if ((rc = make_tmap(&tb, g->b, 4, dims, str, box)) != FFVC_OK) return rc;
     } else {
       uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->K, n_in, n_out};
@@ -695,9 +750,30 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   p.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
 
   const long long tiles = (long long)((g->M + tile_m - 1) / tile_m) * ((g->N + block_n - 1) / block_n) * batch * splits;
-  const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-  gemm_tcgen05_kernel<<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (two_cta == 1) {
+    // one CTA pair (cluster of 2) per tile, persistent over min(tiles, SMs/2) pairs
+    const long long pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ta, tb, p);
+    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+  } else {
+    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
+    gemm_tcgen05_kernel<false><<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, p);
+  }
+  e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   count_launch();
   return FFVC_OK;

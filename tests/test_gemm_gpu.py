@@ -187,3 +187,54 @@ def test_batch_inner_attention_heads():
     v = qkv[..., 2 * W:].float().reshape(Nn, T, Hh, dh).transpose(1, 2)
     refo = (Pp[..., :T].float() @ v).transpose(1, 2).reshape(Nn, T, W)
     _check(O, refo, 2e-2)
+
+
+# ------------------------------------------------------------------ CTA-pair (cta_group::2) kernel, forced
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 256, 256), (1024, 1024, 512), (300, 200, 136), (4096, 128, 1024)])
+def test_two_cta_kmajor(M, N, K):
+    a, b = _rand(M, K, seed=41), _rand(N, K, seed=42)
+    bias = torch.randn(N, device=DEV)
+    res = _rand(M, N, seed=43)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    pre = torch.empty_like(out)
+    ops.gemm(a, b, out, M, N, K, two_cta=1, bias=bias, res=res, act=ops.ACT_GELU, pre_out=pre)
+    ref_pre = a.float() @ b.float().t() + bias
+    _check(pre, ref_pre, 2e-2)
+    _check(out, F.gelu(ref_pre) + res.float(), 2e-2)
+
+
+def test_two_cta_mn_major_forms():
+    M, N, K = 512, 1024, 256        # dgrad: dX[m,k] = sum_n dY[m,n] W[n,k]
+    dy, w = _rand(M, N, seed=44), _rand(N, K, seed=45)
+    out = torch.empty(M, K, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(dy, w, out, M, K, N, b_mode=ops.MNMAJOR, b_ld=K, two_cta=1)
+    _check(out, dy.float() @ w.float(), 2e-2)
+    M, N, K = 1024, 512, 384        # wgrad: dW[n,k] = sum_m dY[m,n] X[m,k]
+    dy, x = _rand(M, N, seed=46), _rand(M, K, seed=47)
+    o2 = torch.zeros(N, K, device=DEV, dtype=torch.float32)
+    ops.gemm(dy, x, o2, N, K, M, a_mode=ops.MNMAJOR, b_mode=ops.MNMAJOR, a_ld=N, b_ld=K, atomic=True, splits=2, two_cta=1)
+    _check(o2, dy.float().t() @ x.float(), 1e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 256, 256), (1, 64, 64, 128, 128), (1, 256, 256, 64, 128)])
+def test_two_cta_conv3x3(n, h, w, cin, cout):
+    x = _rand(n, h, w, cin, seed=48)
+    wt = (_rand(cout, cin, 3, 3, seed=49).float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(cout, device=DEV)
+    res = _rand(n, h, w, cout, seed=50)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    out = torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(x, wp, out, n * h * w, cout, 9 * cin, a_mode=ops.CONV3X3, conv=(n, h, w, cin), bias=bias, res=res, two_cta=1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    _check(out, ref, 2e-2)
+
+
+def test_two_cta_batched_token_mix():
+    Bt, T, D, J = 4, 256, 512, 1024
+    w, h = _rand(J, T, seed=51), _rand(Bt, T, D, seed=52)
+    bias = torch.randn(J, device=DEV)
+    out = torch.empty(Bt, J, D, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(w, h, out, J, D, T, b_mode=ops.MNMAJOR, b_role=ops.ROLE_OUT, b_bs=T * D, b_ld=D, batch=Bt, out_bs=J * D, bias=bias,
+             bias_mode=2, act=ops.ACT_GELU, two_cta=1)
+    ref = F.gelu(torch.einsum("jt,btd->bjd", w.float(), h.float()) + bias[None, :, None])
+    _check(out, ref, 2e-2)

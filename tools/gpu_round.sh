@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi.txt 2>&1
 for f in test_gemm_gpu test_ops_gpu test_models_gpu; do
-  timeout -k 10 900 python -m pytest tests/$f.py -q -m gpu -p no:cacheprovider --tb=short 2>&1 | cut -c1-400 > gpurun_out/$f.log
+  timeout -k 10 300 python -m pytest tests/$f.py -q -m gpu -p no:cacheprovider --tb=short 2>&1 | cut -c1-400 > gpurun_out/$f.log
   echo "== $f: $(tail -1 gpurun_out/$f.log)"
 done
 timeout -k 10 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "== smoke rc=$? $(tail -1 gpurun_out/smoke.log)"
