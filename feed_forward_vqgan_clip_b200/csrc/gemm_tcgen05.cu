@@ -628,10 +628,11 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   // ---- CTA-pair (cta_group::2) variant: 256-row pair tiles, block_n 128 / 256; auto-selected for large problems
   int two_cta = g->two_cta;   // 0 auto, 1 force, -1 never
   if (two_cta == 0) {
-    const int bn2 = g->N > 128 ? 256 : 128;
-    const long long pair_tiles = (long long)((g->M + 255) / 256) * ((g->N + bn2 - 1) / bn2) * batch * splits;
+    // pair tiles are 256 x 256; with N <= 128 the pair's MMAs are too short (64 cycles) for the single issuing thread to
+    // hide its per-stage barrier round trip, so those shapes stay on the 1-CTA 256-row tile
+    const long long pair_tiles = (long long)((g->M + 255) / 256) * ((g->N + 255) / 256) * batch * splits;
     const bool conv_ok = g->a_mode != FFVC_OP_CONV3X3 || (((long long)g->conv_h * g->conv_w) % 256 == 0);
-    two_cta = (g->block_n <= 0 && g->tile_m <= 0 && g->M >= 256 && g->N >= 128 && conv_ok && pair_tiles >= g_num_sms / 2) ? 1 : -1;
+    two_cta = (g->block_n <= 0 && g->tile_m <= 0 && g->M >= 256 && g->N > 128 && conv_ok && pair_tiles >= g_num_sms / 4) ? 1 : -1;
   }
   if (two_cta == 1) {
     if (g->block_n <= 0) block_n = g->N > 128 ? 256 : 128;

@@ -158,7 +158,8 @@ class TrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: NCCL's watchdog thread may touch CUDA while we capture (world > 1)
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             body()
         return self
 
