@@ -206,6 +206,58 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
 }
 
 // ------------------------------------------------------------------------------------ GroupNorm
+// Per-thread 8-channel partial sums (s, q) -> per-group sums in shared memory sm[0..G) / sm[G..2G).
+// Channels are first combined per group in registers, then lanes of the warp that own the same channel vector
+// (vec_per_pix < 32) are folded with shuffles, so each warp issues one shared atomic per (vector, group).
+__device__ __forceinline__ void gn_fold_to_smem(float (&s)[8], float (&q)[8], float* sm, int G, int cpg, int vc,
+                                                int vec_per_pix) {
+  const int lane = threadIdx.x & 31;
+  if (vec_per_pix < 32) {
+    for (int o = vec_per_pix; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+      }
+    }
+    if (lane >= vec_per_pix) return;
+  }
+  if (cpg >= 8) {
+    float ss = 0.f, qq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ss += s[j];
+      qq += q[j];
+    }
+    const int g = (vc * 8) / cpg;
+    atomicAdd(&sm[g], ss);
+    atomicAdd(&sm[G + g], qq);
+  } else {
+    // cpg in {1, 2, 4}: fold neighbours with static register indices (no dynamic indexing -> no local memory)
+    if (cpg >= 2) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        s[j] += s[j + 1];
+        q[j] += q[j + 1];
+      }
+    }
+    if (cpg >= 4) {
+      s[0] += s[2];
+      q[0] += q[2];
+      s[4] += s[6];
+      q[4] += q[6];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j % cpg == 0) {
+        const int g = (vc * 8 + j) / cpg;
+        atomicAdd(&sm[g], s[j]);
+        atomicAdd(&sm[G + g], q[j]);
+      }
+    }
+  }
+}
+
 // x: NHWC bf16, G groups of cpg = C/G consecutive channels.  Statistics per (n, g) over HW*cpg elements.
 // Pass 1: partial (sum, sumsq) per CTA -> double atomics into ws[N*G*2].  C % 8 == 0.
 // Each thread owns one 8-channel vector column (fixed group set) and strides over pixels.
@@ -238,14 +290,7 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat1
         q[j] += v[j] * v[j];
       }
     }
-    if (pl < pstride) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = (vc * 8 + j) / cpg;
-        atomicAdd(&sm[g], s[j]);
-        atomicAdd(&sm[G + g], q[j]);
-      }
-    }
+    gn_fold_to_smem(s, q, sm, G, cpg, vc, vec_per_pix);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < G; i += blockDim.x) {
@@ -349,12 +394,7 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_stats_kernel(const __nv_bfl
         q[j] += g * xh;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (vc * 8 + j) / cpg;
-      atomicAdd(&sm[g], s[j]);
-      atomicAdd(&sm[G + g], q[j]);
-    }
+    gn_fold_to_smem(s, q, sm, G, cpg, vc, vec_per_pix);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < G; i += blockDim.x) {
