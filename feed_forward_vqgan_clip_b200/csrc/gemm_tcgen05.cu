@@ -37,8 +37,7 @@ static constexpr int kBlockK = 64;
 static constexpr int kStages = 4;
 static constexpr int kStageABytes = 256 * kBlockK * 2;      // up to 256 rows of A  (32 KB)
 static constexpr int kStageBytes = 48 * 1024;               // A (16|32 KB) + B (32|16 KB)
-static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/ +
-                                  8 * 2560 /*store staging: 8 epilogue warps*/;
+static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/;
 static constexpr int kNumThreads = 320;
 static constexpr int kNumEpiWarps = 8;
 static constexpr int kTmemCols = 512;
@@ -136,43 +135,12 @@ __device__ __forceinline__ void unpack_bf16x32(const uint4 (&pk)[4], float (&f)[
   }
 }
 
-// Coalesced bf16 row stores through a per-warp shared-memory staging tile.  Each lane holds 32 consecutive columns
-// (64 B) of ITS row; storing that directly makes every st.global.v4 touch 32 different 128-byte lines.  Instead the
-// warp parks the 32 x 64 B block in smem (80-byte row pitch: conflict-free) and re-reads it so that 4 lanes cover one
-// row: each st.global.v4 then writes 8 rows x 64 B contiguous segments (4x fewer LSU wavefronts).
-//   stage   : this warp's 32 x 80 B staging buffer (shared-space byte address)
-//   base    : output pointer of the warp's first row at this chunk's first column
-//   row_cnt : number of valid rows of this warp (rows >= row_cnt are not stored)
-__device__ __forceinline__ void store_chunk_staged(uint32_t stage, const float (&v)[32], __nv_bfloat16* base, long long ldc,
-                                                   int row_cnt, int lane) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 pk = pack_bf16x8(v + 8 * j);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + lane * 80 + j * 16), "r"(pk.x), "r"(pk.y), "r"(pk.z),
-                 "r"(pk.w)
-                 : "memory");
-  }
-  __syncwarp();
-  const int unit = lane & 3, r0 = lane >> 2;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int row = r0 + 8 * i;
-    uint4 pk;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pk.x), "=r"(pk.y), "=r"(pk.z), "=r"(pk.w) : "r"(stage + row * 80 + unit * 16));
-    if (row < row_cnt) *reinterpret_cast<uint4*>(base + (long long)row * ldc + unit * 8) = pk;
-  }
-  __syncwarp();
-}
-
 // fused epilogue on 32 consecutive columns of one output row.
 //   sbias : column bias of this tile staged in shared memory (already offset to this chunk), or nullptr
 //   pf_aux / pf_res : aux / residual of this chunk prefetched into registers (valid when `vec` is true)
-//   row_ok  : this lane's row is inside M (lanes with row_ok == false still take part in the warp-collective stores)
-//   stage / warp_base_off / row_cnt / lane : see store_chunk_staged (used when `vec`)
 __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[32], int gn0, long long off, float rbias,
                                                bool vec, const float* sbias, const uint4 (&pf_aux)[4],
-                                               const uint4 (&pf_res)[4], bool row_ok, uint32_t stage, long long warp_base_off,
-                                               int row_cnt, int lane) {
+                                               const uint4 (&pf_res)[4]) {
   const int ncols = min(32, p.N - gn0);
   float v[32];
   if (p.alpha != 1.0f) {
@@ -198,8 +166,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
   if (p.pre_out != nullptr) {
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(p.pre_out) + off;
     if (vec) {
-      store_chunk_staged(stage, v, reinterpret_cast<__nv_bfloat16*>(p.pre_out) + warp_base_off, p.ldc, row_cnt, lane);
-    } else if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(po + i) = pack_bf16x8(v + i);
+    } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (i < ncols) po[i] = __float2bfloat16(v[i]);
@@ -221,19 +190,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
     float x[32];
     if (vec) {
       unpack_bf16x32(pf_res, x);
-    } else if (row_ok) {
+    } else {
       const __nv_bfloat16* rs = p.res + off;
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = (i < ncols) ? __bfloat162float(rs[i]) : 0.f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] += x[i];
   }
   if (p.out_fp32) {
-    if (!row_ok) return;
     float* o = reinterpret_cast<float*>(p.out) + off;
     if (p.atomic) {
 #pragma unroll
@@ -250,8 +215,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
     if (vec) {
-      store_chunk_staged(stage, v, reinterpret_cast<__nv_bfloat16*>(p.out) + warp_base_off, p.ldc, row_cnt, lane);
-    } else if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(o + i) = pack_bf16x8(v + i);
+    } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (i < ncols) o[i] = __float2bfloat16(v[i]);
@@ -474,7 +440,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tmem_col0 = 0;
     }
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));  // [2][256] floats
-    const uint32_t stage_smem = bias_smem + 2048u + (uint32_t)(warp - 2) * 2560u;               // 32 rows x 80 B per warp
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 8 == 0) && (p.out_bs % 8 == 0) && (p.out_bs_inner % 8 == 0);
@@ -489,7 +454,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int bi_in = bi % p.batch_inner, bi_out = bi / p.batch_inner;
       const long long row_off = (long long)bi_out * p.out_bs + (long long)bi_in * p.out_bs_inner + (long long)gm * p.ldc;
       const bool row_ok = gm < p.M;
-      const int row_cnt = min(32, p.M - (gm - lane));   // valid rows of this warp in this tile (may be <= 0)
       float* sbias = sbias_all + acc * 256;
       // stage this tile's column bias in shared memory (double-buffered with the accumulator stage) and prefetch the first
       // chunk's aux / residual: all of it overlaps the wait for the MMA warp
@@ -530,9 +494,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           cur_res[j] = pf_res[j];
         }
         if (c + 32 < c_end) prefetch(c + 32);
-        if (gn0 < p.N && row_cnt > 0)   // warp-uniform: the staged stores are warp-collective
-          epilogue_chunk(p, r, gn0, row_off + gn0, rbias, vec_ok && (gn0 + 32 <= p.N), sbias + c, cur_aux, cur_res, row_ok,
-                         stage_smem, row_off - (long long)lane * p.ldc + gn0, row_cnt, lane);
+        if (row_ok && gn0 < p.N)
+          epilogue_chunk(p, r, gn0, row_off + gn0, rbias, vec_ok && (gn0 + 32 <= p.N), sbias + c, cur_aux, cur_res);
         __syncwarp();
       }
       // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp (of the leader CTA)
