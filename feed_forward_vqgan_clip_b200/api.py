@@ -1,6 +1,6 @@
 """The reference's Python call surface for the train-step path, backed by the B200 engines.
 
-    build_model(config)                      main.py:448-502   (model_type mlp_mixer; others raise -> SURVEY §8f next)
+    build_model(config)                      main.py:448-502   (model_type mlp_mixer, vitgan)
     load_vqgan_model(config_path, ckpt)      main.py:84-103
     load_clip_model(name, path)              main.py:1308-1333 (OpenAI ViT-B/32 and OpenCLIP ViT-B-32 architectures)
     MakeCutouts / synth / clamp_with_grad / vector_quantize      main.py:105-229
@@ -16,6 +16,7 @@ import torch
 from .clip_vit import CLIP, VIT_B32
 from .cutouts import MakeCutouts, sample_params  # noqa: F401
 from .mixer import Mixer
+from .vitgan_mapper import Generator as VitGAN
 from .train_step import FusedAdam, TrainStep  # noqa: F401
 from .vqgan import F16_16384, VQModel, clamp_with_grad, synth, vector_quantize  # noqa: F401
 
@@ -47,8 +48,12 @@ def build_model(config, vq_channels=256):
     if model_type == "mlp_mixer":
         return Mixer(input_dim=clip_dim + noise_dim, image_size=vq_image_size, channels=vq_channels, patch_size=1,
                      dim=_get(config, "dim"), depth=_get(config, "depth"), dropout=_get(config, "dropout", 0))
-    raise NotImplementedError("model_type %r: vitgan / simple_vitgan / xtransformer mappers are SURVEY §8 rows a2/a3 "
-                              "(scheduled after the Mixer path)" % model_type)
+    if model_type == "vitgan":                                                   # main.py:459-468
+        return VitGAN(initialize_size=vq_image_size // 8, dropout=_get(config, "dropout", 0), out_channels=vq_channels,
+                      input_dim=clip_dim + noise_dim, dim=_get(config, "dim"), num_heads=_get(config, "num_heads", 6),
+                      blocks=_get(config, "depth"))
+    raise NotImplementedError("model_type %r: simple_vitgan / xtransformer mappers are not built yet (SURVEY §8 row a3)"
+                              % model_type)
 
 
 def load_vqgan_model(config_path=None, checkpoint_path=None):

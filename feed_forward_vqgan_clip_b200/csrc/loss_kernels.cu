@@ -60,6 +60,46 @@ __global__ void __launch_bounds__(256) spherical_loss_kernel(const float* __rest
   }
 }
 
+// Total-variation loss of main.py:423-428 on an NHWC fp32 image, forward + backward fused:
+//   tv = 0.5 * (mean |Y[y+1] - Y[y]| + mean |Y[x+1] - Y[x]|);  dimg += coef * d(tv)/d(img);  loss += coef * tv
+__global__ void __launch_bounds__(256) tv_loss_kernel(const float* __restrict__ img, float* __restrict__ loss, float* __restrict__ dimg,
+                                                      int B, int H, int W, int C, float coef) {
+  const long long total = (long long)B * H * W * C;
+  const float wy = 0.5f * coef / ((float)B * C * (H - 1) * W), wx = 0.5f * coef / ((float)B * C * H * (W - 1));
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int x = (int)(p % W);
+    p /= W;
+    const int y = (int)(p % H);
+    const float v = img[i];
+    float g = 0.f;
+    auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
+    if (y > 0) g += wy * sgn(v - img[i - (long long)W * C]);
+    if (y < H - 1) {
+      const float d = img[i + (long long)W * C] - v;
+      g -= wy * sgn(d);
+      acc += wy * fabsf(d);
+    }
+    if (x > 0) g += wx * sgn(v - img[i - C]);
+    if (x < W - 1) {
+      const float d = img[i + C] - v;
+      g -= wx * sgn(d);
+      acc += wx * fabsf(d);
+    }
+    (void)c;
+    if (dimg) dimg[i] += g;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0 && loss) atomicAdd(loss, acc);
+}
+// y[i] += a * x[i]  (the gradient of l2_coef * mean(z^2), main.py:758-762: a = 2 * l2_coef / numel)
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, float a, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] += a * x[i];
+}
+
 }  // namespace ffvc
 
 using namespace ffvc;
@@ -70,6 +110,25 @@ extern "C" int ffvc_spherical_loss(const float* embed, const float* target, floa
   cudaMemsetAsync(loss_out, 0, sizeof(float), st);
   spherical_loss_kernel<<<(N + 7) / 8, 256, 0, st>>>(embed, target, loss_out, dembed,
                                                     reinterpret_cast<__nv_bfloat16*>(dembed_bf16), N, B, D, coef);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+extern "C" int ffvc_tv_loss(const float* img, float* loss_accum, float* dimg_accum, int B, int H, int W, int C, float coef,
+                            void* stream) {
+  if (H < 2 || W < 2) return set_error(FFVC_ERR_ARG, "tv_loss: image must be at least 2x2");
+  const long long total = (long long)B * H * W * C;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  tv_loss_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, loss_accum, dimg_accum, B, H, W, C, coef);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_axpy_f32(const float* x, float* y, float a, long long n, void* stream) {
+  long long g = (n + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  if (g < 1) g = 1;
+  axpy_kernel<<<(unsigned)g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, a, n);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

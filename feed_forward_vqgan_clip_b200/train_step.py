@@ -53,7 +53,7 @@ class FusedAdam:
 
 class TrainStep:
     def __init__(self, net, vq, perceptor, cutn=8, lr=1e-3, cut_size=224, target_loss_coef=1.0, world_size=1,
-                 process_group=None, seed=0):
+                 process_group=None, seed=0, l2_coef=0.0, tv_coef=0.0):
         self.net, self.vq, self.perceptor = net, vq, perceptor
         self.mix = net.engine()
         self.dec = vq.engine()
@@ -62,6 +62,8 @@ class TrainStep:
         self.cutn, self.cut_size = cutn, cut_size
         self.cut = CutoutEngine(cut_size, cutn, self.clip.patch, self.dev)
         self.coef = target_loss_coef
+        self.l2_coef, self.tv_coef = float(l2_coef), float(tv_coef)          # main.py:690-691,758-773,831
+        self.aux_loss = torch.zeros(2, device=self.dev, dtype=F32)           # [l2, tv] (already scaled by their coefficients)
         self.opt = FusedAdam(self.mix, lr=lr)
         self.world, self.pg = world_size, process_group
         self.opt.set_grad_scale(1.0 / world_size)
@@ -87,17 +89,25 @@ class TrainStep:
         emb, sv_e = clip.forward(patches)
         demb = torch.empty(N, clip.E, device=self.dev, dtype=F32)
         call("spherical_loss", emb, out_feats, self.loss, demb, None, N, B, clip.E, self.coef)
+        self.aux_loss.zero_()
         # ---- backward
         dpatch = clip.backward(sv_e, demb)
         del sv_e
         dimg = cut.backward(sv_c, dpatch)
         del sv_c, dpatch
+        if self.tv_coef > 0:                                             # tv_coef * tv_loss(xr), main.py:769-773,831
+            H = img.shape[1]
+            call("tv_loss", img, self.aux_loss[1:2], dimg, B, H, img.shape[2], 3, self.tv_coef)
         dzq = dec.backward(tape, dimg)                                   # [B*T, C] bf16 (straight-through to z)
         del tape
         dzq32 = torch.empty(B * S * S, C, device=self.dev, dtype=F32)
         call("cast_bf16_f32", dzq, dzq32, dzq.numel())
         dz = torch.empty_like(dzq32)
         call("clamp_bwd", dzq32, z, dz, dz.numel(), self.z_lo, self.z_hi)
+        if self.l2_coef > 0:                                             # l2_coef * mean(z**2) on the pre-clamp z, main.py:758-762
+            call("sumsq", z, self.aux_loss[0:1], z.numel())
+            self.aux_loss[0:1].mul_(self.l2_coef / z.numel())
+            call("axpy_f32", z, dz, 2.0 * self.l2_coef / z.numel(), z.numel())
         mix.zero_grad_arena()
         mix.backward(sv_m, dz)
         del sv_m

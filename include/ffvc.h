@@ -184,6 +184,29 @@ int ffvc_cutout_final_bwd(const float* cut1, const float* hinv, const float* sat
 int ffvc_spherical_loss(const float* embed, const float* target, float* loss_out, float* dembed, void* dembed_bf16, int N,
                         int B, int D, float coef, void* stream);
 
+/* total-variation loss (main.py:423-428) on NHWC fp32, fwd+bwd: loss_accum += coef*tv, dimg_accum += coef*d(tv)/d(img);
+ * axpy for the z-L2 term's gradient (main.py:758-762). */
+int ffvc_tv_loss(const float* img, float* loss_accum, float* dimg_accum, int B, int H, int W, int C, float coef, void* stream);
+int ffvc_axpy_f32(const float* x, float* y, float a, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VitGAN mapper pieces (vitgan.py:8-21,44-97,254-260).
+ * SLN modulation: s = w * (gamma * n + beta), n = LayerNorm(hl) from ffvc_layernorm_fwd; gamma / beta are DEVICE scalars.
+ * bwd: dn (bf16), dw_acc += (fp32, shared by every SLN that consumes w), dgamma / dbeta += (fp32). */
+int ffvc_sln_mod_fwd(const void* n, const void* w, const float* gamma, const float* beta, void* s, long long total, void* stream);
+int ffvc_sln_mod_bwd(const void* ds, const void* n, const void* w, const float* gamma, const float* beta, void* dn, float* dw_acc,
+                     float* dgamma, float* dbeta, long long total, void* stream);
+/* attention with the reference's '(d k h)' interleaved projection layout: qkv [B][T][ld_qkv], column d*3H + k*H + h;
+ * out [B][T][ld_out], column h*dh + d; probs [B*H][T][T] fp32 saved for the backward.  T <= 32, dh <= 256. */
+int ffvc_vitgan_attn_fwd(const void* qkv, void* out, float* probs, int B, int T, int H, int dh, int ld_qkv, int ld_out,
+                         float scale, void* stream);
+int ffvc_vitgan_attn_bwd(const void* qkv, const float* probs, const void* dout, void* dqkv, int B, int T, int H, int dh, int ld_qkv,
+                         int ld_out, float scale, void* stream);
+/* fp32 [rows][cols] -> bf16 [rows][ld] (zero padded): gives 1020-wide operands a TMA-legal 16-byte row pitch. */
+int ffvc_cast_f32_bf16_pitched(const float* src, void* dst, int rows, int cols, int ld, void* stream);
+/* y[b][:] = bf16(x[:]) for b < B (pos_emb1D broadcast over the batch). */
+int ffvc_broadcast_rows(const float* x, void* y, int B, long long n, void* stream);
+
 /* sizeof() of the ABI structs, for binding self-checks. */
 int ffvc_sizeof(const char* name);
 

@@ -15,7 +15,7 @@ from . import vqgan as ovq
 
 class OracleTrainer:
     def __init__(self, sd_mixer, sd_vq, sd_clip, image_size, channels, vq_cfg=ovq.F16_16384, clip_cfg=oclip.VIT_B32,
-                 cutn=8, cut_size=224, lr=1e-3, act="quick_gelu"):
+                 cutn=8, cut_size=224, lr=1e-3, act="quick_gelu", l2_coef=0.0, tv_coef=0.0, mapper="mixer", num_heads=6):
         self.params = {k: v.clone().requires_grad_(True) for k, v in sd_mixer.items()}
         self.sd_vq, self.sd_clip = sd_vq, sd_clip
         self.S, self.C = image_size, channels
@@ -24,15 +24,24 @@ class OracleTrainer:
         cb = sd_vq["quantize.embedding.weight"]
         self.z_lo, self.z_hi = float(cb.min()), float(cb.max())              # main.py:645-646,763
         self.last_indices = None
+        self.l2_coef, self.tv_coef, self.mapper, self.num_heads = l2_coef, tv_coef, mapper, num_heads
 
     def step(self, inp_feats, out_feats, prm):
-        z = omix.mixer_forward(self.params, inp_feats, self.S, self.C).contiguous()          # main.py:754-757
+        if self.mapper == "vitgan":
+            from . import vitgan as ovit
+            z = ovit.vitgan_forward(self.params, inp_feats, self.C, self.num_heads).contiguous()
+        else:
+            z = omix.mixer_forward(self.params, inp_feats, self.S, self.C).contiguous()      # main.py:754-757
+        l2 = (z ** 2).mean() if self.l2_coef > 0 else 0.0                                    # main.py:758-762
         z = ovq.clamp_with_grad(z, self.z_lo, self.z_hi)                                     # main.py:763
         xr, idx = ovq.synth(self.sd_vq, z, self.vq_cfg, return_indices=True)                 # main.py:767
         self.last_indices = idx
         x = ocut.make_cutouts(xr, self.cutn, prm, self.cut_size, normalize=True)             # main.py:796-797
         embed = oclip.encode_image(self.sd_clip, x, self.clip_cfg, act=self.act).float()     # main.py:799
-        loss = oloss.spherical_dist_loss(embed, out_feats, self.cutn)                        # main.py:801-811
+        tv = oloss.tv_loss(xr) if self.tv_coef > 0 else 0.0                                  # main.py:769-773
+        dists = oloss.spherical_dist_loss(embed, out_feats, self.cutn)                       # main.py:801-811
+        self.last_terms = (float(dists), float(l2), float(tv))
+        loss = dists + self.l2_coef * l2 + self.tv_coef * tv                                 # main.py:831
         self.opt.zero_grad()                                                                 # main.py:825
         loss.backward()                                                                      # main.py:832
         self.grads = {k: p.grad.clone() for k, p in self.params.items()}

@@ -38,6 +38,23 @@ def golden_mixer():
     torch.save(out, os.path.join(OUT, "mixer.pt"))
 
 
+def golden_vitgan():
+    from vitgan import Generator
+    torch.manual_seed(4)
+    cfg = dict(initialize_size=1, dim=24, blocks=2, num_heads=3, out_channels=4, input_dim=16)      # T = 8, dim_head = 8
+    net = Generator(**cfg)
+    x = torch.randn(3, 16)
+    y = net(x)
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    big = Generator(initialize_size=2, dim=1024, blocks=32, num_heads=6, out_channels=256, input_dim=512)
+    torch.save(dict(cfg=cfg, state_dict={k: v.detach().clone() for k, v in net.state_dict().items()}, x=x, w=w, y=y.detach(),
+                    grads={k: p.grad.clone() for k, p in net.named_parameters()},
+                    count_32x1024=sum(p.numel() for p in big.parameters()),
+                    keys_32x1024=[(k, tuple(v.shape)) for k, v in big.state_dict().items() if ".blocks." not in k or ".blocks.0." in k]),
+               os.path.join(OUT, "vitgan.pt"))
+
+
 def golden_clip():
     from cloob import VisualTransformer
     torch.manual_seed(1)
@@ -58,7 +75,7 @@ def golden_clip():
 def golden_glue():
     for name in ["clize", "omegaconf", "kornia", "kornia.augmentation", "taming", "taming.models",
                  "taming.models.cond_transformer", "taming.models.vqgan", "taming.modules", "taming.modules.losses",
-                 "taming.modules.losses.lpips", "clip", "clip.simple_tokenizer", "transformer", "vitgan",
+                 "taming.modules.losses.lpips", "clip", "clip.simple_tokenizer", "transformer",
                  "torch.utils.tensorboard"]:
         sys.modules.setdefault(name, MagicMock())
     os.environ["USE_HOROVOD"] = "false"
@@ -109,6 +126,7 @@ def golden_glue():
 
 if __name__ == "__main__":
     golden_mixer()
+    golden_vitgan()
     golden_clip()
     golden_glue()
     for f in sorted(os.listdir(OUT)):

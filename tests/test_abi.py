@@ -64,3 +64,19 @@ def test_vqgan_and_clip_state_dict_keys_match_oracle_layout():
     assert set(vis.state_dict().keys()) == set(refc.keys())
     for k, v in vis.state_dict().items():
         assert v.shape == refc[k].shape, k
+
+
+def test_vitgan_state_dict_contract_and_seeded_init_match_reference_golden():
+    from feed_forward_vqgan_clip_b200.vitgan_mapper import Generator
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "vitgan.pt"))
+    torch.manual_seed(4)
+    net = Generator(**gold["cfg"])
+    sd, ref = net.state_dict(), gold["state_dict"]
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and torch.equal(sd[k], ref[k]), k
+    # full-size known answers: 415,078,530 parameters, to_qkv (3060, 1024), w_out (1024, 1020)
+    shapes = dict(gold["keys_32x1024"])
+    assert gold["count_32x1024"] == 415078530
+    assert shapes["Transformer_Encoder.blocks.0.attn.to_qkv.weight"] == (3060, 1024)
+    assert shapes["Transformer_Encoder.blocks.0.attn.w_out.weight"] == (1024, 1020)

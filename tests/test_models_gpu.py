@@ -20,6 +20,8 @@ from feed_forward_vqgan_clip_b200.cutouts import sample_params
 from feed_forward_vqgan_clip_b200.mixer import Mixer
 from feed_forward_vqgan_clip_b200.train_step import TrainStep
 from feed_forward_vqgan_clip_b200.vqgan import VQModel, synth
+from feed_forward_vqgan_clip_b200.vitgan_mapper import Generator as VitGAN
+import oracle.vitgan as ovit
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -87,6 +89,40 @@ def test_mixer_forward_backward_vs_oracle(cfg, B):
     # the state_dict survives the flat-arena re-pointing
     for k, v in net.state_dict().items():
         assert torch.equal(v.cpu(), sd_ref[k].detach())
+
+
+# ----------------------------------------------------------------------------------------------------- VitGAN mapper
+@pytest.mark.parametrize("dim,heads", [(96, 6), (128, 6)])      # 128/6 -> head dim 21, weight dim 126: the padded-pitch path
+def test_vitgan_forward_backward_vs_oracle(dim, heads):
+    cfg = dict(initialize_size=2, dim=dim, blocks=2, num_heads=heads, out_channels=64, input_dim=64)
+    torch.manual_seed(3)
+    net = VitGAN(**cfg)
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if p.dim() >= 2 and p.numel() > 1:
+                p.copy_(p.to(torch.bfloat16).float())
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    net = net.to(DEV)
+    B = 3
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 64, generator=g).to(torch.bfloat16).float()
+    w = torch.randn(B, 64, 16, 16, generator=g)
+    y = net(x.to(DEV))
+    yr = ovit.vitgan_forward(sd_ref, x, 64, heads)
+    assert y.shape == yr.shape
+    close(y, yr, 3e-2, "vitgan fwd")
+    (y * w.to(DEV)).sum().backward()
+    (yr * w).sum().backward()
+    bad = []
+    for n, p in net.named_parameters():
+        ref_g = sd_ref[n].grad
+        c = cos(p.grad, ref_g)
+        err = (p.grad.detach().float().cpu() - ref_g).abs().max().item()
+        scale = ref_g.abs().max().item() + 1e-9
+        ok = (c > 0.99 and err <= 6e-2 * scale) if p.numel() > 1 else err <= 6e-2 * max(scale, 1.0)
+        if not ok:
+            bad.append((n, round(c, 4), err, scale))
+    assert not bad, bad
 
 
 # ----------------------------------------------------------------------------------------------------- VQGAN decoder
@@ -197,6 +233,45 @@ def test_train_step_vs_oracle_step():
         if p.numel() >= 4096:
             du, dr = p.detach().cpu() - sd_m[n], ref_params[n] - sd_m[n]
             assert cos(du, dr) > 0.8, (n, cos(du, dr))   # sign-like first Adam step: tiny gradients flip sign
+
+
+def test_train_step_vitgan_with_l2_and_tv_vs_oracle_step():
+    """VitGAN mapper (config #3 family) + the optional l2 / tv terms of main.py:758-773,831 through the fused step."""
+    vcfg = dict(initialize_size=2, dim=128, blocks=2, num_heads=6, out_channels=64, input_dim=64)
+    torch.manual_seed(13)
+    net = VitGAN(**vcfg)
+    with torch.no_grad():
+        net.w_out[0].weight.mul_(4.0)
+        for p in net.parameters():
+            if p.dim() >= 2 and p.numel() > 1:
+                p.copy_(p.to(torch.bfloat16).float())
+    sd_m = {k: v.clone() for k, v in net.state_dict().items()}
+    vq, sd_v = _vq_pair(seed=8)
+    sd_c = bf16_round_sd(oclip.init_clip_state_dict(SMALL_CLIP, seed=9))
+    clip = CLIP(SMALL_CLIP)
+    clip.visual.load_state_dict(sd_c)
+    clip = clip.to(DEV).eval().requires_grad_(False)
+    net = net.to(DEV)
+    B, cutn, lr = 2, 4, 1e-3
+    g = torch.Generator().manual_seed(14)
+    x = (torch.randn(B, 64, generator=g) * 0.45).to(torch.bfloat16).float()
+    prm = sample_params(cutn * B, 224, g)
+    ts = TrainStep(net, vq, clip, cutn=cutn, lr=lr, l2_coef=0.1, tv_coef=0.5)
+    loss = ts.step(x.to(DEV), None, prm)
+    torch.cuda.synchronize()
+    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 64, SMALL_VQ, SMALL_CLIP, cutn=cutn, lr=lr, l2_coef=0.1, tv_coef=0.5,
+                        mapper="vitgan", num_heads=6)
+    otr.step(x, x, prm)
+    dists, l2, tv = otr.last_terms
+    agree = (ts.last_indices.cpu().long().view(-1) == otr.last_indices.view(-1)).float().mean().item()
+    assert agree > 0.97, agree
+    assert abs(loss.item() - dists) < 3e-2 * abs(dists), (loss.item(), dists)
+    aux = ts.aux_loss.cpu().tolist()
+    assert abs(aux[0] - 0.1 * l2) < 3e-2 * 0.1 * l2 + 1e-6, (aux, l2)
+    assert abs(aux[1] - 0.5 * tv) < 5e-2 * 0.5 * tv + 1e-6, (aux, tv)
+    eng = net.engine()
+    sims = {n: cos(gv, otr.grads[n]) for (n, p), gv in zip(net.named_parameters(), eng.grad_views) if p.numel() >= 4096}
+    assert min(sims.values()) > 0.95, sims
 
 
 def test_cuda_graph_replay_matches_eager():

@@ -272,3 +272,70 @@ def test_cutouts_fwd_bwd_vs_oracle():
     err = (dimg - xr.grad).abs()
     scale = xr.grad.abs().max().item()
     assert (err > 3e-2 * scale).float().mean().item() < 1e-3, (err.max().item(), scale)
+
+
+def test_tv_loss_fwd_bwd_vs_reference_expression():
+    import oracle.loss as ol
+    B, H, W = 2, 24, 40
+    g = torch.Generator().manual_seed(7)
+    img = torch.rand(B, 3, H, W, generator=g)
+    xr = img.clone().requires_grad_(True)
+    ref = 0.3 * ol.tv_loss(xr)                               # main.py:423-428
+    ref.backward()
+    nhwc = img.permute(0, 2, 3, 1).contiguous().to(DEV)
+    loss = torch.zeros(1, device=DEV)
+    dimg = torch.ones(B, H, W, 3, device=DEV)                # accumulates on top of an existing gradient
+    call("tv_loss", nhwc, loss, dimg, B, H, W, 3, 0.3)
+    assert abs(loss.item() - ref.item()) < 1e-6
+    assert torch.allclose(dimg.cpu() - 1.0, xr.grad.permute(0, 2, 3, 1), atol=1e-7)
+    x = rnd(1000, seed=8, dtype=F32)
+    y = rnd(1000, seed=9, dtype=F32)
+    y0 = y.clone()
+    call("axpy_f32", x, y, 0.25, 1000)
+    assert torch.allclose(y, y0 + 0.25 * x)
+
+
+def test_sln_and_vitgan_attention_kernels():
+    R, D = 96, 128
+    n, w, ds = rnd(R, D, seed=1), rnd(R, D, seed=2), rnd(R, D, seed=3)
+    gamma, beta = torch.tensor([0.7], device=DEV), torch.tensor([-0.4], device=DEV)
+    s = torch.empty_like(n)
+    call("sln_mod_fwd", n, w, gamma, beta, s, R * D)
+    nf, wf = n.float().requires_grad_(True), w.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    sr = gr * wf * nf + br * wf                               # vitgan.py:21
+    close(s, sr)
+    sr.backward(ds.float())
+    dn = torch.empty_like(n)
+    dw = torch.zeros(R, D, device=DEV)
+    dg, db = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    call("sln_mod_bwd", ds, n, w, gamma, beta, dn, dw, dg, db, R * D)
+    close(dn, nf.grad)
+    close(dw, wf.grad, 1e-3)
+    assert abs(dg.item() - gr.grad.item()) < 1e-2 * abs(gr.grad.item()) + 1e-2
+    assert abs(db.item() - br.grad.item()) < 1e-2 * abs(br.grad.item()) + 1e-2
+    # attention with the '(d k h)' interleaved layout (vitgan.py:82)
+    B, T, H, dh = 3, 16, 6, 21
+    Wd = H * dh
+    Q3, Wp = (3 * Wd + 7) // 8 * 8, (Wd + 7) // 8 * 8
+    qkv = torch.zeros(B, T, Q3, device=DEV, dtype=BF)
+    qkv[..., :3 * Wd] = rnd(B, T, 3 * Wd, seed=4)
+    out = torch.zeros(B, T, Wp, device=DEV, dtype=BF)
+    probs = torch.empty(B * H, T, T, device=DEV)
+    scale = 128 ** -0.5
+    call("vitgan_attn_fwd", qkv, out, probs, B, T, H, dh, Q3, Wp, scale)
+    x = qkv[..., :3 * Wd].float().requires_grad_(True)
+    q, k, v = x.view(B, T, dh, 3, H).permute(3, 0, 4, 1, 2)
+    a = torch.softmax(torch.einsum("bhid,bhjd->bhij", q, k) * scale, -1)
+    r = torch.einsum("bhij,bhjd->bhid", a, v).permute(0, 2, 1, 3).reshape(B, T, Wd)
+    close(out[..., :Wd], r)
+    do = torch.zeros(B, T, Wp, device=DEV, dtype=BF)
+    do[..., :Wd] = rnd(B, T, Wd, seed=5)
+    r.backward(do[..., :Wd].float())
+    dqkv = torch.zeros(B, T, Q3, device=DEV, dtype=BF)
+    call("vitgan_attn_bwd", qkv, probs, do, dqkv, B, T, H, dh, Q3, Wp, scale)
+    close(dqkv[..., :3 * Wd], x.grad)
+    src = rnd(40, 126, seed=6, dtype=F32)
+    dst = torch.empty(40, 128, device=DEV, dtype=BF)
+    call("cast_f32_bf16_pitched", src, dst, 40, 126, 128)
+    assert torch.equal(dst[:, :126], src.to(BF)) and float(dst[:, 126:].abs().max()) == 0.0

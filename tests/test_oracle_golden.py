@@ -29,6 +29,17 @@ def test_mixer_oracle_matches_reference_forward_and_grads():
     assert sum(v.numel() for v in sd.values()) == 38948480
 
 
+def test_vitgan_oracle_matches_reference_forward_and_grads():
+    import oracle.vitgan as ovit
+    g = torch.load(os.path.join(G, "vitgan.pt"))
+    sd = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    y = ovit.vitgan_forward(sd, g["x"], g["cfg"]["out_channels"], g["cfg"]["num_heads"])
+    assert torch.allclose(y, g["y"], rtol=1e-5, atol=1e-6)
+    (y * g["w"]).sum().backward()
+    for k, ref in g["grads"].items():
+        assert torch.allclose(sd[k].grad, ref, rtol=1e-4, atol=1e-5), k
+
+
 def test_clip_oracle_matches_reference_twin():
     g = torch.load(os.path.join(G, "clip_vit.pt"))
     x = g["x"].clone().requires_grad_(True)
