@@ -21,7 +21,7 @@ class GemmParams(C.Structure):
         ("a_batch_stride_inner", C.c_int64), ("b_batch_stride_inner", C.c_int64),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
         ("batch", C.c_int), ("batch_inner", C.c_int), ("k_segs", C.c_int), ("splits", C.c_int), ("block_n", C.c_int),
-        ("tile_m", C.c_int), ("two_cta", C.c_int),
+        ("tile_m", C.c_int), ("two_cta", C.c_int), ("epi_warps", C.c_int),
         ("conv_n", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_c", C.c_int),
         ("out", C.c_void_p), ("pre_out", C.c_void_p), ("aux", C.c_void_p), ("res", C.c_void_p),
         ("bias", C.c_void_p),

@@ -96,35 +96,38 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
   return pk;
 }
 
-// activation / activation-gradient on a 32-wide register chunk; the switch is hoisted out of the element loop so each
+// activation / activation-gradient on a CW-wide register chunk; the switch is hoisted out of the element loop so each
 // case is straight-line code (a per-element runtime branch costs more than the math)
-__device__ __forceinline__ void act_chunk(float (&v)[32], int act) {
+template <int CW>
+__device__ __forceinline__ void act_chunk(float (&v)[CW], int act) {
   if (act == FFVC_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_f(v[i]);
+    for (int i = 0; i < CW; ++i) v[i] = gelu_f(v[i]);
   } else if (act == FFVC_ACT_QUICKGELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = quick_gelu_f(v[i]);
+    for (int i = 0; i < CW; ++i) v[i] = quick_gelu_f(v[i]);
   } else if (act == FFVC_ACT_SWISH) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = swish_f(v[i]);
+    for (int i = 0; i < CW; ++i) v[i] = swish_f(v[i]);
   }
 }
-__device__ __forceinline__ void mulgrad_chunk(float (&v)[32], const float (&x)[32], int act) {
+template <int CW>
+__device__ __forceinline__ void mulgrad_chunk(float (&v)[CW], const float (&x)[CW], int act) {
   if (act == FFVC_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= gelu_grad_f(x[i]);
+    for (int i = 0; i < CW; ++i) v[i] *= gelu_grad_f(x[i]);
   } else if (act == FFVC_ACT_QUICKGELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= quick_gelu_grad_f(x[i]);
+    for (int i = 0; i < CW; ++i) v[i] *= quick_gelu_grad_f(x[i]);
   } else if (act == FFVC_ACT_SWISH) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= swish_grad_f(x[i]);
+    for (int i = 0; i < CW; ++i) v[i] *= swish_grad_f(x[i]);
   }
 }
-__device__ __forceinline__ void unpack_bf16x32(const uint4 (&pk)[4], float (&f)[32]) {
+template <int CW>
+__device__ __forceinline__ void unpack_bf16xN(const uint4 (&pk)[CW / 8], float (&f)[CW]) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
+  for (int q = 0; q < CW / 8; ++q) {
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[q]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -138,21 +141,22 @@ __device__ __forceinline__ void unpack_bf16x32(const uint4 (&pk)[4], float (&f)[
 // fused epilogue on 32 consecutive columns of one output row.
 //   sbias : column bias of this tile staged in shared memory (already offset to this chunk), or nullptr
 //   pf_aux / pf_res : aux / residual of this chunk prefetched into registers (valid when `vec` is true)
-__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[32], int gn0, long long off, float rbias,
-                                               bool vec, const float* sbias, const uint4 (&pf_aux)[4],
-                                               const uint4 (&pf_res)[4]) {
-  const int ncols = min(32, p.N - gn0);
-  float v[32];
+template <int CW>
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[CW], int gn0, long long off, float rbias,
+                                               bool vec, const float* sbias, const uint4 (&pf_aux)[CW / 8],
+                                               const uint4 (&pf_res)[CW / 8]) {
+  const int ncols = min(CW, p.N - gn0);
+  float v[CW];
   if (p.alpha != 1.0f) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
   } else {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
   }
   if (p.bias_mode == 1) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
+    for (int i = 0; i < CW; i += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(sbias + i);   // smem broadcast; zero beyond N
       v[i] += b4.x;
       v[i + 1] += b4.y;
@@ -161,65 +165,65 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
     }
   } else if (p.bias_mode == 2) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += rbias;
+    for (int i = 0; i < CW; ++i) v[i] += rbias;
   }
   if (p.pre_out != nullptr) {
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(p.pre_out) + off;
     if (vec) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(po + i) = pack_bf16x8(v + i);
+      for (int i = 0; i < CW; i += 8) *reinterpret_cast<uint4*>(po + i) = pack_bf16x8(v + i);
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
+      for (int i = 0; i < CW; ++i)
         if (i < ncols) po[i] = __float2bfloat16(v[i]);
     }
   }
-  act_chunk(v, p.act);
+  act_chunk<CW>(v, p.act);
   if (p.mul_mode != FFVC_ACT_NONE) {
-    float x[32];
+    float x[CW];
     if (vec) {
-      unpack_bf16x32(pf_aux, x);
+      unpack_bf16xN<CW>(pf_aux, x);
     } else {
       const __nv_bfloat16* ax = p.aux + off;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = (i < ncols) ? __bfloat162float(ax[i]) : 0.f;
+      for (int i = 0; i < CW; ++i) x[i] = (i < ncols) ? __bfloat162float(ax[i]) : 0.f;
     }
-    mulgrad_chunk(v, x, p.mul_mode);
+    mulgrad_chunk<CW>(v, x, p.mul_mode);
   }
   if (p.res != nullptr) {
-    float x[32];
+    float x[CW];
     if (vec) {
-      unpack_bf16x32(pf_res, x);
+      unpack_bf16xN<CW>(pf_res, x);
     } else {
       const __nv_bfloat16* rs = p.res + off;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = (i < ncols) ? __bfloat162float(rs[i]) : 0.f;
+      for (int i = 0; i < CW; ++i) x[i] = (i < ncols) ? __bfloat162float(rs[i]) : 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += x[i];
+    for (int i = 0; i < CW; ++i) v[i] += x[i];
   }
   if (p.out_fp32) {
     float* o = reinterpret_cast<float*>(p.out) + off;
     if (p.atomic) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
+      for (int i = 0; i < CW; ++i)
         if (i < ncols) atomicAdd(o + i, v[i]);
-    } else if (ncols == 32 && (p.ldc % 4 == 0) && (p.out_bs % 4 == 0) && (p.out_bs_inner % 4 == 0)) {
+    } else if (ncols == CW && (p.ldc % 4 == 0) && (p.out_bs % 4 == 0) && (p.out_bs_inner % 4 == 0)) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      for (int i = 0; i < CW; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
+      for (int i = 0; i < CW; ++i)
         if (i < ncols) o[i] = v[i];
     }
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
     if (vec) {
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) *reinterpret_cast<uint4*>(o + i) = pack_bf16x8(v + i);
+      for (int i = 0; i < CW; i += 8) *reinterpret_cast<uint4*>(o + i) = pack_bf16x8(v + i);
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
+      for (int i = 0; i < CW; ++i)
         if (i < ncols) o[i] = __float2bfloat16(v[i]);
     }
   }
@@ -230,8 +234,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
 //   HALF of the B tile; the leader CTA issues tcgen05.mma M=256 that reads both CTAs' shared memory, so every SM
 //   reads / is written only (A + B/2) per k-step instead of (A + B): the 1-CTA kernel is shared-memory-bandwidth
 //   bound (128 B/clk/SM) at ~55-65 % of the tensor pipe, the pair removes a third of that traffic.  6-stage ring.
-template <bool kTwoCta>
-__global__ void __launch_bounds__(kNumThreads, 1)
+template <bool kTwoCta, int kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmDev p) {
   constexpr int kStagesT = kTwoCta ? 6 : kStages;
@@ -261,7 +265,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kTwoCta ? 2 * kNumEpiWarps : kNumEpiWarps);
+      mbar_init(tempty_bar(a), kTwoCta ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -423,22 +427,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;       // 0 / 1: column half (128-row CTA tile) or row sub-tile (256-row 1-CTA tile)
-    const int etid = threadIdx.x - 64;      // 0..255 among the epilogue threads
+    const int slice = (warp - 2) >> 2;      // 0 .. kEpiWarps/4-1: which row sub-tile / column part this warp covers
+    constexpr int kSlices = kEpiWarps / 4;
+    const int etid = threadIdx.x - 64;      // 0 .. 32*kEpiWarps-1 among the epilogue threads
     const bool two_sub = !kTwoCta && p.tile_m == 256;
-    const int row_in_tile = (kTwoCta ? (int)rank * 128 : 0) + (two_sub ? half * 128 : 0) + q * 32 + lane;
-    // columns this warp covers inside the tile
-    int c_begin, c_end, tmem_col0;
-    if (two_sub) {
-      c_begin = 0;
-      c_end = p.block_n;
-      tmem_col0 = half * 128;
-    } else {
-      const int hcols = (p.block_n >= 64) ? p.block_n / 2 : p.block_n;
-      c_begin = half * hcols;
-      c_end = (p.block_n >= 64) ? c_begin + hcols : (half == 0 ? p.block_n : 0);
-      tmem_col0 = 0;
+    const int sub = two_sub ? (slice & 1) : 0;                       // row sub-tile (1-CTA 256-row tiles)
+    const int cparts = two_sub ? kSlices / 2 : kSlices;              // column parts the tile is split into
+    const int cpart = two_sub ? (slice >> 1) : slice;
+    const int row_in_tile = (kTwoCta ? (int)rank * 128 : 0) + sub * 128 + q * 32 + lane;
+    // columns this warp covers inside the tile: block_n / cparts when that is a multiple of 32, else the first
+    // warps take 32-column chunks and the rest idle
+    int c_begin, c_end;
+    {
+      int per = p.block_n / cparts;
+      if (per < 32) per = 32;
+      c_begin = cpart * per;
+      c_end = min(p.block_n, c_begin + per);
+      if (c_begin >= p.block_n) c_begin = c_end = 0;
     }
+    const int tmem_col0 = sub * 128;
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));  // [2][256] floats
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -459,43 +466,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       // chunk's aux / residual: all of it overlaps the wait for the MMA warp
       if (p.bias_mode == 1) {
         if (etid < p.block_n) sbias[etid] = (n0 + etid < p.N) ? p.bias[n0 + etid] : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
       const float rbias = (p.bias_mode == 2 && row_ok) ? p.bias[gm] : 0.0f;
-      uint4 pf_aux[4], pf_res[4];
+      constexpr int CW = (kEpiWarps == 16) ? 16 : 32;   // columns per register chunk
+      uint4 pf_aux[CW / 8], pf_res[CW / 8];
       auto prefetch = [&](int c) {
         const int gn0 = n0 + c;
-        if (row_ok && vec_ok && gn0 + 32 <= p.N) {
+        if (row_ok && vec_ok && gn0 + CW <= p.N) {
           if (want_aux) {
             const uint4* ax = reinterpret_cast<const uint4*>(p.aux + row_off + gn0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pf_aux[j] = ax[j];
+            for (int j = 0; j < CW / 8; ++j) pf_aux[j] = ax[j];
           }
           if (want_res) {
             const uint4* rs = reinterpret_cast<const uint4*>(p.res + row_off + gn0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pf_res[j] = rs[j];
+            for (int j = 0; j < CW / 8; ++j) pf_res[j] = rs[j];
           }
         }
       };
       if (c_begin < c_end) prefetch(c_begin);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      for (int c = c_begin; c < c_end; c += 32) {
-        uint32_t r[32];
+      for (int c = c_begin; c < c_end; c += CW) {
+        uint32_t r[CW];
         const uint32_t taddr = tmem_base + (uint32_t)(acc * 256 + tmem_col0 + c) + ((uint32_t)(q * 32) << 16);
-        tmem_ld_32x32(taddr, r);
+        if constexpr (CW == 16) tmem_ld_32x16(taddr, r); else tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
         const int gn0 = n0 + c;
-        uint4 cur_aux[4], cur_res[4];
+        uint4 cur_aux[CW / 8], cur_res[CW / 8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < CW / 8; ++j) {
           cur_aux[j] = pf_aux[j];
           cur_res[j] = pf_res[j];
         }
-        if (c + 32 < c_end) prefetch(c + 32);
+        if (c + CW < c_end) prefetch(c + CW);
         if (row_ok && gn0 < p.N)
-          epilogue_chunk(p, r, gn0, row_off + gn0, rbias, vec_ok && (gn0 + 32 <= p.N), sbias + c, cur_aux, cur_res);
+          epilogue_chunk<CW>(p, r, gn0, row_off + gn0, rbias, vec_ok && (gn0 + CW <= p.N), sbias + c, cur_aux, cur_res);
         __syncwarp();
       }
       // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp (of the leader CTA)
@@ -596,9 +604,13 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     if (g_num_sms <= 0) return set_error(FFVC_ERR_CUDA, "gemm: no CUDA device");
   }
   if (!g_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
     g_attr_set = true;
   }
@@ -752,13 +764,17 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
 
   const long long tiles = (long long)((g->M + tile_m - 1) / tile_m) * ((g->N + block_n - 1) / block_n) * batch * splits;
   cudaError_t e;
+  // 16 epilogue warps when the epilogue does real math (activation / activation gradient): with 8 warps (2 per scheduler)
+  // those epilogues run at IPC ~0.4 and pace the whole kernel for short-K GEMMs
+  const bool wide_epi = (p.act != FFVC_ACT_NONE || p.mul_mode != FFVC_ACT_NONE) && block_n >= 128 && g->epi_warps != 8;
+  const int nthreads = wide_epi ? 64 + 32 * 16 : kNumThreads;
   if (two_cta == 1) {
     // one CTA pair (cluster of 2) per tile, persistent over min(tiles, SMs/2) pairs
     const long long pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(2 * pairs));
-    cfg.blockDim = dim3(kNumThreads);
+    cfg.blockDim = dim3(nthreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -768,11 +784,13 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, ta, tb, p);
+    e = wide_epi ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 16>, ta, tb, p)
+                 : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 8>, ta, tb, p);
     if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   } else {
     const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-    gemm_tcgen05_kernel<false><<<grid, kNumThreads, kSmemBytes, stream>>>(ta, tb, p);
+    if (wide_epi) gemm_tcgen05_kernel<false, 16><<<grid, nthreads, kSmemBytes, stream>>>(ta, tb, p);
+    else gemm_tcgen05_kernel<false, 8><<<grid, nthreads, kSmemBytes, stream>>>(ta, tb, p);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));

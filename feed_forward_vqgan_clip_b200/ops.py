@@ -45,7 +45,7 @@ def gemm(a, b, out, M, N, K, *, a_mode=KMAJOR, b_mode=KMAJOR, a_ld=None, b_ld=No
          a_role=ROLE_BCAST, b_role=ROLE_BCAST, a_bs=0, b_bs=0, batch=1, k_segs=1, splits=1, block_n=0,
          conv=None, pre_out=None, aux=None, res=None, bias=None, ldc=None, out_bs=0, atomic=False,
          bias_mode=1, act=ACT_NONE, mul_mode=ACT_NONE, alpha=1.0, a_off=0, b_off=0, out_off=0, batch_inner=1,
-         a_bs_in=0, b_bs_in=0, out_bs_in=0, tile_m=0, two_cta=0):
+         a_bs_in=0, b_bs_in=0, out_bs_in=0, tile_m=0, two_cta=0, epi_warps=0):
     """out[b,m,n] (+)= epilogue(alpha * sum_k A[m,k] B[n,k]); see include/ffvc.h:ffvc_gemm.
     a_off / out_off: element offsets added to the base pointers."""
     p = GemmParams()
@@ -61,7 +61,7 @@ def gemm(a, b, out, M, N, K, *, a_mode=KMAJOR, b_mode=KMAJOR, a_ld=None, b_ld=No
     p.a_batch_stride, p.b_batch_stride = a_bs, b_bs
     p.M, p.N, p.K = M, N, K
     p.batch, p.k_segs, p.splits, p.block_n = batch, k_segs, splits, block_n
-    p.batch_inner, p.tile_m, p.two_cta = batch_inner, tile_m, two_cta
+    p.batch_inner, p.tile_m, p.two_cta, p.epi_warps = batch_inner, tile_m, two_cta, epi_warps
     p.a_batch_stride_inner, p.b_batch_stride_inner, p.out_batch_stride_inner = a_bs_in, b_bs_in, out_bs_in
     if conv is not None:
         p.conv_n, p.conv_h, p.conv_w, p.conv_c = conv

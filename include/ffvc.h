@@ -73,6 +73,7 @@ typedef struct {
   int block_n;             /* 0 = auto, else 32/64/128/256 */
   int tile_m;              /* 0 = auto, else 128/256 (256 needs block_n <= 128) */
   int two_cta;             /* 0 = auto, 1 = force the CTA-pair (cta_group::2) kernel, -1 = never */
+  int epi_warps;           /* 0 = auto (16 for activation epilogues), 8 = force the 8-warp epilogue */
   /* CONV3X3 (A is NHWC [conv_n][conv_h][conv_w][conv_c], pad 1, stride 1; M = n*h*w; K = 9*c) */
   int conv_n, conv_h, conv_w, conv_c;
   /* epilogue */

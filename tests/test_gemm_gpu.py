@@ -238,3 +238,24 @@ def test_two_cta_batched_token_mix():
              bias_mode=2, act=ops.ACT_GELU, two_cta=1)
     ref = F.gelu(torch.einsum("jt,btd->bjd", w.float(), h.float()) + bias[None, :, None])
     _check(out, ref, 2e-2)
+
+
+@pytest.mark.parametrize("epi", [0, 8])
+@pytest.mark.parametrize("two", [-1, 1])
+def test_epilogue_warp_variants_agree(epi, two):
+    """activation epilogues run on 16 warps (16-column chunks) by default; epi_warps=8 forces the 8-warp / 32-column form"""
+    M, N, K = 512, 256, 128
+    a, b = _rand(M, K, seed=61), _rand(N, K, seed=62)
+    bias = torch.randn(N, device=DEV)
+    aux, res = _rand(M, N, seed=63), _rand(M, N, seed=64)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    pre = torch.empty_like(out)
+    ops.gemm(a, b, out, M, N, K, bias=bias, act=ops.ACT_QUICKGELU, pre_out=pre, res=res, two_cta=two, epi_warps=epi)
+    ref_pre = a.float() @ b.float().t() + bias
+    _check(pre, ref_pre, 2e-2)
+    _check(out, ref_pre * torch.sigmoid(1.702 * ref_pre) + res.float(), 2e-2)
+    out2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(a, b, out2, M, N, K, aux=aux, mul_mode=ops.ACT_GELU, two_cta=two, epi_warps=epi, tile_m=0)
+    x = aux.float()
+    gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * 3.141592653589793) ** 0.5
+    _check(out2, (a.float() @ b.float().t()) * gp, 2e-2)
