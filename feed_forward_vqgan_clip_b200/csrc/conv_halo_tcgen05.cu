@@ -1,0 +1,338 @@
+// 3x3 convolution (pad 1, stride 1) on NHWC bf16 as an implicit GEMM with HALO REUSE in shared memory, for wide images
+// (W a multiple of 128) and Cout <= 128 — the 128-channel layers of the VQGAN decoder at 128x128 and 256x256, which hold
+// ~60 % of the decoder's FLOPs (taming Decoder, call site main.py:142).
+//
+// The tap-by-tap form (ffvc_gemm, CONV3X3 mode) loads one shifted 4-D TMA box per filter tap: every input pixel crosses
+// L2 -> SM nine times and those layers are L2-bandwidth bound (profiles/r01_ncu_full_gemm_summary.md).  Here a CTA owns
+// 2 output rows x 128 pixels; per 64-channel chunk it loads the (2+2) x (128+2) pixel HALO once (one TMA box, 128B
+// swizzle, zero fill = padding) and the nine taps are nine UMMA descriptors into that same buffer: output row `sub`, tap
+// (r, s) starts at halo row (sub + r), pixel s — 128 consecutive 128-byte rows.  Those start addresses are 128 B- but not
+// 1024 B-aligned, so the descriptor carries the swizzle phase in its base-offset field ((addr >> 7) & 7).
+// A-operand traffic drops 9x (66.5 KB per 64-channel chunk instead of 9 x 32 KB); weights stream through a 4-stage ring.
+//
+// Same warp roles, TMEM double buffering and fused epilogue as gemm_tcgen05_kernel (gemm_common.cuh).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "ffvc_internal.h"
+#include "ptx.cuh"
+#include "gemm_common.cuh"
+
+namespace ffvc {
+
+static constexpr int kHaloRows = 4;                                   // 2 output rows + 1 above + 1 below
+static constexpr int kHaloPix = 130;                                  // 128 output pixels + 1 left + 1 right
+static constexpr int kHaloBytes = kHaloRows * kHaloPix * 128;         // 66,560 B per 64-channel chunk
+static constexpr int kHaloStride = (kHaloBytes + 1023) / 1024 * 1024; // 67,584 B (keeps every buffer 1024 B-aligned)
+static constexpr int kBStages = 4;
+static constexpr int kBStageBytes = 128 * 64 * 2;                     // up to 128 output channels x 64 input channels
+static constexpr int kHaloSmem = 2 * kHaloStride + kBStages * kBStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/;
+static constexpr int kHaloThreads = 320;
+static constexpr int kHaloEpiWarps = 8;
+
+// descriptor for a K-major, 128B-swizzled operand whose start is 128 B- (not 1024 B-) aligned
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t saddr) {
+  uint64_t d = umma_smem_desc_sw128(saddr, 16u, 1024u);
+  d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;   // matrix base offset = swizzle phase of the first row
+  return d;
+}
+
+__global__ void __launch_bounds__(kHaloThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const GemmDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t halo_base = smem_base;                               // [2][kHaloStride]
+  const uint32_t b_base = smem_base + 2 * kHaloStride;                // [kBStages][kBStageBytes]
+  const uint32_t bar_base = b_base + kBStages * kBStageBytes;
+  auto hfull_bar = [&](int i) { return bar_base + 8u * i; };          // 2
+  auto hempty_bar = [&](int i) { return bar_base + 8u * (2 + i); };   // 2
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (4 + s); };    // 4
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (8 + s); };   // 4
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (12 + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (14 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * 16;
+  const uint32_t bias_smem = bar_base + 256u;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_w);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(hfull_bar(i), 1);
+      mbar_init(hempty_bar(i), 1);
+    }
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), kHaloEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  // tile = image n, output rows (2*ty, 2*ty+1), pixels [128*tx, 128*tx + 128)
+  const int H = p.conv_h, W = p.conv_w;
+  const int tiles_x = W / 128, tiles_y = H / 2;
+  const long long total_tiles = (long long)p.batch * tiles_y * tiles_x;   // p.batch = number of images
+  const int cblocks = p.conv_cblocks;                                     // Cin / 64
+  const uint32_t b_bytes = (uint32_t)p.block_n * 128u;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int hb = 0, bs = 0;
+      uint32_t hphase = 0, bphase = 0;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int tx = (int)(t % tiles_x);
+        const int ty = (int)((t / tiles_x) % tiles_y);
+        const int img = (int)(t / ((long long)tiles_x * tiles_y));
+        for (int c = 0; c < cblocks; ++c) {
+          mbar_wait(hempty_bar(hb), hphase ^ 1u);
+          mbar_expect_tx(hfull_bar(hb), (uint32_t)kHaloBytes);
+          tma_load_4d(halo_base + hb * kHaloStride, &tmap_x, hfull_bar(hb), c * 64, tx * 128 - 1, ty * 2 - 1, img);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bempty_bar(bs), bphase ^ 1u);
+            mbar_expect_tx(bfull_bar(bs), b_bytes);
+            tma_load_4d(b_base + bs * kBStageBytes, &tmap_w, bfull_bar(bs), (tap * cblocks + c) * 64, 0, 0, 0);
+            if (++bs == kBStages) {
+              bs = 0;
+              bphase ^= 1u;
+            }
+          }
+          if (++hb == 2) {
+            hb = 0;
+            hphase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_m(128, p.block_n, 0, 0);
+      int hb = 0, bs = 0, acc = 0;
+      uint32_t hphase = 0, bphase = 0, acc_phase = 0;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
+        for (int c = 0; c < cblocks; ++c) {
+          mbar_wait(hfull_bar(hb), hphase);
+          tc_fence_after();
+          const uint32_t halo = halo_base + hb * kHaloStride;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bfull_bar(bs), bphase);
+            tc_fence_after();
+            const uint32_t sb = b_base + bs * kBStageBytes;
+            const int r = tap / 3, s = tap % 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t db = umma_smem_desc_sw128(sb + k * 32u, 16u, 1024u);
+              const uint32_t accum = (c > 0 || tap > 0 || k > 0) ? 1u : 0u;
+#pragma unroll
+              for (int sub = 0; sub < 2; ++sub) {
+                const uint32_t arow = (uint32_t)((sub + r) * kHaloPix + s);       // first halo row of this A tile
+                const uint64_t da = umma_smem_desc_sw128_off(halo + arow * 128u + k * 32u);
+                umma_bf16(tmem_d + sub * 128, da, db, idesc, accum);
+              }
+            }
+            umma_commit(bempty_bar(bs));
+            if (++bs == kBStages) {
+              bs = 0;
+              bphase ^= 1u;
+            }
+          }
+          umma_commit(hempty_bar(hb));   // halo buffer free once its 9 x 8 MMAs retired
+          if (++hb == 2) {
+            hb = 0;
+            hphase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..9): sub-tile = output row
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (p.ldc % 8 == 0);
+    const bool want_aux = p.mul_mode != FFVC_ACT_NONE, want_res = p.res != nullptr;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int tx = (int)(t % tiles_x);
+      const int ty = (int)((t / tiles_x) % tiles_y);
+      const int img = (int)(t / ((long long)tiles_x * tiles_y));
+      const long long gm = ((long long)img * H + (ty * 2 + sub)) * W + tx * 128 + q * 32 + lane;   // flattened pixel index
+      const long long row_off = gm * p.ldc;
+      float* sbias = sbias_all + acc * 256;
+      if (p.bias_mode == 1) {
+        if (etid < p.block_n) sbias[etid] = (etid < p.N) ? p.bias[etid] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      constexpr int CW = 32;
+      uint4 pf_aux[CW / 8], pf_res[CW / 8];
+      auto prefetch = [&](int c) {
+        if (vec_ok && c + CW <= p.N) {
+          if (want_aux) {
+            const uint4* ax = reinterpret_cast<const uint4*>(p.aux + row_off + c);
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j) pf_aux[j] = ax[j];
+          }
+          if (want_res) {
+            const uint4* rs = reinterpret_cast<const uint4*>(p.res + row_off + c);
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j) pf_res[j] = rs[j];
+          }
+        }
+      };
+      prefetch(0);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      for (int c = 0; c < p.block_n; c += CW) {
+        uint32_t r[CW];
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * 256 + sub * 128 + c) + ((uint32_t)(q * 32) << 16);
+        tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        uint4 cur_aux[CW / 8], cur_res[CW / 8];
+#pragma unroll
+        for (int j = 0; j < CW / 8; ++j) {
+          cur_aux[j] = pf_aux[j];
+          cur_res[j] = pf_res[j];
+        }
+        if (c + CW < p.block_n) prefetch(c + CW);
+        if (c < p.N) epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok && (c + CW <= p.N), sbias + c, cur_aux, cur_res);
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode4(CUtensorMap* m, const void* base, const uint64_t* dims, const uint64_t* strides_elems, const uint32_t* box) {
+  static PFN_encodeTiled2 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || !ptr)
+      return set_error(FFVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    fn = reinterpret_cast<PFN_encodeTiled2>(ptr);
+  }
+  cuuint64_t gdim[4], gstr[3];
+  cuuint32_t bdim[4], estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+  }
+  for (int i = 1; i < 4; ++i) gstr[i - 1] = strides_elems[i] * 2ull;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(FFVC_ERR_CUDA, "conv_halo: cuTensorMapEncodeTiled failed");
+  return FFVC_OK;
+}
+
+}  // namespace ffvc
+
+using namespace ffvc;
+
+// x: [n][h][w][cin] bf16 NHWC; w: [cout][9][cin] bf16 (tap-major); out: [n*h*w][ldc] bf16.  Epilogue fields as ffvc_gemm.
+extern "C" int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                                 const float* bias, const void* res, const void* aux, int mul_mode, int act, void* stream) {
+  if (!x || !w || !out) return set_error(FFVC_ERR_ARG, "conv_halo: null pointer");
+  if (wd % 128 != 0 || h % 2 != 0) return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: needs W % 128 == 0 and even H");
+  if (cin % 64 != 0 || cout < 1 || cout > 128) return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: needs Cin % 64 == 0, Cout <= 128");
+  static bool attr_done = false;
+  static int num_sms = 0;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_done = true;
+  }
+  const int block_n = cout > 64 ? 128 : (cout > 32 ? 64 : 32);
+  CUtensorMap tx, tw;
+  {
+    uint64_t dims[4] = {(uint64_t)cin, (uint64_t)wd, (uint64_t)h, (uint64_t)n};
+    uint64_t str[4] = {1, (uint64_t)cin, (uint64_t)wd * cin, (uint64_t)h * wd * cin};
+    uint32_t box[4] = {64, (uint32_t)kHaloPix, (uint32_t)kHaloRows, 1};
+    int rc = encode4(&tx, x, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)9 * cin, (uint64_t)cout, 1, 1};
+    uint64_t str[4] = {1, (uint64_t)9 * cin, (uint64_t)9 * cin * 8, (uint64_t)9 * cin * 8};
+    uint32_t box[4] = {64, (uint32_t)block_n, 1, 1};
+    int rc = encode4(&tw, w, dims, str, box);
+    if (rc) return rc;
+  }
+  GemmDev p;
+  memset(&p, 0, sizeof(p));
+  p.M = n * h * wd;
+  p.N = cout;
+  p.batch = n;
+  p.batch_inner = 1;
+  p.tile_m = 256;
+  p.block_n = block_n;
+  p.conv_h = h;
+  p.conv_w = wd;
+  p.conv_cblocks = cin / 64;
+  p.out = out;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(aux);
+  p.res = reinterpret_cast<const __nv_bfloat16*>(res);
+  p.bias = bias;
+  p.ldc = ldc;
+  p.bias_mode = bias ? 1 : 0;
+  p.act = act;
+  p.mul_mode = aux ? mul_mode : 0;
+  p.alpha = 1.0f;
+  const long long tiles = (long long)n * (h / 2) * (wd / 128);
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+  count_launch();
+  return FFVC_OK;
+}

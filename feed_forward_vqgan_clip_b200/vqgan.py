@@ -192,14 +192,25 @@ class DecoderEngine:
         return self._ws
 
     # ---------------------------------------------------------------- primitive ops (forward + backward closure)
+    USE_HALO = True    # shared-memory halo reuse for the wide (W % 128 == 0), <= 128-output-channel 3x3 convs
+
+    def _halo_ok(self, H, W, cin, cout):
+        return self.USE_HALO and W % 128 == 0 and H % 2 == 0 and cin % 64 == 0 and cout <= 128 and cout % 8 == 0
+
     def conv3(self, x, name, N, H, W, cin, cout, res=None, out_f32=False):
         out = self._new(N * H * W, cout, dtype=F32 if out_f32 else BF16)
+        if not out_f32 and self._halo_ok(H, W, cin, cout):
+            call("conv3x3_halo", x, self.pk[name + ".w"], out, N, H, W, cin, cout, cout, self.pk[name + ".b"], res, None, 0, 0)
+            return out
         ops.gemm(x, self.pk[name + ".w"], out, N * H * W, cout, 9 * cin, a_mode=ops.CONV3X3, conv=(N, H, W, cin),
                  bias=self.pk[name + ".b"], res=res)
         return out
 
     def conv3_dgrad(self, dy, name, N, H, W, cin, cout, res=None):
         dx = self._new(N * H * W, cin)
+        if self._halo_ok(H, W, cout, cin):
+            call("conv3x3_halo", dy, self.pk[name + ".wT"], dx, N, H, W, cout, cin, cin, None, res, None, 0, 0)
+            return dx
         ops.gemm(dy, self.pk[name + ".wT"], dx, N * H * W, cin, 9 * cout, a_mode=ops.CONV3X3, conv=(N, H, W, cout), res=res)
         return dx
 

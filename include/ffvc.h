@@ -95,6 +95,13 @@ typedef struct {
 
 int ffvc_gemm(const ffvc_gemm_params* p, void* stream);
 
+/* 3x3 conv (pad 1, stride 1) with shared-memory halo reuse: NHWC bf16 x [n][h][w][cin], packed weights [cout][9][cin]
+ * (tap-major, as for FFVC_OP_CONV3X3), bf16 out [n*h*w][ldc].  Requires w % 128 == 0, even h, cin % 64 == 0, cout <= 128:
+ * the wide 128-channel layers of the VQGAN decoder, where the tap-by-tap form is L2-bandwidth bound.
+ * Epilogue: + bias[cout] (fp32, optional), act, * act'(aux) (mul_mode), + res (bf16, optional), like ffvc_gemm. */
+int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                      const float* bias, const void* res, const void* aux, int mul_mode, int act, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (bf16 in/out, fp32 stats).  mlp_mixer_pytorch.py:11,37; cloob.py:170-176.
  * bwd: dx = LN'(dy) (+ add, the residual-path gradient); dgamma/dbeta (fp32, accumulated) optional.   */

@@ -259,3 +259,21 @@ def test_epilogue_warp_variants_agree(epi, two):
     x = aux.float()
     gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * 3.141592653589793) ** 0.5
     _check(out2, (a.float() @ b.float().t()) * gp, 2e-2)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(1, 4, 128, 64, 128), (2, 16, 128, 128, 128), (1, 6, 256, 128, 64), (2, 128, 128, 256, 128)])
+def test_conv3x3_halo_reuse(n, h, w, cin, cout):
+    from feed_forward_vqgan_clip_b200.ops import call
+    x = _rand(n, h, w, cin, seed=71)
+    wt = (_rand(cout, cin, 3, 3, seed=72).float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(cout, device=DEV)
+    res = _rand(n, h, w, cout, seed=73)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    out = torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16)
+    call("conv3x3_halo", x, wp, out, n, h, w, cin, cout, cout, bias, res, None, 0, 0)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    _check(out, ref, 2e-2)
+    # and it agrees with the tap-by-tap implicit GEMM bit-for-bit up to accumulation order
+    out2 = torch.empty_like(out)
+    ops.gemm(x, wp, out2, n * h * w, cout, 9 * cin, a_mode=ops.CONV3X3, conv=(n, h, w, cin), bias=bias, res=res)
+    _check(out, out2.float(), 1e-2)

@@ -274,6 +274,31 @@ def test_train_step_vitgan_with_l2_and_tv_vs_oracle_step():
     assert min(sims.values()) > 0.95, sims
 
 
+def test_generate_inference_path_vs_oracle():
+    """main.py:1056-1059 (test) / predict.py:113-117: forward-only mapper -> clamp -> synth"""
+    from feed_forward_vqgan_clip_b200 import api
+    mcfg = dict(input_dim=64, image_size=16, channels=64, patch_size=1, dim=128, depth=2)
+    torch.manual_seed(21)
+    net = Mixer(**mcfg)
+    with torch.no_grad():
+        net.final_proj.weight.mul_(6.0)
+        for p in net.parameters():
+            if p.dim() >= 2:
+                p.copy_(p.to(torch.bfloat16).float())
+    sd_m = {k: v.clone() for k, v in net.state_dict().items()}
+    vq, sd_v = _vq_pair(seed=8)
+    x = (torch.randn(3, 64, generator=torch.Generator().manual_seed(22)) * 0.45).to(torch.bfloat16).float()
+    img = api.generate(net.to(DEV), vq, x.to(DEV))
+    cb = sd_v["quantize.embedding.weight"]
+    with torch.no_grad():
+        z = omix.mixer_forward(sd_m, x, 16, 64).contiguous().clamp(float(cb.min()), float(cb.max()))
+        ref = ovq.synth(sd_v, z, SMALL_VQ)
+    assert img.shape == ref.shape == (3, 3, 32, 32)
+    # a flipped VQ code changes a 2x2-latent neighbourhood of pixels: compare robustly
+    diff = (img.cpu() - ref).abs()
+    assert (diff > 3e-2).float().mean().item() < 0.05, diff.max()
+
+
 def test_cuda_graph_replay_matches_eager():
     mcfg = dict(input_dim=64, image_size=16, channels=64, patch_size=1, dim=128, depth=1)
 
