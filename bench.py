@@ -110,6 +110,12 @@ def cpu_reference(steps, warmup, sample_batch):
     import oracle.vqgan as ovq
     from oracle.train_step import OracleTrainer
     from feed_forward_vqgan_clip_b200.cutouts import sample_params
+    # torchrun exports OMP_NUM_THREADS=1: the reference arm must use all the host cores it can
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, cores))
     cores = torch.get_num_threads()
     sd_m = omix.init_mixer_state_dict(CLIP_DIM, MIXER["image_size"], MIXER["channels"], MIXER["dim"], MIXER["depth"], seed=0)
     sd_v = ovq.init_vqgan_state_dict(seed=1)
@@ -129,6 +135,16 @@ def cpu_reference(steps, warmup, sample_batch):
     return dict(value=sample_batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
                 sample="%d step(s) of %d prompt(s) (config #2 nets, fp32, torch CPU, %d threads) after %d warm-up"
                        % (len(times), sample_batch, cores, warmup))
+
+
+def _finish(world):
+    """Leave without tearing NCCL down: destroying the communicator while a captured CUDA graph still references its
+    kernels can block forever (observed at N=2); the OS reclaims everything."""
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():
@@ -281,8 +297,7 @@ def main():
         ops.gemm = real_gemm
 
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
+        _finish(world)
         return
 
     fp = flops_per_prompt()
@@ -302,8 +317,7 @@ def main():
         r = cpu_reference(1, 1, args.cpu_sample_batch)
         line["cpu_baseline"] = {"value": r["value"], "unit": "prompts/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    _finish(world)
 
 
 if __name__ == "__main__":

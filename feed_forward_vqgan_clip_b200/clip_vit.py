@@ -60,19 +60,26 @@ class VisualTransformer(nn.Module):
 
 
 class CLIP(nn.Module):
-    """The slice of clip.model.CLIP the train step touches."""
+    """The slice of clip.model.CLIP the train step touches: encode_image (differentiable), encode_text (forward only),
+    logit_scale.  The text tower's parameters sit at the top level like OpenAI CLIP's state_dict (token_embedding.weight,
+    positional_embedding, transformer.*, ln_final.*, text_projection)."""
 
-    def __init__(self, cfg=VIT_B32, act="quick_gelu"):
+    def __init__(self, cfg=VIT_B32, act="quick_gelu", text_cfg=None):
         super().__init__()
         self.visual = VisualTransformer(act=act, **cfg)
         self.logit_scale = nn.Parameter(torch.ones([]) * 4.6052)
+        self.text = None
+        if text_cfg is not None:
+            from .clip_text import TextTransformer
+            self.text = TextTransformer(act=act, **text_cfg)
 
     def encode_image(self, image):
         return self.visual(image)
 
     def encode_text(self, text):
-        raise NotImplementedError("encode_text is SURVEY §8(f) 'next': the train step consumes pre-computed text "
-                                  "embeddings (main.py:733 only runs for integer token inputs)")
+        if self.text is None:
+            raise NotImplementedError("this CLIP was built without a text tower (pass text_cfg=clip_text.TEXT_B32)")
+        return self.text(text)
 
 
 class _EncodeFn(torch.autograd.Function):

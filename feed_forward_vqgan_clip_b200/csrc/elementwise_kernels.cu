@@ -117,6 +117,43 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
     ds[row * ld + i] = __float2bfloat16(i < n ? __bfloat162float(p[row * ld + i]) * (dp[row * ld + i] - dot) * scale : 0.f);
 }
 
+// causal variant (CLIP text transformer, cloob.py:304-310): row r of sequence position t = r % T attends to columns 0..t
+__global__ void __launch_bounds__(256) softmax_causal_fwd_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p,
+                                                                 long long rows, int T, int ld) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int n = (int)(row % T) + 1;
+  const float* sr = s + row * ld;
+  float mx = -FLT_MAX;
+  for (int i = lane; i < n; i += 32) mx = fmaxf(mx, sr[i]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int i = lane; i < n; i += 32) sum += __expf(sr[i] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  for (int i = lane; i < ld; i += 32) p[row * ld + i] = __float2bfloat16(i < n ? __expf(sr[i] - mx) * inv : 0.f);
+}
+// token embedding gather + positional embedding (cloob.py:526-528): x[b][t][:] = bf16(emb[tok[b][t]][:] + pos[t][:])
+__global__ void embed_tokens_kernel(const long long* __restrict__ tok, const float* __restrict__ emb, const float* __restrict__ pos,
+                                    __nv_bfloat16* __restrict__ x, long long rows, int T, int W) {
+  const long long total = rows * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / W;
+    const int w = (int)(i % W);
+    x[i] = __float2bfloat16(emb[tok[r] * W + w] + pos[(r % T) * W + w]);
+  }
+}
+// dst[b][:] = src[b*T + idx[b]][:]   (features at the EOT token, cloob.py:536)
+__global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const long long* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ dst, int B, int T, int W) {
+  const long long total = (long long)B * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / W), w = (int)(i % W);
+    dst[i] = src[((long long)b * T + idx[b]) * W + w];
+  }
+}
+
 // ---------------------------------------------------------------- bias gradients
 // db[n] += sum_rows dy[row][n]; each thread owns 8 consecutive columns (16-byte loads), n % 8 == 0 fast path
 __global__ void __launch_bounds__(128) colsum_vec_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
@@ -647,6 +684,24 @@ extern "C" int ffvc_clip_assemble(const void* pe, const float* cls, const float*
 extern "C" int ffvc_copy_rows(const void* src, void* dst, long long rows, int D, long long src_stride, long long dst_stride,
                               void* stream) {
   copy_rows_kernel<<<grid_for(rows * D, 256), 256, 0, ST(stream)>>>(CBF(src), BF(dst), rows, D, src_stride, dst_stride);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+extern "C" int ffvc_softmax_causal_fwd(const float* s, void* p, long long rows, int T, int ld, void* stream) {
+  if (ld < T) return set_error(FFVC_ERR_ARG, "softmax_causal: ld < T");
+  softmax_causal_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(s, BF(p), rows, T, ld);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_embed_tokens(const long long* tok, const float* emb, const float* pos, void* x, long long rows, int T, int W,
+                                 void* stream) {
+  embed_tokens_kernel<<<grid_for(rows * W, 256), 256, 0, ST(stream)>>>(tok, emb, pos, BF(x), rows, T, W);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_gather_rows(const void* src, const long long* idx, void* dst, int B, int T, int W, void* stream) {
+  gather_rows_kernel<<<grid_for((long long)B * W, 256), 256, 0, ST(stream)>>>(CBF(src), idx, BF(dst), B, T, W);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

@@ -132,6 +132,12 @@ int ffvc_transpose(const void* in, void* out, int B, int R, int Cc, int in_fp32,
 int ffvc_softmax_fwd(const float* s, void* p, long long rows, int n, int ld, void* stream);
 int ffvc_softmax_bwd(const void* p, const float* dp, void* ds, long long rows, int n, int ld, float scale, void* stream);
 
+/* CLIP text transformer pieces (encode_text, cloob.py:525-538): causal row softmax (row r attends to columns 0..r % T),
+ * token-embedding gather + positional add (tok int64), and the gather of the EOT-token rows. */
+int ffvc_softmax_causal_fwd(const float* s, void* p, long long rows, int T, int ld, void* stream);
+int ffvc_embed_tokens(const long long* tok, const float* emb, const float* pos, void* x, long long rows, int T, int W, void* stream);
+int ffvc_gather_rows(const void* src, const long long* idx, void* dst, int B, int T, int W, void* stream);
+
 /* bias gradients: db[n] += sum_rows dy[row][n];  db[j] += sum_{b,d} dy[b][j][d]. */
 int ffvc_colsum(const void* dy, float* db, long long rows, int n, void* stream);
 int ffvc_rowsum(const void* dy, float* db, int B, int J, int D, void* stream);

@@ -72,6 +72,24 @@ def golden_clip():
                os.path.join(OUT, "clip_vit.pt"))
 
 
+def golden_clip_text():
+    from cloob import TextTransformer
+    torch.manual_seed(5)
+    cfg = dict(embed_dim=32, context_length=77, vocab_size=300, transformer_width=128, transformer_heads=2, transformer_layers=2)
+    net = TextTransformer(**cfg)
+    for p in net.parameters():
+        p.data.add_(0.02 * torch.randn_like(p))
+    text = torch.zeros(4, 77, dtype=torch.long)
+    for b in range(4):
+        n = 5 + 7 * b
+        text[b, :n] = torch.randint(1, 298, (n,))
+        text[b, n] = 299                                   # EOT = highest id
+    with torch.no_grad():
+        y = net(text)
+    torch.save(dict(cfg=cfg, state_dict={k: v.detach().clone() for k, v in net.state_dict().items()}, text=text, y=y),
+               os.path.join(OUT, "clip_text.pt"))
+
+
 def golden_glue():
     for name in ["clize", "omegaconf", "kornia", "kornia.augmentation", "taming", "taming.models",
                  "taming.models.cond_transformer", "taming.models.vqgan", "taming.modules", "taming.modules.losses",
@@ -128,6 +146,7 @@ if __name__ == "__main__":
     golden_mixer()
     golden_vitgan()
     golden_clip()
+    golden_clip_text()
     golden_glue()
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".pt"):
