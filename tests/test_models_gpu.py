@@ -299,6 +299,17 @@ def test_generate_inference_path_vs_oracle():
     assert (diff > 3e-2).float().mean().item() < 0.05, diff.max()
 
 
+def test_clip_encode_text_vs_reference_golden():
+    """encode_text on token ids (main.py:733): compared with the output of the reference's in-tree CLIP text tower"""
+    import os
+    from feed_forward_vqgan_clip_b200.clip_text import TextTransformer
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "clip_text.pt"))
+    net = TextTransformer(**g["cfg"])
+    net.load_state_dict(g["state_dict"])
+    y = net.to(DEV)(g["text"].to(DEV))
+    close(y, g["y"], 3e-2, "encode_text")
+
+
 def test_cuda_graph_replay_matches_eager():
     mcfg = dict(input_dim=64, image_size=16, channels=64, patch_size=1, dim=128, depth=1)
 

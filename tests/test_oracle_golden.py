@@ -51,6 +51,13 @@ def test_clip_oracle_matches_reference_twin():
     assert sum(v.numel() for v in oclip.init_clip_state_dict().values()) == 87849216
 
 
+def test_clip_text_oracle_matches_reference_twin():
+    import oracle.clip_text as otext
+    g = torch.load(os.path.join(G, "clip_text.pt"))
+    y = otext.encode_text(g["state_dict"], g["text"], g["cfg"]["transformer_heads"])
+    assert torch.allclose(y, g["y"], rtol=1e-4, atol=1e-5), (y - g["y"]).abs().max()
+
+
 def test_glue_oracle_matches_reference_main_py():
     g = torch.load(os.path.join(G, "glue.pt"))
     c = g["clamp"]
