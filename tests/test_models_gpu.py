@@ -125,6 +125,44 @@ def test_vitgan_forward_backward_vs_oracle(dim, heads):
     assert not bad, bad
 
 
+# ----------------------------------------------------------------------------------------------------- X-transformer mapper
+def test_xtransformer_forward_backward_vs_oracle():
+    import oracle.xtransformer as oxt
+    from feed_forward_vqgan_clip_b200.xtransformer import XTransformer
+    cfg = dict(input_dim=64, image_size=16, channels=64, dim=128, depth=2, heads=2, initial_proj=True, add_input=False)
+    torch.manual_seed(5)
+    net = XTransformer(**cfg)
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if p.dim() >= 2:
+                p.copy_(p.to(torch.bfloat16).float())
+    sd_ref = {k: v.clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    net = net.to(DEV)
+    B = 2
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, 64, generator=g).to(torch.bfloat16).float()
+    w = torch.randn(B, 64, 16, 16, generator=g)
+    y = net(x.to(DEV))
+    yr = oxt.xtransformer_forward(sd_ref, x, 16, 64, 2)
+    assert y.shape == yr.shape
+    close(y, yr, 3e-2, "xtransformer fwd")
+    (y * w.to(DEV)).sum().backward()
+    (yr * w).sum().backward()
+    bad = []
+    for n, p in net.named_parameters():
+        ref_g = sd_ref[n].grad
+        if ref_g is None:
+            continue
+        live = ref_g[:256] if n.endswith("pos_emb.emb.weight") else ref_g
+        mine = p.grad[:256] if n.endswith("pos_emb.emb.weight") else p.grad
+        c = cos(mine, live)
+        err = (mine.detach().float().cpu() - live).abs().max().item()
+        scale = live.abs().max().item() + 1e-9
+        if not (c > 0.99 and err <= 6e-2 * scale):
+            bad.append((n, round(c, 4), err, scale))
+    assert not bad, bad
+
+
 # ----------------------------------------------------------------------------------------------------- VQGAN decoder
 def _vq_pair(seed=0):
     sd = bf16_round_sd(ovq.init_vqgan_state_dict(SMALL_VQ, seed=seed))
