@@ -42,12 +42,14 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == FFVC_ACT_GELU) return gelu_f(v);
   if (act == FFVC_ACT_QUICKGELU) return quick_gelu_f(v);
   if (act == FFVC_ACT_SWISH) return swish_f(v);
+  if (act == FFVC_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 __device__ __forceinline__ float apply_act_grad(float x, int act) {
   if (act == FFVC_ACT_GELU) return gelu_grad_f(x);
   if (act == FFVC_ACT_QUICKGELU) return quick_gelu_grad_f(x);
   if (act == FFVC_ACT_SWISH) return swish_grad_f(x);
+  if (act == FFVC_ACT_RELU) return x > 0.f ? 1.0f : 0.f;
   return 1.0f;
 }
 __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
@@ -76,6 +78,9 @@ __device__ __forceinline__ void act_chunk(float (&v)[CW], int act) {
   } else if (act == FFVC_ACT_SWISH) {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] = swish_f(v[i]);
+  } else if (act == FFVC_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
   }
 }
 template <int CW>
@@ -89,6 +94,9 @@ __device__ __forceinline__ void mulgrad_chunk(float (&v)[CW], const float (&x)[C
   } else if (act == FFVC_ACT_SWISH) {
 #pragma unroll
     for (int i = 0; i < CW; ++i) v[i] *= swish_grad_f(x[i]);
+  } else if (act == FFVC_ACT_RELU) {   // aux may be the pre- or the post-activation tensor: relu(x) > 0 <=> x > 0
+#pragma unroll
+    for (int i = 0; i < CW; ++i) v[i] = x[i] > 0.f ? v[i] : 0.f;
   }
 }
 template <int CW>

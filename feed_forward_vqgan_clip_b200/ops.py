@@ -9,7 +9,7 @@ from ._lib import GemmParams, check
 
 KMAJOR, MNMAJOR, CONV3X3 = 0, 1, 2
 ROLE_BCAST, ROLE_OUT, ROLE_SEG = 0, 1, 2
-ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_SWISH = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_SWISH, ACT_RELU = 0, 1, 2, 3, 4
 
 BF16 = torch.bfloat16
 F32 = torch.float32

@@ -53,7 +53,7 @@ class FusedAdam:
 
 class TrainStep:
     def __init__(self, net, vq, perceptor, cutn=8, lr=1e-3, cut_size=224, target_loss_coef=1.0, world_size=1,
-                 process_group=None, seed=0, l2_coef=0.0, tv_coef=0.0):
+                 process_group=None, seed=0, l2_coef=0.0, tv_coef=0.0, diversity_coef=0.0, repeat=1, lpips_net=None):
         self.net, self.vq, self.perceptor = net, vq, perceptor
         self.mix = net.engine()
         self.dec = vq.engine()
@@ -63,7 +63,9 @@ class TrainStep:
         self.cut = CutoutEngine(cut_size, cutn, self.clip.patch, self.dev)
         self.coef = target_loss_coef
         self.l2_coef, self.tv_coef = float(l2_coef), float(tv_coef)          # main.py:690-691,758-773,831
-        self.aux_loss = torch.zeros(2, device=self.dev, dtype=F32)           # [l2, tv] (already scaled by their coefficients)
+        self.aux_loss = torch.zeros(3, device=self.dev, dtype=F32)           # [l2, tv, -diversity] (already scaled by their coefficients)
+        self.diversity_coef, self.repeat = float(diversity_coef), int(repeat)  # main.py:532-537,739-740,776-791
+        self.div = lpips_net.engine() if (lpips_net is not None and self.diversity_coef != 0) else None
         self.opt = FusedAdam(self.mix, lr=lr)
         self.world, self.pg = world_size, process_group
         self.opt.set_grad_scale(1.0 / world_size)
@@ -95,6 +97,8 @@ class TrainStep:
         del sv_e
         dimg = cut.backward(sv_c, dpatch)
         del sv_c, dpatch
+        if self.div is not None and self.repeat > 1:                     # - diversity_coef * div, main.py:776-791,831
+            self.div.forward_backward(img, self.repeat, B // self.repeat, self.diversity_coef, dimg, self.aux_loss[2:3])
         if self.tv_coef > 0:                                             # tv_coef * tv_loss(xr), main.py:769-773,831
             H = img.shape[1]
             call("tv_loss", img, self.aux_loss[1:2], dimg, B, H, img.shape[2], 3, self.tv_coef)
@@ -139,6 +143,8 @@ class TrainStep:
         """Eager step.  inp / out_feats: (B, clip_dim) fp32 CUDA tensors; prm: explicit cutout parameters or None."""
         if out_feats is None:
             out_feats = inp
+        if self.repeat > 1:                                              # main.py:739-740
+            inp, out_feats = inp.repeat(self.repeat, 1), out_feats.repeat(self.repeat, 1)
         B = inp.shape[0]
         prm = self._stage_params(prm if prm is not None else self.new_params(B), B)
         return self._device_step(inp.contiguous().float(), out_feats.contiguous().float(), prm)

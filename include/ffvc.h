@@ -38,7 +38,7 @@ enum { FFVC_OP_KMAJOR = 0, FFVC_OP_MNMAJOR = 1, FFVC_OP_CONV3X3 = 2 };
 /* role of an operand's 3rd (batch) dimension */
 enum { FFVC_ROLE_BROADCAST = 0, FFVC_ROLE_OUT_BATCH = 1, FFVC_ROLE_K_SEGMENT = 2 };
 /* activations */
-enum { FFVC_ACT_NONE = 0, FFVC_ACT_GELU = 1, FFVC_ACT_QUICKGELU = 2, FFVC_ACT_SWISH = 3 };
+enum { FFVC_ACT_NONE = 0, FFVC_ACT_GELU = 1, FFVC_ACT_QUICKGELU = 2, FFVC_ACT_SWISH = 3, FFVC_ACT_RELU = 4 };
 
 const char* ffvc_last_error(void);
 /* library / build information: returns the sm arch the kernels were compiled for (100). */
@@ -202,6 +202,18 @@ int ffvc_spherical_loss(const float* embed, const float* target, float* loss_out
  * axpy for the z-L2 term's gradient (main.py:758-762). */
 int ffvc_tv_loss(const float* img, float* loss_accum, float* dimg_accum, int B, int H, int W, int C, float coef, void* stream);
 int ffvc_axpy_f32(const float* x, float* y, float a, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LPIPS-VGG16 diversity term (main.py:532-537,776-791): 2x2 max-pool on NHWC bf16, per-channel image normalisation on NHWC
+ * fp32 x 3 (mean / std are HOST float[3]; the backward ACCUMULATES into dx), and the fused normalize_tensor + pairwise
+ * squared difference of the `repeat` samples of each prompt for one VGG tap: feats [R*B][HW][C] bf16 (sample r*B + b),
+ * loss_accum += scale * div, dfeat = scale * d(div)/d(feats). */
+int ffvc_maxpool2x2_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int ffvc_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+int ffvc_normalize3_fwd(const float* x, float* y, long long n, const float* mean, const float* std_, void* stream);
+int ffvc_normalize3_bwd(const float* dy, float* dx_accum, long long n, const float* std_, void* stream);
+int ffvc_relu_mask(const void* g, const void* post, void* out, long long n, void* stream);
+int ffvc_diversity_tap(const void* feats, float* loss_accum, void* dfeat, int R, int B, int HW, int C, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * VitGAN mapper pieces (vitgan.py:8-21,44-97,254-260).

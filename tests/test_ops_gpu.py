@@ -339,3 +339,52 @@ def test_sln_and_vitgan_attention_kernels():
     dst = torch.empty(40, 128, device=DEV, dtype=BF)
     call("cast_f32_bf16_pitched", src, dst, 40, 126, 128)
     assert torch.equal(dst[:, :126], src.to(BF)) and float(dst[:, 126:].abs().max()) == 0.0
+
+
+def test_lpips_diversity_engine_vs_oracle():
+    """VGG16 taps + normalize_tensor + pairwise differences (main.py:776-782): value and gradient w.r.t. the image"""
+    import oracle.lpips as ol
+    from feed_forward_vqgan_clip_b200.lpips import LpipsVGG16
+    from feed_forward_vqgan_clip_b200.cutouts import CLIP_MEAN, CLIP_STD
+    sd = {k: (v.to(BF).float() if v.dim() == 4 else v) for k, v in ol.init_vgg_state_dict(seed=3).items()}
+    net = LpipsVGG16()
+    net.load_state_dict(sd)
+    eng = net.to(DEV).engine()
+    R, bs, H = 2, 1, 256
+    g = torch.Generator().manual_seed(4)
+    xr = torch.rand(R * bs, 3, H, H, generator=g)
+    mean, std = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1), torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+    xo = xr.clone().requires_grad_(True)
+    div = ol.diversity(sd, xo, R, bs, mean, std)
+    (-0.7 * div).backward()
+    img = xr.permute(0, 2, 3, 1).contiguous().to(DEV)
+    dimg = torch.zeros_like(img)
+    loss = torch.zeros(1, device=DEV)
+    eng.forward_backward(img, R, bs, 0.7, dimg, loss)
+    assert abs(loss.item() - (-0.7 * div.item())) < 3e-2 * abs(0.7 * div.item()), (loss.item(), div.item())
+    ref = xo.grad.permute(0, 2, 3, 1)
+    mine = dimg.cpu()
+    cs = float((mine * ref).sum() / (mine.norm() * ref.norm() + 1e-30))
+    assert cs > 0.98, cs
+
+
+def test_maxpool_and_relu_epilogue():
+    x = rnd(2, 8, 8, 64, seed=1)
+    y = torch.empty(2, 4, 4, 64, device=DEV, dtype=BF)
+    call("maxpool2x2_fwd", x, y, 2, 8, 8, 64)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    assert torch.equal(y.float(), yr.permute(0, 2, 3, 1))
+    dy = rnd(2, 4, 4, 64, seed=2)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    dx = torch.empty_like(x)
+    call("maxpool2x2_bwd", x, dy, dx, 2, 8, 8, 64)
+    assert torch.equal(dx.float(), xr.grad.permute(0, 2, 3, 1))
+    a, b = rnd(256, 64, seed=3), rnd(128, 64, seed=4)
+    out = torch.empty(256, 128, device=DEV, dtype=BF)
+    ops.gemm(a, b, out, 256, 128, 64, act=ops.ACT_RELU)
+    close(out, torch.relu(a.float() @ b.float().t()))
+    aux = rnd(256, 128, seed=5)
+    out2 = torch.empty(256, 128, device=DEV, dtype=BF)
+    ops.gemm(a, b, out2, 256, 128, 64, aux=aux, mul_mode=ops.ACT_RELU)
+    close(out2, (a.float() @ b.float().t()) * (aux.float() > 0))
