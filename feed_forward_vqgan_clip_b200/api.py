@@ -80,12 +80,15 @@ def load_clip_model(model_type="ViT-B/32", path=None):
         act = "quick_gelu"
     else:
         raise NotImplementedError("perceptor %r (only the ViT-B/32 family is on the benchmark path)" % model_type)
-    model = CLIP(VIT_B32, act=act)
+    from .clip_text import TEXT_B32
+    model = CLIP(VIT_B32, act=act, text_cfg=TEXT_B32)
     if path and os.path.exists(path):
         sd = torch.load(path, map_location="cpu")
         sd = sd.get("state_dict", sd)
         vis = {k[len("visual."):]: v.float() for k, v in sd.items() if k.startswith("visual.")}
         model.visual.load_state_dict(vis)
+        txt = {k: v.float() for k, v in sd.items() if k in model.text.state_dict()}
+        model.text.load_state_dict(txt, strict=False)
     return model.eval().requires_grad_(False)
 
 
@@ -108,4 +111,6 @@ def train_step(net, vq, perceptor, config=None, **kw):
     """Build the fused step object for `net` (Mixer), `vq` (VQModel) and `perceptor` (CLIP), all on the same GPU."""
     cfg = config or {}
     return TrainStep(net, vq, perceptor, cutn=_get(cfg, "cutn", 8), lr=_get(cfg, "lr", 1e-3),
-                     target_loss_coef=_get(cfg, "target_loss_coef", 1.0), **kw)
+                     target_loss_coef=_get(cfg, "target_loss_coef", 1.0), l2_coef=_get(cfg, "l2_coef", 0.0) or 0.0,
+                     tv_coef=_get(cfg, "tv_coef", 0.0) or 0.0, diversity_coef=_get(cfg, "diversity_coef", 0.0) or 0.0,
+                     repeat=_get(cfg, "repeat", 1) or 1, **kw)
