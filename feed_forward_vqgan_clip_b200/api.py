@@ -93,7 +93,7 @@ def load_clip_model(model_type="ViT-B/32", path=None):
 
 
 @torch.no_grad()
-def generate(net, vq, inp_feats):
+def generate(net, vq, inp_feats, return_indices=False):
     """Inference path of `test` / `predict` (main.py:1056-1059, predict.py:113-117): mapper -> clamp -> VQ -> decode,
     forward only, every kernel from libffvc_sm100.so.  inp_feats: (B, clip_dim [+ noise_dim]) fp32 CUDA tensor.
     Returns the generated images (B, 3, 16*S, 16*S) in [0, 1] (what the reference hands to `make_grid`)."""
@@ -102,9 +102,10 @@ def generate(net, vq, inp_feats):
     B = x.shape[0]
     z, _ = mix.forward(x)                                    # [B*S*S, C] fp32 token-major
     lo, hi = float(dec.codebook.min()), float(dec.codebook.max())      # main.py:1057-1058: clamp to the codebook range
-    zq, _, _ = dec.quantize(z, lo, hi)
+    zq, idx, _ = dec.quantize(z, lo, hi)
     img, _ = dec.forward(zq.view(B, mix.S, mix.S, mix.C))    # [B, H, W, 3] fp32, already (x+1)/2 clamped to [0,1]
-    return img.permute(0, 3, 1, 2)
+    img = img.permute(0, 3, 1, 2)
+    return (img, idx.view(B, mix.S, mix.S)) if return_indices else img
 
 
 def train_step(net, vq, perceptor, config=None, **kw):

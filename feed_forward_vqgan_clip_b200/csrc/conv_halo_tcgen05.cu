@@ -7,7 +7,9 @@
 // 2 output rows x 128 pixels; per 64-channel chunk it loads the (2+2) x (128+2) pixel HALO once (one TMA box, 128B
 // swizzle, zero fill = padding) and the nine taps are nine UMMA descriptors into that same buffer: output row `sub`, tap
 // (r, s) starts at halo row (sub + r), pixel s — 128 consecutive 128-byte rows.  Those start addresses are 128 B- but not
-// 1024 B-aligned, so the descriptor carries the swizzle phase in its base-offset field ((addr >> 7) & 7).
+// 1024 B-aligned.  Measured on B200: the tensor core applies the 128B-swizzle XOR to the ABSOLUTE shared-memory address
+// (bits [4:6] ^= bits [7:9]), exactly like TMA does when it writes the box, so the descriptor needs NO base-offset: with
+// the field left 0 the results are exact, with ((addr >> 7) & 7) in it they are garbage (both variants were run).
 // A-operand traffic drops 9x (66.5 KB per 64-channel chunk instead of 9 x 32 KB); weights stream through a 4-stage ring.
 //
 // Same warp roles, TMEM double buffering and fused epilogue as gemm_tcgen05_kernel (gemm_common.cuh).
@@ -34,11 +36,9 @@ static constexpr int kHaloSmem = 2 * kHaloStride + kBStages * kBStageBytes + 102
 static constexpr int kHaloThreads = 320;
 static constexpr int kHaloEpiWarps = 8;
 
-// descriptor for a K-major, 128B-swizzled operand whose start is 128 B- (not 1024 B-) aligned
+// descriptor for a K-major, 128B-swizzled operand whose start is 128 B- (not 1024 B-) aligned: base-offset field stays 0
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t saddr) {
-  uint64_t d = umma_smem_desc_sw128(saddr, 16u, 1024u);
-  d |= static_cast<uint64_t>((saddr >> 7) & 7u) << 49;   // matrix base offset = swizzle phase of the first row
-  return d;
+  return umma_smem_desc_sw128(saddr, 16u, 1024u);
 }
 
 __global__ void __launch_bounds__(kHaloThreads, 1)

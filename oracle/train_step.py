@@ -26,21 +26,23 @@ class OracleTrainer:
         self.last_indices = None
         self.l2_coef, self.tv_coef, self.mapper, self.num_heads = l2_coef, tv_coef, mapper, num_heads
 
-    def step(self, inp_feats, out_feats, prm):
+    def step(self, inp_feats, out_feats, prm, force_idx=None):
         if self.mapper == "vitgan":
             from . import vitgan as ovit
             z = ovit.vitgan_forward(self.params, inp_feats, self.C, self.num_heads).contiguous()
         else:
             z = omix.mixer_forward(self.params, inp_feats, self.S, self.C).contiguous()      # main.py:754-757
+        z.retain_grad()
+        self.last_z = z
         l2 = (z ** 2).mean() if self.l2_coef > 0 else 0.0                                    # main.py:758-762
         z = ovq.clamp_with_grad(z, self.z_lo, self.z_hi)                                     # main.py:763
-        xr, idx = ovq.synth(self.sd_vq, z, self.vq_cfg, return_indices=True)                 # main.py:767
+        xr, idx = ovq.synth(self.sd_vq, z, self.vq_cfg, return_indices=True, force_idx=force_idx)   # main.py:767
         self.last_indices = idx
         x = ocut.make_cutouts(xr, self.cutn, prm, self.cut_size, normalize=True)             # main.py:796-797
         embed = oclip.encode_image(self.sd_clip, x, self.clip_cfg, act=self.act).float()     # main.py:799
         tv = oloss.tv_loss(xr) if self.tv_coef > 0 else 0.0                                  # main.py:769-773
         dists = oloss.spherical_dist_loss(embed, out_feats, self.cutn)                       # main.py:801-811
-        self.last_terms = (float(dists), float(l2), float(tv))
+        self.last_terms = tuple(float(t.detach()) if torch.is_tensor(t) else float(t) for t in (dists, l2, tv))
         loss = dists + self.l2_coef * l2 + self.tv_coef * tv                                 # main.py:831
         self.opt.zero_grad()                                                                 # main.py:825
         loss.backward()                                                                      # main.py:832

@@ -117,15 +117,17 @@ class _ClampWithGrad(torch.autograd.Function):    # main.py:118-129
 clamp_with_grad = _ClampWithGrad.apply
 
 
-def vector_quantize(x, codebook):                 # main.py:134-138
+def vector_quantize(x, codebook, force_idx=None):                 # main.py:134-138
+    """force_idx (tests only): use these code indices instead of the argmin — lets a parity test compare gradients
+    downstream of the quantiser without the few near-tie flips bf16 mapper noise produces."""
     d = x.pow(2).sum(dim=-1, keepdim=True) + codebook.pow(2).sum(dim=1) - 2 * x @ codebook.T
-    idx = d.argmin(-1)
+    idx = d.argmin(-1) if force_idx is None else force_idx.view(d.shape[:-1]).long()
     x_q = F.one_hot(idx, codebook.shape[0]).to(d.dtype) @ codebook
     return _ReplaceGrad.apply(x_q, x), idx
 
 
-def synth(sd, z, cfg=F16_16384, return_indices=False):   # main.py:140-143
-    z_q, idx = vector_quantize(z.movedim(1, 3), sd["quantize.embedding.weight"])
+def synth(sd, z, cfg=F16_16384, return_indices=False, force_idx=None):   # main.py:140-143
+    z_q, idx = vector_quantize(z.movedim(1, 3), sd["quantize.embedding.weight"], force_idx)
     x = clamp_with_grad(decode(sd, z_q.movedim(3, 1), cfg).add(1).div(2), 0, 1)
     return (x, idx) if return_indices else x
 

@@ -114,12 +114,16 @@ def test_vitgan_forward_backward_vs_oracle(dim, heads):
     (y * w.to(DEV)).sum().backward()
     (yr * w).sum().backward()
     bad = []
+    # the SLN gamma / beta are scalars: their gradient is ONE sum over B*T*D products that largely cancel, so bf16 storage
+    # noise of the summands (measured on the CPU by rounding the oracle's SLN tensors: +-0.1 at these sizes) is compared
+    # with the common magnitude of those sums, not with the (possibly near-zero) value of an individual one
+    scalar_scale = max(sd_ref[n].grad.abs().max().item() for n, p in net.named_parameters() if p.numel() == 1)
     for n, p in net.named_parameters():
         ref_g = sd_ref[n].grad
         c = cos(p.grad, ref_g)
         err = (p.grad.detach().float().cpu() - ref_g).abs().max().item()
         scale = ref_g.abs().max().item() + 1e-9
-        ok = (c > 0.99 and err <= 6e-2 * scale) if p.numel() > 1 else err <= 6e-2 * max(scale, 1.0)
+        ok = (c > 0.99 and err <= 6e-2 * scale) if p.numel() > 1 else err <= 1e-2 * max(scalar_scale, 1.0)
         if not ok:
             bad.append((n, round(c, 4), err, scale))
     assert not bad, bad
@@ -255,11 +259,14 @@ def test_train_step_vs_oracle_step():
     torch.cuda.synchronize()
     otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 64, SMALL_VQ, SMALL_CLIP, cutn=cutn, lr=lr)
     ref_loss = otr.step(x, x, prm)
-    ref_idx, ref_grads = otr.last_indices, otr.grads
-    ref_params = {k: v.detach() for k, v in otr.params.items()}
-    agree = (ts.last_indices.cpu().long().view(-1) == ref_idx.view(-1)).float().mean().item()
+    agree = (ts.last_indices.cpu().long().view(-1) == otr.last_indices.view(-1)).float().mean().item()
     assert agree > 0.97, agree                                  # bf16 mapper noise may flip a few near-tie codes
     assert abs(loss.item() - ref_loss) < 3e-2 * abs(ref_loss), (loss.item(), ref_loss)
+    # gradients: the argmin is discontinuous, so the oracle is re-run on the SAME code indices the CUDA step picked
+    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 64, SMALL_VQ, SMALL_CLIP, cutn=cutn, lr=lr)
+    otr.step(x, x, prm, force_idx=ts.last_indices.cpu().long())
+    ref_grads = otr.grads
+    ref_params = {k: v.detach() for k, v in otr.params.items()}
     eng = net.engine()
     sims = {}
     for (n, p), gv in zip(net.named_parameters(), eng.grad_views):
@@ -308,6 +315,9 @@ def test_train_step_vitgan_with_l2_and_tv_vs_oracle_step():
     assert abs(aux[0] - 0.1 * l2) < 3e-2 * 0.1 * l2 + 1e-6, (aux, l2)
     assert abs(aux[1] - 0.5 * tv) < 5e-2 * 0.5 * tv + 1e-6, (aux, tv)
     eng = net.engine()
+    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 64, SMALL_VQ, SMALL_CLIP, cutn=cutn, lr=lr, l2_coef=0.1, tv_coef=0.5,
+                        mapper="vitgan", num_heads=6)
+    otr.step(x, x, prm, force_idx=ts.last_indices.cpu().long())   # same code indices as the CUDA step (argmin is discontinuous)
     sims = {n: cos(gv, otr.grads[n]) for (n, p), gv in zip(net.named_parameters(), eng.grad_views) if p.numel() >= 4096}
     assert min(sims.values()) > 0.95, sims
 
@@ -326,15 +336,19 @@ def test_generate_inference_path_vs_oracle():
     sd_m = {k: v.clone() for k, v in net.state_dict().items()}
     vq, sd_v = _vq_pair(seed=8)
     x = (torch.randn(3, 64, generator=torch.Generator().manual_seed(22)) * 0.45).to(torch.bfloat16).float()
-    img = api.generate(net.to(DEV), vq, x.to(DEV))
+    img, idx = api.generate(net.to(DEV), vq, x.to(DEV), return_indices=True)
     cb = sd_v["quantize.embedding.weight"]
     with torch.no_grad():
         z = omix.mixer_forward(sd_m, x, 16, 64).contiguous().clamp(float(cb.min()), float(cb.max()))
-        ref = ovq.synth(sd_v, z, SMALL_VQ)
+        _, ref_idx = ovq.synth(sd_v, z, SMALL_VQ, return_indices=True)
+        # the decoder mixes globally (attention at 16x16, GroupNorm): one flipped near-tie code moves every pixel a little,
+        # so the image is compared with the oracle decoding the SAME codes and the codes are compared separately
+        ref = ovq.synth(sd_v, z, SMALL_VQ, force_idx=idx.cpu().long())
+    agree = (idx.cpu().long().view(-1) == ref_idx.view(-1)).float().mean().item()
+    assert agree > 0.97, agree
     assert img.shape == ref.shape == (3, 3, 32, 32)
-    # a flipped VQ code changes a 2x2-latent neighbourhood of pixels: compare robustly
-    diff = (img.cpu() - ref).abs()
-    assert (diff > 3e-2).float().mean().item() < 0.05, diff.max()
+    close(img, ref, 3e-2, "generate")
+    assert float(img.min()) >= 0 and float(img.max()) <= 1
 
 
 def test_clip_encode_text_vs_reference_golden():
