@@ -276,9 +276,9 @@ static int encode4(CUtensorMap* m, const void* base, const uint64_t* dims, const
 
 using namespace ffvc;
 
-// x: [n][h][w][cin] bf16 NHWC; w: [cout][9][cin] bf16 (tap-major); out: [n*h*w][ldc] bf16.  Epilogue fields as ffvc_gemm.
+// x: [n][h][w][cin] bf16 NHWC; w: [cout][9][cin] bf16 (tap-major); out: [n*h*w][ldc] bf16 (fp32 when out_fp32).  Epilogue fields as ffvc_gemm.
 extern "C" int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
-                                 const float* bias, const void* res, const void* aux, int mul_mode, int act, void* stream) {
+                                 const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32, void* stream) {
   if (!x || !w || !out) return set_error(FFVC_ERR_ARG, "conv_halo: null pointer");
   if (wd % 128 != 0 || h % 2 != 0) return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: needs W % 128 == 0 and even H");
   if (cin % 64 != 0 || cout < 1 || cout > 128) return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: needs Cin % 64 == 0, Cout <= 128");
@@ -324,6 +324,7 @@ extern "C" int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n,
   p.res = reinterpret_cast<const __nv_bfloat16*>(res);
   p.bias = bias;
   p.ldc = ldc;
+  p.out_fp32 = out_fp32 ? 1 : 0;
   p.bias_mode = bias ? 1 : 0;
   p.act = act;
   p.mul_mode = aux ? mul_mode : 0;

@@ -155,27 +155,67 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const 
 }
 
 // ---------------------------------------------------------------- bias gradients
-// db[n] += sum_rows dy[row][n]; each thread owns 8 consecutive columns (16-byte loads), n % 8 == 0 fast path
-__global__ void __launch_bounds__(128) colsum_vec_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
+// db[n] += sum_rows dy[row][n], n % 8 == 0.  One persistent CTA per SM, 512 threads = (row lanes) x (8-column vectors);
+// 8 rows in flight per thread (16-byte loads), row lanes folded through shared memory, then ONE vector reduction
+// (red.global.add.v4.f32) per 4 columns per CTA: the earlier form issued a scalar atomic per column from 512 small CTAs and
+// was bound by same-line atomic serialisation (0.7 TB/s); this one streams at HBM rate.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__global__ void __launch_bounds__(512) colsum_vec_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
                                                          long long rows, int n, int rows_per_cta) {
-  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  extern __shared__ float cs[];                       // [lanes][ncv*8] partials when lanes > 1
+  const int ncv = n >> 3;                             // column vectors
+  const int lanes = max(1, (int)blockDim.x / ncv);    // row lanes that fit in the CTA
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
   const long long r1 = min(rows, r0 + rows_per_cta);
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (c >= n) return;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll 4
-  for (long long r = r0; r < r1; ++r) {
-    const uint4 pk = *reinterpret_cast<const uint4*>(dy + r * n + c);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+  {
+    const int cv0 = blockIdx.y * blockDim.x;            // column block (gridDim.y > 1 only when n > 4096)
+    const int t = threadIdx.x;
+    const int cv = cv0 + (lanes > 1 ? t % ncv : t);
+    const int rl = lanes > 1 ? t / ncv : 0;
+    const bool active = cv < ncv && rl < lanes;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+      const __nv_bfloat16* base = dy + (long long)cv * 8;
+      for (long long r = r0 + rl; r < r1; r += (long long)lanes * 8) {
+        uint4 pk[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(h[j]);
-      acc[2 * j] += f.x;
-      acc[2 * j + 1] += f.y;
+        for (int u = 0; u < 8; ++u) {
+          const long long rr = r + (long long)u * lanes;
+          pk[u] = rr < r1 ? __ldcs(reinterpret_cast<const uint4*>(base + rr * n)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[u]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            acc[2 * j] += f.x;
+            acc[2 * j + 1] += f.y;
+          }
+        }
+      }
+    }
+    if (lanes > 1) {
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cs[(rl * ncv + cv) * 8 + j] = acc[j];
+      }
+      __syncthreads();
+      if (active && rl == 0) {
+        for (int l = 1; l < lanes; ++l) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += cs[(l * ncv + cv) * 8 + j];
+        }
+      }
+      __syncthreads();
+    }
+    if (active && rl == 0) {
+      red_add_v4(db + cv * 8, acc[0], acc[1], acc[2], acc[3]);
+      red_add_v4(db + cv * 8 + 4, acc[4], acc[5], acc[6], acc[7]);
     }
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&db[c + j], acc[j]);
 }
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
                                                      long long rows, int n, int rows_per_cta) {
@@ -187,7 +227,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
   for (long long r = r0; r < r1; ++r) acc += __bfloat162float(dy[r * n + c]);
   atomicAdd(&db[c], acc);
 }
-// db[j] += sum_{b,d} dy[b][j][d]   (row-bias of the token-mixing Conv1d)
+// db[j] += sum_{b,d} dy[b][j][d]   (row-bias of the token-mixing Conv1d); one warp per row, 16-byte loads when D % 8 == 0
 __global__ void __launch_bounds__(256) rowsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db, int B,
                                                      int J, int D) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -195,7 +235,26 @@ __global__ void __launch_bounds__(256) rowsum_kernel(const __nv_bfloat16* __rest
   if (row >= (long long)B * J) return;
   const __nv_bfloat16* r = dy + row * D;
   float acc = 0.f;
-  for (int i = lane; i < D; i += 32) acc += __bfloat162float(r[i]);
+  if ((D & 7) == 0) {
+    const uint4* rv = reinterpret_cast<const uint4*>(r);
+    const int nv = D >> 3;
+    for (int i = lane; i < nv; i += 128) {
+      uint4 pk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pk[u] = (i + 32 * u < nv) ? __ldcs(rv + i + 32 * u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[u]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          acc += f.x + f.y;
+        }
+      }
+    }
+  } else {
+    for (int i = lane; i < D; i += 32) acc += __bfloat162float(r[i]);
+  }
   acc = warp_sum(acc);
   if (lane == 0) atomicAdd(&db[row % J], acc);
 }
@@ -566,13 +625,22 @@ extern "C" int ffvc_softmax_bwd(const void* p, const float* dp, void* ds, long l
   return FFVC_OK;
 }
 extern "C" int ffvc_colsum(const void* dy, float* db, long long rows, int n, void* stream) {
-  if (n % 8 == 0) {
-    // enough CTAs to fill the machine: (n/1024 column blocks) x (row chunks)
-    const int cols_blocks = (n / 8 + 127) / 128;
-    int rows_per_cta = 512;
-    while (rows_per_cta > 32 && (long long)cols_blocks * ((rows + rows_per_cta - 1) / rows_per_cta) < 148 * 4) rows_per_cta >>= 1;
-    dim3 grid(cols_blocks, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
-    colsum_vec_kernel<<<grid, 128, 0, ST(stream)>>>(CBF(dy), db, rows, n, rows_per_cta);
+  if (n % 8 == 0 && (reinterpret_cast<uintptr_t>(db) & 15) == 0) {
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    const int ncv = n / 8;
+    const int lanes = ncv >= 512 ? 1 : 512 / ncv;
+    long long rows_per_cta = (rows + sms - 1) / sms;
+    const long long q = (long long)lanes * 8;                      // whole unrolled row batches per CTA
+    rows_per_cta = (rows_per_cta + q - 1) / q * q;
+    const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
+    const size_t smem = lanes > 1 ? (size_t)lanes * ncv * 8 * sizeof(float) : 0;
+    colsum_vec_kernel<<<dim3(grid, (unsigned)((ncv + 511) / 512)), 512, smem, ST(stream)>>>(CBF(dy), db, rows, n, (int)rows_per_cta);
   } else {
     const int rows_per_cta = 512;
     dim3 grid((n + 255) / 256, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));

@@ -65,39 +65,62 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
   return pk;
 }
 
-// activation / activation-gradient on a CW-wide register chunk; the switch is hoisted out of the element loop so each
-// case is straight-line code (a per-element runtime branch costs more than the math)
+// activation / activation-gradient on a CW-wide register chunk held as CW/2 float2 pairs; the switch is hoisted out of
+// the element loop so each case is straight-line code (a per-element runtime branch costs more than the math).  GELU and
+// its gradient run on the packed two-element forms (FFMA2 polynomial, no MUFU in the forward): these epilogues are
+// issue-slot bound for the K = 256 token-mixing GEMMs.
 template <int CW>
-__device__ __forceinline__ void act_chunk(float (&v)[CW], int act) {
+__device__ __forceinline__ void act_chunk(float2 (&v)[CW / 2], int act) {
   if (act == FFVC_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = gelu_f(v[i]);
+    for (int i = 0; i < CW / 2; ++i) v[i] = gelu2(v[i]);
   } else if (act == FFVC_ACT_QUICKGELU) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = quick_gelu_f(v[i]);
+    for (int i = 0; i < CW / 2; ++i) v[i] = quick_gelu2(v[i]);
   } else if (act == FFVC_ACT_SWISH) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = swish_f(v[i]);
+    for (int i = 0; i < CW / 2; ++i) v[i] = make_float2(swish_f(v[i].x), swish_f(v[i].y));
   } else if (act == FFVC_ACT_RELU) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int i = 0; i < CW / 2; ++i) v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
   }
 }
 template <int CW>
-__device__ __forceinline__ void mulgrad_chunk(float (&v)[CW], const float (&x)[CW], int act) {
+__device__ __forceinline__ void mulgrad_chunk(float2 (&v)[CW / 2], const float2 (&x)[CW / 2], int act) {
   if (act == FFVC_ACT_GELU) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] *= gelu_grad_f(x[i]);
+    for (int i = 0; i < CW / 2; ++i) v[i] = __fmul2_rn(v[i], gelu_grad2(x[i]));
   } else if (act == FFVC_ACT_QUICKGELU) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] *= quick_gelu_grad_f(x[i]);
+    for (int i = 0; i < CW / 2; ++i) v[i] = __fmul2_rn(v[i], quick_gelu_grad2(x[i]));
   } else if (act == FFVC_ACT_SWISH) {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] *= swish_grad_f(x[i]);
+    for (int i = 0; i < CW / 2; ++i) v[i] = __fmul2_rn(v[i], make_float2(swish_grad_f(x[i].x), swish_grad_f(x[i].y)));
   } else if (act == FFVC_ACT_RELU) {   // aux may be the pre- or the post-activation tensor: relu(x) > 0 <=> x > 0
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = x[i] > 0.f ? v[i] : 0.f;
+    for (int i = 0; i < CW / 2; ++i) v[i] = make_float2(x[i].x > 0.f ? v[i].x : 0.f, x[i].y > 0.f ? v[i].y : 0.f);
   }
+}
+template <int CW>
+__device__ __forceinline__ void unpack_bf16x2N(const uint4 (&pk)[CW / 8], float2 (&f)[CW / 2]) {
+#pragma unroll
+  for (int q = 0; q < CW / 8; ++q) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[q]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f[q * 4 + j] = __bfloat1622float2(h[j]);
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8_2(const float2* v) {
+  uint4 pk;
+  __nv_bfloat162 h0 = __float22bfloat162_rn(v[0]);
+  __nv_bfloat162 h1 = __float22bfloat162_rn(v[1]);
+  __nv_bfloat162 h2 = __float22bfloat162_rn(v[2]);
+  __nv_bfloat162 h3 = __float22bfloat162_rn(v[3]);
+  pk.x = *reinterpret_cast<uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  pk.z = *reinterpret_cast<uint32_t*>(&h2);
+  pk.w = *reinterpret_cast<uint32_t*>(&h3);
+  return pk;
 }
 template <int CW>
 __device__ __forceinline__ void unpack_bf16xN(const uint4 (&pk)[CW / 8], float (&f)[CW]) {
@@ -121,85 +144,96 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
                                                bool vec, const float* sbias, const uint4 (&pf_aux)[CW / 8],
                                                const uint4 (&pf_res)[CW / 8]) {
   const int ncols = min(CW, p.N - gn0);
-  float v[CW];
+  float2 v[CW / 2];
   if (p.alpha != 1.0f) {
+    const float2 al = make_float2(p.alpha, p.alpha);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+    for (int i = 0; i < CW / 2; ++i) v[i] = __fmul2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), al);
   } else {
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < CW / 2; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
   }
   if (p.bias_mode == 1) {
 #pragma unroll
-    for (int i = 0; i < CW; i += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sbias + i);   // smem broadcast; zero beyond N
-      v[i] += b4.x;
-      v[i + 1] += b4.y;
-      v[i + 2] += b4.z;
-      v[i + 3] += b4.w;
+    for (int i = 0; i < CW / 4; ++i) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + 4 * i);   // smem broadcast; zero beyond N
+      v[2 * i] = __fadd2_rn(v[2 * i], make_float2(b4.x, b4.y));
+      v[2 * i + 1] = __fadd2_rn(v[2 * i + 1], make_float2(b4.z, b4.w));
     }
   } else if (p.bias_mode == 2) {
+    const float2 rb = make_float2(rbias, rbias);
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] += rbias;
+    for (int i = 0; i < CW / 2; ++i) v[i] = __fadd2_rn(v[i], rb);
   }
   if (p.pre_out != nullptr) {
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(p.pre_out) + off;
     if (vec) {
 #pragma unroll
-      for (int i = 0; i < CW; i += 8) *reinterpret_cast<uint4*>(po + i) = pack_bf16x8(v + i);
+      for (int i = 0; i < CW / 8; ++i) *reinterpret_cast<uint4*>(po + 8 * i) = pack_bf16x8_2(v + 4 * i);
     } else {
 #pragma unroll
-      for (int i = 0; i < CW; ++i)
-        if (i < ncols) po[i] = __float2bfloat16(v[i]);
+      for (int i = 0; i < CW / 2; ++i) {
+        if (2 * i < ncols) po[2 * i] = __float2bfloat16(v[i].x);
+        if (2 * i + 1 < ncols) po[2 * i + 1] = __float2bfloat16(v[i].y);
+      }
     }
   }
   act_chunk<CW>(v, p.act);
   if (p.mul_mode != FFVC_ACT_NONE) {
-    float x[CW];
+    float2 x[CW / 2];
     if (vec) {
-      unpack_bf16xN<CW>(pf_aux, x);
+      unpack_bf16x2N<CW>(pf_aux, x);
     } else {
       const __nv_bfloat16* ax = p.aux + off;
 #pragma unroll
-      for (int i = 0; i < CW; ++i) x[i] = (i < ncols) ? __bfloat162float(ax[i]) : 0.f;
+      for (int i = 0; i < CW / 2; ++i)
+        x[i] = make_float2((2 * i < ncols) ? __bfloat162float(ax[2 * i]) : 0.f, (2 * i + 1 < ncols) ? __bfloat162float(ax[2 * i + 1]) : 0.f);
     }
     mulgrad_chunk<CW>(v, x, p.mul_mode);
   }
   if (p.res != nullptr) {
-    float x[CW];
+    float2 x[CW / 2];
     if (vec) {
-      unpack_bf16xN<CW>(pf_res, x);
+      unpack_bf16x2N<CW>(pf_res, x);
     } else {
       const __nv_bfloat16* rs = p.res + off;
 #pragma unroll
-      for (int i = 0; i < CW; ++i) x[i] = (i < ncols) ? __bfloat162float(rs[i]) : 0.f;
+      for (int i = 0; i < CW / 2; ++i)
+        x[i] = make_float2((2 * i < ncols) ? __bfloat162float(rs[2 * i]) : 0.f, (2 * i + 1 < ncols) ? __bfloat162float(rs[2 * i + 1]) : 0.f);
     }
 #pragma unroll
-    for (int i = 0; i < CW; ++i) v[i] += x[i];
+    for (int i = 0; i < CW / 2; ++i) v[i] = __fadd2_rn(v[i], x[i]);
   }
   if (p.out_fp32) {
     float* o = reinterpret_cast<float*>(p.out) + off;
     if (p.atomic) {
 #pragma unroll
-      for (int i = 0; i < CW; ++i)
-        if (i < ncols) atomicAdd(o + i, v[i]);
+      for (int i = 0; i < CW / 2; ++i) {
+        if (2 * i < ncols) atomicAdd(o + 2 * i, v[i].x);
+        if (2 * i + 1 < ncols) atomicAdd(o + 2 * i + 1, v[i].y);
+      }
     } else if (ncols == CW && (p.ldc % 4 == 0) && (p.out_bs % 4 == 0) && (p.out_bs_inner % 4 == 0)) {
 #pragma unroll
-      for (int i = 0; i < CW; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      for (int i = 0; i < CW / 4; ++i)
+        *reinterpret_cast<float4*>(o + 4 * i) = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 1].x, v[2 * i + 1].y);
     } else {
 #pragma unroll
-      for (int i = 0; i < CW; ++i)
-        if (i < ncols) o[i] = v[i];
+      for (int i = 0; i < CW / 2; ++i) {
+        if (2 * i < ncols) o[2 * i] = v[i].x;
+        if (2 * i + 1 < ncols) o[2 * i + 1] = v[i].y;
+      }
     }
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
     if (vec) {
 #pragma unroll
-      for (int i = 0; i < CW; i += 8) *reinterpret_cast<uint4*>(o + i) = pack_bf16x8(v + i);
+      for (int i = 0; i < CW / 8; ++i) *reinterpret_cast<uint4*>(o + 8 * i) = pack_bf16x8_2(v + 4 * i);
     } else {
 #pragma unroll
-      for (int i = 0; i < CW; ++i)
-        if (i < ncols) o[i] = __float2bfloat16(v[i]);
+      for (int i = 0; i < CW / 2; ++i) {
+        if (2 * i < ncols) o[2 * i] = __float2bfloat16(v[i].x);
+        if (2 * i + 1 < ncols) o[2 * i + 1] = __float2bfloat16(v[i].y);
+      }
     }
   }
 }

@@ -457,6 +457,286 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfl
   }
 }
 
+
+// ------------------------------------------------------------------------------------ GroupNorm, single-kernel forms
+// The two-kernel forms above read every tensor twice from HBM (statistics pass + apply pass).  The fused forms keep the
+// second read in the 126 MB L2: ONE persistent grid (one 512-thread CTA per SM) walks the batch sample by sample; for
+// sample n every CTA accumulates the statistics of its pixel slice (phase A), publishes them with double atomics and
+// bumps a per-sample arrival counter; once the counter shows the whole grid, it normalises the SAME slice (phase B) —
+// which it, and only it, streamed a moment ago, so the re-read hits L2 (one sample of the 256x256x128 tensor is 16.8 MB).
+// Phase A of sample n+1 is issued BEFORE the wait for sample n (software pipelining), so the grid-wide arrival is
+// practically always complete when a CTA looks at it and nobody idles at the barrier.
+// HBM traffic: forward 4 B/element (was 6), backward 6 B/element (was 10).
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_stream(const __nv_bfloat16* p) {   // last use of the line: evict-first
+  return __ldcs(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void st_stream(__nv_bfloat16* p, const uint4& v) { __stcs(reinterpret_cast<uint4*>(p), v); }
+
+static constexpr int kGnThreads = 512;
+static constexpr int kGnUnroll = 4;
+static constexpr int kGnUnrollBwd = 2;   // backward holds 6 per-channel coefficient vectors: 2 x (x, dy, add) loads in flight fit 128 registers
+
+// publish this CTA's per-group partial sums (shared memory, [2][G] floats) for sample n and signal arrival
+__device__ __forceinline__ void gn_publish(const float* part, double* ws, int* cnt, int n, int G) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    atomicAdd(&ws[((long long)n * G + i) * 2 + 0], (double)part[i]);
+    atomicAdd(&ws[((long long)n * G + i) * 2 + 1], (double)part[G + i]);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(&cnt[n], 1);
+}
+__device__ __forceinline__ void gn_wait(const int* cnt, int n, int expected) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire_gpu(&cnt[n]) < expected) __nanosleep(40);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kGnThreads, 1)
+groupnorm_fused_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                           __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                           double* __restrict__ ws, int* __restrict__ cnt, int N, int HW, int C, int G, int ppc, int swish,
+                           float eps, int pipeline) {
+  extern __shared__ float sm[];          // part[2][2G] (by sample parity) + stat[2G]
+  float* stat = sm + 4 * G;
+  const int cpg = C / G, vpp = C >> 3;
+  const int vc = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = kGnThreads / vpp;
+  const int p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);
+  const double inv_count = 1.0 / ((double)HW * cpg);
+  float gm[8], bt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gm[j] = gamma[vc * 8 + j];
+    bt[j] = beta[vc * 8 + j];
+  }
+  auto phase_a = [&](int n) {
+    float* part = sm + (n & 1) * 2 * G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) part[i] = 0.f;
+    __syncthreads();
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const __nv_bfloat16* base = x + (long long)n * HW * C + vc * 8;
+    for (int p = p0 + pl; p < p1; p += pstride * kGnUnroll) {
+      uint4 pk[kGnUnroll];
+#pragma unroll
+      for (int u = 0; u < kGnUnroll; ++u) {
+        const int pp = p + u * pstride;
+        pk[u] = pp < p1 ? *reinterpret_cast<const uint4*>(base + (long long)pp * C) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < kGnUnroll; ++u) {
+        float v[8];
+        unpack8(pk[u], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[j];
+          q[j] = fmaf(v[j], v[j], q[j]);
+        }
+      }
+    }
+    gn_fold_to_smem(s, q, part, G, cpg, vc, vpp);
+    gn_publish(part, ws, cnt, n, G);
+  };
+  auto phase_b = [&](int n) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (vc * 8 + j) / cpg;
+      sc[j] = stat[G + g] * gm[j];
+      sh[j] = bt[j] - stat[g] * sc[j];
+    }
+    const long long base = (long long)n * HW * C + vc * 8;
+    for (int p = p0 + pl; p < p1; p += pstride * kGnUnroll) {
+      uint4 pk[kGnUnroll];
+#pragma unroll
+      for (int u = 0; u < kGnUnroll; ++u) {
+        const int pp = p + u * pstride;
+        if (pp < p1) pk[u] = ld_stream(x + base + (long long)pp * C);
+      }
+#pragma unroll
+      for (int u = 0; u < kGnUnroll; ++u) {
+        const int pp = p + u * pstride;
+        if (pp < p1) {
+          float v[8], o[8];
+          unpack8(pk[u], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(v[j], sc[j], sh[j]);
+            o[j] = swish ? swish_f(t) : t;
+          }
+          st_stream(y + base + (long long)pp * C, pack8(o));
+        }
+      }
+    }
+  };
+  if (pipeline) phase_a(0);
+  for (int n = 0; n < N; ++n) {
+    if (pipeline) {
+      if (n + 1 < N) phase_a(n + 1);
+    } else {
+      phase_a(n);
+    }
+    gn_wait(cnt, n, (int)gridDim.x);
+    if (threadIdx.x < G) {
+      const long long gi = (long long)n * G + threadIdx.x;
+      const double m = __ldcg(&ws[2 * gi]) * inv_count;
+      double var = __ldcg(&ws[2 * gi + 1]) * inv_count - m * m;
+      if (var < 0) var = 0;
+      const float mu = (float)m, rs = (float)(1.0 / sqrt(var + (double)eps));
+      stat[threadIdx.x] = mu;
+      stat[G + threadIdx.x] = rs;
+      if (blockIdx.x == 0) {
+        mean_out[gi] = mu;
+        rstd_out[gi] = rs;
+      }
+    }
+    __syncthreads();
+    phase_b(n);
+    __syncthreads();   // stat is rewritten in the next iteration
+  }
+}
+
+__global__ void __launch_bounds__(kGnThreads, 1)
+groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                           const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx,
+                           double* __restrict__ ws, int* __restrict__ cnt, int N, int HW, int C, int G, int ppc, int swish,
+                           int pipeline) {
+  extern __shared__ float sm[];          // part[2][2G] + stat[2G]
+  float* stat = sm + 4 * G;
+  const int cpg = C / G, vpp = C >> 3;
+  const int vc = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = kGnThreads / vpp;
+  const int p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);
+  const float inv_count = 1.0f / ((float)HW * cpg);
+  float gm[8], bt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gm[j] = gamma[vc * 8 + j];
+    bt[j] = beta[vc * 8 + j];
+  }
+  // g = dy * act'(u) * gamma and xhat for one 8-channel vector
+  auto grad8 = [&](const uint4& xk, const uint4& dk, const float (&mu)[8], const float (&rs)[8], float (&g)[8], float (&xh)[8]) {
+    float v[8], d[8];
+    unpack8(xk, v);
+    unpack8(dk, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      xh[j] = (v[j] - mu[j]) * rs[j];
+      const float u = fmaf(xh[j], gm[j], bt[j]);
+      g[j] = d[j] * (swish ? swish_grad_f(u) : 1.0f) * gm[j];
+    }
+  };
+  auto load_stats = [&](int n, float (&mu)[8], float (&rs)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = n * G + (vc * 8 + j) / cpg;
+      mu[j] = mean[g];
+      rs[j] = rstd[g];
+    }
+  };
+  auto phase_a = [&](int n) {
+    float* part = sm + (n & 1) * 2 * G;
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) part[i] = 0.f;
+    __syncthreads();
+    float s[8], q[8], mu[8], rs[8];
+    load_stats(n, mu, rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const long long base = (long long)n * HW * C + vc * 8;
+    for (int p = p0 + pl; p < p1; p += pstride * kGnUnrollBwd) {
+      uint4 xk[kGnUnrollBwd], dk[kGnUnrollBwd];
+#pragma unroll
+      for (int u = 0; u < kGnUnrollBwd; ++u) {
+        const int pp = p + u * pstride;
+        if (pp < p1) {
+          xk[u] = *reinterpret_cast<const uint4*>(x + base + (long long)pp * C);
+          dk[u] = *reinterpret_cast<const uint4*>(dy + base + (long long)pp * C);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGnUnrollBwd; ++u) {
+        const int pp = p + u * pstride;
+        if (pp < p1) {
+          float g[8], xh[8];
+          grad8(xk[u], dk[u], mu, rs, g, xh);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s[j] += g[j];
+            q[j] = fmaf(g[j], xh[j], q[j]);
+          }
+        }
+      }
+    }
+    gn_fold_to_smem(s, q, part, G, cpg, vc, vpp);
+    gn_publish(part, ws, cnt, n, G);
+  };
+  auto phase_b = [&](int n) {
+    float mu[8], rs[8], s1[8], s2[8];
+    load_stats(n, mu, rs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (vc * 8 + j) / cpg;
+      s1[j] = stat[g];
+      s2[j] = stat[G + g];
+    }
+    const long long base = (long long)n * HW * C + vc * 8;
+    for (int p = p0 + pl; p < p1; p += pstride * kGnUnrollBwd) {
+      uint4 xk[kGnUnrollBwd], dk[kGnUnrollBwd], ak[kGnUnrollBwd];
+#pragma unroll
+      for (int u = 0; u < kGnUnrollBwd; ++u) {
+        const int pp = p + u * pstride;
+        if (pp < p1) {
+          xk[u] = ld_stream(x + base + (long long)pp * C);
+          dk[u] = ld_stream(dy + base + (long long)pp * C);
+          if (add) ak[u] = ld_stream(add + base + (long long)pp * C);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kGnUnrollBwd; ++u) {
+        const int pp = p + u * pstride;
+        if (pp < p1) {
+          float g[8], xh[8], o[8];
+          grad8(xk[u], dk[u], mu, rs, g, xh);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rs[j] * (g[j] - s1[j] - xh[j] * s2[j]);
+          if (add) {
+            float a[8];
+            unpack8(ak[u], a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] += a[j];
+          }
+          st_stream(dx + base + (long long)pp * C, pack8(o));
+        }
+      }
+    }
+  };
+  if (pipeline) phase_a(0);
+  for (int n = 0; n < N; ++n) {
+    if (pipeline) {
+      if (n + 1 < N) phase_a(n + 1);
+    } else {
+      phase_a(n);
+    }
+    gn_wait(cnt, n, (int)gridDim.x);
+    if (threadIdx.x < G) {
+      const long long gi = (long long)n * G + threadIdx.x;
+      stat[threadIdx.x] = (float)__ldcg(&ws[2 * gi]) * inv_count;
+      stat[G + threadIdx.x] = (float)__ldcg(&ws[2 * gi + 1]) * inv_count;
+    }
+    __syncthreads();
+    phase_b(n);
+    __syncthreads();
+  }
+}
+
 }  // namespace ffvc
 
 using namespace ffvc;
@@ -564,6 +844,70 @@ extern "C" int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* me
                                                  reinterpret_cast<const __nv_bfloat16*>(add),
                                                  reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, ppc2,
                                                  1.0f / ((float)HW * (C / G)), swish);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+// ---- single-kernel forms (see groupnorm_fused_*_kernel).  ws: 2*N*G doubles followed by N ints (ffvc_groupnorm_ws_bytes).
+static int g_gn_sms = 0;
+static int gn_fused_grid(int HW, int C, int* ppc_out) {
+  if (g_gn_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_gn_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_gn_sms <= 0) g_gn_sms = 148;
+  }
+  const int pstride = kGnThreads / (C >> 3);
+  int ppc = (HW + g_gn_sms - 1) / g_gn_sms;
+  ppc = (ppc + pstride - 1) / pstride * pstride;          // whole thread-rows of pixels per CTA
+  *ppc_out = ppc;
+  return (HW + ppc - 1) / ppc;                            // <= number of SMs: every CTA is resident (the kernel spins on arrivals)
+}
+static int gn_fused_check(int C, int G) {
+  if (C % 8 != 0 || G <= 0 || G > 128 || C % G != 0 || kGnThreads % (C / 8) != 0)
+    return set_error(FFVC_ERR_ARG, "groupnorm_fused: C must be a multiple of 8, divisible by G, C/8 must divide 512");
+  return FFVC_OK;
+}
+static int g_gn_pipeline = 1;
+static bool gn_pipeline_default() { return g_gn_pipeline != 0; }
+// schedule of the single-kernel forms: 1 (default) = statistics of sample n+1 are issued before the wait for sample n
+extern "C" int ffvc_groupnorm_set_pipeline(int on) {
+  g_gn_pipeline = on ? 1 : 0;
+  return FFVC_OK;
+}
+
+extern "C" long long ffvc_groupnorm_ws_bytes(int N, int G) { return (long long)sizeof(double) * 2 * N * G + (long long)sizeof(int) * N; }
+
+extern "C" int ffvc_groupnorm_fused_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                                        double* ws, int N, int HW, int C, int G, int swish, float eps, void* stream) {
+  int rc = gn_fused_check(C, G);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(ws, 0, (size_t)ffvc_groupnorm_ws_bytes(N, G), st);
+  int ppc;
+  const int grid = gn_fused_grid(HW, C, &ppc);
+  int* cnt = reinterpret_cast<int*>(ws + 2 * (long long)N * G);
+  groupnorm_fused_fwd_kernel<<<grid, kGnThreads, 6 * G * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, ws, cnt, N, HW, C, G,
+      ppc, swish, eps, gn_pipeline_default() ? 1 : 0);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+extern "C" int ffvc_groupnorm_fused_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                                        const float* beta, double* ws, const void* add, void* dx, int N, int HW, int C, int G,
+                                        int swish, void* stream) {
+  int rc = gn_fused_check(C, G);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(ws, 0, (size_t)ffvc_groupnorm_ws_bytes(N, G), st);
+  int ppc;
+  const int grid = gn_fused_grid(HW, C, &ppc);
+  int* cnt = reinterpret_cast<int*>(ws + 2 * (long long)N * G);
+  groupnorm_fused_bwd_kernel<<<grid, kGnThreads, 6 * G * sizeof(float), st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta,
+      reinterpret_cast<const __nv_bfloat16*>(add), reinterpret_cast<__nv_bfloat16*>(dx), ws, cnt, N, HW, C, G, ppc, swish,
+      gn_pipeline_default() ? 1 : 0);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

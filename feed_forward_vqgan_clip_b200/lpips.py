@@ -73,7 +73,7 @@ class DiversityEngine:
         act = ops.ACT_RELU if (relu and not dgrad) else ops.ACT_NONE
         mul = ops.ACT_RELU if aux is not None else ops.ACT_NONE
         if W % 128 == 0 and H % 2 == 0 and cin % 64 == 0 and cout <= 128:
-            call("conv3x3_halo", x, self.pk[wkey], out, N, H, W, cin, cout, cout, bias, None, aux, mul, act)
+            call("conv3x3_halo", x, self.pk[wkey], out, N, H, W, cin, cout, cout, bias, None, aux, mul, act, 0)
         else:
             ops.gemm(x, self.pk[wkey], out, N * H * W, cout, 9 * cin, a_mode=ops.CONV3X3, conv=(N, H, W, cin), bias=bias,
                      act=act, aux=aux, mul_mode=mul)

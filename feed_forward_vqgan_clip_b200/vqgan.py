@@ -194,13 +194,15 @@ class DecoderEngine:
     # ---------------------------------------------------------------- primitive ops (forward + backward closure)
     USE_HALO = True    # shared-memory halo reuse for the wide (W % 128 == 0), <= 128-output-channel 3x3 convs
 
-    def _halo_ok(self, H, W, cin, cout):
-        return self.USE_HALO and W % 128 == 0 and H % 2 == 0 and cin % 64 == 0 and cout <= 128 and cout % 8 == 0
+    def _halo_ok(self, H, W, cin, cout, out_f32=False):
+        return (self.USE_HALO and W % 128 == 0 and H % 2 == 0 and cin % 64 == 0 and cout <= 128
+                and (cout % 8 == 0 or out_f32))
 
     def conv3(self, x, name, N, H, W, cin, cout, res=None, out_f32=False):
         out = self._new(N * H * W, cout, dtype=F32 if out_f32 else BF16)
-        if not out_f32 and self._halo_ok(H, W, cin, cout):
-            call("conv3x3_halo", x, self.pk[name + ".w"], out, N, H, W, cin, cout, cout, self.pk[name + ".b"], res, None, 0, 0)
+        if self._halo_ok(H, W, cin, cout, out_f32):      # incl. the 128 -> 3 conv_out (fp32 image, scalar stores)
+            call("conv3x3_halo", x, self.pk[name + ".w"], out, N, H, W, cin, cout, cout, self.pk[name + ".b"], res, None, 0, 0,
+                 int(out_f32))
             return out
         ops.gemm(x, self.pk[name + ".w"], out, N * H * W, cout, 9 * cin, a_mode=ops.CONV3X3, conv=(N, H, W, cin),
                  bias=self.pk[name + ".b"], res=res)
@@ -209,7 +211,7 @@ class DecoderEngine:
     def conv3_dgrad(self, dy, name, N, H, W, cin, cout, res=None):
         dx = self._new(N * H * W, cin)
         if self._halo_ok(H, W, cout, cin):
-            call("conv3x3_halo", dy, self.pk[name + ".wT"], dx, N, H, W, cout, cin, cin, None, res, None, 0, 0)
+            call("conv3x3_halo", dy, self.pk[name + ".wT"], dx, N, H, W, cout, cin, cin, None, res, None, 0, 0, 0)
             return dx
         ops.gemm(dy, self.pk[name + ".wT"], dx, N * H * W, cin, 9 * cout, a_mode=ops.CONV3X3, conv=(N, H, W, cout), res=res)
         return dx
@@ -224,17 +226,28 @@ class DecoderEngine:
         ops.linear_dgrad(dy, self.pk[name + ".w"], dx, M, cout, cin, res=res)
         return dx
 
+    # GroupNorm: tensors with >= GN_FUSED_MIN elements per sample go through the single-kernel, L2-resident forms
+    # (statistics + apply of one sample back to back); the small ones keep the two-pass kernels
+    GN_FUSED_MIN = 512 * 1024
+
+    def _gn_fused(self, HW, C):
+        return HW * C >= self.GN_FUSED_MIN and 512 % (C // 8) == 0
+
     def gn(self, x, name, N, HW, C, swish):
         mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
-        call("groupnorm_stats", x, self._gn_ws(N * 64), mean, rstd, N, HW, C, 32, 1e-6)
         y = self._new(N * HW, C)
+        if self._gn_fused(HW, C):
+            call("groupnorm_fused_fwd", x, self.pk[name + ".g"], self.pk[name + ".be"], y, mean, rstd, self._gn_ws(N * 65), N, HW, C,
+                 32, int(swish), 1e-6)
+            return y, (mean, rstd)
+        call("groupnorm_stats", x, self._gn_ws(N * 65), mean, rstd, N, HW, C, 32, 1e-6)
         call("groupnorm_apply", x, mean, rstd, self.pk[name + ".g"], self.pk[name + ".be"], y, N, HW, C, 32, int(swish))
         return y, (mean, rstd)
 
     def gn_bwd(self, dy, x, stats, name, N, HW, C, swish, add=None):
         dx = self._new(N * HW, C)
-        call("groupnorm_bwd", dy, x, stats[0], stats[1], self.pk[name + ".g"], self.pk[name + ".be"], self._gn_ws(N * 64),
-             add, dx, N, HW, C, 32, int(swish))
+        call("groupnorm_fused_bwd" if self._gn_fused(HW, C) else "groupnorm_bwd", dy, x, stats[0], stats[1], self.pk[name + ".g"],
+             self.pk[name + ".be"], self._gn_ws(N * 65), add, dx, N, HW, C, 32, int(swish))
         return dx
 
     def resblock(self, x, name, N, H, W, cin, cout, tape):

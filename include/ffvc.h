@@ -100,7 +100,7 @@ int ffvc_gemm(const ffvc_gemm_params* p, void* stream);
  * the wide 128-channel layers of the VQGAN decoder, where the tap-by-tap form is L2-bandwidth bound.
  * Epilogue: + bias[cout] (fp32, optional), act, * act'(aux) (mul_mode), + res (bf16, optional), like ffvc_gemm. */
 int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
-                      const float* bias, const void* res, const void* aux, int mul_mode, int act, void* stream);
+                      const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (bf16 in/out, fp32 stats).  mlp_mixer_pytorch.py:11,37; cloob.py:170-176.
@@ -119,6 +119,18 @@ int ffvc_groupnorm_apply(const void* x, const float* mean, const float* rstd, co
 int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                        const float* beta, double* ws, const void* add, void* dx, int N, int HW, int C, int G, int swish,
                        void* stream);
+
+/* Single-kernel GroupNorm [+ swish]: one persistent grid walks the batch sample by sample, statistics pass and apply
+ * pass of a sample back to back so the second read hits L2 (forward 4 B/element of HBM traffic instead of 6, backward 6
+ * instead of 10).  Same arithmetic as the two-pass entry points; also writes mean / rstd [N*G] for the backward.
+ * ws: ffvc_groupnorm_ws_bytes(N, G) bytes of scratch (2*N*G doubles + N arrival counters), zeroed by the call.       */
+long long ffvc_groupnorm_ws_bytes(int N, int G);
+int ffvc_groupnorm_set_pipeline(int on);   /* 1 (default): statistics of sample n+1 are issued before the wait for sample n */
+int ffvc_groupnorm_fused_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                             double* ws, int N, int HW, int C, int G, int swish, float eps, void* stream);
+int ffvc_groupnorm_fused_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, double* ws, const void* add, void* dx, int N, int HW, int C, int G,
+                             int swish, void* stream);
 
 /* nearest-neighbour 2x upsample, NHWC bf16 (taming Upsample); bwd sums the 2x2 block. */
 int ffvc_upsample2x_fwd(const void* x, void* y, int N, int H, int W, int C, void* stream);

@@ -270,10 +270,24 @@ def test_conv3x3_halo_reuse(n, h, w, cin, cout):
     res = _rand(n, h, w, cout, seed=73)
     wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
     out = torch.empty(n, h, w, cout, device=DEV, dtype=torch.bfloat16)
-    call("conv3x3_halo", x, wp, out, n, h, w, cin, cout, cout, bias, res, None, 0, 0)
+    call("conv3x3_halo", x, wp, out, n, h, w, cin, cout, cout, bias, res, None, 0, 0, 0)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
     _check(out, ref, 2e-2)
     # and it agrees with the tap-by-tap implicit GEMM bit-for-bit up to accumulation order
     out2 = torch.empty_like(out)
     ops.gemm(x, wp, out2, n * h * w, cout, 9 * cin, a_mode=ops.CONV3X3, conv=(n, h, w, cin), bias=bias, res=res)
     _check(out, out2.float(), 1e-2)
+
+
+def test_conv3x3_halo_three_channel_fp32_out():
+    """the decoder's conv_out (128 -> 3 channels, fp32 image) on the halo kernel: N = 3 inside a 32-column tile, scalar stores"""
+    from feed_forward_vqgan_clip_b200.ops import call
+    n, h, w, cin, cout = 2, 8, 128, 128, 3
+    x = _rand(n, h, w, cin, seed=81)
+    wt = (_rand(cout, cin, 3, 3, seed=82).float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(cout, device=DEV)
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * cin).contiguous()
+    out = torch.full((n, h, w, cout), 7.0, device=DEV, dtype=torch.float32)
+    call("conv3x3_halo", x, wp, out, n, h, w, cin, cout, cout, bias, None, None, 0, 0, 1)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    _check(out, ref, 2e-2)

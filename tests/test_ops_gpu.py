@@ -72,6 +72,40 @@ def test_groupnorm_fwd_bwd(N, HW, C, swish):
     close(dx, xr.grad.permute(0, 2, 1) + add.float())
 
 
+@pytest.mark.parametrize("pipeline", [1, 0])
+@pytest.mark.parametrize("N,HW,C,swish", [(2, 256, 512, 1), (3, 1024, 128, 1), (1, 4096, 64, 0), (5, 16384, 128, 1), (2, 4096, 256, 1),
+                                          (3, 100, 64, 1)])
+def test_groupnorm_fused_single_kernel_forms(N, HW, C, swish, pipeline):
+    """the L2-resident single-kernel GroupNorm (persistent grid + per-sample arrival counters) against torch AND against
+    the two-pass kernels; both schedules (phase A of sample n+1 before / after the wait for sample n)"""
+    from feed_forward_vqgan_clip_b200 import _lib
+    x, dy, add = rnd(N, HW, C, seed=1), rnd(N, HW, C, seed=2), rnd(N, HW, C, seed=3)
+    gamma = 1 + 0.1 * torch.randn(C, device=DEV)
+    beta = 0.1 * torch.randn(C, device=DEV)
+    _lib.load().ffvc_groupnorm_set_pipeline(pipeline)
+    nbytes = _lib.load().ffvc_groupnorm_ws_bytes(N, 32)
+    assert nbytes == N * 64 * 8 + N * 4
+    ws = torch.empty((nbytes + 7) // 8, device=DEV, dtype=torch.float64)
+    mean, rstd = torch.empty(N * 32, device=DEV), torch.empty(N * 32, device=DEV)
+    y = torch.empty_like(x)
+    call("groupnorm_fused_fwd", x, gamma, beta, y, mean, rstd, ws, N, HW, C, 32, swish, 1e-6)
+    xr = x.float().permute(0, 2, 1).contiguous().requires_grad_(True)       # (N, C, HW)
+    u = F.group_norm(xr, 32, gamma, beta, eps=1e-6)
+    yr = u * torch.sigmoid(u) if swish else u
+    close(y, yr.permute(0, 2, 1))
+    mean2, rstd2, y2 = torch.empty_like(mean), torch.empty_like(rstd), torch.empty_like(x)
+    call("groupnorm_stats", x, ws, mean2, rstd2, N, HW, C, 32, 1e-6)
+    call("groupnorm_apply", x, mean2, rstd2, gamma, beta, y2, N, HW, C, 32, swish)
+    assert torch.allclose(mean, mean2, atol=1e-5) and torch.allclose(rstd, rstd2, rtol=1e-4)
+    assert (y.float() - y2.float()).abs().max().item() <= 2e-2 * y2.float().abs().max().item()
+    yr.backward(dy.float().permute(0, 2, 1))
+    for a in (add, None):
+        dx = torch.empty_like(x)
+        call("groupnorm_fused_bwd", dy, x, mean, rstd, gamma, beta, ws, a, dx, N, HW, C, 32, swish)
+        close(dx, xr.grad.permute(0, 2, 1) + (a.float() if a is not None else 0))
+    _lib.load().ffvc_groupnorm_set_pipeline(1)
+
+
 def test_upsample_and_transpose():
     x = rnd(2, 8, 8, 64, seed=1)
     y = torch.empty(2, 16, 16, 64, device=DEV, dtype=BF)
@@ -104,15 +138,23 @@ def test_softmax_fwd_bwd():
     close(ds, 0.5 * pf * (dp - (pf * dp).sum(-1, keepdim=True)))
 
 
+@pytest.mark.parametrize("rows,n", [(3000, 520), (16384, 1024), (4096, 4096), (64, 65536), (777, 8), (5, 6152), (1000, 30)])
+def test_colsum_bias_grad(rows, n):
+    dy = rnd(rows, n, seed=1)
+    db = torch.full((n,), 0.5, device=DEV)                     # accumulates into the gradient arena
+    call("colsum", dy, db, rows, n)
+    close(db, dy.float().sum(0) + 0.5, 2e-3)
+
+
+@pytest.mark.parametrize("B,J,D", [(4, 96, 128), (8, 256, 1024), (2, 33, 2056), (3, 17, 100)])
+def test_rowsum_bias_grad(B, J, D):
+    d3 = rnd(B, J, D, seed=2)
+    dj = torch.zeros(J, device=DEV)
+    call("rowsum", d3, dj, B, J, D)
+    close(dj, d3.float().sum(dim=(0, 2)), 2e-3)
+
+
 def test_bias_grads_and_casts():
-    dy = rnd(3000, 520, seed=1)
-    db = torch.zeros(520, device=DEV)
-    call("colsum", dy, db, 3000, 520)
-    close(db, dy.float().sum(0), 1e-3)
-    d3 = rnd(4, 96, 128, seed=2)
-    dj = torch.zeros(96, device=DEV)
-    call("rowsum", d3, dj, 4, 96, 128)
-    close(dj, d3.float().sum(dim=(0, 2)), 1e-3)
     x = rnd(1000, seed=3, dtype=F32)
     y = torch.empty(1000, device=DEV, dtype=BF)
     call("cast_f32_bf16", x, y, 1000)

@@ -20,7 +20,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--out", default="gpurun_out/step_breakdown.md")
+    ap.add_argument("--gn-pipeline", type=int, default=1)
     args = ap.parse_args()
+    from feed_forward_vqgan_clip_b200 import _lib
+    _lib.load().ffvc_groupnorm_set_pipeline(args.gn_pipeline)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     ts = bench.build_b200(dev, args.batch, 1, None)
