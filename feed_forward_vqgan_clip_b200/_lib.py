@@ -27,7 +27,7 @@ class GemmParams(C.Structure):
         ("bias", C.c_void_p),
         ("ldc", C.c_int64), ("out_batch_stride", C.c_int64), ("out_batch_stride_inner", C.c_int64),
         ("out_fp32", C.c_int), ("atomic", C.c_int), ("bias_mode", C.c_int), ("act", C.c_int),
-        ("mul_mode", C.c_int), ("alpha", C.c_float),
+        ("mul_mode", C.c_int), ("alpha", C.c_float), ("argmin_out", C.c_void_p),
     ]
 
 

@@ -147,12 +147,24 @@ class ClipEngine:
         call("layernorm_bwd", dy, x, self.sd32[name + ".weight"], st[0], st[1], add, dx, None, None, rows, self.W)
         return dx
 
-    # ---- multi-head attention on the tensor cores: per (sequence, head) GEMMs batched through 4-D tensor maps
-    # (inner batch = head: 64-element column slice of the fused qkv rows; outer batch = sequence), T padded to 64.
+    # ---- multi-head attention.  Short sequences take the fused per-(sequence, head) kernel; the general form runs as
+    # per (sequence, head) tcgen05 GEMMs batched through 4-D tensor maps (inner batch = head: 64-element column slice of
+    # the fused qkv rows; outer batch = sequence), T padded to 64.
     TP = 64
+
+    FUSED_ATTN = True   # tests switch it off to exercise the general (batched tcgen05 GEMM) attention path
+
+    def _fused_attn(self):
+        """T <= 64 tokens, 64-wide heads (every ViT-B/32 at 224 x 224): one CTA per (sequence, head) on mma.sync, scores and
+        probabilities never leave the SM and nothing but qkv is saved for the backward (ffvc_mha_small_*)."""
+        return self.FUSED_ATTN and self.T <= 64 and self.W == 64 * self.Hh
 
     def _attn_fwd(self, qkv, N):
         W, T, Hh, TP = self.W, self.T, self.Hh, self.TP
+        if self._fused_attn():
+            a = self._new(N * T, W)
+            call("mha_small_fwd", qkv, a, N, T, Hh, 64, 0.125)
+            return a, None
         S = self._new(N, Hh, T, TP, dtype=F32)
         ops.gemm(qkv, qkv, S, T, T, 64, a_ld=3 * W, b_ld=3 * W, b_off=W, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT,
                  batch=N * Hh, batch_inner=Hh, a_bs=T * 3 * W, b_bs=T * 3 * W, a_bs_in=64, b_bs_in=64, ldc=TP,
@@ -168,6 +180,10 @@ class ClipEngine:
 
     def _attn_bwd(self, qkv, P, da, N):
         W, T, Hh, TP = self.W, self.T, self.Hh, self.TP
+        if P is None:
+            dqkv = self._new(N * T, 3 * W)
+            call("mha_small_bwd", qkv, da, dqkv, N, T, Hh, 64, 0.125)
+            return dqkv
         kw = dict(batch=N * Hh, batch_inner=Hh, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT, block_n=64)
         dP = self._new(N, Hh, T, TP, dtype=F32)            # dP[i,j] = sum_d dO[i,d] V[j,d]
         ops.gemm(da, qkv, dP, T, T, 64, a_ld=W, b_ld=3 * W, b_off=2 * W, a_bs=T * W, a_bs_in=64, b_bs=T * 3 * W, b_bs_in=64,

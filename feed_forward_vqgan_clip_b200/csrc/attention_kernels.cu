@@ -1,8 +1,18 @@
 // Small-sequence multi-head attention for the CLIP ViT (T = 50 tokens, 12 heads x 64), forward and backward.
 // Reference: nn.MultiheadAttention inside ResidualAttentionBlock.attention, cloob.py:188,198-200.
-// One CTA per (sequence, head): Q, K, V (and dO) live in shared memory as fp32, scores never touch HBM.
+//
+// One CTA (4 warps) per (sequence, head).  Q, K, V (and dO) are staged once in shared memory as bf16 (144-byte row pitch:
+// conflict-free ldmatrix), every matmul runs on the warp-level tensor-core path (mma.sync m16n8k16, bf16 in, fp32
+// accumulate) and scores / probabilities never touch HBM:
+//   forward : warp w owns query rows 16w..16w+15:  S = Q K^T -> softmax in registers -> O = P V
+//             (the S accumulators of two adjacent 8-column tiles ARE the A fragment of the next MMA: no shuffles)
+//   backward: probabilities are recomputed (nothing but qkv is saved by the forward);
+//             phase 1, per query-row tile: P, dP = dO V^T, dS = P (dP - rowsum(P dP)) scale, dQ = dS K; P and dS go to smem
+//             phase 2, per key-row tile  : dV = P^T dO, dK = dS^T Q   (A operands read transposed with ldmatrix.trans)
+// A 50 x 50 x 64 problem is far too small for a 128-row tcgen05 tile (the batched tcgen05 form it replaces padded 50
+// rows to 128 and spent 100 us per launch in tile overheads); mma.sync at a few hundred MMAs per head is the right tool.
 // qkv layout: [N][T][3*W] bf16 (the fused in_proj output: q | k | v along the last dim), head h owns columns
-// h*64..h*64+63 of each third.  out / dout: [N][T][W] bf16.
+// h*64..h*64+63 of each third.  out / dout: [N][T][W] bf16.  T <= 64, head_dim == 64.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -15,146 +25,258 @@ namespace ffvc {
 
 static constexpr int kDh = 64;
 static constexpr int kTmax = 64;
+static constexpr int kPitch = 72;                       // bf16 elements per shared-memory row (144 B)
+static constexpr int kTileElems = kTmax * kPitch;       // one [64][72] bf16 operand tile
 
-__device__ __forceinline__ void load_head(const __nv_bfloat16* __restrict__ base, long long row_stride, int T, float* dst) {
-  // dst[t][kDh+1] fp32, coalesced 16B loads: 8 vectors per row
-  for (int i = threadIdx.x; i < T * 8; i += blockDim.x) {
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D (16x8, fp32) += A (16x16, bf16, row) * B (16x8, bf16, col)
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// stage T rows x 64 columns (bf16, global row stride `row_stride` elements) into a [64][kPitch] tile; rows >= T are zeroed
+__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ base, long long row_stride, int T, __nv_bfloat16* dst) {
+  for (int i = threadIdx.x; i < kTmax * 8; i += blockDim.x) {
     const int t = i >> 3, v = i & 7;
-    const uint4 pk = *reinterpret_cast<const uint4*>(base + (long long)t * row_stride + v * 8);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk);
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+    if (t < T) pk = *reinterpret_cast<const uint4*>(base + (long long)t * row_stride + v * 8);
+    *reinterpret_cast<uint4*>(dst + t * kPitch + v * 8) = pk;
+  }
+}
+
+// acc[nt] (16 x 8 tiles, nt = 0..7) = A[m0.., :64] * B^T where A, B are [row][k] tiles in shared memory (k contiguous):
+// the Q K^T / dO V^T form (both operands read with plain ldmatrix)
+__device__ __forceinline__ void mm_rows_x_rows(float (&acc)[8][4], uint32_t a_tile, uint32_t b_tile, int m0, int lane) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __bfloat1622float2(h[j]);
-      dst[t * (kDh + 1) + v * 8 + 2 * j] = f.x;
-      dst[t * (kDh + 1) + v * 8 + 2 * j + 1] = f.y;
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a0, a1, a2, a3;
+    ldsm_x4(a_tile + (uint32_t)(((m0 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + kk * 16 + (lane >> 4) * 8) * 2), a0, a1, a2, a3);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(b_tile + (uint32_t)(((np * 16 + (lane & 7) + (lane >> 4) * 8) * kPitch + kk * 16 + ((lane >> 3) & 1) * 8) * 2), b0, b1, b2, b3);
+      mma16816(acc[2 * np], a0, a1, a2, a3, b0, b1);
+      mma16816(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
+    }
+  }
+}
+// acc[nt] (16 x 8 tiles over the 64 output columns) += A * B with A given as register fragments af[kk][4] (k = 64 in four
+// 16-wide steps) and B a [k][n] tile in shared memory (n contiguous): the P V / dS K form (B read with ldmatrix.trans)
+__device__ __forceinline__ void mm_frag_x_cols(float (&acc)[8][4], const uint32_t (&af)[4][4], uint32_t b_tile, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(b_tile + (uint32_t)(((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + np * 16 + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
+      mma16816(acc[2 * np], af[kk][0], af[kk][1], af[kk][2], af[kk][3], b0, b1);
+      mma16816(acc[2 * np + 1], af[kk][0], af[kk][1], af[kk][2], af[kk][3], b2, b3);
+    }
+  }
+}
+// acc[nt] += A^T * B where A^T(m, k) is stored as at_tile[k][m] and B(k, n) as b_tile[k][n] (both read with ldmatrix.trans):
+// the P^T dO / dS^T Q form
+__device__ __forceinline__ void mm_colsT_x_cols(float (&acc)[8][4], uint32_t at_tile, uint32_t b_tile, int m0, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a0, a1, a2, a3;
+    const int mi = lane >> 3;
+    ldsm_x4_t(at_tile + (uint32_t)(((kk * 16 + (lane & 7) + (mi >> 1) * 8) * kPitch + m0 + (mi & 1) * 8) * 2), a0, a1, a2, a3);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(b_tile + (uint32_t)(((kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kPitch + np * 16 + (lane >> 4) * 8) * 2), b0, b1, b2, b3);
+      mma16816(acc[2 * np], a0, a1, a2, a3, b0, b1);
+      mma16816(acc[2 * np + 1], a0, a1, a2, a3, b2, b3);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) mha_small_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
+// softmax over the 64 (masked to T) columns of the two rows (g, g + 8) a thread holds pieces of; s holds raw dot products.
+// On return s holds the normalised probabilities (exactly 0 in the masked columns).
+__device__ __forceinline__ void softmax_rows(float (&s)[8][4], int T, float scale, int lane) {
+  const float k = scale * 1.4426950408889634f;
+  const int t2 = (lane & 3) * 2;
+  float mx0 = -FLT_MAX, mx1 = -FLT_MAX;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = nt * 8 + t2 + (e & 1);
+      s[nt][e] = col < T ? s[nt][e] * k : -FLT_MAX;
+    }
+    mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+    mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = nt * 8 + t2 + (e & 1);
+      const float p = col < T ? ex2_approx(s[nt][e] - ((e & 2) ? mx1 : mx0)) : 0.f;
+      s[nt][e] = p;
+      if (e & 2) sum1 += p; else sum0 += p;
+    }
+  }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    s[nt][0] *= inv0;
+    s[nt][1] *= inv0;
+    s[nt][2] *= inv1;
+    s[nt][3] *= inv1;
+  }
+}
+// the fp32 accumulator tiles of a 16 x 64 matrix as the bf16 A fragments of the next MMA (k = 64 in four steps)
+__device__ __forceinline__ void acc_to_afrag(const float (&s)[8][4], uint32_t (&af)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    af[kk][0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+    af[kk][1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+    af[kk][2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+    af[kk][3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+  }
+}
+// store a 16 x 64 accumulator (rows m0 + g, m0 + g + 8) as bf16 to global rows of stride `ld` elements; rows >= T are skipped
+__device__ __forceinline__ void store_rows(const float (&acc)[8][4], __nv_bfloat16* __restrict__ dst, long long ld, int m0, int T, int lane) {
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    if (m0 + g < T) *reinterpret_cast<uint32_t*>(dst + (long long)(m0 + g) * ld + nt * 8 + t2) = pack_bf16(acc[nt][0], acc[nt][1]);
+    if (m0 + g + 8 < T) *reinterpret_cast<uint32_t*>(dst + (long long)(m0 + g + 8) * ld + nt * 8 + t2) = pack_bf16(acc[nt][2], acc[nt][3]);
+  }
+}
+__device__ __forceinline__ void zero_acc(float (&acc)[8][4]) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+}
+
+__global__ void __launch_bounds__(128) mha_small_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                             __nv_bfloat16* __restrict__ out, int T, int heads, float scale) {
-  extern __shared__ float sm[];
-  float* q = sm;
-  float* k = q + kTmax * (kDh + 1);
-  float* v = k + kTmax * (kDh + 1);
-  float* s = v + kTmax * (kDh + 1);  // [T][kTmax+1]
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(sm_raw);
+  __nv_bfloat16* ks = qs + kTileElems;
+  __nv_bfloat16* vs = ks + kTileElems;
   const int n = blockIdx.x / heads, h = blockIdx.x % heads;
   const int W = heads * kDh;
   const __nv_bfloat16* base = qkv + (long long)n * T * 3 * W + h * kDh;
-  load_head(base, 3 * W, T, q);
-  load_head(base + W, 3 * W, T, k);
-  load_head(base + 2 * W, 3 * W, T, v);
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-    const int a = i / T, b = i % T;
-    float acc = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < kDh; ++d) acc = fmaf(q[a * (kDh + 1) + d], k[b * (kDh + 1) + d], acc);
-    s[a * (kTmax + 1) + b] = acc * scale;
-  }
+  stage_tile(base, 3 * W, T, qs);
+  stage_tile(base + W, 3 * W, T, ks);
+  stage_tile(base + 2 * W, 3 * W, T, vs);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int a = warp; a < T; a += (blockDim.x >> 5)) {
-    float mx = -FLT_MAX;
-    for (int b = lane; b < T; b += 32) mx = fmaxf(mx, s[a * (kTmax + 1) + b]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int b = lane; b < T; b += 32) {
-      const float e = __expf(s[a * (kTmax + 1) + b] - mx);
-      s[a * (kTmax + 1) + b] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    for (int b = lane; b < T; b += 32) s[a * (kTmax + 1) + b] *= inv;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * (kDh / 2); i += blockDim.x) {
-    const int a = i / (kDh / 2), d2 = i % (kDh / 2);
-    float o0 = 0.f, o1 = 0.f;
-    for (int b = 0; b < T; ++b) {
-      const float p = s[a * (kTmax + 1) + b];
-      o0 = fmaf(p, v[b * (kDh + 1) + 2 * d2], o0);
-      o1 = fmaf(p, v[b * (kDh + 1) + 2 * d2 + 1], o1);
-    }
-    *reinterpret_cast<__nv_bfloat162*>(out + ((long long)n * T + a) * W + h * kDh + 2 * d2) = __floats2bfloat162_rn(o0, o1);
-  }
+  const int m0 = warp * 16;
+  if (m0 >= T) return;
+  float s[8][4];
+  zero_acc(s);
+  mm_rows_x_rows(s, smem_u32(qs), smem_u32(ks), m0, lane);
+  softmax_rows(s, T, scale, lane);
+  uint32_t pf[4][4];
+  acc_to_afrag(s, pf);
+  float o[8][4];
+  zero_acc(o);
+  mm_frag_x_cols(o, pf, smem_u32(vs), lane);
+  store_rows(o, out + (long long)n * T * W + h * kDh, W, m0, T, lane);
 }
 
 // dqkv: [N][T][3W] bf16 gradient of the fused projection output.  Probabilities are recomputed.
-__global__ void __launch_bounds__(256) mha_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(128) mha_small_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                             const __nv_bfloat16* __restrict__ dout,
                                                             __nv_bfloat16* __restrict__ dqkv, int T, int heads, float scale) {
-  extern __shared__ float sm[];
-  float* q = sm;
-  float* k = q + kTmax * (kDh + 1);
-  float* v = k + kTmax * (kDh + 1);
-  float* dO = v + kTmax * (kDh + 1);
-  float* p = dO + kTmax * (kDh + 1);     // [T][kTmax+1] probabilities
-  float* ds = p + kTmax * (kTmax + 1);   // [T][kTmax+1] dS
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(sm_raw);
+  __nv_bfloat16* ks = qs + kTileElems;
+  __nv_bfloat16* vs = ks + kTileElems;
+  __nv_bfloat16* dos = vs + kTileElems;
+  __nv_bfloat16* ps = dos + kTileElems;     // P  [i][j]
+  __nv_bfloat16* dss = ps + kTileElems;     // dS [i][j]
   const int n = blockIdx.x / heads, h = blockIdx.x % heads;
   const int W = heads * kDh;
   const __nv_bfloat16* base = qkv + (long long)n * T * 3 * W + h * kDh;
-  load_head(base, 3 * W, T, q);
-  load_head(base + W, 3 * W, T, k);
-  load_head(base + 2 * W, 3 * W, T, v);
-  load_head(dout + (long long)n * T * W + h * kDh, W, T, dO);
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
-    const int a = i / T, b = i % T;
-    float acc = 0.f, acc2 = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < kDh; ++d) {
-      acc = fmaf(q[a * (kDh + 1) + d], k[b * (kDh + 1) + d], acc);
-      acc2 = fmaf(dO[a * (kDh + 1) + d], v[b * (kDh + 1) + d], acc2);
-    }
-    p[a * (kTmax + 1) + b] = acc * scale;
-    ds[a * (kTmax + 1) + b] = acc2;  // dP
-  }
-  __syncthreads();
+  stage_tile(base, 3 * W, T, qs);
+  stage_tile(base + W, 3 * W, T, ks);
+  stage_tile(base + 2 * W, 3 * W, T, vs);
+  stage_tile(dout + (long long)n * T * W + h * kDh, W, T, dos);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int a = warp; a < T; a += (blockDim.x >> 5)) {
-    float mx = -FLT_MAX;
-    for (int b = lane; b < T; b += 32) mx = fmaxf(mx, p[a * (kTmax + 1) + b]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int b = lane; b < T; b += 32) {
-      const float e = __expf(p[a * (kTmax + 1) + b] - mx);
-      p[a * (kTmax + 1) + b] = e;
-      sum += e;
+  const int m0 = warp * 16;
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+  if (m0 >= T) {   // this warp's query rows do not exist: their P / dS rows must still be finite for phase 2
+    for (int i = lane; i < 16 * 8; i += 32) {
+      *reinterpret_cast<uint4*>(ps + (m0 + (i >> 3)) * kPitch + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(dss + (m0 + (i >> 3)) * kPitch + (i & 7) * 8) = make_uint4(0u, 0u, 0u, 0u);
     }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    float dot = 0.f;
-    for (int b = lane; b < T; b += 32) {
-      const float pv = p[a * (kTmax + 1) + b] * inv;
-      p[a * (kTmax + 1) + b] = pv;
-      dot += pv * ds[a * (kTmax + 1) + b];
-    }
-    dot = warp_sum(dot);
-    for (int b = lane; b < T; b += 32)
-      ds[a * (kTmax + 1) + b] = p[a * (kTmax + 1) + b] * (ds[a * (kTmax + 1) + b] - dot) * scale;
   }
   __syncthreads();
   __nv_bfloat16* ob = dqkv + (long long)n * T * 3 * W + h * kDh;
-  for (int i = threadIdx.x; i < T * (kDh / 2); i += blockDim.x) {
-    const int a = i / (kDh / 2), d2 = i % (kDh / 2);
-    float dq0 = 0.f, dq1 = 0.f, dk0 = 0.f, dk1 = 0.f, dv0 = 0.f, dv1 = 0.f;
-    for (int b = 0; b < T; ++b) {
-      const float dsab = ds[a * (kTmax + 1) + b];  // dS[a][b]
-      const float dsba = ds[b * (kTmax + 1) + a];  // dS[b][a]
-      const float pba = p[b * (kTmax + 1) + a];    // P[b][a]
-      dq0 = fmaf(dsab, k[b * (kDh + 1) + 2 * d2], dq0);
-      dq1 = fmaf(dsab, k[b * (kDh + 1) + 2 * d2 + 1], dq1);
-      dk0 = fmaf(dsba, q[b * (kDh + 1) + 2 * d2], dk0);
-      dk1 = fmaf(dsba, q[b * (kDh + 1) + 2 * d2 + 1], dk1);
-      dv0 = fmaf(pba, dO[b * (kDh + 1) + 2 * d2], dv0);
-      dv1 = fmaf(pba, dO[b * (kDh + 1) + 2 * d2 + 1], dv1);
+  if (m0 < T) {
+    // ---- phase 1: rows i of this warp
+    float p[8][4], dp[8][4];
+    zero_acc(p);
+    mm_rows_x_rows(p, smem_u32(qs), smem_u32(ks), m0, lane);
+    softmax_rows(p, T, scale, lane);
+    zero_acc(dp);
+    mm_rows_x_rows(dp, smem_u32(dos), smem_u32(vs), m0, lane);
+    float d0 = 0.f, d1 = 0.f;   // rowsum(P * dP) for rows g, g + 8
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      d0 = fmaf(p[nt][0], dp[nt][0], fmaf(p[nt][1], dp[nt][1], d0));
+      d1 = fmaf(p[nt][2], dp[nt][2], fmaf(p[nt][3], dp[nt][3], d1));
     }
-    __nv_bfloat16* r = ob + (long long)a * 3 * W + 2 * d2;
-    *reinterpret_cast<__nv_bfloat162*>(r) = __floats2bfloat162_rn(dq0, dq1);
-    *reinterpret_cast<__nv_bfloat162*>(r + W) = __floats2bfloat162_rn(dk0, dk1);
-    *reinterpret_cast<__nv_bfloat162*>(r + 2 * W) = __floats2bfloat162_rn(dv0, dv1);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      // P to shared memory (bf16) for phase 2, then dS in place of dP
+      *reinterpret_cast<uint32_t*>(ps + (m0 + g) * kPitch + nt * 8 + t2) = pack_bf16(p[nt][0], p[nt][1]);
+      *reinterpret_cast<uint32_t*>(ps + (m0 + g + 8) * kPitch + nt * 8 + t2) = pack_bf16(p[nt][2], p[nt][3]);
+      dp[nt][0] = p[nt][0] * (dp[nt][0] - d0) * scale;
+      dp[nt][1] = p[nt][1] * (dp[nt][1] - d0) * scale;
+      dp[nt][2] = p[nt][2] * (dp[nt][2] - d1) * scale;
+      dp[nt][3] = p[nt][3] * (dp[nt][3] - d1) * scale;
+      *reinterpret_cast<uint32_t*>(dss + (m0 + g) * kPitch + nt * 8 + t2) = pack_bf16(dp[nt][0], dp[nt][1]);
+      *reinterpret_cast<uint32_t*>(dss + (m0 + g + 8) * kPitch + nt * 8 + t2) = pack_bf16(dp[nt][2], dp[nt][3]);
+    }
+    uint32_t dsf[4][4];
+    acc_to_afrag(dp, dsf);
+    float dq[8][4];
+    zero_acc(dq);
+    mm_frag_x_cols(dq, dsf, smem_u32(ks), lane);          // dQ = dS K
+    store_rows(dq, ob, 3 * W, m0, T, lane);
+  }
+  __syncthreads();
+  if (m0 < T) {
+    // ---- phase 2: rows j (keys) of this warp
+    float acc[8][4];
+    zero_acc(acc);
+    mm_colsT_x_cols(acc, smem_u32(dss), smem_u32(qs), m0, lane);   // dK = dS^T Q
+    store_rows(acc, ob + W, 3 * W, m0, T, lane);
+    zero_acc(acc);
+    mm_colsT_x_cols(acc, smem_u32(ps), smem_u32(dos), m0, lane);   // dV = P^T dO
+    store_rows(acc, ob + 2 * W, 3 * W, m0, T, lane);
   }
 }
 
@@ -162,17 +284,23 @@ __global__ void __launch_bounds__(256) mha_small_bwd_kernel(const __nv_bfloat16*
 
 using namespace ffvc;
 
+static int mha_setup() {
+  static bool done = false;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(mha_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kTileElems * 2);
+    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+    done = true;
+  }
+  return FFVC_OK;
+}
+
 extern "C" int ffvc_mha_small_fwd(const void* qkv, void* out, int N, int T, int heads, int head_dim, float scale,
                                   void* stream) {
   if (head_dim != kDh || T > kTmax || T < 1) return set_error(FFVC_ERR_UNSUPPORTED, "mha_small: head_dim must be 64 and T <= 64");
-  const size_t smem = (size_t)(3 * kTmax * (kDh + 1) + kTmax * (kTmax + 1)) * sizeof(float);
-  static bool done = false;
-  if (!done) {
-    cudaFuncSetAttribute(mha_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(mha_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
-    done = true;
-  }
-  mha_small_fwd_kernel<<<N * heads, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  if ((heads * kDh) % 8 != 0) return set_error(FFVC_ERR_ARG, "mha_small: width must be a multiple of 8");
+  int rc = mha_setup();
+  if (rc) return rc;
+  mha_small_fwd_kernel<<<N * heads, 128, 3 * kTileElems * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), T, heads, scale);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
@@ -181,14 +309,9 @@ extern "C" int ffvc_mha_small_fwd(const void* qkv, void* out, int N, int T, int 
 extern "C" int ffvc_mha_small_bwd(const void* qkv, const void* dout, void* dqkv, int N, int T, int heads, int head_dim,
                                   float scale, void* stream) {
   if (head_dim != kDh || T > kTmax || T < 1) return set_error(FFVC_ERR_UNSUPPORTED, "mha_small: head_dim must be 64 and T <= 64");
-  const size_t smem = (size_t)(4 * kTmax * (kDh + 1) + 2 * kTmax * (kTmax + 1)) * sizeof(float);
-  static bool done = false;
-  if (!done) {
-    cudaFuncSetAttribute(mha_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(mha_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
-    done = true;
-  }
-  mha_small_bwd_kernel<<<N * heads, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  int rc = mha_setup();
+  if (rc) return rc;
+  mha_small_bwd_kernel<<<N * heads, 128, 6 * kTileElems * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout),
       reinterpret_cast<__nv_bfloat16*>(dqkv), T, heads, scale);
   FFVC_CHECK_LAUNCH();

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cstdint>
+#include <cstring>
 #include <cfloat>
 
 #include "ffvc_internal.h"
@@ -155,66 +156,59 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const 
 }
 
 // ---------------------------------------------------------------- bias gradients
-// db[n] += sum_rows dy[row][n], n % 8 == 0.  One persistent CTA per SM, 512 threads = (row lanes) x (8-column vectors);
-// 8 rows in flight per thread (16-byte loads), row lanes folded through shared memory, then ONE vector reduction
-// (red.global.add.v4.f32) per 4 columns per CTA: the earlier form issued a scalar atomic per column from 512 small CTAs and
-// was bound by same-line atomic serialisation (0.7 TB/s); this one streams at HBM rate.
+// db[n] += sum_rows dy[row][n], n % 8 == 0.  A CTA (512 threads) owns a slab of <= 32 eight-column vectors (512 B of every
+// row) x a chunk of rows: thread = (row lane, column vector), 8 rows in flight per thread (16-byte streaming loads), row
+// lanes folded through shared memory, then ONE vector reduction (red.global.add.v4.f32) per 4 columns per CTA.  Splitting
+// by column slabs keeps the number of atomics that hit one address at (row chunks) ~ SMs / slabs: the earlier forms (one
+// scalar atomic per column from 512 small CTAs; then full-width rows per CTA) were bound by same-line atomic serialisation.
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 __global__ void __launch_bounds__(512) colsum_vec_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
-                                                         long long rows, int n, int rows_per_cta) {
-  extern __shared__ float cs[];                       // [lanes][ncv*8] partials when lanes > 1
-  const int ncv = n >> 3;                             // column vectors
-  const int lanes = max(1, (int)blockDim.x / ncv);    // row lanes that fit in the CTA
-  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+                                                         long long rows, int n, int cvw, int rows_per_cta) {
+  extern __shared__ float cs[];                       // [lanes][cvw * 8] partials
+  const int ncv = n >> 3;                             // column vectors in a row
+  const int lanes = (int)blockDim.x / cvw;            // row lanes
+  const int cvl = threadIdx.x % cvw, rl = threadIdx.x / cvw;
+  const int cv = blockIdx.x * cvw + cvl;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = min(rows, r0 + rows_per_cta);
-  {
-    const int cv0 = blockIdx.y * blockDim.x;            // column block (gridDim.y > 1 only when n > 4096)
-    const int t = threadIdx.x;
-    const int cv = cv0 + (lanes > 1 ? t % ncv : t);
-    const int rl = lanes > 1 ? t / ncv : 0;
-    const bool active = cv < ncv && rl < lanes;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (active) {
-      const __nv_bfloat16* base = dy + (long long)cv * 8;
-      for (long long r = r0 + rl; r < r1; r += (long long)lanes * 8) {
-        uint4 pk[8];
+  const bool active = cv < ncv && rl < lanes;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    const __nv_bfloat16* base = dy + (long long)cv * 8;
+    for (long long r = r0 + rl; r < r1; r += (long long)lanes * 8) {
+      uint4 pk[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const long long rr = r + (long long)u * lanes;
-          pk[u] = rr < r1 ? __ldcs(reinterpret_cast<const uint4*>(base + rr * n)) : make_uint4(0u, 0u, 0u, 0u);
-        }
+      for (int u = 0; u < 8; ++u) {
+        const long long rr = r + (long long)u * lanes;
+        pk[u] = rr < r1 ? __ldcs(reinterpret_cast<const uint4*>(base + rr * n)) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[u]);
+      for (int u = 0; u < 8; ++u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[u]);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h[j]);
-            acc[2 * j] += f.x;
-            acc[2 * j + 1] += f.y;
-          }
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
         }
       }
     }
-    if (lanes > 1) {
-      if (active) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) cs[(rl * ncv + cv) * 8 + j] = acc[j];
-      }
-      __syncthreads();
-      if (active && rl == 0) {
-        for (int l = 1; l < lanes; ++l) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) acc[j] += cs[(l * ncv + cv) * 8 + j];
-        }
-      }
-      __syncthreads();
-    }
-    if (active && rl == 0) {
-      red_add_v4(db + cv * 8, acc[0], acc[1], acc[2], acc[3]);
-      red_add_v4(db + cv * 8 + 4, acc[4], acc[5], acc[6], acc[7]);
-    }
+    for (int j = 0; j < 8; ++j) cs[(rl * cvw + cvl) * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  // fold the row lanes: thread (l, cvl) with l < 8 sums column j = l of vector cvl over all lanes
+  if (cv < ncv && rl < 8) {
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += cs[(l * cvw + cvl) * 8 + rl];
+    cs[cvl * 8 + rl] = t;   // lane 0's slot; every reader of slot (0, cvl, rl) is this thread
+  }
+  __syncthreads();
+  if (cv < ncv && rl < 2) {
+    const float* q = cs + cvl * 8 + rl * 4;
+    red_add_v4(db + cv * 8 + rl * 4, q[0], q[1], q[2], q[3]);
   }
 }
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
@@ -389,6 +383,63 @@ __global__ void __launch_bounds__(256) vq_nearest_kernel(const float* __restrict
       if (zq_bf16) zq_bf16[(row0 + r) * C + c] = __float2bfloat16(v);
       if (zq_f32) zq_f32[(row0 + r) * C + c] = v;
     }
+  }
+}
+// ---- tensor-core nearest-code search (ffvc_vq_nearest_tc): operand preparation and the final gather.
+// A 2-term bf16 split x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) carries 16 mantissa bits; the GEMM contracts
+// [z_hi | z_hi | z_lo] with [c_hi | c_lo | c_hi] (K = 3C), i.e. z.c up to the lo.lo term (relative 2^-16 per product, random
+// sign: ~1e-4 absolute on a 256-term dot product of O(1) values), accumulated in fp32 by the tensor core.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16(x);
+  lo = __float2bfloat16(x - __bfloat162float(hi));
+}
+__global__ void vq_split_codebook_kernel(const float* __restrict__ cb, __nv_bfloat16* __restrict__ cs, float* __restrict__ cnorm,
+                                         int ncodes, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= ncodes) return;
+  float s = 0.f;
+  for (int i = lane; i < C; i += 32) {
+    const float v = cb[(long long)row * C + i];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    __nv_bfloat16* o = cs + (long long)row * 3 * C;
+    o[i] = hi;
+    o[C + i] = lo;
+    o[2 * C + i] = hi;
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) cnorm[row] = s;
+}
+__global__ void vq_split_z_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ zs, float* __restrict__ zc,
+                                  long long P, int C, float lo_, float hi_) {
+  const long long total = P * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i % C);
+    const float v = fminf(fmaxf(z[i], lo_), hi_);       // clamp_with_grad forward (main.py:763)
+    if (zc) zc[i] = v;
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    __nv_bfloat16* o = zs + r * 3 * C;
+    o[c] = hi;
+    o[C + c] = hi;
+    o[2 * C + c] = lo;
+  }
+}
+__global__ void vq_gather_kernel(const unsigned long long* __restrict__ keys, const float* __restrict__ codebook,
+                                 int* __restrict__ idx_out, __nv_bfloat16* __restrict__ zq_bf16, float* __restrict__ zq_f32,
+                                 long long P, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= P) return;
+  const int code = (int)(keys[row] & 0xffffffffull);
+  if (lane == 0) idx_out[row] = code;
+  for (int c = lane; c < C; c += 32) {
+    const float v = codebook[(long long)code * C + c];
+    if (zq_bf16) zq_bf16[row * C + c] = __float2bfloat16(v);
+    if (zq_f32) zq_f32[row * C + c] = v;
   }
 }
 __global__ void rownorm2_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int C) {
@@ -634,13 +685,16 @@ extern "C" int ffvc_colsum(const void* dy, float* db, long long rows, int n, voi
       if (sms <= 0) sms = 148;
     }
     const int ncv = n / 8;
-    const int lanes = ncv >= 512 ? 1 : 512 / ncv;
-    long long rows_per_cta = (rows + sms - 1) / sms;
+    const int cvw = ncv < 32 ? ncv : 32;                           // column vectors per CTA slab
+    const int lanes = 512 / cvw;                                   // >= 16 row lanes (needs >= 8 for the fold)
+    const int slabs = (ncv + cvw - 1) / cvw;
+    long long chunks = sms / slabs > 0 ? sms / slabs : 1;          // row chunks so that slabs * chunks ~ SMs
     const long long q = (long long)lanes * 8;                      // whole unrolled row batches per CTA
-    rows_per_cta = (rows_per_cta + q - 1) / q * q;
-    const unsigned grid = (unsigned)((rows + rows_per_cta - 1) / rows_per_cta);
-    const size_t smem = lanes > 1 ? (size_t)lanes * ncv * 8 * sizeof(float) : 0;
-    colsum_vec_kernel<<<dim3(grid, (unsigned)((ncv + 511) / 512)), 512, smem, ST(stream)>>>(CBF(dy), db, rows, n, (int)rows_per_cta);
+    long long rows_per_cta = ((rows + chunks - 1) / chunks + q - 1) / q * q;
+    chunks = (rows + rows_per_cta - 1) / rows_per_cta;
+    if (slabs > 65535 || chunks > 65535) return set_error(FFVC_ERR_ARG, "colsum: tensor too large");
+    colsum_vec_kernel<<<dim3((unsigned)slabs, (unsigned)chunks), 512, 512 * 8 * sizeof(float), ST(stream)>>>(
+        CBF(dy), db, rows, n, cvw, (int)rows_per_cta);
   } else {
     const int rows_per_cta = 512;
     dim3 grid((n + 255) / 256, (unsigned)((rows + rows_per_cta - 1) / rows_per_cta));
@@ -695,6 +749,42 @@ extern "C" int ffvc_vq_nearest(const float* z, const float* codebook, const floa
     vq_nearest_kernel<64><<<grid, 256, smem, ST(stream)>>>(z, codebook, codeT, cnorm, idx, BF(zq_bf16), zq_f32, zc, P, ncodes, lo, hi);
   else
     return set_error(FFVC_ERR_UNSUPPORTED, "vq_nearest: embed dim must be 64 or 256");
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_vq_prepare_codebook(const float* codebook, void* csplit_bf16, float* cnorm, int ncodes, int C, void* stream) {
+  if (!codebook || !csplit_bf16 || !cnorm) return set_error(FFVC_ERR_ARG, "vq_prepare_codebook: null pointer");
+  vq_split_codebook_kernel<<<(ncodes + 7) / 8, 256, 0, ST(stream)>>>(codebook, BF(csplit_bf16), cnorm, ncodes, C);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_vq_nearest_tc(const float* z, const float* codebook, const void* csplit_bf16, const float* cnorm,
+                                  void* zsplit_bf16, void* keys_u64, int* idx, void* zq_bf16, float* zq_f32, float* zc, long long P,
+                                  int C, int ncodes, float lo, float hi, void* stream) {
+  if (!z || !codebook || !csplit_bf16 || !cnorm || !zsplit_bf16 || !keys_u64 || !idx)
+    return set_error(FFVC_ERR_ARG, "vq_nearest_tc: null pointer");
+  if ((3 * C) % 8 != 0 || P <= 0 || P > 0x7fffffffLL) return set_error(FFVC_ERR_ARG, "vq_nearest_tc: 3*C must be a multiple of 8");
+  vq_split_z_kernel<<<grid_for(P * C, 256), 256, 0, ST(stream)>>>(z, BF(zsplit_bf16), zc, P, C, lo, hi);
+  FFVC_CHECK_LAUNCH();
+  cudaMemsetAsync(keys_u64, 0xFF, sizeof(unsigned long long) * P, ST(stream));
+  ffvc_gemm_params g;
+  memset(&g, 0, sizeof(g));
+  g.a = zsplit_bf16;
+  g.b = csplit_bf16;
+  g.a_ld = g.b_ld = 3 * C;
+  g.M = (int)P;
+  g.N = ncodes;
+  g.K = 3 * C;
+  g.batch = g.k_segs = g.splits = 1;
+  g.bias = cnorm;                  // d = |c|^2 - 2 z.c   (|z|^2 is constant per row and dropped)
+  g.bias_mode = 1;
+  g.alpha = -2.0f;
+  g.ldc = ncodes;
+  g.argmin_out = keys_u64;
+  int rc = ffvc_gemm(&g, stream);
+  if (rc) return rc;
+  vq_gather_kernel<<<(unsigned)((P + 7) / 8), 256, 0, ST(stream)>>>(reinterpret_cast<const unsigned long long*>(keys_u64), codebook,
+                                                                     idx, BF(zq_bf16), zq_f32, P, C);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

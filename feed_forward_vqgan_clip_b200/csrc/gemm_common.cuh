@@ -36,6 +36,7 @@ struct GemmDev {
   int act;        // FFVC_ACT_*
   int mul_mode;   // multiply by act'(aux): FFVC_ACT_*
   float alpha;
+  unsigned long long* argmin;   // optional: per-row arg-min epilogue (see ffvc_gemm_params.argmin_out)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -63,6 +64,49 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
   pk.z = *reinterpret_cast<uint32_t*>(&h2);
   pk.w = *reinterpret_cast<uint32_t*>(&h3);
   return pk;
+}
+
+// Compile-time epilogue configuration.  The fused epilogue is driven by runtime flags (activation, activation-gradient
+// multiplier, bias mode, second output, residual, fp32 / atomic output, alpha); evaluated per 16-column chunk they cost more
+// instructions than the math itself (ncu source page of the K = 256 token-mixing GEMM: 375 warp instructions per chunk,
+// 112 of them arithmetic — PRMT copies of unused prefetch registers, predicated-off loads, an indirect branch on the
+// activation code, spill reloads).  kEpi >= 0 bakes the hot combinations in (bf16 output, alpha = 1, no atomics):
+//   bits [0:3) activation, [3:6) activation-gradient multiplier, [6:8) bias mode, 8 second (pre-activation) output, 9 residual
+// kEpi = -1 keeps every flag at run time (all other call sites, incl. the halo-reuse conv kernel).
+constexpr int epi_code(int act, int mul, int bias_mode, int pre, int res) {
+  return act | (mul << 3) | (bias_mode << 6) | (pre << 8) | (res << 9);
+}
+template <int kEpi>
+struct Epi {
+  static constexpr bool kGen = kEpi < 0;
+  __device__ __forceinline__ static int act(const GemmDev& p) { if constexpr (kGen) return p.act; else return kEpi & 7; }
+  __device__ __forceinline__ static int mul(const GemmDev& p) { if constexpr (kGen) return p.mul_mode; else return (kEpi >> 3) & 7; }
+  __device__ __forceinline__ static int bias(const GemmDev& p) { if constexpr (kGen) return p.bias_mode; else return (kEpi >> 6) & 3; }
+  __device__ __forceinline__ static bool pre(const GemmDev& p) { if constexpr (kGen) return p.pre_out != nullptr; else return ((kEpi >> 8) & 1) != 0; }
+  __device__ __forceinline__ static bool res(const GemmDev& p) { if constexpr (kGen) return p.res != nullptr; else return ((kEpi >> 9) & 1) != 0; }
+  __device__ __forceinline__ static bool f32(const GemmDev& p) { if constexpr (kGen) return p.out_fp32 != 0; else return false; }
+  __device__ __forceinline__ static bool atomic(const GemmDev& p) { if constexpr (kGen) return p.atomic != 0; else return false; }
+  __device__ __forceinline__ static bool scaled(const GemmDev& p) { if constexpr (kGen) return p.alpha != 1.0f; else return false; }
+  __device__ __forceinline__ static bool argmin(const GemmDev& p) { if constexpr (kGen) return p.argmin != nullptr; else return false; }
+};
+
+// order-preserving map float -> uint32 (smaller float <-> smaller unsigned)
+__device__ __forceinline__ uint32_t float_order_bits(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// arg-min epilogue on one CW-wide chunk of one output row: v = alpha * acc + bias[n]; running (best, n) in registers
+template <int CW>
+__device__ __forceinline__ void argmin_chunk(const GemmDev& p, const uint32_t (&r)[CW], int gn0, const float* sbias, float& best,
+                                             int& besti) {
+#pragma unroll
+  for (int i = 0; i < CW; ++i) {
+    const float v = fmaf(__uint_as_float(r[i]), p.alpha, sbias ? sbias[i] : 0.f);
+    if (gn0 + i < p.N && v < best) {    // strict <: ties keep the lowest column (torch.argmin)
+      best = v;
+      besti = gn0 + i;
+    }
+  }
 }
 
 // activation / activation-gradient on a CW-wide register chunk held as CW/2 float2 pairs; the switch is hoisted out of
@@ -110,6 +154,19 @@ __device__ __forceinline__ void unpack_bf16x2N(const uint4 (&pk)[CW / 8], float2
     for (int j = 0; j < 4; ++j) f[q * 4 + j] = __bfloat1622float2(h[j]);
   }
 }
+// 256-bit global accesses (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256): one full 32-byte sector per lane.  In the TMEM register
+// layout a lane owns one output ROW, so a warp store touches 32 different lines whatever the width; 32 B per lane halves the
+// number of L1 store requests (and partial-sector writes) of the epilogue relative to 16-byte stores.
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ uint4 pack_bf16x8_2(const float2* v) {
   uint4 pk;
   __nv_bfloat162 h0 = __float22bfloat162_rn(v[0]);
@@ -139,13 +196,14 @@ __device__ __forceinline__ void unpack_bf16xN(const uint4 (&pk)[CW / 8], float (
 // fused epilogue on 32 consecutive columns of one output row.
 //   sbias : column bias of this tile staged in shared memory (already offset to this chunk), or nullptr
 //   pf_aux / pf_res : aux / residual of this chunk prefetched into registers (valid when `vec` is true)
-template <int CW>
+template <int CW, int kEpi = -1>
 __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[CW], int gn0, long long off, float rbias,
                                                bool vec, const float* sbias, const uint4 (&pf_aux)[CW / 8],
-                                               const uint4 (&pf_res)[CW / 8]) {
+                                               const uint4 (&pf_res)[CW / 8], bool vec32 = false) {
+  using E = Epi<kEpi>;
   const int ncols = min(CW, p.N - gn0);
   float2 v[CW / 2];
-  if (p.alpha != 1.0f) {
+  if (E::scaled(p)) {
     const float2 al = make_float2(p.alpha, p.alpha);
 #pragma unroll
     for (int i = 0; i < CW / 2; ++i) v[i] = __fmul2_rn(make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), al);
@@ -153,21 +211,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
 #pragma unroll
     for (int i = 0; i < CW / 2; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
   }
-  if (p.bias_mode == 1) {
+  if (E::bias(p) == 1) {
 #pragma unroll
     for (int i = 0; i < CW / 4; ++i) {
       const float4 b4 = *reinterpret_cast<const float4*>(sbias + 4 * i);   // smem broadcast; zero beyond N
       v[2 * i] = __fadd2_rn(v[2 * i], make_float2(b4.x, b4.y));
       v[2 * i + 1] = __fadd2_rn(v[2 * i + 1], make_float2(b4.z, b4.w));
     }
-  } else if (p.bias_mode == 2) {
+  } else if (E::bias(p) == 2) {
     const float2 rb = make_float2(rbias, rbias);
 #pragma unroll
     for (int i = 0; i < CW / 2; ++i) v[i] = __fadd2_rn(v[i], rb);
   }
-  if (p.pre_out != nullptr) {
+  if (E::pre(p)) {
     __nv_bfloat16* po = reinterpret_cast<__nv_bfloat16*>(p.pre_out) + off;
-    if (vec) {
+    if (vec32) {
+#pragma unroll
+      for (int i = 0; i < CW / 16; ++i) st_global_256(po + 16 * i, pack_bf16x8_2(v + 8 * i), pack_bf16x8_2(v + 8 * i + 4));
+    } else if (vec) {
 #pragma unroll
       for (int i = 0; i < CW / 8; ++i) *reinterpret_cast<uint4*>(po + 8 * i) = pack_bf16x8_2(v + 4 * i);
     } else {
@@ -178,8 +239,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
       }
     }
   }
-  act_chunk<CW>(v, p.act);
-  if (p.mul_mode != FFVC_ACT_NONE) {
+  act_chunk<CW>(v, E::act(p));
+  if (E::mul(p) != FFVC_ACT_NONE) {
     float2 x[CW / 2];
     if (vec) {
       unpack_bf16x2N<CW>(pf_aux, x);
@@ -189,9 +250,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
       for (int i = 0; i < CW / 2; ++i)
         x[i] = make_float2((2 * i < ncols) ? __bfloat162float(ax[2 * i]) : 0.f, (2 * i + 1 < ncols) ? __bfloat162float(ax[2 * i + 1]) : 0.f);
     }
-    mulgrad_chunk<CW>(v, x, p.mul_mode);
+    mulgrad_chunk<CW>(v, x, E::mul(p));
   }
-  if (p.res != nullptr) {
+  if (E::res(p)) {
     float2 x[CW / 2];
     if (vec) {
       unpack_bf16x2N<CW>(pf_res, x);
@@ -204,9 +265,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
 #pragma unroll
     for (int i = 0; i < CW / 2; ++i) v[i] = __fadd2_rn(v[i], x[i]);
   }
-  if (p.out_fp32) {
+  if (E::f32(p)) {
     float* o = reinterpret_cast<float*>(p.out) + off;
-    if (p.atomic) {
+    if (E::atomic(p)) {
 #pragma unroll
       for (int i = 0; i < CW / 2; ++i) {
         if (2 * i < ncols) atomicAdd(o + 2 * i, v[i].x);
@@ -225,7 +286,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
     }
   } else {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-    if (vec) {
+    if (vec32) {
+#pragma unroll
+      for (int i = 0; i < CW / 16; ++i) st_global_256(o + 16 * i, pack_bf16x8_2(v + 8 * i), pack_bf16x8_2(v + 8 * i + 4));
+    } else if (vec) {
 #pragma unroll
       for (int i = 0; i < CW / 8; ++i) *reinterpret_cast<uint4*>(o + 8 * i) = pack_bf16x8_2(v + 4 * i);
     } else {

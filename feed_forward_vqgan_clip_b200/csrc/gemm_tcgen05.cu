@@ -48,7 +48,7 @@ static constexpr int kTmemCols = 512;
 //   HALF of the B tile; the leader CTA issues tcgen05.mma M=256 that reads both CTAs' shared memory, so every SM
 //   reads / is written only (A + B/2) per k-step instead of (A + B): the 1-CTA kernel is shared-memory-bandwidth
 //   bound (128 B/clk/SM) at ~55-65 % of the tensor pipe, the pair removes a third of that traffic.  6-stage ring.
-template <bool kTwoCta, int kEpiWarps>
+template <bool kTwoCta, int kEpiWarps, int kEpi>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmDev p) {
@@ -263,8 +263,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));  // [2][256] floats
     int acc = 0;
     uint32_t acc_phase = 0;
+    using E = Epi<kEpi>;
     const bool vec_ok = (p.ldc % 8 == 0) && (p.out_bs % 8 == 0) && (p.out_bs_inner % 8 == 0);
-    const bool want_aux = p.mul_mode != FFVC_ACT_NONE, want_res = p.res != nullptr;
+    // 32-byte accesses: every row / batch stride a multiple of 16 elements and 32-byte aligned base pointers (bf16 outputs)
+    const bool vec32_ok = vec_ok && !E::f32(p) && (p.ldc % 16 == 0) && (p.out_bs % 16 == 0) && (p.out_bs_inner % 16 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.pre_out) |
+                            reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.res)) & 31) == 0;
+    const bool want_aux = E::mul(p) != FFVC_ACT_NONE, want_res = E::res(p);
     for (long long t = tile_first; t < total_tiles; t += tile_step) {
       const int rem = (int)(t % tiles_all_batches);
       const int bi = rem / tiles_per_batch;
@@ -278,29 +283,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       float* sbias = sbias_all + acc * 256;
       // stage this tile's column bias in shared memory (double-buffered with the accumulator stage) and prefetch the first
       // chunk's aux / residual: all of it overlaps the wait for the MMA warp
-      if (p.bias_mode == 1) {
+      if (E::bias(p) == 1) {
         if (etid < p.block_n) sbias[etid] = (n0 + etid < p.N) ? p.bias[n0 + etid] : 0.f;
         asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       }
-      const float rbias = (p.bias_mode == 2 && row_ok) ? p.bias[gm] : 0.0f;
+      const float rbias = (E::bias(p) == 2 && row_ok) ? p.bias[gm] : 0.0f;
       constexpr int CW = (kEpiWarps == 16) ? 16 : 32;   // columns per register chunk
       uint4 pf_aux[CW / 8], pf_res[CW / 8];
       auto prefetch = [&](int c) {
         const int gn0 = n0 + c;
         if (row_ok && vec_ok && gn0 + CW <= p.N) {
           if (want_aux) {
-            const uint4* ax = reinterpret_cast<const uint4*>(p.aux + row_off + gn0);
+            if (vec32_ok) {
 #pragma unroll
-            for (int j = 0; j < CW / 8; ++j) pf_aux[j] = ax[j];
+              for (int j = 0; j < CW / 16; ++j) ld_global_256(p.aux + row_off + gn0 + 16 * j, pf_aux[2 * j], pf_aux[2 * j + 1]);
+            } else {
+              const uint4* ax = reinterpret_cast<const uint4*>(p.aux + row_off + gn0);
+#pragma unroll
+              for (int j = 0; j < CW / 8; ++j) pf_aux[j] = ax[j];
+            }
           }
           if (want_res) {
-            const uint4* rs = reinterpret_cast<const uint4*>(p.res + row_off + gn0);
+            if (vec32_ok) {
 #pragma unroll
-            for (int j = 0; j < CW / 8; ++j) pf_res[j] = rs[j];
+              for (int j = 0; j < CW / 16; ++j) ld_global_256(p.res + row_off + gn0 + 16 * j, pf_res[2 * j], pf_res[2 * j + 1]);
+            } else {
+              const uint4* rs = reinterpret_cast<const uint4*>(p.res + row_off + gn0);
+#pragma unroll
+              for (int j = 0; j < CW / 8; ++j) pf_res[j] = rs[j];
+            }
           }
         }
       };
-      if (c_begin < c_end) prefetch(c_begin);
+      if ((want_aux || want_res) && c_begin < c_end) prefetch(c_begin);
+      float am_best = 3.402823466e+38f;
+      int am_idx = -1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       for (int c = c_begin; c < c_end; c += CW) {
@@ -310,15 +327,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld_wait();
         const int gn0 = n0 + c;
         uint4 cur_aux[CW / 8], cur_res[CW / 8];
+        if (want_aux) {
 #pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          cur_aux[j] = pf_aux[j];
-          cur_res[j] = pf_res[j];
+          for (int j = 0; j < CW / 8; ++j) cur_aux[j] = pf_aux[j];
         }
-        if (c + CW < c_end) prefetch(c + CW);
-        if (row_ok && gn0 < p.N)
-          epilogue_chunk<CW>(p, r, gn0, row_off + gn0, rbias, vec_ok && (gn0 + CW <= p.N), sbias + c, cur_aux, cur_res);
+        if (want_res) {
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) cur_res[j] = pf_res[j];
+        }
+        if ((want_aux || want_res) && c + CW < c_end) prefetch(c + CW);
+        if (E::argmin(p)) {
+          if (row_ok && gn0 < p.N) argmin_chunk<CW>(p, r, gn0, E::bias(p) == 1 ? sbias + c : nullptr, am_best, am_idx);
+        } else if (row_ok && gn0 < p.N) {
+          epilogue_chunk<CW, kEpi>(p, r, gn0, row_off + gn0, rbias, vec_ok && (gn0 + CW <= p.N), sbias + c, cur_aux, cur_res,
+                                   vec32_ok && (gn0 + CW <= p.N));
+        }
         __syncwarp();
+      }
+      if (E::argmin(p) && row_ok && am_idx >= 0) {
+        const unsigned long long key = ((unsigned long long)float_order_bits(am_best) << 32) | (unsigned)am_idx;
+        atomicMin(p.argmin + (long long)bi * p.M + gm, key);
       }
       // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp (of the leader CTA)
       tc_fence_before();
@@ -394,13 +422,65 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
 static int g_num_sms = 0;
 static bool g_attr_set = false;
 
+
+// ---- kernel instantiations: generic epilogue x {1-CTA, CTA pair} x {8, 16 epilogue warps}, plus the compile-time epilogues
+// of the mapper / CLIP activation GEMMs on the 16-warp form
+static constexpr int kNumEpiCodes = 5;
+static constexpr int kEpiCodes[kNumEpiCodes] = {
+    epi_code(FFVC_ACT_GELU, FFVC_ACT_NONE, 1, 1, 0),        // channel-mix Linear 1: + bias, GELU, pre-activation saved
+    epi_code(FFVC_ACT_GELU, FFVC_ACT_NONE, 2, 1, 0),        // token-mix Conv1d 1: + row bias, GELU, pre-activation saved
+    epi_code(FFVC_ACT_NONE, FFVC_ACT_GELU, 0, 0, 0),        // dgrad through GELU: x gelu'(pre-activation)
+    epi_code(FFVC_ACT_QUICKGELU, FFVC_ACT_NONE, 1, 1, 0),   // CLIP c_fc: + bias, QuickGELU, pre-activation saved
+    epi_code(FFVC_ACT_NONE, FFVC_ACT_QUICKGELU, 0, 0, 0),   // CLIP dgrad through QuickGELU
+};
+
+template <bool kTwoCta, int kEpiWarps, int kEpi>
+static cudaError_t launch_one(const cudaLaunchConfig_t& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p) {
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<kTwoCta, kEpiWarps, kEpi>, ta, tb, p);
+}
+template <bool kTwoCta>
+static cudaError_t launch_wide(const cudaLaunchConfig_t& cfg, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p) {
+  if (epi == kEpiCodes[0]) return launch_one<kTwoCta, 16, kEpiCodes[0]>(cfg, ta, tb, p);
+  if (epi == kEpiCodes[1]) return launch_one<kTwoCta, 16, kEpiCodes[1]>(cfg, ta, tb, p);
+  if (epi == kEpiCodes[2]) return launch_one<kTwoCta, 16, kEpiCodes[2]>(cfg, ta, tb, p);
+  if (epi == kEpiCodes[3]) return launch_one<kTwoCta, 16, kEpiCodes[3]>(cfg, ta, tb, p);
+  if (epi == kEpiCodes[4]) return launch_one<kTwoCta, 16, kEpiCodes[4]>(cfg, ta, tb, p);
+  return launch_one<kTwoCta, 16, -1>(cfg, ta, tb, p);
+}
+static cudaError_t launch_gemm(const cudaLaunchConfig_t& cfg, bool two_cta, bool wide_epi, int epi, const CUtensorMap& ta,
+                               const CUtensorMap& tb, const GemmDev& p) {
+  if (wide_epi) return two_cta ? launch_wide<true>(cfg, epi, ta, tb, p) : launch_wide<false>(cfg, epi, ta, tb, p);
+  return two_cta ? launch_one<true, 8, -1>(cfg, ta, tb, p) : launch_one<false, 8, -1>(cfg, ta, tb, p);
+}
+template <bool kTwoCta, int kEpiWarps, int kEpi>
+static cudaError_t set_attr_one() {
+  return cudaFuncSetAttribute(gemm_tcgen05_kernel<kTwoCta, kEpiWarps, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+}
+template <bool kTwoCta>
+static cudaError_t set_attr_all() {
+  cudaError_t e = set_attr_one<kTwoCta, 8, -1>();
+  if (e == cudaSuccess) e = set_attr_one<kTwoCta, 16, -1>();
+  if (e == cudaSuccess) e = set_attr_one<kTwoCta, 16, kEpiCodes[0]>();
+  if (e == cudaSuccess) e = set_attr_one<kTwoCta, 16, kEpiCodes[1]>();
+  if (e == cudaSuccess) e = set_attr_one<kTwoCta, 16, kEpiCodes[2]>();
+  if (e == cudaSuccess) e = set_attr_one<kTwoCta, 16, kEpiCodes[3]>();
+  if (e == cudaSuccess) e = set_attr_one<kTwoCta, 16, kEpiCodes[4]>();
+  return e;
+}
+static int set_gemm_attrs() {
+  cudaError_t e = set_attr_all<false>();
+  if (e == cudaSuccess) e = set_attr_all<true>();
+  if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+  return FFVC_OK;
+}
+
 }  // namespace ffvc
 
 using namespace ffvc;
 
 extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-  if (!g || !g->a || !g->b || !g->out) return set_error(FFVC_ERR_ARG, "gemm: null pointer");
+  if (!g || !g->a || !g->b || (!g->out && !g->argmin_out)) return set_error(FFVC_ERR_ARG, "gemm: null pointer");
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return set_error(FFVC_ERR_ARG, "gemm: non-positive dimension");
   const int batch = g->batch > 0 ? g->batch : 1;
   const int batch_inner = g->batch_inner > 0 ? g->batch_inner : 1;
@@ -418,14 +498,8 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     if (g_num_sms <= 0) return set_error(FFVC_ERR_CUDA, "gemm: no CUDA device");
   }
   if (!g_attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+    int rc_attr = set_gemm_attrs();
+    if (rc_attr) return rc_attr;
     g_attr_set = true;
   }
 
@@ -575,6 +649,8 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   p.act = g->act;
   p.mul_mode = g->aux ? g->mul_mode : 0;
   p.alpha = g->alpha == 0.0f ? 1.0f : g->alpha;
+  p.argmin = reinterpret_cast<unsigned long long*>(g->argmin_out);
+  if (p.argmin && (p.bias_mode == 2 || splits > 1)) return set_error(FFVC_ERR_ARG, "gemm: the arg-min epilogue takes a per-column bias only and no split-K");
 
   const long long tiles = (long long)((g->M + tile_m - 1) / tile_m) * ((g->N + block_n - 1) / block_n) * batch * splits;
   cudaError_t e;
@@ -582,30 +658,34 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   // those epilogues run at IPC ~0.4 and pace the whole kernel for short-K GEMMs
   const bool wide_epi = (p.act != FFVC_ACT_NONE || p.mul_mode != FFVC_ACT_NONE) && block_n >= 128 && g->epi_warps != 8;
   const int nthreads = wide_epi ? 64 + 32 * 16 : kNumThreads;
+  // compile-time epilogue for the hot activation epilogues (see Epi<> in gemm_common.cuh); everything else stays generic
+  int epi = -1;
+  if (wide_epi && !p.out_fp32 && !p.atomic && p.alpha == 1.0f && !p.argmin && g->epi_warps != 16) {
+    const int code = epi_code(p.act, p.mul_mode, p.bias_mode, p.pre_out != nullptr, p.res != nullptr);
+    for (int i = 0; i < kNumEpiCodes; ++i)
+      if (kEpiCodes[i] == code) epi = code;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(nthreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
   if (two_cta == 1) {
     // one CTA pair (cluster of 2) per tile, persistent over min(tiles, SMs/2) pairs
     const long long pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(2 * pairs));
-    cfg.blockDim = dim3(nthreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = wide_epi ? cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 16>, ta, tb, p)
-                 : cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 8>, ta, tb, p);
-    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   } else {
-    const int grid = (int)(tiles < g_num_sms ? tiles : g_num_sms);
-    if (wide_epi) gemm_tcgen05_kernel<false, 16><<<grid, nthreads, kSmemBytes, stream>>>(ta, tb, p);
-    else gemm_tcgen05_kernel<false, 8><<<grid, nthreads, kSmemBytes, stream>>>(ta, tb, p);
+    cfg.gridDim = dim3((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
   }
+  e = launch_gemm(cfg, two_cta == 1, wide_epi, epi, ta, tb, p);
+  if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   count_launch();

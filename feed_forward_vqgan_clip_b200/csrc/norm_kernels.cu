@@ -349,15 +349,17 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
   }
 }
 
-// backward pass 1: per (n,g) sums of g = dy*act'(u)*gamma and g*xhat  (double atomics into ws)
-__global__ void __launch_bounds__(256) groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                                  const __nv_bfloat16* __restrict__ x,
-                                                                  const float* __restrict__ mean,
-                                                                  const float* __restrict__ rstd,
-                                                                  const float* __restrict__ gamma,
-                                                                  const float* __restrict__ beta,
-                                                                  double* __restrict__ ws, int HW, int C, int G,
-                                                                  int pix_per_cta, int swish) {
+// backward pass 1: per (n,g) sums of g = dy*act'(u)*gamma and g*xhat  (double atomics into ws).
+// Four pixels per thread in flight (8 independent 16-byte loads) and folded per-channel coefficients
+// (xhat = v*R + M, u = xhat*gamma + beta) keep enough bytes in flight per SM to approach the HBM rate.
+__global__ void __launch_bounds__(256, 2) groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                     const __nv_bfloat16* __restrict__ x,
+                                                                     const float* __restrict__ mean,
+                                                                     const float* __restrict__ rstd,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta,
+                                                                     double* __restrict__ ws, int HW, int C, int G,
+                                                                     int pix_per_cta, int swish) {
   extern __shared__ float sm[];  // [2][G]
   const int n = blockIdx.y;
   const int cpg = C / G;
@@ -370,28 +372,42 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_stats_kernel(const __nv_bfl
   const int pl = threadIdx.x / vec_per_pix;
   const int pstride = blockDim.x / vec_per_pix;
   if (pstride > 0 && pl < pstride) {
-    float s[8], q[8], gm[8], bt[8], mu[8], rs[8];
+    float s[8], q[8], gm[8], bt[8], R[8], M[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = vc * 8 + j;
       s[j] = q[j] = 0.f;
       gm[j] = gamma[c];
       bt[j] = beta[c];
-      mu[j] = mean[n * G + c / cpg];
-      rs[j] = rstd[n * G + c / cpg];
+      R[j] = rstd[n * G + c / cpg];
+      M[j] = -mean[n * G + c / cpg] * R[j];
     }
-    const long long base = (long long)n * HW * C;
-    for (int p = p0 + pl; p < p1; p += pstride) {
-      float v[8], d[8];
-      unpack8(*reinterpret_cast<const uint4*>(x + base + (long long)p * C + vc * 8), v);
-      unpack8(*reinterpret_cast<const uint4*>(dy + base + (long long)p * C + vc * 8), d);
+    const long long base = (long long)n * HW * C + vc * 8;
+    for (int p = p0 + pl; p < p1; p += pstride * 4) {
+      uint4 xk[4], dk[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (v[j] - mu[j]) * rs[j];
-        const float u = xh * gm[j] + bt[j];
-        const float g = d[j] * (swish ? swish_grad_f(u) : 1.0f) * gm[j];
-        s[j] += g;
-        q[j] += g * xh;
+      for (int u = 0; u < 4; ++u) {
+        const int pp = p + u * pstride;
+        if (pp < p1) {
+          xk[u] = *reinterpret_cast<const uint4*>(x + base + (long long)pp * C);
+          dk[u] = *reinterpret_cast<const uint4*>(dy + base + (long long)pp * C);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p + u * pstride < p1) {
+          float v[8], d[8];
+          unpack8(xk[u], v);
+          unpack8(dk[u], d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = fmaf(v[j], R[j], M[j]);
+            const float uu = fmaf(xh, gm[j], bt[j]);
+            const float g = d[j] * (swish ? swish_grad_f(uu) : 1.0f) * gm[j];
+            s[j] += g;
+            q[j] = fmaf(g, xh, q[j]);
+          }
+        }
       }
     }
     gn_fold_to_smem(s, q, sm, G, cpg, vc, vec_per_pix);
@@ -403,17 +419,18 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_stats_kernel(const __nv_bfl
   }
 }
 
-// backward pass 2: dx = rstd * (g - S1/cnt - xhat * S2/cnt) (+ add); same thread mapping as the apply kernel
-__global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                                  const __nv_bfloat16* __restrict__ x,
-                                                                  const float* __restrict__ mean,
-                                                                  const float* __restrict__ rstd,
-                                                                  const float* __restrict__ gamma,
-                                                                  const float* __restrict__ beta,
-                                                                  const double* __restrict__ ws,
-                                                                  const __nv_bfloat16* __restrict__ add,
-                                                                  __nv_bfloat16* __restrict__ dx, int HW, int C, int G,
-                                                                  int pix_per_cta, float inv_count, int swish) {
+// backward pass 2: dx = rstd * (g - S1/cnt - xhat * S2/cnt) (+ add); same thread mapping as the apply kernel, two pixels per
+// thread in flight (up to 6 independent 16-byte loads)
+__global__ void __launch_bounds__(256, 2) groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                     const __nv_bfloat16* __restrict__ x,
+                                                                     const float* __restrict__ mean,
+                                                                     const float* __restrict__ rstd,
+                                                                     const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta,
+                                                                     const double* __restrict__ ws,
+                                                                     const __nv_bfloat16* __restrict__ add,
+                                                                     __nv_bfloat16* __restrict__ dx, int HW, int C, int G,
+                                                                     int pix_per_cta, float inv_count, int swish) {
   const int n = blockIdx.y;
   const int cpg = C / G;
   const int vec_per_pix = C >> 3;
@@ -422,41 +439,56 @@ __global__ void __launch_bounds__(256) groupnorm_bwd_apply_kernel(const __nv_bfl
   const int pstride = blockDim.x / vec_per_pix;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  float mu[8], rs[8], gm[8], bt[8], s1[8], s2[8];
+  float R[8], M[8], gm[8], bt[8], c1[8], c2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = vc * 8 + j;
     const int g = n * G + c / cpg;
-    mu[j] = mean[g];
-    rs[j] = rstd[g];
+    R[j] = rstd[g];
+    M[j] = -mean[g] * R[j];
     gm[j] = gamma[c];
     bt[j] = beta[c];
-    s1[j] = (float)ws[2 * g] * inv_count;
-    s2[j] = (float)ws[2 * g + 1] * inv_count;
+    c1[j] = (float)ws[2 * g] * inv_count * R[j];        // rstd * S1 / cnt
+    c2[j] = (float)ws[2 * g + 1] * inv_count * R[j];    // rstd * S2 / cnt
   }
   const long long base = (long long)n * HW * C + vc * 8;
-  for (int p = p0 + pl; p < p1; p += pstride) {
-    const long long off = base + (long long)p * C;
-    float v[8], d[8], o[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + off), v);
-    unpack8(*reinterpret_cast<const uint4*>(dy + off), d);
+  for (int p = p0 + pl; p < p1; p += pstride * 2) {
+    uint4 xk[2], dk[2], ak[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float xh = (v[j] - mu[j]) * rs[j];
-      const float u = fmaf(xh, gm[j], bt[j]);
-      const float g = d[j] * (swish ? swish_grad_f(u) : 1.0f) * gm[j];
-      o[j] = rs[j] * (g - s1[j] - xh * s2[j]);
+    for (int u = 0; u < 2; ++u) {
+      const int pp = p + u * pstride;
+      if (pp < p1) {
+        const long long off = base + (long long)pp * C;
+        xk[u] = __ldcs(reinterpret_cast<const uint4*>(x + off));
+        dk[u] = __ldcs(reinterpret_cast<const uint4*>(dy + off));
+        if (add) ak[u] = __ldcs(reinterpret_cast<const uint4*>(add + off));
+      }
     }
-    if (add) {
-      float a[8];
-      unpack8(*reinterpret_cast<const uint4*>(add + off), a);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    for (int u = 0; u < 2; ++u) {
+      const int pp = p + u * pstride;
+      if (pp < p1) {
+        float v[8], d[8], o[8];
+        unpack8(xk[u], v);
+        unpack8(dk[u], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(v[j], R[j], M[j]);
+          const float uu = fmaf(xh, gm[j], bt[j]);
+          const float g = d[j] * (swish ? swish_grad_f(uu) : 1.0f) * gm[j];
+          o[j] = fmaf(g, R[j], -fmaf(xh, c2[j], c1[j]));
+        }
+        if (add) {
+          float a[8];
+          unpack8(ak[u], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        __stcs(reinterpret_cast<uint4*>(dx + base + (long long)pp * C), pack8(o));
+      }
     }
-    *reinterpret_cast<uint4*>(dx + off) = pack8(o);
   }
 }
-
 
 // ------------------------------------------------------------------------------------ GroupNorm, single-kernel forms
 // The two-kernel forms above read every tensor twice from HBM (statistics pass + apply pass).  The fused forms keep the

@@ -45,7 +45,7 @@ def gemm(a, b, out, M, N, K, *, a_mode=KMAJOR, b_mode=KMAJOR, a_ld=None, b_ld=No
          a_role=ROLE_BCAST, b_role=ROLE_BCAST, a_bs=0, b_bs=0, batch=1, k_segs=1, splits=1, block_n=0,
          conv=None, pre_out=None, aux=None, res=None, bias=None, ldc=None, out_bs=0, atomic=False,
          bias_mode=1, act=ACT_NONE, mul_mode=ACT_NONE, alpha=1.0, a_off=0, b_off=0, out_off=0, batch_inner=1,
-         a_bs_in=0, b_bs_in=0, out_bs_in=0, tile_m=0, two_cta=0, epi_warps=0):
+         a_bs_in=0, b_bs_in=0, out_bs_in=0, tile_m=0, two_cta=0, epi_warps=0, argmin_out=None):
     """out[b,m,n] (+)= epilogue(alpha * sum_k A[m,k] B[n,k]); see include/ffvc.h:ffvc_gemm.
     a_off / out_off: element offsets added to the base pointers."""
     p = GemmParams()
@@ -65,15 +65,16 @@ def gemm(a, b, out, M, N, K, *, a_mode=KMAJOR, b_mode=KMAJOR, a_ld=None, b_ld=No
     p.a_batch_stride_inner, p.b_batch_stride_inner, p.out_batch_stride_inner = a_bs_in, b_bs_in, out_bs_in
     if conv is not None:
         p.conv_n, p.conv_h, p.conv_w, p.conv_c = conv
-    p.out = out.data_ptr() + out_off * out.element_size()
+    p.out = None if out is None else out.data_ptr() + out_off * out.element_size()
+    p.argmin_out = None if argmin_out is None else argmin_out.data_ptr()
     p.pre_out = None if pre_out is None else pre_out.data_ptr()
     p.aux = None if aux is None else aux.data_ptr()
     p.res = None if res is None else res.data_ptr()
     p.bias = None if bias is None else bias.data_ptr()
     p.ldc = N if ldc is None else ldc
     p.out_batch_stride = out_bs
-    assert out.dtype in (F32, BF16)
-    p.out_fp32 = 1 if out.dtype == F32 else 0
+    assert out is None or out.dtype in (F32, BF16)
+    p.out_fp32 = 1 if (out is not None and out.dtype == F32) else 0
     p.atomic = 1 if atomic else 0
     p.bias_mode, p.act, p.mul_mode, p.alpha = bias_mode, act, mul_mode, alpha
     check(_lib.load().ffvc_gemm(C.byref(p), _stream()))

@@ -226,12 +226,13 @@ class DecoderEngine:
         ops.linear_dgrad(dy, self.pk[name + ".w"], dx, M, cout, cin, res=res)
         return dx
 
-    # GroupNorm: tensors with >= GN_FUSED_MIN elements per sample go through the single-kernel, L2-resident forms
-    # (statistics + apply of one sample back to back); the small ones keep the two-pass kernels
-    GN_FUSED_MIN = 512 * 1024
+    # GroupNorm: two-pass kernels (statistics, apply).  The single-kernel L2-resident forms (ffvc_groupnorm_fused_*) are
+    # selectable per tensor size through GN_FUSED_MIN (elements per sample); measured on B200 they lose to the two-pass
+    # kernels (one 512-thread CTA per SM keeps too few register-staged loads in flight), so they are off by default.
+    GN_FUSED_MIN = None
 
     def _gn_fused(self, HW, C):
-        return HW * C >= self.GN_FUSED_MIN and 512 % (C // 8) == 0
+        return self.GN_FUSED_MIN is not None and HW * C >= self.GN_FUSED_MIN and 512 % (C // 8) == 0
 
     def gn(self, x, name, N, HW, C, swish):
         mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
@@ -391,12 +392,27 @@ class DecoderEngine:
         return d
 
     # ---------------------------------------------------------------- VQ (clamp + nearest code), main.py:763,134-138
+    VQ_TENSOR_CORE = True    # False: the fp32 SIMT search (ffvc_vq_nearest)
+    csplit = None
+
     def quantize(self, z_tok, lo, hi):
         """z_tok: [P, C] fp32 token-major latent.  Returns (zq bf16 [P,C], idx int32 [P], z_clamped fp32)."""
         P, C = z_tok.shape
         idx = self._new(P, dtype=torch.int32)
         zq = self._new(P, C)
         zc = self._new(P, C, dtype=F32)
+        if self.VQ_TENSOR_CORE and C % 8 == 0:
+            # distance search as one tcgen05 GEMM over a bf16 hi/lo split (K = 3C) with an arg-min epilogue
+            if self.csplit is None:
+                ncodes = self.codebook.shape[0]
+                self.csplit = self._new(ncodes, 3 * C)
+                self.cnorm_tc = self._new(ncodes, dtype=F32)
+                call("vq_prepare_codebook", self.codebook, self.csplit, self.cnorm_tc, ncodes, C)
+            zsplit = self._new(P, 3 * C)
+            keys = self._new(P, dtype=torch.int64)
+            call("vq_nearest_tc", z_tok, self.codebook, self.csplit, self.cnorm_tc, zsplit, keys, idx, zq, None, zc, P, C,
+                 self.codebook.shape[0], float(lo), float(hi))
+            return zq, idx, zc
         call("vq_nearest", z_tok, self.codebook, self.codeT, self.cnorm, idx, zq, None, zc, P, C, self.codebook.shape[0],
              float(lo), float(hi))
         return zq, idx, zc

@@ -73,7 +73,8 @@ typedef struct {
   int block_n;             /* 0 = auto, else 32/64/128/256 */
   int tile_m;              /* 0 = auto, else 128/256 (256 needs block_n <= 128) */
   int two_cta;             /* 0 = auto, 1 = force the CTA-pair (cta_group::2) kernel, -1 = never */
-  int epi_warps;           /* 0 = auto (16 for activation epilogues), 8 = force the 8-warp epilogue */
+  int epi_warps;           /* 0 = auto (16 for activation epilogues, compile-time epilogue where one exists),
+                              8 = force the 8-warp epilogue, 16 = 16-warp epilogue with run-time flags only */
   /* CONV3X3 (A is NHWC [conv_n][conv_h][conv_w][conv_c], pad 1, stride 1; M = n*h*w; K = 9*c) */
   int conv_n, conv_h, conv_w, conv_c;
   /* epilogue */
@@ -91,6 +92,8 @@ typedef struct {
   int act;                 /* FFVC_ACT_* */
   int mul_mode;            /* FFVC_ACT_* whose derivative multiplies */
   float alpha;             /* 0 is treated as 1 */
+  void* argmin_out;        /* optional uint64 [batch][M]: instead of storing, keep per row the minimum of v = alpha*acc + bias over n
+                              as (order-preserving bits of v) << 32 | n  (atomicMin; caller presets 0xFF..); ties -> lowest n */
 } ffvc_gemm_params;
 
 int ffvc_gemm(const ffvc_gemm_params* p, void* stream);
@@ -164,6 +167,15 @@ int ffvc_sumsq(const float* x, float* out, long long n, void* stream);
  * codeT = codebook transposed [C][ncodes]; cnorm = |code|^2.  zc (optional) = clamped z. */
 int ffvc_vq_nearest(const float* z, const float* codebook, const float* codeT, const float* cnorm, int* idx, void* zq_bf16,
                     float* zq_f32, float* zc, long long P, int C, int ncodes, float lo, float hi, void* stream);
+/* Same result on the tensor cores: the distance search d(p, c) = |c|^2 - 2 z_p.c runs as ONE tcgen05 GEMM over a 3-way
+ * bf16 split of both operands (z = hi + lo, c = hi + lo; K = 3*C: hi.hi + hi.lo + lo.hi, fp32 accumulation: dot-product
+ * error ~1e-4, the same order as fp32 rounding of the reference's own |z|^2 + |c|^2 - 2 z.c) with a per-row arg-min epilogue.
+ *   ffvc_vq_prepare_codebook: once per (frozen) codebook: csplit [ncodes][3*C] bf16 = [hi | lo | hi], cnorm [ncodes] fp32.
+ *   ffvc_vq_nearest_tc: zsplit [P][3*C] bf16 and keys [P] uint64 are caller-provided scratch.                          */
+int ffvc_vq_prepare_codebook(const float* codebook, void* csplit_bf16, float* cnorm, int ncodes, int C, void* stream);
+int ffvc_vq_nearest_tc(const float* z, const float* codebook, const void* csplit_bf16, const float* cnorm, void* zsplit_bf16,
+                       void* keys_u64, int* idx, void* zq_bf16, float* zq_f32, float* zc, long long P, int C, int ncodes,
+                       float lo, float hi, void* stream);
 /* ClampWithGrad.backward (main.py:126-129). */
 int ffvc_clamp_bwd(const float* g, const float* x, float* gx, long long n, float lo, float hi, void* stream);
 /* xr = clamp_with_grad((d + 1) / 2, 0, 1) and its backward (main.py:142). */

@@ -153,7 +153,7 @@ def test_gelu_epilogue_matches_exact_erf_gelu():
     out = torch.empty(M, N, device=DEV, dtype=torch.float32)
     ops.gemm(a, b, out, M, N, K, act=ops.ACT_GELU)
     ref = F.gelu(a.float() @ b.float().t())                 # exact (erf) GELU, nn.GELU() default
-    assert (out - ref).abs().max().item() < 5e-5
+    assert (out - ref).abs().max().item() < 1e-4     # packed-polynomial CDF: |gelu error| <= 5.6e-5 (ptx.cuh: gelu_phi2)
     aux = _rand(M, N, seed=31)
     out2 = torch.empty(M, N, device=DEV, dtype=torch.float32)
     ops.gemm(a, b, out2, M, N, K, aux=aux, mul_mode=ops.ACT_GELU)
@@ -291,3 +291,26 @@ def test_conv3x3_halo_three_channel_fp32_out():
     call("conv3x3_halo", x, wp, out, n, h, w, cin, cout, cout, bias, None, None, 0, 0, 1)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
     _check(out, ref, 2e-2)
+
+
+@pytest.mark.parametrize("M,N,K,two", [(300, 520, 192, -1), (1024, 2048, 128, 1), (257, 16384, 64, 0)])
+def test_argmin_epilogue(M, N, K, two):
+    """per-row arg-min of alpha * A.B^T + bias[n] without storing the product (the VQ distance search); ties -> lowest n"""
+    a, b = _rand(M, K, seed=91), _rand(N, K, seed=92)
+    bias = torch.randn(N, device=DEV)
+    keys = torch.full((M,), -1, device=DEV, dtype=torch.int64)          # 0xFF.. = +inf key
+    ops.gemm(a, b, None, M, N, K, bias=bias, alpha=-2.0, argmin_out=keys, two_cta=two)
+    v = -2.0 * (a.float() @ b.float().t()) + bias
+    idx = (keys & 0xFFFFFFFF).long()
+    ref = v.argmin(-1)
+    picked, best = v.gather(1, idx[:, None])[:, 0], v.min(-1).values
+    assert (idx == ref).float().mean().item() > 0.99
+    assert (picked - best).abs().max().item() < 1e-2 * max(1.0, best.abs().max().item())   # any disagreement is a near tie
+    # a duplicated column must lose to its first occurrence
+    b2 = b.clone()
+    b2[N - 1] = b2[3]
+    bias2 = bias.clone()
+    bias2[N - 1] = bias2[3]
+    keys.fill_(-1)
+    ops.gemm(a, b2, None, M, N, K, bias=bias2, alpha=-2.0, argmin_out=keys, two_cta=two)
+    assert int(((keys & 0xFFFFFFFF) == N - 1).sum()) == 0

@@ -210,12 +210,14 @@ def test_synth_vs_oracle_with_straight_through():
 
 
 # ----------------------------------------------------------------------------------------------------- CLIP ViT
-@pytest.mark.parametrize("act", ["quick_gelu", "gelu"])
-def test_clip_encode_image_forward_backward_vs_oracle(act):
+@pytest.mark.parametrize("act,fused_attn", [("quick_gelu", True), ("gelu", True), ("quick_gelu", False)])
+def test_clip_encode_image_forward_backward_vs_oracle(act, fused_attn):
+    """fused_attn: the per-(sequence, head) mma.sync attention kernel (default for T <= 64) vs the batched tcgen05 GEMM form"""
     sd = bf16_round_sd(oclip.init_clip_state_dict(SMALL_CLIP, seed=5))
     vis = VisualTransformer(act=act, **SMALL_CLIP)
     vis.load_state_dict(sd)
     vis = vis.to(DEV).eval().requires_grad_(False)
+    vis.engine().FUSED_ATTN = fused_attn
     g = torch.Generator().manual_seed(6)
     N = 4
     x = torch.randn(N, 3, 224, 224, generator=g).to(torch.bfloat16).float()

@@ -164,7 +164,7 @@ def test_bias_grads_and_casts():
     assert torch.equal(z, y.float())
 
 
-@pytest.mark.parametrize("C,ncodes,P", [(256, 16384, 512), (64, 512, 300)])
+@pytest.mark.parametrize("C,ncodes,P", [(256, 16384, 512), (64, 512, 300), (256, 16384, 4096)])
 def test_vq_nearest_matches_reference_argmin(C, ncodes, P):
     g = torch.Generator().manual_seed(0)
     cb = torch.randn(ncodes, C, generator=g).to(DEV)
@@ -191,6 +191,26 @@ def test_vq_nearest_matches_reference_argmin(C, ncodes, P):
         assert abs(d[r, idx[r]].item() - d[r, ref[r]].item()) < 1e-3
     assert torch.equal(zq32, cb[idx.long()])
     assert torch.equal(zq, cb[idx.long()].to(BF))
+    # ---- the tensor-core search (bf16 hi/lo split GEMM, K = 3C, arg-min epilogue) must pick the same codes
+    csplit = torch.empty(ncodes, 3 * C, device=DEV, dtype=BF)
+    cn2 = torch.empty(ncodes, device=DEV)
+    call("vq_prepare_codebook", cb, csplit, cn2, ncodes, C)
+    assert torch.allclose(cn2, cn, rtol=1e-5)
+    hi_ = cb.to(BF)
+    assert torch.equal(csplit[:, :C], hi_) and torch.equal(csplit[:, 2 * C:], hi_)
+    assert torch.equal(csplit[:, C:2 * C], (cb - hi_.float()).to(BF))
+    zsplit = torch.empty(P, 3 * C, device=DEV, dtype=BF)
+    keys = torch.empty(P, device=DEV, dtype=torch.int64)
+    idx2 = torch.empty(P, device=DEV, dtype=torch.int32)
+    zq2, zq322, zc2 = torch.empty_like(zq), torch.empty_like(zq32), torch.empty_like(zc)
+    call("vq_nearest_tc", z, cb, csplit, cn2, zsplit, keys, idx2, zq2, zq322, zc2, P, C, ncodes, lo, hi)
+    assert torch.equal(zc2, zcl)
+    agree2 = (idx2.long() == ref).float().mean().item()
+    assert agree2 >= 0.999, agree2
+    for r in (idx2.long() != ref).nonzero().flatten().tolist():
+        assert abs(d[r, idx2[r]].item() - d[r, ref[r]].item()) < 2e-3
+    assert torch.equal(zq322, cb[idx2.long()])
+    assert torch.equal(zq2, cb[idx2.long()].to(BF))
 
 
 def test_clamp_bwd_truth_table():
@@ -251,8 +271,10 @@ def test_adam_matches_torch():
     assert torch.equal(shadow, p.to(BF))
 
 
-def test_mha_small_fwd_bwd():
-    N, T, Hh, dh = 6, 50, 12, 64
+@pytest.mark.parametrize("N,T,Hh", [(6, 50, 12), (3, 64, 2), (2, 17, 3), (5, 1, 1), (2, 33, 4)])
+def test_mha_small_fwd_bwd(N, T, Hh):
+    """tensor-core (mma.sync) attention for short sequences; every 16-row tile count and ragged tails"""
+    dh = 64
     W = Hh * dh
     qkv = rnd(N, T, 3 * W, seed=1, scale=0.7)
     out = torch.empty(N, T, W, device=DEV, dtype=BF)
