@@ -164,7 +164,7 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-__global__ void __launch_bounds__(512) colsum_vec_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
+__global__ void __launch_bounds__(512, 2) colsum_vec_kernel(const __nv_bfloat16* __restrict__ dy, float* __restrict__ db,
                                                          long long rows, int n, int cvw, int rows_per_cta) {
   extern __shared__ float cs[];                       // [lanes][cvw * 8] partials
   const int ncv = n >> 3;                             // column vectors in a row
@@ -688,7 +688,7 @@ extern "C" int ffvc_colsum(const void* dy, float* db, long long rows, int n, voi
     const int cvw = ncv < 32 ? ncv : 32;                           // column vectors per CTA slab
     const int lanes = 512 / cvw;                                   // >= 16 row lanes (needs >= 8 for the fold)
     const int slabs = (ncv + cvw - 1) / cvw;
-    long long chunks = sms / slabs > 0 ? sms / slabs : 1;          // row chunks so that slabs * chunks ~ SMs
+    long long chunks = 2 * sms / slabs > 0 ? 2 * sms / slabs : 1;  // row chunks so that slabs * chunks ~ 2 CTAs per SM
     const long long q = (long long)lanes * 8;                      // whole unrolled row batches per CTA
     long long rows_per_cta = ((rows + chunks - 1) / chunks + q - 1) / q * q;
     chunks = (rows + rows_per_cta - 1) / rows_per_cta;

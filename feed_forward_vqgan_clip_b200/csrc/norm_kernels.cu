@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
 // ------------------------------------------------------------------------------------ LayerNorm backward
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;  optional dx += add (residual path);
 // optional dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (fp32 atomics, one per column per CTA).
-template <int kMaxV>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+template <int kMaxV, bool kWgrad>
+__global__ void __launch_bounds__(256, kWgrad ? 2 : 3) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                const __nv_bfloat16* __restrict__ x,
                                                                const float* __restrict__ gamma,
                                                                const float* __restrict__ mean,
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int nvec = D >> 3;
-  const bool wgrad = dgamma != nullptr;
-  float accg[kMaxV][8], accb[kMaxV][8];
+  constexpr bool wgrad = kWgrad;
+  float accg[wgrad ? kMaxV : 1][8], accb[wgrad ? kMaxV : 1][8];
   if (wgrad) {
 #pragma unroll
     for (int i = 0; i < kMaxV; ++i)
@@ -124,8 +124,11 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
     const uint4* dr = reinterpret_cast<const uint4*>(dy + row * D);
     const float mu = mean[row], rs = rstd[row];
-    // the row stays packed (bf16) in registers between the two passes: 8 registers per 16 values instead of 16
-    uint4 xp[kMaxV], dp[kMaxV];
+    // the row stays packed (bf16) in registers between the two passes: 8 registers per 16 values instead of 16;
+    // the residual-path gradient is fetched with the same batch of loads (it is only needed after the reductions)
+    // (only in the no-wgrad form: the wgrad accumulators leave no registers for it)
+    uint4 xp[kMaxV], dp[kMaxV], ap[kWgrad ? 1 : kMaxV];
+    const uint4* ar = add ? reinterpret_cast<const uint4*>(add + row * D) : nullptr;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxV; ++i) {
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
       if (c < nvec) {
         xp[i] = xr[c];
         dp[i] = dr[c];
+        if (!kWgrad && ar) ap[kWgrad ? 0 : i] = ar[c];
       }
     }
 #pragma unroll
@@ -151,8 +155,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
           s1 += g;
           s2 += g * xh;
           if (wgrad) {
-            accg[i][j] += dv[j] * xh;
-            accb[i][j] += dv[j];
+            accg[wgrad ? i : 0][j] += dv[j] * xh;
+            accb[wgrad ? i : 0][j] += dv[j];
           }
         }
       }
@@ -160,7 +164,6 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
     s1 = warp_sum(s1) / D;
     s2 = warp_sum(s2) / D;
     uint4* ox = reinterpret_cast<uint4*>(dx + row * D);
-    const uint4* ar = add ? reinterpret_cast<const uint4*>(add + row * D) : nullptr;
 #pragma unroll
     for (int i = 0; i < kMaxV; ++i) {
       const int c = lane + 32 * i;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
         }
         if (ar) {
           float av[8];
-          unpack8(ar[c], av);
+          unpack8(kWgrad ? ar[c] : ap[kWgrad ? 0 : i], av);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += av[j];
         }
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
   }
   if (wgrad) {
 #pragma unroll
-    for (int i = 0; i < kMaxV; ++i) {
+    for (int i = 0; i < (wgrad ? kMaxV : 1); ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
 #pragma unroll
@@ -343,16 +346,19 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const __nv_bfloat1
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float u = fmaf(v[j], sc[j], sh[j]);
-      o[j] = swish ? swish_f(u) : u;
+      o[j] = swish ? swish_fast_f(u) : u;
     }
     *reinterpret_cast<uint4*>(y + base + (long long)p * C) = pack8(o);
   }
 }
 
 // backward pass 1: per (n,g) sums of g = dy*act'(u)*gamma and g*xhat  (double atomics into ws).
-// Four pixels per thread in flight (8 independent 16-byte loads) and folded per-channel coefficients
-// (xhat = v*R + M, u = xhat*gamma + beta) keep enough bytes in flight per SM to approach the HBM rate.
-__global__ void __launch_bounds__(256, 2) groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy,
+// Register diet -> occupancy: the statistics of a thread's 8 channels belong to only GPV = max(1, 8 / cpg) distinct groups,
+// so the per-group coefficients (xhat = v*R + M) are held per group, not per channel (template on GPV); with two pixels per
+// thread in flight the kernels fit 64 registers -> 4 CTAs (32 warps) per SM, which is what keeps HBM busy here: measured,
+// many light warps beat few warps with deep unrolling on this part.
+template <int GPV>
+__global__ void __launch_bounds__(256, 4) groupnorm_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                      const __nv_bfloat16* __restrict__ x,
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd,
@@ -361,6 +367,7 @@ __global__ void __launch_bounds__(256, 2) groupnorm_bwd_stats_kernel(const __nv_
                                                                      double* __restrict__ ws, int HW, int C, int G,
                                                                      int pix_per_cta, int swish) {
   extern __shared__ float sm[];  // [2][G]
+  constexpr int CPV = 8 / GPV;   // channels of the vector that share a group
   const int n = blockIdx.y;
   const int cpg = C / G;
   const int vec_per_pix = C >> 3;
@@ -372,21 +379,24 @@ __global__ void __launch_bounds__(256, 2) groupnorm_bwd_stats_kernel(const __nv_
   const int pl = threadIdx.x / vec_per_pix;
   const int pstride = blockDim.x / vec_per_pix;
   if (pstride > 0 && pl < pstride) {
-    float s[8], q[8], gm[8], bt[8], R[8], M[8];
+    float s[8], q[8], gm[8], bt[8], R[GPV], M[GPV];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = vc * 8 + j;
       s[j] = q[j] = 0.f;
-      gm[j] = gamma[c];
-      bt[j] = beta[c];
-      R[j] = rstd[n * G + c / cpg];
-      M[j] = -mean[n * G + c / cpg] * R[j];
+      gm[j] = gamma[vc * 8 + j];
+      bt[j] = beta[vc * 8 + j];
+    }
+#pragma unroll
+    for (int k = 0; k < GPV; ++k) {
+      const int g = n * G + (vc * 8 + k * CPV) / cpg;
+      R[k] = rstd[g];
+      M[k] = -mean[g] * R[k];
     }
     const long long base = (long long)n * HW * C + vc * 8;
-    for (int p = p0 + pl; p < p1; p += pstride * 4) {
-      uint4 xk[4], dk[4];
+    for (int p = p0 + pl; p < p1; p += pstride * 2) {
+      uint4 xk[2], dk[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int pp = p + u * pstride;
         if (pp < p1) {
           xk[u] = *reinterpret_cast<const uint4*>(x + base + (long long)pp * C);
@@ -394,16 +404,16 @@ __global__ void __launch_bounds__(256, 2) groupnorm_bwd_stats_kernel(const __nv_
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         if (p + u * pstride < p1) {
           float v[8], d[8];
           unpack8(xk[u], v);
           unpack8(dk[u], d);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float xh = fmaf(v[j], R[j], M[j]);
+            const float xh = fmaf(v[j], R[j / CPV], M[j / CPV]);
             const float uu = fmaf(xh, gm[j], bt[j]);
-            const float g = d[j] * (swish ? swish_grad_f(uu) : 1.0f) * gm[j];
+            const float g = d[j] * (swish ? swish_grad_fast_f(uu) : 1.0f) * gm[j];
             s[j] += g;
             q[j] = fmaf(g, xh, q[j]);
           }
@@ -419,9 +429,9 @@ __global__ void __launch_bounds__(256, 2) groupnorm_bwd_stats_kernel(const __nv_
   }
 }
 
-// backward pass 2: dx = rstd * (g - S1/cnt - xhat * S2/cnt) (+ add); same thread mapping as the apply kernel, two pixels per
-// thread in flight (up to 6 independent 16-byte loads)
-__global__ void __launch_bounds__(256, 2) groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
+// backward pass 2: dx = rstd * (g - S1/cnt - xhat * S2/cnt) (+ add); same thread mapping as the apply kernel
+template <int GPV>
+__global__ void __launch_bounds__(256, 4) groupnorm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy,
                                                                      const __nv_bfloat16* __restrict__ x,
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd,
@@ -431,6 +441,7 @@ __global__ void __launch_bounds__(256, 2) groupnorm_bwd_apply_kernel(const __nv_
                                                                      const __nv_bfloat16* __restrict__ add,
                                                                      __nv_bfloat16* __restrict__ dx, int HW, int C, int G,
                                                                      int pix_per_cta, float inv_count, int swish) {
+  constexpr int CPV = 8 / GPV;
   const int n = blockIdx.y;
   const int cpg = C / G;
   const int vec_per_pix = C >> 3;
@@ -439,54 +450,39 @@ __global__ void __launch_bounds__(256, 2) groupnorm_bwd_apply_kernel(const __nv_
   const int pstride = blockDim.x / vec_per_pix;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  float R[8], M[8], gm[8], bt[8], c1[8], c2[8];
+  float R[GPV], M[GPV], c1[GPV], c2[GPV], gm[8], bt[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = vc * 8 + j;
-    const int g = n * G + c / cpg;
-    R[j] = rstd[g];
-    M[j] = -mean[g] * R[j];
-    gm[j] = gamma[c];
-    bt[j] = beta[c];
-    c1[j] = (float)ws[2 * g] * inv_count * R[j];        // rstd * S1 / cnt
-    c2[j] = (float)ws[2 * g + 1] * inv_count * R[j];    // rstd * S2 / cnt
+    gm[j] = gamma[vc * 8 + j];
+    bt[j] = beta[vc * 8 + j];
+  }
+#pragma unroll
+  for (int k = 0; k < GPV; ++k) {
+    const int g = n * G + (vc * 8 + k * CPV) / cpg;
+    R[k] = rstd[g];
+    M[k] = -mean[g] * R[k];
+    c1[k] = (float)ws[2 * g] * inv_count * R[k];        // rstd * S1 / cnt
+    c2[k] = (float)ws[2 * g + 1] * inv_count * R[k];    // rstd * S2 / cnt
   }
   const long long base = (long long)n * HW * C + vc * 8;
-  for (int p = p0 + pl; p < p1; p += pstride * 2) {
-    uint4 xk[2], dk[2], ak[2];
+  for (int p = p0 + pl; p < p1; p += pstride) {
+    const long long off = base + (long long)p * C;
+    const uint4 xk = __ldcs(reinterpret_cast<const uint4*>(x + off));
+    const uint4 dk = __ldcs(reinterpret_cast<const uint4*>(dy + off));
+    uint4 ak = make_uint4(0u, 0u, 0u, 0u);
+    if (add) ak = __ldcs(reinterpret_cast<const uint4*>(add + off));
+    float v[8], d[8], o[8], a[8];
+    unpack8(xk, v);
+    unpack8(dk, d);
+    unpack8(ak, a);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int pp = p + u * pstride;
-      if (pp < p1) {
-        const long long off = base + (long long)pp * C;
-        xk[u] = __ldcs(reinterpret_cast<const uint4*>(x + off));
-        dk[u] = __ldcs(reinterpret_cast<const uint4*>(dy + off));
-        if (add) ak[u] = __ldcs(reinterpret_cast<const uint4*>(add + off));
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float xh = fmaf(v[j], R[j / CPV], M[j / CPV]);
+      const float uu = fmaf(xh, gm[j], bt[j]);
+      const float g = d[j] * (swish ? swish_grad_fast_f(uu) : 1.0f) * gm[j];
+      o[j] = fmaf(g, R[j / CPV], a[j] - fmaf(xh, c2[j / CPV], c1[j / CPV]));
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int pp = p + u * pstride;
-      if (pp < p1) {
-        float v[8], d[8], o[8];
-        unpack8(xk[u], v);
-        unpack8(dk[u], d);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = fmaf(v[j], R[j], M[j]);
-          const float uu = fmaf(xh, gm[j], bt[j]);
-          const float g = d[j] * (swish ? swish_grad_f(uu) : 1.0f) * gm[j];
-          o[j] = fmaf(g, R[j], -fmaf(xh, c2[j], c1[j]));
-        }
-        if (add) {
-          float a[8];
-          unpack8(ak[u], a);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += a[j];
-        }
-        __stcs(reinterpret_cast<uint4*>(dx + base + (long long)pp * C), pack8(o));
-      }
-    }
+    __stcs(reinterpret_cast<uint4*>(dx + off), pack8(o));
   }
 }
 
@@ -602,7 +598,7 @@ groupnorm_fused_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float t = fmaf(v[j], sc[j], sh[j]);
-            o[j] = swish ? swish_f(t) : t;
+            o[j] = swish ? swish_fast_f(t) : t;
           }
           st_stream(y + base + (long long)pp * C, pack8(o));
         }
@@ -663,7 +659,7 @@ groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bflo
     for (int j = 0; j < 8; ++j) {
       xh[j] = (v[j] - mu[j]) * rs[j];
       const float u = fmaf(xh[j], gm[j], bt[j]);
-      g[j] = d[j] * (swish ? swish_grad_f(u) : 1.0f) * gm[j];
+      g[j] = d[j] * (swish ? swish_grad_fast_f(u) : 1.0f) * gm[j];
     }
   };
   auto load_stats = [&](int n, float (&mu)[8], float (&rs)[8]) {
@@ -799,16 +795,20 @@ extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* ga
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int wpb = 8;
   long long want = (rows + wpb - 1) / wpb;
-  const unsigned grid = (unsigned)(want < 148 * 2 ? want : 148 * 2);
+  const int per_sm = dgamma ? 2 : 3;
+  const unsigned grid = (unsigned)(want < 148 * per_sm ? want : 148 * per_sm);
   const size_t smem = dgamma ? 2 * D * sizeof(float) : 0;
   auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto ab = reinterpret_cast<const __nv_bfloat16*>(add);
   auto dxb = reinterpret_cast<__nv_bfloat16*>(dx);
-  if (D <= 1024)
-    layernorm_bwd_kernel<4><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
-  else
-    layernorm_bwd_kernel<8><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
+  if (D <= 1024) {
+    if (dgamma) layernorm_bwd_kernel<4, true><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
+    else layernorm_bwd_kernel<4, false><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
+  } else {
+    if (dgamma) layernorm_bwd_kernel<8, true><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
+    else layernorm_bwd_kernel<8, false><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
+  }
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
@@ -856,6 +856,16 @@ extern "C" int ffvc_groupnorm_apply(const void* x, const float* mean, const floa
 }
 
 // dx = d/dx [ act(GN(x)) ] . dy  (+ add).  ws: N*G*2 doubles scratch.
+template <int GPV>
+static void gn_bwd_launch(dim3 grid, cudaStream_t st, const __nv_bfloat16* dyb, const __nv_bfloat16* xb, const float* mean,
+                          const float* rstd, const float* gamma, const float* beta, double* ws, const __nv_bfloat16* add,
+                          __nv_bfloat16* dx, int HW, int C, int G, int ppc, int swish) {
+  groupnorm_bwd_stats_kernel<GPV><<<grid, 256, 2 * G * sizeof(float), st>>>(dyb, xb, mean, rstd, gamma, beta, ws, HW, C, G, ppc, swish);
+  groupnorm_bwd_apply_kernel<GPV><<<grid, 256, 0, st>>>(dyb, xb, mean, rstd, gamma, beta, ws, add, dx, HW, C, G, ppc,
+                                                         1.0f / ((float)HW * (C / G)), swish);
+}
+
+// dx = d/dx [ act(GN(x)) ] . dy  (+ add).  ws: N*G*2 doubles scratch.
 extern "C" int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                                   const float* gamma, const float* beta, double* ws, const void* add, void* dx, int N,
                                   int HW, int C, int G, int swish, void* stream) {
@@ -863,19 +873,20 @@ extern "C" int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* me
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st);
-  const int pix_per_cta = gn_pix_per_cta(N, HW);
-  dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
+  int ppc = 1024;   // pixels per CTA: aim for >= 16 CTAs per SM worth of work (4 resident), at least 64 pixels each
+  while (ppc > 64 && (long long)N * ((HW + ppc - 1) / ppc) < 148 * 16) ppc >>= 1;
+  dim3 grid((HW + ppc - 1) / ppc, N);
   auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
-  groupnorm_bwd_stats_kernel<<<grid, 256, 2 * G * sizeof(float), st>>>(dyb, xb, mean, rstd, gamma, beta, ws, HW, C, G,
-                                                                      pix_per_cta, swish);
-  FFVC_CHECK_LAUNCH();
-  const int ppc2 = gn_pix_per_cta(N, HW);
-  dim3 g2((HW + ppc2 - 1) / ppc2, N);
-  groupnorm_bwd_apply_kernel<<<g2, 256, 0, st>>>(dyb, xb, mean, rstd, gamma, beta, ws,
-                                                 reinterpret_cast<const __nv_bfloat16*>(add),
-                                                 reinterpret_cast<__nv_bfloat16*>(dx), HW, C, G, ppc2,
-                                                 1.0f / ((float)HW * (C / G)), swish);
+  auto ab = reinterpret_cast<const __nv_bfloat16*>(add);
+  auto dxb = reinterpret_cast<__nv_bfloat16*>(dx);
+  const int cpg = C / G;
+  // groups covered by one 8-channel vector: 8 / cpg when cpg divides 8, else (cpg a multiple of 8) exactly one
+  if (cpg >= 8 && cpg % 8 == 0) gn_bwd_launch<1>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, HW, C, G, ppc, swish);
+  else if (cpg == 4) gn_bwd_launch<2>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, HW, C, G, ppc, swish);
+  else if (cpg == 2) gn_bwd_launch<4>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, HW, C, G, ppc, swish);
+  else if (cpg == 1) gn_bwd_launch<8>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, HW, C, G, ppc, swish);
+  else return set_error(FFVC_ERR_UNSUPPORTED, "groupnorm_bwd: channels per group must be 1, 2, 4 or a multiple of 8");
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

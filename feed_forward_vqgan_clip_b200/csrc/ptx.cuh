@@ -315,6 +315,20 @@ __device__ __forceinline__ float quick_gelu_grad_f(float x) {
   const float s = sigmoid_f(1.702f * x);
   return s + 1.702f * x * s * (1.0f - s);
 }
+// sigmoid through ONE MUFU op: sigma(x) = 0.5 + 0.5 tanh(x / 2) (tanh.approx.f32, relative error 2^-11 -> |sigma error| <= 2.5e-4).
+// Used by the GroupNorm + swish kernels, which are MUFU / issue bound with the two-op (EX2 + RCP) form; the error is 16x below
+// the bf16 rounding of the value that is stored.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast_f(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ float swish_fast_f(float x) { return x * sigmoid_fast_f(x); }
+__device__ __forceinline__ float swish_grad_fast_f(float x) {
+  const float s = sigmoid_fast_f(x);
+  return s * fmaf(x, 1.0f - s, 1.0f);
+}
 __device__ __forceinline__ float swish_f(float x) { return x * sigmoid_f(x); }
 __device__ __forceinline__ float swish_grad_f(float x) {
   const float s = sigmoid_f(x);

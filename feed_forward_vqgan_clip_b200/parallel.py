@@ -52,3 +52,21 @@ def allreduce_scalars(values, world, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         t /= world
     return t
+
+
+def install_horovod_shim():
+    """Make `import horovod.torch as hvd` (main.py:45) resolve to the torch.distributed-backed shim shipped in
+    feed_forward_vqgan_clip_b200/hvd_shim, unless a real Horovod is installed.  Returns the module."""
+    import importlib
+    import sys
+    try:
+        import horovod.torch as hvd                      # a real installation wins
+        return hvd
+    except Exception:
+        pass
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hvd_shim")
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    for k in [k for k in sys.modules if k == "horovod" or k.startswith("horovod.")]:
+        del sys.modules[k]
+    return importlib.import_module("horovod.torch")

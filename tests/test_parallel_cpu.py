@@ -59,3 +59,75 @@ def test_two_rank_gloo_data_parallel_logic():
     assert ok0 and ok1                          # broadcast restored rank 1's parameters
     assert s0 == s1 == [0.5, 2.0]
     assert sum0 == sum1                         # same seed -> identical replicas
+
+
+# ----------------------------------------------------------------------------------------------------- horovod.torch shim
+def _hvd_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    hvd = parallel.install_horovod_shim()
+    hvd.init("gloo")
+    assert (hvd.rank(), hvd.size(), hvd.local_rank()) == (rank, world, rank)
+    torch.manual_seed(rank)                                   # DIFFERENT initial weights per rank on purpose
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 4))
+    opt = torch.optim.Adam(net.parameters(), lr=1e-2)         # main.py:591
+    opt = hvd.DistributedOptimizer(opt)                       # main.py:627
+    hvd.broadcast_parameters(net.state_dict(), root_rank=0)   # main.py:628
+    hvd.broadcast_optimizer_state(opt, root_rank=0)           # main.py:629
+    w0 = torch.cat([p.detach().flatten() for p in net.parameters()]).clone()
+    x = torch.full((4, 8), float(rank + 1))                   # rank-dependent batch shard
+    loss = net(x).pow(2).mean()
+    opt.zero_grad()
+    loss.backward()
+    g_local = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+    opt.step()                                                # averages the gradients first
+    g_avg = torch.cat([p.grad.flatten() for p in net.parameters()]).clone()
+    w1 = torch.cat([p.detach().flatten() for p in net.parameters()]).clone()
+    noise = hvd.broadcast(torch.full((3,), float(rank)), root_rank=0)          # main.py:686
+    lsum = hvd.allreduce(torch.tensor(float(rank + 1)), average=False)         # main.py:367
+    lavg = hvd.allreduce(torch.tensor(float(rank + 1)))                        # main.py:839
+    # flat-arena fast path: parameters that are views of one buffer get a single all-reduce
+    arena = torch.zeros(24)
+    pa, pb = torch.nn.Parameter(arena[:16].view(4, 4)), torch.nn.Parameter(arena[16:24])
+    garena = torch.full((24,), float(rank + 1))
+    pa.grad, pb.grad = garena[:16].view(4, 4), garena[16:24]
+    o2 = hvd.DistributedOptimizer(torch.optim.SGD([pa, pb], lr=1.0))
+    o2.step()
+    hvd.join()
+    # plain lists: tensors on an mp queue are shared through file descriptors that die with this process
+    q.put((rank, w0.tolist(), g_local.tolist(), g_avg.tolist(), w1.tolist(), noise.tolist(), float(lsum), float(lavg), arena.tolist()))
+    hvd.shutdown()
+
+
+def test_horovod_shim_two_ranks_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_hvd_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    T = torch.tensor
+    (_, w0a, gla, gaa, w1a, na, sa, aa, ara), (_, w0b, glb, gab, w1b, nb, sb, ab, arb) = res
+    w0a, gla, gaa, w1a, ara, w0b, glb, gab, w1b, arb = (T(v) for v in (w0a, gla, gaa, w1a, ara, w0b, glb, gab, w1b, arb))
+    assert torch.equal(w0a, w0b)                                       # broadcast_parameters made the replicas identical
+    assert not torch.allclose(gla, glb)                                # the shards really differ
+    assert torch.allclose(gaa, (gla + glb) / 2, atol=1e-7) and torch.equal(gaa, gab)   # Horovod default: average
+    assert torch.equal(w1a, w1b)                                       # so the replicas stay identical after the step
+    assert na == nb == [0.0, 0.0, 0.0]
+    assert sa == sb == 3.0 and aa == ab == 1.5
+    assert torch.allclose(ara, torch.full((24,), -1.5)) and torch.equal(ara, arb)      # SGD lr=1 on the averaged arena gradient
+
+
+def test_horovod_shim_single_process_is_a_no_op():
+    hvd = parallel.install_horovod_shim()
+    assert hvd.size() == 1 and hvd.rank() == 0
+    t = torch.arange(4.0)
+    assert torch.equal(hvd.allreduce(t), t) and torch.equal(hvd.broadcast(t, 0), t)
+    opt = hvd.DistributedOptimizer(torch.optim.SGD([torch.nn.Parameter(torch.ones(2))], lr=0.1))
+    opt.step()
+    hvd.join()

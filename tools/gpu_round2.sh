@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU session 3: full test suite, step breakdown (GN pipeline on / off), bench.
+# GPU session 5: full test suite, step breakdown, bench.
 mkdir -p gpurun_out
 for f in test_gemm_gpu test_ops_gpu test_models_gpu; do
   timeout -k 10 400 python -m pytest tests/$f.py -q -m gpu -p no:cacheprovider --tb=short > gpurun_out/$f.full 2>&1; rc=$?
@@ -7,7 +7,6 @@ for f in test_gemm_gpu test_ops_gpu test_models_gpu; do
   echo "== $f (rc=$rc): $(tail -1 gpurun_out/$f.log)"
   if [ $rc -eq 124 ] || [ $rc -eq 137 ]; then echo "== $f TIMED OUT: aborting"; exit 1; fi
 done
-timeout -k 10 300 python tools/prof_step.py --out gpurun_out/step_breakdown_p1.md > gpurun_out/prof_step_p1.log 2>&1; echo "== prof_step p1 rc=$?"; head -42 gpurun_out/prof_step_p1.log | cut -c1-160
-timeout -k 10 300 python tools/prof_step.py --gn-pipeline 0 --out gpurun_out/step_breakdown_p0.md > gpurun_out/prof_step_p0.log 2>&1; echo "== prof_step p0 rc=$?"; grep -E "groupnorm|^# " gpurun_out/prof_step_p0.log | head -12 | cut -c1-160
+timeout -k 10 300 python tools/prof_step.py --out gpurun_out/step_breakdown_c7.md > gpurun_out/prof_step_c7.log 2>&1; echo "== prof_step rc=$?"; head -44 gpurun_out/prof_step_c5.log | cut -c1-160
 timeout -k 10 600 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "== smoke rc=$? $(tail -1 gpurun_out/smoke.log)"
 timeout -k 10 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "== bench rc=$?"; tail -c 2500 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
