@@ -37,6 +37,7 @@ struct GemmDev {
   int mul_mode;   // multiply by act'(aux): FFVC_ACT_*
   float alpha;
   unsigned long long* argmin;   // optional: per-row arg-min epilogue (see ffvc_gemm_params.argmin_out)
+  int tma_store;                // 1: the epilogue warps stage their results in shared memory and TMA-store them
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -302,5 +303,49 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
   }
 }
 
+
+// Compute-only form of the fused epilogue for the compile-time configurations (bf16 output, alpha = 1, full vector chunk):
+// returns the packed bf16 results (and the packed pre-activation when the configuration has one) instead of storing them —
+// the TMA-store epilogue stages them in shared memory.
+template <int CW, int kEpi>
+__device__ __forceinline__ void epilogue_chunk_pack(const GemmDev& p, const uint32_t (&r)[CW], float rbias, const float* sbias,
+                                                    const uint4 (&pf_aux)[CW / 8], const uint4 (&pf_res)[CW / 8],
+                                                    uint4 (&out_pk)[CW / 8], uint4 (&pre_pk)[CW / 8]) {
+  using E = Epi<kEpi>;
+  static_assert(kEpi >= 0, "compile-time epilogue configurations only");
+  float2 v[CW / 2];
+#pragma unroll
+  for (int i = 0; i < CW / 2; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+  if (E::bias(p) == 1) {
+#pragma unroll
+    for (int i = 0; i < CW / 4; ++i) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + 4 * i);
+      v[2 * i] = __fadd2_rn(v[2 * i], make_float2(b4.x, b4.y));
+      v[2 * i + 1] = __fadd2_rn(v[2 * i + 1], make_float2(b4.z, b4.w));
+    }
+  } else if (E::bias(p) == 2) {
+    const float2 rb = make_float2(rbias, rbias);
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i) v[i] = __fadd2_rn(v[i], rb);
+  }
+  if (E::pre(p)) {
+#pragma unroll
+    for (int i = 0; i < CW / 8; ++i) pre_pk[i] = pack_bf16x8_2(v + 4 * i);
+  }
+  act_chunk<CW>(v, E::act(p));
+  if (E::mul(p) != FFVC_ACT_NONE) {
+    float2 x[CW / 2];
+    unpack_bf16x2N<CW>(pf_aux, x);
+    mulgrad_chunk<CW>(v, x, E::mul(p));
+  }
+  if (E::res(p)) {
+    float2 x[CW / 2];
+    unpack_bf16x2N<CW>(pf_res, x);
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i) v[i] = __fadd2_rn(v[i], x[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < CW / 8; ++i) out_pk[i] = pack_bf16x8_2(v + 4 * i);
+}
 
 }  // namespace ffvc

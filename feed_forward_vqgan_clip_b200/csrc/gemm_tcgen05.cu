@@ -48,11 +48,16 @@ static constexpr int kTmemCols = 512;
 //   HALF of the B tile; the leader CTA issues tcgen05.mma M=256 that reads both CTAs' shared memory, so every SM
 //   reads / is written only (A + B/2) per k-step instead of (A + B): the 1-CTA kernel is shared-memory-bandwidth
 //   bound (128 B/clk/SM) at ~55-65 % of the tensor pipe, the pair removes a third of that traffic.  6-stage ring.
-template <bool kTwoCta, int kEpiWarps, int kEpi>
+template <bool kTwoCta, int kEpiWarps, int kEpi, bool kTma>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmDev p) {
-  constexpr int kStagesT = kTwoCta ? 6 : kStages;
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_pre, const GemmDev p) {
+  // TMA-store epilogue (kTma: compile-time epilogues on the CTA-pair kernel, short K): the ring shrinks to 4 stages and the
+  // freed 64 KB hold one [pre-activation | output] staging buffer (2 x 2 KB) per epilogue warp.  Measured: it pays for
+  // K <= 512 (the epilogue dominates and 4 stages cover the whole K loop); for K = 1024 the shallower ring costs more than the
+  // store offload returns, so the host only selects it for short K.
+  constexpr bool kCanTmaStore = kTma && kTwoCta && kEpiWarps == 16 && kEpi >= 0;
+  constexpr int kStagesT = kTwoCta ? (kCanTmaStore ? 4 : 6) : kStages;
   constexpr int kStageBytesT = kTwoCta ? 32 * 1024 : kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128B swizzle atoms.
@@ -270,6 +275,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                           ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.pre_out) |
                             reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.res)) & 31) == 0;
     const bool want_aux = E::mul(p) != FFVC_ACT_NONE, want_res = E::res(p);
+    // TMA-store path: this warp's staging buffers ([32 rows][32 columns] bf16 = 2 KB each, 64B-swizzled: 16-byte chunk j of
+    // row r lives at chunk j ^ ((r >> 1) & 3) — what the tensor map expects and conflict-free for one-row-per-lane writes)
+    const bool tma_store = kCanTmaStore && p.tma_store;
+    const uint32_t stg_pre = smem_base + 4u * 32u * 1024u + (uint32_t)(warp - 2) * 4096u;
+    const uint32_t stg_out = stg_pre + 2048u;
+    const uint32_t stg_row = (uint32_t)lane * 64u, stg_sw = (uint32_t)((lane >> 1) & 3);
+    bool stg_busy = false;     // a bulk store of this warp may still be reading the staging buffers
     for (long long t = tile_first; t < total_tiles; t += tile_step) {
       const int rem = (int)(t % tiles_all_batches);
       const int bi = rem / tiles_per_batch;
@@ -336,6 +348,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int j = 0; j < CW / 8; ++j) cur_res[j] = pf_res[j];
         }
         if ((want_aux || want_res) && c + CW < c_end) prefetch(c + CW);
+        if constexpr (kCanTmaStore) {
+          // (a 32-column group that sticks out of N takes the direct-store path below: its partial chunk needs element guards)
+          if (tma_store && n0 + c_begin + ((c - c_begin) & ~31) + 32 <= p.N) {
+            // registers -> swizzled shared memory -> one TMA store per 32-column group (rows / columns beyond M / N are
+            // clipped by the tensor map); no global store instruction is issued by the epilogue warps
+            uint4 o_pk[CW / 8], p_pk[CW / 8];
+            epilogue_chunk_pack<CW, kEpi>(p, r, rbias, sbias + c, cur_aux, cur_res, o_pk, p_pk);
+            const int half = ((c - c_begin) >> 4) & 1;                 // which half of the 32-column group
+            if (half == 0 && stg_busy) {
+              if (lane == 0) bulk_wait_read0();
+              __syncwarp();
+              stg_busy = false;
+            }
+            const uint32_t ch0 = ((uint32_t)(2 * half) ^ stg_sw) * 16u, ch1 = ((uint32_t)(2 * half + 1) ^ stg_sw) * 16u;
+            st_shared_v4(stg_out + stg_row + ch0, o_pk[0]);
+            st_shared_v4(stg_out + stg_row + ch1, o_pk[1]);
+            if (E::pre(p)) {
+              st_shared_v4(stg_pre + stg_row + ch0, p_pk[0]);
+              st_shared_v4(stg_pre + stg_row + ch1, p_pk[1]);
+            }
+            if (half == 1) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                const int col0 = n0 + c - 16, row0 = tm * p.tile_m + (int)rank * 128 + q * 32;
+                tma_store_4d(&tmap_out, stg_out, col0, row0, bi_in, bi_out);
+                if (E::pre(p)) tma_store_4d(&tmap_pre, stg_pre, col0, row0, bi_in, bi_out);
+                bulk_commit_group();
+              }
+              stg_busy = true;
+            }
+            __syncwarp();
+            continue;
+          }
+        }
         if (E::argmin(p)) {
           if (row_ok && gn0 < p.N) argmin_chunk<CW>(p, r, gn0, E::bias(p) == 1 ? sbias + c : nullptr, am_best, am_idx);
         } else if (row_ok && gn0 < p.N) {
@@ -359,6 +406,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         acc_phase ^= 1u;
       }
     }
+    if (kCanTmaStore && stg_busy && lane == 0) bulk_wait_all();   // the staging buffers must outlive the stores reading them
   }
 
   tc_fence_before();
@@ -387,7 +435,7 @@ static PFN_encodeTiled get_encode_fn() {
 
 // dims/strides in elements (bf16); rank 4; dim0 contiguous.
 static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                     const uint32_t* box) {
+                     const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return set_error(FFVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5];
@@ -405,7 +453,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
   }
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return set_error(FFVC_ERR_ARG, "gemm: operand not 16B aligned");
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
-                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -421,6 +469,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
 
 static int g_num_sms = 0;
 static bool g_attr_set = false;
+static int g_tma_store_enabled = 1;   // ffvc_gemm_set_tma_store(0) keeps the direct-store epilogue (A/B measurements, tests)
 
 
 // ---- kernel instantiations: generic epilogue x {1-CTA, CTA pair} x {8, 16 epilogue warps}, plus the compile-time epilogues
@@ -435,26 +484,34 @@ static constexpr int kEpiCodes[kNumEpiCodes] = {
 };
 
 template <bool kTwoCta, int kEpiWarps, int kEpi>
-static cudaError_t launch_one(const cudaLaunchConfig_t& cfg, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p) {
-  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<kTwoCta, kEpiWarps, kEpi>, ta, tb, p);
+static cudaError_t launch_one(const cudaLaunchConfig_t& cfg, const CUtensorMap* tm, const GemmDev& p) {
+  if constexpr (kTwoCta && kEpiWarps == 16 && kEpi >= 0) {
+    if (p.tma_store) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<kTwoCta, kEpiWarps, kEpi, true>, tm[0], tm[1], tm[2], tm[3], p);
+  }
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<kTwoCta, kEpiWarps, kEpi, false>, tm[0], tm[1], tm[2], tm[3], p);
 }
 template <bool kTwoCta>
-static cudaError_t launch_wide(const cudaLaunchConfig_t& cfg, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& p) {
-  if (epi == kEpiCodes[0]) return launch_one<kTwoCta, 16, kEpiCodes[0]>(cfg, ta, tb, p);
-  if (epi == kEpiCodes[1]) return launch_one<kTwoCta, 16, kEpiCodes[1]>(cfg, ta, tb, p);
-  if (epi == kEpiCodes[2]) return launch_one<kTwoCta, 16, kEpiCodes[2]>(cfg, ta, tb, p);
-  if (epi == kEpiCodes[3]) return launch_one<kTwoCta, 16, kEpiCodes[3]>(cfg, ta, tb, p);
-  if (epi == kEpiCodes[4]) return launch_one<kTwoCta, 16, kEpiCodes[4]>(cfg, ta, tb, p);
-  return launch_one<kTwoCta, 16, -1>(cfg, ta, tb, p);
+static cudaError_t launch_wide(const cudaLaunchConfig_t& cfg, int epi, const CUtensorMap* tm, const GemmDev& p) {
+  if (epi == kEpiCodes[0]) return launch_one<kTwoCta, 16, kEpiCodes[0]>(cfg, tm, p);
+  if (epi == kEpiCodes[1]) return launch_one<kTwoCta, 16, kEpiCodes[1]>(cfg, tm, p);
+  if (epi == kEpiCodes[2]) return launch_one<kTwoCta, 16, kEpiCodes[2]>(cfg, tm, p);
+  if (epi == kEpiCodes[3]) return launch_one<kTwoCta, 16, kEpiCodes[3]>(cfg, tm, p);
+  if (epi == kEpiCodes[4]) return launch_one<kTwoCta, 16, kEpiCodes[4]>(cfg, tm, p);
+  return launch_one<kTwoCta, 16, -1>(cfg, tm, p);
 }
-static cudaError_t launch_gemm(const cudaLaunchConfig_t& cfg, bool two_cta, bool wide_epi, int epi, const CUtensorMap& ta,
-                               const CUtensorMap& tb, const GemmDev& p) {
-  if (wide_epi) return two_cta ? launch_wide<true>(cfg, epi, ta, tb, p) : launch_wide<false>(cfg, epi, ta, tb, p);
-  return two_cta ? launch_one<true, 8, -1>(cfg, ta, tb, p) : launch_one<false, 8, -1>(cfg, ta, tb, p);
+static cudaError_t launch_gemm(const cudaLaunchConfig_t& cfg, bool two_cta, bool wide_epi, int epi, const CUtensorMap* tm,
+                               const GemmDev& p) {
+  if (wide_epi) return two_cta ? launch_wide<true>(cfg, epi, tm, p) : launch_wide<false>(cfg, epi, tm, p);
+  return two_cta ? launch_one<true, 8, -1>(cfg, tm, p) : launch_one<false, 8, -1>(cfg, tm, p);
 }
 template <bool kTwoCta, int kEpiWarps, int kEpi>
 static cudaError_t set_attr_one() {
-  return cudaFuncSetAttribute(gemm_tcgen05_kernel<kTwoCta, kEpiWarps, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<kTwoCta, kEpiWarps, kEpi, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if constexpr (kTwoCta && kEpiWarps == 16 && kEpi >= 0) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tcgen05_kernel<kTwoCta, kEpiWarps, kEpi, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  }
+  return e;
 }
 template <bool kTwoCta>
 static cudaError_t set_attr_all() {
@@ -477,6 +534,11 @@ static int set_gemm_attrs() {
 }  // namespace ffvc
 
 using namespace ffvc;
+
+extern "C" int ffvc_gemm_set_tma_store(int on) {
+  g_tma_store_enabled = on < 0 ? 0 : (on > 2 ? 2 : on);
+  return FFVC_OK;
+}
 
 extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
@@ -684,7 +746,25 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   } else {
     cfg.gridDim = dim3((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
   }
-  e = launch_gemm(cfg, two_cta == 1, wide_epi, epi, ta, tb, p);
+  // TMA-store epilogue: compile-time epilogue on the pair kernel, bf16 output(s) whose rows / batches start on 16-byte boundaries
+  CUtensorMap tms[4];
+  tms[0] = ta;
+  tms[1] = tb;
+  tms[2] = ta;   // placeholders when the direct-store epilogue runs
+  tms[3] = ta;
+  p.tma_store = 0;
+  const int total_kb_host = p.kb_per_seg * k_segs;
+  if (epi >= 0 && two_cta == 1 && g_tma_store_enabled && (total_kb_host <= 8 || g_tma_store_enabled == 2) && p.ldc % 8 == 0 && p.out_bs % 8 == 0 && p.out_bs_inner % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.pre_out) & 15) == 0) {
+    uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->M, (uint64_t)batch_inner, (uint64_t)batch_outer};
+    uint64_t str[4] = {1, (uint64_t)p.ldc, batch_inner > 1 ? (uint64_t)p.out_bs_inner : (uint64_t)p.ldc * 8,
+                       batch_outer > 1 ? (uint64_t)p.out_bs : (uint64_t)p.ldc * 8};
+    uint32_t box[4] = {32, 32, 1, 1};
+    if ((rc = make_tmap(&tms[2], p.out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) != FFVC_OK) return rc;
+    if (p.pre_out && (rc = make_tmap(&tms[3], p.pre_out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B)) != FFVC_OK) return rc;
+    p.tma_store = 1;
+  }
+  e = launch_gemm(cfg, two_cta == 1, wide_epi, epi, tms, p);
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));

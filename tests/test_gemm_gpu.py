@@ -314,3 +314,53 @@ def test_argmin_epilogue(M, N, K, two):
     keys.fill_(-1)
     ops.gemm(a, b2, None, M, N, K, bias=bias2, alpha=-2.0, argmin_out=keys, two_cta=two)
     assert int(((keys & 0xFFFFFFFF) == N - 1).sum()) == 0
+
+
+@pytest.mark.parametrize("cfg", ["gelu_bias_pre", "gelu_rowbias_pre", "mul_gelu", "qgelu_bias_pre", "mul_qgelu"])
+@pytest.mark.parametrize("M,N,K,batch", [(512, 512, 128, 1), (300, 520, 64, 1), (256, 1024, 256, 3), (1000, 264, 192, 2)])
+def test_tma_store_epilogue_matches_direct_stores(cfg, M, N, K, batch):
+    """the compile-time epilogues of the CTA-pair kernel write through shared memory + TMA stores (ragged M / N are clipped by
+    the tensor map, batches are map dimensions): bit-identical to the direct-store epilogue and right against torch"""
+    from feed_forward_vqgan_clip_b200 import _lib
+    lib = _lib.load()
+    a = _rand(batch, M, K, seed=101)
+    b = _rand(N, K, seed=102)
+    aux = _rand(batch, M, N, seed=103)
+    bias_c, bias_r = torch.randn(N, device=DEV), torch.randn(M, device=DEV)
+    kw = dict(two_cta=1, a_role=ops.ROLE_OUT, a_bs=M * K, batch=batch, out_bs=M * N)
+    outs = []
+    for tma in (2, 0):
+        lib.ffvc_gemm_set_tma_store(tma)
+        out = torch.full((batch, M, N), 7.0, device=DEV, dtype=torch.bfloat16)
+        pre = torch.full((batch, M, N), 7.0, device=DEV, dtype=torch.bfloat16)
+        if cfg == "gelu_bias_pre":
+            ops.gemm(a, b, out, M, N, K, bias=bias_c, act=ops.ACT_GELU, pre_out=pre, **kw)
+        elif cfg == "gelu_rowbias_pre":
+            ops.gemm(a, b, out, M, N, K, bias=bias_r, bias_mode=2, act=ops.ACT_GELU, pre_out=pre, **kw)
+        elif cfg == "mul_gelu":
+            ops.gemm(a, b, out, M, N, K, aux=aux, mul_mode=ops.ACT_GELU, **kw)
+        elif cfg == "qgelu_bias_pre":
+            ops.gemm(a, b, out, M, N, K, bias=bias_c, act=ops.ACT_QUICKGELU, pre_out=pre, **kw)
+        else:
+            ops.gemm(a, b, out, M, N, K, aux=aux, mul_mode=ops.ACT_QUICKGELU, **kw)
+        outs.append((out, pre))
+    lib.ffvc_gemm_set_tma_store(1)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    acc = torch.einsum("bmk,nk->bmn", a.float(), b.float())
+    x = aux.float()
+    if cfg == "gelu_bias_pre":
+        _check(outs[0][1], acc + bias_c, 2e-2)
+        _check(outs[0][0], F.gelu(acc + bias_c), 2e-2)
+    elif cfg == "gelu_rowbias_pre":
+        _check(outs[0][1], acc + bias_r[None, :, None], 2e-2)
+        _check(outs[0][0], F.gelu(acc + bias_r[None, :, None]), 2e-2)
+    elif cfg == "mul_gelu":
+        gp = 0.5 * (1 + torch.erf(x / 2 ** 0.5)) + x * torch.exp(-0.5 * x * x) / (2 * 3.141592653589793) ** 0.5
+        _check(outs[0][0], acc * gp, 2e-2)
+    elif cfg == "qgelu_bias_pre":
+        u = acc + bias_c
+        _check(outs[0][1], u, 2e-2)
+        _check(outs[0][0], u * torch.sigmoid(1.702 * u), 2e-2)
+    else:
+        sg = torch.sigmoid(1.702 * x)
+        _check(outs[0][0], acc * (sg + 1.702 * x * sg * (1 - sg)), 2e-2)
