@@ -157,6 +157,8 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--bucket-layers", type=int, default=None,
+                    help="N>1: mixer layers per gradient all-reduce bucket (overlapped with backward); 0 = one all-reduce after backward")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,6 +166,8 @@ def main():
     config = {"workload": "config#2: MLP-Mixer 32x1024 -> VQGAN f16/16384 decode -> 8 cutouts -> CLIP ViT-B/32, 256x256",
               "per_gpu_batch": args.batch, "global_batch": args.batch * world, "cutn": CUTN,
               "parallelism": "dp%d" % world, "l2": "inputs larger than L2 (tens of GB of activations per step)"}
+    if world > 1:
+        config["grad_allreduce"] = "flat fp32 arena, buckets of mixer layers overlapped with backward on a side stream (NCCL)"
 
     if args.impl == "reference":
         if rank != 0:
@@ -190,6 +194,8 @@ def main():
 
     B = args.batch
     ts = build_b200(dev, B, world, pg)
+    if args.bucket_layers is not None:
+        ts.bucket_layers = args.bucket_layers
     x_host = [synthetic_embeddings(B, 1000 + 7919 * rank + i).pin_memory() for i in range(4)]
 
     ops.reset_launch_count()

@@ -217,8 +217,14 @@ class MixerEngine:
         return z, sv
 
     # ------------------------------------------------------------------ backward (dgrad + wgrad, into self.grad)
-    def backward(self, sv, dz):
-        """dz: (B*T, C) fp32.  Accumulates every parameter gradient into the flat fp32 arena `self.grad`."""
+    def layer_starts(self):
+        """arena offset of the first parameter of every mixer layer (mixer.2 .. mixer.L+1), ascending"""
+        return [min(off for n, off in self.offs.items() if n.startswith("mixer.%d." % i)) for i in range(2, self.L + 2)]
+
+    def backward(self, sv, dz, on_layer_done=None):
+        """dz: (B*T, C) fp32.  Accumulates every parameter gradient into the flat fp32 arena `self.grad`.
+        on_layer_done(k): called right after the gradients of mixer layer k (0-based, last layer first) — and of everything
+        registered after it — are complete: the data-parallel step uses it to start bucketed all-reduces during backward."""
         B, T, C, D, L, IN = sv["B"], self.T, self.C, self.D, self.L, self.IN
         dev = self.dev
         R = B * T
@@ -274,6 +280,8 @@ class MixerEngine:
             call("layernorm_bwd", dn1, lv["Ha"], self.wf(p + "0.norm.weight"), lv["mu1"], lv["rs1"], dHb, dHa,
                  self.g(p + "0.norm.weight"), self.g(p + "0.norm.bias"), R, D)
             dH = dHa
+            if on_layer_done is not None:
+                on_layer_done(i - 2)
         # mixer.1 (Linear C -> D)
         ops.linear_wgrad(dH, sv["tok"], self.g("mixer.1.weight"), R, D, C, splits=sp(D, C, R))
         call("colsum", dH, self.g("mixer.1.bias"), R, D)

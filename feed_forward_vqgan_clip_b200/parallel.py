@@ -38,6 +38,23 @@ def allreduce_flat_grads(flat_grad, world, group=None):
     return 1.0 / world
 
 
+def bucket_ranges(layer_starts, total, layers_per_bucket):
+    """Contiguous [lo, hi) slices of the flat gradient arena in the order backward completes them.
+    layer_starts: arena offset of the first parameter of every mixer layer, ascending (layer 0 first); backward finishes
+    the layers last-to-first, so bucket k covers layers [L - (k+1)*n, L - k*n) plus, for k = 0, everything registered
+    after the last layer (final norm, output projection); the head of the arena (input projections, finished last) is the
+    final slice.  The slices tile [0, total) exactly once."""
+    L = len(layer_starts)
+    out, hi, i = [], total, L
+    while i > 0:
+        j = max(0, i - layers_per_bucket)
+        out.append((layer_starts[j], hi))
+        hi, i = layer_starts[j], j
+    if hi > 0:
+        out.append((0, hi))
+    return out
+
+
 def broadcast_flat(flat, src=0, group=None):
     """hvd.broadcast_parameters / broadcast_optimizer_state equivalent on a flat arena (main.py:628-629)."""
     if dist.is_initialized() and dist.get_world_size() > 1:

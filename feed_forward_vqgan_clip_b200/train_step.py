@@ -69,6 +69,11 @@ class TrainStep:
         self.opt = FusedAdam(self.mix, lr=lr)
         self.world, self.pg = world_size, process_group
         self.opt.set_grad_scale(1.0 / world_size)
+        # data parallel: the flat gradient arena is all-reduced in buckets of `bucket_layers` mixer layers on a side stream
+        # WHILE backward is still producing the earlier layers' gradients (the reference gets this from Horovod's hooks,
+        # main.py:627); engines without per-layer completion callbacks fall back to one all-reduce after backward
+        self.bucket_layers = 8
+        self.comm_stream = torch.cuda.Stream(device=self.dev) if world_size > 1 else None
         cb = self.dec.codebook
         self.z_lo, self.z_hi = float(cb.min()), float(cb.max())          # main.py:645-646,763 (global scalars)
         self.gen = torch.Generator().manual_seed(seed)
@@ -113,10 +118,32 @@ class TrainStep:
             self.aux_loss[0:1].mul_(self.l2_coef / z.numel())
             call("axpy_f32", z, dz, 2.0 * self.l2_coef / z.numel(), z.numel())
         mix.zero_grad_arena()
-        mix.backward(sv_m, dz)
+        if self.world > 1 and self.bucket_layers > 0 and hasattr(mix, "layer_starts"):
+            from .parallel import bucket_ranges
+            ranges = bucket_ranges(mix.layer_starts(), mix.total, self.bucket_layers)
+            main, comm = torch.cuda.current_stream(), self.comm_stream
+            first_layer_of_bucket = {mix.L - min(mix.L, (k + 1) * self.bucket_layers): k for k in range(len(ranges) - 1)}
+
+            def reduce_slice(lo, hi):
+                ev = torch.cuda.Event()
+                ev.record(main)                       # gradients of [lo, hi) are complete at this point of the main stream
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    torch.distributed.all_reduce(mix.grad[lo:hi], group=self.pg)
+
+            def on_layer_done(k):
+                if k in first_layer_of_bucket:
+                    reduce_slice(*ranges[first_layer_of_bucket[k]])
+
+            mix.backward(sv_m, dz, on_layer_done=on_layer_done)
+            if ranges[-1][0] == 0 and len(ranges) > len(first_layer_of_bucket):
+                reduce_slice(*ranges[-1])             # head of the arena: input projections, finished last
+            main.wait_stream(comm)
+        else:
+            mix.backward(sv_m, dz)
+            if self.world > 1:
+                torch.distributed.all_reduce(mix.grad, group=self.pg)   # one NCCL all-reduce over NVLink (main.py:627)
         del sv_m
-        if self.world > 1:
-            torch.distributed.all_reduce(mix.grad, group=self.pg)       # one NCCL all-reduce over NVLink (main.py:627)
         self.opt.apply()
         return self.loss
 

@@ -131,3 +131,52 @@ def test_horovod_shim_single_process_is_a_no_op():
     opt = hvd.DistributedOptimizer(torch.optim.SGD([torch.nn.Parameter(torch.ones(2))], lr=0.1))
     opt.step()
     hvd.join()
+
+
+# ----------------------------------------------------------------------------------------------------- bucketed all-reduce
+def test_bucket_ranges_tile_the_arena_in_backward_order():
+    import random
+    rnd = random.Random(0)
+    for _ in range(50):
+        L = rnd.randint(1, 40)
+        starts, o = [], rnd.choice([0, 8, 4096])
+        for _l in range(L):
+            starts.append(o)
+            o += 8 * rnd.randint(1, 50)
+        total = o + 8 * rnd.randint(0, 20)
+        n = rnd.randint(1, 12)
+        r = parallel.bucket_ranges(starts, total, n)
+        assert r[0][1] == total and r[-1][0] == 0                       # tail first (finished first), head last
+        assert all(a[0] == b[1] for a, b in zip(r, r[1:]))              # contiguous, descending, no overlap
+        assert all(lo < hi for lo, hi in r)
+        assert all(lo in starts or lo == 0 for lo, hi in r)             # cuts only at layer boundaries
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    parallel.init_from_env("gloo")
+    g = torch.Generator().manual_seed(100 + rank)
+    grad = torch.randn(5000, generator=g)
+    whole = grad.clone()
+    dist.all_reduce(whole)
+    starts = [40 + 155 * i for i in range(32)]
+    for lo, hi in parallel.bucket_ranges(starts, 5000, 8):
+        dist.all_reduce(grad[lo:hi])                                   # slices are views: reduced in place
+    q.put((rank, torch.equal(grad, whole)))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_equals_single_allreduce_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res)
