@@ -43,6 +43,43 @@ static constexpr int kNumThreads = 320;
 static constexpr int kNumEpiWarps = 8;
 static constexpr int kTmemCols = 512;
 
+// Work decomposition shared by the three warp roles (they must walk the same sequence).
+//   regular : output tiles (x split-K slices) are dealt round-robin to the persistent CTAs / CTA pairs;
+//   stream-K: the linearised (tile, k-block) space is cut into one CONTIGUOUS range per worker, so every worker gets the
+//             same number of k-blocks whatever the tile count (64 pair tiles on 74 CTA pairs ran at 86 %); a worker touches
+//             at most two partial tiles and accumulates them with the fp32 atomic epilogue (wgrad GEMMs only).
+struct WorkIter {
+  long long t, t_step, t_end, tiles_all;
+  long long u, u_end;
+  int total_kb, splits, stream_k;
+  __device__ __forceinline__ WorkIter(const GemmDev& p, long long worker, long long workers, long long tiles_all_, int total_kb_)
+      : t(worker), t_step(workers), t_end(tiles_all_ * p.splits), tiles_all(tiles_all_), total_kb(total_kb_), splits(p.splits),
+        stream_k(p.stream_k) {
+    const long long units = tiles_all_ * total_kb_;
+    u = units * worker / workers;
+    u_end = units * (worker + 1) / workers;
+  }
+  // next work item: tile index `rem` (over tiles x batches) and its k-block range; false when this worker is done
+  __device__ __forceinline__ bool next(int& rem, int& kb_begin, int& kb_end) {
+    if (stream_k) {
+      if (u >= u_end) return false;
+      rem = (int)(u / total_kb);
+      kb_begin = (int)(u % total_kb);
+      const long long left = u_end - u;
+      kb_end = (left < (long long)(total_kb - kb_begin)) ? kb_begin + (int)left : total_kb;
+      u += kb_end - kb_begin;
+      return true;
+    }
+    if (t >= t_end) return false;
+    const int split = (int)(t / tiles_all);
+    rem = (int)(t % tiles_all);
+    kb_begin = (int)((long long)total_kb * split / splits);
+    kb_end = (int)((long long)total_kb * (split + 1) / splits);
+    t += t_step;
+    return true;
+  }
+};
+
 // kTwoCta = false: one CTA per tile (128 or 256 rows).
 // kTwoCta = true : a CTA PAIR (cluster of 2, cta_group::2) per 256-row tile — each CTA stages its own 128 rows of A and
 //   HALF of the B tile; the leader CTA issues tcgen05.mma M=256 that reads both CTAs' shared memory, so every SM
@@ -108,7 +145,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int tiles_per_batch = tiles_m * tiles_n;
   const int total_kb = p.kb_per_seg * p.k_segs;
   const long long tiles_all_batches = (long long)tiles_per_batch * p.batch;
-  const long long total_tiles = tiles_all_batches * p.splits;
   const long long tile_first = kTwoCta ? (blockIdx.x >> 1) : blockIdx.x;
   const long long tile_step = kTwoCta ? (gridDim.x >> 1) : gridDim.x;
   const int rows_cta = kTwoCta ? 128 : p.tile_m;             // rows of A this CTA stages
@@ -126,17 +162,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (kTwoCta) tma_load_4d_2sm(dst, desc, bar, c0, c1, c2, c3);
         else tma_load_4d(dst, desc, bar, c0, c1, c2, c3);
       };
-      for (long long t = tile_first; t < total_tiles; t += tile_step) {
-        const int split = (int)(t / tiles_all_batches);
-        const int rem = (int)(t % tiles_all_batches);
+      WorkIter it(p, tile_first, tile_step, tiles_all_batches, total_kb);
+      int rem, kb_begin, kb_end;
+      while (it.next(rem, kb_begin, kb_end)) {
         const int bi = rem / tiles_per_batch;
         const int tm = (rem % tiles_per_batch) / tiles_n;
         const int tn = rem % tiles_n;
         const int m0 = tm * p.tile_m + (kTwoCta ? (int)rank * 128 : 0);
         const int n0 = tn * p.block_n + (kTwoCta ? (int)rank * bn_cta : 0);
         const int bi_in = bi % p.batch_inner, bi_out = bi / p.batch_inner;
-        const int kb_begin = (int)((long long)total_kb * split / p.splits);
-        const int kb_end = (int)((long long)total_kb * (split + 1) / p.splits);
         // conv: decompose the flattened pixel index of the tile origin
         int cimg = 0, cy0 = 0, cx0 = 0;
         if (p.a_mode == FFVC_OP_CONV3X3) {
@@ -203,10 +237,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (long long t = tile_first; t < total_tiles; t += tile_step) {
-        const int split = (int)(t / tiles_all_batches);
-        const int kb_begin = (int)((long long)total_kb * split / p.splits);
-        const int kb_end = (int)((long long)total_kb * (split + 1) / p.splits);
+      WorkIter it(p, tile_first, tile_step, tiles_all_batches, total_kb);
+      int rem, kb_begin, kb_end;
+      while (it.next(rem, kb_begin, kb_end)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
@@ -282,8 +315,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t stg_out = stg_pre + 2048u;
     const uint32_t stg_row = (uint32_t)lane * 64u, stg_sw = (uint32_t)((lane >> 1) & 3);
     bool stg_busy = false;     // a bulk store of this warp may still be reading the staging buffers
-    for (long long t = tile_first; t < total_tiles; t += tile_step) {
-      const int rem = (int)(t % tiles_all_batches);
+    WorkIter it(p, tile_first, tile_step, tiles_all_batches, total_kb);
+    int rem, kb_begin_unused, kb_end_unused;
+    while (it.next(rem, kb_begin_unused, kb_end_unused)) {
       const int bi = rem / tiles_per_batch;
       const int tm = (rem % tiles_per_batch) / tiles_n;
       const int tn = rem % tiles_n;
@@ -469,6 +503,8 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
 
 static int g_num_sms = 0;
 static bool g_attr_set = false;
+static int g_stream_k_enabled = 0;    // ffvc_gemm_set_stream_k(1): measured no better than split-K on this workload (the wgrad
+                                      // GEMMs are L2-operand-bandwidth bound, not tail bound), so it is opt-in
 static int g_tma_store_enabled = 1;   // ffvc_gemm_set_tma_store(0) keeps the direct-store epilogue (A/B measurements, tests)
 
 
@@ -534,6 +570,11 @@ static int set_gemm_attrs() {
 }  // namespace ffvc
 
 using namespace ffvc;
+
+extern "C" int ffvc_gemm_set_stream_k(int on) {
+  g_stream_k_enabled = on ? 1 : 0;
+  return FFVC_OK;
+}
 
 extern "C" int ffvc_gemm_set_tma_store(int on) {
   g_tma_store_enabled = on < 0 ? 0 : (on > 2 ? 2 : on);
@@ -696,6 +737,17 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     }
   }
   if (splits > p.kb_per_seg * k_segs) splits = p.splits = p.kb_per_seg * k_segs;
+  // stream-K for the fp32-atomic (wgrad) GEMMs whose tile count does not fill the machine evenly: replaces split-K
+  {
+    const long long tiles0 = (long long)((g->M + tile_m - 1) / tile_m) * ((g->N + block_n - 1) / block_n) * batch;
+    const long long workers = (two_cta == 1) ? g_num_sms / 2 : g_num_sms;
+    const long long total_kb_h = (long long)p.kb_per_seg * k_segs;
+    const long long waves_x100 = tiles0 * splits * 100 / workers;            // work items per worker, in percent
+    const bool uneven = (waves_x100 % 100) != 0 && waves_x100 < 800;         // a fractional last wave that matters
+    p.stream_k = (g_stream_k_enabled && g->out_fp32 && g->atomic && !g->argmin_out && !g->bias && !g->res && !g->aux && !g->pre_out &&
+                  g->act == FFVC_ACT_NONE && uneven && tiles0 * total_kb_h >= 4 * workers) ? 1 : 0;
+    if (p.stream_k) splits = p.splits = 1;
+  }
 
   p.out = g->out;
   p.pre_out = g->pre_out;
@@ -735,7 +787,7 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   cfg.stream = stream;
   if (two_cta == 1) {
     // one CTA pair (cluster of 2) per tile, persistent over min(tiles, SMs/2) pairs
-    const long long pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+    const long long pairs = (p.stream_k || tiles >= g_num_sms / 2) ? g_num_sms / 2 : tiles;
     cfg.gridDim = dim3((unsigned)(2 * pairs));
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -744,7 +796,7 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    cfg.gridDim = dim3((unsigned)(tiles < g_num_sms ? tiles : g_num_sms));
+    cfg.gridDim = dim3((unsigned)((p.stream_k || tiles >= g_num_sms) ? g_num_sms : tiles));
   }
   // TMA-store epilogue: compile-time epilogue on the pair kernel, bf16 output(s) whose rows / batches start on 16-byte boundaries
   CUtensorMap tms[4];

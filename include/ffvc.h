@@ -100,6 +100,10 @@ int ffvc_gemm(const ffvc_gemm_params* p, void* stream);
 /* 1 (default): compile-time-epilogue GEMMs on the CTA-pair kernel with K <= 512 write their bf16 outputs through shared memory
  * and TMA stores; 2: for every K; 0: every epilogue stores straight from registers (A/B measurements, tests). */
 int ffvc_gemm_set_tma_store(int on);
+/* 1: fp32-atomic GEMMs whose tiles do not fill the SMs evenly run stream-K (every CTA / CTA pair gets the same number of
+ * k-blocks of the linearised (tile, k-block) space); 0 (default): split-K as requested by the caller.  Measured equal or
+ * slightly slower than split-K on config #2 (those GEMMs are bound by L2 -> SM operand traffic), hence opt-in. */
+int ffvc_gemm_set_stream_k(int on);
 
 /* 3x3 conv (pad 1, stride 1) with shared-memory halo reuse: NHWC bf16 x [n][h][w][cin], packed weights [cout][9][cin]
  * (tap-major, as for FFVC_OP_CONV3X3), bf16 out [n*h*w][ldc].  Requires w % 128 == 0, even h, cin % 64 == 0, cout <= 128:

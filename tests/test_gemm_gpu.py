@@ -364,3 +364,25 @@ def test_tma_store_epilogue_matches_direct_stores(cfg, M, N, K, batch):
     else:
         sg = torch.sigmoid(1.702 * x)
         _check(outs[0][0], acc * (sg + 1.702 * x * sg * (1 - sg)), 2e-2)
+
+
+@pytest.mark.parametrize("M,N,K,segs,two", [(1024, 1024, 4096, 1, 0), (4096, 1024, 2048, 1, 1), (256, 1024, 512, 8, 0), (304, 200, 1000, 1, 0)])
+def test_stream_k_wgrad_matches_split_k(M, N, K, segs, two):
+    """fp32-atomic (wgrad) GEMMs whose tiles do not fill the SMs evenly run stream-K: contiguous (tile, k-block) ranges per
+    worker, partial tiles accumulated atomically — same result as split-K and as torch"""
+    from feed_forward_vqgan_clip_b200 import _lib
+    lib = _lib.load()
+    # dW[m, n] += sum_seg sum_k A[seg][k][m] * B[seg][k][n]   (both operands MN-major, like linear_wgrad)
+    a, b = _rand(segs, K, M, seed=111), _rand(segs, K, N, seed=112)
+    ref = torch.einsum("skm,skn->mn", a.float(), b.float())
+    outs = []
+    for sk in (1, 0):
+        lib.ffvc_gemm_set_stream_k(sk)
+        out = torch.full((M, N), 0.25, device=DEV, dtype=torch.float32)
+        ops.gemm(a, b, out, M, N, K, a_mode=ops.MNMAJOR, b_mode=ops.MNMAJOR, a_ld=M, b_ld=N, a_role=ops.ROLE_SEG, a_bs=K * M,
+                 b_role=ops.ROLE_SEG, b_bs=K * N, k_segs=segs, splits=4, atomic=True, two_cta=two)
+        outs.append(out)
+    lib.ffvc_gemm_set_stream_k(0)
+    _check(outs[0] - 0.25, ref, 2e-3)
+    _check(outs[1] - 0.25, ref, 2e-3)
+    assert (outs[0] - outs[1]).abs().max().item() <= 2e-3 * ref.abs().max().item()

@@ -24,6 +24,8 @@ def main():
     args = ap.parse_args()
     from feed_forward_vqgan_clip_b200 import _lib
     _lib.load().ffvc_groupnorm_set_pipeline(args.gn_pipeline)
+    if os.environ.get("FFVC_STREAM_K") is not None:
+        _lib.load().ffvc_gemm_set_stream_k(int(os.environ["FFVC_STREAM_K"]))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     ts = bench.build_b200(dev, args.batch, 1, None)
