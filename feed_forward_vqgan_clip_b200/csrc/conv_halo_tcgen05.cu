@@ -181,6 +181,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 8 == 0);
+    // 32-byte (256-bit) row accesses when every row starts on a 32-byte boundary (bf16 output): half the L1 requests
+    const bool vec32_ok = vec_ok && !p.out_fp32 && (p.ldc % 16 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.res)) & 31) == 0;
     const bool want_aux = p.mul_mode != FFVC_ACT_NONE, want_res = p.res != nullptr;
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int tx = (int)(t % tiles_x);
@@ -198,18 +201,28 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       auto prefetch = [&](int c) {
         if (vec_ok && c + CW <= p.N) {
           if (want_aux) {
-            const uint4* ax = reinterpret_cast<const uint4*>(p.aux + row_off + c);
+            if (vec32_ok) {
 #pragma unroll
-            for (int j = 0; j < CW / 8; ++j) pf_aux[j] = ax[j];
+              for (int j = 0; j < CW / 16; ++j) ld_global_256(p.aux + row_off + c + 16 * j, pf_aux[2 * j], pf_aux[2 * j + 1]);
+            } else {
+              const uint4* ax = reinterpret_cast<const uint4*>(p.aux + row_off + c);
+#pragma unroll
+              for (int j = 0; j < CW / 8; ++j) pf_aux[j] = ax[j];
+            }
           }
           if (want_res) {
-            const uint4* rs = reinterpret_cast<const uint4*>(p.res + row_off + c);
+            if (vec32_ok) {
 #pragma unroll
-            for (int j = 0; j < CW / 8; ++j) pf_res[j] = rs[j];
+              for (int j = 0; j < CW / 16; ++j) ld_global_256(p.res + row_off + c + 16 * j, pf_res[2 * j], pf_res[2 * j + 1]);
+            } else {
+              const uint4* rs = reinterpret_cast<const uint4*>(p.res + row_off + c);
+#pragma unroll
+              for (int j = 0; j < CW / 8; ++j) pf_res[j] = rs[j];
+            }
           }
         }
       };
-      prefetch(0);
+      if (want_aux || want_res) prefetch(0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       for (int c = 0; c < p.block_n; c += CW) {
@@ -218,13 +231,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
         uint4 cur_aux[CW / 8], cur_res[CW / 8];
+        if (want_aux) {
 #pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          cur_aux[j] = pf_aux[j];
-          cur_res[j] = pf_res[j];
+          for (int j = 0; j < CW / 8; ++j) cur_aux[j] = pf_aux[j];
         }
-        if (c + CW < p.block_n) prefetch(c + CW);
-        if (c < p.N) epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok && (c + CW <= p.N), sbias + c, cur_aux, cur_res);
+        if (want_res) {
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) cur_res[j] = pf_res[j];
+        }
+        if ((want_aux || want_res) && c + CW < p.block_n) prefetch(c + CW);
+        if (c < p.N)
+          epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok && (c + CW <= p.N), sbias + c, cur_aux, cur_res, vec32_ok && (c + CW <= p.N));
         __syncwarp();
       }
       tc_fence_before();

@@ -34,62 +34,73 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------------------------------ LayerNorm forward
-// One warp per row; D % 8 == 0, D <= 32*8*kMaxV.
+// One warp per row, rows dealt round-robin to the resident warps; D % 8 == 0, D <= 32*8*kMaxV.  gamma / beta are staged in
+// shared memory once per CTA: re-reading them from global for every row made the kernel L1-bound (ncu: 24 sectors per
+// load request, 8 KB of parameter traffic per 2 KB row, 66 % L1 throughput at 1.5 TB/s of useful traffic).
 template <int kMaxV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                                                             float* __restrict__ rstd, long long rows, int D, float eps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (row >= rows) return;
-  const int nvec = D >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
-  float v[kMaxV][8];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
-      unpack8(xr[c], v[i]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
-    }
+  extern __shared__ float sgb[];   // [gamma D][beta D]
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    sgb[i] = gamma[i];
+    sgb[D + i] = beta[i];
   }
-  s = warp_sum(s);
-  const float mu = s / D;
-  float q = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  const float4* sg4 = reinterpret_cast<const float4*>(sgb);
+  const float4* sb4 = reinterpret_cast<const float4*>(sgb + D);
+  for (long long row = (long long)blockIdx.x * wpb + warp; row < rows; row += (long long)gridDim.x * wpb) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * D);
+    float v[kMaxV][8];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
+    for (int i = 0; i < kMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        unpack8(xr[c], v[i]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = v[i][j] - mu;
-        q += d * d;
+        for (int j = 0; j < 8; ++j) s += v[i][j];
       }
     }
-  }
-  q = warp_sum(q);
-  const float rs = rsqrtf(q / D + eps);
-  if (lane == 0) {
-    if (mean) mean[row] = mu;
-    if (rstd) rstd[row] = rs;
-  }
-  uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+    s = warp_sum(s);
+    const float mu = s / D;
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nvec) {
-      float o[8];
-      const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
-      const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * c], b1 = reinterpret_cast<const float4*>(beta)[2 * c + 1];
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int i = 0; i < kMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * gg[j] + bb[j];
-      yr[c] = pack8(o);
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mu;
+          q += d * d;
+        }
+      }
+    }
+    q = warp_sum(q);
+    const float rs = rsqrtf(q / D + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = rs;
+    }
+    uint4* yr = reinterpret_cast<uint4*>(y + row * D);
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float o[8];
+        const float4 g0 = sg4[2 * c], g1 = sg4[2 * c + 1];
+        const float4 b0 = sb4[2 * c], b1 = sb4[2 * c + 1];
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mu) * rs * gg[j] + bb[j];
+        yr[c] = pack8(o);
+      }
     }
   }
 }
@@ -106,7 +117,11 @@ __global__ void __launch_bounds__(256, kWgrad ? 2 : 3) layernorm_bwd_kernel(cons
                                                                const __nv_bfloat16* __restrict__ add,
                                                                __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                                float* __restrict__ dbeta, long long rows, int D) {
-  extern __shared__ float sm[];  // [2][D] when dgamma != nullptr
+  extern __shared__ float sm_all[];  // [gamma D] then, when dgamma != nullptr, [2][D] accumulators
+  float* sgam = sm_all;
+  float* sm = sm_all + D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) sgam[i] = gamma[i];   // re-reading gamma from global per row was L1-bound
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwarps = blockDim.x >> 5;
   const int nvec = D >> 3;
@@ -146,7 +161,7 @@ __global__ void __launch_bounds__(256, kWgrad ? 2 : 3) layernorm_bwd_kernel(cons
         float xv[8], dv[8];
         unpack8(xp[i], xv);
         unpack8(dp[i], dv);
-        const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
+        const float4 g0 = reinterpret_cast<const float4*>(sgam)[2 * c], g1 = reinterpret_cast<const float4*>(sgam)[2 * c + 1];
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -171,7 +186,7 @@ __global__ void __launch_bounds__(256, kWgrad ? 2 : 3) layernorm_bwd_kernel(cons
         float xv[8], dv[8], o[8];
         unpack8(xp[i], xv);
         unpack8(dp[i], dv);
-        const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
+        const float4 g0 = reinterpret_cast<const float4*>(sgam)[2 * c], g1 = reinterpret_cast<const float4*>(sgam)[2 * c + 1];
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -775,13 +790,15 @@ extern "C" int ffvc_layernorm_fwd(const void* x, const float* gamma, const float
   if (rows <= 0) return FFVC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int wpb = 8;
-  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  long long want = (rows + wpb - 1) / wpb;
+  const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);      // resident warps loop over the rows
+  const size_t smem = 2 * (size_t)D * sizeof(float);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yb = reinterpret_cast<__nv_bfloat16*>(y);
   if (D <= 1024)
-    layernorm_fwd_kernel<4><<<grid, wpb * 32, 0, st>>>(xb, gamma, beta, yb, mean, rstd, rows, D, eps);
+    layernorm_fwd_kernel<4><<<grid, wpb * 32, smem, st>>>(xb, gamma, beta, yb, mean, rstd, rows, D, eps);
   else
-    layernorm_fwd_kernel<8><<<grid, wpb * 32, 0, st>>>(xb, gamma, beta, yb, mean, rstd, rows, D, eps);
+    layernorm_fwd_kernel<8><<<grid, wpb * 32, smem, st>>>(xb, gamma, beta, yb, mean, rstd, rows, D, eps);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
@@ -797,7 +814,7 @@ extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* ga
   long long want = (rows + wpb - 1) / wpb;
   const int per_sm = dgamma ? 2 : 3;
   const unsigned grid = (unsigned)(want < 148 * per_sm ? want : 148 * per_sm);
-  const size_t smem = dgamma ? 2 * D * sizeof(float) : 0;
+  const size_t smem = (dgamma ? 3 : 1) * (size_t)D * sizeof(float);
   auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto ab = reinterpret_cast<const __nv_bfloat16*>(add);
