@@ -114,4 +114,6 @@ def train_step(net, vq, perceptor, config=None, **kw):
     return TrainStep(net, vq, perceptor, cutn=_get(cfg, "cutn", 8), lr=_get(cfg, "lr", 1e-3),
                      target_loss_coef=_get(cfg, "target_loss_coef", 1.0), l2_coef=_get(cfg, "l2_coef", 0.0) or 0.0,
                      tv_coef=_get(cfg, "tv_coef", 0.0) or 0.0, diversity_coef=_get(cfg, "diversity_coef", 0.0) or 0.0,
-                     repeat=_get(cfg, "repeat", 1) or 1, **kw)
+                     repeat=_get(cfg, "repeat", 1) or 1, clip_grad_norm=_get(cfg, "clip_grad_norm", None),
+                     scheduler=_get(cfg, "scheduler", None), use_ema=bool(_get(cfg, "use_ema", False)),
+                     ema_decay=_get(cfg, "ema_decay", 0.995), **kw)

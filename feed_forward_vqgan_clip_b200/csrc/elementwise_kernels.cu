@@ -559,45 +559,126 @@ __global__ void __launch_bounds__(256) im2col3x3_cin3_kernel(const float* __rest
 
 // ---------------------------------------------------------------- fused Adam (torch.optim.Adam defaults, main.py:591,835)
 // p,g,m,v fp32 flat arenas; also refreshes the bf16 shadow the GEMMs read.  grad_scale folds the DP average.
+// hyper (DEVICE float[16], so a captured CUDA graph sees per-step values):
+//   [0] lr of this step   [1] beta1   [2] beta2   [3] eps   [4] 1-beta1^t   [5] sqrt(1-beta2^t)   [6] grad_scale   [7] weight_decay
+//   [8] t (steps taken)   [9] clip_grad_norm max_norm (0 = off, main.py:693,833-834)   [10] sum g^2 of this step (ffvc_sumsq)
+//   [11] clip coefficient of this step (adam_tick)   [12] base lr   [13] cosine T_max (0 = constant lr, main.py:702-705)
+//   [14] cosine eta_min   [15] EMA decay (0 = off; torch_ema semantics, main.py:524-525,843-844)
+struct AdamCoef {
+  float b1, b2, eps, bc2_sqrt, gscale, wd, step_size, ema_omd;
+};
+__device__ __forceinline__ AdamCoef adam_coef(const float* __restrict__ hyper) {
+  AdamCoef c;
+  c.b1 = hyper[1];
+  c.b2 = hyper[2];
+  c.eps = hyper[3];
+  c.bc2_sqrt = hyper[5];
+  c.gscale = hyper[6] * (hyper[9] > 0.f ? hyper[11] : 1.f);
+  c.wd = hyper[7];
+  c.step_size = hyper[0] / hyper[4];
+  // torch_ema: num_updates += 1; decay = min(decay, (1 + num_updates) / (10 + num_updates)); shadow -= (1 - decay) * (shadow - p)
+  const float t = hyper[8];
+  c.ema_omd = 1.f - fminf(hyper[15], (1.f + t) / (10.f + t));
+  return c;
+}
+__device__ __forceinline__ float adam_one(const AdamCoef& c, float pv, float gv, float& mv, float& vv) {
+  gv *= c.gscale;
+  if (c.wd != 0.f) gv += c.wd * pv;
+  mv = c.b1 * mv + (1.f - c.b1) * gv;
+  vv = c.b2 * vv + (1.f - c.b2) * gv * gv;
+  const float denom = sqrtf(vv) / c.bc2_sqrt + c.eps;
+  return pv - c.step_size * (mv / denom);
+}
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n,
-                                                   const float* __restrict__ hyper) {
-  // hyper (device, so a captured CUDA graph sees per-step values): lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t),
-  // grad_scale, weight_decay
-  const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], bc1 = hyper[4], bc2_sqrt = hyper[5];
-  const float grad_scale = hyper[6], wd = hyper[7];
-  const float step_size = lr / bc1;
+                                                   float* __restrict__ v, __nv_bfloat16* __restrict__ shadow,
+                                                   float* __restrict__ ema, long long n, const float* __restrict__ hyper) {
+  const AdamCoef c = adam_coef(hyper);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float gv = g[i] * grad_scale;
-    const float pv = p[i];
-    if (wd != 0.f) gv += wd * pv;
-    const float mv = b1 * m[i] + (1.f - b1) * gv;
-    const float vv = b2 * v[i] + (1.f - b2) * gv * gv;
+    float mv = m[i], vv = v[i];
+    const float np = adam_one(c, p[i], g[i], mv, vv);
     m[i] = mv;
     v[i] = vv;
-    const float denom = sqrtf(vv) / bc2_sqrt + eps;
-    const float np = pv - step_size * (mv / denom);
     p[i] = np;
     if (shadow) shadow[i] = __float2bfloat16(np);
+    if (ema) {
+      const float e = ema[i];
+      ema[i] = e - c.ema_omd * (e - np);
+    }
+  }
+}
+// 16-byte form of the same update (n % 4 == 0, 16-byte aligned arenas): identical arithmetic per element
+template <bool kEma>
+__global__ void __launch_bounds__(256) adam_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                        float4* __restrict__ m, float4* __restrict__ v,
+                                                        uint2* __restrict__ shadow, float4* __restrict__ ema, long long n4,
+                                                        const float* __restrict__ hyper) {
+  const AdamCoef c = adam_coef(hyper);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 pv = p[i], gv = g[i];
+    float4 mv = m[i], vv = v[i];
+    float4 np;
+    np.x = adam_one(c, pv.x, gv.x, mv.x, vv.x);
+    np.y = adam_one(c, pv.y, gv.y, mv.y, vv.y);
+    np.z = adam_one(c, pv.z, gv.z, mv.z, vv.z);
+    np.w = adam_one(c, pv.w, gv.w, mv.w, vv.w);
+    m[i] = mv;
+    v[i] = vv;
+    p[i] = np;
+    if (shadow) {
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(np.x, np.y), h1 = __floats2bfloat162_rn(np.z, np.w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&h0);
+      o.y = *reinterpret_cast<const uint32_t*>(&h1);
+      shadow[i] = o;
+    }
+    if (kEma) {
+      float4 e = ema[i];
+      e.x -= c.ema_omd * (e.x - np.x);
+      e.y -= c.ema_omd * (e.y - np.y);
+      e.z -= c.ema_omd * (e.z - np.z);
+      e.w -= c.ema_omd * (e.w - np.w);
+      ema[i] = e;
+    }
   }
 }
 
-// advance Adam's step counter on the device and refresh the bias corrections (graph-capturable, no host staging)
+// advance Adam's step counter on the device and refresh the per-step scalars (graph-capturable, no host staging):
+// bias corrections, the cosine-annealed learning rate (torch CosineAnnealingLR closed form; the reference steps the scheduler
+// AFTER opt.step(), main.py:835-837, so update t uses epoch t-1) and the clip_grad_norm_ coefficient min(1, max/(norm+1e-6)).
 __global__ void adam_tick_kernel(float* __restrict__ hyper) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const float t = hyper[8] + 1.0f;
     hyper[8] = t;
     hyper[4] = 1.0f - powf(hyper[1], t);
     hyper[5] = sqrtf(1.0f - powf(hyper[2], t));
+    if (hyper[13] > 0.f)
+      hyper[0] = hyper[14] + (hyper[12] - hyper[14]) * 0.5f * (1.0f + cospif((t - 1.0f) / hyper[13]));
+    if (hyper[9] > 0.f) {
+      const float norm = sqrtf(hyper[10]) * hyper[6];         // norm of the averaged gradient (grad_scale = 1 / world)
+      hyper[11] = fminf(1.0f, hyper[9] / (norm + 1e-6f));
+    }
   }
 }
 
-__global__ void sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, float* __restrict__ out, long long n) {
   float acc = 0.f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  const long long n4 = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? (n >> 2) : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 t = x4[i];
+    acc += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     acc += x[i] * x[i];
   acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+  __shared__ float part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += part[w];
+    atomicAdd(out, s);
+  }
 }
 
 
@@ -810,12 +891,37 @@ extern "C" int ffvc_conv3x3_cin3(const float* x, const float* w, void* y, int N,
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
-extern "C" int ffvc_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
-                              const float* hyper_dev, void* stream) {
+static int adam_launch(float* p, const float* g, float* m, float* v, void* shadow_bf16, float* ema, long long n,
+                       const float* hyper_dev, void* stream) {
   if (!hyper_dev) return set_error(FFVC_ERR_ARG, "adam: hyper-parameter block is null");
-  adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(p, g, m, v, BF(shadow_bf16), n, hyper_dev);
+  if (n <= 0) return FFVC_OK;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(ema) |
+                       (reinterpret_cast<uintptr_t>(shadow_bf16) << 1);       // the bf16 shadow only needs 8-byte alignment
+  if ((n & 3) == 0 && (al & 15) == 0) {
+    const long long n4 = n >> 2;
+    if (ema)
+      adam_vec4_kernel<true><<<grid_for(n4, 256, 148 * 8), 256, 0, ST(stream)>>>(
+          reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+          reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(shadow_bf16), reinterpret_cast<float4*>(ema), n4, hyper_dev);
+    else
+      adam_vec4_kernel<false><<<grid_for(n4, 256, 148 * 8), 256, 0, ST(stream)>>>(
+          reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+          reinterpret_cast<float4*>(v), reinterpret_cast<uint2*>(shadow_bf16), nullptr, n4, hyper_dev);
+  } else {
+    adam_kernel<<<grid_for(n, 256, 148 * 8), 256, 0, ST(stream)>>>(p, g, m, v, BF(shadow_bf16), ema, n, hyper_dev);
+  }
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
+}
+extern "C" int ffvc_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n,
+                              const float* hyper_dev, void* stream) {
+  return adam_launch(p, g, m, v, shadow_bf16, nullptr, n, hyper_dev, stream);
+}
+extern "C" int ffvc_adam_step_ema(float* p, const float* g, float* m, float* v, void* shadow_bf16, float* ema, long long n,
+                                  const float* hyper_dev, void* stream) {
+  if (!ema) return set_error(FFVC_ERR_ARG, "adam_step_ema: ema arena is null");
+  return adam_launch(p, g, m, v, shadow_bf16, ema, n, hyper_dev, stream);
 }
 extern "C" int ffvc_im2col3x3_cin3(const float* x, void* col, int N, int H, int W, void* stream) {
   im2col3x3_cin3_kernel<<<grid_for((long long)N * H * W, 256), 256, 0, ST(stream)>>>(x, BF(col), N, H, W);

@@ -5,6 +5,8 @@
 namespace ffvc {
 int set_error(int code, const char* msg);
 void count_launch(int n = 1);
+enum { OPT_LN_V2 = 0, OPT_POOL_V2 = 1, OPT_COUNT = 2 };
+int option(int id);   // kernel-selection switch (ffvc_set_option / FFVC_OPTS)
 }  // namespace ffvc
 
 #define FFVC_CHECK_LAUNCH()                                                        \

@@ -24,7 +24,10 @@ from .cutouts import CutoutEngine, sample_params
 
 
 class FusedAdam:
-    """torch.optim.Adam semantics (lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) on the mapper's flat arena."""
+    """The reference's optimizer block (main.py:591,693,702-709,825-837,843-844) on the mapper's flat arena, one launch:
+    torch.optim.Adam (lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0), optional `clip_grad_norm_(max_norm)`, optional
+    cosine annealing (CosineAnnealingLR(T_max, eta_min=0)), optional torch_ema ExponentialMovingAverage(decay).
+    Every per-step scalar lives in a device block (`hyper`, layout in include/ffvc.h) so a captured CUDA graph sees it."""
 
     def __init__(self, engine, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.eng = engine
@@ -32,28 +35,122 @@ class FusedAdam:
         self.m = torch.zeros_like(engine.arena)
         self.v = torch.zeros_like(engine.arena)
         self.t = 0
+        self.clip, self.ema = 0.0, None
         b1, b2 = betas
-        self.hyper = torch.tensor([lr, b1, b2, eps, 1.0, 1.0, 1.0, weight_decay, 0.0, 0, 0, 0, 0, 0, 0, 0], dtype=F32).to(engine.dev)
+        self.hyper = torch.tensor([lr, b1, b2, eps, 1.0, 1.0, 1.0, weight_decay, 0.0, 0.0, 0.0, 1.0, lr, 0.0, 0.0, 0.0],
+                                  dtype=F32).to(engine.dev)
 
     def set_lr(self, lr):
         self.lr = lr
         self.hyper[0:1].fill_(lr)
+        self.hyper[12:13].fill_(lr)
 
     def set_grad_scale(self, s):
         self.hyper[6:7].fill_(s)
 
+    def set_clip_grad_norm(self, max_norm):
+        """main.py:693,833-834.  The norm is taken over the (rank-averaged) flat gradient arena."""
+        self.clip = float(max_norm or 0.0)
+        self.hyper[9:10].fill_(self.clip)
+
+    def set_cosine(self, t_max, eta_min=0.0):
+        """main.py:702-705: CosineAnnealingLR(opt, T_max=steps, eta_min=0); t_max = 0 switches the schedule off."""
+        self.hyper[13:14].fill_(float(t_max))
+        self.hyper[14:15].fill_(float(eta_min))
+
+    def enable_ema(self, decay=0.995):
+        """main.py:524-525,615: ExponentialMovingAverage(net.parameters(), decay) — the shadow copy is one more flat arena,
+        updated inside the Adam launch."""
+        if self.ema is None:
+            self.ema = self.eng.arena.clone()
+        self.hyper[15:16].fill_(float(decay))
+
     def apply(self):
-        """tick the device-side step counter (bias corrections) and update parameters + bf16 shadow in one pass."""
+        """tick the device-side step counter (bias corrections, lr, clip coefficient) and update parameters + bf16 shadow
+        (+ EMA) in one pass."""
         e = self.eng
         self.t += 1
+        if self.clip > 0:
+            call("sumsq", e.grad, self.hyper[10:11], e.total)
         call("adam_tick", self.hyper)
-        call("adam_step", e.arena, e.grad, self.m, self.v, e.shadow, e.total, self.hyper)
+        if self.ema is not None:
+            call("adam_step_ema", e.arena, e.grad, self.m, self.v, e.shadow, self.ema, e.total, self.hyper)
+        else:
+            call("adam_step", e.arena, e.grad, self.m, self.v, e.shadow, e.total, self.hyper)
         e.ext_shadow_fresh = True
+
+    # ---- checkpoint I/O in torch.optim.Adam's own format (main.py:593-596 loads it, :911 saves it as opt.th)
+    def _slices(self):
+        e = self.eng
+        for i, p in enumerate(e.params):
+            off = p.data_ptr() - e.arena.data_ptr()
+            assert off % 4 == 0
+            yield i, off // 4, p.numel(), p.shape
+
+    def state_dict(self):
+        step = int(self.hyper[8].item())
+        state = {}
+        if step > 0:
+            for i, off, n, shape in self._slices():
+                state[i] = {"step": torch.tensor(float(step)), "exp_avg": self.m[off:off + n].view(shape).clone(),
+                            "exp_avg_sq": self.v[off:off + n].view(shape).clone()}
+        group = {"lr": float(self.hyper[0].item()), "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "decoupled_weight_decay": False, "params": list(range(len(self.eng.params)))}
+        if float(self.hyper[13].item()) > 0:
+            group["initial_lr"] = float(self.hyper[12].item())
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        state = sd["state"]
+        step = 0
+        for i, off, n, shape in self._slices():
+            st = state.get(i, state.get(str(i)))
+            if st is None:
+                continue
+            self.m[off:off + n].copy_(st["exp_avg"].reshape(-1))
+            self.v[off:off + n].copy_(st["exp_avg_sq"].reshape(-1))
+            step = max(step, int(st["step"]))
+        self.t = step
+        self.hyper[8:9].fill_(float(step))
+        g = sd["param_groups"][0]
+        self.hyper[0:1].fill_(float(g["lr"]))
+        self.hyper[12:13].fill_(float(g.get("initial_lr", g["lr"])))
+
+    # ---- EMA access (torch_ema's copy_to / average_parameters, main.py:905-910)
+    def ema_state_dict(self):
+        """state_dict of the mapper with the EMA weights (what the reference writes to checkpoint_ema.th)."""
+        assert self.ema is not None, "EMA is not enabled"
+        e = self.eng
+        sd = {k: v.clone() for k, v in e.m.state_dict().items()}
+        for (name, _), (i, off, n, shape) in zip(e.m.named_parameters(), self._slices()):
+            sd[name] = self.ema[off:off + n].view(shape).clone()
+        return sd
+
+    def average_parameters(self):
+        """context manager: parameters temporarily replaced by their EMA (torch_ema.average_parameters)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def _ctx():
+            e = self.eng
+            keep = e.arena.clone()
+            e.arena.copy_(self.ema)
+            e.ext_shadow_fresh = False
+            e._shadow_version = None
+            try:
+                yield
+            finally:
+                e.arena.copy_(keep)
+                e.ext_shadow_fresh = False
+                e._shadow_version = None
+        return _ctx()
 
 
 class TrainStep:
     def __init__(self, net, vq, perceptor, cutn=8, lr=1e-3, cut_size=224, target_loss_coef=1.0, world_size=1,
-                 process_group=None, seed=0, l2_coef=0.0, tv_coef=0.0, diversity_coef=0.0, repeat=1, lpips_net=None):
+                 process_group=None, seed=0, l2_coef=0.0, tv_coef=0.0, diversity_coef=0.0, repeat=1, lpips_net=None,
+                 clip_grad_norm=None, scheduler=None, total_steps=0, use_ema=False, ema_decay=0.995):
         self.net, self.vq, self.perceptor = net, vq, perceptor
         self.mix = net.engine()
         self.dec = vq.engine()
@@ -69,6 +166,14 @@ class TrainStep:
         self.opt = FusedAdam(self.mix, lr=lr)
         self.world, self.pg = world_size, process_group
         self.opt.set_grad_scale(1.0 / world_size)
+        if clip_grad_norm:                                                 # main.py:693,833-834
+            self.opt.set_clip_grad_norm(clip_grad_norm)
+        if scheduler is not None:                                          # main.py:702-709
+            if scheduler != "cosine":
+                raise ValueError(scheduler)
+            self.opt.set_cosine(total_steps)
+        if use_ema:                                                        # main.py:510,524-525,843-844
+            self.opt.enable_ema(ema_decay)
         # data parallel: the flat gradient arena is all-reduced in buckets of `bucket_layers` mixer layers on a side stream
         # WHILE backward is still producing the earlier layers' gradients (the reference gets this from Horovod's hooks,
         # main.py:627); engines without per-layer completion callbacks fall back to one all-reduce after backward

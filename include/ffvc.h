@@ -46,6 +46,12 @@ int ffvc_arch(void);
 /* number of kernels this library has launched since the last reset (bench.py "gpu_launches"). */
 long long ffvc_launch_count(void);
 void ffvc_reset_launch_count(void);
+/* kernel-selection switches (A/B measurement of alternative kernels for the same op; results are identical up to
+ * summation order).  Names: "ln_v2" (column-owning LayerNorm kernels), "pool_v2" (tiled cutout-pool backward).
+ * Initial values come from the environment variable FFVC_OPTS="name=0|1,...".  Returns the previous value, -1 if the
+ * name is unknown. */
+int ffvc_set_option(const char* name, int value);
+int ffvc_get_option(const char* name);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05.mma, TMEM accumulators, TMA operand staging).
@@ -195,13 +201,20 @@ int ffvc_conv3x3_cin3(const float* x, const float* w, void* y, int N, int H, int
  * dgrad of conv_out runs as a tcgen05 GEMM with K = 32. */
 int ffvc_im2col3x3_cin3(const float* x, void* col, int N, int H, int W, void* stream);
 
-/* fused Adam (torch.optim.Adam semantics, main.py:591,835) over a flat fp32 arena; refreshes the bf16 shadow. */
-/* hyper_dev: DEVICE float[16] = {lr, beta1, beta2, eps, 1-beta1^t, sqrt(1-beta2^t), grad_scale, weight_decay, t, ...}
- * (device-resident so a captured CUDA graph sees each step's values).  ffvc_adam_tick increments t and refreshes
- * the two bias-correction slots on the device. */
+/* fused optimizer step over a flat fp32 arena: torch.optim.Adam (main.py:591,835) + optional clip_grad_norm_
+ * (main.py:693,833-834) + optional CosineAnnealingLR (main.py:702-705,836-837) + optional torch_ema update
+ * (main.py:524-525,843-844); refreshes the bf16 shadow the GEMMs read.
+ * hyper_dev: DEVICE float[16] (device-resident so a captured CUDA graph sees each step's values):
+ *   [0] lr of this step  [1] beta1  [2] beta2  [3] eps  [4] 1-beta1^t  [5] sqrt(1-beta2^t)  [6] grad_scale (1/world)
+ *   [7] weight_decay  [8] t  [9] clip max_norm (0 = off)  [10] sum g^2 (caller: ffvc_sumsq(grad, hyper+10) before the tick)
+ *   [11] clip coefficient (written by the tick)  [12] base lr  [13] cosine T_max (0 = constant lr)  [14] cosine eta_min
+ *   [15] EMA decay (0 = off)
+ * ffvc_adam_tick increments t and refreshes slots 4, 5, (0), (11) on the device; ffvc_adam_step[_ema] applies the update. */
 int ffvc_adam_tick(float* hyper_dev, void* stream);
 int ffvc_adam_step(float* p, const float* g, float* m, float* v, void* shadow_bf16, long long n, const float* hyper_dev,
                    void* stream);
+int ffvc_adam_step_ema(float* p, const float* g, float* m, float* v, void* shadow_bf16, float* ema, long long n,
+                       const float* hyper_dev, void* stream);
 
 /* CLIP ViT multi-head attention for short sequences (T <= 64, head_dim 64); qkv [N][T][3W] bf16 (cloob.py:198-200). */
 int ffvc_mha_small_fwd(const void* qkv, void* out, int N, int T, int heads, int head_dim, float scale, void* stream);

@@ -80,3 +80,41 @@ def test_vitgan_state_dict_contract_and_seeded_init_match_reference_golden():
     assert gold["count_32x1024"] == 415078530
     assert shapes["Transformer_Encoder.blocks.0.attn.to_qkv.weight"] == (3060, 1024)
     assert shapes["Transformer_Encoder.blocks.0.attn.w_out.weight"] == (1024, 1020)
+
+
+def test_option_switches_and_env_override():
+    lib = _lib.load()
+    assert lib.ffvc_get_option(b"no_such_option") == -1
+    for name in (b"ln_v2", b"pool_v2"):
+        old = lib.ffvc_get_option(name)
+        assert old in (0, 1)
+        assert lib.ffvc_set_option(name, 1 - old) == old and lib.ffvc_get_option(name) == 1 - old
+        lib.ffvc_set_option(name, old)
+
+
+def test_fused_adam_state_dict_is_torch_adam_compatible():
+    """opt.th (main.py:593-596,911) round trip: torch.optim.Adam loads FusedAdam's dict and vice versa (host logic only)."""
+    from types import SimpleNamespace
+    from feed_forward_vqgan_clip_b200.train_step import FusedAdam
+    a, b = torch.nn.Parameter(torch.randn(2, 4)), torch.nn.Parameter(torch.randn(8))
+    arena = torch.zeros(16)
+    arena[:8], arena[8:] = a.data.view(-1), b.data
+    a.data, b.data = arena[:8].view(2, 4), arena[8:]
+    eng = SimpleNamespace(arena=arena, grad=torch.zeros(16), shadow=None, total=16, dev=torch.device("cpu"), params=[a, b])
+    opt = FusedAdam(eng, lr=3e-4)
+    assert opt.state_dict()["state"] == {}                        # like a fresh torch optimizer
+    opt.m.normal_()
+    opt.v.uniform_()
+    opt.hyper[8] = 3
+    sd = opt.state_dict()
+    assert sd["state"][0]["exp_avg"].shape == (2, 4) and sd["state"][1]["exp_avg_sq"].shape == (8,)
+    t = torch.optim.Adam([torch.nn.Parameter(torch.zeros(2, 4)), torch.nn.Parameter(torch.zeros(8))])
+    t.load_state_dict(sd)
+    for q in t.param_groups[0]["params"]:
+        q.grad = torch.ones_like(q)
+    t.step()
+    assert int(t.state_dict()["state"][0]["step"]) == 4 and t.param_groups[0]["lr"] == pytest.approx(3e-4)
+    opt2 = FusedAdam(eng)
+    opt2.load_state_dict(t.state_dict())
+    assert float(opt2.hyper[8]) == 4.0 and float(opt2.hyper[0]) == pytest.approx(3e-4)
+    assert torch.equal(opt2.m[:8].view(2, 4), t.state_dict()["state"][0]["exp_avg"])

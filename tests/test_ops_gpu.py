@@ -271,6 +271,53 @@ def test_adam_matches_torch():
     assert torch.equal(shadow, p.to(BF))
 
 
+@pytest.mark.parametrize("n", [10008, 10007])
+def test_optimizer_block_clip_cosine_ema(n):
+    """the reference's optimizer block (main.py:591,693,702-705,833-837,843-844): clip_grad_norm_ -> Adam -> cosine
+    scheduler -> torch_ema update, through FusedAdam's device-side scalars.  n % 4 == 0 takes the 16-byte kernel."""
+    from types import SimpleNamespace
+    from feed_forward_vqgan_clip_b200.train_step import FusedAdam
+    T_MAX, CLIP, DECAY, WORLD = 6, 0.7, 0.9, 2
+    p0 = rnd(n, seed=1, dtype=F32)
+    par = torch.nn.Parameter(p0.clone())
+    eng = SimpleNamespace(arena=par.data, grad=torch.zeros(n, device=DEV), shadow=torch.empty(n, device=DEV, dtype=BF),
+                          total=n, dev=torch.device(DEV), params=[par], ext_shadow_fresh=False, _shadow_version=None)
+    opt = FusedAdam(eng, lr=2e-3)
+    opt.set_grad_scale(1.0 / WORLD)
+    opt.set_clip_grad_norm(CLIP)
+    opt.set_cosine(T_MAX)
+    opt.enable_ema(DECAY)
+    ref = p0.clone().cpu().requires_grad_(True)
+    ropt = torch.optim.Adam([ref], lr=2e-3)
+    rsch = torch.optim.lr_scheduler.CosineAnnealingLR(ropt, T_max=T_MAX, eta_min=0)
+    ema, num_updates = ref.detach().clone(), 0
+    for step in range(1, 6):
+        g = rnd(n, seed=10 + step, dtype=F32) * (0.02 if step % 2 else 0.001)     # clipped on odd steps only
+        eng.grad.copy_(g)
+        opt.apply()
+        ref.grad = (g / WORLD).cpu()
+        torch.nn.utils.clip_grad_norm_([ref], CLIP)
+        ropt.step()
+        rsch.step()
+        num_updates += 1                                            # torch_ema.ExponentialMovingAverage.update
+        d = min(DECAY, (1 + num_updates) / (10 + num_updates))
+        ema.sub_((1.0 - d) * (ema - ref.detach()))
+        assert torch.allclose(par.data.cpu(), ref.detach(), rtol=2e-5, atol=2e-6), step
+        assert torch.allclose(opt.ema.cpu(), ema, rtol=2e-5, atol=2e-6), step
+    assert torch.equal(eng.shadow, par.data.to(BF))
+    # checkpoint round trip in torch.optim.Adam's own format (opt.th, main.py:593-596,911)
+    sd = opt.state_dict()
+    rsd = ropt.state_dict()
+    assert torch.allclose(sd["state"][0]["exp_avg"].cpu(), rsd["state"][0]["exp_avg"], rtol=1e-4, atol=1e-7)
+    assert torch.allclose(sd["state"][0]["exp_avg_sq"].cpu(), rsd["state"][0]["exp_avg_sq"], rtol=1e-4, atol=1e-9)
+    assert int(sd["state"][0]["step"]) == int(rsd["state"][0]["step"]) == 5
+    fresh = torch.optim.Adam([torch.nn.Parameter(p0.clone())], lr=2e-3)
+    fresh.load_state_dict(sd)                                       # torch accepts our dict
+    opt2 = FusedAdam(eng, lr=2e-3)
+    opt2.load_state_dict(rsd)                                       # and we accept torch's
+    assert torch.allclose(opt2.m.cpu(), rsd["state"][0]["exp_avg"]) and float(opt2.hyper[8]) == 5.0
+
+
 @pytest.mark.parametrize("N,T,Hh", [(6, 50, 12), (3, 64, 2), (2, 17, 3), (5, 1, 1), (2, 33, 4)])
 def test_mha_small_fwd_bwd(N, T, Hh):
     """tensor-core (mma.sync) attention for short sequences; every 16-row tile count and ragged tails"""
