@@ -86,6 +86,54 @@ __global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __rest
   }
 }
 
+// Same gather, laid out so that no 64-bit division is needed and the window geometry is shared by the 3 channels:
+// blockIdx.y = (image, input row), threads run along x.  (The flat form above spends most of its time in emulated
+// 64-bit div/mod: ~10 of them per element.)  Identical arithmetic per element.
+__global__ void __launch_bounds__(128) pool_bwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                            float* __restrict__ dx, int H, int W, int P) {
+  const int ix = blockIdx.x * 128 + threadIdx.x;
+  if (ix >= W) return;
+  const int b = blockIdx.y / H, iy = blockIdx.y - b * H;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  const int oy_lo = max(0, (iy * P) / H - 1), oy_hi = min(P - 1, ((iy + 1) * P + H - 1) / H);
+  const int ox_lo = max(0, (ix * P) / W - 1), ox_hi = min(P - 1, ((ix + 1) * P + W - 1) / W);
+  const float* xb = x + (long long)b * H * W * 3;
+  const int me = iy * W + ix;
+  for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    const int y0 = (oy * H) / P, y1 = ((oy + 1) * H + P - 1) / P;
+    if (iy < y0 || iy >= y1) continue;
+    for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+      const int x0 = (ox * W) / P, x1 = ((ox + 1) * W + P - 1) / P;
+      if (ix < x0 || ix >= x1) continue;
+      const float* gp = dy + (((long long)b * P + oy) * P + ox) * 3;
+      const float g0 = gp[0], g1 = gp[1], g2 = gp[2];
+      const int area = (y1 - y0) * (x1 - x0);
+      acc0 += 0.5f * g0 / area;
+      acc1 += 0.5f * g1 / area;
+      acc2 += 0.5f * g2 / area;
+      // arg max of the window per channel (first maximum in row-major order, like ATen's adaptive_max_pool2d)
+      float m0 = -FLT_MAX, m1 = -FLT_MAX, m2 = -FLT_MAX;
+      int p0 = y0 * W + x0, p1 = p0, p2 = p0;
+      for (int yy = y0; yy < y1; ++yy)
+        for (int xx = x0; xx < x1; ++xx) {
+          const int pos = yy * W + xx;
+          const float* xp = xb + (long long)pos * 3;
+          const float v0 = xp[0], v1 = xp[1], v2 = xp[2];
+          if (v0 > m0) { m0 = v0; p0 = pos; }
+          if (v1 > m1) { m1 = v1; p1 = pos; }
+          if (v2 > m2) { m2 = v2; p2 = pos; }
+        }
+      if (p0 == me) acc0 += 0.5f * g0;
+      if (p1 == me) acc1 += 0.5f * g1;
+      if (p2 == me) acc2 += 0.5f * g2;
+    }
+  }
+  float* o = dx + ((long long)b * H * W + me) * 3;
+  o[0] = acc0;
+  o[1] = acc1;
+  o[2] = acc2;
+}
+
 // ------------------------------------------------------------------------------ bilinear homography sampling
 struct Taps {
   int x0, y0, x1, y1;
@@ -333,7 +381,10 @@ extern "C" int ffvc_cutout_pool_fwd(const float* x, float* y, int B, int H, int 
   return FFVC_OK;
 }
 extern "C" int ffvc_cutout_pool_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int P, void* stream) {
-  pool_bwd_kernel<<<grid_for_c((long long)B * H * W * 3, 256), 256, 0, ST(stream)>>>(x, dy, dx, B, H, W, P);
+  if (option(OPT_POOL_V2) && (long long)B * H <= 65535 && (long long)(H > W ? H : W) * (P + 1) < (1LL << 30))
+    pool_bwd_rows_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)(B * H)), 128, 0, ST(stream)>>>(x, dy, dx, H, W, P);
+  else
+    pool_bwd_kernel<<<grid_for_c((long long)B * H * W * 3, 256), 256, 0, ST(stream)>>>(x, dy, dx, B, H, W, P);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

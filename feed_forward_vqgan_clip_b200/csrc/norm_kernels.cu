@@ -223,6 +223,204 @@ __global__ void __launch_bounds__(256, kWgrad ? 2 : 3) layernorm_bwd_kernel(cons
   }
 }
 
+// ------------------------------------------------------------------------------------ LayerNorm, column-owning form
+// A CTA has exactly D/8 threads; thread c owns columns [8c, 8c+8) of every row the CTA visits.  gamma / beta and the
+// per-column accumulators (dgamma, dbeta, column sums of dx) are then 8 registers each whatever D is (the warp-per-row
+// form above needs D/32 of them per lane: 64 accumulator registers at D = 1024, two CTAs per SM), and kRows rows are in
+// flight per iteration (kRows x 2-3 independent 16-byte loads per thread, issued before anything else).  Row statistics:
+// warp shuffles, then one shared-memory exchange between the CTA's warps per iteration (double-buffered, so ONE
+// __syncthreads per kRows rows).  The backward kernel can also emit, from the values it stores, the two bias gradients the
+// mixer needs from dx (mlp_mixer_pytorch.py:16-23): column sums (Linear bias) and per-token row sums (Conv1d bias) —
+// otherwise two more passes over the tensor.
+template <int kThreads, int kRows>
+__global__ void __launch_bounds__(kThreads) layernorm_fwd_cols_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                      const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta,
+                                                                      __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
+                                                                      float* __restrict__ rstd, long long rows, float eps) {
+  constexpr int D = kThreads * 8;
+  constexpr int NW = kThreads / 32;
+  __shared__ float red[2][2][NW][kRows];     // [iteration parity][sum | centred sumsq][warp][row]
+  const int c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // parameter loads are issued first but only consumed after the first rows' reductions: the latencies overlap
+  const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
+  const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * c], b1 = reinterpret_cast<const float4*>(beta)[2 * c + 1];
+  const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  int it = 0;
+  for (long long r0 = (long long)blockIdx.x * kRows; r0 < rows; r0 += (long long)gridDim.x * kRows, it ^= 1) {
+    uint4 xp[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+      xp[r] = (r0 + r < rows) ? reinterpret_cast<const uint4*>(x + (r0 + r) * D)[c] : make_uint4(0u, 0u, 0u, 0u);
+    float v[kRows][8], mu[kRows], rs[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      unpack8(xp[r], v[r]);
+      float sacc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sacc += v[r][j];
+      sacc = warp_sum(sacc);
+      if (lane == 0) red[it][0][warp][r] = sacc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += red[it][0][w][r];
+      mu[r] = t * (1.0f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[r][j] - mu[r];
+        q += d * d;
+      }
+      q = warp_sum(q);
+      if (lane == 0) red[it][1][warp][r] = q;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += red[it][1][w][r];
+      rs[r] = rsqrtf(t * (1.0f / D) + eps);
+      if (r0 + r < rows) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[r][j] - mu[r]) * rs[r] * gam[j] + bet[j];
+        reinterpret_cast<uint4*>(y + (r0 + r) * D)[c] = pack8(o);
+        if (c == 0) {
+          if (mean) mean[r0 + r] = mu[r];
+          if (rstd) rstd[r0 + r] = rs[r];
+        }
+      }
+    }
+  }
+}
+
+template <int kThreads, int kRows, bool kWgrad>
+__global__ void __launch_bounds__(kThreads, 512 / kThreads) layernorm_bwd_cols_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ add,
+    __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum_out,
+    float* __restrict__ rowsum_out, int rowsum_T, long long rows) {
+  constexpr int D = kThreads * 8;
+  constexpr int NW = kThreads / 32;
+  __shared__ float red[2][NW][2 * kRows];
+  extern __shared__ float srow[];             // [rowsum_T] per-token partial sums of this CTA (only when rowsum_out)
+  const int c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (rowsum_out) {
+    for (int i = threadIdx.x; i < rowsum_T; i += kThreads) srow[i] = 0.f;
+    __syncthreads();
+  }
+  const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
+  const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  float ag[kWgrad ? 8 : 1], ab[kWgrad ? 8 : 1], ac[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ac[j] = 0.f;
+    if (kWgrad) ag[kWgrad ? j : 0] = ab[kWgrad ? j : 0] = 0.f;
+  }
+  int it = 0;
+  for (long long r0 = (long long)blockIdx.x * kRows; r0 < rows; r0 += (long long)gridDim.x * kRows, it ^= 1) {
+    uint4 xp[kRows], dp[kRows], ap[kRows];
+    float mu[kRows], rs[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const long long row = r0 + r;
+      const bool ok = row < rows;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      xp[r] = ok ? reinterpret_cast<const uint4*>(x + row * D)[c] : z;
+      dp[r] = ok ? reinterpret_cast<const uint4*>(dy + row * D)[c] : z;
+      ap[r] = (ok && add) ? reinterpret_cast<const uint4*>(add + row * D)[c] : z;
+      mu[r] = ok ? mean[row] : 0.f;
+      rs[r] = ok ? rstd[row] : 0.f;           // rstd = 0 makes a row past the end contribute exactly nothing
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      float xv[8], dv[8];
+      unpack8(xp[r], xv);
+      unpack8(dp[r], dv);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mu[r]) * rs[r];
+        const float g = dv[j] * gam[j];
+        s1 += g;
+        s2 += g * xh;
+        if (kWgrad) {
+          ag[kWgrad ? j : 0] += dv[j] * xh;
+          ab[kWgrad ? j : 0] += dv[j];
+        }
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) {
+        red[it][warp][2 * r] = s1;
+        red[it][warp][2 * r + 1] = s2;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        s1 += red[it][w][2 * r];
+        s2 += red[it][w][2 * r + 1];
+      }
+      s1 *= (1.0f / D);
+      s2 *= (1.0f / D);
+      float xv[8], dv[8], av[8], o[8];
+      unpack8(xp[r], xv);
+      unpack8(dp[r], dv);
+      unpack8(ap[r], av);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mu[r]) * rs[r];
+        o[j] = rs[r] * (dv[j] * gam[j] - s1 - xh * s2) + av[j];
+      }
+      const uint4 pk = pack8(o);
+      const bool ok = r0 + r < rows;
+      if (ok) reinterpret_cast<uint4*>(dx + (r0 + r) * D)[c] = pk;
+      if (colsum_out || rowsum_out) {         // sums of the values as stored (bf16-rounded), like a pass over dx would see
+        float q[8];
+        unpack8(pk, q);
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          ac[j] += q[j];
+          t += q[j];
+        }
+        if (rowsum_out) {
+          t = warp_sum(t);
+          if (lane == 0 && ok) atomicAdd(&srow[(int)((r0 + r) % rowsum_T)], t);
+        }
+      }
+    }
+  }
+  if (kWgrad) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&dgamma[8 * c + j], ag[kWgrad ? j : 0]);
+      atomicAdd(&dbeta[8 * c + j], ab[kWgrad ? j : 0]);
+    }
+  }
+  if (colsum_out) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&colsum_out[8 * c + j], ac[j]);
+  }
+  if (rowsum_out) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < rowsum_T; i += kThreads) {
+      const float t = srow[i];
+      if (t != 0.f) atomicAdd(&rowsum_out[i], t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ GroupNorm
 // Per-thread 8-channel partial sums (s, q) -> per-group sums in shared memory sm[0..G) / sm[G..2G).
 // Channels are first combined per group in registers, then lanes of the warp that own the same channel vector
@@ -784,17 +982,47 @@ groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bflo
 
 using namespace ffvc;
 
+template <int kThreads>
+static void ln_fwd_cols_launch(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean,
+                               float* rstd, long long rows, float eps, cudaStream_t st) {
+  constexpr int kRows = 4;
+  static int per_sm = 0;                       // resident CTAs per SM of this instantiation: the grid is one full wave
+  if (per_sm == 0) {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_fwd_cols_kernel<kThreads, kRows>, kThreads, 0);
+    per_sm = n > 0 ? n : 1;
+  }
+  const long long want = (rows + kRows - 1) / kRows;
+  const unsigned grid = (unsigned)(want < 148LL * per_sm ? want : 148LL * per_sm);
+  layernorm_fwd_cols_kernel<kThreads, kRows><<<grid, kThreads, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, eps);
+}
+static bool ln_cols_ok(int D, const void* a, const void* b, const void* c, const void* d) {
+  const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                       reinterpret_cast<uintptr_t>(d);
+  return (D == 256 || D == 512 || D == 768 || D == 1024) && (al & 15) == 0;
+}
+
 extern "C" int ffvc_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean,
                                   float* rstd, long long rows, int D, float eps, void* stream) {
   if (D % 8 != 0 || D > 2048) return set_error(FFVC_ERR_ARG, "layernorm: D must be a multiple of 8 and <= 2048");
   if (rows <= 0) return FFVC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y);
+  if (option(OPT_LN_FWD_V2) && ln_cols_ok(D, x, y, gamma, beta)) {
+    switch (D) {
+      case 256: ln_fwd_cols_launch<32>(xb, gamma, beta, yb, mean, rstd, rows, eps, st); break;
+      case 512: ln_fwd_cols_launch<64>(xb, gamma, beta, yb, mean, rstd, rows, eps, st); break;
+      case 768: ln_fwd_cols_launch<96>(xb, gamma, beta, yb, mean, rstd, rows, eps, st); break;
+      default: ln_fwd_cols_launch<128>(xb, gamma, beta, yb, mean, rstd, rows, eps, st); break;
+    }
+    FFVC_CHECK_LAUNCH();
+    return FFVC_OK;
+  }
   const int wpb = 8;
   long long want = (rows + wpb - 1) / wpb;
   const unsigned grid = (unsigned)(want < 148 * 8 ? want : 148 * 8);      // resident warps loop over the rows
   const size_t smem = 2 * (size_t)D * sizeof(float);
-  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
-  auto yb = reinterpret_cast<__nv_bfloat16*>(y);
   if (D <= 1024)
     layernorm_fwd_kernel<4><<<grid, wpb * 32, smem, st>>>(xb, gamma, beta, yb, mean, rstd, rows, D, eps);
   else
@@ -827,6 +1055,67 @@ extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* ga
     else layernorm_bwd_kernel<8, false><<<grid, wpb * 32, smem, st>>>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, rows, D);
   }
   FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+template <int kThreads>
+static void ln_bwd_cols_launch(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
+                               const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx, float* dgamma, float* dbeta,
+                               float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, cudaStream_t st) {
+  constexpr int kRows = 4;
+  const size_t smem = rowsum_out ? (size_t)rowsum_T * sizeof(float) : 0;
+  static int per_sm_w = 0, per_sm_n = 0;       // resident CTAs per SM (wgrad / no-wgrad form): the grid is one full wave
+  if (per_sm_w == 0) {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_cols_kernel<kThreads, kRows, true>, kThreads, 4096);
+    per_sm_w = n > 0 ? n : 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_cols_kernel<kThreads, kRows, false>, kThreads, 4096);
+    per_sm_n = n > 0 ? n : 1;
+  }
+  const int per_sm = dgamma ? per_sm_w : per_sm_n;
+  const long long want = (rows + kRows - 1) / kRows;
+  const unsigned grid = (unsigned)(want < 148LL * per_sm ? want : 148LL * per_sm);
+  if (dgamma)
+    layernorm_bwd_cols_kernel<kThreads, kRows, true><<<grid, kThreads, smem, st>>>(dy, x, gamma, mean, rstd, add, dx, dgamma,
+                                                                                  dbeta, colsum_out, rowsum_out, rowsum_T, rows);
+  else
+    layernorm_bwd_cols_kernel<kThreads, kRows, false><<<grid, kThreads, smem, st>>>(dy, x, gamma, mean, rstd, add, dx, dgamma,
+                                                                                   dbeta, colsum_out, rowsum_out, rowsum_T, rows);
+}
+
+// LayerNorm backward that also accumulates bias gradients taken from its own output:
+//   colsum_out[d] += sum_rows dx[row][d]           (optional)
+//   rowsum_out[t] += sum_{row % T == t, d} dx[row][d]   (optional; rows = B*T token-major)
+// One fused kernel when the column-owning form applies (D in {256,512,768,1024}, option "ln_bwd_v2"), otherwise the
+// warp-per-row kernel followed by ffvc_colsum / ffvc_rowsum over dx.
+extern "C" int ffvc_layernorm_bwd_sums(const void* dy, const void* x, const float* gamma, const float* mean,
+                                       const float* rstd, const void* add, void* dx, float* dgamma, float* dbeta,
+                                       float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, int D,
+                                       void* stream) {
+  if (D % 8 != 0 || D > 2048) return set_error(FFVC_ERR_ARG, "layernorm: D must be a multiple of 8 and <= 2048");
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return set_error(FFVC_ERR_ARG, "layernorm_bwd: dgamma/dbeta both or none");
+  if (rowsum_out && (rowsum_T <= 0 || rows % rowsum_T != 0 || rowsum_T > 8192))
+    return set_error(FFVC_ERR_ARG, "layernorm_bwd_sums: rows must be a multiple of rowsum_T (<= 8192)");
+  if (rows <= 0) return FFVC_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (option(OPT_LN_BWD_V2) && ln_cols_ok(D, dy, x, dx, add) && ln_cols_ok(D, gamma, nullptr, nullptr, nullptr)) {
+    auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+    auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+    auto ab = reinterpret_cast<const __nv_bfloat16*>(add);
+    auto dxb = reinterpret_cast<__nv_bfloat16*>(dx);
+    switch (D) {
+      case 256: ln_bwd_cols_launch<32>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st); break;
+      case 512: ln_bwd_cols_launch<64>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st); break;
+      case 768: ln_bwd_cols_launch<96>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st); break;
+      default: ln_bwd_cols_launch<128>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st); break;
+    }
+    FFVC_CHECK_LAUNCH();
+    return FFVC_OK;
+  }
+  int rc = ffvc_layernorm_bwd(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, rows, D, stream);
+  if (rc) return rc;
+  if (colsum_out && (rc = ffvc_colsum(dx, colsum_out, rows, D, stream))) return rc;
+  if (rowsum_out && (rc = ffvc_rowsum(dx, rowsum_out, (int)(rows / rowsum_T), rowsum_T, D, stream))) return rc;
   return FFVC_OK;
 }
 

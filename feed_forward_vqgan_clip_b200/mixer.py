@@ -242,14 +242,16 @@ class MixerEngine:
         ops.linear_dgrad(dzb, self.w("final_proj.weight"), dnf, R, C, D)
         q = "mixer.%d." % (L + 2)
         dH = new(R, D)
-        call("layernorm_bwd", dnf, sv["HL"], self.wf(q + "weight"), sv["muf"], sv["rsf"], None, dH,
-             self.g(q + "weight"), self.g(q + "bias"), R, D)
+        # every LayerNorm backward also emits the bias gradient that is a plain sum of its output dx (one fused pass):
+        # column sums -> bias of the Linear whose output gradient dx is; per-token row sums -> bias of the token-mixing Conv1d
+        call("layernorm_bwd_sums", dnf, sv["HL"], self.wf(q + "weight"), sv["muf"], sv["rsf"], None, dH,
+             self.g(q + "weight"), self.g(q + "bias"), self.g("mixer.%d.1.fn.3.bias" % (L + 1)), None, 0, R, D)
         for i in range(L + 1, 1, -1):
             p = "mixer.%d." % i
             lv = sv["layers"][i - 2]
             # ---- channel mixing
             ops.linear_wgrad(dH, lv["G2"], self.g(p + "1.fn.3.weight"), R, D, 4 * D, splits=sp(D, 4 * D, R))
-            call("colsum", dH, self.g(p + "1.fn.3.bias"), R, D)
+            # (bias gradient of 1.fn.3 = colsum(dH): emitted by the LayerNorm backward that produced dH)
             dU2 = new(R, 4 * D)
             ops.linear_dgrad(dH, self.w(p + "1.fn.3.weight"), dU2, R, D, 4 * D, aux=lv["U2"], mul_mode=ops.ACT_GELU)
             ops.linear_wgrad(dU2, lv["n2"], self.g(p + "1.fn.0.weight"), R, 4 * D, D, splits=sp(4 * D, D, R))
@@ -258,13 +260,12 @@ class MixerEngine:
             ops.linear_dgrad(dU2, self.w(p + "1.fn.0.weight"), dn2, R, 4 * D, D)
             del dU2
             dHb = new(R, D)
-            call("layernorm_bwd", dn2, lv["Hb"], self.wf(p + "1.norm.weight"), lv["mu2"], lv["rs2"], dH, dHb,
-                 self.g(p + "1.norm.weight"), self.g(p + "1.norm.bias"), R, D)
+            call("layernorm_bwd_sums", dn2, lv["Hb"], self.wf(p + "1.norm.weight"), lv["mu2"], lv["rs2"], dH, dHb,
+                 self.g(p + "1.norm.weight"), self.g(p + "1.norm.bias"), None, self.g(p + "0.fn.3.bias"), T, R, D)
             # ---- token mixing:  Hb[b] = Wt2 . G1[b] + bt2 + Ha[b]
             seg_splits = sp(T, 4 * T, B * D)
             ops.gemm(dHb, lv["G1"], self.g(p + "0.fn.3.weight"), T, 4 * T, D, a_role=ops.ROLE_SEG, a_bs=T * D,
                      b_role=ops.ROLE_SEG, b_bs=4 * T * D, k_segs=B, splits=seg_splits, atomic=True)
-            call("rowsum", dHb, self.g(p + "0.fn.3.bias"), B, T, D)
             dU1 = new(B, 4 * T, D)
             ops.gemm(self.w(p + "0.fn.3.weight"), dHb, dU1, 4 * T, D, T, a_mode=ops.MNMAJOR, a_ld=4 * T,
                      b_mode=ops.MNMAJOR, b_ld=D, b_role=ops.ROLE_OUT, b_bs=T * D, batch=B, out_bs=4 * T * D,
@@ -277,14 +278,14 @@ class MixerEngine:
                      b_mode=ops.MNMAJOR, b_ld=D, b_role=ops.ROLE_OUT, b_bs=4 * T * D, batch=B, out_bs=T * D)
             del dU1
             dHa = new(R, D)
-            call("layernorm_bwd", dn1, lv["Ha"], self.wf(p + "0.norm.weight"), lv["mu1"], lv["rs1"], dHb, dHa,
-                 self.g(p + "0.norm.weight"), self.g(p + "0.norm.bias"), R, D)
+            nxt = "mixer.%d.1.fn.3.bias" % (i - 1) if i > 2 else "mixer.1.bias"     # the Linear whose output gradient dHa is
+            call("layernorm_bwd_sums", dn1, lv["Ha"], self.wf(p + "0.norm.weight"), lv["mu1"], lv["rs1"], dHb, dHa,
+                 self.g(p + "0.norm.weight"), self.g(p + "0.norm.bias"), self.g(nxt), None, 0, R, D)
             dH = dHa
             if on_layer_done is not None:
                 on_layer_done(i - 2)
         # mixer.1 (Linear C -> D)
         ops.linear_wgrad(dH, sv["tok"], self.g("mixer.1.weight"), R, D, C, splits=sp(D, C, R))
-        call("colsum", dH, self.g("mixer.1.bias"), R, D)
         dtok = new(R, C)
         ops.linear_dgrad(dH, self.w("mixer.1.weight"), dtok, R, D, C)
         dP = new(B, C * T)

@@ -52,7 +52,9 @@ def bf16_round_sd(sd):
 # ----------------------------------------------------------------------------------------------------- mixer
 @pytest.mark.parametrize("cfg,B", [(dict(input_dim=64, image_size=16, channels=64, patch_size=1, dim=128, depth=2), 3),
                                    (dict(input_dim=512, image_size=16, channels=256, patch_size=1, dim=256, depth=1), 2)])
-def test_mixer_forward_backward_vs_oracle(cfg, B):
+@pytest.mark.parametrize("ln_v2", [0, 1])
+def test_mixer_forward_backward_vs_oracle(cfg, B, ln_v2, ffvc_options):
+    ffvc_options(ln_fwd_v2=ln_v2, ln_bwd_v2=ln_v2)       # dim 256 takes the column-owning LayerNorm kernels when on
     torch.manual_seed(0)
     net = Mixer(**cfg)
     with torch.no_grad():

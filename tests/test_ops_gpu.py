@@ -27,8 +27,13 @@ def close(out, ref, tol=2e-2):
     assert err <= tol * scale, "max err %g vs scale %g" % (err, scale)
 
 
-@pytest.mark.parametrize("rows,D", [(1000, 1024), (77, 768), (4096, 128)])
-def test_layernorm_fwd_bwd(rows, D):
+@pytest.mark.parametrize("v2", [0, 1])
+@pytest.mark.parametrize("rows,D,T", [(1000, 1024, 250), (77, 768, 11), (4096, 128, 256), (1030, 256, 103), (6, 512, 3),
+                                      (16384, 1024, 256), (3, 1024, 1)])
+def test_layernorm_fwd_bwd(rows, D, T, v2, ffvc_options):
+    """v2 = 1: the column-owning kernels (D in {256, 512, 768, 1024}; other D fall back to the warp-per-row form), including
+    ragged row counts (rows % 4 != 0) and the fused bias-gradient sums of dx."""
+    ffvc_options(ln_fwd_v2=v2, ln_bwd_v2=v2)
     x, dy = rnd(rows, D, seed=1), rnd(rows, D, seed=2)
     add = rnd(rows, D, seed=3)
     gamma = 1 + 0.1 * torch.randn(D, device=DEV)
@@ -40,6 +45,8 @@ def test_layernorm_fwd_bwd(rows, D):
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     yr = F.layer_norm(xr, (D,), gr, br, 1e-5)
     close(y, yr)
+    assert torch.allclose(mean, x.float().mean(1), atol=1e-4)
+    assert torch.allclose(rstd, (x.float().var(1, unbiased=False) + 1e-5).rsqrt(), rtol=1e-3)
     yr.backward(dy.float())
     dx = torch.empty_like(x)
     dg, db = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
@@ -50,6 +57,25 @@ def test_layernorm_fwd_bwd(rows, D):
     dx2 = torch.empty_like(x)
     call("layernorm_bwd", dy, x, gamma, mean, rstd, None, dx2, None, None, rows, D)
     close(dx2, xr.grad)
+    # the fused form: same dx / dgamma / dbeta, plus column sums and per-token row sums of the dx it stored
+    for with_w, with_add, with_col, with_row in [(1, 1, 1, 1), (1, 1, 1, 0), (1, 0, 0, 1), (0, 1, 1, 1), (0, 0, 0, 0)]:
+        dx3 = torch.empty_like(x)
+        dg3, db3 = 0.5 + torch.zeros(D, device=DEV), 0.25 + torch.zeros(D, device=DEV)     # accumulate semantics
+        cs, rsum = 2.0 + torch.zeros(D, device=DEV), 3.0 + torch.zeros(T, device=DEV)
+        call("layernorm_bwd_sums", dy, x, gamma, mean, rstd, add if with_add else None, dx3, dg3 if with_w else None,
+             db3 if with_w else None, cs if with_col else None, rsum if with_row else None, T, rows, D)
+        close(dx3, xr.grad + (add.float() if with_add else 0))
+        if with_w:
+            close(dg3 - 0.5, gr.grad, 1e-2)
+            close(db3 - 0.25, br.grad, 1e-2)
+        ref_cs = dx3.float().sum(0)
+        ref_rs = dx3.float().view(rows // T, T, D).sum((0, 2))
+        tol = 1e-3 * dx3.float().abs().sum(0).max().item() + 1e-3
+        if with_col:
+            assert (cs - 2.0 - ref_cs).abs().max().item() <= tol
+        if with_row:
+            tol_r = 1e-3 * dx3.float().abs().view(rows // T, T, D).sum((0, 2)).max().item() + 1e-3
+            assert (rsum - 3.0 - ref_rs).abs().max().item() <= tol_r
 
 
 @pytest.mark.parametrize("N,HW,C,swish", [(2, 256, 512, 1), (3, 1024, 128, 1), (1, 4096, 64, 0), (2, 16384, 128, 1)])
@@ -356,9 +382,11 @@ def test_spherical_loss():
     close(demb.cpu(), e.grad, 1e-3)
 
 
-def test_cutouts_fwd_bwd_vs_oracle():
+@pytest.mark.parametrize("pool_v2", [0, 1])
+def test_cutouts_fwd_bwd_vs_oracle(pool_v2, ffvc_options):
     import oracle.cutouts as oc
     from feed_forward_vqgan_clip_b200.cutouts import CutoutEngine, sample_params, params_to_device
+    ffvc_options(pool_v2=pool_v2)
     B, H, cutn, P = 2, 256, 4, 224
     g = torch.Generator().manual_seed(5)
     x = torch.rand(B, 3, H, H, generator=g)
@@ -383,6 +411,24 @@ def test_cutouts_fwd_bwd_vs_oracle():
     err = (dimg - xr.grad).abs()
     scale = xr.grad.abs().max().item()
     assert (err > 3e-2 * scale).float().mean().item() < 1e-3, (err.max().item(), scale)
+
+
+@pytest.mark.parametrize("B,H,P", [(2, 256, 224), (3, 32, 224), (1, 512, 224), (2, 100, 37)])
+def test_cutout_pool_bwd_row_kernel_matches_flat_kernel_and_autograd(B, H, P, ffvc_options):
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(B, H, H, 3, generator=g).to(DEV)
+    dy = torch.randn(B, P, P, 3, generator=g).to(DEV)
+    outs = []
+    for v2 in (0, 1):
+        ffvc_options(pool_v2=v2)
+        dx = torch.full((B, H, H, 3), 7.0, device=DEV)
+        call("cutout_pool_bwd", x, dy, dx, B, H, H, P)
+        outs.append(dx)
+    assert torch.allclose(outs[0], outs[1], rtol=1e-6, atol=1e-7)       # same arithmetic per element
+    xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)          # main.py:218 on NCHW
+    yr = (F.adaptive_avg_pool2d(xr, P) + F.adaptive_max_pool2d(xr, P)) / 2
+    yr.backward(dy.permute(0, 3, 1, 2))
+    close(outs[1].permute(0, 3, 1, 2), xr.grad, 1e-5)
 
 
 def test_tv_loss_fwd_bwd_vs_reference_expression():
