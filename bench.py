@@ -74,6 +74,23 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def load_traffic():
+    """per-launch DRAM traffic of the tcgen05 GEMM family from the committed ncu launch list of one step
+    (tools/one_step.py under ncu --metrics ...dram__bytes_read.sum,dram__bytes_write.sum; tools/summarize_launches.py --json)."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if f.endswith("_traffic.json"):
+            best = os.path.join(pdir, f)
+    if best is None:
+        return None, None
+    try:
+        d = json.load(open(best))
+        return d["gemm_family"]["dram_bytes_per_launch"], "profiles/" + os.path.basename(best)
+    except Exception:
+        return None, None
+
+
 def flops_per_prompt():
     """SURVEY App. B formulas, config #2 (S=16, D=1024, L=32, cutn=8)."""
     T, C, D, L = 256, 256, 1024, 32
@@ -308,8 +325,10 @@ def main():
             gemm_flops = sum(fl)
             achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
             peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+            traffic, traffic_src = load_traffic()
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel + conv3x3_halo_kernel (tcgen05 GEMM family)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src + " (sustained cuBLAS bf16)",
+                    "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (read + write), mean over the family's launches of one step",
+                    "traffic_source": traffic_src, "flops_per_launch": gemm_flops / max(1, len(ev)), "peak_source": peak_src + " (sustained cuBLAS bf16)",
                     "launches_per_step": len(ev), "gemm_ms_per_step": gemm_ms, "eager_step_ms": s_all.elapsed_time(e_all),
                     "gemm_share_of_step": gemm_ms / ms_per_step, "flops_per_step_executed": gemm_flops,
                     "how": "CUDA events around every ffvc_gemm / ffvc_conv3x3_halo launch of one eager step; share = their time / graph step time"}
