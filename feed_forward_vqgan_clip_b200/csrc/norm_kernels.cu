@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_fwd_cols_kernel(const __nv
 }
 
 template <int kThreads, int kRows, bool kWgrad>
-__global__ void __launch_bounds__(kThreads, 512 / kThreads) layernorm_bwd_cols_kernel(
+__global__ void __launch_bounds__(kThreads, (kRows >= 4 ? 512 : 640) / kThreads) layernorm_bwd_cols_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ add,
     __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum_out,
@@ -982,10 +982,9 @@ groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bflo
 
 using namespace ffvc;
 
-template <int kThreads>
-static void ln_fwd_cols_launch(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean,
-                               float* rstd, long long rows, float eps, cudaStream_t st) {
-  constexpr int kRows = 4;
+template <int kThreads, int kRows>
+static void ln_fwd_cols_launch_r(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean,
+                                 float* rstd, long long rows, float eps, cudaStream_t st) {
   static int per_sm = 0;                       // resident CTAs per SM of this instantiation: the grid is one full wave
   if (per_sm == 0) {
     int n = 0;
@@ -995,6 +994,13 @@ static void ln_fwd_cols_launch(const __nv_bfloat16* x, const float* gamma, const
   const long long want = (rows + kRows - 1) / kRows;
   const unsigned grid = (unsigned)(want < 148LL * per_sm ? want : 148LL * per_sm);
   layernorm_fwd_cols_kernel<kThreads, kRows><<<grid, kThreads, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, eps);
+}
+// option value 1: 4 rows in flight per CTA iteration, 2: 8 rows (more bytes in flight per thread, fewer resident CTAs)
+template <int kThreads>
+static void ln_fwd_cols_launch(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean,
+                               float* rstd, long long rows, float eps, cudaStream_t st) {
+  if (option(OPT_LN_FWD_V2) == 2) ln_fwd_cols_launch_r<kThreads, 8>(x, gamma, beta, y, mean, rstd, rows, eps, st);
+  else ln_fwd_cols_launch_r<kThreads, 4>(x, gamma, beta, y, mean, rstd, rows, eps, st);
 }
 static bool ln_cols_ok(int D, const void* a, const void* b, const void* c, const void* d) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
@@ -1058,11 +1064,10 @@ extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* ga
   return FFVC_OK;
 }
 
-template <int kThreads>
-static void ln_bwd_cols_launch(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
-                               const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx, float* dgamma, float* dbeta,
-                               float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, cudaStream_t st) {
-  constexpr int kRows = 4;
+template <int kThreads, int kRows>
+static void ln_bwd_cols_launch_r(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
+                                 const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx, float* dgamma, float* dbeta,
+                                 float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, cudaStream_t st) {
   const size_t smem = rowsum_out ? (size_t)rowsum_T * sizeof(float) : 0;
   static int per_sm_w = 0, per_sm_n = 0;       // resident CTAs per SM (wgrad / no-wgrad form): the grid is one full wave
   if (per_sm_w == 0) {
@@ -1081,6 +1086,16 @@ static void ln_bwd_cols_launch(const __nv_bfloat16* dy, const __nv_bfloat16* x, 
   else
     layernorm_bwd_cols_kernel<kThreads, kRows, false><<<grid, kThreads, smem, st>>>(dy, x, gamma, mean, rstd, add, dx, dgamma,
                                                                                    dbeta, colsum_out, rowsum_out, rowsum_T, rows);
+}
+// option value 1: 4 rows in flight per CTA iteration (128 registers), 2: 2 rows (fewer registers, more resident CTAs)
+template <int kThreads>
+static void ln_bwd_cols_launch(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
+                               const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx, float* dgamma, float* dbeta,
+                               float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, cudaStream_t st) {
+  if (option(OPT_LN_BWD_V2) == 2)
+    ln_bwd_cols_launch_r<kThreads, 2>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st);
+  else
+    ln_bwd_cols_launch_r<kThreads, 4>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st);
 }
 
 // LayerNorm backward that also accumulates bias gradients taken from its own output:

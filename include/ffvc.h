@@ -47,7 +47,8 @@ int ffvc_arch(void);
 long long ffvc_launch_count(void);
 void ffvc_reset_launch_count(void);
 /* kernel-selection switches (A/B measurement of alternative kernels for the same op; results are identical up to
- * summation order).  Names: "ln_fwd_v2" / "ln_bwd_v2" (column-owning LayerNorm kernels), "pool_v2" (tiled cutout-pool backward).
+ * summation order).  Names: "ln_fwd_v2" / "ln_bwd_v2" (column-owning LayerNorm kernels; 1 = 4 rows in flight per CTA, 2 = 8 rows fwd / 2 rows bwd),
+ * "pool_v2" (row-mapped cutout-pool backward).
  * Initial values come from the environment variable FFVC_OPTS="name=0|1,...".  Returns the previous value, -1 if the
  * name is unknown. */
 int ffvc_set_option(const char* name, int value);

@@ -27,11 +27,11 @@ def close(out, ref, tol=2e-2):
     assert err <= tol * scale, "max err %g vs scale %g" % (err, scale)
 
 
-@pytest.mark.parametrize("v2", [0, 1])
+@pytest.mark.parametrize("v2", [0, 1, 2])
 @pytest.mark.parametrize("rows,D,T", [(1000, 1024, 250), (77, 768, 11), (4096, 128, 256), (1030, 256, 103), (6, 512, 3),
                                       (16384, 1024, 256), (3, 1024, 1)])
 def test_layernorm_fwd_bwd(rows, D, T, v2, ffvc_options):
-    """v2 = 1: the column-owning kernels (D in {256, 512, 768, 1024}; other D fall back to the warp-per-row form), including
+    """v2 = 1 / 2: the column-owning kernels with 4 / 8 (fwd) and 4 / 2 (bwd) rows in flight (D in {256, 512, 768, 1024}; other D fall back to the warp-per-row form), including
     ragged row counts (rows % 4 != 0) and the fused bias-gradient sums of dx."""
     ffvc_options(ln_fwd_v2=v2, ln_bwd_v2=v2)
     x, dy = rnd(rows, D, seed=1), rnd(rows, D, seed=2)

@@ -75,7 +75,7 @@ def main():
 
     for i in range(NSETS):
         ln_fwd(i)
-    for v2 in (0, 1):
+    for v2 in (0, 1, 2):
         setopt(ln_fwd_v2=v2, ln_bwd_v2=v2)
         t = timeit(ln_fwd)
         out["layernorm_fwd 16384x1024 v2=%d" % v2] = {"us": t, "GBps": 2 * tensor_bytes / t / 1e3}
@@ -106,7 +106,7 @@ def main():
 
     for i in range(NSETS):
         ln2_fwd(i)
-    for v2 in (0, 1):
+    for v2 in (0, 1, 2):
         setopt(ln_fwd_v2=v2, ln_bwd_v2=v2)
         t = timeit(ln2_fwd)
         out["layernorm_fwd 25600x768 v2=%d" % v2] = {"us": t, "GBps": 2 * rows2 * D2 * 2 / t / 1e3}

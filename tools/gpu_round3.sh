@@ -12,8 +12,8 @@ for f in test_ops_gpu test_models_gpu test_gemm_gpu; do
 done
 timeout -k 10 240 python tools/ab_kernels.py > gpurun_out/ab_kernels.json 2> gpurun_out/ab_kernels.err; echo "== ab_kernels rc=$?"; cat gpurun_out/ab_kernels.json | tr -d '\n' | cut -c1-3000; echo; tail -3 gpurun_out/ab_kernels.err
 FFVC_OPTS=$ON timeout -k 10 400 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_on.json 2> gpurun_out/bench_on.err; echo "== bench ON rc=$?"; cut -c1-700 gpurun_out/bench_on.json; tail -3 gpurun_out/bench_on.err
-timeout -k 10 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_off.json 2> gpurun_out/bench_off.err; echo "== bench OFF rc=$?"; cut -c1-400 gpurun_out/bench_off.json; tail -3 gpurun_out/bench_off.err
 FFVC_OPTS=$ON timeout -k 10 400 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
    --clock-control none --csv --log-file gpurun_out/launches_on.csv python tools/one_step.py > gpurun_out/one_step.log 2>&1
 echo "== ncu rc=$? lines=$(wc -l < gpurun_out/launches_on.csv) $(tail -1 gpurun_out/one_step.log)"
+timeout -k 10 400 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_off.json 2> gpurun_out/bench_off.err; echo "== bench OFF rc=$?"; cut -c1-400 gpurun_out/bench_off.json; tail -3 gpurun_out/bench_off.err
 FFVC_OPTS=$ON timeout -k 10 300 python tools/prof_step.py --out gpurun_out/step_breakdown_on.md > gpurun_out/prof_step.log 2>&1; echo "== prof_step rc=$?"
