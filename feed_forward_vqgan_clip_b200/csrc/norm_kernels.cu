@@ -223,40 +223,66 @@ __global__ void __launch_bounds__(256, kWgrad ? 2 : 3) layernorm_bwd_kernel(cons
   }
 }
 
-// ------------------------------------------------------------------------------------ LayerNorm, column-owning form
+// ------------------------------------------------------------------------------------ LayerNorm, column-owning pipelined form
 // A CTA has exactly D/8 threads; thread c owns columns [8c, 8c+8) of every row the CTA visits.  gamma / beta and the
 // per-column accumulators (dgamma, dbeta, column sums of dx) are then 8 registers each whatever D is (the warp-per-row
-// form above needs D/32 of them per lane: 64 accumulator registers at D = 1024, two CTAs per SM), and kRows rows are in
-// flight per iteration (kRows x 2-3 independent 16-byte loads per thread, issued before anything else).  Row statistics:
-// warp shuffles, then one shared-memory exchange between the CTA's warps per iteration (double-buffered, so ONE
-// __syncthreads per kRows rows).  The backward kernel can also emit, from the values it stores, the two bias gradients the
-// mixer needs from dx (mlp_mixer_pytorch.py:16-23): column sums (Linear bias) and per-token row sums (Conv1d bias) —
-// otherwise two more passes over the tensor.
-template <int kThreads, int kRows>
-__global__ void __launch_bounds__(kThreads) layernorm_fwd_cols_kernel(const __nv_bfloat16* __restrict__ x,
+// form above needs D/32 of them per lane: 64 accumulator registers at D = 1024, two CTAs per SM).  Rows travel through a
+// cp.async ring in shared memory: each thread copies ITS OWN 16-byte column slice of kRows rows per stage and is the only
+// reader of it, so a stage needs cp.async.wait_group but no barrier, the loads of the next kStages-1 row groups are in
+// flight while the current one is reduced, and nothing in flight occupies registers.  (A first version kept the rows in
+// registers: under the 128-register cap ptxas serialised the loads between the shuffles — 79 us against 60 us for the
+// warp-per-row kernel + separate sum kernels, profiles/r01_ab_kernels.md.)  Row statistics: warp shuffles, then one
+// shared-memory exchange between the CTA's warps per row group (double-buffered: ONE __syncthreads per group).
+// The backward kernel can also emit, from the values it stores, the two bias gradients the mixer takes from dx
+// (mlp_mixer_pytorch.py:16-23): column sums (Linear bias) and per-token row sums (Conv1d bias) — otherwise two more passes.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? 16 : 0;                  // src-size 0: nothing is read, the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int kThreads, int kRows, int kStages>
+__global__ void __launch_bounds__(kThreads) layernorm_fwd_pipe_kernel(const __nv_bfloat16* __restrict__ x,
                                                                       const float* __restrict__ gamma,
                                                                       const float* __restrict__ beta,
                                                                       __nv_bfloat16* __restrict__ y, float* __restrict__ mean,
                                                                       float* __restrict__ rstd, long long rows, float eps) {
   constexpr int D = kThreads * 8;
   constexpr int NW = kThreads / 32;
-  __shared__ float red[2][2][NW][kRows];     // [iteration parity][sum | centred sumsq][warp][row]
+  extern __shared__ __align__(16) unsigned char ln_smem[];
+  uint4* stage = reinterpret_cast<uint4*>(ln_smem);          // [kStages][kRows][kThreads]
+  __shared__ float red[2][2][NW][kRows];                      // [group parity][sum | centred sumsq][warp][row]
   const int c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // parameter loads are issued first but only consumed after the first rows' reductions: the latencies overlap
+  const long long stride = (long long)gridDim.x * kRows;
+  long long rnext = (long long)blockIdx.x * kRows;
+  auto issue = [&](int s) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const long long row = rnext + r;
+      const bool ok = row < rows;
+      cp_async16(smem_u32(&stage[(s * kRows + r) * kThreads + c]), ok ? (const void*)(x + row * D + 8 * c) : (const void*)x, ok);
+    }
+    cp_async_commit();
+    rnext += stride;
+  };
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) issue(s);
   const float4 g0 = reinterpret_cast<const float4*>(gamma)[2 * c], g1 = reinterpret_cast<const float4*>(gamma)[2 * c + 1];
   const float4 b0 = reinterpret_cast<const float4*>(beta)[2 * c], b1 = reinterpret_cast<const float4*>(beta)[2 * c + 1];
   const float gam[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
   const float bet[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-  int it = 0;
-  for (long long r0 = (long long)blockIdx.x * kRows; r0 < rows; r0 += (long long)gridDim.x * kRows, it ^= 1) {
-    uint4 xp[kRows];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r)
-      xp[r] = (r0 + r < rows) ? reinterpret_cast<const uint4*>(x + (r0 + r) * D)[c] : make_uint4(0u, 0u, 0u, 0u);
-    float v[kRows][8], mu[kRows], rs[kRows];
+  int it = 0, cur = 0;
+  for (long long r0 = (long long)blockIdx.x * kRows; r0 < rows; r0 += stride, it ^= 1) {
+    issue(cur == 0 ? kStages - 1 : cur - 1);                  // refill the stage consumed by the previous group
+    cp_async_wait<kStages - 1>();                             // this thread's slice of the current stage has landed
+    float v[kRows][8], mu[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      unpack8(xp[r], v[r]);
+      unpack8(stage[(cur * kRows + r) * kThreads + c], v[r]);
       float sacc = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) sacc += v[r][j];
@@ -285,32 +311,53 @@ __global__ void __launch_bounds__(kThreads) layernorm_fwd_cols_kernel(const __nv
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < NW; ++w) t += red[it][1][w][r];
-      rs[r] = rsqrtf(t * (1.0f / D) + eps);
+      const float rs = rsqrtf(t * (1.0f / D) + eps);
       if (r0 + r < rows) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[r][j] - mu[r]) * rs[r] * gam[j] + bet[j];
+        for (int j = 0; j < 8; ++j) o[j] = (v[r][j] - mu[r]) * rs * gam[j] + bet[j];
         reinterpret_cast<uint4*>(y + (r0 + r) * D)[c] = pack8(o);
         if (c == 0) {
           if (mean) mean[r0 + r] = mu[r];
-          if (rstd) rstd[r0 + r] = rs[r];
+          if (rstd) rstd[r0 + r] = rs;
         }
       }
     }
+    cur = (cur + 1 == kStages) ? 0 : cur + 1;
   }
+  cp_async_wait<0>();
 }
 
-template <int kThreads, int kRows, bool kWgrad>
-__global__ void __launch_bounds__(kThreads, (kRows >= 4 ? 512 : 640) / kThreads) layernorm_bwd_cols_kernel(
+template <int kThreads, int kRows, int kStages, bool kWgrad>
+__global__ void __launch_bounds__(kThreads) layernorm_bwd_pipe_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ add,
     __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum_out,
     float* __restrict__ rowsum_out, int rowsum_T, long long rows) {
   constexpr int D = kThreads * 8;
   constexpr int NW = kThreads / 32;
+  extern __shared__ __align__(16) unsigned char ln_smem[];
+  uint4* stage = reinterpret_cast<uint4*>(ln_smem);                                   // [kStages][kRows][3: x, dy, add][kThreads]
+  float* srow = reinterpret_cast<float*>(ln_smem + (size_t)kStages * kRows * 3 * kThreads * 16);   // [rowsum_T]
   __shared__ float red[2][NW][2 * kRows];
-  extern __shared__ float srow[];             // [rowsum_T] per-token partial sums of this CTA (only when rowsum_out)
   const int c = threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long stride = (long long)gridDim.x * kRows;
+  long long rnext = (long long)blockIdx.x * kRows;
+  auto issue = [&](int s) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const long long row = rnext + r;
+      const bool ok = row < rows;
+      uint4* slot = &stage[((s * kRows + r) * 3) * kThreads + c];
+      cp_async16(smem_u32(slot), ok ? (const void*)(x + row * D + 8 * c) : (const void*)x, ok);
+      cp_async16(smem_u32(slot + kThreads), ok ? (const void*)(dy + row * D + 8 * c) : (const void*)dy, ok);
+      if (add) cp_async16(smem_u32(slot + 2 * kThreads), ok ? (const void*)(add + row * D + 8 * c) : (const void*)add, ok);
+    }
+    cp_async_commit();
+    rnext += stride;
+  };
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) issue(s);
   if (rowsum_out) {
     for (int i = threadIdx.x; i < rowsum_T; i += kThreads) srow[i] = 0.f;
     __syncthreads();
@@ -323,26 +370,34 @@ __global__ void __launch_bounds__(kThreads, (kRows >= 4 ? 512 : 640) / kThreads)
     ac[j] = 0.f;
     if (kWgrad) ag[kWgrad ? j : 0] = ab[kWgrad ? j : 0] = 0.f;
   }
-  int it = 0;
-  for (long long r0 = (long long)blockIdx.x * kRows; r0 < rows; r0 += (long long)gridDim.x * kRows, it ^= 1) {
-    uint4 xp[kRows], dp[kRows], ap[kRows];
+  // per-row statistics of the NEXT row group are fetched one group ahead (registers), like the ring hides the row loads
+  float mu_n[kRows], rs_n[kRows];
+  auto fetch_stats = [&](long long r0) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const bool ok = r0 + r < rows;
+      mu_n[r] = ok ? mean[r0 + r] : 0.f;
+      rs_n[r] = ok ? rstd[r0 + r] : 0.f;      // rstd = 0 (and zero-filled data) makes a row past the end contribute nothing
+    }
+  };
+  fetch_stats((long long)blockIdx.x * kRows);
+  int it = 0, cur = 0;
+  for (long long r0 = (long long)blockIdx.x * kRows; r0 < rows; r0 += stride, it ^= 1) {
+    issue(cur == 0 ? kStages - 1 : cur - 1);                  // refill the stage consumed by the previous group
     float mu[kRows], rs[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      const long long row = r0 + r;
-      const bool ok = row < rows;
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      xp[r] = ok ? reinterpret_cast<const uint4*>(x + row * D)[c] : z;
-      dp[r] = ok ? reinterpret_cast<const uint4*>(dy + row * D)[c] : z;
-      ap[r] = (ok && add) ? reinterpret_cast<const uint4*>(add + row * D)[c] : z;
-      mu[r] = ok ? mean[row] : 0.f;
-      rs[r] = ok ? rstd[row] : 0.f;           // rstd = 0 makes a row past the end contribute exactly nothing
+      mu[r] = mu_n[r];
+      rs[r] = rs_n[r];
     }
+    fetch_stats(r0 + stride);
+    cp_async_wait<kStages - 1>();                             // this thread's slices of the current stage have landed
+    const uint4* st = &stage[(cur * kRows * 3) * kThreads + c];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       float xv[8], dv[8];
-      unpack8(xp[r], xv);
-      unpack8(dp[r], dv);
+      unpack8(st[(r * 3) * kThreads], xv);
+      unpack8(st[(r * 3 + 1) * kThreads], dv);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -373,14 +428,19 @@ __global__ void __launch_bounds__(kThreads, (kRows >= 4 ? 512 : 640) / kThreads)
       }
       s1 *= (1.0f / D);
       s2 *= (1.0f / D);
-      float xv[8], dv[8], av[8], o[8];
-      unpack8(xp[r], xv);
-      unpack8(dp[r], dv);
-      unpack8(ap[r], av);
+      float xv[8], dv[8], o[8];
+      unpack8(st[(r * 3) * kThreads], xv);
+      unpack8(st[(r * 3 + 1) * kThreads], dv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = (xv[j] - mu[r]) * rs[r];
-        o[j] = rs[r] * (dv[j] * gam[j] - s1 - xh * s2) + av[j];
+        o[j] = rs[r] * (dv[j] * gam[j] - s1 - xh * s2);
+      }
+      if (add) {
+        float av[8];
+        unpack8(st[(r * 3 + 2) * kThreads], av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += av[j];
       }
       const uint4 pk = pack8(o);
       const bool ok = r0 + r < rows;
@@ -400,7 +460,9 @@ __global__ void __launch_bounds__(kThreads, (kRows >= 4 ? 512 : 640) / kThreads)
         }
       }
     }
+    cur = (cur + 1 == kStages) ? 0 : cur + 1;
   }
+  cp_async_wait<0>();
   if (kWgrad) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -982,25 +1044,27 @@ groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bflo
 
 using namespace ffvc;
 
-template <int kThreads, int kRows>
-static void ln_fwd_cols_launch_r(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean,
+template <int kThreads, int kRows, int kStages>
+static void ln_fwd_pipe_launch_r(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean,
                                  float* rstd, long long rows, float eps, cudaStream_t st) {
+  constexpr int kSmem = kStages * kRows * kThreads * 16;
   static int per_sm = 0;                       // resident CTAs per SM of this instantiation: the grid is one full wave
   if (per_sm == 0) {
+    cudaFuncSetAttribute(layernorm_fwd_pipe_kernel<kThreads, kRows, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_fwd_cols_kernel<kThreads, kRows>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_fwd_pipe_kernel<kThreads, kRows, kStages>, kThreads, kSmem);
     per_sm = n > 0 ? n : 1;
   }
   const long long want = (rows + kRows - 1) / kRows;
   const unsigned grid = (unsigned)(want < 148LL * per_sm ? want : 148LL * per_sm);
-  layernorm_fwd_cols_kernel<kThreads, kRows><<<grid, kThreads, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, eps);
+  layernorm_fwd_pipe_kernel<kThreads, kRows, kStages><<<grid, kThreads, kSmem, st>>>(x, gamma, beta, y, mean, rstd, rows, eps);
 }
-// option value 1: 4 rows in flight per CTA iteration, 2: 8 rows (more bytes in flight per thread, fewer resident CTAs)
+// option value 1: 8 rows per group, 2 stages;  2: 4 rows per group, 4 stages (same shared memory, finer-grained ring)
 template <int kThreads>
 static void ln_fwd_cols_launch(const __nv_bfloat16* x, const float* gamma, const float* beta, __nv_bfloat16* y, float* mean,
                                float* rstd, long long rows, float eps, cudaStream_t st) {
-  if (option(OPT_LN_FWD_V2) == 2) ln_fwd_cols_launch_r<kThreads, 8>(x, gamma, beta, y, mean, rstd, rows, eps, st);
-  else ln_fwd_cols_launch_r<kThreads, 4>(x, gamma, beta, y, mean, rstd, rows, eps, st);
+  if (option(OPT_LN_FWD_V2) == 2) ln_fwd_pipe_launch_r<kThreads, 4, 4>(x, gamma, beta, y, mean, rstd, rows, eps, st);
+  else ln_fwd_pipe_launch_r<kThreads, 8, 2>(x, gamma, beta, y, mean, rstd, rows, eps, st);
 }
 static bool ln_cols_ok(int D, const void* a, const void* b, const void* c, const void* d) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
@@ -1064,38 +1128,42 @@ extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* ga
   return FFVC_OK;
 }
 
-template <int kThreads, int kRows>
-static void ln_bwd_cols_launch_r(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
+template <int kThreads, int kRows, int kStages>
+static void ln_bwd_pipe_launch_r(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
                                  const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx, float* dgamma, float* dbeta,
                                  float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, cudaStream_t st) {
-  const size_t smem = rowsum_out ? (size_t)rowsum_T * sizeof(float) : 0;
+  constexpr int kRing = kStages * kRows * 3 * kThreads * 16;
+  constexpr int kMaxSmem = kRing + 2048 * 4;                 // ring + per-token sums (rowsum_T <= 2048)
   static int per_sm_w = 0, per_sm_n = 0;       // resident CTAs per SM (wgrad / no-wgrad form): the grid is one full wave
   if (per_sm_w == 0) {
+    cudaFuncSetAttribute(layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    cudaFuncSetAttribute(layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_cols_kernel<kThreads, kRows, true>, kThreads, 4096);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, true>, kThreads, kRing + 1024);
     per_sm_w = n > 0 ? n : 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_cols_kernel<kThreads, kRows, false>, kThreads, 4096);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, false>, kThreads, kRing + 1024);
     per_sm_n = n > 0 ? n : 1;
   }
+  const size_t smem = (size_t)kRing + (rowsum_out ? (size_t)rowsum_T * sizeof(float) : 0);
   const int per_sm = dgamma ? per_sm_w : per_sm_n;
   const long long want = (rows + kRows - 1) / kRows;
   const unsigned grid = (unsigned)(want < 148LL * per_sm ? want : 148LL * per_sm);
   if (dgamma)
-    layernorm_bwd_cols_kernel<kThreads, kRows, true><<<grid, kThreads, smem, st>>>(dy, x, gamma, mean, rstd, add, dx, dgamma,
-                                                                                  dbeta, colsum_out, rowsum_out, rowsum_T, rows);
+    layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, true><<<grid, kThreads, smem, st>>>(
+        dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows);
   else
-    layernorm_bwd_cols_kernel<kThreads, kRows, false><<<grid, kThreads, smem, st>>>(dy, x, gamma, mean, rstd, add, dx, dgamma,
-                                                                                   dbeta, colsum_out, rowsum_out, rowsum_T, rows);
+    layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, false><<<grid, kThreads, smem, st>>>(
+        dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows);
 }
-// option value 1: 4 rows in flight per CTA iteration (128 registers), 2: 2 rows (fewer registers, more resident CTAs)
+// option value 1: 4 rows per group, 2 stages;  2: 2 rows per group, 4 stages (same shared memory, finer-grained ring)
 template <int kThreads>
 static void ln_bwd_cols_launch(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
                                const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx, float* dgamma, float* dbeta,
                                float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, cudaStream_t st) {
   if (option(OPT_LN_BWD_V2) == 2)
-    ln_bwd_cols_launch_r<kThreads, 2>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st);
+    ln_bwd_pipe_launch_r<kThreads, 2, 4>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st);
   else
-    ln_bwd_cols_launch_r<kThreads, 4>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st);
+    ln_bwd_pipe_launch_r<kThreads, 4, 2>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st);
 }
 
 // LayerNorm backward that also accumulates bias gradients taken from its own output:
@@ -1109,11 +1177,12 @@ extern "C" int ffvc_layernorm_bwd_sums(const void* dy, const void* x, const floa
                                        void* stream) {
   if (D % 8 != 0 || D > 2048) return set_error(FFVC_ERR_ARG, "layernorm: D must be a multiple of 8 and <= 2048");
   if ((dgamma == nullptr) != (dbeta == nullptr)) return set_error(FFVC_ERR_ARG, "layernorm_bwd: dgamma/dbeta both or none");
-  if (rowsum_out && (rowsum_T <= 0 || rows % rowsum_T != 0 || rowsum_T > 8192))
-    return set_error(FFVC_ERR_ARG, "layernorm_bwd_sums: rows must be a multiple of rowsum_T (<= 8192)");
+  if (rowsum_out && (rowsum_T <= 0 || rows % rowsum_T != 0))
+    return set_error(FFVC_ERR_ARG, "layernorm_bwd_sums: rows must be a multiple of rowsum_T");
   if (rows <= 0) return FFVC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (option(OPT_LN_BWD_V2) && ln_cols_ok(D, dy, x, dx, add) && ln_cols_ok(D, gamma, nullptr, nullptr, nullptr)) {
+  if (option(OPT_LN_BWD_V2) && ln_cols_ok(D, dy, x, dx, add) && ln_cols_ok(D, gamma, nullptr, nullptr, nullptr) &&
+      (!rowsum_out || rowsum_T <= 2048)) {
     auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
     auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
     auto ab = reinterpret_cast<const __nv_bfloat16*>(add);
