@@ -332,8 +332,7 @@ template <int kThreads, int kRows, int kStages, bool kWgrad>
 __global__ void __launch_bounds__(kThreads) layernorm_bwd_pipe_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
     const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ add,
-    __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ colsum_out,
-    float* __restrict__ rowsum_out, int rowsum_T, long long rows) {
+    __nv_bfloat16* __restrict__ dx, float* __restrict__ ws, bool want_colsum, bool want_rowsum, int rowsum_T, long long rows) {
   constexpr int D = kThreads * 8;
   constexpr int NW = kThreads / 32;
   extern __shared__ __align__(16) unsigned char ln_smem[];
@@ -358,7 +357,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_pipe_kernel(
   };
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) issue(s);
-  if (rowsum_out) {
+  if (want_rowsum) {
     for (int i = threadIdx.x; i < rowsum_T; i += kThreads) srow[i] = 0.f;
     __syncthreads();
   }
@@ -445,7 +444,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_pipe_kernel(
       const uint4 pk = pack8(o);
       const bool ok = r0 + r < rows;
       if (ok) reinterpret_cast<uint4*>(dx + (r0 + r) * D)[c] = pk;
-      if (colsum_out || rowsum_out) {         // sums of the values as stored (bf16-rounded), like a pass over dx would see
+      if (want_colsum || want_rowsum) {         // sums of the values as stored (bf16-rounded), like a pass over dx would see
         float q[8];
         unpack8(pk, q);
         float t = 0.f;
@@ -454,7 +453,7 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_pipe_kernel(
           ac[j] += q[j];
           t += q[j];
         }
-        if (rowsum_out) {
+        if (want_rowsum) {
           t = warp_sum(t);
           if (lane == 0 && ok) atomicAdd(&srow[(int)((r0 + r) % rowsum_T)], t);
         }
@@ -463,24 +462,51 @@ __global__ void __launch_bounds__(kThreads) layernorm_bwd_pipe_kernel(
     cur = (cur + 1 == kStages) ? 0 : cur + 1;
   }
   cp_async_wait<0>();
+  // per-CTA partial sums go to this CTA's row of the workspace [gridDim.x][3*D + rowsum_T]; ln_bwd_finalize_kernel folds the
+  // rows.  (Direct atomicAdd from every CTA serialises gridDim.x deep on each of the 3*D addresses when the CTAs finish
+  // together: measured ~45 us of a 79 us kernel at 592 CTAs, profiles/r01_ab_kernels.md.)
+  float* my = ws + (size_t)blockIdx.x * (3 * D + rowsum_T);
   if (kWgrad) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&dgamma[8 * c + j], ag[kWgrad ? j : 0]);
-      atomicAdd(&dbeta[8 * c + j], ab[kWgrad ? j : 0]);
-    }
+    reinterpret_cast<float4*>(my)[2 * c] = make_float4(ag[0], ag[kWgrad ? 1 : 0], ag[kWgrad ? 2 : 0], ag[kWgrad ? 3 : 0]);
+    reinterpret_cast<float4*>(my)[2 * c + 1] = make_float4(ag[kWgrad ? 4 : 0], ag[kWgrad ? 5 : 0], ag[kWgrad ? 6 : 0], ag[kWgrad ? 7 : 0]);
+    reinterpret_cast<float4*>(my + D)[2 * c] = make_float4(ab[0], ab[kWgrad ? 1 : 0], ab[kWgrad ? 2 : 0], ab[kWgrad ? 3 : 0]);
+    reinterpret_cast<float4*>(my + D)[2 * c + 1] = make_float4(ab[kWgrad ? 4 : 0], ab[kWgrad ? 5 : 0], ab[kWgrad ? 6 : 0], ab[kWgrad ? 7 : 0]);
   }
-  if (colsum_out) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&colsum_out[8 * c + j], ac[j]);
+  if (want_colsum) {
+    reinterpret_cast<float4*>(my + 2 * D)[2 * c] = make_float4(ac[0], ac[1], ac[2], ac[3]);
+    reinterpret_cast<float4*>(my + 2 * D)[2 * c + 1] = make_float4(ac[4], ac[5], ac[6], ac[7]);
   }
-  if (rowsum_out) {
+  if (want_rowsum) {
     __syncthreads();
-    for (int i = threadIdx.x; i < rowsum_T; i += kThreads) {
-      const float t = srow[i];
-      if (t != 0.f) atomicAdd(&rowsum_out[i], t);
-    }
+    for (int i = threadIdx.x; i < rowsum_T; i += kThreads) my[3 * D + i] = srow[i];
   }
+}
+
+// out[i] += sum_p ws[p][i] for the sections that were requested: [0,D) dgamma, [D,2D) dbeta, [2D,3D) colsum, [3D,3D+T) rowsum.
+// gridDim.y chunks of parts per column block: the atomic depth per address is gridDim.y (8), not the number of CTAs.
+__global__ void __launch_bounds__(256) ln_bwd_finalize_kernel(const float* __restrict__ ws, int nparts, int D, int T,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              float* __restrict__ colsum_out, float* __restrict__ rowsum_out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int width = 3 * D + T;
+  if (i >= width) return;
+  float* out;
+  if (i < D) out = dgamma ? dgamma + i : nullptr;
+  else if (i < 2 * D) out = dbeta ? dbeta + (i - D) : nullptr;
+  else if (i < 3 * D) out = colsum_out ? colsum_out + (i - 2 * D) : nullptr;
+  else out = rowsum_out ? rowsum_out + (i - 3 * D) : nullptr;
+  if (!out) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int p = blockIdx.y;
+  const int step = gridDim.y;
+  for (; p + 3 * step < nparts; p += 4 * step) {
+    a0 += ws[(size_t)p * width + i];
+    a1 += ws[(size_t)(p + step) * width + i];
+    a2 += ws[(size_t)(p + 2 * step) * width + i];
+    a3 += ws[(size_t)(p + 3 * step) * width + i];
+  }
+  for (; p < nparts; p += step) a0 += ws[(size_t)p * width + i];
+  atomicAdd(out, (a0 + a1) + (a2 + a3));
 }
 
 // ------------------------------------------------------------------------------------ GroupNorm
@@ -780,6 +806,42 @@ __device__ __forceinline__ uint4 ld_stream(const __nv_bfloat16* p) {   // last u
 }
 __device__ __forceinline__ void st_stream(__nv_bfloat16* p, const uint4& v) { __stcs(reinterpret_cast<uint4*>(p), v); }
 
+// Per-thread cp.async ring over this thread's strided sequence of 16-byte vectors (up to NT tensors per item).  Slots are
+// private to the thread ([slot][tensor][thread] in shared memory), so consuming one needs cp.async.wait_group only — no
+// barrier — and kDepth-1 items (x NT x 16 B x 512 threads) are in flight per CTA without occupying registers.  This is what
+// the single-kernel GroupNorm forms lacked with register-staged loads (32 KB in flight per SM).
+template <int kDepth, int NT>
+struct VecRing {
+  uint4* smem;                       // [kDepth][NT][blockDim.x]
+  const __nv_bfloat16* ptr[NT];      // this thread's first item of every tensor (nullptr: tensor absent)
+  long long stride;                  // elements between consecutive items
+  int issued, total;
+  __device__ __forceinline__ void issue() {
+    if (issued < total) {
+      const int slot = issued & (kDepth - 1);
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        if (ptr[t]) cp_async16(smem_u32(smem + (slot * NT + t) * blockDim.x + threadIdx.x), ptr[t] + (long long)issued * stride, true);
+    }
+    cp_async_commit();
+    ++issued;
+  }
+  __device__ __forceinline__ void start(int n_items) {
+    total = n_items;
+    issued = 0;
+#pragma unroll
+    for (int i = 0; i < kDepth - 1; ++i) issue();
+  }
+  // item k (consumed in order): top up the ring, wait for the oldest group, hand out the slot
+  __device__ __forceinline__ const uint4* next(int k) {
+    issue();
+    cp_async_wait<kDepth - 1>();
+    return smem + ((k & (kDepth - 1)) * NT) * blockDim.x + threadIdx.x;
+  }
+  __device__ __forceinline__ void drain() { cp_async_wait<0>(); }
+};
+static constexpr int kGnRingDepthFwd = 16, kGnRingDepthBwd = 8;
+
 static constexpr int kGnThreads = 512;
 static constexpr int kGnUnroll = 4;
 static constexpr int kGnUnrollBwd = 2;   // backward holds 6 per-channel coefficient vectors: 2 x (x, dy, add) loads in flight fit 128 registers
@@ -802,6 +864,7 @@ __device__ __forceinline__ void gn_wait(const int* cnt, int n, int expected) {
   __syncthreads();
 }
 
+template <bool kRing>
 __global__ void __launch_bounds__(kGnThreads, 1)
 groupnorm_fused_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
@@ -812,6 +875,8 @@ groupnorm_fused_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
   const int cpg = C / G, vpp = C >> 3;
   const int vc = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = kGnThreads / vpp;
   const int p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);
+  const int my_items = (p0 + pl < p1) ? (p1 - p0 - pl + pstride - 1) / pstride : 0;      // pixel vectors this thread visits per sample
+  uint4* ring_smem = reinterpret_cast<uint4*>(sm + ((6 * G + 3) & ~3));                   // 16-byte aligned, after part[] / stat[]
   const double inv_count = 1.0 / ((double)HW * cpg);
   float gm[8], bt[8];
 #pragma unroll
@@ -827,6 +892,23 @@ groupnorm_fused_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     const __nv_bfloat16* base = x + (long long)n * HW * C + vc * 8;
+    if (kRing) {
+      VecRing<kGnRingDepthFwd, 1> ring;
+      ring.smem = ring_smem;
+      ring.ptr[0] = base + (long long)(p0 + pl) * C;
+      ring.stride = (long long)pstride * C;
+      ring.start(my_items);
+      for (int k = 0; k < my_items; ++k) {
+        float v[8];
+        unpack8(*ring.next(k), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += v[j];
+          q[j] = fmaf(v[j], v[j], q[j]);
+        }
+      }
+      ring.drain();
+    } else
     for (int p = p0 + pl; p < p1; p += pstride * kGnUnroll) {
       uint4 pk[kGnUnroll];
 #pragma unroll
@@ -857,6 +939,25 @@ groupnorm_fused_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
       sh[j] = bt[j] - stat[g] * sc[j];
     }
     const long long base = (long long)n * HW * C + vc * 8;
+    if (kRing) {
+      VecRing<kGnRingDepthFwd, 1> ring;
+      ring.smem = ring_smem;
+      ring.ptr[0] = x + base + (long long)(p0 + pl) * C;
+      ring.stride = (long long)pstride * C;
+      ring.start(my_items);
+      __nv_bfloat16* yo = y + base + (long long)(p0 + pl) * C;
+      for (int k = 0; k < my_items; ++k) {
+        float v[8], o[8];
+        unpack8(*ring.next(k), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = fmaf(v[j], sc[j], sh[j]);
+          o[j] = swish ? swish_fast_f(t) : t;
+        }
+        st_stream(yo + (long long)k * pstride * C, pack8(o));
+      }
+      ring.drain();
+    } else
     for (int p = p0 + pl; p < p1; p += pstride * kGnUnroll) {
       uint4 pk[kGnUnroll];
 #pragma unroll
@@ -907,6 +1008,7 @@ groupnorm_fused_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __r
   }
 }
 
+template <bool kRing>
 __global__ void __launch_bounds__(kGnThreads, 1)
 groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                            const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
@@ -918,6 +1020,8 @@ groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bflo
   const int cpg = C / G, vpp = C >> 3;
   const int vc = threadIdx.x % vpp, pl = threadIdx.x / vpp, pstride = kGnThreads / vpp;
   const int p0 = blockIdx.x * ppc, p1 = min(HW, p0 + ppc);
+  const int my_items = (p0 + pl < p1) ? (p1 - p0 - pl + pstride - 1) / pstride : 0;
+  uint4* ring_smem = reinterpret_cast<uint4*>(sm + ((6 * G + 3) & ~3));
   const float inv_count = 1.0f / ((float)HW * cpg);
   float gm[8], bt[8];
 #pragma unroll
@@ -954,6 +1058,26 @@ groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bflo
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     const long long base = (long long)n * HW * C + vc * 8;
+    if (kRing) {
+      VecRing<kGnRingDepthBwd, 3> ring;                     // same slot geometry as phase B (x, dy, add); add unused here
+      ring.smem = ring_smem;
+      ring.ptr[0] = x + base + (long long)(p0 + pl) * C;
+      ring.ptr[1] = dy + base + (long long)(p0 + pl) * C;
+      ring.ptr[2] = nullptr;
+      ring.stride = (long long)pstride * C;
+      ring.start(my_items);
+      for (int k = 0; k < my_items; ++k) {
+        const uint4* sl = ring.next(k);
+        float g[8], xh[8];
+        grad8(sl[0], sl[blockDim.x], mu, rs, g, xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += g[j];
+          q[j] = fmaf(g[j], xh[j], q[j]);
+        }
+      }
+      ring.drain();
+    } else
     for (int p = p0 + pl; p < p1; p += pstride * kGnUnrollBwd) {
       uint4 xk[kGnUnrollBwd], dk[kGnUnrollBwd];
 #pragma unroll
@@ -991,6 +1115,31 @@ groupnorm_fused_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bflo
       s2[j] = stat[G + g];
     }
     const long long base = (long long)n * HW * C + vc * 8;
+    if (kRing) {
+      VecRing<kGnRingDepthBwd, 3> ring;
+      ring.smem = ring_smem;
+      ring.ptr[0] = x + base + (long long)(p0 + pl) * C;
+      ring.ptr[1] = dy + base + (long long)(p0 + pl) * C;
+      ring.ptr[2] = add ? add + base + (long long)(p0 + pl) * C : nullptr;
+      ring.stride = (long long)pstride * C;
+      ring.start(my_items);
+      __nv_bfloat16* dxo = dx + base + (long long)(p0 + pl) * C;
+      for (int k = 0; k < my_items; ++k) {
+        const uint4* sl = ring.next(k);
+        float g[8], xh[8], o[8];
+        grad8(sl[0], sl[blockDim.x], mu, rs, g, xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs[j] * (g[j] - s1[j] - xh[j] * s2[j]);
+        if (add) {
+          float a[8];
+          unpack8(sl[2 * blockDim.x], a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        st_stream(dxo + (long long)k * pstride * C, pack8(o));
+      }
+      ring.drain();
+    } else
     for (int p = p0 + pl; p < p1; p += pstride * kGnUnrollBwd) {
       uint4 xk[kGnUnrollBwd], dk[kGnUnrollBwd], ak[kGnUnrollBwd];
 #pragma unroll
@@ -1128,10 +1277,12 @@ extern "C" int ffvc_layernorm_bwd(const void* dy, const void* x, const float* ga
   return FFVC_OK;
 }
 
+static const int kLnBwdMaxCtasPerSm = 8;
 template <int kThreads, int kRows, int kStages>
 static void ln_bwd_pipe_launch_r(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
                                  const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx, float* dgamma, float* dbeta,
-                                 float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, cudaStream_t st) {
+                                 float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, float* ws, cudaStream_t st) {
+  constexpr int D = kThreads * 8;
   constexpr int kRing = kStages * kRows * 3 * kThreads * 16;
   constexpr int kMaxSmem = kRing + 2048 * 4;                 // ring + per-token sums (rowsum_T <= 2048)
   static int per_sm_w = 0, per_sm_n = 0;       // resident CTAs per SM (wgrad / no-wgrad form): the grid is one full wave
@@ -1140,30 +1291,38 @@ static void ln_bwd_pipe_launch_r(const __nv_bfloat16* dy, const __nv_bfloat16* x
     cudaFuncSetAttribute(layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, true>, kThreads, kRing + 1024);
-    per_sm_w = n > 0 ? n : 1;
+    per_sm_w = n > 0 ? (n < kLnBwdMaxCtasPerSm ? n : kLnBwdMaxCtasPerSm) : 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, false>, kThreads, kRing + 1024);
-    per_sm_n = n > 0 ? n : 1;
+    per_sm_n = n > 0 ? (n < kLnBwdMaxCtasPerSm ? n : kLnBwdMaxCtasPerSm) : 1;
   }
-  const size_t smem = (size_t)kRing + (rowsum_out ? (size_t)rowsum_T * sizeof(float) : 0);
+  const bool want_row = rowsum_out != nullptr, want_col = colsum_out != nullptr;
+  const int T = want_row ? rowsum_T : 0;
+  const size_t smem = (size_t)kRing + (size_t)T * sizeof(float);
   const int per_sm = dgamma ? per_sm_w : per_sm_n;
   const long long want = (rows + kRows - 1) / kRows;
   const unsigned grid = (unsigned)(want < 148LL * per_sm ? want : 148LL * per_sm);
   if (dgamma)
     layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, true><<<grid, kThreads, smem, st>>>(
-        dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows);
+        dy, x, gamma, mean, rstd, add, dx, ws, want_col, want_row, T, rows);
   else
     layernorm_bwd_pipe_kernel<kThreads, kRows, kStages, false><<<grid, kThreads, smem, st>>>(
-        dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows);
+        dy, x, gamma, mean, rstd, add, dx, ws, want_col, want_row, T, rows);
+  if (dgamma || want_col || want_row) {
+    count_launch();
+    const int width = 3 * D + T;
+    ln_bwd_finalize_kernel<<<dim3((unsigned)((width + 255) / 256), 8), 256, 0, st>>>(ws, (int)grid, D, T, dgamma, dbeta, colsum_out,
+                                                                                      rowsum_out);
+  }
 }
 // option value 1: 4 rows per group, 2 stages;  2: 2 rows per group, 4 stages (same shared memory, finer-grained ring)
 template <int kThreads>
 static void ln_bwd_cols_launch(const __nv_bfloat16* dy, const __nv_bfloat16* x, const float* gamma, const float* mean,
                                const float* rstd, const __nv_bfloat16* add, __nv_bfloat16* dx, float* dgamma, float* dbeta,
-                               float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, cudaStream_t st) {
+                               float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, float* ws, cudaStream_t st) {
   if (option(OPT_LN_BWD_V2) == 2)
-    ln_bwd_pipe_launch_r<kThreads, 2, 4>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st);
+    ln_bwd_pipe_launch_r<kThreads, 2, 4>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, ws, st);
   else
-    ln_bwd_pipe_launch_r<kThreads, 4, 2>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st);
+    ln_bwd_pipe_launch_r<kThreads, 4, 2>(dy, x, gamma, mean, rstd, add, dx, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, ws, st);
 }
 
 // LayerNorm backward that also accumulates bias gradients taken from its own output:
@@ -1173,7 +1332,7 @@ static void ln_bwd_cols_launch(const __nv_bfloat16* dy, const __nv_bfloat16* x, 
 // warp-per-row kernel followed by ffvc_colsum / ffvc_rowsum over dx.
 extern "C" int ffvc_layernorm_bwd_sums(const void* dy, const void* x, const float* gamma, const float* mean,
                                        const float* rstd, const void* add, void* dx, float* dgamma, float* dbeta,
-                                       float* colsum_out, float* rowsum_out, int rowsum_T, long long rows, int D,
+                                       float* colsum_out, float* rowsum_out, int rowsum_T, float* ws, long long rows, int D,
                                        void* stream) {
   if (D % 8 != 0 || D > 2048) return set_error(FFVC_ERR_ARG, "layernorm: D must be a multiple of 8 and <= 2048");
   if ((dgamma == nullptr) != (dbeta == nullptr)) return set_error(FFVC_ERR_ARG, "layernorm_bwd: dgamma/dbeta both or none");
@@ -1181,17 +1340,17 @@ extern "C" int ffvc_layernorm_bwd_sums(const void* dy, const void* x, const floa
     return set_error(FFVC_ERR_ARG, "layernorm_bwd_sums: rows must be a multiple of rowsum_T");
   if (rows <= 0) return FFVC_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (option(OPT_LN_BWD_V2) && ln_cols_ok(D, dy, x, dx, add) && ln_cols_ok(D, gamma, nullptr, nullptr, nullptr) &&
-      (!rowsum_out || rowsum_T <= 2048)) {
+  if (option(OPT_LN_BWD_V2) && ws && ln_cols_ok(D, dy, x, dx, add) && ln_cols_ok(D, gamma, ws, nullptr, nullptr) &&
+      (!rowsum_out || (rowsum_T <= 2048 && rowsum_T % 4 == 0))) {
     auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
     auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
     auto ab = reinterpret_cast<const __nv_bfloat16*>(add);
     auto dxb = reinterpret_cast<__nv_bfloat16*>(dx);
     switch (D) {
-      case 256: ln_bwd_cols_launch<32>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st); break;
-      case 512: ln_bwd_cols_launch<64>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st); break;
-      case 768: ln_bwd_cols_launch<96>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st); break;
-      default: ln_bwd_cols_launch<128>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, st); break;
+      case 256: ln_bwd_cols_launch<32>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, ws, st); break;
+      case 512: ln_bwd_cols_launch<64>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, ws, st); break;
+      case 768: ln_bwd_cols_launch<96>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, ws, st); break;
+      default: ln_bwd_cols_launch<128>(dyb, xb, gamma, mean, rstd, ab, dxb, dgamma, dbeta, colsum_out, rowsum_out, rowsum_T, rows, ws, st); break;
     }
     FFVC_CHECK_LAUNCH();
     return FFVC_OK;
@@ -1201,6 +1360,11 @@ extern "C" int ffvc_layernorm_bwd_sums(const void* dy, const void* x, const floa
   if (colsum_out && (rc = ffvc_colsum(dx, colsum_out, rows, D, stream))) return rc;
   if (rowsum_out && (rc = ffvc_rowsum(dx, rowsum_out, (int)(rows / rowsum_T), rowsum_T, D, stream))) return rc;
   return FFVC_OK;
+}
+
+// bytes of scratch ffvc_layernorm_bwd_sums needs for the fused form (one row of partial sums per resident CTA)
+extern "C" long long ffvc_layernorm_bwd_ws_bytes(int D, int rowsum_T) {
+  return (long long)sizeof(float) * 148 * kLnBwdMaxCtasPerSm * (3LL * D + (rowsum_T > 0 ? rowsum_T : 0));
 }
 
 // pixels per CTA: aim for >= 8 CTAs per SM worth of work, at least 64 pixels each
@@ -1320,9 +1484,21 @@ extern "C" int ffvc_groupnorm_fused_fwd(const void* x, const float* gamma, const
   int ppc;
   const int grid = gn_fused_grid(HW, C, &ppc);
   int* cnt = reinterpret_cast<int*>(ws + 2 * (long long)N * G);
-  groupnorm_fused_fwd_kernel<<<grid, kGnThreads, 6 * G * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, ws, cnt, N, HW, C, G,
-      ppc, swish, eps, gn_pipeline_default() ? 1 : 0);
+  if (option(OPT_GN_RING)) {
+    const size_t smem = (size_t)((6 * G + 3) & ~3) * sizeof(float) + (size_t)kGnRingDepthFwd * kGnThreads * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(groupnorm_fused_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    groupnorm_fused_fwd_kernel<true><<<grid, kGnThreads, smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, ws, cnt, N, HW, C, G,
+        ppc, swish, eps, gn_pipeline_default() ? 1 : 0);
+  } else {
+    groupnorm_fused_fwd_kernel<false><<<grid, kGnThreads, 6 * G * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), gamma, beta, reinterpret_cast<__nv_bfloat16*>(y), mean, rstd, ws, cnt, N, HW, C, G,
+        ppc, swish, eps, gn_pipeline_default() ? 1 : 0);
+  }
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
@@ -1337,10 +1513,23 @@ extern "C" int ffvc_groupnorm_fused_bwd(const void* dy, const void* x, const flo
   int ppc;
   const int grid = gn_fused_grid(HW, C, &ppc);
   int* cnt = reinterpret_cast<int*>(ws + 2 * (long long)N * G);
-  groupnorm_fused_bwd_kernel<<<grid, kGnThreads, 6 * G * sizeof(float), st>>>(
-      reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta,
-      reinterpret_cast<const __nv_bfloat16*>(add), reinterpret_cast<__nv_bfloat16*>(dx), ws, cnt, N, HW, C, G, ppc, swish,
-      gn_pipeline_default() ? 1 : 0);
+  if (option(OPT_GN_RING)) {
+    const size_t smem = (size_t)((6 * G + 3) & ~3) * sizeof(float) + (size_t)kGnRingDepthBwd * 3 * kGnThreads * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(groupnorm_fused_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    groupnorm_fused_bwd_kernel<true><<<grid, kGnThreads, smem, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta,
+        reinterpret_cast<const __nv_bfloat16*>(add), reinterpret_cast<__nv_bfloat16*>(dx), ws, cnt, N, HW, C, G, ppc, swish,
+        gn_pipeline_default() ? 1 : 0);
+  } else {
+    groupnorm_fused_bwd_kernel<false><<<grid, kGnThreads, 6 * G * sizeof(float), st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(x), mean, rstd, gamma, beta,
+        reinterpret_cast<const __nv_bfloat16*>(add), reinterpret_cast<__nv_bfloat16*>(dx), ws, cnt, N, HW, C, G, ppc, swish,
+        gn_pipeline_default() ? 1 : 0);
+  }
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

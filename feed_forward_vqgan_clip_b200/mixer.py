@@ -124,6 +124,9 @@ class MixerEngine:
         self.shapes = dict((n, p.shape) for n, p in m.named_parameters())
         self._shadow_version = None
         self.ext_shadow_fresh = False       # set by FusedAdam when it refreshed the shadow itself
+        from . import _lib
+        # scratch of the fused LayerNorm backward (per-CTA partial sums of dgamma / dbeta / bias gradients)
+        self.ln_ws = torch.empty(int(_lib.load().ffvc_layernorm_bwd_ws_bytes(self.D, self.T)) // 4, device=dev, dtype=F32)
 
     def valid(self):
         return all(p.data_ptr() == q for p, q in zip(self.params, self._ptrs))
@@ -245,7 +248,7 @@ class MixerEngine:
         # every LayerNorm backward also emits the bias gradient that is a plain sum of its output dx (one fused pass):
         # column sums -> bias of the Linear whose output gradient dx is; per-token row sums -> bias of the token-mixing Conv1d
         call("layernorm_bwd_sums", dnf, sv["HL"], self.wf(q + "weight"), sv["muf"], sv["rsf"], None, dH,
-             self.g(q + "weight"), self.g(q + "bias"), self.g("mixer.%d.1.fn.3.bias" % (L + 1)), None, 0, R, D)
+             self.g(q + "weight"), self.g(q + "bias"), self.g("mixer.%d.1.fn.3.bias" % (L + 1)), None, 0, self.ln_ws, R, D)
         for i in range(L + 1, 1, -1):
             p = "mixer.%d." % i
             lv = sv["layers"][i - 2]
@@ -261,7 +264,7 @@ class MixerEngine:
             del dU2
             dHb = new(R, D)
             call("layernorm_bwd_sums", dn2, lv["Hb"], self.wf(p + "1.norm.weight"), lv["mu2"], lv["rs2"], dH, dHb,
-                 self.g(p + "1.norm.weight"), self.g(p + "1.norm.bias"), None, self.g(p + "0.fn.3.bias"), T, R, D)
+                 self.g(p + "1.norm.weight"), self.g(p + "1.norm.bias"), None, self.g(p + "0.fn.3.bias"), T, self.ln_ws, R, D)
             # ---- token mixing:  Hb[b] = Wt2 . G1[b] + bt2 + Ha[b]
             seg_splits = sp(T, 4 * T, B * D)
             ops.gemm(dHb, lv["G1"], self.g(p + "0.fn.3.weight"), T, 4 * T, D, a_role=ops.ROLE_SEG, a_bs=T * D,
@@ -280,7 +283,7 @@ class MixerEngine:
             dHa = new(R, D)
             nxt = "mixer.%d.1.fn.3.bias" % (i - 1) if i > 2 else "mixer.1.bias"     # the Linear whose output gradient dHa is
             call("layernorm_bwd_sums", dn1, lv["Ha"], self.wf(p + "0.norm.weight"), lv["mu1"], lv["rs1"], dHb, dHa,
-                 self.g(p + "0.norm.weight"), self.g(p + "0.norm.bias"), self.g(nxt), None, 0, R, D)
+                 self.g(p + "0.norm.weight"), self.g(p + "0.norm.bias"), self.g(nxt), None, 0, self.ln_ws, R, D)
             dH = dHa
             if on_layer_done is not None:
                 on_layer_done(i - 2)

@@ -13,6 +13,8 @@ Architecture restated from taming-transformers — see oracle/
 """
 import math
 
+import os
+
 import torch
 from torch import nn
 
@@ -229,7 +231,7 @@ class DecoderEngine:
     # GroupNorm: two-pass kernels (statistics, apply).  The single-kernel L2-resident forms (ffvc_groupnorm_fused_*) are
     # selectable per tensor size through GN_FUSED_MIN (elements per sample); measured on B200 they lose to the two-pass
     # kernels (one 512-thread CTA per SM keeps too few register-staged loads in flight), so they are off by default.
-    GN_FUSED_MIN = None
+    GN_FUSED_MIN = int(os.environ["FFVC_GN_FUSED_MIN"]) if os.environ.get("FFVC_GN_FUSED_MIN") else None
 
     def _gn_fused(self, HW, C):
         return self.GN_FUSED_MIN is not None and HW * C >= self.GN_FUSED_MIN and 512 % (C // 8) == 0

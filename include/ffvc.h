@@ -48,7 +48,7 @@ long long ffvc_launch_count(void);
 void ffvc_reset_launch_count(void);
 /* kernel-selection switches (A/B measurement of alternative kernels for the same op; results are identical up to
  * summation order).  Names: "ln_fwd_v2" / "ln_bwd_v2" (column-owning LayerNorm kernels; 1 = 4 rows in flight per CTA, 2 = 8 rows fwd / 2 rows bwd),
- * "pool_v2" (row-mapped cutout-pool backward).
+ * "pool_v2" (row-mapped cutout-pool backward), "gn_ring" (cp.async rings in the single-kernel GroupNorm forms).
  * Initial values come from the environment variable FFVC_OPTS="name=0|1,...".  Returns the previous value, -1 if the
  * name is unknown. */
 int ffvc_set_option(const char* name, int value);
@@ -128,10 +128,13 @@ int ffvc_layernorm_bwd(const void* dy, const void* x, const float* gamma, const 
                        const void* add, void* dx, float* dgamma, float* dbeta, long long rows, int D, void* stream);
 /* same, and the bias gradients the mixer takes from dx (mlp_mixer_pytorch.py:16-23,32-38; autograd, main.py:832) in the
  * same pass: colsum_out[d] += sum_rows dx[row][d] (Linear bias), rowsum_out[t] += sum_{row % rowsum_T == t, d} dx[row][d]
- * (token-mixing Conv1d bias; rows = B*rowsum_T token-major).  Either may be NULL. */
+ * (token-mixing Conv1d bias; rows = B*rowsum_T token-major).  Either may be NULL.
+ * ws: caller-owned scratch of ffvc_layernorm_bwd_ws_bytes(D, rowsum_T) bytes (per-CTA partial sums, folded by a second tiny
+ * kernel instead of grid-deep atomics); NULL selects the unfused kernels. */
 int ffvc_layernorm_bwd_sums(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                             const void* add, void* dx, float* dgamma, float* dbeta, float* colsum_out, float* rowsum_out,
-                            int rowsum_T, long long rows, int D, void* stream);
+                            int rowsum_T, float* ws, long long rows, int D, void* stream);
+long long ffvc_layernorm_bwd_ws_bytes(int D, int rowsum_T);
 
 /* GroupNorm(G groups, eps) [+ swish] on NHWC bf16 — taming Normalize + nonlinearity.
  * ws: N*G*2 doubles of scratch.  bwd gives dx only (frozen affine), optionally + add.                 */

@@ -58,12 +58,14 @@ def test_layernorm_fwd_bwd(rows, D, T, v2, ffvc_options):
     call("layernorm_bwd", dy, x, gamma, mean, rstd, None, dx2, None, None, rows, D)
     close(dx2, xr.grad)
     # the fused form: same dx / dgamma / dbeta, plus column sums and per-token row sums of the dx it stored
+    from feed_forward_vqgan_clip_b200 import _lib
+    ws = torch.full((int(_lib.load().ffvc_layernorm_bwd_ws_bytes(D, T)) // 4,), float("nan"), device=DEV)   # never read unwritten
     for with_w, with_add, with_col, with_row in [(1, 1, 1, 1), (1, 1, 1, 0), (1, 0, 0, 1), (0, 1, 1, 1), (0, 0, 0, 0)]:
         dx3 = torch.empty_like(x)
         dg3, db3 = 0.5 + torch.zeros(D, device=DEV), 0.25 + torch.zeros(D, device=DEV)     # accumulate semantics
         cs, rsum = 2.0 + torch.zeros(D, device=DEV), 3.0 + torch.zeros(T, device=DEV)
         call("layernorm_bwd_sums", dy, x, gamma, mean, rstd, add if with_add else None, dx3, dg3 if with_w else None,
-             db3 if with_w else None, cs if with_col else None, rsum if with_row else None, T, rows, D)
+             db3 if with_w else None, cs if with_col else None, rsum if with_row else None, T, ws, rows, D)
         close(dx3, xr.grad + (add.float() if with_add else 0))
         if with_w:
             close(dg3 - 0.5, gr.grad, 1e-2)
@@ -98,13 +100,16 @@ def test_groupnorm_fwd_bwd(N, HW, C, swish):
     close(dx, xr.grad.permute(0, 2, 1) + add.float())
 
 
+@pytest.mark.parametrize("ring", [0, 1])
 @pytest.mark.parametrize("pipeline", [1, 0])
 @pytest.mark.parametrize("N,HW,C,swish", [(2, 256, 512, 1), (3, 1024, 128, 1), (1, 4096, 64, 0), (5, 16384, 128, 1), (2, 4096, 256, 1),
-                                          (3, 100, 64, 1)])
-def test_groupnorm_fused_single_kernel_forms(N, HW, C, swish, pipeline):
+                                          (3, 100, 64, 1), (2, 65536, 128, 1)])
+def test_groupnorm_fused_single_kernel_forms(N, HW, C, swish, pipeline, ring, ffvc_options):
     """the L2-resident single-kernel GroupNorm (persistent grid + per-sample arrival counters) against torch AND against
-    the two-pass kernels; both schedules (phase A of sample n+1 before / after the wait for sample n)"""
+    the two-pass kernels; both schedules (phase A of sample n+1 before / after the wait for sample n); ring = 1: loads
+    through per-thread cp.async rings (also a thread with more items than the ring is deep: 65536 pixels / 148 CTAs)"""
     from feed_forward_vqgan_clip_b200 import _lib
+    ffvc_options(gn_ring=ring)
     x, dy, add = rnd(N, HW, C, seed=1), rnd(N, HW, C, seed=2), rnd(N, HW, C, seed=3)
     gamma = 1 + 0.1 * torch.randn(C, device=DEV)
     beta = 0.1 * torch.randn(C, device=DEV)

@@ -56,6 +56,7 @@ def main():
     dg, db, cs = (torch.zeros(D, device=DEV) for _ in range(3))
     rs = torch.zeros(T, device=DEV)
     tensor_bytes = rows * D * 2
+    ws = torch.empty(int(_lib.load().ffvc_layernorm_bwd_ws_bytes(D, T)) // 4, device=DEV)
 
     def ln_fwd(i):
         s = sets[i]
@@ -63,11 +64,11 @@ def main():
 
     def ln_bwd_col(i):       # LN1 backward of a mixer layer: wgrad + residual add + column sums of dx
         s = sets[i]
-        call("layernorm_bwd_sums", s["dy"], s["x"], gamma, s["mean"], s["rstd"], s["add"], s["y"], dg, db, cs, None, 0, rows, D)
+        call("layernorm_bwd_sums", s["dy"], s["x"], gamma, s["mean"], s["rstd"], s["add"], s["y"], dg, db, cs, None, 0, ws, rows, D)
 
     def ln_bwd_row(i):       # LN2 backward: wgrad + residual add + per-token row sums of dx
         s = sets[i]
-        call("layernorm_bwd_sums", s["dy"], s["x"], gamma, s["mean"], s["rstd"], s["add"], s["y"], dg, db, None, rs, T, rows, D)
+        call("layernorm_bwd_sums", s["dy"], s["x"], gamma, s["mean"], s["rstd"], s["add"], s["y"], dg, db, None, rs, T, ws, rows, D)
 
     def ln_bwd_plain(i):
         s = sets[i]
@@ -102,7 +103,7 @@ def main():
 
     def ln2_bwd(i):
         s = sets2[i]
-        call("layernorm_bwd_sums", s["dy"], s["x"], gamma2, s["mean"], s["rstd"], s["add"], s["y"], None, None, None, None, 0, rows2, D2)
+        call("layernorm_bwd_sums", s["dy"], s["x"], gamma2, s["mean"], s["rstd"], s["add"], s["y"], None, None, None, None, 0, ws, rows2, D2)
 
     for i in range(NSETS):
         ln2_fwd(i)
@@ -114,6 +115,44 @@ def main():
         out["layernorm_bwd (frozen) 25600x768 v2=%d" % v2] = {"us": t, "GBps": 4 * rows2 * D2 * 2 / t / 1e3}
     setopt(ln_fwd_v2=0, ln_bwd_v2=0)
     del sets, sets2
+    # ---------------- GroupNorm(32)+swish at the decoder's shapes: two-pass kernels vs the single-kernel L2-resident forms
+    for (N, HW, C) in ((64, 65536, 128), (64, 16384, 128), (64, 16384, 256), (64, 4096, 256)):
+        g = torch.Generator(device=DEV).manual_seed(7)
+        x = torch.randn(N, HW, C, device=DEV, generator=g).to(BF)
+        dy = torch.randn(N, HW, C, device=DEV, generator=g).to(BF)
+        add = torch.randn(N, HW, C, device=DEV, generator=g).to(BF)
+        y = torch.empty_like(x)
+        gam, bet = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+        gws = torch.empty((int(_lib.load().ffvc_groupnorm_ws_bytes(N, 32)) + 7) // 8, device=DEV, dtype=torch.float64)
+        mean, rstd = torch.empty(N * 32, device=DEV), torch.empty(N * 32, device=DEV)
+        tb = N * HW * C * 2
+
+        def two_fwd(i):
+            call("groupnorm_stats", x, gws, mean, rstd, N, HW, C, 32, 1e-6)
+            call("groupnorm_apply", x, mean, rstd, gam, bet, y, N, HW, C, 32, 1)
+
+        def two_bwd(i):
+            call("groupnorm_bwd", dy, x, mean, rstd, gam, bet, gws, add, y, N, HW, C, 32, 1)
+
+        def fused_fwd(i):
+            call("groupnorm_fused_fwd", x, gam, bet, y, mean, rstd, gws, N, HW, C, 32, 1, 1e-6)
+
+        def fused_bwd(i):
+            call("groupnorm_fused_bwd", dy, x, mean, rstd, gam, bet, gws, add, y, N, HW, C, 32, 1)
+
+        tag = "%dx%dx%d" % (N, HW, C)
+        t = timeit(two_fwd)
+        out["groupnorm fwd two-pass %s" % tag] = {"us": t, "GBps": 3 * tb / t / 1e3}
+        t = timeit(two_bwd)
+        out["groupnorm bwd two-pass %s" % tag] = {"us": t, "GBps": 6 * tb / t / 1e3}
+        for ring in (0, 1):
+            setopt(gn_ring=ring)
+            t = timeit(fused_fwd)
+            out["groupnorm fwd fused ring=%d %s" % (ring, tag)] = {"us": t, "GBps_algorithmic_2pass": 3 * tb / t / 1e3}
+            t = timeit(fused_bwd)
+            out["groupnorm bwd fused ring=%d %s" % (ring, tag)] = {"us": t, "GBps_algorithmic_2pass": 6 * tb / t / 1e3}
+        setopt(gn_ring=0)
+        del x, dy, add, y
     # ---------------- cutout pool backward (64 images 256x256 -> 224x224)
     B, H, P = 64, 256, 224
     ps = [dict(x=torch.rand(B, H, H, 3, device=DEV), dy=torch.randn(B, P, P, 3, device=DEV), dx=torch.empty(B, H, H, 3, device=DEV))
