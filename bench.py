@@ -283,7 +283,7 @@ def main():
     roof = None
     if rank == 0:
         peaks, peak_src = load_peaks()
-        ev, fl = [], []
+        ev, fl, by = [], [], []
         real_gemm = ops.gemm
 
         def timed_gemm(a, b, out, M, Nn, K, **kw):
@@ -292,7 +292,19 @@ def main():
             r = real_gemm(a, b, out, M, Nn, K, **kw)
             e.record()
             ev.append((s, e))
-            fl.append(2.0 * M * Nn * K * kw.get("batch", 1) * kw.get("k_segs", 1))
+            nb, segs = kw.get("batch", 1), kw.get("k_segs", 1)       # `batch` is the total (outer x inner) batch count
+            fl.append(2.0 * M * Nn * K * nb * segs)
+            # algorithmic DRAM bytes of this launch: each operand once (broadcast operands are shared by the batch), the
+            # output once, plus every extra epilogue stream (pre-activation copy, act' operand, residual)
+            a_n = (nb if kw.get("a_role", 0) == 1 else 1) * (segs if kw.get("a_role", 0) == 2 else 1)
+            b_n = (nb if kw.get("b_role", 0) == 1 else 1) * (segs if kw.get("b_role", 0) == 2 else 1)
+            if kw.get("a_mode", 0) == 2:          # implicit-GEMM 3x3 conv: the NHWC tensor is read once, K = 9 * Cin
+                a_bytes = 2.0 * M * K / 9
+            else:
+                a_bytes = 2.0 * M * K * a_n
+            o_sz = 4.0 if (out is not None and out.dtype == torch.float32) else 2.0
+            extra = sum(2.0 for k_ in ("pre_out", "aux", "res") if kw.get(k_) is not None)
+            by.append(a_bytes + 2.0 * Nn * K * b_n + M * Nn * nb * (o_sz + extra))
             return r
 
         from feed_forward_vqgan_clip_b200 import vqgan as _vq_mod
@@ -308,6 +320,8 @@ def main():
             ev.append((s, e))
             n_, h_, w_, cin_, cout_ = a[3:8]
             fl.append(2.0 * n_ * h_ * w_ * cout_ * 9 * cin_)
+            streams = 1 + (1 if a[10] is not None else 0) + (1 if a[11] is not None else 0)      # out (+ res) (+ aux)
+            by.append(n_ * h_ * w_ * (2.0 * cin_ + (4.0 if a[14] else 2.0) * cout_ + 2.0 * cout_ * (streams - 1)) + 2.0 * 9 * cin_ * cout_)
 
         xd0 = x_host[0].to(dev)
         if world == 1:
@@ -315,7 +329,7 @@ def main():
             torch.cuda.synchronize()
             ops.gemm = timed_gemm
             _vq_mod.call = timed_call
-            del ev[:], fl[:]
+            del ev[:], fl[:], by[:]
             s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s_all.record()
             ts.step(xd0)
@@ -328,7 +342,8 @@ def main():
             traffic, traffic_src = load_traffic()
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel + conv3x3_halo_kernel (tcgen05 GEMM family)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (read + write), mean over the family's launches of one step",
-                    "traffic_source": traffic_src, "flops_per_launch": gemm_flops / max(1, len(ev)), "peak_source": peak_src + " (sustained cuBLAS bf16)",
+                    "traffic_source": traffic_src, "algorithmic_bytes_per_launch": sum(by) / max(1, len(by)),
+                    "flops_per_launch": gemm_flops / max(1, len(ev)), "peak_source": peak_src + " (sustained cuBLAS bf16)",
                     "launches_per_step": len(ev), "gemm_ms_per_step": gemm_ms, "eager_step_ms": s_all.elapsed_time(e_all),
                     "gemm_share_of_step": gemm_ms / ms_per_step, "flops_per_step_executed": gemm_flops,
                     "how": "CUDA events around every ffvc_gemm / ffvc_conv3x3_halo launch of one eager step; share = their time / graph step time"}

@@ -28,7 +28,7 @@ static int opt_index(const char* name) {
   return -1;
 }
 static void opts_init() {
-  static const int defaults[OPT_COUNT] = {0, 0, 0, 0};
+  static const int defaults[OPT_COUNT] = {2, 1, 1, 1}   /* measured: profiles/r01_ab_kernels.md */;
   for (int i = 0; i < OPT_COUNT; ++i) g_opts[i].store(defaults[i]);
   const char* env = getenv("FFVC_OPTS");
   if (!env) return;
