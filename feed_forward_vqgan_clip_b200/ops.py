@@ -1,6 +1,8 @@
 """Thin Python wrappers over the C ABI (include/ffvc.h).  Tensors are torch CUDA tensors used purely as
 device-memory handles; every computation happens in libffvc_sm100.so.  No fallback path exists."""
 import ctypes as C
+import json
+import os
 
 import torch
 
@@ -41,7 +43,52 @@ def reset_launch_count():
     _lib.load().ffvc_reset_launch_count()
 
 
-def gemm(a, b, out, M, N, K, *, a_mode=KMAJOR, b_mode=KMAJOR, a_ld=None, b_ld=None,
+# ------------------------------------------------------------------ per-shape launch configurations measured on B200
+# tools/tune_gemm.py times every legal (two_cta, tile_m, block_n, epi_warps, splits) combination of every distinct GEMM of the
+# bench step on the GPU box and writes the winners to gemm_tuned.json; a call that leaves those knobs at their defaults picks
+# its entry up here.  Shapes without an entry use the heuristics in ffvc_gemm.  FFVC_GEMM_TUNED=0 disables the table.
+_TUNED = None
+TUNED_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gemm_tuned.json")
+
+
+def tuned_table():
+    global _TUNED
+    if _TUNED is None:
+        _TUNED = {}
+        if os.environ.get("FFVC_GEMM_TUNED", "1") != "0" and os.path.exists(TUNED_PATH):
+            with open(TUNED_PATH) as f:
+                _TUNED = json.load(f).get("table", {})
+    return _TUNED
+
+
+def gemm_key(M, N, K, out_fp32, kw):
+    """identity of a GEMM launch as far as the choice of tile configuration is concerned"""
+    g = kw.get
+    conv = g("conv")
+    return ",".join(str(v) for v in (
+        M, N, K, g("a_mode", 0), g("b_mode", 0), g("a_role", 0), g("b_role", 0), g("batch", 1), g("batch_inner", 1), g("k_segs", 1),
+        int(out_fp32), int(bool(g("atomic", False))), 0 if g("bias") is None else g("bias_mode", 1), g("act", 0), g("mul_mode", 0),
+        int(g("pre_out") is not None), int(g("res") is not None), int(g("aux") is not None), int(g("argmin_out") is not None),
+        "x".join(str(c) for c in conv) if conv is not None else "-"))
+
+
+def gemm(a, b, out, M, N, K, **kw):
+    """ffvc_gemm with the measured per-shape configuration (if any) filled in for knobs the caller left at their defaults"""
+    if not (kw.get("block_n") or kw.get("tile_m") or kw.get("two_cta") or kw.get("epi_warps")):
+        t = tuned_table()
+        if t:
+            cfg = t.get(gemm_key(M, N, K, out is not None and out.dtype == F32, kw))
+            if cfg:
+                kw = dict(kw)
+                for k_ in ("block_n", "tile_m", "two_cta", "epi_warps"):
+                    if cfg.get(k_):
+                        kw[k_] = cfg[k_]
+                if cfg.get("splits") and kw.get("atomic"):
+                    kw["splits"] = cfg["splits"]
+    return gemm_raw(a, b, out, M, N, K, **kw)
+
+
+def gemm_raw(a, b, out, M, N, K, *, a_mode=KMAJOR, b_mode=KMAJOR, a_ld=None, b_ld=None,
          a_role=ROLE_BCAST, b_role=ROLE_BCAST, a_bs=0, b_bs=0, batch=1, k_segs=1, splits=1, block_n=0,
          conv=None, pre_out=None, aux=None, res=None, bias=None, ldc=None, out_bs=0, atomic=False,
          bias_mode=1, act=ACT_NONE, mul_mode=ACT_NONE, alpha=1.0, a_off=0, b_off=0, out_off=0, batch_inner=1,
