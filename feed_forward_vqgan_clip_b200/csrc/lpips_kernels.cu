@@ -188,6 +188,76 @@ __global__ void __launch_bounds__(256) diversity_kernel(const __nv_bfloat16* __r
   if (lane == 0) atomicAdd(loss_accum, w * lsum);
 }
 
+// Same term for any number of repeats R (mode 'all', main.py:783-787, is the same expression with R = batch, B = 1; also
+// 'between_same_prompts' with repeat > 4).  With S = sum_r a_r:  sum_{r1,r2} |a_r1 - a_r2|^2 = 2 R sum_r |a_r|^2 - 2 |S|^2 and
+// d/da_r = 4 (R a_r - S): two streaming passes over the R feature vectors of a pixel (the second one hits L2), nothing but S
+// in registers.  One warp per (b, pixel); C <= 512.
+__global__ void __launch_bounds__(256) diversity_anyr_kernel(const __nv_bfloat16* __restrict__ feats, float* __restrict__ loss_accum,
+                                                             __nv_bfloat16* __restrict__ dfeat, int R, int B, int HW, int C,
+                                                             float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + warp;   // over B * HW
+  if (item >= (long long)B * HW) return;
+  const int b = (int)(item / HW);
+  const int pix = (int)(item % HW);
+  constexpr int kMaxPerLane = 16;   // C <= 512
+  const int per = (C + 31) / 32;
+  float S[kMaxPerLane];
+#pragma unroll
+  for (int k = 0; k < kMaxPerLane; ++k) S[k] = 0.f;
+  float q = 0.f;                     // sum_r |a_r|^2
+  for (int r = 0; r < R; ++r) {
+    const __nv_bfloat16* f = feats + (((long long)r * B + b) * HW + pix) * C;
+    float v[kMaxPerLane], ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const int c = lane + 32 * k;
+      v[k] = (k < per && c < C) ? __bfloat162float(f[c]) : 0.f;
+      ss += v[k] * v[k];
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / (sqrtf(ss) + 1e-10f);
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) S[k] += v[k] * inv;
+    q += ss * inv * inv;
+  }
+  float s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxPerLane; ++k) s2 += S[k] * S[k];
+  s2 = warp_sum(s2);
+  const float w = scale / ((float)R * R * B * HW);
+  if (lane == 0) atomicAdd(loss_accum, w * (2.0f * R * q - 2.0f * s2));
+  if (!dfeat) return;
+  for (int r = 0; r < R; ++r) {
+    const long long off = (((long long)r * B + b) * HW + pix) * C;
+    const __nv_bfloat16* f = feats + off;
+    float a[kMaxPerLane], ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const int c = lane + 32 * k;
+      a[k] = (k < per && c < C) ? __bfloat162float(f[c]) : 0.f;
+      ss += a[k] * a[k];
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss), inv = 1.0f / (nrm + 1e-10f);
+    float g[kMaxPerLane], dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      a[k] *= inv;
+      g[k] = 4.0f * w * (R * a[k] - S[k]);
+      dot += g[k] * a[k];
+    }
+    dot = warp_sum(dot);
+    const float corr = nrm > 0.f ? (nrm + 1e-10f) / nrm : 0.f;
+    __nv_bfloat16* o = dfeat + off;
+#pragma unroll
+    for (int k = 0; k < kMaxPerLane; ++k) {
+      const int c = lane + 32 * k;
+      if (k < per && c < C) o[c] = __float2bfloat16(inv * (g[k] - a[k] * dot * corr));
+    }
+  }
+}
+
 }  // namespace ffvc
 
 using namespace ffvc;
@@ -222,9 +292,12 @@ extern "C" int ffvc_normalize3_bwd(const float* dy, float* dx_accum, long long n
 }
 extern "C" int ffvc_diversity_tap(const void* feats, float* loss_accum, void* dfeat, int R, int B, int HW, int C, float scale,
                                   void* stream) {
-  if (R < 1 || R > 4 || C > 512) return set_error(FFVC_ERR_UNSUPPORTED, "diversity_tap: repeat <= 4 and C <= 512");
+  if (R < 1 || C > 512) return set_error(FFVC_ERR_UNSUPPORTED, "diversity_tap: C <= 512");
   const long long items = (long long)B * HW;
-  diversity_kernel<4><<<(unsigned)((items + 7) / 8), 256, 0, ST(stream)>>>(CBF(feats), loss_accum, BF(dfeat), R, B, HW, C, scale);
+  if (R <= 4)
+    diversity_kernel<4><<<(unsigned)((items + 7) / 8), 256, 0, ST(stream)>>>(CBF(feats), loss_accum, BF(dfeat), R, B, HW, C, scale);
+  else
+    diversity_anyr_kernel<<<(unsigned)((items + 7) / 8), 256, 0, ST(stream)>>>(CBF(feats), loss_accum, BF(dfeat), R, B, HW, C, scale);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

@@ -6,7 +6,8 @@
 Arithmetic: libffvc_sm100.so — 3x3 convs as tcgen05 implicit GEMMs with a fused ReLU epilogue (halo-reuse kernel on the wide
 layers, im2col K=27 form for the 3-channel first layer), 2x2 max-pool, and a fused normalize_tensor + pairwise-difference
 kernel per tap; backward = dgrad convs with the ReLU mask applied in the epilogue.
-Mode 'between_same_prompts' only (the default, main.py:695); it needs repeat >= 2 to be non-zero.
+Mode 'between_same_prompts' (the default, main.py:695; needs repeat >= 2 to be non-zero) and mode 'all' (main.py:783-787:
+the same expression with repeat = batch, bs = 1 — `forward_backward(xr, N, 1, ...)`).
 """
 import ctypes as C
 

@@ -150,7 +150,8 @@ class FusedAdam:
 class TrainStep:
     def __init__(self, net, vq, perceptor, cutn=8, lr=1e-3, cut_size=224, target_loss_coef=1.0, world_size=1,
                  process_group=None, seed=0, l2_coef=0.0, tv_coef=0.0, diversity_coef=0.0, repeat=1, lpips_net=None,
-                 clip_grad_norm=None, scheduler=None, total_steps=0, use_ema=False, ema_decay=0.995):
+                 clip_grad_norm=None, scheduler=None, total_steps=0, use_ema=False, ema_decay=0.995,
+                 diversity_mode="between_same_prompts"):
         self.net, self.vq, self.perceptor = net, vq, perceptor
         self.mix = net.engine()
         self.dec = vq.engine()
@@ -163,6 +164,9 @@ class TrainStep:
         self.aux_loss = torch.zeros(3, device=self.dev, dtype=F32)           # [l2, tv, -diversity] (already scaled by their coefficients)
         self.diversity_coef, self.repeat = float(diversity_coef), int(repeat)  # main.py:532-537,739-740,776-791
         self.div = lpips_net.engine() if (lpips_net is not None and self.diversity_coef != 0) else None
+        if diversity_mode not in ("between_same_prompts", "all"):       # main.py:695,788-789
+            raise ValueError("diversity_mode should be 'between_same_prompts' lr 'all'")
+        self.diversity_mode = diversity_mode
         self.opt = FusedAdam(self.mix, lr=lr)
         self.world, self.pg = world_size, process_group
         self.opt.set_grad_scale(1.0 / world_size)
@@ -171,6 +175,8 @@ class TrainStep:
         if scheduler is not None:                                          # main.py:702-709
             if scheduler != "cosine":
                 raise ValueError(scheduler)
+            if total_steps <= 0:
+                raise ValueError("the cosine schedule needs total_steps (T_max = number of training steps, main.py:704-705)")
             self.opt.set_cosine(total_steps)
         if use_ema:                                                        # main.py:510,524-525,843-844
             self.opt.enable_ema(ema_decay)
@@ -207,7 +213,9 @@ class TrainStep:
         del sv_e
         dimg = cut.backward(sv_c, dpatch)
         del sv_c, dpatch
-        if self.div is not None and self.repeat > 1:                     # - diversity_coef * div, main.py:776-791,831
+        if self.div is not None and self.diversity_mode == "all":        # every pair of the (repeated) batch, main.py:783-787
+            self.div.forward_backward(img, B, 1, self.diversity_coef, dimg, self.aux_loss[2:3])
+        elif self.div is not None and self.repeat > 1:                   # - diversity_coef * div, main.py:776-782,831
             self.div.forward_backward(img, self.repeat, B // self.repeat, self.diversity_coef, dimg, self.aux_loss[2:3])
         if self.tv_coef > 0:                                             # tv_coef * tv_loss(xr), main.py:769-773,831
             H = img.shape[1]

@@ -1,5 +1,5 @@
 """ORACLE (test infrastructure, not product): CPU fp32 restatement of the LPIPS-VGG16 diversity term of the train step,
-main.py:776-791 (mode 'between_same_prompts') + `normalize_tensor` and the `vgg16` feature slices of
+main.py:776-791 (modes 'between_same_prompts' and 'all') + `normalize_tensor` and the `vgg16` feature slices of
 taming.modules.losses.lpips (absent package; torchvision VGG16 `features` split at relu1_2, relu2_2, relu3_3, relu4_3,
 relu5_3 — SURVEY App. A.5).  PARITY UNPINNED at the taming / torchvision-weights boundary: structure restated, weights
 random.  The loop over taps and the pairwise-difference expression are the reference's own lines."""
@@ -39,10 +39,16 @@ def normalize_tensor(x, eps=1e-10):                       # taming lpips.normali
     return x / (torch.sqrt(torch.sum(x ** 2, dim=1, keepdim=True)) + eps)
 
 
-def diversity(sd, xr, repeat, bs, mean, std):             # main.py:776-782
+def diversity(sd, xr, repeat, bs, mean, std, mode="between_same_prompts"):             # main.py:776-789
     div = 0
     for feats in vgg_taps(sd, (xr - mean) / std):
         feats = normalize_tensor(feats)
         _, cc, hh, ww = feats.shape
-        div = div + ((feats.view(repeat, 1, bs, cc, hh, ww) - feats.view(1, repeat, bs, cc, hh, ww)) ** 2).sum(dim=3).mean()
+        if mode == "between_same_prompts":
+            div = div + ((feats.view(repeat, 1, bs, cc, hh, ww) - feats.view(1, repeat, bs, cc, hh, ww)) ** 2).sum(dim=3).mean()
+        elif mode == "all":                                                                    # main.py:783-787
+            nb = len(feats)
+            div = div + ((feats.view(nb, 1, cc, hh, ww) - feats.view(1, nb, cc, hh, ww)) ** 2).sum(dim=2).mean()
+        else:
+            raise ValueError("diversity_mode should be 'between_same_prompts' lr 'all'")
     return div

@@ -503,6 +503,27 @@ def test_sln_and_vitgan_attention_kernels():
     assert torch.equal(dst[:, :126], src.to(BF)) and float(dst[:, 126:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("R,C,HW", [(2, 64, 50), (4, 512, 9), (5, 128, 33), (16, 512, 7), (7, 40, 21)])
+def test_diversity_tap_kernels_vs_reference_expression(R, C, HW):
+    """main.py:779-787 on one tap: R <= 4 takes the in-register kernel, R > 4 (mode 'all': R = batch, B = 1; or repeat > 4)
+    the streaming kernel; value and gradient w.r.t. the features"""
+    import oracle.lpips as ol
+    for B in (1, 3):
+        f = rnd(R * B, HW, C, seed=R + B).abs() + 0.05                      # post-ReLU features
+        fr = f.float().cpu().permute(0, 2, 1).reshape(R * B, C, HW, 1).clone().requires_grad_(True)
+        a = ol.normalize_tensor(fr)
+        div = ((a.view(R, 1, B, C, HW, 1) - a.view(1, R, B, C, HW, 1)) ** 2).sum(dim=3).mean()
+        (-0.6 * div).backward()
+        if B == 1:                                                          # 'all' is the same expression with B = 1
+            div_all = ((a.view(R, 1, C, HW, 1) - a.view(1, R, C, HW, 1)) ** 2).sum(dim=2).mean()
+            assert abs(div_all.item() - div.item()) < 1e-6
+        loss = torch.zeros(1, device=DEV)
+        d = torch.empty_like(f)
+        call("diversity_tap", f, loss, d, R, B, HW, C, -0.6)
+        assert abs(loss.item() + 0.6 * div.item()) < 2e-3 * abs(0.6 * div.item()) + 1e-6
+        close(d.float().cpu().view(R * B, HW, C), fr.grad.view(R * B, C, HW).permute(0, 2, 1), 2e-2)
+
+
 def test_lpips_diversity_engine_vs_oracle():
     """VGG16 taps + normalize_tensor + pairwise differences (main.py:776-782): value and gradient w.r.t. the image"""
     import oracle.lpips as ol
