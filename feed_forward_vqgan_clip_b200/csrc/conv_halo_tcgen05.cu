@@ -32,7 +32,8 @@ static constexpr int kHaloBytes = kHaloRows * kHaloPix * 128;         // 66,560 
 static constexpr int kHaloStride = (kHaloBytes + 1023) / 1024 * 1024; // 67,584 B (keeps every buffer 1024 B-aligned)
 static constexpr int kBStages = 4;
 static constexpr int kBStageBytes = 128 * 64 * 2;                     // up to 128 output channels x 64 input channels
-static constexpr int kHaloSmem = 2 * kHaloStride + kBStages * kBStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/;
+static constexpr int kHaloSmem = 2 * kHaloStride + kBStages * kBStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/ +
+                                 4096 /*GroupNorm partial sums: [2 tiles][8 warps][4 chunks][16]*/;
 static constexpr int kHaloThreads = 320;
 static constexpr int kHaloEpiWarps = 8;
 
@@ -56,6 +57,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   auto tempty_bar = [&](int a) { return bar_base + 8u * (14 + a); };
   const uint32_t tmem_slot = bar_base + 8u * 16;
   const uint32_t bias_smem = bar_base + 256u;
+  const uint32_t gn_smem = bias_smem + 2048u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,6 +180,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int sub = (warp - 2) >> 2;
     const int etid = threadIdx.x - 64;
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
+    float* gn_part = reinterpret_cast<float*>(smem_raw + (gn_smem - smem_u32(smem_raw)));   // [2 (acc)][8 warps][4 chunks][16]
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 8 == 0);
@@ -240,13 +243,61 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           for (int j = 0; j < CW / 8; ++j) cur_res[j] = pf_res[j];
         }
         if ((want_aux || want_res) && c + CW < p.block_n) prefetch(c + CW);
-        if (c < p.N)
-          epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok && (c + CW <= p.N), sbias + c, cur_aux, cur_res, vec32_ok && (c + CW <= p.N));
+        if (!p.gn_ws) {
+          if (c < p.N)
+            epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok && (c + CW <= p.N), sbias + c, cur_aux, cur_res, vec32_ok && (c + CW <= p.N));
+        } else {
+          // GroupNorm(32) statistics of the tensor being written (Cout = 128: 4 channels per group, 8 groups per 32-column
+          // chunk), taken from the bf16-rounded values a later pass over the tensor would read.  Per lane 8 sums + 8 sums of
+          // squares; a recursive-halving butterfly (8+4+2+1+1 = 16 shuffles) leaves lane L with kind (L>>4) of group (L>>1)&7
+          // summed over the warp's 32 pixels; one slot per warp and chunk in shared memory, folded per tile below.
+          float2 vf[CW / 2];
+          epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok, sbias + c, cur_aux, cur_res, vec32_ok, vf);
+          float vals[16];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float2 a = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g].x, vf[2 * g].y));
+            const float2 b = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g + 1].x, vf[2 * g + 1].y));
+            vals[g] = (a.x + a.y) + (b.x + b.y);
+            vals[8 + g] = fmaf(a.x, a.x, a.y * a.y) + fmaf(b.x, b.x, b.y * b.y);
+          }
+          const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+          float n8[8], n4[4], n2[2];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float send = b4 ? vals[i] : vals[i + 8], keep = b4 ? vals[i + 8] : vals[i];
+            n8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float send = b3 ? n8[i] : n8[i + 4], keep = b3 ? n8[i + 4] : n8[i];
+            n4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const float send = b2 ? n4[i] : n4[i + 2], keep = b2 ? n4[i + 2] : n4[i];
+            n2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          float n1 = (b1 ? n2[1] : n2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? n2[0] : n2[1], 2);
+          n1 += __shfl_xor_sync(0xffffffffu, n1, 1);
+          if ((lane & 1) == 0) gn_part[(((acc * 8 + (warp - 2)) * 4 + (c >> 5)) << 4) + ((lane >> 4) << 3) + ((lane >> 1) & 7)] = n1;
+        }
         __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) mbar_arrive(tempty_bar(acc));           // the accumulator is free for the MMA warp before the fold below
+      if (p.gn_ws) {
+        // fold the 8 warps' slots of this tile: thread (kind, group) -> one double atomic per (image, group, kind) and tile
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (etid < 64) {
+          const int kind = etid >> 5, g = etid & 31;
+          float tot = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) tot += gn_part[(((acc * 8 + w8) * 4 + (g >> 3)) << 4) + (kind << 3) + (g & 7)];
+          atomicAdd(&p.gn_ws[((long long)img * 32 + g) * 2 + kind], (double)tot);
+        }
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -294,9 +345,12 @@ static int encode4(CUtensorMap* m, const void* base, const uint64_t* dims, const
 using namespace ffvc;
 
 // x: [n][h][w][cin] bf16 NHWC; w: [cout][9][cin] bf16 (tap-major); out: [n*h*w][ldc] bf16 (fp32 when out_fp32).  Epilogue fields as ffvc_gemm.
-extern "C" int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
-                                 const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32, void* stream) {
+static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                               const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32,
+                               double* gn_ws, void* stream) {
   if (!x || !w || !out) return set_error(FFVC_ERR_ARG, "conv_halo: null pointer");
+  if (gn_ws && (cout != 128 || out_fp32 || ldc % 16 != 0))
+    return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: epilogue GroupNorm statistics need Cout = 128 (32 groups of 4), bf16 output");
   if (wd % 128 != 0 || h % 2 != 0) return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: needs W % 128 == 0 and even H");
   if (cin % 64 != 0 || cout < 1 || cout > 128) return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: needs Cin % 64 == 0, Cout <= 128");
   static bool attr_done = false;
@@ -346,6 +400,8 @@ extern "C" int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n,
   p.act = act;
   p.mul_mode = aux ? mul_mode : 0;
   p.alpha = 1.0f;
+  p.gn_ws = gn_ws;
+  if (gn_ws) cudaMemsetAsync(gn_ws, 0, sizeof(double) * 2 * 32 * (size_t)n, reinterpret_cast<cudaStream_t>(stream));
   const long long tiles = (long long)n * (h / 2) * (wd / 128);
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
@@ -353,4 +409,19 @@ extern "C" int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n,
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   count_launch();
   return FFVC_OK;
+}
+
+extern "C" int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                                 const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32, void* stream) {
+  return conv3x3_halo_launch(x, w, out, n, h, wd, cin, cout, ldc, bias, res, aux, mul_mode, act, out_fp32, nullptr, stream);
+}
+
+// Same convolution; the epilogue also accumulates, per (image, group), the sum and the sum of squares of the tensor it stores
+// (GroupNorm(32, 128) statistics: taming `Normalize` of the NEXT layer) into gn_ws[n][32][2] doubles
+// (zeroed here) — ffvc_groupnorm_finalize turns them into mean / rstd, and the separate statistics pass over the tensor
+// (one full read) is not needed.
+extern "C" int ffvc_conv3x3_halo_gn(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                                    const float* bias, const void* res, double* gn_ws, void* stream) {
+  if (!gn_ws) return set_error(FFVC_ERR_ARG, "conv_halo_gn: null statistics workspace");
+  return conv3x3_halo_launch(x, w, out, n, h, wd, cin, cout, ldc, bias, res, nullptr, 0, 0, 0, gn_ws, stream);
 }

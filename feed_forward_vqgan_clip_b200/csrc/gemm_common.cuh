@@ -39,6 +39,7 @@ struct GemmDev {
   unsigned long long* argmin;   // optional: per-row arg-min epilogue (see ffvc_gemm_params.argmin_out)
   int stream_k;                 // 1: contiguous (tile, k-block) ranges per worker instead of whole tiles (atomic fp32 output)
   int tma_store;                // 1: the epilogue warps stage their results in shared memory and TMA-store them
+  double* gn_ws;                // conv3x3_halo only: per-(image, group) sum / sum of squares of the stored output (GroupNorm(32) statistics)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -201,7 +202,7 @@ __device__ __forceinline__ void unpack_bf16xN(const uint4 (&pk)[CW / 8], float (
 template <int CW, int kEpi = -1>
 __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t (&r)[CW], int gn0, long long off, float rbias,
                                                bool vec, const float* sbias, const uint4 (&pf_aux)[CW / 8],
-                                               const uint4 (&pf_res)[CW / 8], bool vec32 = false) {
+                                               const uint4 (&pf_res)[CW / 8], bool vec32 = false, float2* vfinal = nullptr) {
   using E = Epi<kEpi>;
   const int ncols = min(CW, p.N - gn0);
   float2 v[CW / 2];
@@ -266,6 +267,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, const uint32_t 
     }
 #pragma unroll
     for (int i = 0; i < CW / 2; ++i) v[i] = __fadd2_rn(v[i], x[i]);
+  }
+  if (vfinal) {                 // hand the final values to the caller (GroupNorm statistics of the output)
+#pragma unroll
+    for (int i = 0; i < CW / 2; ++i) vfinal[i] = v[i];
   }
   if (E::f32(p)) {
     float* o = reinterpret_cast<float*>(p.out) + off;

@@ -1396,6 +1396,16 @@ extern "C" int ffvc_groupnorm_stats(const void* x, double* ws, float* mean, floa
   return FFVC_OK;
 }
 
+// ws[N*G][2] = (sum, sum of squares) per (sample, group) -> mean / rstd.  For statistics produced elsewhere (the conv epilogue).
+extern "C" int ffvc_groupnorm_finalize(const double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps,
+                                       void* stream) {
+  if (G <= 0 || C % G != 0) return set_error(FFVC_ERR_ARG, "groupnorm_finalize: C must be divisible by G");
+  groupnorm_finalize_kernel<<<(N * G + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ws, mean, rstd, N * G,
+                                                                                                       (double)HW * (C / G), eps);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
 extern "C" int ffvc_groupnorm_apply(const void* x, const float* mean, const float* rstd, const float* gamma,
                                     const float* beta, void* y, int N, int HW, int C, int G, int swish, void* stream) {
   int rc = gn_check(C, G);

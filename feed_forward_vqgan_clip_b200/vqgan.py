@@ -181,6 +181,7 @@ class DecoderEngine:
         self.cnorm = torch.empty(cb.shape[0], device=self.dev, dtype=F32)
         call("rownorm2", cb, self.cnorm, cb.shape[0], cb.shape[1])
         self._ws = None
+        self._epi_stats = {}            # data_ptr of a conv output -> (mean, rstd, numel) from that conv's epilogue
 
     def valid(self):
         return self.model.post_quant_conv.weight.data_ptr() == self._ptr
@@ -200,8 +201,20 @@ class DecoderEngine:
         return (self.USE_HALO and W % 128 == 0 and H % 2 == 0 and cin % 64 == 0 and cout <= 128
                 and (cout % 8 == 0 or out_f32))
 
+    # GroupNorm statistics from the epilogue of the conv that writes the tensor (ffvc_conv3x3_halo_gn): every forward
+    # 128-channel halo conv of the decoder feeds a Normalize (norm2 of its block, norm1 of the next block, norm_out), so its
+    # (mean, rstd) are produced on the fly and `gn` skips the statistics pass.  FFVC_GN_EPI_STATS=0 selects the separate pass.
+    GN_EPI_STATS = os.environ.get("FFVC_GN_EPI_STATS", "0") == "1"
+
     def conv3(self, x, name, N, H, W, cin, cout, res=None, out_f32=False):
         out = self._new(N * H * W, cout, dtype=F32 if out_f32 else BF16)
+        if self.GN_EPI_STATS and cout == 128 and not out_f32 and self._halo_ok(H, W, cin, cout):
+            ws = self._gn_ws(N * 65)
+            mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
+            call("conv3x3_halo_gn", x, self.pk[name + ".w"], out, N, H, W, cin, cout, cout, self.pk[name + ".b"], res, ws)
+            call("groupnorm_finalize", ws, mean, rstd, N, H * W, cout, 32, 1e-6)
+            self._epi_stats[out.data_ptr()] = (mean, rstd, N * H * W * cout)
+            return out
         if self._halo_ok(H, W, cin, cout, out_f32):      # incl. the 128 -> 3 conv_out (fp32 image, scalar stores)
             call("conv3x3_halo", x, self.pk[name + ".w"], out, N, H, W, cin, cout, cout, self.pk[name + ".b"], res, None, 0, 0,
                  int(out_f32))
@@ -243,7 +256,11 @@ class DecoderEngine:
             call("groupnorm_fused_fwd", x, self.pk[name + ".g"], self.pk[name + ".be"], y, mean, rstd, self._gn_ws(N * 65), N, HW, C,
                  32, int(swish), 1e-6)
             return y, (mean, rstd)
-        call("groupnorm_stats", x, self._gn_ws(N * 65), mean, rstd, N, HW, C, 32, 1e-6)
+        st = self._epi_stats.pop(x.data_ptr(), None)
+        if st is not None and st[2] == N * HW * C:       # statistics came with the conv that wrote x
+            mean, rstd = st[0], st[1]
+        else:
+            call("groupnorm_stats", x, self._gn_ws(N * 65), mean, rstd, N, HW, C, 32, 1e-6)
         call("groupnorm_apply", x, mean, rstd, self.pk[name + ".g"], self.pk[name + ".be"], y, N, HW, C, 32, int(swish))
         return y, (mean, rstd)
 
@@ -326,6 +343,7 @@ class DecoderEngine:
         cfg = self.cfg
         N, S = zq.shape[0], zq.shape[1]
         tape = []
+        self._epi_stats.clear()
         H = W = S
         E, Z = cfg["embed_dim"], cfg["z_channels"]
         block_in = cfg["ch"] * cfg["ch_mult"][-1]

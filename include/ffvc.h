@@ -118,6 +118,13 @@ int ffvc_gemm_set_stream_k(int on);
  * Epilogue: + bias[cout] (fp32, optional), act, * act'(aux) (mul_mode), + res (bf16, optional), like ffvc_gemm. */
 int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
                       const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32, void* stream);
+/* same conv (bias, optional residual, bf16 out, Cout = 128); its epilogue also accumulates the GroupNorm(32) statistics of the
+ * tensor it writes — sum and sum of squares per (image, group) of the bf16-rounded output — into gn_ws[n][32][2] doubles
+ * (zeroed by the call).  ffvc_groupnorm_finalize(gn_ws, ...) gives the mean / rstd taming's next `Normalize` needs, so
+ * ffvc_groupnorm_stats (one more read of the tensor) is skipped. */
+int ffvc_conv3x3_halo_gn(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                         const float* bias, const void* res, double* gn_ws, void* stream);
+int ffvc_groupnorm_finalize(const double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (bf16 in/out, fp32 stats).  mlp_mixer_pytorch.py:11,37; cloob.py:170-176.

@@ -386,3 +386,32 @@ def test_stream_k_wgrad_matches_split_k(M, N, K, segs, two):
     _check(outs[0] - 0.25, ref, 2e-3)
     _check(outs[1] - 0.25, ref, 2e-3)
     assert (outs[0] - outs[1]).abs().max().item() <= 2e-3 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("n,h,w,cin,with_res", [(2, 128, 128, 128, True), (3, 4, 256, 64, False), (1, 256, 256, 128, True)])
+def test_conv3x3_halo_epilogue_groupnorm_statistics(n, h, w, cin, with_res):
+    """ffvc_conv3x3_halo_gn: same output as ffvc_conv3x3_halo, and the (mean, rstd) its epilogue produces equal those of the
+    separate statistics pass over the stored tensor (taming Normalize = GroupNorm(32, eps 1e-6))"""
+    from feed_forward_vqgan_clip_b200.ops import call
+    BF = torch.bfloat16
+    cout = 128
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(n, h, w, cin, generator=g)).to(DEV).to(BF)
+    wt = (torch.randn(cout, 9, cin, generator=g) * (9 * cin) ** -0.5).to(DEV).to(BF)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    res = torch.randn(n * h * w, cout, generator=g).to(DEV).to(BF) if with_res else None
+    out0 = torch.empty(n * h * w, cout, device=DEV, dtype=BF)
+    call("conv3x3_halo", x, wt, out0, n, h, w, cin, cout, cout, bias, res, None, 0, 0, 0)
+    out1 = torch.empty_like(out0)
+    ws = torch.full((n * 65,), 123.0, device=DEV, dtype=torch.float64)          # the call zeroes what it uses
+    call("conv3x3_halo_gn", x, wt, out1, n, h, w, cin, cout, cout, bias, res, ws)
+    assert torch.equal(out0, out1)
+    mean, rstd = torch.empty(n * 32, device=DEV), torch.empty(n * 32, device=DEV)
+    call("groupnorm_finalize", ws, mean, rstd, n, h * w, cout, 32, 1e-6)
+    ws2 = torch.empty(n * 65, device=DEV, dtype=torch.float64)
+    mean2, rstd2 = torch.empty_like(mean), torch.empty_like(rstd)
+    call("groupnorm_stats", out1, ws2, mean2, rstd2, n, h * w, cout, 32, 1e-6)
+    assert torch.allclose(mean, mean2, atol=1e-5, rtol=1e-5), (mean - mean2).abs().max()
+    assert torch.allclose(rstd, rstd2, rtol=1e-4), ((rstd - rstd2) / rstd2).abs().max()
+    o = out1.float().view(n, h * w, 32, 4)
+    assert torch.allclose(mean.view(n, 32), o.mean((1, 3)), atol=1e-4)

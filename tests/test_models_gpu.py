@@ -194,6 +194,33 @@ def test_decoder_forward_backward_vs_oracle():
     close(zc.grad, zr.grad, 6e-2, "decoder dgrad")
 
 
+def test_decoder_epilogue_groupnorm_statistics_match_separate_pass():
+    """full-size f16/16384 decoder (256x256 image, B = 1): GroupNorm statistics taken from the conv epilogues
+    (ffvc_conv3x3_halo_gn, the 128-channel layers at 128x128 and 256x256) against the separate statistics pass"""
+    from feed_forward_vqgan_clip_b200.vqgan import DecoderEngine, VQModel
+    torch.manual_seed(5)
+    vq = VQModel().to(DEV).eval().requires_grad_(False)
+    eng = vq.engine()
+    g = torch.Generator().manual_seed(6)
+    zq = torch.randn(1, 16, 16, 256, generator=g).to(DEV).to(torch.bfloat16)
+    dimg = torch.randn(1, 256, 256, 3, generator=g).to(DEV)
+    outs = []
+    old = DecoderEngine.GN_EPI_STATS
+    try:
+        for flag in (False, True):
+            DecoderEngine.GN_EPI_STATS = flag
+            img, tape = eng.forward(zq, post=False)
+            assert not eng._epi_stats, "every epilogue statistic must be consumed by the Normalize that follows its conv"
+            dz = eng.backward(tape, dimg.clone(), post=False)
+            outs.append((img.clone(), dz.float().clone()))
+    finally:
+        DecoderEngine.GN_EPI_STATS = old
+    (i0, d0), (i1, d1) = outs
+    assert (i0 - i1).abs().max().item() <= 2e-2 * i0.abs().max().item()
+    assert cos(d0, d1) > 0.999
+    close(d1, d0, 3e-2, "decoder dgrad, epilogue statistics")
+
+
 def test_synth_vs_oracle_with_straight_through():
     vq, sd = _vq_pair(seed=4)
     g = torch.Generator().manual_seed(3)
