@@ -204,11 +204,13 @@ class DecoderEngine:
     # GroupNorm statistics from the epilogue of the conv that writes the tensor (ffvc_conv3x3_halo_gn): every forward
     # 128-channel halo conv of the decoder feeds a Normalize (norm2 of its block, norm1 of the next block, norm_out), so its
     # (mean, rstd) are produced on the fly and `gn` skips the statistics pass.  FFVC_GN_EPI_STATS=0 selects the separate pass.
-    GN_EPI_STATS = os.environ.get("FFVC_GN_EPI_STATS", "0") == "1"
+    GN_EPI_STATS = os.environ.get("FFVC_GN_EPI_STATS", "1") == "1"    # measured +0.9 % prompts/s (profiles/r01_ab_kernels.md)
 
-    def conv3(self, x, name, N, H, W, cin, cout, res=None, out_f32=False):
+    def conv3(self, x, name, N, H, W, cin, cout, res=None, out_f32=False, gn_next=True):
+        """gn_next: the output goes straight into a Normalize (true for every decoder conv but the last one of a level
+        that is followed by Upsample, and conv_out)"""
         out = self._new(N * H * W, cout, dtype=F32 if out_f32 else BF16)
-        if self.GN_EPI_STATS and cout == 128 and not out_f32 and self._halo_ok(H, W, cin, cout):
+        if gn_next and self.GN_EPI_STATS and cout == 128 and not out_f32 and self._halo_ok(H, W, cin, cout):
             ws = self._gn_ws(N * 65)
             mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
             call("conv3x3_halo_gn", x, self.pk[name + ".w"], out, N, H, W, cin, cout, cout, self.pk[name + ".b"], res, ws)
@@ -270,14 +272,14 @@ class DecoderEngine:
              self.pk[name + ".be"], self._gn_ws(N * 65), add, dx, N, HW, C, 32, int(swish))
         return dx
 
-    def resblock(self, x, name, N, H, W, cin, cout, tape):
+    def resblock(self, x, name, N, H, W, cin, cout, tape, gn_next=True):
         HW = H * W
         a1, st1 = self.gn(x, name + ".norm1", N, HW, cin, True)
         h1 = self.conv3(a1, name + ".conv1", N, H, W, cin, cout)
         del a1
         a2, st2 = self.gn(h1, name + ".norm2", N, HW, cout, True)
         short = x if cin == cout else self.conv1(x, name + ".nin_shortcut", N * HW, cin, cout)
-        out = self.conv3(a2, name + ".conv2", N, H, W, cout, cout, res=short)
+        out = self.conv3(a2, name + ".conv2", N, H, W, cout, cout, res=short, gn_next=gn_next)
         del a2, short
 
         def bwd(d):
@@ -357,7 +359,9 @@ class DecoderEngine:
         c = block_in
         for i_level, blocks, has_attn, has_up in self.layout:
             for j, (cin, cout) in enumerate(blocks):
-                h = self.resblock(h, "decoder.up.%d.block.%d" % (i_level, j), N, H, W, cin, cout, tape)
+                last = j == len(blocks) - 1
+                h = self.resblock(h, "decoder.up.%d.block.%d" % (i_level, j), N, H, W, cin, cout, tape,
+                                  gn_next=has_attn or not (last and has_up))     # the level's last block feeds Upsample, not a Normalize
                 if has_attn:
                     h = self.attn(h, "decoder.up.%d.attn.%d" % (i_level, j), N, H, W, cout, tape)
                 c = cout
