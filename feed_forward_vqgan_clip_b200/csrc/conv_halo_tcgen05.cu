@@ -187,7 +187,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // 32-byte (256-bit) row accesses when every row starts on a 32-byte boundary (bf16 output): half the L1 requests
     const bool vec32_ok = vec_ok && !p.out_fp32 && (p.ldc % 16 == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.res)) & 31) == 0;
-    const bool want_aux = p.mul_mode != FFVC_ACT_NONE, want_res = p.res != nullptr;
+    const bool gnb = p.gn_ws && p.gn_bwd;
+    const bool want_aux = p.mul_mode != FFVC_ACT_NONE || gnb, want_res = p.res != nullptr;
+    if (gnb && etid < 128) {                  // gamma / beta of the Normalize, once per CTA (the bias staging area is free: dgrad)
+      sbias_all[etid] = p.gn_gamma[etid];
+      sbias_all[128 + etid] = p.gn_beta[etid];
+    }
     for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int tx = (int)(t % tiles_x);
       const int ty = (int)((t / tiles_x) % tiles_y);
@@ -197,6 +202,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       float* sbias = sbias_all + acc * 256;
       if (p.bias_mode == 1) {
         if (etid < p.block_n) sbias[etid] = (etid < p.N) ? p.bias[etid] : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      float* gstat = sbias_all + 256 + acc * 64;       // this tile's image: [32] rstd, [32] -mean * rstd
+      if (gnb) {
+        if (etid < 32) {
+          const float rs = p.gn_rstd[(long long)img * 32 + etid];
+          gstat[etid] = rs;
+          gstat[32 + etid] = -p.gn_mean[(long long)img * 32 + etid] * rs;
+        }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       constexpr int CW = 32;
@@ -254,12 +268,39 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           float2 vf[CW / 2];
           epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok, sbias + c, cur_aux, cur_res, vec32_ok, vf);
           float vals[16];
+          if (!gnb) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const float2 a = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g].x, vf[2 * g].y));
-            const float2 b = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g + 1].x, vf[2 * g + 1].y));
-            vals[g] = (a.x + a.y) + (b.x + b.y);
-            vals[8 + g] = fmaf(a.x, a.x, a.y * a.y) + fmaf(b.x, b.x, b.y * b.y);
+            for (int g = 0; g < 8; ++g) {
+              const float2 a = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g].x, vf[2 * g].y));
+              const float2 b = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g + 1].x, vf[2 * g + 1].y));
+              vals[g] = (a.x + a.y) + (b.x + b.y);
+              vals[8 + g] = fmaf(a.x, a.x, a.y * a.y) + fmaf(b.x, b.x, b.y * b.y);
+            }
+          } else {
+            // backward statistics of the Normalize + swish whose output gradient this conv just produced (vf = dy, aux = its
+            // input x): g = dy * swish'(gamma * xhat + beta) * gamma;  vals = sum g | sum g * xhat per group (groupnorm_bwd_stats_kernel)
+            float2 xx[CW / 2];
+            unpack_bf16x2N<CW>(cur_aux, xx);
+            const float* sgam = sbias_all + c;
+            const float* sbet = sbias_all + 128 + c;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const float rs = gstat[(c >> 2) + g], mrs = gstat[32 + (c >> 2) + g];
+              float sg = 0.f, sq = 0.f;
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const float2 d = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g + h2].x, vf[2 * g + h2].y));
+                const float2 xv = xx[2 * g + h2];
+                const float gam0 = sgam[4 * g + 2 * h2], gam1 = sgam[4 * g + 2 * h2 + 1];
+                const float xh0 = fmaf(xv.x, rs, mrs), xh1 = fmaf(xv.y, rs, mrs);
+                const float g0 = d.x * swish_grad_fast_f(fmaf(xh0, gam0, sbet[4 * g + 2 * h2])) * gam0;
+                const float g1 = d.y * swish_grad_fast_f(fmaf(xh1, gam1, sbet[4 * g + 2 * h2 + 1])) * gam1;
+                sg += g0 + g1;
+                sq = fmaf(g0, xh0, fmaf(g1, xh1, sq));
+              }
+              vals[g] = sg;
+              vals[8 + g] = sq;
+            }
           }
           const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
           float n8[8], n4[4], n2[2];
@@ -347,7 +388,8 @@ using namespace ffvc;
 // x: [n][h][w][cin] bf16 NHWC; w: [cout][9][cin] bf16 (tap-major); out: [n*h*w][ldc] bf16 (fp32 when out_fp32).  Epilogue fields as ffvc_gemm.
 static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
                                const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32,
-                               double* gn_ws, void* stream) {
+                               double* gn_ws, void* stream, const float* gnb_mean = nullptr, const float* gnb_rstd = nullptr,
+                               const float* gnb_gamma = nullptr, const float* gnb_beta = nullptr) {
   if (!x || !w || !out) return set_error(FFVC_ERR_ARG, "conv_halo: null pointer");
   if (gn_ws && (cout != 128 || out_fp32 || ldc % 16 != 0))
     return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: epilogue GroupNorm statistics need Cout = 128 (32 groups of 4), bf16 output");
@@ -401,6 +443,13 @@ static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, i
   p.mul_mode = aux ? mul_mode : 0;
   p.alpha = 1.0f;
   p.gn_ws = gn_ws;
+  if (gnb_mean) {
+    p.gn_bwd = 1;
+    p.gn_mean = gnb_mean;
+    p.gn_rstd = gnb_rstd;
+    p.gn_gamma = gnb_gamma;
+    p.gn_beta = gnb_beta;
+  }
   if (gn_ws) cudaMemsetAsync(gn_ws, 0, sizeof(double) * 2 * 32 * (size_t)n, reinterpret_cast<cudaStream_t>(stream));
   const long long tiles = (long long)n * (h / 2) * (wd / 128);
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
@@ -424,4 +473,17 @@ extern "C" int ffvc_conv3x3_halo_gn(const void* x, const void* w, void* out, int
                                     const float* bias, const void* res, double* gn_ws, void* stream) {
   if (!gn_ws) return set_error(FFVC_ERR_ARG, "conv_halo_gn: null statistics workspace");
   return conv3x3_halo_launch(x, w, out, n, h, wd, cin, cout, ldc, bias, res, nullptr, 0, 0, 0, gn_ws, stream);
+}
+
+// dgrad form with the backward statistics of the Normalize + swish in FRONT of the forward conv: `out` (= dy of that layer,
+// Cout = 128 channels) is stored as usual; the epilogue also reads the layer's input gn_x at the same positions and
+// accumulates sum g and sum g * xhat per (image, group), g = dy * swish'(gamma * xhat + beta) * gamma, into gn_ws[n][32][2]
+// doubles (zeroed here) — exactly what ffvc_groupnorm_bwd's first pass computes from two more reads of dy and x;
+// ffvc_groupnorm_bwd_apply finishes the job.
+extern "C" int ffvc_conv3x3_halo_gnbwd(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                                       const void* res, const void* gn_x, const float* gn_mean, const float* gn_rstd,
+                                       const float* gn_gamma, const float* gn_beta, double* gn_ws, void* stream) {
+  if (!gn_ws || !gn_x || !gn_mean || !gn_rstd || !gn_gamma || !gn_beta) return set_error(FFVC_ERR_ARG, "conv_halo_gnbwd: null pointer");
+  return conv3x3_halo_launch(x, w, out, n, h, wd, cin, cout, ldc, nullptr, res, gn_x, 0, 0, 0, gn_ws, stream, gn_mean, gn_rstd,
+                             gn_gamma, gn_beta);
 }

@@ -40,6 +40,13 @@ struct GemmDev {
   int stream_k;                 // 1: contiguous (tile, k-block) ranges per worker instead of whole tiles (atomic fp32 output)
   int tma_store;                // 1: the epilogue warps stage their results in shared memory and TMA-store them
   double* gn_ws;                // conv3x3_halo only: per-(image, group) sum / sum of squares of the stored output (GroupNorm(32) statistics)
+  // conv3x3_halo only, gn_bwd = 1: the stored output is dy of a Normalize + swish whose INPUT is `aux`; the epilogue accumulates the
+  // backward statistics sum g, sum g * xhat (g = dy * swish'(u) * gamma, u = gamma * xhat + beta) into gn_ws instead
+  int gn_bwd;
+  const float* gn_mean;         // [images][32]
+  const float* gn_rstd;
+  const float* gn_gamma;        // [128]
+  const float* gn_beta;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -1429,6 +1429,39 @@ static void gn_bwd_launch(dim3 grid, cudaStream_t st, const __nv_bfloat16* dyb, 
                                                          1.0f / ((float)HW * (C / G)), swish);
 }
 
+template <int GPV>
+static void gn_bwd_apply_launch(dim3 grid, cudaStream_t st, const __nv_bfloat16* dyb, const __nv_bfloat16* xb, const float* mean,
+                                const float* rstd, const float* gamma, const float* beta, const double* ws, const __nv_bfloat16* add,
+                                __nv_bfloat16* dx, int HW, int C, int G, int ppc, int swish) {
+  groupnorm_bwd_apply_kernel<GPV><<<grid, 256, 0, st>>>(dyb, xb, mean, rstd, gamma, beta, ws, add, dx, HW, C, G, ppc,
+                                                         1.0f / ((float)HW * (C / G)), swish);
+}
+
+// second pass of ffvc_groupnorm_bwd alone: sums[N*G][2] = (sum g, sum g * xhat) were produced elsewhere (the dgrad conv's
+// epilogue, ffvc_conv3x3_halo_gnbwd).
+extern "C" int ffvc_groupnorm_bwd_apply(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                                        const float* beta, const double* sums, const void* add, void* dx, int N, int HW, int C,
+                                        int G, int swish, void* stream) {
+  int rc = gn_check(C, G);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int ppc = 1024;
+  while (ppc > 64 && (long long)N * ((HW + ppc - 1) / ppc) < 148 * 16) ppc >>= 1;
+  dim3 grid((HW + ppc - 1) / ppc, N);
+  auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto ab = reinterpret_cast<const __nv_bfloat16*>(add);
+  auto dxb = reinterpret_cast<__nv_bfloat16*>(dx);
+  const int cpg = C / G;
+  if (cpg >= 8 && cpg % 8 == 0) gn_bwd_apply_launch<1>(grid, st, dyb, xb, mean, rstd, gamma, beta, sums, ab, dxb, HW, C, G, ppc, swish);
+  else if (cpg == 4) gn_bwd_apply_launch<2>(grid, st, dyb, xb, mean, rstd, gamma, beta, sums, ab, dxb, HW, C, G, ppc, swish);
+  else if (cpg == 2) gn_bwd_apply_launch<4>(grid, st, dyb, xb, mean, rstd, gamma, beta, sums, ab, dxb, HW, C, G, ppc, swish);
+  else if (cpg == 1) gn_bwd_apply_launch<8>(grid, st, dyb, xb, mean, rstd, gamma, beta, sums, ab, dxb, HW, C, G, ppc, swish);
+  else return set_error(FFVC_ERR_UNSUPPORTED, "groupnorm_bwd: channels per group must be 1, 2, 4 or a multiple of 8");
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
 // dx = d/dx [ act(GN(x)) ] . dy  (+ add).  ws: N*G*2 doubles scratch.
 extern "C" int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                                   const float* gamma, const float* beta, double* ws, const void* add, void* dx, int N,

@@ -225,8 +225,21 @@ class DecoderEngine:
                  bias=self.pk[name + ".b"], res=res)
         return out
 
-    def conv3_dgrad(self, dy, name, N, H, W, cin, cout, res=None):
+    # Backward statistics of a Normalize + swish from the epilogue of the dgrad conv that produces its output gradient
+    # (ffvc_conv3x3_halo_gnbwd): `gnb` = (x, (mean, rstd), norm name) of the Normalize in front of this conv.  Returns
+    # (dx, sums) — sums is None when the fused form does not apply and gn_bwd runs its own statistics pass.
+    GN_EPI_BWD = os.environ.get("FFVC_GN_EPI_BWD", "0") == "1"
+
+    def conv3_dgrad(self, dy, name, N, H, W, cin, cout, res=None, gnb=None):
         dx = self._new(N * H * W, cin)
+        if gnb is not None:
+            if self.GN_EPI_BWD and cin == 128 and res is None and self._halo_ok(H, W, cout, cin):
+                x, st, nname = gnb
+                sums = self._new(N * 64, dtype=torch.float64)
+                call("conv3x3_halo_gnbwd", dy, self.pk[name + ".wT"], dx, N, H, W, cout, cin, cin, None, x, st[0], st[1],
+                     self.pk[nname + ".g"], self.pk[nname + ".be"], sums)
+                return dx, sums
+            return self.conv3_dgrad(dy, name, N, H, W, cin, cout, res=res), None
         if self._halo_ok(H, W, cout, cin):
             call("conv3x3_halo", dy, self.pk[name + ".wT"], dx, N, H, W, cout, cin, cin, None, res, None, 0, 0, 0)
             return dx
@@ -266,8 +279,12 @@ class DecoderEngine:
         call("groupnorm_apply", x, mean, rstd, self.pk[name + ".g"], self.pk[name + ".be"], y, N, HW, C, 32, int(swish))
         return y, (mean, rstd)
 
-    def gn_bwd(self, dy, x, stats, name, N, HW, C, swish, add=None):
+    def gn_bwd(self, dy, x, stats, name, N, HW, C, swish, add=None, sums=None):
         dx = self._new(N * HW, C)
+        if sums is not None:          # (sum g, sum g * xhat) came with the dgrad conv that wrote dy
+            call("groupnorm_bwd_apply", dy, x, stats[0], stats[1], self.pk[name + ".g"], self.pk[name + ".be"], sums, add, dx,
+                 N, HW, C, 32, int(swish))
+            return dx
         call("groupnorm_fused_bwd" if self._gn_fused(HW, C) else "groupnorm_bwd", dy, x, stats[0], stats[1], self.pk[name + ".g"],
              self.pk[name + ".be"], self._gn_ws(N * 65), add, dx, N, HW, C, 32, int(swish))
         return dx
@@ -283,11 +300,11 @@ class DecoderEngine:
         del a2, short
 
         def bwd(d):
-            d2 = self.conv3_dgrad(d, name + ".conv2", N, H, W, cout, cout)
-            dh1 = self.gn_bwd(d2, h1, st2, name + ".norm2", N, HW, cout, True)
-            d1 = self.conv3_dgrad(dh1, name + ".conv1", N, H, W, cin, cout)
+            d2, s2 = self.conv3_dgrad(d, name + ".conv2", N, H, W, cout, cout, gnb=(h1, st2, name + ".norm2"))
+            dh1 = self.gn_bwd(d2, h1, st2, name + ".norm2", N, HW, cout, True, sums=s2)
+            d1, s1 = self.conv3_dgrad(dh1, name + ".conv1", N, H, W, cin, cout, gnb=(x, st1, name + ".norm1"))
             ds = d if cin == cout else self.conv1_dgrad(d, name + ".nin_shortcut", N * HW, cin, cout)
-            return self.gn_bwd(d1, x, st1, name + ".norm1", N, HW, cin, True, add=ds)
+            return self.gn_bwd(d1, x, st1, name + ".norm1", N, HW, cin, True, add=ds, sums=s1)
 
         tape.append(bwd)
         return out

@@ -125,6 +125,16 @@ int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int
 int ffvc_conv3x3_halo_gn(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
                          const float* bias, const void* res, double* gn_ws, void* stream);
 int ffvc_groupnorm_finalize(const double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps, void* stream);
+/* dgrad form (no bias): `out` = dy of the Normalize + swish in front of the forward conv (Cout = 128 channels), stored as
+ * usual; the epilogue also reads that layer's input gn_x at the same positions and accumulates the backward statistics
+ * sum g, sum g * xhat per (image, group), g = dy * swish'(gamma * xhat + beta) * gamma, into gn_ws[n][32][2] doubles (zeroed by
+ * the call) — the first pass of ffvc_groupnorm_bwd (two more reads of dy and x).  ffvc_groupnorm_bwd_apply is its second pass. */
+int ffvc_conv3x3_halo_gnbwd(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                            const void* res, const void* gn_x, const float* gn_mean, const float* gn_rstd, const float* gn_gamma,
+                            const float* gn_beta, double* gn_ws, void* stream);
+int ffvc_groupnorm_bwd_apply(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                             const float* beta, const double* sums, const void* add, void* dx, int N, int HW, int C, int G,
+                             int swish, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim (bf16 in/out, fp32 stats).  mlp_mixer_pytorch.py:11,37; cloob.py:170-176.

@@ -415,3 +415,37 @@ def test_conv3x3_halo_epilogue_groupnorm_statistics(n, h, w, cin, with_res):
     assert torch.allclose(rstd, rstd2, rtol=1e-4), ((rstd - rstd2) / rstd2).abs().max()
     o = out1.float().view(n, h * w, 32, 4)
     assert torch.allclose(mean.view(n, 32), o.mean((1, 3)), atol=1e-4)
+
+
+@pytest.mark.parametrize("n,h,w,cin", [(2, 128, 128, 128), (3, 4, 256, 64), (1, 256, 256, 128)])
+def test_conv3x3_halo_epilogue_groupnorm_backward_statistics(n, h, w, cin):
+    """ffvc_conv3x3_halo_gnbwd: same dgrad output as ffvc_conv3x3_halo; the (sum g, sum g*xhat) its epilogue accumulates equal
+    the first pass of ffvc_groupnorm_bwd over (dy, x), and ffvc_groupnorm_bwd_apply on them gives the same dx"""
+    from feed_forward_vqgan_clip_b200.ops import call
+    BF = torch.bfloat16
+    cout = 128                                            # channels of dy = channels of the Normalize
+    g = torch.Generator().manual_seed(5)
+    dyin = torch.randn(n, h, w, cin, generator=g).to(DEV).to(BF)
+    wt = (torch.randn(cout, 9, cin, generator=g) * (9 * cin) ** -0.5).to(DEV).to(BF)
+    x = (0.5 + 1.5 * torch.randn(n * h * w, cout, generator=g)).to(DEV).to(BF)
+    add = torch.randn(n * h * w, cout, generator=g).to(DEV).to(BF)
+    gamma = (1 + 0.2 * torch.randn(cout, generator=g)).to(DEV)
+    beta = (0.2 * torch.randn(cout, generator=g)).to(DEV)
+    ws0 = torch.empty(n * 65, device=DEV, dtype=torch.float64)
+    mean, rstd = torch.empty(n * 32, device=DEV), torch.empty(n * 32, device=DEV)
+    call("groupnorm_stats", x, ws0, mean, rstd, n, h * w, cout, 32, 1e-6)
+    dy0 = torch.empty(n * h * w, cout, device=DEV, dtype=BF)
+    call("conv3x3_halo", dyin, wt, dy0, n, h, w, cin, cout, cout, None, None, None, 0, 0, 0)
+    dx0 = torch.empty_like(dy0)
+    ws_ref = torch.empty(n * 65, device=DEV, dtype=torch.float64)
+    call("groupnorm_bwd", dy0, x, mean, rstd, gamma, beta, ws_ref, add, dx0, n, h * w, cout, 32, 1)
+    dy1 = torch.empty_like(dy0)
+    sums = torch.full((n * 64,), 7.0, device=DEV, dtype=torch.float64)
+    call("conv3x3_halo_gnbwd", dyin, wt, dy1, n, h, w, cin, cout, cout, None, x, mean, rstd, gamma, beta, sums)
+    assert torch.equal(dy0, dy1)
+    ref = ws_ref[:n * 64]
+    err = (sums - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+    dx1 = torch.empty_like(dy0)
+    call("groupnorm_bwd_apply", dy1, x, mean, rstd, gamma, beta, sums, add, dx1, n, h * w, cout, 32, 1)
+    assert (dx1.float() - dx0.float()).abs().max().item() <= 2e-2 * dx0.float().abs().max().item()

@@ -205,16 +205,16 @@ def test_decoder_epilogue_groupnorm_statistics_match_separate_pass():
     zq = torch.randn(1, 16, 16, 256, generator=g).to(DEV).to(torch.bfloat16)
     dimg = torch.randn(1, 256, 256, 3, generator=g).to(DEV)
     outs = []
-    old = DecoderEngine.GN_EPI_STATS
+    old = DecoderEngine.GN_EPI_STATS, DecoderEngine.GN_EPI_BWD
     try:
         for flag in (False, True):
-            DecoderEngine.GN_EPI_STATS = flag
+            DecoderEngine.GN_EPI_STATS = DecoderEngine.GN_EPI_BWD = flag      # forward statistics and backward statistics
             img, tape = eng.forward(zq, post=False)
             assert not eng._epi_stats, "every epilogue statistic must be consumed by the Normalize that follows its conv"
             dz = eng.backward(tape, dimg.clone(), post=False)
             outs.append((img.clone(), dz.float().clone()))
     finally:
-        DecoderEngine.GN_EPI_STATS = old
+        DecoderEngine.GN_EPI_STATS, DecoderEngine.GN_EPI_BWD = old
     (i0, d0), (i1, d1) = outs
     assert (i0 - i1).abs().max().item() <= 2e-2 * i0.abs().max().item()
     assert cos(d0, d1) > 0.999

@@ -1,5 +1,5 @@
 #!/bin/bash
-# GPU session: epilogue GroupNorm statistics (ffvc_conv3x3_halo_gn) — tests, conv micro-timing, bench A/B.
+# GPU session: epilogue GroupNorm statistics (ffvc_conv3x3_halo_gn / _gnbwd) — tests, conv micro-timing, bench A/B.
 mkdir -p gpurun_out
 for f in test_gemm_gpu test_models_gpu test_ops_gpu; do
   timeout -k 10 420 python -m pytest tests/$f.py -q -m gpu -p no:cacheprovider --tb=short > gpurun_out/$f.full 2>&1; rc=$?
@@ -33,9 +33,18 @@ for r in (None, res):
     b = t(lambda: (call("conv3x3_halo_gn", x, wt, out, n, h, w, c, c, c, bias, r, ws), call("groupnorm_finalize", ws, mean, rstd, n, h * w, c, 32, 1e-6)))
     s_ = t(lambda: call("groupnorm_stats", out, ws, mean, rstd, n, h * w, c, 32, 1e-6))
     print("conv 64x256x256 128->128 res=%s: plain %.1f us, with epilogue stats + finalize %.1f us (separate stats pass %.1f us)" % (r is not None, a, b, s_))
+gam, bet = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+call("groupnorm_stats", res, ws, mean, rstd, n, h * w, c, 32, 1e-6)
+sums = torch.empty(n * 64, device=DEV, dtype=torch.float64)
+dx = torch.empty_like(out)
+a = t(lambda: call("conv3x3_halo", x, wt, out, n, h, w, c, c, c, None, None, None, 0, 0, 0))
+b = t(lambda: call("conv3x3_halo_gnbwd", x, wt, out, n, h, w, c, c, c, None, res, mean, rstd, gam, bet, sums))
+full = t(lambda: call("groupnorm_bwd", out, res, mean, rstd, gam, bet, ws, x.view(n * h * w, c), dx, n, h * w, c, 32, 1))
+app = t(lambda: call("groupnorm_bwd_apply", out, res, mean, rstd, gam, bet, sums, x.view(n * h * w, c), dx, n, h * w, c, 32, 1))
+print("dgrad conv: plain %.1f us, with backward statistics %.1f us; groupnorm_bwd two passes %.1f us, apply only %.1f us" % (a, b, full, app))
 PY
-run_bench() {  # name, FFVC_GN_EPI_STATS
-  FFVC_GN_EPI_STATS="$2" timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err
+run_bench() {  # name, FFVC_GN_EPI_BWD
+  FFVC_GN_EPI_BWD="$2" timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err
   echo "== bench $1 rc=$? $(python -c "import json,sys; d=json.load(open('gpurun_out/bench_$1.json')); print(round(d['value'],1), 'prompts/s', round(d['ms_per_step'],2), 'ms', d['clocks'], 'loss', d['last_loss'])" 2>&1 | tail -1)"; tail -2 gpurun_out/bench_$1.err
 }
 run_bench epi0 0
