@@ -228,7 +228,7 @@ class DecoderEngine:
     # Backward statistics of a Normalize + swish from the epilogue of the dgrad conv that produces its output gradient
     # (ffvc_conv3x3_halo_gnbwd): `gnb` = (x, (mean, rstd), norm name) of the Normalize in front of this conv.  Returns
     # (dx, sums) — sums is None when the fused form does not apply and gn_bwd runs its own statistics pass.
-    GN_EPI_BWD = os.environ.get("FFVC_GN_EPI_BWD", "0") == "1"
+    GN_EPI_BWD = os.environ.get("FFVC_GN_EPI_BWD", "1") == "1"      # measured +1.1 % prompts/s (profiles/r01_ab_kernels.md)
 
     def conv3_dgrad(self, dy, name, N, H, W, cin, cout, res=None, gnb=None):
         dx = self._new(N * H * W, cin)
