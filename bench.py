@@ -311,7 +311,7 @@ def main():
         real_call = _vq_mod.call
 
         def timed_call(name, *a):
-            if name != "conv3x3_halo":            # the halo-reuse 3x3 conv is the same tcgen05 kernel family
+            if not name.startswith("conv3x3_halo"):   # the halo-reuse 3x3 conv (plain / + GroupNorm statistics) is the same tcgen05 family
                 return real_call(name, *a)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -320,8 +320,13 @@ def main():
             ev.append((s, e))
             n_, h_, w_, cin_, cout_ = a[3:8]
             fl.append(2.0 * n_ * h_ * w_ * cout_ * 9 * cin_)
-            streams = 1 + (1 if a[10] is not None else 0) + (1 if a[11] is not None else 0)      # out (+ res) (+ aux)
-            by.append(n_ * h_ * w_ * (2.0 * cin_ + (4.0 if a[14] else 2.0) * cout_ + 2.0 * cout_ * (streams - 1)) + 2.0 * 9 * cin_ * cout_)
+            if name == "conv3x3_halo":                     # (..., ldc, bias, res, aux, mul_mode, act, out_fp32)
+                extra, o_sz = (a[10] is not None) + (a[11] is not None), (4.0 if a[14] else 2.0)
+            elif name == "conv3x3_halo_gn":                # (..., ldc, bias, res, gn_ws)
+                extra, o_sz = (a[10] is not None), 2.0
+            else:                                          # conv3x3_halo_gnbwd: (..., ldc, res, gn_x, ...): reads the Normalize's input too
+                extra, o_sz = (a[9] is not None) + 1, 2.0
+            by.append(n_ * h_ * w_ * (2.0 * cin_ + o_sz * cout_ + 2.0 * cout_ * extra) + 2.0 * 9 * cin_ * cout_)
 
         xd0 = x_host[0].to(dev)
         if world == 1:

@@ -56,9 +56,10 @@ def main():
         real_call(name, *a)
         e.record()
         key, fl = name, 0.0
-        if name == "conv3x3_halo":
+        if name.startswith("conv3x3_halo"):
             n, h, w, cin, cout = a[3:8]
-            key = "conv3x3_halo n%d %dx%d %d->%d%s%s" % (n, h, w, cin, cout, " res" if a[10] is not None else "", " aux" if a[11] is not None else "")
+            res = a[9] if name == "conv3x3_halo_gnbwd" else a[10]
+            key = "%s n%d %dx%d %d->%d%s" % (name, n, h, w, cin, cout, " res" if res is not None else "")
             fl = 2.0 * n * h * w * cout * 9 * cin
         else:
             ints = [str(v) for v in a if isinstance(v, int) and not isinstance(v, bool)][:5]
