@@ -281,25 +281,34 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             // input x): g = dy * swish'(gamma * xhat + beta) * gamma;  vals = sum g | sum g * xhat per group (groupnorm_bwd_stats_kernel)
             float2 xx[CW / 2];
             unpack_bf16x2N<CW>(cur_aux, xx);
-            const float* sgam = sbias_all + c;
-            const float* sbet = sbias_all + 128 + c;
+            // packed (FFMA2) arithmetic, gamma / beta of a group as one 16-byte shared-memory broadcast each: the epilogue warps
+            // pace the tile in this form, so instructions per element are what counts
+            const float4* sg4 = reinterpret_cast<const float4*>(sbias_all + c);
+            const float4* sb4 = reinterpret_cast<const float4*>(sbias_all + 128 + c);
+            const float2 half2 = make_float2(0.5f, 0.5f);
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               const float rs = gstat[(c >> 2) + g], mrs = gstat[32 + (c >> 2) + g];
-              float sg = 0.f, sq = 0.f;
+              const float2 rs2 = make_float2(rs, rs), mrs2 = make_float2(mrs, mrs);
+              const float4 G4 = sg4[g], B4 = sb4[g];
+              float2 as = make_float2(0.f, 0.f), aq = make_float2(0.f, 0.f);
 #pragma unroll
               for (int h2 = 0; h2 < 2; ++h2) {
+                const float2 gam = h2 ? make_float2(G4.z, G4.w) : make_float2(G4.x, G4.y);
+                const float2 bet = h2 ? make_float2(B4.z, B4.w) : make_float2(B4.x, B4.y);
                 const float2 d = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g + h2].x, vf[2 * g + h2].y));
-                const float2 xv = xx[2 * g + h2];
-                const float gam0 = sgam[4 * g + 2 * h2], gam1 = sgam[4 * g + 2 * h2 + 1];
-                const float xh0 = fmaf(xv.x, rs, mrs), xh1 = fmaf(xv.y, rs, mrs);
-                const float g0 = d.x * swish_grad_fast_f(fmaf(xh0, gam0, sbet[4 * g + 2 * h2])) * gam0;
-                const float g1 = d.y * swish_grad_fast_f(fmaf(xh1, gam1, sbet[4 * g + 2 * h2 + 1])) * gam1;
-                sg += g0 + g1;
-                sq = fmaf(g0, xh0, fmaf(g1, xh1, sq));
+                const float2 xh = __ffma2_rn(xx[2 * g + h2], rs2, mrs2);
+                const float2 u = __ffma2_rn(xh, gam, bet);
+                const float2 hu = __fmul2_rn(u, half2);
+                const float2 sg = __ffma2_rn(make_float2(tanh_approx(hu.x), tanh_approx(hu.y)), half2, half2);   // sigmoid(u)
+                const float2 w2 = __ffma2_rn(make_float2(-sg.x, -sg.y), u, u);                                  // u (1 - s)
+                const float2 sw = __ffma2_rn(sg, w2, sg);                                                       // swish'(u)
+                const float2 gg = __fmul2_rn(__fmul2_rn(d, sw), gam);
+                as = __fadd2_rn(as, gg);
+                aq = __ffma2_rn(gg, xh, aq);
               }
-              vals[g] = sg;
-              vals[8 + g] = sq;
+              vals[g] = as.x + as.y;
+              vals[8 + g] = aq.x + aq.y;
             }
           }
           const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
