@@ -34,15 +34,17 @@ static constexpr int kBStages = 4;
 static constexpr int kBStageBytes = 128 * 64 * 2;                     // up to 128 output channels x 64 input channels
 static constexpr int kHaloSmem = 2 * kHaloStride + kBStages * kBStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/ +
                                  4096 /*GroupNorm partial sums: [2 tiles][8 warps][4 chunks][16]*/;
-static constexpr int kHaloThreads = 320;
-static constexpr int kHaloEpiWarps = 8;
+// epilogue warps: 8 (one per 32-pixel row group, 32-column chunks) or 16 (two per row group, each 64 of the 128 columns in
+// 16-column chunks): the GroupNorm-statistics epilogues do ~20 instructions per element and, on 8 warps (2 per scheduler), pace
+// the tile; 16 warps halve the work per warp and double the latency hiding
 
 // descriptor for a K-major, 128B-swizzled operand whose start is 128 B- (not 1024 B-) aligned: base-offset field stays 0
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t saddr) {
   return umma_smem_desc_sw128(saddr, 16u, 1024u);
 }
 
-__global__ void __launch_bounds__(kHaloThreads, 1)
+template <int kEW>
+__global__ void __launch_bounds__(64 + 32 * kEW, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,7 +77,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), kHaloEpiWarps);
+      mbar_init(tempty_bar(a), kEW);
     }
     fence_mbar_init();
   }
@@ -177,10 +179,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9): sub-tile = output row
     const int q = warp & 3;
-    const int sub = (warp - 2) >> 2;
+    const int ew = warp - 2;                  // 0 .. kEW-1
+    const int sub = (ew >> 2) & 1;            // output row of the tile
+    const int rowwarp = ew & 7;               // 32-pixel row group (sub, q)
+    const int c_begin = (ew >> 3) * (p.block_n / (kEW / 8));   // kEW = 16: the upper 8 warps take the upper half of the columns
+    const int c_end = c_begin + p.block_n / (kEW / 8);
     const int etid = threadIdx.x - 64;
     float* sbias_all = reinterpret_cast<float*>(smem_raw + (bias_smem - smem_u32(smem_raw)));
-    float* gn_part = reinterpret_cast<float*>(smem_raw + (gn_smem - smem_u32(smem_raw)));   // [2 (acc)][8 warps][4 chunks][16]
+    float* gn_part = reinterpret_cast<float*>(smem_raw + (gn_smem - smem_u32(smem_raw)));   // [2 (acc)][8 row groups][2 kinds][32 groups]
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.ldc % 8 == 0);
@@ -202,7 +208,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       float* sbias = sbias_all + acc * 256;
       if (p.bias_mode == 1) {
         if (etid < p.block_n) sbias[etid] = (etid < p.N) ? p.bias[etid] : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
       }
       float* gstat = sbias_all + 256 + acc * 64;       // this tile's image: [32] rstd, [32] -mean * rstd
       if (gnb) {
@@ -211,9 +217,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           gstat[etid] = rs;
           gstat[32 + etid] = -p.gn_mean[(long long)img * 32 + etid] * rs;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEW) : "memory");
       }
-      constexpr int CW = 32;
+      constexpr int CW = kEW == 16 ? 16 : 32;
+      constexpr int GPC = CW / 4;              // GroupNorm groups (4 channels) per chunk
       uint4 pf_aux[CW / 8], pf_res[CW / 8];
       auto prefetch = [&](int c) {
         if (vec_ok && c + CW <= p.N) {
@@ -239,13 +246,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           }
         }
       };
-      if (want_aux || want_res) prefetch(0);
+      if (want_aux || want_res) prefetch(c_begin);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      for (int c = 0; c < p.block_n; c += CW) {
+      for (int c = c_begin; c < c_end; c += CW) {
         uint32_t r[CW];
         const uint32_t taddr = tmem_base + (uint32_t)(acc * 256 + sub * 128 + c) + ((uint32_t)(q * 32) << 16);
-        tmem_ld_32x32(taddr, r);
+        if constexpr (CW == 32) tmem_ld_32x32(taddr, r);
+        else tmem_ld_32x16(taddr, r);
         tmem_ld_wait();
         uint4 cur_aux[CW / 8], cur_res[CW / 8];
         if (want_aux) {
@@ -256,7 +264,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
           for (int j = 0; j < CW / 8; ++j) cur_res[j] = pf_res[j];
         }
-        if ((want_aux || want_res) && c + CW < p.block_n) prefetch(c + CW);
+        if ((want_aux || want_res) && c + CW < c_end) prefetch(c + CW);
         if (!p.gn_ws) {
           if (c < p.N)
             epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok && (c + CW <= p.N), sbias + c, cur_aux, cur_res, vec32_ok && (c + CW <= p.N));
@@ -267,14 +275,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           // summed over the warp's 32 pixels; one slot per warp and chunk in shared memory, folded per tile below.
           float2 vf[CW / 2];
           epilogue_chunk<CW>(p, r, c, row_off + c, 0.f, vec_ok, sbias + c, cur_aux, cur_res, vec32_ok, vf);
-          float vals[16];
+          float vals[2 * GPC];
           if (!gnb) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < GPC; ++g) {
               const float2 a = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g].x, vf[2 * g].y));
               const float2 b = __bfloat1622float2(__floats2bfloat162_rn(vf[2 * g + 1].x, vf[2 * g + 1].y));
               vals[g] = (a.x + a.y) + (b.x + b.y);
-              vals[8 + g] = fmaf(a.x, a.x, a.y * a.y) + fmaf(b.x, b.x, b.y * b.y);
+              vals[GPC + g] = fmaf(a.x, a.x, a.y * a.y) + fmaf(b.x, b.x, b.y * b.y);
             }
           } else {
             // backward statistics of the Normalize + swish whose output gradient this conv just produced (vf = dy, aux = its
@@ -287,7 +295,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const float4* sb4 = reinterpret_cast<const float4*>(sbias_all + 128 + c);
             const float2 half2 = make_float2(0.5f, 0.5f);
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < GPC; ++g) {
               const float rs = gstat[(c >> 2) + g], mrs = gstat[32 + (c >> 2) + g];
               const float2 rs2 = make_float2(rs, rs), mrs2 = make_float2(mrs, mrs);
               const float4 G4 = sg4[g], B4 = sb4[g];
@@ -308,29 +316,42 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 aq = __ffma2_rn(gg, xh, aq);
               }
               vals[g] = as.x + as.y;
-              vals[8 + g] = aq.x + aq.y;
+              vals[GPC + g] = aq.x + aq.y;
             }
           }
+          // recursive halving over the warp's 32 pixels: after the exchange with lane ^ 16 a lane keeps the sums (bit 4 = 0) or the
+          // second kind (bit 4 = 1); every further step halves the groups it keeps; the last steps are plain butterfly sums
           const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-          float n8[8], n4[4], n2[2];
+          float h1[GPC];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float send = b4 ? vals[i] : vals[i + 8], keep = b4 ? vals[i + 8] : vals[i];
-            n8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          for (int i = 0; i < GPC; ++i) {
+            const float send = b4 ? vals[i] : vals[i + GPC], keep = b4 ? vals[i + GPC] : vals[i];
+            h1[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
           }
+          float h2[GPC / 2];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float send = b3 ? n8[i] : n8[i + 4], keep = b3 ? n8[i + 4] : n8[i];
-            n4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          for (int i = 0; i < GPC / 2; ++i) {
+            const float send = b3 ? h1[i] : h1[i + GPC / 2], keep = b3 ? h1[i + GPC / 2] : h1[i];
+            h2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
           }
+          float h3[GPC / 4];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float send = b2 ? n4[i] : n4[i + 2], keep = b2 ? n4[i + 2] : n4[i];
-            n2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          for (int i = 0; i < GPC / 4; ++i) {
+            const float send = b2 ? h2[i] : h2[i + GPC / 4], keep = b2 ? h2[i + GPC / 4] : h2[i];
+            h3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
           }
-          float n1 = (b1 ? n2[1] : n2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? n2[0] : n2[1], 2);
-          n1 += __shfl_xor_sync(0xffffffffu, n1, 1);
-          if ((lane & 1) == 0) gn_part[(((acc * 8 + (warp - 2)) * 4 + (c >> 5)) << 4) + ((lane >> 4) << 3) + ((lane >> 1) & 7)] = n1;
+          float fin;
+          int gl;                                     // group of the chunk this lane ends up with
+          if constexpr (GPC == 8) {
+            fin = (b1 ? h3[1] : h3[0]) + __shfl_xor_sync(0xffffffffu, b1 ? h3[0] : h3[1], 2);
+            gl = (lane >> 1) & 7;
+          } else {
+            fin = h3[0] + __shfl_xor_sync(0xffffffffu, h3[0], 2);
+            gl = (lane >> 2) & 3;
+          }
+          fin += __shfl_xor_sync(0xffffffffu, fin, 1);
+          // slot [tile parity][row group][kind][group 0..31]: written exactly once per tile, by the warp that owns these columns
+          if ((lane & (GPC == 8 ? 1 : 3)) == 0) gn_part[(((acc * 8 + rowwarp) * 2 + (lane >> 4)) << 5) + (c >> 2) + gl] = fin;
         }
         __syncwarp();
       }
@@ -339,12 +360,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       if (lane == 0) mbar_arrive(tempty_bar(acc));           // the accumulator is free for the MMA warp before the fold below
       if (p.gn_ws) {
         // fold the 8 warps' slots of this tile: thread (kind, group) -> one double atomic per (image, group, kind) and tile
-        asm volatile("bar.sync 2, 256;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(32 * kEW) : "memory");
         if (etid < 64) {
           const int kind = etid >> 5, g = etid & 31;
           float tot = 0.f;
 #pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) tot += gn_part[(((acc * 8 + w8) * 4 + (g >> 3)) << 4) + (kind << 3) + (g & 7)];
+          for (int w8 = 0; w8 < 8; ++w8) tot += gn_part[(((acc * 8 + w8) * 2 + kind) << 5) + g];
           atomicAdd(&p.gn_ws[((long long)img * 32 + g) * 2 + kind], (double)tot);
         }
       }
@@ -407,7 +428,9 @@ static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, i
   static bool attr_done = false;
   static int num_sms = 0;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
     if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
@@ -462,7 +485,12 @@ static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, i
   if (gn_ws) cudaMemsetAsync(gn_ws, 0, sizeof(double) * 2 * 32 * (size_t)n, reinterpret_cast<cudaStream_t>(stream));
   const long long tiles = (long long)n * (h / 2) * (wd / 128);
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  conv3x3_halo_kernel<<<grid, kHaloThreads, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+  // 16 epilogue warps for the GroupNorm-statistics epilogues (option "halo_epi16": 1 = backward statistics, 2 = forward too)
+  const int epi16 = gn_ws ? option(OPT_HALO_EPI16) : 0;
+  if (block_n == 128 && ((epi16 >= 1 && p.gn_bwd) || epi16 >= 2))
+    conv3x3_halo_kernel<16><<<grid, 64 + 32 * 16, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+  else
+    conv3x3_halo_kernel<8><<<grid, 64 + 32 * 8, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   count_launch();

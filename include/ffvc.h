@@ -48,7 +48,8 @@ long long ffvc_launch_count(void);
 void ffvc_reset_launch_count(void);
 /* kernel-selection switches (A/B measurement of alternative kernels for the same op; results are identical up to
  * summation order).  Names: "ln_fwd_v2" / "ln_bwd_v2" (column-owning LayerNorm kernels; 1 = 4 rows in flight per CTA, 2 = 8 rows fwd / 2 rows bwd),
- * "pool_v2" (row-mapped cutout-pool backward), "gn_ring" (cp.async rings in the single-kernel GroupNorm forms).
+ * "pool_v2" (row-mapped cutout-pool backward), "gn_ring" (cp.async rings in the single-kernel GroupNorm forms),
+ * "halo_epi16" (16 epilogue warps in the halo conv's GroupNorm-statistics forms: 1 = backward statistics, 2 = forward too).
  * Initial values come from the environment variable FFVC_OPTS="name=0|1,...".  Returns the previous value, -1 if the
  * name is unknown. */
 int ffvc_set_option(const char* name, int value);

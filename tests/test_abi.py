@@ -85,7 +85,7 @@ def test_vitgan_state_dict_contract_and_seeded_init_match_reference_golden():
 def test_option_switches_and_env_override():
     lib = _lib.load()
     assert lib.ffvc_get_option(b"no_such_option") == -1
-    for name in (b"ln_fwd_v2", b"ln_bwd_v2", b"pool_v2", b"gn_ring"):
+    for name in (b"ln_fwd_v2", b"ln_bwd_v2", b"pool_v2", b"gn_ring", b"halo_epi16"):
         old = lib.ffvc_get_option(name)
         assert old in (0, 1, 2)
         assert lib.ffvc_set_option(name, 0) == old and lib.ffvc_get_option(name) == 0

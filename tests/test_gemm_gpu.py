@@ -388,11 +388,13 @@ def test_stream_k_wgrad_matches_split_k(M, N, K, segs, two):
     assert (outs[0] - outs[1]).abs().max().item() <= 2e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("epi16", [0, 2])
 @pytest.mark.parametrize("n,h,w,cin,with_res", [(2, 128, 128, 128, True), (3, 4, 256, 64, False), (1, 256, 256, 128, True)])
-def test_conv3x3_halo_epilogue_groupnorm_statistics(n, h, w, cin, with_res):
+def test_conv3x3_halo_epilogue_groupnorm_statistics(n, h, w, cin, with_res, epi16, ffvc_options):
     """ffvc_conv3x3_halo_gn: same output as ffvc_conv3x3_halo, and the (mean, rstd) its epilogue produces equal those of the
     separate statistics pass over the stored tensor (taming Normalize = GroupNorm(32, eps 1e-6))"""
     from feed_forward_vqgan_clip_b200.ops import call
+    ffvc_options(halo_epi16=epi16)                       # 8 or 16 epilogue warps
     BF = torch.bfloat16
     cout = 128
     g = torch.Generator().manual_seed(3)
@@ -417,11 +419,13 @@ def test_conv3x3_halo_epilogue_groupnorm_statistics(n, h, w, cin, with_res):
     assert torch.allclose(mean.view(n, 32), o.mean((1, 3)), atol=1e-4)
 
 
+@pytest.mark.parametrize("epi16", [0, 1])
 @pytest.mark.parametrize("n,h,w,cin", [(2, 128, 128, 128), (3, 4, 256, 64), (1, 256, 256, 128)])
-def test_conv3x3_halo_epilogue_groupnorm_backward_statistics(n, h, w, cin):
+def test_conv3x3_halo_epilogue_groupnorm_backward_statistics(n, h, w, cin, epi16, ffvc_options):
     """ffvc_conv3x3_halo_gnbwd: same dgrad output as ffvc_conv3x3_halo; the (sum g, sum g*xhat) its epilogue accumulates equal
     the first pass of ffvc_groupnorm_bwd over (dy, x), and ffvc_groupnorm_bwd_apply on them gives the same dx"""
     from feed_forward_vqgan_clip_b200.ops import call
+    ffvc_options(halo_epi16=epi16)
     BF = torch.bfloat16
     cout = 128                                            # channels of dy = channels of the Normalize
     g = torch.Generator().manual_seed(5)

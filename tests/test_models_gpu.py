@@ -198,12 +198,13 @@ MID_VQ = dict(ch=128, ch_mult=(1, 1), num_res_blocks=1, attn_resolutions=(), res
               embed_dim=64, n_embed=512)      # 128 channels at 128 x 128: the halo-reuse conv kernel and its GroupNorm epilogues
 
 
-@pytest.mark.parametrize("epilogue_stats", [False, True])
-def test_decoder_wide_layers_vs_oracle(epilogue_stats):
+@pytest.mark.parametrize("epilogue_stats,epi16", [(False, 0), (True, 0), (True, 2)])
+def test_decoder_wide_layers_vs_oracle(epilogue_stats, epi16, ffvc_options):
     """decoder with 128-channel layers at 128 x 128 (ffvc_conv3x3_halo*) against the CPU oracle, with the GroupNorm statistics
     taken by separate passes (False) or by the conv epilogues — forward (ffvc_conv3x3_halo_gn) and backward
     (ffvc_conv3x3_halo_gnbwd + ffvc_groupnorm_bwd_apply) (True).  Same tolerance for both."""
     from feed_forward_vqgan_clip_b200.vqgan import DecoderEngine
+    ffvc_options(halo_epi16=epi16)                        # 16 epilogue warps in the statistics epilogues
     sd = bf16_round_sd(ovq.init_vqgan_state_dict(MID_VQ, seed=7))
     vq = VQModel(MID_VQ)
     vq.load_state_dict(sd)

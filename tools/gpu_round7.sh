@@ -30,13 +30,21 @@ call("groupnorm_stats", res, ws, mean, rstd, n, h * w, c, 32, 1e-6)
 sums = torch.empty(n * 64, device=DEV, dtype=torch.float64)
 a = t(lambda: call("conv3x3_halo", x, wt, out, n, h, w, c, c, c, None, None, None, 0, 0, 0))
 b = t(lambda: call("conv3x3_halo_gnbwd", x, wt, out, n, h, w, c, c, c, None, res, mean, rstd, gam, bet, sums))
-print("dgrad conv: plain %.1f us, with backward statistics (FFMA2 epilogue) %.1f us" % (a, b))
+from feed_forward_vqgan_clip_b200 import _lib
+_lib.load().ffvc_set_option(b"halo_epi16", 2)
+b16 = t(lambda: call("conv3x3_halo_gnbwd", x, wt, out, n, h, w, c, c, c, None, res, mean, rstd, gam, bet, sums))
+bias = torch.randn(c, device=DEV)
+f16 = t(lambda: call("conv3x3_halo_gn", x, wt, out, n, h, w, c, c, c, bias, res, ws))
+_lib.load().ffvc_set_option(b"halo_epi16", 0)
+f8 = t(lambda: call("conv3x3_halo_gn", x, wt, out, n, h, w, c, c, c, bias, res, ws))
+print("dgrad conv: plain %.1f us, with backward statistics 8 warps %.1f us, 16 warps %.1f us; fwd conv+res with statistics 8 warps %.1f, 16 warps %.1f" % (a, b, b16, f8, f16))
 PY
 run_bench() {
-  FFVC_GN_EPI_BWD="$2" timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err
+  FFVC_OPTS="halo_epi16=$2" timeout -k 10 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err
   echo "== bench $1 rc=$? $(python -c "import json,sys; d=json.load(open('gpurun_out/bench_$1.json')); print(round(d['value'],1), 'prompts/s', round(d['ms_per_step'],2), 'ms', 'gemm TF', round(d['roofline']['achieved'],1), d['roofline']['launches_per_step'])" 2>&1 | tail -1)"; tail -2 gpurun_out/bench_$1.err
 }
-run_bench b0 0
-run_bench b1 1
-run_bench b0b 0
-run_bench b1b 1
+run_bench e0 0
+run_bench e1 1
+run_bench e2 2
+run_bench e0b 0
+run_bench e2b 2
