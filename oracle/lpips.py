@@ -1,8 +1,8 @@
 """ORACLE (test infrastructure, not product): CPU fp32 restatement of the LPIPS-VGG16 diversity term of the train step,
 main.py:776-791 (modes 'between_same_prompts' and 'all') + `normalize_tensor` and the `vgg16` feature slices of
 taming.modules.losses.lpips (absent package; torchvision VGG16 `features` split at relu1_2, relu2_2, relu3_3, relu4_3,
-relu5_3 — SURVEY App. A.5).  PARITY UNPINNED at the taming / torchvision-weights boundary: structure restated, weights
-random.  The loop over taps and the pairwise-difference expression are the reference's own lines."""
+relu5_3 — SURVEY App. A.5).  The slice structure is PINNED against torchvision.models.vgg16().features with shared random weights
+(tests/test_oracle_golden.py); taming's normalize_tensor and the pretrained weights are absent (restated / random).  The loop over taps and the pairwise-difference expression are the reference's own lines."""
 import torch
 import torch.nn.functional as F
 

@@ -2,6 +2,7 @@
 (tests/golden/make_golden.py, run against /root/reference).  No GPU, no reference needed at test time."""
 import os
 
+import pytest
 import torch
 
 import oracle.clip_vit as oclip
@@ -122,3 +123,68 @@ def test_cutout_oracle_runs_and_is_differentiable():
     y0 = oc.make_cutouts(x.detach(), 3, ident, 32, normalize=False)
     pooled = (torch.nn.functional.adaptive_avg_pool2d(x.detach(), 32) + torch.nn.functional.adaptive_max_pool2d(x.detach(), 32)) / 2
     assert torch.allclose(y0, pooled.repeat(3, 1, 1, 1), atol=2e-6)
+
+
+def test_lpips_vgg16_taps_match_torchvision_vgg16_features():
+    """oracle/lpips.py restates taming's `vgg16` slices (relu1_2, relu2_2, relu3_3, relu4_3, relu5_3 of torchvision's VGG16
+    `features`).  taming is absent, torchvision is not: pin the STRUCTURE (layer order, pooling positions, tap
+    points, key numbering) against torchvision.models.vgg16 with the same random weights."""
+    torchvision = pytest.importorskip("torchvision")
+    import oracle.lpips as ol
+    torch.manual_seed(11)
+    feats = torchvision.models.vgg16(weights=None).features.eval()
+    sd = {}
+    for s, idxs in ol.VGG16_SLICES:
+        for i in idxs:
+            assert isinstance(feats[i], torch.nn.Conv2d) and tuple(feats[i].weight.shape[:2]) == ol.VGG16_CH[i][::-1]
+            sd["slice%d.%d.weight" % (s, i)] = feats[i].weight.detach().clone()
+            sd["slice%d.%d.bias" % (s, i)] = feats[i].bias.detach().clone()
+    x = torch.randn(2, 3, 64, 64)
+    mine = ol.vgg_taps(sd, x)
+    ends = [4, 9, 16, 23, 30]                      # taming lpips.vgg16: slices end after relu1_2 ... relu5_3
+    h, start, ref = x, 0, []
+    with torch.no_grad():
+        for e in ends:
+            for i in range(start, e):
+                h = feats[i](h)
+            ref.append(h)
+            start = e
+    assert len(mine) == 5
+    for a, b in zip(mine, ref):
+        assert a.shape == b.shape and torch.allclose(a, b, atol=1e-5, rtol=1e-5)
+
+
+def test_clip_vit_restatement_matches_transformers_clip_vision_model():
+    """secondary cross-check: an independent implementation of the CLIP ViT — transformers'
+    CLIPVisionModelWithProjection, random init — gives the oracle's embedding when its weights are mapped to the CLIP
+    `visual.*` key names the oracle (and the reference's cloob twin) use."""
+    transformers = pytest.importorskip("transformers")
+    import oracle.clip_vit as oc
+    cfg = dict(input_resolution=64, patch_size=32, width=64, layers=2, heads=2, output_dim=32)
+    hf_cfg = transformers.CLIPVisionConfig(hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                                           image_size=64, patch_size=32, projection_dim=32, hidden_act="quick_gelu",
+                                           layer_norm_eps=1e-5, attention_dropout=0.0)
+    torch.manual_seed(12)
+    m = transformers.CLIPVisionModelWithProjection(hf_cfg).eval()
+    with torch.no_grad():
+        for p in m.parameters():                   # HF initialises LayerNorms to (1, 0) and biases to 0: make every term matter
+            p.add_(0.05 * torch.randn_like(p))
+    hf = {k: v.detach() for k, v in m.state_dict().items()}
+    v = "vision_model."
+    sd = {"conv1.weight": hf[v + "embeddings.patch_embedding.weight"], "class_embedding": hf[v + "embeddings.class_embedding"],
+          "positional_embedding": hf[v + "embeddings.position_embedding.weight"], "proj": hf["visual_projection.weight"].t(),
+          "ln_pre.weight": hf[v + "pre_layrnorm.weight"], "ln_pre.bias": hf[v + "pre_layrnorm.bias"],
+          "ln_post.weight": hf[v + "post_layernorm.weight"], "ln_post.bias": hf[v + "post_layernorm.bias"]}
+    for l in range(2):
+        a, b = v + "encoder.layers.%d." % l, "transformer.resblocks.%d." % l
+        sd[b + "attn.in_proj_weight"] = torch.cat([hf[a + "self_attn.%s_proj.weight" % n] for n in "qkv"])
+        sd[b + "attn.in_proj_bias"] = torch.cat([hf[a + "self_attn.%s_proj.bias" % n] for n in "qkv"])
+        sd[b + "attn.out_proj.weight"], sd[b + "attn.out_proj.bias"] = hf[a + "self_attn.out_proj.weight"], hf[a + "self_attn.out_proj.bias"]
+        for mine, theirs in (("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"), ("mlp.c_fc", "mlp.fc1"), ("mlp.c_proj", "mlp.fc2")):
+            sd[b + mine + ".weight"], sd[b + mine + ".bias"] = hf[a + theirs + ".weight"], hf[a + theirs + ".bias"]
+    x = torch.randn(3, 3, 64, 64)
+    with torch.no_grad():
+        ref = m(pixel_values=x).image_embeds
+        out = oc.encode_image(sd, x, cfg, act="quick_gelu")
+    assert out.shape == ref.shape == (3, 32)
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-4), (out - ref).abs().max()
