@@ -1,8 +1,10 @@
 """ORACLE (test infrastructure, not product): CPU fp32 restatement of the VQGAN pieces on the hot path.
 
-PARITY UNPINNED at the third-party boundary: the decoder arithmetic lives in
-`taming-transformers-rom1504==0.0.6` (requirements.txt:2), which is neither under /root/reference nor
-installed here.  This file restates its published architecture (taming/modules/diffusionmodules/model.py:
+Third-party boundary: the decoder arithmetic lives in `taming-transformers-rom1504==0.0.6` (requirements.txt:2), which
+is neither under /root/reference nor installed here, so it is NOT pinned by taming itself.  It is cross-checked against an
+independent implementation of the same decoder that IS importable here — transformers' JanusVQVAEDecoder, random weights
+mapped onto taming's key names: output and input gradient agree to 1e-5 (tests/test_oracle_golden.py).
+This file restates the published architecture (taming/modules/diffusionmodules/model.py:
 Decoder, ResnetBlock, AttnBlock, Upsample, Normalize, nonlinearity; taming/models/vqgan.py: VQModel.decode)
 for the `vqgan_imagenet_f16_16384` config, with the package's state_dict key names.
 What IS pinned against the reference's own code (tests/golden/make_golden.py imports /root/reference/main.py):

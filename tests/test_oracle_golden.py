@@ -188,3 +188,48 @@ def test_clip_vit_restatement_matches_transformers_clip_vision_model():
         out = oc.encode_image(sd, x, cfg, act="quick_gelu")
     assert out.shape == ref.shape == (3, 32)
     assert torch.allclose(out, ref, atol=2e-5, rtol=1e-4), (out - ref).abs().max()
+
+
+def test_vqgan_decoder_restatement_matches_transformers_janus_vqvae_decoder():
+    """taming-transformers (the reference's VQGAN, main.py:29,84-103,142) is absent from the reference tree and the image, so
+    oracle/vqgan.py restates its Decoder from the published architecture.  transformers ships an independent
+    implementation of the same decoder family (JanusVQVAEDecoder: GroupNorm(32, 1e-6) + swish ResnetBlocks with nin_shortcut,
+    single-head AttnBlock at the lowest resolution, nearest-2x + conv Upsample, mid block_1 / attn_1 / block_2, norm_out, conv_out).
+    With its random weights mapped onto taming's key names (only the level index differs: HF appends levels in processing
+    order) the restatement reproduces its output and input gradient — every key and shape corresponds one to one."""
+    pytest.importorskip("transformers")
+    from transformers.models.janus import modeling_janus as mj
+    from transformers.models.janus.configuration_janus import JanusVQVAEConfig
+    hf_cfg = JanusVQVAEConfig(embed_dim=16, num_embeddings=64, double_latent=False, latent_channels=16, in_channels=3, out_channels=3,
+                              base_channels=32, channel_multiplier=[1, 2, 2], num_res_blocks=2, dropout=0.0)
+    torch.manual_seed(21)
+    dec = mj.JanusVQVAEDecoder(hf_cfg).eval()
+    with torch.no_grad():
+        for p in dec.parameters():                 # GroupNorm starts at (1, 0): make every term matter
+            p.add_(0.05 * torch.randn_like(p))
+    cfg = dict(ch=32, ch_mult=(1, 2, 2), num_res_blocks=2, attn_resolutions=(8,), resolution=32, z_channels=16, out_ch=3,
+               embed_dim=16, n_embed=64)
+    ref_sd = ovq.init_vqgan_state_dict(cfg, seed=0)
+    levels = len(cfg["ch_mult"])
+    sd = {}
+    for k, v in dec.state_dict().items():
+        parts = k.split(".")
+        if parts[0] == "up":
+            parts[1] = str(levels - 1 - int(parts[1]))
+        sd["decoder." + ".".join(parts)] = v.detach().clone()
+    sd["post_quant_conv.weight"] = torch.eye(16).view(16, 16, 1, 1)            # identity: compare the Decoder alone
+    sd["post_quant_conv.bias"] = torch.zeros(16)
+    sd["quantize.embedding.weight"] = ref_sd["quantize.embedding.weight"]
+    assert set(sd) == set(ref_sd)
+    for k in ref_sd:
+        assert sd[k].shape == ref_sd[k].shape, k
+    z = torch.randn(2, 16, 8, 8)
+    w = torch.randn(2, 3, 32, 32)
+    za, zb = z.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    a = dec(za)
+    b = ovq.decode(sd, zb, cfg)
+    assert a.shape == b.shape == (2, 3, 32, 32)
+    assert torch.allclose(a, b, atol=1e-5, rtol=1e-5), (a - b).abs().max()
+    (a * w).sum().backward()
+    (b * w).sum().backward()
+    assert torch.allclose(za.grad, zb.grad, atol=1e-4, rtol=1e-4), (za.grad - zb.grad).abs().max()
