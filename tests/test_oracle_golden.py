@@ -233,3 +233,35 @@ def test_vqgan_decoder_restatement_matches_transformers_janus_vqvae_decoder():
     (a * w).sum().backward()
     (b * w).sum().backward()
     assert torch.allclose(za.grad, zb.grad, atol=1e-4, rtol=1e-4), (za.grad - zb.grad).abs().max()
+
+
+def test_cutout_warp_and_hue_restatements_match_torchvision():
+    """kornia (the reference's augmentation library, main.py:18,170-200) is absent; torchvision is not.  Two conventions of
+    oracle/cutouts.py are checked against torchvision's independent implementations of the same operations:
+      * the inverse affine map built by cutouts.sample_params (rotate about the centre, then translate; pixel centres at integer
+        coordinates; bilinear taps) against transforms.v2.functional.affine — interior pixels (the padding modes differ),
+      * the HSV round trip + hue shift against adjust_hue (hue factor f <-> 2 pi f radians)."""
+    pytest.importorskip("torchvision")
+    import math
+    import torchvision.transforms.v2.functional as TF
+    from torchvision.transforms import InterpolationMode
+    import oracle.cutouts as oc
+    torch.manual_seed(31)
+    P = 64
+    img = torch.rand(2, 3, P, P)
+    for f in (0.07, -0.04, 0.1):
+        a = oc.color_jitter(img, torch.ones(2), torch.full((2,), f * 2 * math.pi))
+        assert torch.allclose(a, TF.adjust_hue(img, f), atol=1e-5), f
+    c = (P - 1) / 2.0
+    for ang_deg, tx, ty in ((10.0, 3.0, -2.0), (-14.0, -5.0, 4.0), (0.0, 6.0, 6.0)):
+        ang = ang_deg * math.pi / 180
+        ca, sa = math.cos(ang), math.sin(ang)
+        inv = torch.zeros(2, 3, 3)                      # same expressions as cutouts.sample_params ("Af")
+        inv[:, 0, 0], inv[:, 0, 1], inv[:, 0, 2] = ca, sa, c - ca * (c + tx) - sa * (c + ty)
+        inv[:, 1, 0], inv[:, 1, 1], inv[:, 1, 2] = -sa, ca, c + sa * (c + tx) - ca * (c + ty)
+        inv[:, 2, 2] = 1.0
+        a = oc.warp(img, inv, "zeros")
+        b = TF.affine(img, angle=ang_deg, translate=[tx, ty], scale=1.0, shear=[0.0, 0.0], interpolation=InterpolationMode.BILINEAR,
+                      fill=0.0)
+        m = slice(14, P - 14)
+        assert torch.allclose(a[..., m, m], b[..., m, m], atol=2e-5), (ang_deg, (a - b)[..., m, m].abs().max())
