@@ -191,6 +191,7 @@ class TrainStep:
         self.loss = torch.zeros(1, device=self.dev, dtype=F32)
         self.graph = None
         self.static = None
+        self._next_prm = None           # augmentation parameters drawn ahead of the next replay()
         self.last_indices = None
 
     # ------------------------------------------------------------------ one step on device-resident inputs
@@ -320,14 +321,20 @@ class TrainStep:
         return self
 
     def replay(self, inp, out_feats=None, prm=None):
-        """inp may be a pinned host tensor (H2D copy on the current stream) or a device tensor."""
+        """inp may be a pinned host tensor (H2D copy on the current stream) or a device tensor.  With prm=None the
+        augmentation parameters of the NEXT call are drawn right after this step's graph launch, i.e. while the GPU works."""
         st = self.static
         B = st["inp"].shape[0]
         st["inp"].copy_(inp, non_blocking=True)
         st["out"].copy_(inp if out_feats is None else out_feats, non_blocking=True)
-        prm = prm if prm is not None else self.new_params(B)
+        presample = prm is None
+        if presample:
+            prm = self._next_prm if self._next_prm is not None else self.new_params(B)
+            self._next_prm = None
         for k in ("affine_inv", "persp_inv", "sat", "hue"):
             st[k].copy_(prm[k], non_blocking=True)
         st["erase"].copy_(torch.tensor([int(t) for t in prm["erase"]], dtype=torch.int32), non_blocking=True)
         self.graph.replay()
+        if presample:
+            self._next_prm = self.new_params(B)
         return self.loss

@@ -118,3 +118,53 @@ def test_fused_adam_state_dict_is_torch_adam_compatible():
     opt2.load_state_dict(t.state_dict())
     assert float(opt2.hyper[8]) == 4.0 and float(opt2.hyper[0]) == pytest.approx(3e-4)
     assert torch.equal(opt2.m[:8].view(2, 4), t.state_dict()["state"][0]["exp_avg"])
+
+
+def test_perspective_inverse_map_closed_form_matches_linear_solve():
+    """cutouts._quad_to_square (closed form used by sample_params) against the general 8x8 solve it replaced"""
+    from feed_forward_vqgan_clip_b200 import cutouts as C
+    torch.manual_seed(3)
+    n, q = 1000, 223.0
+    r = torch.rand(n, 8, dtype=torch.float64) * (0.7 * q / 2)
+    dst = torch.stack([torch.stack([r[:, 0], r[:, 1]], -1), torch.stack([q - r[:, 2], r[:, 3]], -1),
+                       torch.stack([q - r[:, 4], q - r[:, 5]], -1), torch.stack([r[:, 6], q - r[:, 7]], -1)], dim=1)
+    src = torch.tensor([[0, 0], [q, 0], [q, q], [0, q]], dtype=torch.float64).expand(n, 4, 2)
+    a, b = C._persp_coeffs(dst, src), C._quad_to_square(dst, q)
+    assert ((a - b).abs() / (a.abs() + 1e-9)).max().item() < 1e-8
+    pts = torch.cat([dst, torch.ones(n, 4, 1, dtype=torch.float64)], -1) @ b.transpose(1, 2)
+    assert (pts[..., :2] / pts[..., 2:] - src).abs().max().item() < 1e-9
+    eye = C._quad_to_square(src[:3].clone(), q)                       # undistorted corners -> identity
+    assert torch.allclose(eye, torch.eye(3, dtype=torch.float64).expand(3, 3, 3), atol=1e-12)
+
+
+def test_replay_host_logic_draws_next_parameters_after_the_launch():
+    """TrainStep.replay on stand-in objects (no GPU): static buffers are filled from the host tensors, the graph is launched
+    once, the parameters of the next call are drawn after the launch and consumed by it, explicit parameters bypass that"""
+    from types import SimpleNamespace
+    from feed_forward_vqgan_clip_b200.cutouts import sample_params
+    from feed_forward_vqgan_clip_b200.train_step import TrainStep
+    B, cutn = 2, 3
+    N = B * cutn
+    st = dict(inp=torch.zeros(B, 8), out=torch.zeros(B, 8), affine_inv=torch.zeros(N, 3, 3), persp_inv=torch.zeros(N, 3, 3),
+              sat=torch.zeros(N), hue=torch.zeros(N), erase=torch.zeros(4, dtype=torch.int32))
+    events = []
+    fake = SimpleNamespace(static=st, graph=SimpleNamespace(replay=lambda: events.append("launch")), loss=torch.zeros(1), cutn=cutn,
+                           cut_size=224, gen=torch.Generator().manual_seed(1), _next_prm=None)
+
+    def new_params(b):
+        events.append("sample")
+        return TrainStep.new_params(fake, b)
+
+    fake.new_params = new_params
+    x = torch.randn(B, 8)
+    TrainStep.replay(fake, x)
+    assert events == ["sample", "launch", "sample"] and torch.equal(st["inp"], x) and torch.equal(st["out"], x)
+    ahead = fake._next_prm
+    assert ahead is not None
+    TrainStep.replay(fake, x)
+    assert events == ["sample", "launch", "sample", "launch", "sample"]
+    assert torch.equal(st["affine_inv"], ahead["affine_inv"]) and torch.equal(st["sat"], ahead["sat"])
+    explicit = sample_params(N, 224, torch.Generator().manual_seed(9), with_noise=False)
+    kept = fake._next_prm
+    TrainStep.replay(fake, x, None, explicit)
+    assert events[-1] == "launch" and fake._next_prm is kept and torch.equal(st["persp_inv"], explicit["persp_inv"])
