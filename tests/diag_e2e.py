@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """GPU diagnostic: where does the whole-step gradient of the tiny VitGAN / Mixer configs deviate from the oracle?
 Prints index agreement, per-parameter cosine with free and with forced VQ indices, and the cosine of dz (the gradient
-entering the mapper).  python tools/diag_e2e.py > gpurun_out/diag_e2e.log"""
+entering the mapper).  python tests/diag_e2e.py > gpurun_out/diag_e2e.log"""
 import os
 import sys
 
