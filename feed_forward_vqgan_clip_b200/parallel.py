@@ -31,6 +31,22 @@ def shard_range(n_total, rank, world):
     return rank * per, (rank + 1) * per
 
 
+def shard_cutout_params(prm, cutn, n_total, lo, hi):
+    """Augmentation parameters of the prompts [lo, hi) of a global batch of n_total prompts.
+    MakeCutouts orders its output cutout-major — cutout k of prompt j is row k * B + j (main.py:219, `repeat(cutn, ...)`) —
+    so a rank that owns prompts [lo, hi) needs rows {k * n_total + j : lo <= j < hi} of every per-cutout tensor, re-packed
+    as k * (hi - lo) + (j - lo).  The erase rectangle is one per batch (RandomErasing(same_on_batch=True), main.py:189-190)
+    and is shared.  With parameters sharded this way a data-parallel step over any world size reproduces the single-process
+    step on the global batch (tests/test_parallel_cpu.py, tests/test_zz_full_size_gpu.py)."""
+    out = {}
+    for k, v in prm.items():
+        if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == cutn * n_total:
+            out[k] = v.reshape(cutn, n_total, *v.shape[1:])[:, lo:hi].reshape(cutn * (hi - lo), *v.shape[1:]).contiguous()
+        else:
+            out[k] = v
+    return out
+
+
 def allreduce_flat_grads(flat_grad, world, group=None):
     """Sum-all-reduce the flat gradient arena in place; returns the scale Adam must apply (1/world)."""
     if world > 1:

@@ -180,3 +180,47 @@ def test_bucketed_allreduce_equals_single_allreduce_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res)
+
+
+def test_sharded_step_reproduces_the_global_batch_step_oracle():
+    """Size-independent property of the path: the train step is a mean over independent prompts, so the
+    gradient of the global batch equals the average of the shard gradients when every shard gets ITS prompts' cutout
+    parameters (parallel.shard_cutout_params).  Checked here on the CPU oracle; tests/test_zz_full_size_gpu.py checks the
+    same property on the CUDA path at BASELINE config #2's full size."""
+    import oracle.clip_vit as oclip
+    import oracle.mixer as omix
+    import oracle.vqgan as ovq
+    from oracle.train_step import OracleTrainer
+    from feed_forward_vqgan_clip_b200.cutouts import sample_params
+    vq_cfg = dict(ch=32, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(4,), resolution=8, z_channels=32, out_ch=3,
+                  embed_dim=32, n_embed=64)
+    clip_cfg = dict(input_resolution=64, patch_size=32, width=64, layers=1, heads=2, output_dim=32)
+    S, C, cutn, B, cut = 4, 32, 3, 4, 64
+    sd_m = omix.init_mixer_state_dict(32, S, C, 64, 1, seed=0)
+    sd_m["final_proj.weight"] = sd_m["final_proj.weight"] * 6.0
+    sd_v, sd_c = ovq.init_vqgan_state_dict(vq_cfg, seed=1), oclip.init_clip_state_dict(clip_cfg, seed=2)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 32, generator=g) * 0.45
+    prm = sample_params(cutn * B, cut, g)
+
+    def run(xs, ps):
+        tr = OracleTrainer(sd_m, sd_v, sd_c, S, C, vq_cfg, clip_cfg, cutn=cutn, cut_size=cut)
+        loss = tr.step(xs, xs, ps)
+        return loss, tr.grads, tr.last_indices
+
+    loss_full, g_full, idx_full = run(x, prm)
+    world = 2
+    losses, grads, idx = [], [], []
+    for r in range(world):
+        lo, hi = parallel.shard_range(B, r, world)
+        ps = parallel.shard_cutout_params(prm, cutn, B, lo, hi)
+        assert ps["affine_inv"].shape[0] == cutn * (hi - lo) and ps["erase"] == prm["erase"]
+        # row k * Bs + (j - lo) of the shard is row k * B + j of the global batch
+        assert torch.equal(ps["hue"][1 * (hi - lo) + 1], prm["hue"][1 * B + lo + 1])
+        l, gr, ix = run(x[lo:hi], ps)
+        losses.append(l), grads.append(gr), idx.append(ix.reshape(hi - lo, -1))
+    assert torch.equal(torch.cat(idx).reshape(-1), idx_full.reshape(-1))
+    assert abs(sum(losses) / world - loss_full) < 1e-5 * abs(loss_full)
+    for k in g_full:
+        avg = sum(gr[k] for gr in grads) / world
+        assert torch.allclose(avg, g_full[k], rtol=1e-3, atol=1e-6 * float(g_full[k].abs().max()) + 1e-9), k

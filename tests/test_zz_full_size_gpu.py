@@ -1,0 +1,116 @@
+"""Full-size checks of the hot path on the GPU (BASELINE.json configs[1]: MLP-Mixer 32x1024 -> VQGAN f16/16384 -> 8 cutouts
+-> CLIP ViT-B/32, 256x256, 64 prompts) through size-independent properties — the CPU oracle needs minutes per prompt at
+this size, so parity at full size is argued from properties of the path instead (the small-size tests compare with the
+oracle directly):
+
+  * batch sharding: the step is a mean over independent prompts, so the global-batch gradient equals the average of the
+    shard gradients and the VQ indices (integer work) are the same whichever way the batch is cut — this is also the
+    data-parallel contract of SURVEY §8e (main.py:627: Horovod averages the ranks' gradients);
+  * the quantised latents are rows of the codebook, and no other code is closer (fp32 check on a sample of rows);
+  * the synthesised image lies in [0, 1] (clamp_with_grad, main.py:142), the loss in the range of 2*asin(d/2)^2.
+
+The file sorts last on purpose: it allocates ~45 GB.
+"""
+import math
+
+import pytest
+import torch
+
+from feed_forward_vqgan_clip_b200 import parallel
+from feed_forward_vqgan_clip_b200.clip_vit import CLIP
+from feed_forward_vqgan_clip_b200.cutouts import sample_params
+from feed_forward_vqgan_clip_b200.mixer import Mixer
+from feed_forward_vqgan_clip_b200.train_step import TrainStep
+from feed_forward_vqgan_clip_b200.vqgan import VQModel
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+MIXER = dict(input_dim=512, image_size=16, channels=256, patch_size=1, dim=1024, depth=32)
+CUTN, B, CUT = 8, 64, 224
+
+
+def _restore(eng, keep):
+    """put the mapper's master weights back (the step ends with Adam) and force a fresh bf16 shadow"""
+    eng.arena.copy_(keep)
+    eng.ext_shadow_fresh = False
+    eng._shadow_version = None
+
+
+def test_config2_full_size_step_is_invariant_to_batch_sharding():
+    torch.manual_seed(0)
+    net = Mixer(**MIXER)
+    vq = VQModel()
+    with torch.no_grad():
+        vq.quantize.embedding.weight.normal_(0, 1)
+    clip = CLIP()
+    net, vq, clip = net.to(DEV), vq.to(DEV).eval().requires_grad_(False), clip.to(DEV).eval().requires_grad_(False)
+    ts = TrainStep(net, vq, clip, cutn=CUTN, lr=1e-3)
+    eng = ts.mix
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(B, 512, generator=g) * 0.45).float().to(DEV)
+    prm = sample_params(CUTN * B, CUT, g, with_noise=False)
+    gd = torch.Generator(device=DEV).manual_seed(2)
+    N = CUTN * B
+    prm["facs"] = torch.rand(N, device=DEV, generator=gd) * 0.1                      # main.py:223-225
+    prm["noise_raw"] = torch.randn(N, 3, CUT, CUT, device=DEV, generator=gd)
+    for k in ("affine_inv", "persp_inv", "sat", "hue"):
+        prm[k] = prm[k].to(DEV)
+
+    keep = eng.arena.clone()
+    loss_full = float(ts.step(x, None, prm).item())
+    g_full = eng.grad.clone()
+    idx_full = ts.last_indices.clone().view(B, -1)
+
+    # ---- properties of the full-size step itself
+    assert math.isfinite(loss_full) and 0.0 <= loss_full <= 2.0 * (math.pi / 2) ** 2 + 1e-3, loss_full
+    assert torch.isfinite(g_full).all() and float(g_full.abs().max()) > 0
+    cb = vq.quantize.embedding.weight.detach().float()
+    assert int(idx_full.min()) >= 0 and int(idx_full.max()) < cb.shape[0]
+    assert idx_full.unique().numel() > 64, "the VQ search collapsed onto a handful of codes"
+
+    # ---- the same 64 prompts in 4 shards of 16
+    world = 4
+    acc = torch.zeros_like(g_full)
+    losses, idx = [], []
+    for r in range(world):
+        _restore(eng, keep)
+        lo, hi = parallel.shard_range(B, r, world)
+        ps = parallel.shard_cutout_params(prm, CUTN, B, lo, hi)
+        losses.append(float(ts.step(x[lo:hi].contiguous(), None, ps).item()))
+        acc += eng.grad
+        idx.append(ts.last_indices.clone().view(hi - lo, -1))
+    acc /= world
+    torch.cuda.synchronize()
+    same = (torch.cat(idx) == idx_full).float().mean().item()
+    assert same >= 0.999, same                        # integer work: identical rows of z pick identical codes
+    mean_loss = sum(losses) / world
+    assert abs(mean_loss - loss_full) <= 2e-3 * abs(loss_full), (mean_loss, loss_full)
+    a, b = acc.double(), g_full.double()
+    cosine = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300))
+    rel = float((a - b).norm() / (b.norm() + 1e-300))
+    assert cosine >= 0.999 and rel <= 3e-2, (cosine, rel)
+
+
+def test_full_size_vq_rows_are_nearest_codebook_rows():
+    """ffvc_vq_nearest_tc at the full 16384 latents x 16384 codes: z_q rows are codebook rows, and on a sample of rows no
+    other code is closer in fp32 than the one chosen (up to the fp32 rounding of the distance expression, main.py:135-137)."""
+    torch.manual_seed(3)
+    vq = VQModel()
+    with torch.no_grad():
+        vq.quantize.embedding.weight.normal_(0, 1)
+    vq = vq.to(DEV).eval().requires_grad_(False)
+    dec = vq.engine()
+    cb = vq.quantize.embedding.weight.detach().float()
+    lo, hi = float(cb.min()), float(cb.max())
+    z = torch.randn(B * 256, 256, device=DEV) * 1.5
+    zq, idx, zc = dec.quantize(z, lo, hi)
+    idx = idx.view(-1).long()
+    assert torch.equal(zq.view(-1, 256), cb[idx].to(torch.bfloat16))      # the decoder reads bf16 rows of the codebook
+    assert torch.equal(zc, z.clamp(lo, hi))
+    rows = torch.arange(0, z.shape[0], 16, device=DEV)
+    zs = z[rows].clamp(lo, hi).double()
+    d = (zs * zs).sum(1, keepdim=True) + (cb.double() ** 2).sum(1)[None] - 2.0 * zs @ cb.double().t()
+    best = d.min(dim=1).values
+    chosen = d.gather(1, idx[rows, None])[:, 0]
+    assert float((chosen - best).max()) <= 2e-3, float((chosen - best).max())     # a different pick must be a numerical tie
+    assert (d.argmin(dim=1) == idx[rows]).float().mean().item() >= 0.999
