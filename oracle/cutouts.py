@@ -3,7 +3,8 @@ with the default augmentation list ('Af','Pe','Ji','Er') (main.py:164-165,171-17
 the CLIP normalisation (main.py:631-632,797).
 
 Third-party boundary: the warps / colour jitter / erasing are `kornia==0.5.10` (requirements.txt:9; absent) — NOT pinned by
-kornia; the affine map + bilinear convention and the HSV hue shift are cross-checked against torchvision (tests/test_oracle_golden.py).  Their *sampling* is host policy; the *arithmetic* is restated here on EXPLICIT
+kornia; the affine and perspective inverse maps + bilinear convention, the erase rectangle and the HSV hue shift are cross-checked
+against torchvision's affine / perspective / erase / adjust_hue (tests/test_oracle_golden.py).  Their *sampling* is host policy; the *arithmetic* is restated here on EXPLICIT
 parameters: per-cutout inverse homographies for RandomAffine (border padding) and
 RandomPerspective (zero padding), per-cutout saturation factor / hue shift (HSV round trip as in
 kornia.color.rgb_to_hsv / hsv_to_rgb), one erase rectangle for the whole batch (same_on_batch=True), and the

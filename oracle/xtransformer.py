@@ -1,7 +1,9 @@
 """ORACLE (test infrastructure, not product): CPU fp32 restatement of the reference X-transformer mapper.
 
 `XTransformer.forward` itself is in-tree (transformer.py:28-46) but its arithmetic lives in `x-transformers==0.19.1`
-(requirements.txt:20), which is absent from /root/reference and from this image: PARITY UNPINNED.  Restated from the
+(requirements.txt:20), which is absent from /root/reference and from this image: PARITY UNPINNED by the package itself.  The stack (positions,
+causal pre-LN blocks, final norm) is cross-checked against an independent implementation of the same architecture,
+transformers' GPT2Model with mapped random weights (output + input gradient, tests/test_oracle_golden.py).  Restated from the
 package's published architecture: ContinuousTransformerWrapper(project_in Linear, learned absolute
 positional embedding, Decoder = causal pre-LayerNorm AttentionLayers alternating Attention (to_q/to_k/to_v without bias,
 dim_head 64, scale 64**-0.5, causal mask, to_out with bias) and FeedForward (Linear, exact GELU, Linear, mult 4), final

@@ -265,3 +265,105 @@ def test_cutout_warp_and_hue_restatements_match_torchvision():
                       fill=0.0)
         m = slice(14, P - 14)
         assert torch.allclose(a[..., m, m], b[..., m, m], atol=2e-5), (ang_deg, (a - b)[..., m, m].abs().max())
+
+
+def test_xtransformer_stack_restatement_matches_transformers_gpt2():
+    """x-transformers (transformer.py:3,11-20) is absent from the reference tree and the image, so oracle/xtransformer.py
+    restates ContinuousTransformerWrapper + Decoder from the published architecture.  transformers' GPT2Model
+    is an independent implementation of the same stack — learned absolute positions added unscaled, causal pre-LayerNorm
+    blocks (attention scaled by head_dim**-0.5, projections q|k|v -> out, residual; LayerNorm, Linear-GELU-Linear x4, residual),
+    final LayerNorm.  It only exists with heads * head_dim == dim, so the check runs at dim 128 = 2 heads x 64 (x-transformers'
+    fixed dim_head); with its weights mapped onto the package's key names (Conv1D stores [in, out]; the qkv bias, which
+    x-transformers does not have, is zeroed) the restatement reproduces GPT-2's hidden states and input gradient."""
+    transformers = pytest.importorskip("transformers")
+    import oracle.xtransformer as ox
+    S, C, dim, heads, depth, in_dim = 3, 16, 128, 2, 2, 24
+    T = S * S
+    hf_cfg = transformers.GPT2Config(vocab_size=8, n_positions=T + 1, n_embd=dim, n_layer=depth, n_head=heads, n_inner=4 * dim,
+                                     activation_function="gelu", resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0,
+                                     layer_norm_epsilon=1e-5, scale_attn_weights=True, scale_attn_by_inverse_layer_idx=False,
+                                     reorder_and_upcast_attn=False)
+    torch.manual_seed(41)
+    m = transformers.GPT2Model(hf_cfg).eval()
+    with torch.no_grad():
+        for p in m.parameters():                   # LayerNorms start at (1, 0), biases at 0: make every term matter
+            p.add_(0.05 * torch.randn_like(p))
+        for l in range(depth):
+            m.h[l].attn.c_attn.bias.zero_()
+    hf = {k: v.detach() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(42)
+    sd = {"proj.weight": torch.randn(T * dim, in_dim, generator=g) * 0.2, "proj.bias": torch.randn(T * dim, generator=g) * 0.1,
+          "transformer.project_in.weight": torch.randn(dim, dim, generator=g) * 0.1,
+          "transformer.project_in.bias": torch.randn(dim, generator=g) * 0.1,
+          "transformer.pos_emb.emb.weight": hf["wpe.weight"],
+          "transformer.norm.weight": hf["ln_f.weight"], "transformer.norm.bias": hf["ln_f.bias"],
+          "transformer.project_out.weight": torch.randn(C, dim, generator=g) * 0.1,
+          "transformer.project_out.bias": torch.randn(C, generator=g) * 0.1}
+    for l in range(depth):
+        a, f, h = "transformer.attn_layers.layers.%d." % (2 * l), "transformer.attn_layers.layers.%d." % (2 * l + 1), "h.%d." % l
+        sd[a + "0.weight"], sd[a + "0.bias"] = hf[h + "ln_1.weight"], hf[h + "ln_1.bias"]
+        wq, wk, wv = hf[h + "attn.c_attn.weight"].split(dim, dim=1)                   # Conv1D: [in, 3 * out]
+        sd[a + "1.to_q.weight"], sd[a + "1.to_k.weight"], sd[a + "1.to_v.weight"] = wq.t(), wk.t(), wv.t()
+        sd[a + "1.to_out.weight"], sd[a + "1.to_out.bias"] = hf[h + "attn.c_proj.weight"].t(), hf[h + "attn.c_proj.bias"]
+        sd[f + "0.weight"], sd[f + "0.bias"] = hf[h + "ln_2.weight"], hf[h + "ln_2.bias"]
+        sd[f + "1.net.0.0.weight"], sd[f + "1.net.0.0.bias"] = hf[h + "mlp.c_fc.weight"].t(), hf[h + "mlp.c_fc.bias"]
+        sd[f + "1.net.2.weight"], sd[f + "1.net.2.bias"] = hf[h + "mlp.c_proj.weight"].t(), hf[h + "mlp.c_proj.bias"]
+    assert ox.xt_depth(sd) == depth
+    x = torch.randn(3, in_dim, generator=g)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    F = torch.nn.functional
+    # the wrapper around the stack is transformer.py:30-32,44-46 + two Linears; the stack itself runs in GPT-2
+    e = F.linear(F.linear(xa, sd["proj.weight"], sd["proj.bias"]).view(3, T, dim), sd["transformer.project_in.weight"],
+                 sd["transformer.project_in.bias"])
+    hs = m(inputs_embeds=e).last_hidden_state
+    ref = F.linear(hs, sd["transformer.project_out.weight"], sd["transformer.project_out.bias"]).view(3, S, S, C).permute(0, 3, 1, 2)
+    out = ox.xtransformer_forward(sd, xb, S, C, heads)
+    assert out.shape == ref.shape == (3, C, S, S)
+    assert torch.allclose(out, ref, atol=2e-5, rtol=1e-4), (out - ref).abs().max()
+    w = torch.randn(3, C, S, S, generator=g)
+    (ref * w).sum().backward()
+    (out * w).sum().backward()
+    assert torch.allclose(xa.grad, xb.grad, atol=1e-4, rtol=1e-4), (xa.grad - xb.grad).abs().max()
+    # causality: the latent at token t must not depend on projected tokens after t (Decoder = causal=True, transformer.py:15)
+    sd2 = dict(sd)
+    pw = sd["proj.weight"].clone().view(T, dim, in_dim)
+    pw[T - 1] += 1.0                                     # perturb only the last token's projection
+    sd2["proj.weight"] = pw.view(T * dim, in_dim)
+    with torch.no_grad():
+        o2 = ox.xtransformer_forward(sd2, x, S, C, heads)
+    a1, a2 = out.detach().permute(0, 2, 3, 1).reshape(3, T, C), o2.permute(0, 2, 3, 1).reshape(3, T, C)
+    assert torch.equal(a1[:, :T - 1], a2[:, :T - 1]) and not torch.allclose(a1[:, T - 1], a2[:, T - 1])
+
+
+def test_cutout_perspective_restatement_matches_torchvision():
+    """RandomPerspective's arithmetic (main.py:177-178; kornia absent): the inverse homography cutouts.sample_params builds in
+    closed form (quadrilateral of perturbed corners -> the cut_size square, pixel centres at integer coordinates) and
+    oracle/cutouts.warp's bilinear sampling with zero padding, against torchvision's independent perspective() — which solves the
+    8x8 system for the same four point pairs and samples with pixel centres at half-integers (hence the +0.5 on both point sets)."""
+    pytest.importorskip("torchvision")
+    import torchvision.transforms.v2.functional as TF
+    from torchvision.transforms import InterpolationMode
+    import oracle.cutouts as oc
+    from feed_forward_vqgan_clip_b200.cutouts import _persp_coeffs, _quad_to_square
+    torch.manual_seed(51)
+    P = 48
+    q = float(P - 1)
+    img = torch.rand(1, 3, P, P)
+    g = torch.Generator().manual_seed(52)
+    r = torch.rand(5, 8, generator=g, dtype=torch.float64) * (0.7 * q / 2)            # distortion_scale 0.7, as in sample_params
+    dst = torch.stack([torch.stack([r[:, 0], r[:, 1]], -1), torch.stack([q - r[:, 2], r[:, 3]], -1),
+                       torch.stack([q - r[:, 4], q - r[:, 5]], -1), torch.stack([r[:, 6], q - r[:, 7]], -1)], dim=1)
+    src = torch.tensor([[0, 0], [q, 0], [q, q], [0, q]], dtype=torch.float64)
+    inv = _quad_to_square(dst, q)
+    assert torch.allclose(inv, _persp_coeffs(dst, src.expand(5, 4, 2)), atol=1e-9)    # closed form == the general solve
+    for i in range(5):
+        a = oc.warp(img, inv[i:i + 1].float(), "zeros")
+        b = TF.perspective(img, startpoints=(src + 0.5).tolist(), endpoints=(dst[i] + 0.5).tolist(),
+                           interpolation=InterpolationMode.BILINEAR, fill=None)   # plain zero padding (an explicit fill
+        assert torch.allclose(a, b, atol=5e-5), (i, (a - b).abs().max())              # attenuates edge pixels twice)
+    # RandomErasing(value=0) rectangle convention ([x0, y0, x1, y1), one rectangle for the whole batch) against TF.erase
+    x = torch.rand(2, 3, P, P)
+    prm = dict(affine_inv=torch.eye(3).repeat(4, 1, 1), persp_inv=torch.eye(3).repeat(4, 1, 1), sat=torch.ones(4), hue=torch.zeros(4),
+               erase=[5, 9, 30, 21], noise=torch.zeros(4, 3, P, P))
+    y = oc.make_cutouts(x, 2, prm, P, normalize=False)
+    assert torch.allclose(y, TF.erase(x.repeat(2, 1, 1, 1), i=9, j=5, h=12, w=25, v=torch.zeros(1)), atol=1e-5)   # the identity jitter still runs the HSV round trip
