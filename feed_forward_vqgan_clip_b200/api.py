@@ -1,6 +1,6 @@
 """The reference's Python call surface for the train-step path, backed by the B200 engines.
 
-    build_model(config)                      main.py:448-502   (model_type mlp_mixer, vitgan, xtransformer)
+    build_model(config)                      main.py:448-502   (model_type mlp_mixer, vitgan, simple_vitgan, xtransformer)
     load_vqgan_model(config_path, ckpt)      main.py:84-103
     load_clip_model(name, path)              main.py:1308-1333 (OpenAI ViT-B/32 and OpenCLIP ViT-B-32 architectures)
     MakeCutouts / synth / clamp_with_grad / vector_quantize      main.py:105-229
@@ -16,6 +16,7 @@ import torch
 from .clip_vit import CLIP, VIT_B32
 from .cutouts import MakeCutouts, sample_params  # noqa: F401
 from .mixer import Mixer
+from .simple_vitgan_mapper import SimpleGenerator as SimpleVitGAN
 from .vitgan_mapper import Generator as VitGAN
 from .xtransformer import XTransformer
 from .train_step import FusedAdam, TrainStep  # noqa: F401
@@ -53,11 +54,15 @@ def build_model(config, vq_channels=256):
         return VitGAN(initialize_size=vq_image_size // 8, dropout=_get(config, "dropout", 0), out_channels=vq_channels,
                       input_dim=clip_dim + noise_dim, dim=_get(config, "dim"), num_heads=_get(config, "num_heads", 6),
                       blocks=_get(config, "depth"))
+    if model_type == "simple_vitgan":                                            # main.py:469-478
+        return SimpleVitGAN(size=vq_image_size, dropout=_get(config, "dropout", 0), out_channels=vq_channels,
+                            input_dim=clip_dim + noise_dim, dim=_get(config, "dim"), num_heads=_get(config, "num_heads", 6),
+                            blocks=_get(config, "depth"))
     if model_type == "xtransformer":                                             # main.py:488-499
         return XTransformer(input_dim=clip_dim + noise_dim, image_size=vq_image_size, channels=vq_channels, dim=_get(config, "dim"),
                             depth=_get(config, "depth"), heads=_get(config, "num_heads", 6),
                             initial_proj=_get(config, "initial_proj", True), add_input=_get(config, "add_input", False))
-    raise NotImplementedError("model_type %r (simple_vitgan is not built)" % model_type)
+    raise ValueError("model_type should be 'vitgan' or  'mlp_mixer' or 'xtransformer'")      # main.py:501
 
 
 def load_vqgan_model(config_path=None, checkpoint_path=None):

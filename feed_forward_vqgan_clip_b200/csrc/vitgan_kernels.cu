@@ -170,6 +170,48 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ x, __nv_bfloat16
     y[i] = __float2bfloat16(x[i % n]);
 }
 
+
+// ---- SimpleGenerator (vitgan.py:262-305): the same attention at T = size*size tokens runs as batched tcgen05 GEMMs, which need
+// head-contiguous, 16-byte aligned q | k | v.  The projection WEIGHTS are re-packed (cheap, once per forward) instead of the
+// activations: row (k, h, d) of the packed to_qkv weight is row d*3H + k*H + h of the reference layout ('(d k h)', vitgan.py:82),
+// with the head dimension padded from dh to dhp (zero rows => zero q/k/v columns); w_out's columns are padded the same way.
+__global__ void pack_qkv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int H, int dh, int dhp, int D) {
+  const long long total = 3LL * H * dhp * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % D);
+    const long long r = i / D;
+    const int d = (int)(r % dhp), kh = (int)(r / dhp);
+    wp[i] = __float2bfloat16(d < dh ? w[((long long)d * 3 * H + kh) * D + c] : 0.f);
+  }
+}
+__global__ void unpack_qkv_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int H, int dh, int dhp, int D) {
+  const long long total = 3LL * H * dh * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % D);
+    const long long r = i / D;                       // reference row d*3H + kh
+    const int kh = (int)(r % (3 * H)), d = (int)(r / (3 * H));
+    dw[i] += dwp[((long long)kh * dhp + d) * D + c];
+  }
+}
+__global__ void pack_out_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int H, int dh, int dhp, int D) {
+  const long long total = (long long)D * H * dhp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % (H * dhp));
+    const long long r = i / (H * dhp);
+    const int d = col % dhp, h = col / dhp;
+    wp[i] = __float2bfloat16(d < dh ? w[r * (H * dh) + h * dh + d] : 0.f);
+  }
+}
+__global__ void unpack_out_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int H, int dh, int dhp, int D) {
+  const long long total = (long long)D * H * dh;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % (H * dh));
+    const long long r = i / (H * dh);
+    const int d = col % dh, h = col / dh;
+    dw[i] += dwp[r * (H * dhp) + h * dhp + d];
+  }
+}
+
 }  // namespace ffvc
 
 using namespace ffvc;
@@ -232,6 +274,39 @@ extern "C" int ffvc_cast_f32_bf16_pitched(const float* src, void* dst, int rows,
 }
 extern "C" int ffvc_broadcast_rows(const float* x, void* y, int B, long long n, void* stream) {
   broadcast_rows_kernel<<<grid_for_v((long long)B * n, 256), 256, 0, ST(stream)>>>(x, BF(y), B, n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+static int pack_check(int H, int dh, int dhp, int D) {
+  if (H < 1 || dh < 1 || dhp < dh || D < 1) return set_error(FFVC_ERR_ARG, "vitgan pack: need H >= 1, 1 <= dh <= dhp, D >= 1");
+  return FFVC_OK;
+}
+extern "C" int ffvc_vitgan_pack_qkv_weight(const float* w, void* wp, int H, int dh, int dhp, int D, void* stream) {
+  int rc = pack_check(H, dh, dhp, D);
+  if (rc) return rc;
+  pack_qkv_weight_kernel<<<grid_for_v(3LL * H * dhp * D, 256), 256, 0, ST(stream)>>>(w, BF(wp), H, dh, dhp, D);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_vitgan_unpack_qkv_wgrad(const float* dwp, float* dw, int H, int dh, int dhp, int D, void* stream) {
+  int rc = pack_check(H, dh, dhp, D);
+  if (rc) return rc;
+  unpack_qkv_wgrad_kernel<<<grid_for_v(3LL * H * dh * D, 256), 256, 0, ST(stream)>>>(dwp, dw, H, dh, dhp, D);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_vitgan_pack_out_weight(const float* w, void* wp, int H, int dh, int dhp, int D, void* stream) {
+  int rc = pack_check(H, dh, dhp, D);
+  if (rc) return rc;
+  pack_out_weight_kernel<<<grid_for_v((long long)D * H * dhp, 256), 256, 0, ST(stream)>>>(w, BF(wp), H, dh, dhp, D);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_vitgan_unpack_out_wgrad(const float* dwp, float* dw, int H, int dh, int dhp, int D, void* stream) {
+  int rc = pack_check(H, dh, dhp, D);
+  if (rc) return rc;
+  unpack_out_wgrad_kernel<<<grid_for_v((long long)D * H * dh, 256), 256, 0, ST(stream)>>>(dwp, dw, H, dh, dhp, D);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

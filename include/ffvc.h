@@ -305,6 +305,18 @@ int ffvc_cast_f32_bf16_pitched(const float* src, void* dst, int rows, int cols, 
 /* y[b][:] = bf16(x[:]) for b < B (pos_emb1D broadcast over the batch). */
 int ffvc_broadcast_rows(const float* x, void* y, int B, long long n, void* stream);
 
+/* SimpleGenerator (vitgan.py:262-305; build_model model_type "simple_vitgan", main.py:469-478): the same attention at
+ * T = size*size tokens runs as batched ffvc_gemm launches, which need head-contiguous, 16-byte aligned q | k | v.  The projection
+ * WEIGHTS are re-packed instead of the activations, the head dimension padded from dh to dhp (a multiple of 8):
+ *   pack_qkv:   wp[(k*H + h)*dhp + d][c] = bf16(w[d*3H + k*H + h][c]) for d < dh, 0 in the padding   (to_qkv.weight [3*H*dh][D], '(d k h)' vitgan.py:82)
+ *   unpack_qkv: dw[d*3H + k*H + h][c] += dwp[(k*H + h)*dhp + d][c]                                  (its fp32 gradient)
+ *   pack_out:   wp[r][h*dhp + d] = bf16(w[r][h*dh + d]), 0 in the padding                           (w_out.weight [D][H*dh], vitgan.py:67,96-97)
+ *   unpack_out: dw[r][h*dh + d] += dwp[r][h*dhp + d] */
+int ffvc_vitgan_pack_qkv_weight(const float* w, void* wp, int H, int dh, int dhp, int D, void* stream);
+int ffvc_vitgan_unpack_qkv_wgrad(const float* dwp, float* dw, int H, int dh, int dhp, int D, void* stream);
+int ffvc_vitgan_pack_out_weight(const float* w, void* wp, int H, int dh, int dhp, int D, void* stream);
+int ffvc_vitgan_unpack_out_wgrad(const float* dwp, float* dw, int H, int dh, int dhp, int D, void* stream);
+
 /* sizeof() of the ABI structs, for binding self-checks. */
 int ffvc_sizeof(const char* name);
 

@@ -7,8 +7,9 @@ Follows /root/reference/vitgan.py:
   - Attention                              vitgan.py:44-97     (no-bias to_qkv, split 'b t (d k h) -> k b h t d',
                                                                 scale = dim ** -0.5 (FULL model dim), w_out with bias)
   - MLP (Linear, exact GELU, Linear)       vitgan.py:24-41
+  - SimpleGenerator.forward                vitgan.py:262-305   (T = size*size tokens, hl0 = permuted inp(noise) + pos_emb1D)
 Pinned by tests/test_oracle_golden.py against outputs + parameter gradients of the real reference module
-(tests/golden/vitgan.pt, produced by tests/golden/make_golden.py importing /root/reference/vitgan.py)."""
+(tests/golden/vitgan.pt and simple_vitgan.pt, produced by tests/golden/make_golden.py importing /root/reference/vitgan.py)."""
 import torch
 import torch.nn.functional as F
 
@@ -25,11 +26,9 @@ def vitgan_blocks(sd):
     return n
 
 
-def vitgan_forward(sd, noise, out_channels, num_heads):
-    T, D = sd["pos_emb1D"].shape
-    B = noise.shape[0]
-    x = F.linear(noise, sd["mlp.weight"], sd["mlp.bias"]).view(B, T, D)
-    hl = sd["pos_emb1D"]
+def _encoder(sd, hl, x, num_heads):
+    """GTransformerEncoder (vitgan.py:138-164): hl is transformed, x (the modulation signal) is carried unchanged."""
+    B, T, D = x.shape
     for i in range(vitgan_blocks(sd)):
         p = "Transformer_Encoder.blocks.%d." % i
         s = _sln(sd, p + "norm1.", hl, x)
@@ -44,6 +43,30 @@ def vitgan_forward(sd, noise, out_channels, num_heads):
         s2 = _sln(sd, p + "norm2.", hl_temp, x)
         u = F.gelu(F.linear(s2, sd[p + "mlp.linear1.weight"], sd[p + "mlp.linear1.bias"]))
         hl = F.linear(u, sd[p + "mlp.linear2.weight"], sd[p + "mlp.linear2.bias"]) + hl_temp
+    return hl
+
+
+def vitgan_forward(sd, noise, out_channels, num_heads):
+    T, D = sd["pos_emb1D"].shape
+    B = noise.shape[0]
+    x = F.linear(noise, sd["mlp.weight"], sd["mlp.bias"]).view(B, T, D)
+    hl = _encoder(sd, sd["pos_emb1D"], x, num_heads)
     y = _sln(sd, "sln_norm.", hl, x)
     y = F.linear(y, sd["w_out.0.weight"], sd["w_out.0.bias"])
     return y.reshape(B, out_channels, T, T)
+
+
+def simple_vitgan_forward(sd, noise, out_channels, num_heads):
+    """SimpleGenerator.forward (vitgan.py:296-305; build_model model_type 'simple_vitgan', main.py:469-478): T = size*size
+    tokens; the encoder's hl starts as inp(noise) viewed (B, dim, T), permuted to (B, T, dim), plus pos_emb1D; w_out maps
+    dim -> out_channels per token and the result is permuted to (B, C, size, size)."""
+    T, D = sd["pos_emb1D"].shape
+    B = noise.shape[0]
+    S = int(round(T ** 0.5))
+    inp = F.linear(noise, sd["inp.weight"], sd["inp.bias"])
+    x = F.linear(noise, sd["mlp.weight"], sd["mlp.bias"]).view(B, T, D)
+    hl = inp.view(B, D, T).permute(0, 2, 1) + sd["pos_emb1D"]
+    hl = _encoder(sd, hl, x, num_heads)
+    y = _sln(sd, "sln_norm.", hl, x)
+    y = F.linear(y, sd["w_out.0.weight"], sd["w_out.0.bias"])
+    return y.view(B, S, S, out_channels).permute(0, 3, 1, 2)

@@ -55,6 +55,22 @@ def golden_vitgan():
                os.path.join(OUT, "vitgan.pt"))
 
 
+def golden_simple_vitgan():
+    from vitgan import SimpleGenerator
+    torch.manual_seed(6)
+    cfg = dict(size=3, dim=24, blocks=2, num_heads=3, out_channels=4, input_dim=16)      # T = 9, dim_head = 8
+    net = SimpleGenerator(**cfg)
+    x = torch.randn(3, 16)
+    y = net(x)
+    w = torch.randn_like(y)
+    (y * w).sum().backward()
+    big = SimpleGenerator(size=16, dim=256, blocks=1, num_heads=6, out_channels=256, input_dim=512)
+    torch.save(dict(cfg=cfg, state_dict={k: v.detach().clone() for k, v in net.state_dict().items()}, x=x, w=w, y=y.detach(),
+                    grads={k: p.grad.clone() for k, p in net.named_parameters()},
+                    keys_16x256=[(k, tuple(v.shape)) for k, v in big.state_dict().items()]),
+               os.path.join(OUT, "simple_vitgan.pt"))
+
+
 def golden_clip():
     from cloob import VisualTransformer
     torch.manual_seed(1)
@@ -143,8 +159,13 @@ def golden_glue():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                # regenerate only the named fixtures, e.g. `make_golden.py simple_vitgan`
+        for name in sys.argv[1:]:
+            globals()["golden_" + name]()
+        sys.exit(0)
     golden_mixer()
     golden_vitgan()
+    golden_simple_vitgan()
     golden_clip()
     golden_clip_text()
     golden_glue()

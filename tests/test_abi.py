@@ -82,6 +82,25 @@ def test_vitgan_state_dict_contract_and_seeded_init_match_reference_golden():
     assert shapes["Transformer_Encoder.blocks.0.attn.w_out.weight"] == (1024, 1020)
 
 
+def test_simple_vitgan_state_dict_contract_and_seeded_init_match_reference_golden():
+    """model_type simple_vitgan (main.py:469-478): same keys, shapes, construction order (=> same seeded init) as the reference's
+    vitgan.SimpleGenerator; build_model routes to it with the reference's argument mapping."""
+    from feed_forward_vqgan_clip_b200 import api
+    from feed_forward_vqgan_clip_b200.simple_vitgan_mapper import SimpleGenerator
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "simple_vitgan.pt"))
+    torch.manual_seed(6)
+    net = SimpleGenerator(**gold["cfg"])
+    sd, ref = net.state_dict(), gold["state_dict"]
+    assert list(sd.keys()) == list(ref.keys())
+    for k in ref:
+        assert sd[k].shape == ref[k].shape and torch.equal(sd[k], ref[k]), k
+    big = api.build_model(dict(model_type="simple_vitgan", clip_model="ViT-B/32", vq_image_size=16, noise_dim=0, dim=256, depth=1,
+                               dropout=0))
+    assert [(k, tuple(v.shape)) for k, v in big.state_dict().items()] == [(k, tuple(s)) for k, s in gold["keys_16x256"]]
+    with pytest.raises(ValueError):
+        api.build_model(dict(model_type="no_such_mapper", dim=8, depth=1))
+
+
 def test_option_switches_and_env_override():
     lib = _lib.load()
     assert lib.ffvc_get_option(b"no_such_option") == -1

@@ -41,6 +41,18 @@ def test_vitgan_oracle_matches_reference_forward_and_grads():
         assert torch.allclose(sd[k].grad, ref, rtol=1e-4, atol=1e-5), k
 
 
+def test_simple_vitgan_oracle_matches_reference_forward_and_grads():
+    """model_type 'simple_vitgan' (main.py:469-478): oracle/vitgan.simple_vitgan_forward against the real vitgan.SimpleGenerator"""
+    import oracle.vitgan as ovit
+    g = torch.load(os.path.join(G, "simple_vitgan.pt"))
+    sd = {k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    y = ovit.simple_vitgan_forward(sd, g["x"], g["cfg"]["out_channels"], g["cfg"]["num_heads"])
+    assert y.shape == g["y"].shape and torch.allclose(y, g["y"], rtol=1e-5, atol=1e-6)
+    (y * g["w"]).sum().backward()
+    for k, ref in g["grads"].items():
+        assert torch.allclose(sd[k].grad, ref, rtol=1e-4, atol=1e-5), k
+
+
 def test_clip_oracle_matches_reference_twin():
     g = torch.load(os.path.join(G, "clip_vit.pt"))
     x = g["x"].clone().requires_grad_(True)
