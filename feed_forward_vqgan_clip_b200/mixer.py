@@ -95,8 +95,7 @@ class MixerEngine:
         self.m = m
         self.params = list(m.parameters())
         dev = self.params[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("Mixer runs on CUDA only (no CPU fallback): move the module to a B200 first")
+        ops.require_cuda(dev, "Mixer")
         self.dev = dev
         self.S, self.C, self.D, self.L, self.IN = m.image_size, m.channels, m.dim, m.depth, m.input_dim
         self.T = self.S * self.S

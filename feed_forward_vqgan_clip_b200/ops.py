@@ -17,6 +17,12 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+def require_cuda(dev, what):
+    """every engine calls this on construction: the product path exists on CUDA only"""
+    if dev.type != "cuda":
+        raise RuntimeError("%s runs on CUDA only (no CPU fallback): move the module to a B200 first" % what)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 

@@ -74,7 +74,7 @@ class SimpleVitGANEngine:
         self.m = m
         self.params = list(m.parameters())
         dev = self.params[0].device
-        self._check_device(dev)
+        ops.require_cuda(dev, "the SimpleVitGAN mapper")
         self.dev = dev
         self.S, self.D, self.L, self.H = m.size, m.dim, m.blocks, m.num_heads
         self.T = self.S * self.S
@@ -109,11 +109,6 @@ class SimpleVitGANEngine:
         self.wout = [torch.empty(self.D, self.Wi, device=dev, dtype=BF16) for _ in range(self.L)]
         self._shadow_version = None
         self.ext_shadow_fresh = False
-
-    @staticmethod
-    def _check_device(dev):
-        if dev.type != "cuda":
-            raise RuntimeError("the SimpleVitGAN mapper runs on CUDA only (no CPU fallback)")
 
     def valid(self):
         return all(p.data_ptr() == q for p, q in zip(self.params, self._ptrs))

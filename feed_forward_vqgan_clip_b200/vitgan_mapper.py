@@ -103,8 +103,7 @@ class VitGANEngine:
         self.m = m
         self.params = list(m.parameters())
         dev = self.params[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("the VitGAN mapper runs on CUDA only (no CPU fallback)")
+        ops.require_cuda(dev, "the VitGAN mapper")
         self.dev = dev
         self.T, self.D, self.L, self.H = m.initialize_size * 8, m.dim, m.blocks, m.num_heads
         self.C, self.IN = m.out_channels, m.input_dim

@@ -96,8 +96,7 @@ class XTEngine:
         self.m = m
         self.params = list(m.parameters())
         dev = self.params[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("the X-transformer mapper runs on CUDA only (no CPU fallback)")
+        ops.require_cuda(dev, "the X-transformer mapper")
         self.dev = dev
         self.S, self.C, self.D, self.L, self.H, self.IN = m.image_size, m.channels, m.dim, m.depth, m.heads, m.input_dim
         self.T = self.S * self.S

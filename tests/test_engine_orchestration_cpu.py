@@ -1,0 +1,92 @@
+"""Host logic of the mapper engines on the CPU: every engine's forward / backward ORCHESTRATION — which buffers, with which
+shapes, strides, offsets and epilogues, go into which ffvc_* call, and where each gradient lands in the flat arena — run against
+tests/abi_model.py (a torch statement of the C ABI's contracts) and compared with the CPU oracle.  The product path is
+untouched: `ops.call` / `ops.gemm` are swapped for the model inside these tests only, and `ops.require_cuda` (which makes the
+engines refuse CPU tensors, tests/test_abi.py::test_no_cpu_fallback) is relaxed for their duration."""
+import pytest
+import torch
+
+import abi_model
+import oracle.mixer as omix
+import oracle.vitgan as ovit
+import oracle.xtransformer as oxt
+from feed_forward_vqgan_clip_b200 import mixer, ops, simple_vitgan_mapper, vitgan_mapper, xtransformer
+
+
+@pytest.fixture
+def abi_on_cpu(monkeypatch):
+    monkeypatch.setattr(ops, "gemm_raw", abi_model.gemm_raw)
+    monkeypatch.setattr(ops, "gemm", lambda a, b, out, M, N, K, **kw: abi_model.gemm_raw(a, b, out, M, N, K, **kw))
+    monkeypatch.setattr(ops, "call", abi_model.call)
+    monkeypatch.setattr(ops, "require_cuda", lambda dev, what: None)
+    for mod in (mixer, vitgan_mapper, simple_vitgan_mapper, xtransformer):
+        monkeypatch.setattr(mod, "call", abi_model.call)
+
+
+def cos(a, b):
+    a, b = a.detach().flatten().float(), b.detach().flatten().float()
+    return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _check(net, oracle_forward, x, out_shape):
+    sd = {k: v.clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    y = net(x)
+    yr = oracle_forward(sd)
+    assert y.shape == yr.shape == out_shape
+    assert float((y - yr).detach().abs().max()) <= 3e-2 * float(yr.detach().abs().max())          # bf16 activations against the fp32 oracle
+    w = torch.randn(out_shape, generator=torch.Generator().manual_seed(9))
+    (y * w).sum().backward()
+    (yr * w).sum().backward()
+    gscale = max(float(v.grad.abs().max()) for v in sd.values() if v.grad is not None)
+    for n, p in net.named_parameters():
+        ref = sd[n].grad
+        if ref is None or float(ref.abs().max()) == 0.0:       # e.g. the unused last row of the x-transformer position table
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        err = float((p.grad - ref).abs().max())
+        if p.numel() > 1 and float(ref.abs().max()) > 1e-3 * gscale:
+            assert cos(p.grad, ref) > 0.995 and err <= 6e-2 * float(ref.abs().max()), (n, cos(p.grad, ref), err)
+        else:
+            # scalar SLN gamma / beta (one large cancelling sum) and gradients that are zero in exact arithmetic — the mixer's
+            # second token-mixing bias shifts every channel of a token equally, which each later LayerNorm removes: rounding
+            # noise of the bf16 activations, bounded against the overall gradient magnitude
+            assert err <= 2e-2 * max(1.0, gscale), (n, err, gscale)
+
+
+def test_no_cpu_path_outside_this_fixture():
+    with pytest.raises(RuntimeError):
+        ops.require_cuda(torch.device("cpu"), "x")
+
+
+def test_mixer_engine_orchestration(abi_on_cpu):
+    torch.manual_seed(0)
+    cfg = dict(input_dim=16, image_size=4, channels=8, patch_size=1, dim=32, depth=2)
+    net = mixer.Mixer(**cfg)
+    x = torch.randn(3, 16)
+    _check(net, lambda sd: omix.mixer_forward(sd, x, 4, 8), x, (3, 8, 4, 4))
+
+
+@pytest.mark.parametrize("dim,heads", [(48, 3), (40, 3)])           # 40 / 3 -> head dim 13, weight dim 39 (padded pitches)
+def test_vitgan_engine_orchestration(abi_on_cpu, dim, heads):
+    torch.manual_seed(1)
+    cfg = dict(initialize_size=1, dim=dim, blocks=2, num_heads=heads, out_channels=8, input_dim=16)
+    net = vitgan_mapper.Generator(**cfg)
+    x = torch.randn(3, 16)
+    _check(net, lambda sd: ovit.vitgan_forward(sd, x, 8, heads), x, (3, 8, 8, 8))
+
+
+@pytest.mark.parametrize("dim,heads", [(32, 2), (40, 3)])           # 40 / 3 -> head dim 13 padded to 16 in the packed weights
+def test_simple_vitgan_engine_orchestration(abi_on_cpu, dim, heads):
+    torch.manual_seed(2)
+    cfg = dict(size=4, dim=dim, blocks=2, num_heads=heads, out_channels=8, input_dim=16)
+    net = simple_vitgan_mapper.SimpleGenerator(**cfg)
+    x = torch.randn(3, 16)
+    _check(net, lambda sd: ovit.simple_vitgan_forward(sd, x, 8, heads), x, (3, 8, 4, 4))
+
+
+def test_xtransformer_engine_orchestration(abi_on_cpu):
+    torch.manual_seed(3)
+    cfg = dict(input_dim=16, image_size=4, channels=8, dim=32, depth=2, heads=2, initial_proj=True, add_input=False)
+    net = xtransformer.XTransformer(**cfg)
+    x = torch.randn(3, 16)
+    _check(net, lambda sd: oxt.xtransformer_forward(sd, x, 4, 8, 2), x, (3, 8, 4, 4))
