@@ -5,6 +5,7 @@
     load_clip_model(name, path)              main.py:1308-1333 (OpenAI ViT-B/32 and OpenCLIP ViT-B-32 architectures)
     MakeCutouts / synth / clamp_with_grad / vector_quantize      main.py:105-229
     train_step(net, vq, perceptor, ...)      the body of main.py:729-837 as one fused object (TrainStep)
+    CheckpointWriter(train_step, folder)     main.py:904-911 (checkpoint.th / checkpoint_ema.th / opt.th), asynchronous, optionally sharded
 
 `config` may be any mapping / attribute object with the keys of configs/example.yaml (an OmegaConf DictConfig or a
 plain dict both work); unknown keys are ignored, optional keys defaulted exactly like main.py:450-457,466,496-498.
@@ -13,6 +14,7 @@ import os
 
 import torch
 
+from .checkpoint import CheckpointWriter, load_sharded  # noqa: F401
 from .clip_vit import CLIP, VIT_B32
 from .cutouts import MakeCutouts, sample_params  # noqa: F401
 from .mixer import Mixer
