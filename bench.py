@@ -247,15 +247,16 @@ def main():
     for i in range(args.warmup):
         run_dev(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if rank == 0 else None      # one nvidia-smi poller per job, on the rank that reports
+    if sampler is not None:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
         run_dev(i)
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
