@@ -53,8 +53,7 @@ class TextEngine:
     def __init__(self, m):
         cfg = m.cfg
         self.dev = m.text_projection.device
-        if self.dev.type != "cuda":
-            raise RuntimeError("the CLIP text encoder runs on CUDA only (no CPU fallback)")
+        ops.require_cuda(self.dev, "the CLIP text encoder")
         self.ptr = m.text_projection.data_ptr()
         self.W, self.L, self.Hh, self.E, self.T = (cfg["transformer_width"], cfg["transformer_layers"],
                                                    cfg["transformer_heads"], cfg["embed_dim"], cfg["context_length"])

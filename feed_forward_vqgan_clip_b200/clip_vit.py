@@ -109,8 +109,7 @@ class ClipEngine:
         self.vis = vis
         cfg = vis.cfg
         self.dev = vis.proj.device
-        if self.dev.type != "cuda":
-            raise RuntimeError("the CLIP image encoder runs on CUDA only (no CPU fallback)")
+        ops.require_cuda(self.dev, "the CLIP image encoder")
         self._ptr = vis.proj.data_ptr()
         self.W, self.L, self.Hh, self.E = cfg["width"], cfg["layers"], cfg["heads"], cfg["output_dim"]
         self.patch = cfg["patch_size"]

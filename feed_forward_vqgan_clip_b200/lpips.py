@@ -42,8 +42,7 @@ class LpipsVGG16(nn.Module):
 class DiversityEngine:
     def __init__(self, net):
         self.dev = net.slice1[0].weight.device
-        if self.dev.type != "cuda":
-            raise RuntimeError("the LPIPS diversity term runs on CUDA only (no CPU fallback)")
+        ops.require_cuda(self.dev, "the LPIPS diversity term")
         self.ptr = net.slice1[0].weight.data_ptr()
         self.pk = {}
         for k, v in net.state_dict().items():

@@ -148,8 +148,7 @@ class DecoderEngine:
         self.model = model
         self.cfg = model.cfg
         self.dev = model.post_quant_conv.weight.device
-        if self.dev.type != "cuda":
-            raise RuntimeError("the VQGAN decoder runs on CUDA only (no CPU fallback)")
+        ops.require_cuda(self.dev, "the VQGAN decoder")
         self._ptr = model.post_quant_conv.weight.data_ptr()
         self.layout = _decoder_layout(self.cfg)
         self.pk = {}

@@ -10,6 +10,20 @@ import torch.nn.functional as F
 BF16, F32 = torch.bfloat16, torch.float32
 
 
+def _dgelu(x):
+    return 0.5 * (1 + torch.erf(x * 0.7071067811865476)) + x * torch.exp(-0.5 * x * x) * 0.3989422804014327
+
+
+def _dsig_mul(x, c):          # d/dx [x * sigmoid(c x)]
+    s = torch.sigmoid(c * x)
+    return s * (1 + c * x * (1 - s))
+
+
+# FFVC_ACT_*: none, exact-erf GELU, QuickGELU x*sigmoid(1.702x) (cloob.py:179-181), swish, ReLU — and their derivatives (mul_mode)
+_ACT = {0: lambda v: v, 1: F.gelu, 2: lambda v: v * torch.sigmoid(1.702 * v), 3: lambda v: v * torch.sigmoid(v), 4: torch.relu}
+_DACT = {1: _dgelu, 2: lambda x: _dsig_mul(x, 1.702), 3: lambda x: _dsig_mul(x, 1.0), 4: lambda x: (x > 0).float()}
+
+
 def _mat(t, off, rows, cols, row_stride, col_stride):
     return torch.as_strided(t, (rows, cols), (row_stride, col_stride), t.storage_offset() + off)
 
@@ -41,15 +55,9 @@ def gemm_raw(a, b, out, M, N, K, *, a_mode=0, b_mode=0, a_ld=None, b_ld=None, a_
             v = v + (bias.float()[None, :N] if bias_mode == 1 else bias.float()[:M, None])
         if pre_out is not None:
             _mat(pre_out, oo, M, N, ldc, 1).copy_(v)
-        if act == 1:
-            v = F.gelu(v)
-        elif act != 0:
-            raise NotImplementedError
-        if mul_mode == 1:
-            x = _mat(aux, oo, M, N, ldc, 1).float()
-            v = v * (0.5 * (1 + torch.erf(x * 0.7071067811865476)) + x * torch.exp(-0.5 * x * x) * 0.3989422804014327)
-        elif mul_mode != 0:
-            raise NotImplementedError
+        v = _ACT[act](v)
+        if mul_mode:
+            v = v * _DACT[mul_mode](_mat(aux, oo, M, N, ldc, 1).float())
         if res is not None:
             v = v + _mat(res, oo, M, N, ldc, 1).float()
         O = _mat(out, oo, M, N, ldc, 1)
@@ -90,8 +98,9 @@ def k_layernorm_fwd(x, g, b, y, mean, rstd, R, D, eps):
     mu = xf.mean(1)
     var = xf.var(1, unbiased=False)
     rs = (var + eps).rsqrt()
-    mean.view(-1)[:R] = mu
-    rstd.view(-1)[:R] = rs
+    if mean is not None:
+        mean.view(-1)[:R] = mu
+        rstd.view(-1)[:R] = rs
     y.view(-1)[:R * D] = (((xf - mu[:, None]) * rs[:, None]) * g.view(-1)[:D] + b.view(-1)[:D]).reshape(-1)
 
 
@@ -213,3 +222,45 @@ def k_layernorm_bwd_sums(dy, x, g, mean, rstd, add, dx, dg, db, colsum_out, rows
 
 def k_rowsum(dy, db, B, J, D):
     db.view(-1)[:J].add_(dy.reshape(-1)[:B * J * D].view(B, J, D).float().sum((0, 2)))
+
+
+def k_clip_assemble(pe, cls, pos, x, N, T, W):
+    X = x.view(-1)[:N * T * W].view(N, T, W)
+    X[:, 0] = (cls.view(-1)[:W] + pos.view(-1)[:W])
+    X[:, 1:] = pe.reshape(-1)[:N * (T - 1) * W].view(N, T - 1, W).float() + pos.view(-1)[W:T * W].view(T - 1, W)
+
+
+def k_copy_rows(src, dst, rows, D, src_stride, dst_stride):
+    S = torch.as_strided(src, (rows, D), (src_stride, 1), src.storage_offset())
+    torch.as_strided(dst, (rows, D), (dst_stride, 1), dst.storage_offset()).copy_(S)
+
+
+def _heads(qkv, N, T, H, dh):
+    x = qkv.reshape(-1)[:N * T * 3 * H * dh].view(N, T, 3, H, dh).float().permute(2, 0, 3, 1, 4)      # q | k | v, head-major columns
+    return x[0], x[1], x[2]
+
+
+def k_mha_small_fwd(qkv, out, N, T, H, dh, scale):
+    q, k, v = _heads(qkv, N, T, H, dh)
+    o = torch.softmax(q @ k.transpose(-1, -2) * scale, -1) @ v
+    out.view(-1)[:N * T * H * dh] = o.permute(0, 2, 1, 3).reshape(-1)
+
+
+def k_mha_small_bwd(qkv, dout, dqkv, N, T, H, dh, scale):
+    q, k, v = _heads(qkv, N, T, H, dh)
+    dO = dout.reshape(-1)[:N * T * H * dh].view(N, T, H, dh).float().permute(0, 2, 1, 3)
+    P = torch.softmax(q @ k.transpose(-1, -2) * scale, -1)
+    dP = dO @ v.transpose(-1, -2)
+    dS = P * (dP - (P * dP).sum(-1, keepdim=True)) * scale
+    d = torch.stack([dS @ k, dS.transpose(-1, -2) @ q, P.transpose(-1, -2) @ dO])                    # [3][N][H][T][dh]
+    dqkv.view(-1)[:N * T * 3 * H * dh] = d.permute(1, 3, 0, 2, 4).reshape(-1)
+
+
+def k_embed_tokens(tok, emb, pos, x, rows, T, W):
+    t = tok.reshape(-1)[:rows]
+    x.view(-1)[:rows * W] = (emb.view(-1, W)[t] + pos.view(-1, W)[torch.arange(rows) % T]).reshape(-1)
+
+
+def k_gather_rows(src, idx, dst, B, T, W):
+    S = src.reshape(-1)[:B * T * W].view(B, T, W)
+    dst.view(-1)[:B * W] = S[torch.arange(B), idx.reshape(-1)[:B]].reshape(-1)

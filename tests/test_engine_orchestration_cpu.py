@@ -10,7 +10,9 @@ import abi_model
 import oracle.mixer as omix
 import oracle.vitgan as ovit
 import oracle.xtransformer as oxt
-from feed_forward_vqgan_clip_b200 import mixer, ops, simple_vitgan_mapper, vitgan_mapper, xtransformer
+import oracle.clip_text as otext
+import oracle.clip_vit as oclip
+from feed_forward_vqgan_clip_b200 import clip_text, clip_vit, mixer, ops, simple_vitgan_mapper, vitgan_mapper, xtransformer
 
 
 @pytest.fixture
@@ -19,7 +21,7 @@ def abi_on_cpu(monkeypatch):
     monkeypatch.setattr(ops, "gemm", lambda a, b, out, M, N, K, **kw: abi_model.gemm_raw(a, b, out, M, N, K, **kw))
     monkeypatch.setattr(ops, "call", abi_model.call)
     monkeypatch.setattr(ops, "require_cuda", lambda dev, what: None)
-    for mod in (mixer, vitgan_mapper, simple_vitgan_mapper, xtransformer):
+    for mod in (mixer, vitgan_mapper, simple_vitgan_mapper, xtransformer, clip_vit, clip_text):
         monkeypatch.setattr(mod, "call", abi_model.call)
 
 
@@ -90,3 +92,38 @@ def test_xtransformer_engine_orchestration(abi_on_cpu):
     net = xtransformer.XTransformer(**cfg)
     x = torch.randn(3, 16)
     _check(net, lambda sd: oxt.xtransformer_forward(sd, x, 4, 8, 2), x, (3, 8, 4, 4))
+
+
+@pytest.mark.parametrize("act,fused", [("quick_gelu", True), ("gelu", True), ("quick_gelu", False)])
+def test_clip_image_encoder_orchestration(abi_on_cpu, monkeypatch, act, fused):
+    """ClipEngine (encode_image, main.py:799) forward + input gradient, with the fused short-sequence attention entry point and
+    with the general batched-GEMM attention (padded score rows)."""
+    monkeypatch.setattr(clip_vit.ClipEngine, "FUSED_ATTN", fused)
+    cfg = dict(input_resolution=64, patch_size=32, width=128, layers=2, heads=2, output_dim=32)      # 5 tokens, 64-wide heads
+    sd = oclip.init_clip_state_dict(cfg, seed=5)
+    vis = clip_vit.VisualTransformer(act=act, **cfg)
+    vis.load_state_dict(sd)
+    x = torch.randn(3, 3, 64, 64, generator=torch.Generator().manual_seed(6))
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y = vis(xa)
+    yr = oclip.encode_image(sd, xb, cfg, act=act)
+    assert y.shape == yr.shape == (3, 32)
+    assert float((y - yr).detach().abs().max()) <= 3e-2 * float(yr.detach().abs().max())
+    w = torch.randn(3, 32, generator=torch.Generator().manual_seed(7))
+    (y * w).sum().backward()
+    (yr * w).sum().backward()
+    assert cos(xa.grad, xb.grad) > 0.995
+
+
+def test_clip_text_encoder_orchestration(abi_on_cpu):
+    """TextEngine (encode_text, main.py:733): causal attention over padded score rows, EOT-row gather, projection"""
+    cfg = dict(embed_dim=32, context_length=77, vocab_size=100, transformer_width=128, transformer_heads=2, transformer_layers=2)
+    m = clip_text.TextTransformer(**cfg)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(8)
+    text = torch.randint(1, 90, (3, 77), generator=g)
+    text[0, 10], text[1, 76], text[2, 3] = 99, 99, 99                   # EOT = the largest id, at different positions
+    y = m(text)
+    yr = otext.encode_text(sd, text, 2)
+    assert y.shape == yr.shape == (3, 32)
+    assert float((y - yr).abs().max()) <= 3e-2 * float(yr.abs().max())
