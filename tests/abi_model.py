@@ -32,7 +32,13 @@ def gemm_raw(a, b, out, M, N, K, *, a_mode=0, b_mode=0, a_ld=None, b_ld=None, a_
              k_segs=1, splits=1, block_n=0, conv=None, pre_out=None, aux=None, res=None, bias=None, ldc=None, out_bs=0,
              atomic=False, bias_mode=1, act=0, mul_mode=0, alpha=1.0, a_off=0, b_off=0, out_off=0, batch_inner=1, a_bs_in=0,
              b_bs_in=0, out_bs_in=0, tile_m=0, two_cta=0, epi_warps=0, argmin_out=None):
-    assert conv is None and argmin_out is None, "the model covers the dense forms only"
+    assert argmin_out is None, "the arg-min epilogue is modelled by k_vq_nearest_tc"
+    if a_mode == 2:                                         # FFVC_OP_CONV3X3: implicit GEMM over an NHWC tensor, K = 9 * Cin
+        n, h, w, c = conv
+        assert M == n * h * w and K == 9 * c and batch == 1 and k_segs == 1 and not atomic
+        v = alpha * _conv3x3_packed(a, b, n, h, w, c, N)
+        _epilogue(v, out, N if ldc is None else ldc, bias if bias_mode == 1 else None, res, aux, mul_mode, act)
+        return out
     assert a.dtype == BF16 and b.dtype == BF16
     if a_ld is None:
         a_ld = K if a_mode == 0 else M
@@ -264,3 +270,324 @@ def k_embed_tokens(tok, emb, pos, x, rows, T, W):
 def k_gather_rows(src, idx, dst, B, T, W):
     S = src.reshape(-1)[:B * T * W].view(B, T, W)
     dst.view(-1)[:B * W] = S[torch.arange(B), idx.reshape(-1)[:B]].reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------ VQGAN decoder entry points
+def _nhwc(x, n, h, w, c):
+    return x.reshape(-1)[:n * h * w * c].view(n, h, w, c).float()
+
+
+def _conv3x3_packed(x, w, n, h, wd, cin, cout):
+    """x NHWC, w packed [cout][tap = ky*3+kx][cin] (include/ffvc.h: 'tap-major') -> [n*h*wd, cout] fp32"""
+    W4 = w.reshape(-1)[:cout * 9 * cin].view(cout, 3, 3, cin).float().permute(0, 3, 1, 2)
+    y = F.conv2d(_nhwc(x, n, h, wd, cin).permute(0, 3, 1, 2), W4, padding=1)
+    return y.permute(0, 2, 3, 1).reshape(n * h * wd, cout)
+
+
+def _epilogue(v, out, ldc, bias, res, aux, mul_mode, act):
+    M, N = v.shape
+    if bias is not None:
+        v = v + bias.float()[None, :N]
+    v = _ACT[act](v)
+    if mul_mode:
+        v = v * _DACT[mul_mode](_mat(aux, 0, M, N, ldc, 1).float())
+    if res is not None:
+        v = v + _mat(res, 0, M, N, ldc, 1).float()
+    _mat(out, 0, M, N, ldc, 1).copy_(v)
+
+
+def k_conv3x3_halo(x, w, out, n, h, wd, cin, cout, ldc, bias, res, aux, mul_mode, act, out_fp32):
+    assert wd % 128 == 0 and h % 2 == 0 and cin % 64 == 0 and cout <= 128, "documented shape contract of ffvc_conv3x3_halo"
+    assert (out.dtype == F32) == bool(out_fp32)
+    _epilogue(_conv3x3_packed(x, w, n, h, wd, cin, cout), out, ldc, bias, res, aux, mul_mode, act)
+
+
+def _group_sums(a, b, n, hw, c, groups=32):
+    """per (image, group) sums of a and of a*b  ->  [n][groups][2] doubles"""
+    A = a.view(n, hw, groups, c // groups).double()
+    Bv = b.view(n, hw, groups, c // groups).double()
+    return torch.stack([A.sum((1, 3)), (A * Bv).sum((1, 3))], -1)
+
+
+def k_conv3x3_halo_gn(x, w, out, n, h, wd, cin, cout, ldc, bias, res, gn_ws):
+    assert cout == 128
+    k_conv3x3_halo(x, w, out, n, h, wd, cin, cout, ldc, bias, res, None, 0, 0, 0)
+    o = _mat(out, 0, n * h * wd, cout, ldc, 1).float()            # statistics of the bf16-rounded output
+    gn_ws.view(-1)[:n * 64] = _group_sums(o, o, n, h * wd, cout).reshape(-1)
+
+
+def k_groupnorm_finalize(ws, mean, rstd, N, HW, C, G, eps):
+    s = ws.reshape(-1)[:N * G * 2].view(N, G, 2)
+    cnt = HW * (C // G)
+    mu = s[..., 0] / cnt
+    var = (s[..., 1] / cnt - mu * mu).clamp_min(0)
+    mean.view(-1)[:N * G] = mu.reshape(-1).float()
+    rstd.view(-1)[:N * G] = (var + eps).rsqrt().reshape(-1).float()
+
+
+def k_groupnorm_stats(x, ws, mean, rstd, N, HW, C, G, eps):
+    xf = x.reshape(-1)[:N * HW * C].view(N, HW, G, C // G).double()
+    mu = xf.mean((1, 3))
+    var = xf.var((1, 3), unbiased=False)
+    mean.view(-1)[:N * G] = mu.reshape(-1).float()
+    rstd.view(-1)[:N * G] = (var + eps).rsqrt().reshape(-1).float()
+
+
+def _gn_parts(x, mean, rstd, gamma, beta, N, HW, C, G):
+    xf = x.reshape(-1)[:N * HW * C].view(N, HW, G, C // G).float()
+    xh = (xf - mean.view(-1)[:N * G].view(N, 1, G, 1)) * rstd.view(-1)[:N * G].view(N, 1, G, 1)
+    u = xh * gamma.view(-1)[:C].view(1, 1, G, C // G) + beta.view(-1)[:C].view(1, 1, G, C // G)
+    return xh, u
+
+
+def k_groupnorm_apply(x, mean, rstd, gamma, beta, y, N, HW, C, G, swish):
+    _, u = _gn_parts(x, mean, rstd, gamma, beta, N, HW, C, G)
+    y.view(-1)[:N * HW * C] = (u * torch.sigmoid(u) if swish else u).reshape(-1)
+
+
+def _gn_g(dy, x, mean, rstd, gamma, beta, N, HW, C, G, swish):
+    """g = dy * swish'(gamma * xhat + beta) * gamma  (gradient w.r.t. xhat), and xhat"""
+    xh, u = _gn_parts(x, mean, rstd, gamma, beta, N, HW, C, G)
+    d = dy.reshape(-1)[:N * HW * C].view(N, HW, G, C // G).float()
+    if swish:
+        d = d * _dsig_mul(u, 1.0)
+    return d * gamma.view(-1)[:C].view(1, 1, G, C // G), xh
+
+
+def _gn_dx(g, xh, s0, s1, rstd, add, dx, N, HW, C, G):
+    cnt = HW * (C // G)
+    r = rstd.view(-1)[:N * G].view(N, 1, G, 1)
+    d = r * (g - (s0 / cnt).view(N, 1, G, 1).float() - xh * (s1 / cnt).view(N, 1, G, 1).float())
+    if add is not None:
+        d = d + add.reshape(-1)[:N * HW * C].view(N, HW, G, C // G).float()
+    dx.view(-1)[:N * HW * C] = d.reshape(-1)
+
+
+def k_groupnorm_bwd(dy, x, mean, rstd, gamma, beta, ws, add, dx, N, HW, C, G, swish):
+    g, xh = _gn_g(dy, x, mean, rstd, gamma, beta, N, HW, C, G, swish)
+    _gn_dx(g, xh, g.double().sum((1, 3)), (g * xh).double().sum((1, 3)), rstd, add, dx, N, HW, C, G)
+
+
+def k_conv3x3_halo_gnbwd(x, w, out, n, h, wd, cin, cout, ldc, res, gn_x, gn_mean, gn_rstd, gn_gamma, gn_beta, gn_ws):
+    assert cout == 128
+    k_conv3x3_halo(x, w, out, n, h, wd, cin, cout, ldc, None, res, None, 0, 0, 0)
+    g, xh = _gn_g(_mat(out, 0, n * h * wd, cout, ldc, 1).contiguous(), gn_x, gn_mean, gn_rstd, gn_gamma, gn_beta, n, h * wd, cout, 32, 1)
+    gn_ws.view(-1)[:n * 64] = torch.stack([g.double().sum((1, 3)), (g * xh).double().sum((1, 3))], -1).reshape(-1)
+
+
+def k_groupnorm_bwd_apply(dy, x, mean, rstd, gamma, beta, sums, add, dx, N, HW, C, G, swish):
+    g, xh = _gn_g(dy, x, mean, rstd, gamma, beta, N, HW, C, G, swish)
+    s = sums.reshape(-1)[:N * G * 2].view(N, G, 2)
+    _gn_dx(g, xh, s[..., 0], s[..., 1], rstd, add, dx, N, HW, C, G)
+
+
+def k_upsample2x_fwd(x, y, N, H, W, C):
+    X = _nhwc(x, N, H, W, C)
+    y.view(-1)[:N * 4 * H * W * C] = X.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(-1)
+
+
+def k_upsample2x_bwd(dy, dx, N, H, W, C):
+    D = dy.reshape(-1)[:N * 4 * H * W * C].view(N, H, 2, W, 2, C).float()
+    dx.view(-1)[:N * H * W * C] = D.sum((2, 4)).reshape(-1)
+
+
+def k_image_post_fwd(d, xr, n):
+    xr.view(-1)[:n] = ((d.reshape(-1)[:n] + 1) / 2).clamp(0, 1)
+
+
+def k_clamp_bwd(g, x, gx, n, lo, hi):
+    """ClampWithGrad.backward (main.py:126-129): g * (g * (x - clamp(x)) >= 0)"""
+    gg, xx = g.reshape(-1)[:n], x.reshape(-1)[:n]
+    gx.view(-1)[:n] = gg * ((gg * (xx - xx.clamp(lo, hi))) >= 0).float()
+
+
+def k_image_post_bwd(g, d, gd, n):
+    t = (d.reshape(-1)[:n] + 1) / 2
+    gg = g.reshape(-1)[:n]
+    gd.view(-1)[:n] = 0.5 * gg * ((gg * (t - t.clamp(0, 1))) >= 0).float()
+
+
+def k_im2col3x3_cin3(x, col, N, H, W):
+    X = F.pad(_nhwc(x, N, H, W, 3), (0, 0, 1, 1, 1, 1))
+    taps = [X[:, ky:ky + H, kx:kx + W, :] for ky in range(3) for kx in range(3)]           # col[p][tap*3 + c]
+    c = torch.zeros(N, H, W, 32)
+    c[..., :27] = torch.stack(taps, 3).reshape(N, H, W, 27)
+    col.view(-1)[:N * H * W * 32] = c.reshape(-1)
+
+
+def k_rownorm2(x, out, rows, C):
+    out.view(-1)[:rows] = (x.reshape(-1)[:rows * C].view(rows, C).float() ** 2).sum(1)
+
+
+def k_vq_nearest(z, codebook, codeT, cnorm, idx, zq_bf16, zq_f32, zc, P, C, ncodes, lo, hi):
+    zz = z.reshape(-1)[:P * C].view(P, C).clamp(lo, hi)
+    cb = codebook.reshape(-1)[:ncodes * C].view(ncodes, C)
+    d = (zz.double() ** 2).sum(1, keepdim=True) + (cb.double() ** 2).sum(1)[None] - 2 * zz.double() @ cb.double().t()
+    i = d.argmin(1)
+    idx.view(-1)[:P] = i.to(idx.dtype)
+    if zq_bf16 is not None:
+        zq_bf16.view(-1)[:P * C] = cb[i].reshape(-1)
+    if zq_f32 is not None:
+        zq_f32.view(-1)[:P * C] = cb[i].reshape(-1)
+    if zc is not None:
+        zc.view(-1)[:P * C] = zz.reshape(-1)
+
+
+def k_vq_prepare_codebook(codebook, csplit, cnorm, ncodes, C):
+    cb = codebook.reshape(-1)[:ncodes * C].view(ncodes, C)
+    hi_ = cb.to(BF16)
+    csplit.view(ncodes, 3 * C).copy_(torch.cat([hi_, (cb - hi_.float()).to(BF16), hi_], 1))
+    cnorm.view(-1)[:ncodes] = (cb ** 2).sum(1)
+
+
+def k_vq_nearest_tc(z, codebook, csplit, cnorm, zsplit, keys, idx, zq_bf16, zq_f32, zc, P, C, ncodes, lo, hi):
+    k_vq_nearest(z, codebook, None, cnorm, idx, zq_bf16, zq_f32, zc, P, C, ncodes, lo, hi)
+
+
+# ------------------------------------------------------------------------------------------------ cutouts, losses, optimizer
+# MakeCutouts (main.py:212-229): the stage arithmetic is the restatement the oracle uses (oracle/cutouts.py: warp convention,
+# HSV jitter); what the tests exercise here is the ENGINE's staging — image layout, per-cutout parameter routing, the
+# cutout-major order k*B + j, the patch-major output — and its backward chain, obtained from autograd of each stage.
+import ctypes as _C
+
+import oracle.cutouts as _oc
+
+
+def _host3(addr):
+    return torch.tensor(list((_C.c_float * 3).from_address(addr)))
+
+
+def _pool(x_nchw, P):
+    return (F.adaptive_avg_pool2d(x_nchw, P) + F.adaptive_max_pool2d(x_nchw, P)) / 2
+
+
+def k_cutout_pool_fwd(x, y, B, H, W, P):
+    y.view(-1)[:B * P * P * 3] = _pool(_nhwc(x, B, H, W, 3).permute(0, 3, 1, 2), P).permute(0, 2, 3, 1).reshape(-1)
+
+
+def k_cutout_pool_bwd(x, dy, dx, B, H, W, P):
+    with torch.enable_grad():
+        xi = _nhwc(x, B, H, W, 3).permute(0, 3, 1, 2).clone().requires_grad_(True)
+        g, = torch.autograd.grad(_pool(xi, P), xi, _nhwc(dy, B, P, P, 3).permute(0, 3, 1, 2))
+    dx.view(-1)[:B * H * W * 3] = g.permute(0, 2, 3, 1).reshape(-1)
+
+
+def _warp_stage(src_nchw, hinv, N, n_src, border):
+    return _oc.warp(src_nchw.repeat(N // n_src, 1, 1, 1), hinv.reshape(-1)[:N * 9].view(N, 3, 3), "border" if border else "zeros")
+
+
+def k_cutout_warp_fwd(inp, hinv, out, N, n_src, P, border):
+    o = _warp_stage(_nhwc(inp, n_src, P, P, 3).permute(0, 3, 1, 2), hinv, N, n_src, border)
+    out.view(-1)[:N * P * P * 3] = o.permute(0, 2, 3, 1).reshape(-1)
+
+
+def k_cutout_warp_bwd(dout, hinv, din, N, n_src, P, border):
+    with torch.enable_grad():
+        xi = torch.zeros(n_src, 3, P, P, requires_grad=True)
+        g, = torch.autograd.grad(_warp_stage(xi, hinv, N, n_src, border), xi, _nhwc(dout, N, P, P, 3).permute(0, 3, 1, 2))
+    din.view(-1)[:n_src * P * P * 3] = g.permute(0, 2, 3, 1).reshape(-1)
+
+
+def _final_stage(c_nchw, hinv, sat, hue, erase, N, P):
+    b = _oc.warp(c_nchw, hinv.reshape(-1)[:N * 9].view(N, 3, 3), "zeros")
+    b = _oc.color_jitter(b, sat.reshape(-1)[:N], hue.reshape(-1)[:N])
+    x0, y0, x1, y1 = [int(v) for v in erase.reshape(-1)[:4]]
+    if x1 > x0 and y1 > y0:
+        mask = torch.ones_like(b)
+        mask[:, :, y0:y1, x0:x1] = 0
+        b = b * mask
+    return b
+
+
+def _to_patches(img_nchw, N, P, patch):
+    g = P // patch
+    return img_nchw.reshape(N, 3, g, patch, g, patch).permute(0, 2, 4, 1, 3, 5).reshape(N, g * g, 3 * patch * patch)
+
+
+def k_cutout_final_fwd(cut1, hinv, sat, hue, noise, facs, erase, mean, std, patches, img_out, N, P, patch):
+    b = _final_stage(_nhwc(cut1, N, P, P, 3).permute(0, 3, 1, 2), hinv, sat, hue, erase, N, P)
+    b = b + facs.reshape(-1)[:N].view(N, 1, 1, 1) * noise.reshape(-1)[:N * 3 * P * P].view(N, 3, P, P)       # main.py:223-225
+    b = (b - _host3(mean).view(1, 3, 1, 1)) / _host3(std).view(1, 3, 1, 1)                                   # main.py:797
+    patches.view(-1)[:N * 3 * P * P] = _to_patches(b, N, P, patch).reshape(-1)
+    if img_out is not None:
+        img_out.view(-1)[:N * 3 * P * P] = b.reshape(-1)
+
+
+def k_cutout_final_bwd(cut1, hinv, sat, hue, erase, mean, std, dpatches, dcut1, N, P, patch):
+    g = P // patch
+    dp = dpatches.reshape(-1)[:N * 3 * P * P].view(N, g, g, 3, patch, patch).float().permute(0, 3, 1, 4, 2, 5).reshape(N, 3, P, P)
+    dp = dp / _host3(std).view(1, 3, 1, 1)
+    with torch.enable_grad():
+        ci = _nhwc(cut1, N, P, P, 3).permute(0, 3, 1, 2).clone().requires_grad_(True)
+        gr, = torch.autograd.grad(_final_stage(ci, hinv, sat, hue, erase, N, P), ci, dp)
+    dcut1.view(-1)[:N * P * P * 3] = gr.permute(0, 2, 3, 1).reshape(-1)
+
+
+def k_spherical_loss(embed, target, loss_out, dembed, dembed_bf16, N, B, D, coef):
+    """main.py:801-811: mean(2 * asin(|normalize(H) - normalize(e)| / 2)^2) * coef with H = out_feats.repeat(cutn, 1)"""
+    with torch.enable_grad():
+        e = embed.reshape(-1)[:N * D].view(N, D).clone().requires_grad_(True)
+        Hh = F.normalize(target.reshape(-1)[:B * D].view(B, D).repeat(N // B, 1), dim=-1)
+        loss = ((F.normalize(e, dim=-1) - Hh).norm(dim=-1).div(2).arcsin().pow(2).mul(2)).mean() * coef
+        g, = torch.autograd.grad(loss, e)
+    loss_out.view(-1)[0] = loss.detach()
+    if dembed is not None:
+        dembed.view(-1)[:N * D] = g.reshape(-1)
+    if dembed_bf16 is not None:
+        dembed_bf16.view(-1)[:N * D] = g.reshape(-1)
+
+
+def k_tv_loss(img, loss_accum, dimg_accum, B, H, W, C, coef):
+    """main.py:423-428 on NHWC; ACCUMULATES into loss_accum / dimg_accum"""
+    with torch.enable_grad():
+        x = _nhwc(img, B, H, W, C).permute(0, 3, 1, 2).clone().requires_grad_(True)
+        tv = 0.5 * ((x[:, :, 1:, :] - x[:, :, :-1, :]).abs().mean() + (x[:, :, :, 1:] - x[:, :, :, :-1]).abs().mean()) * coef
+        g, = torch.autograd.grad(tv, x)
+    loss_accum.view(-1)[0] += tv.detach()
+    dimg_accum.view(-1)[:B * H * W * C] += g.permute(0, 2, 3, 1).reshape(-1)
+
+
+def k_sumsq(x, out, n):
+    out.view(-1)[0] = (x.reshape(-1)[:n].double() ** 2).sum().float()
+
+
+def k_axpy_f32(x, y, a, n):
+    y.view(-1)[:n] += a * x.reshape(-1)[:n]
+
+
+def k_adam_tick(h):
+    """include/ffvc.h: the 16-float scalar block; cosine lr of update t uses scheduler epoch t - 1 (main.py:835-837)"""
+    import math
+    t = float(h[8]) + 1.0
+    h[8] = t
+    h[4] = 1.0 - float(h[1]) ** t
+    h[5] = math.sqrt(1.0 - float(h[2]) ** t)
+    if float(h[13]) > 0:
+        h[0] = float(h[14]) + (float(h[12]) - float(h[14])) * 0.5 * (1.0 + math.cos(math.pi * (t - 1.0) / float(h[13])))
+    if float(h[9]) > 0:
+        h[11] = min(1.0, float(h[9]) / (math.sqrt(float(h[10])) * float(h[6]) + 1e-6))
+
+
+def _adam(p, g, m, v, shadow, ema, n, h):
+    gs = float(h[6]) * (float(h[11]) if float(h[9]) > 0 else 1.0)
+    gv = g.reshape(-1)[:n] * gs
+    if float(h[7]) != 0:
+        gv = gv + float(h[7]) * p.view(-1)[:n]
+    b1, b2 = float(h[1]), float(h[2])
+    m.view(-1)[:n] = b1 * m.view(-1)[:n] + (1 - b1) * gv
+    v.view(-1)[:n] = b2 * v.view(-1)[:n] + (1 - b2) * gv * gv
+    p.view(-1)[:n] -= (float(h[0]) / float(h[4])) * m.view(-1)[:n] / (v.view(-1)[:n].sqrt() / float(h[5]) + float(h[3]))
+    if shadow is not None:
+        shadow.view(-1)[:n] = p.view(-1)[:n]
+    if ema is not None:                                   # torch_ema: decay = min(decay, (1 + t) / (10 + t))
+        t = float(h[8])
+        omd = 1.0 - min(float(h[15]), (1.0 + t) / (10.0 + t))
+        ema.view(-1)[:n] -= omd * (ema.view(-1)[:n] - p.view(-1)[:n])
+
+
+def k_adam_step(p, g, m, v, shadow, n, h):
+    _adam(p, g, m, v, shadow, None, n, h)
+
+
+def k_adam_step_ema(p, g, m, v, shadow, ema, n, h):
+    _adam(p, g, m, v, shadow, ema, n, h)

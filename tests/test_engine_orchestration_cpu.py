@@ -127,3 +127,109 @@ def test_clip_text_encoder_orchestration(abi_on_cpu):
     yr = otext.encode_text(sd, text, 2)
     assert y.shape == yr.shape == (3, 32)
     assert float((y - yr).abs().max()) <= 3e-2 * float(yr.abs().max())
+
+
+MID_VQ = dict(ch=128, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(64,), resolution=128, z_channels=64, out_ch=3,
+              embed_dim=64, n_embed=512)      # 128 channels at 128 x 128: the halo-reuse conv entry points and their GroupNorm epilogues
+
+
+@pytest.mark.parametrize("epilogue_stats", [True, False])
+def test_decoder_engine_orchestration(abi_on_cpu, monkeypatch, epilogue_stats):
+    """DecoderEngine (VQModel.decode, main.py:142) forward + gradient w.r.t. z_q: implicit-GEMM convs, the halo-reuse conv
+    entry points with GroupNorm statistics handed from the conv epilogues to the Normalize that follows (forward) / precedes
+    (backward), or the separate statistics passes; attention block; upsample; conv_out and its im2col dgrad."""
+    import oracle.vqgan as ovq
+    from feed_forward_vqgan_clip_b200 import vqgan
+    monkeypatch.setattr(vqgan, "call", abi_model.call)
+    monkeypatch.setattr(vqgan.DecoderEngine, "GN_EPI_STATS", epilogue_stats)
+    monkeypatch.setattr(vqgan.DecoderEngine, "GN_EPI_BWD", epilogue_stats)
+    seen = []
+    monkeypatch.setattr(abi_model, "call", lambda name, *a: (seen.append(name), getattr(abi_model, "k_" + name)(*a))[1])
+    monkeypatch.setattr(vqgan, "call", abi_model.call)
+    sd = ovq.init_vqgan_state_dict(MID_VQ, seed=7)
+    vq = vqgan.VQModel(MID_VQ)
+    vq.load_state_dict(sd)
+    vq = vq.eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(8)
+    zq = torch.randn(1, 64, 64, 64, generator=g)
+    w = torch.randn(1, 3, 128, 128, generator=g)
+    zc, zr = zq.clone().requires_grad_(True), zq.clone().requires_grad_(True)
+    y = vq.decode(zc)
+    assert not vq.engine()._epi_stats, "every epilogue statistic must be consumed by the Normalize that follows its conv"
+    (y * w).sum().backward()
+    yr = ovq.decode(sd, zr, MID_VQ)
+    (yr * w).sum().backward()
+    assert float((y - yr).detach().abs().max()) <= 3e-2 * float(yr.detach().abs().max())
+    assert cos(zc.grad, zr.grad) > 0.99
+    assert ("conv3x3_halo_gn" in seen) == epilogue_stats and ("conv3x3_halo_gnbwd" in seen) == epilogue_stats
+    assert "conv3x3_halo" in seen and "groupnorm_bwd" in seen and "im2col3x3_cin3" in seen
+
+
+SMALL_VQ = dict(ch=64, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(16,), resolution=32, z_channels=64, out_ch=3,
+                embed_dim=64, n_embed=512)
+SMALL_CLIP = dict(input_resolution=64, patch_size=32, width=128, layers=2, heads=2, output_dim=64)
+
+
+@pytest.mark.parametrize("mapper,extras", [("mixer", {}), ("vitgan", dict(l2_coef=0.1, tv_coef=0.5)),
+                                           ("mixer", dict(clip_grad_norm=0.5, scheduler="cosine", total_steps=10, use_ema=True))])
+def test_train_step_orchestration_vs_oracle_step(abi_on_cpu, monkeypatch, mapper, extras):
+    """The whole step of main.py:729-837 — mapper -> clamp -> VQ -> decode -> cutouts -> CLIP -> loss (+ l2 / tv) -> backward
+    -> optimizer block — through TrainStep's host logic, against oracle/train_step.py on the same weights, inputs and
+    augmentation parameters: loss, code indices, every parameter gradient, and the Adam update."""
+    import oracle.vqgan as ovq
+    from oracle.train_step import OracleTrainer
+    from feed_forward_vqgan_clip_b200 import cutouts, train_step, vqgan
+    for mod in (vqgan, cutouts, train_step):
+        monkeypatch.setattr(mod, "call", abi_model.call)
+    torch.manual_seed(7)
+    if mapper == "mixer":
+        net = mixer.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=1)
+        with torch.no_grad():
+            net.final_proj.weight.mul_(6.0)                # spread z over the codebook range so VQ picks varied codes
+    else:
+        net = vitgan_mapper.Generator(initialize_size=2, dim=48, blocks=1, num_heads=3, out_channels=64, input_dim=64)
+        with torch.no_grad():
+            net.w_out[0].weight.mul_(4.0)
+    sd_m = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd_v = ovq.init_vqgan_state_dict(SMALL_VQ, seed=8)
+    sd_c = oclip.init_clip_state_dict(SMALL_CLIP, seed=9)
+    vq = vqgan.VQModel(SMALL_VQ)
+    vq.load_state_dict(sd_v)
+    clip = clip_vit.CLIP(SMALL_CLIP)
+    clip.visual.load_state_dict(sd_c)
+    B, cutn, cut, lr = 2, 3, 64, 1e-3
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(B, 64, generator=g) * 0.45
+    prm = cutouts.sample_params(cutn * B, cut, g)
+    ts = train_step.TrainStep(net, vq.eval().requires_grad_(False), clip.eval().requires_grad_(False), cutn=cutn, lr=lr,
+                              cut_size=cut, **extras)
+    loss = float(ts.step(x, None, prm))
+    okw = {k: v for k, v in extras.items() if k in ("l2_coef", "tv_coef")}
+    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 64, SMALL_VQ, SMALL_CLIP, cutn=cutn, cut_size=cut, lr=lr, mapper=mapper, num_heads=3,
+                        **okw)
+    ref_loss = otr.step(x, x, prm)
+    dists, l2, tv = otr.last_terms
+    assert (ts.last_indices.long().view(-1) == otr.last_indices.view(-1)).float().mean() > 0.97      # bf16 near-ties may flip
+    assert abs(loss - dists) < 3e-2 * abs(dists)                                    # TrainStep.loss is the spherical term
+    if okw:
+        aux = ts.aux_loss.tolist()
+        assert abs(aux[0] - 0.1 * l2) < 3e-2 * abs(0.1 * l2) and abs(aux[1] - 0.5 * tv) < 3e-2 * abs(0.5 * tv)
+    # gradients on the codes the step under test picked (the arg-min is discontinuous)
+    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 64, SMALL_VQ, SMALL_CLIP, cutn=cutn, cut_size=cut, lr=lr, mapper=mapper, num_heads=3,
+                        **okw)
+    otr.step(x, x, prm, force_idx=ts.last_indices.long())
+    eng = net.engine()
+    big = [(n, gv) for (n, p), gv in zip(net.named_parameters(), eng.grad_views) if p.numel() >= 2048]
+    assert big and min(cos(gv, otr.grads[n]) for n, gv in big) > 0.97
+    if not set(extras) & {"clip_grad_norm", "scheduler"}:
+        for n, p in net.named_parameters():                # plain Adam: the first update is -lr * sign(grad)
+            if p.numel() >= 2048:
+                assert cos(p.detach() - sd_m[n], otr.params[n].detach() - sd_m[n]) > 0.8, n
+    else:
+        # optimizer block: clip coefficient from the global gradient norm, cosine lr at scheduler epoch 0, EMA after one update
+        gn = float(eng.grad.double().norm())
+        h = ts.opt.hyper
+        assert abs(float(h[11]) - min(1.0, 0.5 / (gn + 1e-6))) < 1e-4 and abs(float(h[0]) - lr) < 1e-9 and float(h[8]) == 1.0
+        decay = min(0.995, 2.0 / 11.0)                     # torch_ema warm-up after the first update
+        n0, p0 = next(iter(net.named_parameters()))
+        assert torch.allclose(ts.opt.ema_state_dict()[n0], sd_m[n0] - (1 - decay) * (sd_m[n0] - p0.detach()), atol=1e-6)
