@@ -233,3 +233,69 @@ def test_train_step_orchestration_vs_oracle_step(abi_on_cpu, monkeypatch, mapper
         decay = min(0.995, 2.0 / 11.0)                     # torch_ema warm-up after the first update
         n0, p0 = next(iter(net.named_parameters()))
         assert torch.allclose(ts.opt.ema_state_dict()[n0], sd_m[n0] - (1 - decay) * (sd_m[n0] - p0.detach()), atol=1e-6)
+
+
+def test_reference_call_surface_glue_vs_reference_golden(abi_on_cpu, monkeypatch):
+    """api.clamp_with_grad / vector_quantize / synth / MakeCutouts / generate — the names train() calls — as
+    torch.autograd.Functions over the engines: clamp truth table and straight-through VQ gradient against the values the
+    reference's own main.py produced (tests/golden/glue.pt), synth / MakeCutouts / generate against the oracle."""
+    import os
+    import oracle.cutouts as ocut
+    import oracle.vqgan as ovq
+    from feed_forward_vqgan_clip_b200 import api, cutouts, vqgan
+    for mod in (vqgan, cutouts):
+        monkeypatch.setattr(mod, "call", abi_model.call)
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "glue.pt"))
+    c = gold["clamp"]
+    x = c["x"].clone().requires_grad_(True)
+    api.clamp_with_grad(x, 0, 1).backward(c["g"])                       # main.py:118-132
+    assert torch.equal(x.grad, c["gx"])
+    v = gold["vq"]
+    cfg = dict(SMALL_VQ, embed_dim=v["cb"].shape[1], n_embed=v["cb"].shape[0], z_channels=v["cb"].shape[1])
+    vq = vqgan.VQModel(cfg).eval().requires_grad_(False)
+    with torch.no_grad():
+        vq.quantize.embedding.weight.copy_(v["cb"])
+    z = v["z"].clone().requires_grad_(True)
+    zq = api.vector_quantize(z, vq)                                     # main.py:134-138
+    assert torch.allclose(zq, v["zq"])
+    (zq * v["w"]).sum().backward()
+    assert torch.allclose(z.grad, v["dz"])                              # ReplaceGrad: straight-through
+    # synth (main.py:140-143) on a real (small) decoder against the oracle, forward and gradient
+    sd_v = ovq.init_vqgan_state_dict(SMALL_VQ, seed=4)
+    vq = vqgan.VQModel(SMALL_VQ)
+    vq.load_state_dict(sd_v)
+    vq = vq.eval().requires_grad_(False)
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(2, 64, 16, 16, generator=g) * 1.2
+    za, zb = z.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    xa = api.synth(vq, za)
+    xb = ovq.synth(sd_v, zb, SMALL_VQ)
+    assert xa.shape == xb.shape == (2, 3, 32, 32) and float((xa - xb).detach().abs().max()) <= 3e-2
+    w = torch.randn(2, 3, 32, 32, generator=g)
+    (xa * w).sum().backward()
+    (xb * w).sum().backward()
+    assert cos(za.grad, zb.grad) > 0.99
+    # MakeCutouts module (main.py:154-229): (B,3,H,W) in [0,1] -> (cutn*B,3,cut,cut), cutout-major, differentiable
+    mc = api.MakeCutouts(64, 3)
+    prm = cutouts.sample_params(6, 64, g)
+    img = torch.rand(2, 3, 32, 32, generator=g)
+    ia, ib = img.clone().requires_grad_(True), img.clone().requires_grad_(True)
+    mc.next_params = prm
+    ca = mc(ia)
+    cb = ocut.make_cutouts(ib, 3, prm, 64, normalize=False)
+    assert ca.shape == cb.shape == (6, 3, 64, 64) and float((ca - cb).detach().abs().max()) <= 2e-2   # patches pass through bf16
+    wc = torch.randn(6, 3, 64, 64, generator=g)
+    (ca * wc).sum().backward()
+    (cb * wc).sum().backward()
+    assert cos(ia.grad, ib.grad) > 0.99
+    # generate (test / predict, main.py:1056-1059): mapper -> clamp to the codebook range -> VQ -> decode, forward only
+    net = mixer.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=1)
+    with torch.no_grad():
+        net.final_proj.weight.mul_(6.0)
+    sd_m = {k: p.detach().clone() for k, p in net.state_dict().items()}
+    inp = torch.randn(2, 64, generator=g) * 0.45
+    out, idx = api.generate(net, vq, inp, return_indices=True)
+    cbk = sd_v["quantize.embedding.weight"]
+    zr = ovq.clamp_with_grad(omix.mixer_forward(sd_m, inp, 16, 64), float(cbk.min()), float(cbk.max()))
+    ref, ridx = ovq.synth(sd_v, zr, SMALL_VQ, return_indices=True, force_idx=idx.long())
+    assert out.shape == ref.shape == (2, 3, 32, 32) and float((out - ref).abs().max()) <= 3e-2
