@@ -591,3 +591,38 @@ def k_adam_step(p, g, m, v, shadow, n, h):
 
 def k_adam_step_ema(p, g, m, v, shadow, ema, n, h):
     _adam(p, g, m, v, shadow, ema, n, h)
+
+
+# ------------------------------------------------------------------------------------------------ LPIPS-VGG16 diversity term
+def k_normalize3_fwd(x, y, n, mean, std):
+    y.view(-1)[:n] = ((x.reshape(-1)[:n].view(-1, 3) - _host3(mean)) / _host3(std)).reshape(-1)
+
+
+def k_normalize3_bwd(dy, dx_accum, n, std):
+    dx_accum.view(-1)[:n] += (dy.reshape(-1)[:n].view(-1, 3) / _host3(std)).reshape(-1)
+
+
+def k_maxpool2x2_fwd(x, y, N, H, W, C):
+    y.view(-1)[:N * (H // 2) * (W // 2) * C] = F.max_pool2d(_nhwc(x, N, H, W, C).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1)
+
+
+def k_maxpool2x2_bwd(x, dy, dx, N, H, W, C):
+    with torch.enable_grad():
+        xi = _nhwc(x, N, H, W, C).permute(0, 3, 1, 2).clone().requires_grad_(True)
+        g, = torch.autograd.grad(F.max_pool2d(xi, 2, 2), xi, _nhwc(dy, N, H // 2, W // 2, C).permute(0, 3, 1, 2))
+    dx.view(-1)[:N * H * W * C] = g.permute(0, 2, 3, 1).reshape(-1)
+
+
+def k_relu_mask(g, post, out, n):
+    out.view(-1)[:n] = g.reshape(-1)[:n].float() * (post.reshape(-1)[:n].float() > 0)
+
+
+def k_diversity_tap(feats, loss_accum, dfeat, R, B, HW, C, scale):
+    """one VGG tap of main.py:778-782: normalize_tensor over channels, squared differences between the R samples of each prompt"""
+    with torch.enable_grad():
+        f = feats.reshape(-1)[:R * B * HW * C].view(R, B, HW, C).float().clone().requires_grad_(True)
+        fn = f / (f.pow(2).sum(-1, keepdim=True).sqrt() + 1e-10)
+        div = ((fn.view(R, 1, B, HW, C) - fn.view(1, R, B, HW, C)) ** 2).sum(-1).mean() * scale
+        g, = torch.autograd.grad(div, f)
+    loss_accum.view(-1)[0] += div.detach()
+    dfeat.view(-1)[:R * B * HW * C] = g.reshape(-1)

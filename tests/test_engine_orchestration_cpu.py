@@ -299,3 +299,28 @@ def test_reference_call_surface_glue_vs_reference_golden(abi_on_cpu, monkeypatch
     zr = ovq.clamp_with_grad(omix.mixer_forward(sd_m, inp, 16, 64), float(cbk.min()), float(cbk.max()))
     ref, ridx = ovq.synth(sd_v, zr, SMALL_VQ, return_indices=True, force_idx=idx.long())
     assert out.shape == ref.shape == (2, 3, 32, 32) and float((out - ref).abs().max()) <= 3e-2
+
+
+def test_lpips_diversity_engine_orchestration(abi_on_cpu, monkeypatch):
+    """DiversityEngine (main.py:776-782,831): VGG16 slices (im2col first layer, halo and implicit-GEMM convs with ReLU epilogues),
+    the five taps, and the dgrad chain back to the image with ReLU masks, max-pool routing and the 1/std of the normalisation"""
+    import oracle.lpips as ol
+    from feed_forward_vqgan_clip_b200 import lpips
+    from feed_forward_vqgan_clip_b200.cutouts import CLIP_MEAN, CLIP_STD
+    monkeypatch.setattr(lpips, "call", abi_model.call)
+    sd = ol.init_vgg_state_dict(seed=3)
+    net = lpips.LpipsVGG16()
+    net.load_state_dict(sd)
+    eng = net.engine()
+    R, bs, H = 2, 1, 128                      # 128 wide: slice 1 takes the halo conv entry point, the deeper slices the implicit GEMM
+    g = torch.Generator().manual_seed(4)
+    xr = torch.rand(R * bs, 3, H, H, generator=g)
+    mean, std = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1), torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+    xo = xr.clone().requires_grad_(True)
+    div = ol.diversity(sd, xo, R, bs, mean, std)
+    (-0.7 * div).backward()
+    img = xr.permute(0, 2, 3, 1).contiguous()
+    dimg, loss = torch.zeros_like(img), torch.zeros(1)
+    eng.forward_backward(img, R, bs, 0.7, dimg, loss)
+    assert abs(float(loss) - (-0.7 * float(div.detach()))) < 3e-2 * abs(0.7 * float(div.detach()))
+    assert cos(dimg, xo.grad.permute(0, 2, 3, 1)) > 0.98
