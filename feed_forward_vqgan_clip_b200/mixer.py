@@ -223,6 +223,19 @@ class MixerEngine:
         """arena offset of the first parameter of every mixer layer (mixer.2 .. mixer.L+1), ascending"""
         return [min(off for n, off in self.offs.items() if n.startswith("mixer.%d." % i)) for i in range(2, self.L + 2)]
 
+    def late_ranges(self):
+        """arena ranges whose gradient is complete only when backward has ended although they are registered after the layers:
+        the input projection `proj` (its wgrad / bias sum are the last launches of backward) — see parallel.bucket_slices"""
+        out = []
+        for n in ("proj.weight", "proj.bias"):
+            lo = self.offs[n]
+            hi = lo + (self.shapes[n].numel() + 7) // 8 * 8          # slots are padded to 8 elements in the arenas
+            if out and out[-1][1] == lo:
+                out[-1] = (out[-1][0], hi)
+            else:
+                out.append((lo, hi))
+        return out
+
     def backward(self, sv, dz, on_layer_done=None):
         """dz: (B*T, C) fp32.  Accumulates every parameter gradient into the flat fp32 arena `self.grad`.
         on_layer_done(k): called right after the gradients of mixer layer k (0-based, last layer first) — and of everything

@@ -58,8 +58,9 @@ def bucket_ranges(layer_starts, total, layers_per_bucket):
     """Contiguous [lo, hi) slices of the flat gradient arena in the order backward completes them.
     layer_starts: arena offset of the first parameter of every mixer layer, ascending (layer 0 first); backward finishes
     the layers last-to-first, so bucket k covers layers [L - (k+1)*n, L - k*n) plus, for k = 0, everything registered
-    after the last layer (final norm, output projection); the head of the arena (input projections, finished last) is the
-    final slice.  The slices tile [0, total) exactly once."""
+    after the last layer (final norm, output projection); the head of the arena (everything registered before the first layer,
+    finished last) is the final slice.  The slices tile [0, total) exactly once.  Parameters that are registered after the
+    layers but whose gradient is only complete at the very end of backward must be carved out: see bucket_slices."""
     L = len(layer_starts)
     out, hi, i = [], total, L
     while i > 0:
@@ -69,6 +70,36 @@ def bucket_ranges(layer_starts, total, layers_per_bucket):
     if hi > 0:
         out.append((0, hi))
     return out
+
+
+def bucket_slices(layer_starts, total, layers_per_bucket, late=()):
+    """bucket_ranges with the `late` ranges carved out: a list of buckets, each a list of [lo, hi) slices.  Bucket k < last may be
+    all-reduced as soon as backward has finished layer L - (k+1)*n; the LAST bucket — the head of the arena plus every `late`
+    range — only after backward has ended.  `late`: arena ranges whose gradient is complete only then although they are
+    registered after the layers: the mixer's input projection `proj` sits between the final norm and `final_proj` in the
+    reference's registration order (mlp_mixer_pytorch.py:73-76) but its wgrad is the last GEMM of backward.  Reducing it with
+    the first bucket would sum zeros and leave every replica with its own local gradient.
+    The slices of all buckets together tile [0, total) exactly once."""
+    late = sorted((int(lo), int(hi)) for lo, hi in late if hi > lo)
+    ranges = bucket_ranges(layer_starts, total, layers_per_bucket)
+    head = []
+    if ranges and ranges[-1][0] == 0 and (not layer_starts or ranges[-1][1] <= layer_starts[0]):
+        head = [ranges.pop()]
+    buckets = []
+    for lo, hi in ranges:
+        pieces, cur = [], lo
+        for a, b in late:
+            a, b = max(a, lo), min(b, hi)
+            if b <= a:
+                continue
+            if a > cur:
+                pieces.append((cur, a))
+            cur = max(cur, b)
+        if hi > cur:
+            pieces.append((cur, hi))
+        buckets.append(pieces)
+    buckets.append(head + list(late))
+    return buckets
 
 
 def broadcast_flat(flat, src=0, group=None):

@@ -233,25 +233,29 @@ class TrainStep:
             call("axpy_f32", z, dz, 2.0 * self.l2_coef / z.numel(), z.numel())
         mix.zero_grad_arena()
         if self.world > 1 and self.bucket_layers > 0 and hasattr(mix, "layer_starts"):
-            from .parallel import bucket_ranges
-            ranges = bucket_ranges(mix.layer_starts(), mix.total, self.bucket_layers)
+            from .parallel import bucket_slices
+            # bucket k (k < last): the gradients of mixer layers [L - (k+1)*n, L - k*n) (+ the final norm / output projection for
+            # k = 0), complete once backward has finished the first of those layers; last bucket: whatever only completes when
+            # backward has ended — the head of the arena (mixer.1) and the input projection `proj`, which the reference registers
+            # AFTER the layers (mlp_mixer_pytorch.py:73-76) although its wgrad is the last GEMM of backward
+            buckets = bucket_slices(mix.layer_starts(), mix.total, self.bucket_layers, late=mix.late_ranges())
             main, comm = torch.cuda.current_stream(), self.comm_stream
-            first_layer_of_bucket = {mix.L - min(mix.L, (k + 1) * self.bucket_layers): k for k in range(len(ranges) - 1)}
+            first_layer_of_bucket = {mix.L - min(mix.L, (k + 1) * self.bucket_layers): k for k in range(len(buckets) - 1)}
 
-            def reduce_slice(lo, hi):
+            def reduce_bucket(slices):
                 ev = torch.cuda.Event()
-                ev.record(main)                       # gradients of [lo, hi) are complete at this point of the main stream
+                ev.record(main)                       # the gradients of these slices are complete at this point of the main stream
                 comm.wait_event(ev)
                 with torch.cuda.stream(comm):
-                    torch.distributed.all_reduce(mix.grad[lo:hi], group=self.pg)
+                    for lo, hi in slices:
+                        torch.distributed.all_reduce(mix.grad[lo:hi], group=self.pg)
 
             def on_layer_done(k):
                 if k in first_layer_of_bucket:
-                    reduce_slice(*ranges[first_layer_of_bucket[k]])
+                    reduce_bucket(buckets[first_layer_of_bucket[k]])
 
             mix.backward(sv_m, dz, on_layer_done=on_layer_done)
-            if ranges[-1][0] == 0 and len(ranges) > len(first_layer_of_bucket):
-                reduce_slice(*ranges[-1])             # head of the arena: input projections, finished last
+            reduce_bucket(buckets[-1])
             main.wait_stream(comm)
         else:
             mix.backward(sv_m, dz)

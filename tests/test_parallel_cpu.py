@@ -224,3 +224,22 @@ def test_sharded_step_reproduces_the_global_batch_step_oracle():
     for k in g_full:
         avg = sum(gr[k] for gr in grads) / world
         assert torch.allclose(avg, g_full[k], rtol=1e-3, atol=1e-6 * float(g_full[k].abs().max()) + 1e-9), k
+
+
+def test_bucket_slices_carve_out_late_ranges_and_still_tile_the_arena():
+    """parallel.bucket_slices: ranges whose gradient completes only at the end of backward (the mixer's input projection, which
+    the reference registers after the layers) leave the early buckets and join the head of the arena in the last one."""
+    starts, total = [100, 300, 500, 700, 900], 1500          # 5 layers of 200, head [0, 100), tail [1100, 1500)
+    late = [(1200, 1400)]
+    for n in (1, 2, 3, 8):
+        buckets = parallel.bucket_slices(starts, total, n, late=late)
+        assert len(buckets) == -(-5 // n) + 1
+        flat = sorted(s for b in buckets for s in b)
+        assert flat[0][0] == 0 and flat[-1][1] == total and all(a[1] == b[0] for a, b in zip(flat, flat[1:]))
+        assert buckets[-1] == [(0, 100), (1200, 1400)]
+        assert buckets[0][-2:] == [(starts[max(0, 5 - n)], 1200), (1400, 1500)] if n < 5 else True
+        assert all(not (lo < 1400 and 1200 < hi) for b in buckets[:-1] for lo, hi in b)
+    # without late ranges the slices are bucket_ranges' own
+    assert [s for b in parallel.bucket_slices(starts, total, 2) for s in b] == parallel.bucket_ranges(starts, total, 2)
+    # no head (first layer starts at 0): the last bucket holds the late ranges only
+    assert parallel.bucket_slices([0, 200], 500, 1, late=[(450, 500)])[-1] == [(450, 500)]
