@@ -39,19 +39,20 @@ class _NoEvent:
         pass
 
 
-def _patch():
+def _patch(setattr_=setattr):
+    """in the spawned workers the replacements are permanent; in the pytest process they go through monkeypatch.setattr"""
     import abi_model
     from feed_forward_vqgan_clip_b200 import clip_vit, cutouts, mixer, ops, train_step, vqgan
-    ops.gemm_raw = abi_model.gemm_raw
-    ops.gemm = lambda a, b, out, M, N, K, **kw: abi_model.gemm_raw(a, b, out, M, N, K, **kw)
-    ops.call = abi_model.call
-    ops.require_cuda = lambda dev, what: None
+    setattr_(ops, "gemm_raw", abi_model.gemm_raw)
+    setattr_(ops, "gemm", lambda a, b, out, M, N, K, **kw: abi_model.gemm_raw(a, b, out, M, N, K, **kw))
+    setattr_(ops, "call", abi_model.call)
+    setattr_(ops, "require_cuda", lambda dev, what: None)
     for mod in (mixer, vqgan, cutouts, train_step, clip_vit):
-        mod.call = abi_model.call
-    torch.cuda.Stream = lambda device=None: _NoStream()
-    torch.cuda.current_stream = lambda device=None: _NoStream()
-    torch.cuda.Event = lambda *a, **k: _NoEvent()
-    torch.cuda.stream = lambda s: contextlib.nullcontext()
+        setattr_(mod, "call", abi_model.call)
+    setattr_(torch.cuda, "Stream", lambda device=None: _NoStream())
+    setattr_(torch.cuda, "current_stream", lambda device=None: _NoStream())
+    setattr_(torch.cuda, "Event", lambda *a, **k: _NoEvent())
+    setattr_(torch.cuda, "stream", lambda s: contextlib.nullcontext())
 
 
 def _build(world, pg, bucket_layers):
@@ -127,15 +128,13 @@ def _cos(a, b):
     return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300))
 
 
-def test_two_rank_step_equals_the_global_batch_step():
-    import sys
-    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+def test_two_rank_step_equals_the_global_batch_step(monkeypatch):
     res = _run(bucket_layers=2)                              # 3 mixer layers in buckets of 2: [layers 1-2 + tail], [layer 0], [head]
     (_, loss0, g0, p0, calls0, total, idx0), (_, loss1, g1, p1, calls1, _, idx1) = res
     assert torch.equal(g0, g1) and torch.equal(p0, p1)       # both replicas hold the same reduced gradient and take the same step
     assert calls0 == calls1 and sum(calls0) == total         # the all-reduced slices tile the arena exactly once
     # single process, global batch
-    _patch()
+    _patch(monkeypatch.setattr)
     net, ts = _build(1, None, 0)
     keep = ts.mix.arena.clone()
     x, prm = _inputs()
