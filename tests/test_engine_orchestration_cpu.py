@@ -324,3 +324,55 @@ def test_lpips_diversity_engine_orchestration(abi_on_cpu, monkeypatch):
     eng.forward_backward(img, R, bs, 0.7, dimg, loss)
     assert abs(float(loss) - (-0.7 * float(div.detach()))) < 3e-2 * abs(0.7 * float(div.detach()))
     assert cos(dimg, xo.grad.permute(0, 2, 3, 1)) > 0.98
+
+
+@pytest.mark.parametrize("mode", ["between_same_prompts", "all"])
+def test_train_step_with_repeat_and_diversity_vs_reference_expression(abi_on_cpu, monkeypatch, mode):
+    """config #5's extras through TrainStep: the prompt batch repeated `repeat` times (main.py:739-740) and the LPIPS-VGG16
+    diversity term subtracted from the loss (main.py:776-791,831), in both modes, against the same expression built from the
+    oracle pieces.  Identical prompts share their latents, so the decoder here gets a per-sample perturbation through the
+    augmentations only — the diversity value is small but its routing (sample order r * bs + b) is what is checked."""
+    import oracle.cutouts as ocut
+    import oracle.loss as oloss
+    import oracle.lpips as ol
+    import oracle.vqgan as ovq
+    from feed_forward_vqgan_clip_b200 import cutouts, lpips, train_step, vqgan
+    from feed_forward_vqgan_clip_b200.cutouts import CLIP_MEAN, CLIP_STD
+    for mod in (vqgan, cutouts, train_step, lpips):
+        monkeypatch.setattr(mod, "call", abi_model.call)
+    torch.manual_seed(11)
+    net = mixer.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=1)
+    with torch.no_grad():
+        net.final_proj.weight.mul_(6.0)
+    sd_m = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sd_v, sd_c, sd_l = ovq.init_vqgan_state_dict(SMALL_VQ, seed=8), oclip.init_clip_state_dict(SMALL_CLIP, seed=9), ol.init_vgg_state_dict(seed=3)
+    vq = vqgan.VQModel(SMALL_VQ)
+    vq.load_state_dict(sd_v)
+    clip = clip_vit.CLIP(SMALL_CLIP)
+    clip.visual.load_state_dict(sd_c)
+    vgg = lpips.LpipsVGG16()
+    vgg.load_state_dict(sd_l)
+    bs, repeat, cutn, cut, coef = 2, 2, 2, 64, 5.0
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(bs, 64, generator=g) * 0.45
+    prm = cutouts.sample_params(cutn * bs * repeat, cut, g)
+    ts = train_step.TrainStep(net, vq.eval().requires_grad_(False), clip.eval().requires_grad_(False), cutn=cutn, cut_size=cut,
+                              diversity_coef=coef, repeat=repeat, lpips_net=vgg, diversity_mode=mode)
+    loss = float(ts.step(x, None, prm))
+    # the same step from the oracle pieces
+    p = {k: v.clone().requires_grad_(True) for k, v in sd_m.items()}
+    xin = x.repeat(repeat, 1)
+    cb = sd_v["quantize.embedding.weight"]
+    z = ovq.clamp_with_grad(omix.mixer_forward(p, xin, 16, 64).contiguous(), float(cb.min()), float(cb.max()))
+    xr = ovq.synth(sd_v, z, SMALL_VQ, force_idx=ts.last_indices.long())
+    emb = oclip.encode_image(sd_c, ocut.make_cutouts(xr, cutn, prm, cut, normalize=True), SMALL_CLIP)
+    dists = oloss.spherical_dist_loss(emb, xin, cutn)
+    mean, std = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1), torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+    div = ol.diversity(sd_l, xr, repeat, bs, mean, std, mode=mode)
+    (dists - coef * div).backward()
+    dists, div = float(dists.detach()), float(div.detach())
+    assert abs(loss - dists) < 3e-2 * abs(dists)
+    assert abs(float(ts.aux_loss[2]) - (-coef * div)) <= 5e-2 * abs(coef * div) + 1e-6
+    eng = net.engine()
+    big = [(n, gv) for (n, q), gv in zip(net.named_parameters(), eng.grad_views) if q.numel() >= 2048]
+    assert min(cos(gv, p[n].grad) for n, gv in big) > 0.95      # the bf16 VGG stack on 32 x 32 images adds to the step's rounding noise
