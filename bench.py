@@ -100,7 +100,7 @@ def flops_per_prompt():
 
 
 # ------------------------------------------------------------------------------------------------ model construction
-def build_b200(device, batch, world, pg, seed=0):
+def build_b200(device, batch, world, pg, seed=0, rank=0):
     from feed_forward_vqgan_clip_b200.clip_vit import CLIP
     from feed_forward_vqgan_clip_b200.mixer import Mixer
     from feed_forward_vqgan_clip_b200.train_step import TrainStep
@@ -112,7 +112,8 @@ def build_b200(device, batch, world, pg, seed=0):
         vq.quantize.embedding.weight.normal_(0, 1)   # N(0,1) codebook (taming's U(+-1/n) makes ties)
     clip = CLIP()
     net, vq, clip = net.to(device), vq.to(device).eval().requires_grad_(False), clip.to(device).eval().requires_grad_(False)
-    return TrainStep(net, vq, clip, cutn=CUTN, lr=1e-3, world_size=world, process_group=pg, seed=seed + 17)
+    # replicas share the weights' seed; the augmentation stream is per rank (every rank cuts its own prompts differently)
+    return TrainStep(net, vq, clip, cutn=CUTN, lr=1e-3, world_size=world, process_group=pg, seed=seed + 17 + 1000 * rank)
 
 
 def synthetic_embeddings(n, seed):
@@ -210,7 +211,7 @@ def main():
         pg = dist.group.WORLD
 
     B = args.batch
-    ts = build_b200(dev, B, world, pg)
+    ts = build_b200(dev, B, world, pg, rank=rank)
     if args.bucket_layers is not None:
         ts.bucket_layers = args.bucket_layers
     x_host = [synthetic_embeddings(B, 1000 + 7919 * rank + i).pin_memory() for i in range(4)]
