@@ -30,6 +30,12 @@ class OracleTrainer:
         if self.mapper == "vitgan":
             from . import vitgan as ovit
             z = ovit.vitgan_forward(self.params, inp_feats, self.C, self.num_heads).contiguous()
+        elif self.mapper == "simple_vitgan":
+            from . import vitgan as ovit
+            z = ovit.simple_vitgan_forward(self.params, inp_feats, self.C, self.num_heads).contiguous()
+        elif self.mapper == "xtransformer":
+            from . import xtransformer as oxt
+            z = oxt.xtransformer_forward(self.params, inp_feats, self.S, self.C, self.num_heads).contiguous()
         else:
             z = omix.mixer_forward(self.params, inp_feats, self.S, self.C).contiguous()      # main.py:754-757
         z.retain_grad()

@@ -171,7 +171,8 @@ SMALL_CLIP = dict(input_resolution=64, patch_size=32, width=128, layers=2, heads
 
 
 @pytest.mark.parametrize("mapper,extras", [("mixer", {}), ("vitgan", dict(l2_coef=0.1, tv_coef=0.5)),
-                                           ("mixer", dict(clip_grad_norm=0.5, scheduler="cosine", total_steps=10, use_ema=True))])
+                                           ("mixer", dict(clip_grad_norm=0.5, scheduler="cosine", total_steps=10, use_ema=True)),
+                                           ("simple_vitgan", {}), ("xtransformer", {})])
 def test_train_step_orchestration_vs_oracle_step(abi_on_cpu, monkeypatch, mapper, extras):
     """The whole step of main.py:729-837 — mapper -> clamp -> VQ -> decode -> cutouts -> CLIP -> loss (+ l2 / tv) -> backward
     -> optimizer block — through TrainStep's host logic, against oracle/train_step.py on the same weights, inputs and
@@ -186,10 +187,19 @@ def test_train_step_orchestration_vs_oracle_step(abi_on_cpu, monkeypatch, mapper
         net = mixer.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=1)
         with torch.no_grad():
             net.final_proj.weight.mul_(6.0)                # spread z over the codebook range so VQ picks varied codes
-    else:
+    elif mapper == "vitgan":
         net = vitgan_mapper.Generator(initialize_size=2, dim=48, blocks=1, num_heads=3, out_channels=64, input_dim=64)
         with torch.no_grad():
             net.w_out[0].weight.mul_(4.0)
+    elif mapper == "simple_vitgan":
+        net = simple_vitgan_mapper.SimpleGenerator(size=16, dim=48, blocks=1, num_heads=3, out_channels=64, input_dim=64)
+        with torch.no_grad():
+            net.w_out[0].weight.mul_(4.0)
+    else:
+        net = xtransformer.XTransformer(input_dim=64, image_size=16, channels=64, dim=64, depth=1, heads=3, initial_proj=True,
+                                        add_input=False)
+        with torch.no_grad():
+            net.transformer.project_out.weight.mul_(6.0)
     sd_m = {k: v.detach().clone() for k, v in net.state_dict().items()}
     sd_v = ovq.init_vqgan_state_dict(SMALL_VQ, seed=8)
     sd_c = oclip.init_clip_state_dict(SMALL_CLIP, seed=9)
