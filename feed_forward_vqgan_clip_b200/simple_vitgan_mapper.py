@@ -242,8 +242,18 @@ class SimpleVitGANEngine:
         return z, sv
 
     # ------------------------------------------------------------------ backward
-    def backward(self, sv, dz):
-        """dz: (B*T, C) fp32 token-major.  Accumulates all parameter gradients into self.grad."""
+    # ---- data parallel: completion order of the gradients inside the flat arena (parallel.bucket_slices)
+    def layer_starts(self):
+        """arena offset of the first parameter of every encoder block, ascending"""
+        return [min(off for n, off in self.offs.items() if n.startswith("Transformer_Encoder.blocks.%d." % i)) for i in range(self.L)]
+
+    def late_ranges(self):
+        """nothing registered after the blocks finishes late: pos_emb1D and the input projections sit at the head of the arena"""
+        return []
+
+    def backward(self, sv, dz, on_layer_done=None):
+        """dz: (B*T, C) fp32 token-major.  Accumulates all parameter gradients into self.grad.
+        on_layer_done(i): called once the gradients of encoder block i (and of everything registered after it) are complete."""
         B, T, D, L, C, Wi = sv["B"], self.T, self.D, self.L, self.C, self.Wi
         H, dh, dhp = self.H, self.dh, self.dhp
         R = B * T
@@ -288,6 +298,8 @@ class SimpleVitGANEngine:
             ops.linear_dgrad(dqkv, self.wqkv[i], ds1, R, 3 * Wi, D)
             del dqkv
             dhl = self._sln_bwd(ds1, bv["hl"], x, bv["st1"], p + "norm1.", R, dx_acc, dht)
+            if on_layer_done is not None:
+                on_layer_done(i)
         # hl0 = permute(inp(noise)) + pos_emb1D: pos_emb1D receives the batch sum, inp the per-sample transposed gradient
         call("colsum", dhl, self.g("pos_emb1D"), B, T * D)
         dit = self._new(B, D * T)

@@ -232,8 +232,18 @@ class VitGANEngine:
         return z, sv
 
     # ------------------------------------------------------------------ backward
-    def backward(self, sv, dz):
-        """dz: (B*T*T, C) fp32 token-major.  Accumulates all parameter gradients into self.grad."""
+    # ---- data parallel: completion order of the gradients inside the flat arena (parallel.bucket_slices)
+    def layer_starts(self):
+        """arena offset of the first parameter of every encoder block, ascending"""
+        return [min(off for n, off in self.offs.items() if n.startswith("Transformer_Encoder.blocks.%d." % i)) for i in range(self.L)]
+
+    def late_ranges(self):
+        """nothing registered after the blocks finishes late: pos_emb1D and the input projections sit at the head of the arena"""
+        return []
+
+    def backward(self, sv, dz, on_layer_done=None):
+        """dz: (B*T*T, C) fp32 token-major.  Accumulates all parameter gradients into self.grad.
+        on_layer_done(i): called once the gradients of encoder block i (and of everything registered after it) are complete."""
         B, T, D, L, H, C = sv["B"], self.T, self.D, self.L, self.H, self.C
         Wd, Wp, Q3, dh = self.Wd, self.Wp, self.Q3, self.dh
         R = B * T
@@ -277,6 +287,8 @@ class VitGANEngine:
             ds1 = self._new(R, D)
             ops.gemm(dqkv, self.w(p + "attn.to_qkv.weight"), ds1, R, D, 3 * Wd, a_ld=Q3, b_mode=ops.MNMAJOR, b_ld=D)
             dhl = self._sln_bwd(ds1, bv["hl"], x, bv["st1"], p + "norm1.", R, dx_acc, dht)
+            if on_layer_done is not None:
+                on_layer_done(i)
         # pos_emb1D receives the batch-summed gradient of the first block's input (it was broadcast over B)
         call("colsum", dhl, self.g("pos_emb1D"), B, T * D)
         # x = mlp(noise): only wgrad / bias grad (the prompt embedding needs no gradient)

@@ -231,7 +231,18 @@ class XTEngine:
         sv.update(hL=h, nf=nf, stf=(muf, rsf))
         return z, sv
 
-    def backward(self, sv, dz):
+    # ---- data parallel: completion order of the gradients inside the flat arena (parallel.bucket_slices)
+    def layer_starts(self):
+        """arena offset of the first parameter of every (attention, feed-forward) layer pair, ascending"""
+        return [self.offs["transformer.attn_layers.layers.%d.0.weight" % (2 * j)] for j in range(self.L)]
+
+    def late_ranges(self):
+        """`proj` is registered after the transformer (transformer.py:10-23) but its wgrad is the last GEMM of backward"""
+        lo = self.offs["proj.weight"]
+        hi = self.offs["proj.bias"] + (self.numel["proj.bias"] + 7) // 8 * 8
+        return [(lo, hi)]
+
+    def backward(self, sv, dz, on_layer_done=None):
         B, T, D, L, C, Wi = sv["B"], self.T, self.D, self.L, self.C, self.Wi
         R = B * T
         sp = ops.auto_splits
@@ -278,6 +289,8 @@ class XTEngine:
             dh = self._new(R, D)
             call("layernorm_bwd", dn1, lv["h"], self.wf(pa + "0.weight"), lv["st1"][0], lv["st1"][1], dh2, dh,
                  self.g(pa + "0.weight"), self.g(pa + "0.bias"), R, D)
+            if on_layer_done is not None:
+                on_layer_done(j)
         # h = project_in(h0) + pos
         call("colsum", dh, self.g("transformer.pos_emb.emb.weight"), B, T * D)          # sum over the batch; rows beyond T untouched
         ops.linear_wgrad(dh, sv["h0"], self.g("transformer.project_in.weight"), R, D, D, splits=sp(D, D, R))

@@ -42,12 +42,13 @@ class _NoEvent:
 def _patch(setattr_=setattr):
     """in the spawned workers the replacements are permanent; in the pytest process they go through monkeypatch.setattr"""
     import abi_model
-    from feed_forward_vqgan_clip_b200 import clip_vit, cutouts, mixer, ops, train_step, vqgan
+    from feed_forward_vqgan_clip_b200 import (clip_vit, cutouts, mixer, ops, simple_vitgan_mapper, train_step, vitgan_mapper, vqgan,
+                                              xtransformer)
     setattr_(ops, "gemm_raw", abi_model.gemm_raw)
     setattr_(ops, "gemm", lambda a, b, out, M, N, K, **kw: abi_model.gemm_raw(a, b, out, M, N, K, **kw))
     setattr_(ops, "call", abi_model.call)
     setattr_(ops, "require_cuda", lambda dev, what: None)
-    for mod in (mixer, vqgan, cutouts, train_step, clip_vit):
+    for mod in (mixer, vqgan, cutouts, train_step, clip_vit, vitgan_mapper, simple_vitgan_mapper, xtransformer):
         setattr_(mod, "call", abi_model.call)
     setattr_(torch.cuda, "Stream", lambda device=None: _NoStream())
     setattr_(torch.cuda, "current_stream", lambda device=None: _NoStream())
@@ -55,14 +56,32 @@ def _patch(setattr_=setattr):
     setattr_(torch.cuda, "stream", lambda s: contextlib.nullcontext())
 
 
-def _build(world, pg, bucket_layers):
+def _mapper(name):
+    from feed_forward_vqgan_clip_b200 import mixer, simple_vitgan_mapper, vitgan_mapper, xtransformer
+    if name == "mixer":
+        net = mixer.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=DEPTH)
+        out = net.final_proj.weight
+    elif name == "vitgan":
+        net = vitgan_mapper.Generator(initialize_size=2, dim=48, blocks=DEPTH, num_heads=3, out_channels=64, input_dim=64)
+        out = net.w_out[0].weight
+    elif name == "simple_vitgan":
+        net = simple_vitgan_mapper.SimpleGenerator(size=16, dim=48, blocks=DEPTH, num_heads=3, out_channels=64, input_dim=64)
+        out = net.w_out[0].weight
+    else:
+        net = xtransformer.XTransformer(input_dim=64, image_size=16, channels=64, dim=64, depth=DEPTH, heads=3, initial_proj=True,
+                                        add_input=False)
+        out = net.transformer.project_out.weight
+    with torch.no_grad():
+        out.mul_(5.0)                                        # spread z over the codebook range
+    return net
+
+
+def _build(world, pg, bucket_layers, mapper="mixer"):
     import oracle.clip_vit as oclip
     import oracle.vqgan as ovq
-    from feed_forward_vqgan_clip_b200 import clip_vit, mixer, train_step, vqgan
+    from feed_forward_vqgan_clip_b200 import clip_vit, train_step, vqgan
     torch.manual_seed(0)                                     # identical replicas on every rank (main.py:628 broadcasts)
-    net = mixer.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=DEPTH)
-    with torch.no_grad():
-        net.final_proj.weight.mul_(6.0)
+    net = _mapper(mapper)
     vq = vqgan.VQModel(VQ)
     vq.load_state_dict(ovq.init_vqgan_state_dict(VQ, seed=8))
     clip = clip_vit.CLIP(CLIPCFG)
@@ -80,7 +99,7 @@ def _inputs():
     return x, sample_params(CUTN * B, CUT, g)
 
 
-def _worker(rank, world, port, bucket_layers, q):
+def _worker(rank, world, port, bucket_layers, mapper, q):
     try:
         import sys
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -93,7 +112,7 @@ def _worker(rank, world, port, bucket_layers, q):
         real = dist.all_reduce
         dist.all_reduce = lambda t, *a, **k: (calls.append(t.numel()), real(t, *a, **k))[1]
         torch.distributed.all_reduce = dist.all_reduce
-        net, ts = _build(world, dist.group.WORLD, bucket_layers)
+        net, ts = _build(world, dist.group.WORLD, bucket_layers, mapper)
         x, prm = _inputs()
         lo, hi = parallel.shard_range(B, rank, world)
         loss = float(ts.step(x[lo:hi].contiguous(), None, parallel.shard_cutout_params(prm, CUTN, B, lo, hi)))
@@ -107,12 +126,12 @@ def _worker(rank, world, port, bucket_layers, q):
         q.put((rank, "ERROR", traceback.format_exc()))
 
 
-def _run(bucket_layers):
+def _run(bucket_layers, mapper="mixer"):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, bucket_layers, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, bucket_layers, mapper, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
@@ -128,14 +147,18 @@ def _cos(a, b):
     return float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300))
 
 
-def test_two_rank_step_equals_the_global_batch_step(monkeypatch):
-    res = _run(bucket_layers=2)                              # 3 mixer layers in buckets of 2: [layers 1-2 + tail], [layer 0], [head]
+import pytest
+
+
+@pytest.mark.parametrize("mapper", ["mixer", "vitgan", "simple_vitgan", "xtransformer"])
+def test_two_rank_step_equals_the_global_batch_step(monkeypatch, mapper):
+    res = _run(bucket_layers=2, mapper=mapper)                              # 3 mixer layers in buckets of 2: [layers 1-2 + tail], [layer 0], [head]
     (_, loss0, g0, p0, calls0, total, idx0), (_, loss1, g1, p1, calls1, _, idx1) = res
     assert torch.equal(g0, g1) and torch.equal(p0, p1)       # both replicas hold the same reduced gradient and take the same step
     assert calls0 == calls1 and sum(calls0) == total         # the all-reduced slices tile the arena exactly once
     # single process, global batch
     _patch(monkeypatch.setattr)
-    net, ts = _build(1, None, 0)
+    net, ts = _build(1, None, 0, mapper)
     keep = ts.mix.arena.clone()
     x, prm = _inputs()
     loss = float(ts.step(x, None, prm))
@@ -144,10 +167,11 @@ def test_two_rank_step_equals_the_global_batch_step(monkeypatch):
     eng = ts.mix
     buckets = parallel.bucket_slices(eng.layer_starts(), eng.total, 2, late=eng.late_ranges())
     assert calls0 == [hi - lo for b in buckets for lo, hi in b] and len(buckets) == 3
-    # the input projection is registered after the layers but finishes last: it must travel in the LAST bucket, not the first
-    lo, hi = eng.late_ranges()[0]
-    assert (lo, hi) in buckets[-1] and all(not (a < hi and lo < b) for bk in buckets[:-1] for a, b in bk)
-    assert eng.offs["proj.weight"] == lo and float(g_full[lo:hi].abs().max()) > 0
+    # an input projection registered after the layers finishes last: it must travel in the LAST bucket, not the first
+    for lo, hi in eng.late_ranges():
+        assert (lo, hi) in buckets[-1] and all(not (a < hi and lo < b) for bk in buckets[:-1] for a, b in bk)
+        assert eng.offs["proj.weight"] == lo and float(g_full[lo:hi].abs().max()) > 0
+    assert bool(eng.late_ranges()) == (mapper in ("mixer", "xtransformer"))
     same = (torch.cat([idx0.view(B // 2, -1), idx1.view(B // 2, -1)]) == ts.last_indices.view(B, -1)).float().mean()
     assert float(same) > 0.99
     assert abs((loss0 + loss1) / 2 - loss) < 5e-3 * abs(loss)
