@@ -77,6 +77,18 @@ def load_vqgan_model(config_path=None, checkpoint_path=None):
     return model
 
 
+def _read_state_dict(path):
+    """weights from a plain state_dict file, a {"state_dict": ...} checkpoint, a pickled module, or a TorchScript archive (the
+    form OpenAI publishes ViT-B/32 in; clip.load(..., jit=False) rebuilds the model from its state_dict the same way)"""
+    try:
+        obj = torch.load(path, map_location="cpu", weights_only=False)
+    except Exception:
+        obj = torch.jit.load(path, map_location="cpu")
+    if hasattr(obj, "state_dict") and callable(obj.state_dict):
+        return obj.state_dict()
+    return obj.get("state_dict", obj)
+
+
 def load_clip_model(model_type="ViT-B/32", path=None):
     if model_type.startswith("open_clip:"):
         arch = model_type.split(":")[1]
@@ -90,8 +102,7 @@ def load_clip_model(model_type="ViT-B/32", path=None):
     from .clip_text import TEXT_B32
     model = CLIP(VIT_B32, act=act, text_cfg=TEXT_B32)
     if path and os.path.exists(path):
-        sd = torch.load(path, map_location="cpu")
-        sd = sd.get("state_dict", sd)
+        sd = _read_state_dict(path)
         vis = {k[len("visual."):]: v.float() for k, v in sd.items() if k.startswith("visual.")}
         model.visual.load_state_dict(vis)
         txt = {k: v.float() for k, v in sd.items() if k in model.text.state_dict()}

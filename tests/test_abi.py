@@ -187,3 +187,43 @@ def test_replay_host_logic_draws_next_parameters_after_the_launch():
     kept = fake._next_prm
     TrainStep.replay(fake, x, None, explicit)
     assert events[-1] == "launch" and fake._next_prm is kept and torch.equal(st["persp_inv"], explicit["persp_inv"])
+
+
+def test_load_clip_and_vqgan_checkpoints_in_the_published_formats(tmp_path):
+    """api.load_clip_model / load_vqgan_model read what the reference reads (main.py:84-103,1308-1333): CLIP weights as a plain
+    fp16 state_dict (visual.* + text tower keys) or a TorchScript archive, the VQGAN as taming's {"state_dict": ...} checkpoint
+    with encoder / loss keys the decoder-only model ignores.  Host logic only (no engine is built)."""
+    from feed_forward_vqgan_clip_b200 import api
+    from feed_forward_vqgan_clip_b200.clip_vit import CLIP, VIT_B32
+    from feed_forward_vqgan_clip_b200.clip_text import TEXT_B32
+    src = CLIP(VIT_B32, text_cfg=TEXT_B32)
+    sd = {"visual." + k: v.half() for k, v in src.visual.state_dict().items()}
+    sd.update({k: v.half() for k, v in src.text.state_dict().items()})
+    sd["logit_scale"] = torch.tensor(4.6)
+    torch.save(sd, tmp_path / "clip_sd.pt")
+    m = api.load_clip_model("ViT-B/32", str(tmp_path / "clip_sd.pt"))
+    k = "transformer.resblocks.3.mlp.c_fc.weight"
+    assert m.visual.state_dict()[k].dtype == torch.float32
+    assert torch.equal(m.visual.state_dict()[k], src.visual.state_dict()[k].half().float())
+    assert torch.equal(m.text.state_dict()["text_projection"], src.text.state_dict()["text_projection"].half().float())
+    assert not any(p.requires_grad for p in m.parameters())
+
+    class Holder(torch.nn.Module):                       # a TorchScript archive only has to expose state_dict()
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.arange(4.0))
+
+        def forward(self, x):
+            return x + self.w
+    torch.jit.script(Holder()).save(str(tmp_path / "jit.pt"))
+    assert torch.equal(api._read_state_dict(str(tmp_path / "jit.pt"))["w"], torch.arange(4.0))
+
+    vq = api.load_vqgan_model()
+    ck = {"state_dict": {k: v + 1.0 for k, v in vq.state_dict().items()}}
+    ck["state_dict"]["encoder.conv_in.weight"] = torch.zeros(3)          # taming's encoder / loss keys are not ours
+    ck["state_dict"]["loss.discriminator.main.0.weight"] = torch.zeros(3)
+    torch.save(ck, tmp_path / "vqgan.ckpt")
+    vq2 = api.load_vqgan_model(None, str(tmp_path / "vqgan.ckpt"))
+    for k2, v in vq.state_dict().items():
+        assert torch.equal(vq2.state_dict()[k2], v + 1.0), k2
+    assert vq2.quantize.embedding.weight.shape == (16384, 256) and not vq2.training
