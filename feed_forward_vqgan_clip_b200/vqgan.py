@@ -106,7 +106,7 @@ class VQModel(nn.Module):
         self._engine = None
 
     def init_from_ckpt(self, path):
-        sd = torch.load(path, map_location="cpu")
+        sd = torch.load(path, map_location="cpu", weights_only=False)   # Lightning checkpoints carry non-tensor objects
         sd = sd.get("state_dict", sd)
         own = self.state_dict()
         self.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=False)
