@@ -1,0 +1,142 @@
+"""Drop-in check: the REFERENCE's own `train()` (main.py:504-969), unmodified, driven with this package's objects —
+`build_model`, `load_vqgan_model`, `load_clip_model`, `MakeCutouts`, `synth`, `clamp_with_grad` swapped in exactly as
+INTEGRATION.md describes — for a few steps on a configs/example.yaml-shaped config, then the same loop with the reference's own
+`mlp_mixer_pytorch.Mixer` as the mapper: same seed => same initial weights (the state_dict contract), and the per-step losses
+of the two runs agree within the bf16 tolerance, i.e. our Mixer is interchangeable with theirs inside their loop (autograd
+`loss.backward()`, `optim.Adam(net.parameters())`, `net.state_dict()` checkpointing).
+
+Runs only where /root/reference exists (the build container).  main.py's third-party imports that are absent from the image
+(clize, omegaconf, kornia, taming, clip, x_transformers) are stubbed; `OmegaConf.load` is served by a small attribute-dict.
+Device kernels are replaced by tests/abi_model.py (see test_engine_orchestration_cpu.py): the reference picks device "cpu" when
+CUDA is unavailable (main.py:526), which is what makes this run possible without a GPU."""
+import os
+import sys
+from unittest.mock import MagicMock
+
+import pytest
+import torch
+import yaml
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "main.py")), reason="the reference tree is not present")
+
+SMALL_VQ = dict(ch=64, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(16,), resolution=32, z_channels=64, out_ch=3,
+                embed_dim=64, n_embed=512)
+SMALL_CLIP = dict(input_resolution=64, patch_size=32, width=128, layers=1, heads=2, output_dim=64)
+
+
+class Config(dict):
+    """what OmegaConf.load returns as far as main.py uses it: attribute access, .get, hasattr, item assignment, picklable"""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+def _import_reference_main():
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    for name in ["clize", "omegaconf", "kornia", "kornia.augmentation", "taming", "taming.models", "taming.models.cond_transformer",
+                 "taming.models.vqgan", "taming.modules", "taming.modules.losses", "taming.modules.losses.lpips", "clip",
+                 "clip.simple_tokenizer", "x_transformers"]:
+        sys.modules.setdefault(name, MagicMock())
+    os.environ["USE_HOROVOD"] = "false"
+    import main as ref
+    return ref
+
+
+def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps):
+    import abi_model
+    import oracle.clip_vit as oclip
+    import oracle.vqgan as ovq
+    from feed_forward_vqgan_clip_b200 import api, clip_vit, cutouts, mixer, ops, vqgan
+    monkeypatch.setattr(ops, "gemm_raw", abi_model.gemm_raw)
+    monkeypatch.setattr(ops, "gemm", lambda a, b, out, M, N, K, **kw: abi_model.gemm_raw(a, b, out, M, N, K, **kw))
+    monkeypatch.setattr(ops, "call", abi_model.call)
+    monkeypatch.setattr(ops, "require_cuda", lambda dev, what: None)
+    for mod in (mixer, vqgan, cutouts, clip_vit):
+        monkeypatch.setattr(mod, "call", abi_model.call)
+    folder = tmp_path / tag
+    folder.mkdir()
+    g = torch.Generator().manual_seed(0)
+    torch.save(torch.randn(steps * 2, 64, generator=g) * 0.45, folder / "data.pkl")     # float embeddings: encode_text is skipped
+    cfg = yaml.safe_load(open(os.path.join(REF, "configs", "example.yaml")))           # the shipped config, scaled down
+    cfg.update(dim=64, depth=1, cutn=2, batch_size=2, epochs=1, path=str(folder / "data.pkl"), folder=str(folder), log_interval=1,
+               clip_size=64, clip_dim=64, vq_image_size=16)
+    with open(folder / "config.yaml", "w") as f:
+        yaml.safe_dump(cfg, f)
+
+    def load_vq(config_path=None, checkpoint_path=None):
+        m = vqgan.VQModel(SMALL_VQ)
+        m.load_state_dict(ovq.init_vqgan_state_dict(SMALL_VQ, seed=8))
+        return m.eval().requires_grad_(False)
+
+    def load_clip(model_type="ViT-B/32", path=None):
+        m = clip_vit.CLIP(SMALL_CLIP)
+        m.visual.load_state_dict(oclip.init_clip_state_dict(SMALL_CLIP, seed=9))
+        m.logit_scale = torch.nn.Parameter(torch.tensor(4.6))
+        return m.eval().requires_grad_(False)
+
+    # ---- the substitutions of INTEGRATION.md
+    monkeypatch.setattr(ref.OmegaConf, "load", lambda path: Config(yaml.safe_load(open(path))))
+    monkeypatch.setattr(ref, "build_model", lambda config: mapper_factory(config))
+    monkeypatch.setattr(ref, "load_vqgan_model", load_vq)
+    monkeypatch.setattr(ref, "load_clip_model", load_clip)
+    monkeypatch.setattr(ref, "MakeCutouts", api.MakeCutouts)
+    monkeypatch.setattr(ref, "synth", api.synth)
+    monkeypatch.setattr(ref, "clamp_with_grad", api.clamp_with_grad)
+    losses = []
+
+    class Writer:                                            # SummaryWriter stand-in that records the logged scalars
+        def __init__(self, folder):
+            pass
+
+        def add_scalar(self, name, value, step):
+            if name == "loss":
+                losses.append(float(value))
+    monkeypatch.setattr(ref, "SummaryWriter", Writer)
+    torch.manual_seed(123)                                   # mapper init, DataLoader shuffle and the augmentation draws
+    net = ref.train(str(folder / "config.yaml"))
+    return net, losses, folder
+
+
+def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_path):
+    ref = _import_reference_main()
+    from feed_forward_vqgan_clip_b200 import api
+    steps = 3
+
+    def ours(config):
+        net = api.build_model(config, vq_channels=64)
+        with torch.no_grad():
+            net.final_proj.weight.mul_(6.0)
+        return net
+
+    def theirs(config):
+        net = ref.Mixer(input_dim=config.clip_dim + config.noise_dim, image_size=config.vq_image_size, channels=64, patch_size=1,
+                        dim=config.dim, depth=config.depth, dropout=config.dropout)        # main.py:479-487
+        with torch.no_grad():
+            net.final_proj.weight.mul_(6.0)
+        return net
+
+    net_a, loss_a, folder_a = _run(ref, monkeypatch, tmp_path, "ours", ours, steps)
+    net_b, loss_b, folder_b = _run(ref, monkeypatch, tmp_path, "theirs", theirs, steps)
+    assert len(loss_a) == len(loss_b) == steps and all(l == l and 0 < l < 5 for l in loss_a)
+    for a, b in zip(loss_a, loss_b):
+        assert abs(a - b) <= 3e-2 * abs(b), (loss_a, loss_b)
+    # the reference's own checkpointing ran on our module (main.py:904-911): same keys / shapes as on theirs, and the trained
+    # weights moved the same way
+    ck_a = torch.load(folder_a / "checkpoint.th", weights_only=False)
+    ck_b = torch.load(folder_b / "checkpoint.th", weights_only=False)
+    assert list(ck_a["state_dict"].keys()) == list(ck_b["state_dict"].keys())
+    assert ck_a["step"] == ck_b["step"] and os.path.exists(folder_a / "opt.th") and os.path.exists(folder_a / "progress.png")
+    big = [k for k, v in ck_b["state_dict"].items() if v.numel() >= 2048]
+    for k in big:
+        a, b = ck_a["state_dict"][k].flatten(), ck_b["state_dict"][k].flatten()
+        assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.995, k      # 3 sign-like Adam steps on bf16-noisy gradients
+    theirs_fresh = ref.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=1)
+    theirs_fresh.load_state_dict(ck_a["state_dict"])        # a checkpoint written from our module loads into the reference's
