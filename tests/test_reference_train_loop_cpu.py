@@ -50,7 +50,7 @@ def _import_reference_main():
     return ref
 
 
-def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps):
+def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     import abi_model
     import oracle.clip_vit as oclip
     import oracle.vqgan as ovq
@@ -59,15 +59,16 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps):
     monkeypatch.setattr(ops, "gemm", lambda a, b, out, M, N, K, **kw: abi_model.gemm_raw(a, b, out, M, N, K, **kw))
     monkeypatch.setattr(ops, "call", abi_model.call)
     monkeypatch.setattr(ops, "require_cuda", lambda dev, what: None)
-    for mod in (mixer, vqgan, cutouts, clip_vit):
+    from feed_forward_vqgan_clip_b200 import simple_vitgan_mapper, vitgan_mapper
+    for mod in (mixer, vqgan, cutouts, clip_vit, vitgan_mapper, simple_vitgan_mapper):
         monkeypatch.setattr(mod, "call", abi_model.call)
     folder = tmp_path / tag
     folder.mkdir()
     g = torch.Generator().manual_seed(0)
     torch.save(torch.randn(steps * 2, 64, generator=g) * 0.45, folder / "data.pkl")     # float embeddings: encode_text is skipped
     cfg = yaml.safe_load(open(os.path.join(REF, "configs", "example.yaml")))           # the shipped config, scaled down
-    cfg.update(dim=64, depth=1, cutn=2, batch_size=2, epochs=1, path=str(folder / "data.pkl"), folder=str(folder), log_interval=1,
-               clip_size=64, clip_dim=64, vq_image_size=16)
+    cfg.update(depth=1, cutn=2, batch_size=2, epochs=1, path=str(folder / "data.pkl"), folder=str(folder), log_interval=1,
+               clip_size=64, clip_dim=64, vq_image_size=16, **extra_cfg)
     with open(folder / "config.yaml", "w") as f:
         yaml.safe_dump(cfg, f)
 
@@ -84,7 +85,8 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps):
 
     # ---- the substitutions of INTEGRATION.md
     monkeypatch.setattr(ref.OmegaConf, "load", lambda path: Config(yaml.safe_load(open(path))))
-    monkeypatch.setattr(ref, "build_model", lambda config: mapper_factory(config))
+    built = []
+    monkeypatch.setattr(ref, "build_model", lambda config: (built.append(mapper_factory(config)), built[-1])[1])
     monkeypatch.setattr(ref, "load_vqgan_model", load_vq)
     monkeypatch.setattr(ref, "load_clip_model", load_clip)
     monkeypatch.setattr(ref, "MakeCutouts", api.MakeCutouts)
@@ -101,30 +103,39 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps):
                 losses.append(float(value))
     monkeypatch.setattr(ref, "SummaryWriter", Writer)
     torch.manual_seed(123)                                   # mapper init, DataLoader shuffle and the augmentation draws
-    net = ref.train(str(folder / "config.yaml"))
-    return net, losses, folder
+    ref.train(str(folder / "config.yaml"))
+    return built[-1], losses, folder
 
 
-def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_path):
+@pytest.mark.parametrize("model_type", ["mlp_mixer", "vitgan", "simple_vitgan"])
+def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_path, model_type):
     ref = _import_reference_main()
     from feed_forward_vqgan_clip_b200 import api
     steps = 3
+    extra = dict(model_type=model_type, dim=64 if model_type == "mlp_mixer" else 48, num_heads=3)
+
+    def widen(net):                                          # spread z over the codebook range so VQ picks varied codes
+        with torch.no_grad():
+            (net.final_proj if model_type == "mlp_mixer" else net.w_out[0]).weight.mul_(6.0 if model_type == "mlp_mixer" else 4.0)
+        return net
 
     def ours(config):
-        net = api.build_model(config, vq_channels=64)
-        with torch.no_grad():
-            net.final_proj.weight.mul_(6.0)
-        return net
+        return widen(api.build_model(config, vq_channels=64))
 
-    def theirs(config):
-        net = ref.Mixer(input_dim=config.clip_dim + config.noise_dim, image_size=config.vq_image_size, channels=64, patch_size=1,
-                        dim=config.dim, depth=config.depth, dropout=config.dropout)        # main.py:479-487
-        with torch.no_grad():
-            net.final_proj.weight.mul_(6.0)
-        return net
+    def theirs(config):                                      # the constructor calls of main.py:459-487
+        if model_type == "mlp_mixer":
+            return widen(ref.Mixer(input_dim=config.clip_dim + config.noise_dim, image_size=config.vq_image_size, channels=64,
+                                   patch_size=1, dim=config.dim, depth=config.depth, dropout=config.dropout))
+        if model_type == "vitgan":
+            return widen(ref.VitGAN(initialize_size=config.vq_image_size // 8, dropout=config.dropout, out_channels=64,
+                                    input_dim=config.clip_dim + config.noise_dim, dim=config.dim, num_heads=config.get("num_heads", 6),
+                                    blocks=config.depth))
+        return widen(ref.SimpleVitGAN(size=config.vq_image_size, dropout=config.dropout, out_channels=64,
+                                      input_dim=config.clip_dim + config.noise_dim, dim=config.dim,
+                                      num_heads=config.get("num_heads", 6), blocks=config.depth))
 
-    net_a, loss_a, folder_a = _run(ref, monkeypatch, tmp_path, "ours", ours, steps)
-    net_b, loss_b, folder_b = _run(ref, monkeypatch, tmp_path, "theirs", theirs, steps)
+    net_a, loss_a, folder_a = _run(ref, monkeypatch, tmp_path, "ours", ours, steps, extra)
+    net_b, loss_b, folder_b = _run(ref, monkeypatch, tmp_path, "theirs", theirs, steps, extra)
     assert len(loss_a) == len(loss_b) == steps and all(l == l and 0 < l < 5 for l in loss_a)
     for a, b in zip(loss_a, loss_b):
         assert abs(a - b) <= 3e-2 * abs(b), (loss_a, loss_b)
@@ -138,5 +149,4 @@ def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_p
     for k in big:
         a, b = ck_a["state_dict"][k].flatten(), ck_b["state_dict"][k].flatten()
         assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.995, k      # 3 sign-like Adam steps on bf16-noisy gradients
-    theirs_fresh = ref.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=1)
-    theirs_fresh.load_state_dict(ck_a["state_dict"])        # a checkpoint written from our module loads into the reference's
+    net_b.load_state_dict(ck_a["state_dict"])               # a checkpoint written from our module loads into the reference's
