@@ -150,3 +150,71 @@ def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_p
         a, b = ck_a["state_dict"][k].flatten(), ck_b["state_dict"][k].flatten()
         assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.995, k      # 3 sign-like Adam steps on bf16-noisy gradients
     net_b.load_state_dict(ck_a["state_dict"])               # a checkpoint written from our module loads into the reference's
+
+
+# ---------------------------------------------------------------------------------------------- data parallel, main.py's own Horovod calls
+class _Setter:
+    """monkeypatch stand-in for the spawned workers (replacements need not be undone there)"""
+
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+
+def _hvd_worker(rank, world, port, tmp, q):
+    try:
+        import pathlib
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+        torch.set_num_threads(2)
+        from feed_forward_vqgan_clip_b200 import api, parallel
+        parallel.install_horovod_shim()                      # `import horovod.torch as hvd` (main.py:45) now resolves to the shim
+        os.environ.pop("USE_HOROVOD", None)
+        for name in ["clize", "omegaconf", "kornia", "kornia.augmentation", "taming", "taming.models", "taming.models.cond_transformer",
+                     "taming.models.vqgan", "taming.modules", "taming.modules.losses", "taming.modules.losses.lpips", "clip",
+                     "clip.simple_tokenizer", "x_transformers"]:
+            sys.modules.setdefault(name, MagicMock())
+        sys.path.insert(0, REF)
+        import main as ref
+        assert ref.USE_HOROVOD
+
+        def ours(config):
+            net = api.build_model(config, vq_channels=64)
+            with torch.no_grad():
+                net.final_proj.weight.mul_(6.0 + rank)       # replicas start DIFFERENT: hvd.broadcast_parameters must fix that
+            return net
+
+        # 8 prompts, DistributedSampler gives each rank 4 = 2 steps of batch_size 2
+        net, losses, folder = _run(ref, _Setter, pathlib.Path(tmp), "rank%d" % rank, ours, 4, dict(model_type="mlp_mixer", dim=64))
+        flat = net.engine().arena.detach().numpy().copy()
+        q.put((rank, flat, losses, sorted(os.listdir(folder))))
+        ref.hvd.shutdown()
+    except Exception:
+        import traceback
+        q.put((rank, "ERROR", traceback.format_exc(), None))
+
+
+def test_reference_train_loop_data_parallel_through_the_horovod_shim(tmp_path):
+    """main.py with USE_HOROVOD (its own hvd.init / DistributedOptimizer / broadcast_parameters / DistributedSampler / allreduce
+    calls, main.py:528-531,627-629,668-674,838-842) on 2 gloo ranks, `horovod.torch` served by the shim: replicas that start
+    different are made identical, stay identical through the steps, and only rank 0 logs and checkpoints."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_hvd_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=600) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    for r in res:
+        assert not isinstance(r[1], str), r[2]
+    (_, w0, l0, files0), (_, w1, l1, files1) = res
+    assert (w0 == w1).all()                                  # identical replicas after broadcast + 2 averaged steps
+    assert len(l0) == 2 and l1 == []                         # rank 0 is the only logger (main.py:620-624)
+    assert "checkpoint.th" in files0 and "checkpoint.th" not in files1
