@@ -25,6 +25,9 @@ SMALL_VQ = dict(ch=64, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(16,),
 SMALL_CLIP = dict(input_resolution=64, patch_size=32, width=128, layers=1, heads=2, output_dim=64)
 
 
+SMALL_TEXT = dict(embed_dim=64, context_length=77, vocab_size=100, transformer_width=128, transformer_heads=2, transformer_layers=1)
+
+
 class Config(dict):
     """what OmegaConf.load returns as far as main.py uses it: attribute access, .get, hasattr, item assignment, picklable"""
 
@@ -60,12 +63,19 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     monkeypatch.setattr(ops, "call", abi_model.call)
     monkeypatch.setattr(ops, "require_cuda", lambda dev, what: None)
     from feed_forward_vqgan_clip_b200 import simple_vitgan_mapper, vitgan_mapper
-    for mod in (mixer, vqgan, cutouts, clip_vit, vitgan_mapper, simple_vitgan_mapper):
+    from feed_forward_vqgan_clip_b200 import clip_text
+    for mod in (mixer, vqgan, cutouts, clip_vit, clip_text, vitgan_mapper, simple_vitgan_mapper):
         monkeypatch.setattr(mod, "call", abi_model.call)
     folder = tmp_path / tag
     folder.mkdir()
     g = torch.Generator().manual_seed(0)
-    torch.save(torch.randn(steps * 2, 64, generator=g) * 0.45, folder / "data.pkl")     # float embeddings: encode_text is skipped
+    tokens = extra_cfg.pop("tokens", False)
+    if tokens:                                               # token ids (dtype long): train() calls perceptor.encode_text (main.py:733)
+        data = torch.randint(1, 90, (steps * 2, 77), generator=g)
+        data[torch.arange(steps * 2), torch.randint(5, 77, (steps * 2,), generator=g)] = 99          # EOT = the largest id
+    else:
+        data = torch.randn(steps * 2, 64, generator=g) * 0.45                                       # float embeddings: encode_text is skipped
+    torch.save(data, folder / "data.pkl")
     cfg = yaml.safe_load(open(os.path.join(REF, "configs", "example.yaml")))           # the shipped config, scaled down
     cfg.update(depth=1, cutn=2, batch_size=2, epochs=1, path=str(folder / "data.pkl"), folder=str(folder), log_interval=1,
                clip_size=64, clip_dim=64, vq_image_size=16, **extra_cfg)
@@ -78,7 +88,8 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
         return m.eval().requires_grad_(False)
 
     def load_clip(model_type="ViT-B/32", path=None):
-        m = clip_vit.CLIP(SMALL_CLIP)
+        torch.manual_seed(77)                                # the text tower keeps its seeded default init
+        m = clip_vit.CLIP(SMALL_CLIP, text_cfg=SMALL_TEXT)
         m.visual.load_state_dict(oclip.init_clip_state_dict(SMALL_CLIP, seed=9))
         m.logit_scale = torch.nn.Parameter(torch.tensor(4.6))
         return m.eval().requires_grad_(False)
@@ -92,6 +103,7 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     monkeypatch.setattr(ref, "MakeCutouts", api.MakeCutouts)
     monkeypatch.setattr(ref, "synth", api.synth)
     monkeypatch.setattr(ref, "clamp_with_grad", api.clamp_with_grad)
+    monkeypatch.setattr(ref, "decode", lambda ids: " ".join(str(i) for i in ids))      # clip's BPE decoder (progress.txt only) is stubbed
     losses = []
 
     class Writer:                                            # SummaryWriter stand-in that records the logged scalars
@@ -107,8 +119,8 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     return built[-1], losses, folder
 
 
-@pytest.mark.parametrize("model_type", ["mlp_mixer", "vitgan", "simple_vitgan"])
-def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_path, model_type):
+@pytest.mark.parametrize("model_type,tokens", [("mlp_mixer", False), ("vitgan", False), ("simple_vitgan", False), ("mlp_mixer", True)])
+def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_path, model_type, tokens):
     ref = _import_reference_main()
     from feed_forward_vqgan_clip_b200 import api
     steps = 3
@@ -134,8 +146,8 @@ def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_p
                                       input_dim=config.clip_dim + config.noise_dim, dim=config.dim,
                                       num_heads=config.get("num_heads", 6), blocks=config.depth))
 
-    net_a, loss_a, folder_a = _run(ref, monkeypatch, tmp_path, "ours", ours, steps, extra)
-    net_b, loss_b, folder_b = _run(ref, monkeypatch, tmp_path, "theirs", theirs, steps, extra)
+    net_a, loss_a, folder_a = _run(ref, monkeypatch, tmp_path, "ours", ours, steps, dict(extra, tokens=tokens))
+    net_b, loss_b, folder_b = _run(ref, monkeypatch, tmp_path, "theirs", theirs, steps, dict(extra, tokens=tokens))
     assert len(loss_a) == len(loss_b) == steps and all(l == l and 0 < l < 5 for l in loss_a)
     for a, b in zip(loss_a, loss_b):
         assert abs(a - b) <= 3e-2 * abs(b), (loss_a, loss_b)
