@@ -4,6 +4,7 @@
     load_vqgan_model(config_path, ckpt)      main.py:84-103
     load_clip_model(name, path)              main.py:1308-1333 (OpenAI ViT-B/32 and OpenCLIP ViT-B-32 architectures)
     MakeCutouts / synth / clamp_with_grad / vector_quantize      main.py:105-229
+    LPIPS / normalize_tensor                 main.py:30-31,532-537,776-787 (diversity term; `LPIPS().net(x)` -> the five VGG16 taps)
     train_step(net, vq, perceptor, ...)      the body of main.py:729-837 as one fused object (TrainStep)
     CheckpointWriter(train_step, folder)     main.py:904-911 (checkpoint.th / checkpoint_ema.th / opt.th), asynchronous, optionally sharded
 
@@ -17,6 +18,7 @@ import torch
 from .checkpoint import CheckpointWriter, load_sharded  # noqa: F401
 from .clip_vit import CLIP, VIT_B32
 from .cutouts import MakeCutouts, sample_params  # noqa: F401
+from .lpips import LPIPS, normalize_tensor  # noqa: F401
 from .mixer import Mixer
 from .simple_vitgan_mapper import SimpleGenerator as SimpleVitGAN
 from .vitgan_mapper import Generator as VitGAN

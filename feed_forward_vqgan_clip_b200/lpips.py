@@ -38,6 +38,54 @@ class LpipsVGG16(nn.Module):
             self._engine = DiversityEngine(self)
         return self._engine
 
+    def forward(self, x):
+        """The call the reference's loop makes, `lpips.net((xr - mean) / std)` (main.py:778): (N, 3, H, W) fp32 -> the five
+        tap tensors (N, c, h, w) fp32, differentiable w.r.t. x."""
+        return list(_TapsFn.apply(self, x))
+
+
+class _TapsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, net, x):
+        eng = net.engine()
+        N = x.shape[0]
+        taps, saved = eng.features(x.permute(0, 2, 3, 1).contiguous().float())
+        ctx.eng, ctx.saved = eng, saved
+        return tuple(f.float().view(N, h, w, c).permute(0, 3, 1, 2) for _, f, h, w, c in taps)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        eng, saved = ctx.eng, ctx.saved
+        N, H, W = saved["N"], saved["H"], saved["W"]
+        dtap = {}
+        for (s, f, h, w, c), g in zip(saved["taps"], grads):
+            if g is None:
+                g = torch.zeros(N, c, h, w, device=f.device)
+            dtap[s] = g.permute(0, 2, 3, 1).contiguous().to(BF16).view(N * h * w, c)
+        dxn = eng.features_bwd(saved, dtap)
+        return None, dxn.view(N, H, W, 3).permute(0, 3, 1, 2)
+
+
+class LPIPS(nn.Module):
+    """what `train()` builds for the diversity term (main.py:532-537): `LPIPS().net` is the tap network; the reference never
+    uses the linear heads or the scaling layer."""
+
+    def __init__(self):
+        super().__init__()
+        self.net = LpipsVGG16()
+
+    def load_from_pretrained(self, path=None):
+        """taming downloads vgg.pth into its cache; here the weights come from an explicit file when one is given"""
+        if path:
+            sd = torch.load(path, map_location="cpu", weights_only=False)
+            self.net.load_state_dict({k[len("net."):]: v for k, v in sd.items() if k.startswith("net.slice")}, strict=False)
+        return self
+
+
+def normalize_tensor(x, eps=1e-10):
+    """taming.modules.losses.lpips.normalize_tensor (imported at main.py:31, used at :780,:784): plain torch, as there"""
+    return x / (torch.sqrt(torch.sum(x ** 2, dim=1, keepdim=True)) + eps)
+
 
 class DiversityEngine:
     def __init__(self, net):
@@ -79,13 +127,11 @@ class DiversityEngine:
                      act=act, aux=aux, mul_mode=mul)
         return out
 
-    def forward_backward(self, xr, repeat, bs, coef, dimg_accum, loss_accum):
-        """xr: [repeat*bs, H, W, 3] fp32 NHWC in [0,1].  loss_accum[0] += -coef * div;  dimg_accum += -coef * d(div)/d(xr)."""
-        N, H, W, _ = xr.shape
-        assert N == repeat * bs
-        xn = self._new(N, H, W, 3, dtype=F32)
-        call("normalize3_fwd", xr, xn, N * H * W * 3, C.addressof(self._mean), C.addressof(self._std))
-        # ---- forward, keeping every post-ReLU activation (it is both the next layer's input and the ReLU mask)
+    def features(self, xn):
+        """xn: [N, H, W, 3] fp32 NHWC, already normalised.  Returns (taps, saved): taps = [(slice, feats [N*h*w, c] bf16, h, w, c)] at
+        relu1_2, relu2_2, relu3_3, relu4_3, relu5_3; every post-ReLU activation is kept (it is both the next layer's input and
+        the ReLU mask of the backward)."""
+        N, H, W, _ = xn.shape
         acts = {}
         col = self._new(N * H * W, 32)
         call("im2col3x3_cin3", xn, col, N, H, W)
@@ -110,13 +156,11 @@ class DiversityEngine:
                 acts[i] = h
                 ch = cout
             taps.append((s, h, hh, ww, ch))
-        # ---- per-tap diversity + its gradient w.r.t. the tap activation
-        dtap = {}
-        for s, f, th, tw, tc in taps:
-            d = self._new(N * th * tw, tc)
-            call("diversity_tap", f, loss_accum, d, repeat, bs, th * tw, tc, -coef)
-            dtap[s] = d
-        # ---- backward through the VGG stack (frozen: dgrad only), deepest slice first
+        return taps, dict(N=N, H=H, W=W, acts=acts, pools=pools, taps=taps)
+
+    def features_bwd(self, saved, dtap):
+        """dtap: {slice: gradient w.r.t. that tap, [N*h*w, c] bf16} -> gradient w.r.t. xn, [N*H*W, 3] fp32 (frozen net: dgrad only)."""
+        N, H, W, acts, pools, taps = saved["N"], saved["H"], saved["W"], saved["acts"], saved["pools"], saved["taps"]
         g = None
         for s, idxs in reversed(SLICES):
             _, f, th, tw, tc = taps[s - 1]
@@ -138,10 +182,27 @@ class DiversityEngine:
                 gp = self._new(N * sh * sw, sc)
                 call("maxpool2x2_bwd", src, g, gp, N, sh, sw, sc)
                 g = gp
-        # first layer: ReLU mask, then 64 -> 3 dgrad (fp32 out), then the normalisation's 1/std, accumulated into d(xr)
+        # first layer: ReLU mask, then 64 -> 3 dgrad (fp32 out)
         g = self._relu_mask(g, acts[0])
         dxn = self._new(N * H * W, 3, dtype=F32)
         ops.gemm(g, self.pk["slice1.0.wT"], dxn, N * H * W, 3, 9 * 64, a_mode=ops.CONV3X3, conv=(N, H, W, 64))
+        return dxn
+
+    def forward_backward(self, xr, repeat, bs, coef, dimg_accum, loss_accum):
+        """xr: [repeat*bs, H, W, 3] fp32 NHWC in [0,1].  loss_accum[0] += -coef * div;  dimg_accum += -coef * d(div)/d(xr)."""
+        N, H, W, _ = xr.shape
+        assert N == repeat * bs
+        xn = self._new(N, H, W, 3, dtype=F32)
+        call("normalize3_fwd", xr, xn, N * H * W * 3, C.addressof(self._mean), C.addressof(self._std))
+        taps, saved = self.features(xn)
+        # ---- per-tap diversity + its gradient w.r.t. the tap activation
+        dtap = {}
+        for s, f, th, tw, tc in taps:
+            d = self._new(N * th * tw, tc)
+            call("diversity_tap", f, loss_accum, d, repeat, bs, th * tw, tc, -coef)
+            dtap[s] = d
+        # ---- backward through the VGG stack, then the normalisation's 1/std, accumulated into d(xr)
+        dxn = self.features_bwd(saved, dtap)
         call("normalize3_bwd", dxn, dimg_accum, N * H * W * 3, C.addressof(self._std))
 
     def _relu_mask(self, g, post):

@@ -386,3 +386,26 @@ def test_train_step_with_repeat_and_diversity_vs_reference_expression(abi_on_cpu
     eng = net.engine()
     big = [(n, gv) for (n, q), gv in zip(net.named_parameters(), eng.grad_views) if q.numel() >= 2048]
     assert min(cos(gv, p[n].grad) for n, gv in big) > 0.95      # the bf16 VGG stack on 32 x 32 images adds to the step's rounding noise
+
+
+def test_lpips_net_call_surface_vs_oracle_taps(abi_on_cpu, monkeypatch):
+    """`LPIPS().net(x)` as the reference's loop calls it (main.py:778): the five VGG16 taps and the gradient w.r.t. x"""
+    import oracle.lpips as ol
+    from feed_forward_vqgan_clip_b200 import api, lpips
+    monkeypatch.setattr(lpips, "call", abi_model.call)
+    sd = ol.init_vgg_state_dict(seed=3)
+    model = api.LPIPS()
+    model.net.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 32, 32, generator=g)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    mine, ref = model.net(xa), ol.vgg_taps(sd, xb)
+    assert len(mine) == 5
+    la = lb = 0
+    for i, (a, b) in enumerate(zip(mine, ref)):
+        assert a.shape == b.shape and float((a - b).detach().abs().max()) <= 3e-2 * float(b.detach().abs().max()), i
+        w = torch.randn(b.shape, generator=g)
+        la, lb = la + (api.normalize_tensor(a) * w).sum(), lb + (ol.normalize_tensor(b) * w).sum()
+    la.backward()
+    lb.backward()
+    assert cos(xa.grad, xb.grad) > 0.98

@@ -69,7 +69,9 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     folder = tmp_path / tag
     folder.mkdir()
     g = torch.Generator().manual_seed(0)
+    extra_cfg = dict(extra_cfg)
     tokens = extra_cfg.pop("tokens", False)
+    lpips_factory = extra_cfg.pop("lpips_factory", None)
     if tokens:                                               # token ids (dtype long): train() calls perceptor.encode_text (main.py:733)
         data = torch.randint(1, 90, (steps * 2, 77), generator=g)
         data[torch.arange(steps * 2), torch.randint(5, 77, (steps * 2,), generator=g)] = 99          # EOT = the largest id
@@ -104,6 +106,9 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     monkeypatch.setattr(ref, "synth", api.synth)
     monkeypatch.setattr(ref, "clamp_with_grad", api.clamp_with_grad)
     monkeypatch.setattr(ref, "decode", lambda ids: " ".join(str(i) for i in ids))      # clip's BPE decoder (progress.txt only) is stubbed
+    if lpips_factory is not None:                            # main.py:30-31,532-537: LPIPS / normalize_tensor come from taming
+        monkeypatch.setattr(ref, "LPIPS", lpips_factory)
+        monkeypatch.setattr(ref, "normalize_tensor", api.normalize_tensor)
     losses = []
 
     class Writer:                                            # SummaryWriter stand-in that records the logged scalars
@@ -230,3 +235,42 @@ def test_reference_train_loop_data_parallel_through_the_horovod_shim(tmp_path):
     assert (w0 == w1).all()                                  # identical replicas after broadcast + 2 averaged steps
     assert len(l0) == 2 and l1 == []                         # rank 0 is the only logger (main.py:620-624)
     assert "checkpoint.th" in files0 and "checkpoint.th" not in files1
+
+
+def test_reference_train_loop_with_diversity_term_on_api_lpips(monkeypatch, tmp_path):
+    """config #5's extras in the reference's own loop: repeat = 2 and diversity_coef > 0 make train() build `LPIPS()` and call
+    `lpips.net((xr - mean) / std)` + `normalize_tensor` (main.py:532-537,776-791).  Run once with api.LPIPS (VGG16 taps on the
+    engines) and once with a plain-torch LPIPS stand-in built from the oracle's tap network on the SAME weights: the logged
+    losses (dists - diversity_coef * div) agree."""
+    import abi_model
+    import oracle.lpips as ol
+    ref = _import_reference_main()
+    from feed_forward_vqgan_clip_b200 import api, lpips
+    monkeypatch.setattr(lpips, "call", abi_model.call)
+    sd_l = ol.init_vgg_state_dict(seed=3)
+
+    def ours_lpips():
+        m = api.LPIPS()
+        m.net.load_state_dict(sd_l)
+        return m
+
+    class TorchLPIPS(torch.nn.Module):                       # what taming's LPIPS().net computes, in plain torch
+        def __init__(self):
+            super().__init__()
+            self.net = lambda x: ol.vgg_taps(sd_l, x)
+
+        def load_from_pretrained(self):
+            return self
+
+    def mapper(config):
+        net = api.build_model(config, vq_channels=64)
+        with torch.no_grad():
+            net.final_proj.weight.mul_(6.0)
+        return net
+
+    extra = dict(model_type="mlp_mixer", dim=64, repeat=2, diversity_coef=5.0, noise_dim=8)
+    _, loss_a, folder_a = _run(ref, monkeypatch, tmp_path, "api_lpips", mapper, 2, dict(extra, lpips_factory=ours_lpips))
+    _, loss_b, _ = _run(ref, monkeypatch, tmp_path, "torch_lpips", mapper, 2, dict(extra, lpips_factory=TorchLPIPS))
+    assert len(loss_a) == len(loss_b) == 2
+    for a, b in zip(loss_a, loss_b):
+        assert abs(a - b) <= 3e-2 * abs(b) + 1e-3, (loss_a, loss_b)
