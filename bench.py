@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="prompts per GPU")
-    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--cpu-sample-batch", type=int, default=2, help="prompts per CPU step of the reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--bucket-layers", type=int, default=None,
@@ -375,7 +375,7 @@ def main():
     if roof is not None:
         line["roofline"] = roof
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(1, 1, args.cpu_sample_batch)
+        r = cpu_reference(2, 1, args.cpu_sample_batch)          # ~10 s of host time: 1 warm-up + 2 timed steps of 2 prompts
         line["cpu_baseline"] = {"value": r["value"], "unit": "prompts/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(line))
     _finish(world)
