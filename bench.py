@@ -177,6 +177,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--bucket-layers", type=int, default=None,
                     help="N>1: mixer layers per gradient all-reduce bucket (overlapped with backward); 0 = one all-reduce after backward")
+    ap.add_argument("--tail-overlap", action="store_true",
+                    help="N>1: run Adam on the already-reduced slices while the last gradient bucket is in flight (opt-in, unmeasured)")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0,
+                    help="N>1: cap the CTAs NCCL may use (NCCL_MAX_CTAS) so its kernels take fewer SMs from the persistent GEMMs they overlap; 0 = NCCL's default")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -207,6 +211,8 @@ def main():
     pg = None
     if world > 1:
         import torch.distributed as dist
+        if args.nccl_max_ctas > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas)
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
 
@@ -214,6 +220,7 @@ def main():
     ts = build_b200(dev, B, world, pg, rank=rank)
     if args.bucket_layers is not None:
         ts.bucket_layers = args.bucket_layers
+    ts.tail_overlap = bool(args.tail_overlap)
     x_host = [synthetic_embeddings(B, 1000 + 7919 * rank + i).pin_memory() for i in range(4)]
 
     ops.reset_launch_count()

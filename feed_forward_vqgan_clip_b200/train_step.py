@@ -65,19 +65,32 @@ class FusedAdam:
             self.ema = self.eng.arena.clone()
         self.hyper[15:16].fill_(float(decay))
 
-    def apply(self):
-        """tick the device-side step counter (bias corrections, lr, clip coefficient) and update parameters + bf16 shadow
-        (+ EMA) in one pass."""
+    def tick(self):
+        """advance the device-side step counter: bias corrections, lr of this step, clip coefficient (needs the whole gradient)"""
         e = self.eng
         self.t += 1
         if self.clip > 0:
             call("sumsq", e.grad, self.hyper[10:11], e.total)
         call("adam_tick", self.hyper)
+
+    def step_range(self, lo, hi):
+        """the update of arena elements [lo, hi) (8-element aligned slots): parameters, moments, bf16 shadow (+ EMA)"""
+        e = self.eng
+        if hi <= lo:
+            return
+        shadow = e.shadow[lo:hi] if e.shadow is not None else None
         if self.ema is not None:
-            call("adam_step_ema", e.arena, e.grad, self.m, self.v, e.shadow, self.ema, e.total, self.hyper)
+            call("adam_step_ema", e.arena[lo:hi], e.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], shadow, self.ema[lo:hi],
+                 hi - lo, self.hyper)
         else:
-            call("adam_step", e.arena, e.grad, self.m, self.v, e.shadow, e.total, self.hyper)
+            call("adam_step", e.arena[lo:hi], e.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], shadow, hi - lo, self.hyper)
         e.ext_shadow_fresh = True
+
+    def apply(self):
+        """tick the device-side step counter (bias corrections, lr, clip coefficient) and update parameters + bf16 shadow
+        (+ EMA) in one pass."""
+        self.tick()
+        self.step_range(0, self.eng.total)
 
     # ---- checkpoint I/O in torch.optim.Adam's own format (main.py:593-596 loads it, :911 saves it as opt.th)
     def _slices(self):
@@ -184,6 +197,9 @@ class TrainStep:
         # WHILE backward is still producing the earlier layers' gradients (the reference gets this from Horovod's hooks,
         # main.py:627); engines without per-layer completion callbacks fall back to one all-reduce after backward
         self.bucket_layers = 8
+        # opt-in (not yet measured on a GPU): start Adam on the slices whose all-reduce has already been issued while the last
+        # bucket (head of the arena + late ranges) is still in flight; needs the clip coefficient off (it wants the whole norm)
+        self.tail_overlap = False
         self.comm_stream = torch.cuda.Stream(device=self.dev) if world_size > 1 else None
         cb = self.dec.codebook
         self.z_lo, self.z_hi = float(cb.min()), float(cb.max())          # main.py:645-646,763 (global scalars)
@@ -255,6 +271,19 @@ class TrainStep:
                     reduce_bucket(buckets[first_layer_of_bucket[k]])
 
             mix.backward(sv_m, dz, on_layer_done=on_layer_done)
+            if self.tail_overlap and self.opt.clip == 0 and len(buckets) > 1:
+                early = torch.cuda.Event()
+                early.record(comm)                    # every bucket but the last has been issued on the side stream
+                reduce_bucket(buckets[-1])
+                del sv_m
+                self.opt.tick()
+                main.wait_event(early)
+                for lo, hi in sorted(s_ for b in buckets[:-1] for s_ in b):
+                    self.opt.step_range(lo, hi)       # overlaps the last bucket's all-reduce
+                main.wait_stream(comm)
+                for lo, hi in buckets[-1]:
+                    self.opt.step_range(lo, hi)
+                return self.loss
             reduce_bucket(buckets[-1])
             main.wait_stream(comm)
         else:

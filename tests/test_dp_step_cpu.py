@@ -76,7 +76,7 @@ def _mapper(name):
     return net
 
 
-def _build(world, pg, bucket_layers, mapper="mixer"):
+def _build(world, pg, bucket_layers, mapper="mixer", tail_overlap=False):
     import oracle.clip_vit as oclip
     import oracle.vqgan as ovq
     from feed_forward_vqgan_clip_b200 import clip_vit, train_step, vqgan
@@ -89,6 +89,7 @@ def _build(world, pg, bucket_layers, mapper="mixer"):
     ts = train_step.TrainStep(net, vq.eval().requires_grad_(False), clip.eval().requires_grad_(False), cutn=CUTN, lr=1e-3,
                               cut_size=CUT, world_size=world, process_group=pg)
     ts.bucket_layers = bucket_layers
+    ts.tail_overlap = tail_overlap
     return net, ts
 
 
@@ -99,7 +100,7 @@ def _inputs():
     return x, sample_params(CUTN * B, CUT, g)
 
 
-def _worker(rank, world, port, bucket_layers, mapper, q):
+def _worker(rank, world, port, bucket_layers, mapper, tail_overlap, q):
     try:
         import sys
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -112,7 +113,7 @@ def _worker(rank, world, port, bucket_layers, mapper, q):
         real = dist.all_reduce
         dist.all_reduce = lambda t, *a, **k: (calls.append(t.numel()), real(t, *a, **k))[1]
         torch.distributed.all_reduce = dist.all_reduce
-        net, ts = _build(world, dist.group.WORLD, bucket_layers, mapper)
+        net, ts = _build(world, dist.group.WORLD, bucket_layers, mapper, tail_overlap)
         x, prm = _inputs()
         lo, hi = parallel.shard_range(B, rank, world)
         loss = float(ts.step(x[lo:hi].contiguous(), None, parallel.shard_cutout_params(prm, CUTN, B, lo, hi)))
@@ -126,12 +127,12 @@ def _worker(rank, world, port, bucket_layers, mapper, q):
         q.put((rank, "ERROR", traceback.format_exc()))
 
 
-def _run(bucket_layers, mapper="mixer"):
+def _run(bucket_layers, mapper="mixer", tail_overlap=False):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, bucket_layers, mapper, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, bucket_layers, mapper, tail_overlap, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
@@ -184,3 +185,6 @@ def test_single_allreduce_form_gives_the_same_reduced_gradient():
     res_s = _run(bucket_layers=0)                            # one all-reduce of the whole arena after backward
     assert len(res_s[0][4]) == 1 and res_s[0][4][0] == res_s[0][5]
     assert torch.allclose(res_b[0][2], res_s[0][2], rtol=1e-5, atol=1e-7)
+    # opt-in: Adam on the already-reduced slices while the last bucket is in flight — the same update, slice by slice
+    res_t = _run(bucket_layers=2, tail_overlap=True)
+    assert torch.equal(res_t[0][2], res_b[0][2]) and torch.equal(res_t[0][3], res_b[0][3]) and torch.equal(res_t[1][3], res_b[1][3])
