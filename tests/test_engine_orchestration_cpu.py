@@ -409,3 +409,39 @@ def test_lpips_net_call_surface_vs_oracle_taps(abi_on_cpu, monkeypatch):
     la.backward()
     lb.backward()
     assert cos(xa.grad, xb.grad) > 0.98
+
+
+def test_config2_full_architecture_step_orchestration_vs_oracle(abi_on_cpu, monkeypatch):
+    """BASELINE config #2's real architecture — MLP-Mixer 32 x 1024, the full VQGAN f16/16384 decoder, CLIP ViT-B/32, 256 x 256,
+    8 cutouts — one prompt through TrainStep's host logic (the halo conv entry points at 128^2 and 256^2 with their GroupNorm
+    epilogue hand-offs, the 50-token fused attention entry point, the 16384-code VQ ...) against the oracle step: ~45 s."""
+    import oracle.vqgan as ovq
+    from oracle.train_step import OracleTrainer
+    from feed_forward_vqgan_clip_b200 import cutouts, train_step, vqgan
+    for mod in (vqgan, cutouts, train_step):
+        monkeypatch.setattr(mod, "call", abi_model.call)
+
+    def r16(sd):
+        return {k: (v.to(torch.bfloat16).float() if v.dim() >= 2 else v.clone()) for k, v in sd.items()}
+    sd_m = r16(omix.init_mixer_state_dict(512, 16, 256, 1024, 32, seed=0))
+    sd_v, sd_c = r16(ovq.init_vqgan_state_dict(seed=1)), r16(oclip.init_clip_state_dict(seed=2))
+    net = mixer.Mixer(input_dim=512, image_size=16, channels=256, patch_size=1, dim=1024, depth=32)
+    net.load_state_dict(sd_m)
+    vq = vqgan.VQModel()
+    vq.load_state_dict(sd_v)
+    clip = clip_vit.CLIP()
+    clip.visual.load_state_dict(sd_c)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(1, 512, generator=g) * 0.45).to(torch.bfloat16).float()
+    prm = cutouts.sample_params(8, 224, g)
+    ts = train_step.TrainStep(net, vq.eval().requires_grad_(False), clip.eval().requires_grad_(False), cutn=8, lr=1e-3)
+    loss = float(ts.step(x, None, prm))
+    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 256, cutn=8)
+    ref = otr.step(x, x, prm, force_idx=ts.last_indices.long())
+    assert abs(loss - ref) < 1e-2 * abs(ref), (loss, ref)
+    d = (otr.last_z.detach().reshape(1, 256, 256).permute(0, 2, 1).reshape(256, 256).clamp(otr.z_lo, otr.z_hi)[:, None, :]
+         - sd_v["quantize.embedding.weight"][None]).pow(2).sum(-1)                      # the oracle's own arg-min on its own z
+    assert (d.argmin(1) == ts.last_indices.long().view(-1)).float().mean() > 0.95       # 32 bf16 layers flip a few near-ties
+    eng = net.engine()
+    cs = [cos(gv, otr.grads[n]) for (n, p), gv in zip(net.named_parameters(), eng.grad_views) if p.numel() >= 65536]
+    assert len(cs) > 100 and min(cs) > 0.97, min(cs)

@@ -120,3 +120,48 @@ def test_full_size_vq_rows_are_nearest_codebook_rows():
     chosen = d.gather(1, idx[rows, None])[:, 0]
     assert float((chosen - best).max()) <= 2e-3, float((chosen - best).max())     # a different pick must be a numerical tie
     assert (d.argmin(dim=1) == idx[rows]).float().mean().item() >= 0.999
+
+
+def test_config2_full_architecture_step_vs_oracle():
+    """Parity at BASELINE config #2's real architecture (not a scaled-down stand-in): Mixer 32 x 1024, the full VQGAN f16/16384
+    decoder, CLIP ViT-B/32, 256 x 256, 8 cutouts, 2 prompts — the CUDA step against the CPU oracle step on the same bf16-rounded
+    weights, embeddings and augmentation parameters.  The oracle needs a few seconds per prompt on the box's host cores.
+    Tolerances (bf16 compute, 32 + 12 layers deep, against fp32): loss 2 %, code indices 95 %, gradient cosine 0.95 — the CPU
+    statement of the ABI (tests/abi_model.py), which rounds to bf16 at the same places, gives 1e-4, 98.4 % and 0.987."""
+    import oracle.clip_vit as oclip
+    import oracle.mixer as omix
+    import oracle.vqgan as ovq
+    from oracle.train_step import OracleTrainer
+
+    def r16(sd):
+        return {k: (v.to(torch.bfloat16).float() if v.dim() >= 2 else v.clone()) for k, v in sd.items()}
+    sd_m = r16(omix.init_mixer_state_dict(512, 16, 256, 1024, 32, seed=0))
+    sd_v, sd_c = r16(ovq.init_vqgan_state_dict(seed=1)), r16(oclip.init_clip_state_dict(seed=2))
+    net = Mixer(**MIXER)
+    net.load_state_dict(sd_m)
+    vq = VQModel()
+    vq.load_state_dict(sd_v)
+    clip = CLIP()
+    clip.visual.load_state_dict(sd_c)
+    net, vq, clip = net.to(DEV), vq.to(DEV).eval().requires_grad_(False), clip.to(DEV).eval().requires_grad_(False)
+    nb = 2
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(nb, 512, generator=g) * 0.45).to(torch.bfloat16).float()
+    prm = sample_params(CUTN * nb, CUT, g)
+    ts = TrainStep(net, vq, clip, cutn=CUTN, lr=1e-3)
+    loss = float(ts.step(x.to(DEV), None, prm).item())
+    idx = ts.last_indices.cpu().long()
+    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 256, cutn=CUTN)
+    ref = otr.step(x, x, prm, force_idx=idx)          # gradients on the codes the CUDA step picked (the arg-min is discontinuous)
+    assert abs(loss - ref) <= 2e-2 * abs(ref), (loss, ref)
+    cb = sd_v["quantize.embedding.weight"]
+    zt = otr.last_z.detach().reshape(nb, 256, 256).permute(0, 2, 1).reshape(nb * 256, 256).clamp(otr.z_lo, otr.z_hi)
+    own = torch.cat([(zt[i:i + 128, None, :] - cb[None]).pow(2).sum(-1).argmin(1) for i in range(0, zt.shape[0], 128)])
+    assert (own == idx.view(-1)).float().mean().item() >= 0.95
+    eng = net.engine()
+    worst = 1.0
+    for (n, p), gv in zip(net.named_parameters(), eng.grad_views):
+        if p.numel() >= 65536:
+            a, b = gv.detach().float().cpu().flatten().double(), otr.grads[n].flatten().double()
+            worst = min(worst, float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300)))
+    assert worst >= 0.95, worst
