@@ -445,3 +445,37 @@ def test_config2_full_architecture_step_orchestration_vs_oracle(abi_on_cpu, monk
     eng = net.engine()
     cs = [cos(gv, otr.grads[n]) for (n, p), gv in zip(net.named_parameters(), eng.grad_views) if p.numel() >= 65536]
     assert len(cs) > 100 and min(cs) > 0.97, min(cs)
+
+
+@pytest.mark.parametrize("which", ["vitgan_32x1024", "xtransformer_256x16_s32", "simple_vitgan_4x1024"])
+def test_full_size_mappers_orchestration_vs_oracle(abi_on_cpu, which):
+    """The other BASELINE mappers at their real sizes — config #3's VitGAN (dim 1024, 32 blocks, 6 heads of 170: the padded
+    1020-wide projections), config #4's X-transformer (dim 256, depth 16, 1024 tokens for a 512 x 512 image) and the
+    simple_vitgan variant at dim 1024 (head dimension 170 padded to 176) — forward and every parameter gradient vs the oracle."""
+    torch.manual_seed(21)
+    g = torch.Generator().manual_seed(22)
+    if which == "vitgan_32x1024":
+        net = vitgan_mapper.Generator(initialize_size=2, dim=1024, blocks=32, num_heads=6, out_channels=256, input_dim=512)
+        fwd, shape = (lambda sd, x: ovit.vitgan_forward(sd, x, 256, 6)), (2, 256, 16, 16)
+    elif which == "xtransformer_256x16_s32":
+        net = xtransformer.XTransformer(input_dim=512, image_size=32, channels=256, dim=256, depth=16, heads=6, initial_proj=True,
+                                        add_input=False)
+        fwd, shape = (lambda sd, x: oxt.xtransformer_forward(sd, x, 32, 256, 6)), (2, 256, 32, 32)
+    else:
+        net = simple_vitgan_mapper.SimpleGenerator(size=16, dim=1024, blocks=4, num_heads=6, out_channels=256, input_dim=512)
+        fwd, shape = (lambda sd, x: ovit.simple_vitgan_forward(sd, x, 256, 6)), (2, 256, 16, 16)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() >= 2 and p.numel() > 1:
+                p.copy_(p.to(torch.bfloat16).float())
+    x = (torch.randn(2, 512, generator=g) * 0.45).to(torch.bfloat16).float()
+    sd = {k: v.clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    y = net(x)
+    yr = fwd(sd, x)
+    assert y.shape == yr.shape == shape
+    assert float((y - yr).detach().abs().max()) <= 3e-2 * float(yr.detach().abs().max())
+    w = torch.randn(shape, generator=g)
+    (y * w).sum().backward()
+    (yr * w).sum().backward()
+    worst = min(cos(p.grad, sd[n].grad) for n, p in net.named_parameters() if p.numel() >= 65536 and sd[n].grad is not None)
+    assert worst > 0.97, worst
