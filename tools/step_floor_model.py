@@ -42,7 +42,11 @@ def trace_step(B, cutn=8):
         o_sz = 4.0 if out.dtype == torch.float32 else 2.0
         extra = sum(2.0 for k_ in ("pre_out", "aux", "res") if kw.get(k_) is not None)
         by = a_bytes + 2.0 * N * K * b_n + M * N * nb * (o_sz * (2 if kw.get("atomic") else 1) + extra)
-        rec.append(("gemm", 2.0 * M * N * K * nb * segs, by))
+        modes = "AK AM AC".split()[kw.get("a_mode", 0)] + "," + "BK BM".split()[kw.get("b_mode", 0)]
+        epi = "act%d mul%d%s%s%s%s%s" % (kw.get("act", 0), kw.get("mul_mode", 0), " bias%d" % kw.get("bias_mode", 1) if kw.get("bias") is not None else "",
+                                         " res" if kw.get("res") is not None else "", " pre" if kw.get("pre_out") is not None else "",
+                                         " f32" if out.dtype == torch.float32 else "", " atomic" if kw.get("atomic") else "")
+        rec.append(("gemm", 2.0 * M * N * K * nb * segs, by, ("gemm %dx%dx%d b%d seg%d " + modes + " " + epi, (M, N, K, nb, segs))))
         return abi_model.gemm_raw(a, b, out, M, N, K, **kw)
 
     def call(name, *a):
@@ -57,7 +61,13 @@ def trace_step(B, cutn=8):
         by = sum(nbytes(t) for i, t in enumerate(a) if i not in ws)
         if name in ("adam_step", "adam_step_ema"):                      # p, m, v (and ema) are read AND written
             by += sum(nbytes(t) for t in (a[0], a[2], a[3])) + (nbytes(a[5]) if name == "adam_step_ema" else 0)
-        rec.append((("tcgen05 conv " if fl and name.startswith("conv") else "") + name, fl, float(by)))
+        if name.startswith("conv3x3_halo"):
+            res = a[9] if name == "conv3x3_halo_gnbwd" else a[10]
+            key = (name + " n%d %dx%d %d->%d" + (" res" if res is not None else ""), tuple(a[3:8]))
+        else:
+            ints = tuple(v for v in a if isinstance(v, int) and not isinstance(v, bool))[:5]
+            key = (name + " " + ",".join(["%d"] * len(ints)), ints)
+        rec.append((("tcgen05 conv " if fl and name.startswith("conv") else "") + name, fl, float(by), key))
         return abi_model.call(name, *a)
 
     ops.gemm_raw, ops.gemm, ops.call = abi_model.gemm_raw, gemm, call
@@ -89,13 +99,23 @@ def main():
         else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
     bw, tf = peaks["hbm_gbs"] * 1e9, peaks["bf16_tflops_sustained"] * 1e12
     r1, r2 = trace_step(1), trace_step(2)
-    assert [n for n, _, _ in r1] == [n for n, _, _ in r2], "the launch sequence must not depend on the batch size"
+    assert [r[0] for r in r1] == [r[0] for r in r2], "the launch sequence must not depend on the batch size"
     B = args.batch
     fam = collections.OrderedDict()
     tot = [0.0, 0.0, 0.0, 0]
-    for (name, f1, b1), (_, f2, b2) in zip(r1, r2):
+    shapes = collections.OrderedDict()
+    for (name, f1, b1, (fmt, i1)), (_, f2, b2, (_, i2)) in zip(r1, r2):
         fl, by = f1 + (f2 - f1) * (B - 1), b1 + (b2 - b1) * (B - 1)     # linear in the batch: value(B) = v1 + (v2 - v1) (B - 1)
         floor = max(fl / tf, by / bw)
+        try:
+            skey = fmt % tuple(u + (v - u) * (B - 1) for u, v in zip(i1, i2))
+        except TypeError:
+            skey = name
+        se = shapes.setdefault(skey, [0, 0.0, 0.0, 0.0])
+        se[0] += 1
+        se[1] += fl
+        se[2] += by
+        se[3] += floor
         key = "tcgen05 GEMM / conv" if (name == "gemm" or name.startswith("tcgen05")) else name
         e = fam.setdefault(key, [0, 0.0, 0.0, 0.0, 0.0])
         e[0] += 1
@@ -108,11 +128,14 @@ def main():
         tot[2] += floor
         tot[3] += 1
     # measured per-family times of the same launches: the committed CUDA-event breakdown of one eager step
-    measured, mpath = {}, os.path.join(ROOT, "profiles", "r01_step_breakdown_final.md")
+    import re
+    measured, mshape, mpath = {}, {}, os.path.join(ROOT, "profiles", "r01_step_breakdown_final.md")
     if os.path.exists(mpath):
         for ln in open(mpath):
             c = [x.strip() for x in ln.split("|")]
             if len(c) > 4 and c[2].isdigit():
+                k2 = re.sub(r" sp\d+ ", " ", c[1])                      # the split-K factor is a launch knob, not a shape
+                mshape[k2] = mshape.get(k2, 0.0) + float(c[3])
                 nm = c[1].split()[0]
                 nm = "tcgen05 GEMM / conv" if (nm == "gemm" or nm.startswith("conv3x3_halo")) else nm
                 measured[nm] = measured.get(nm, 0.0) + float(c[3])
@@ -133,6 +156,20 @@ def main():
                                                                          tot[2] * 1e3 / msum if msum else 0))
     lines += ["", "Step floor %.1f ms = %.0f prompts/s at B = %d; pure tensor time at the sustained peak %.1f ms; pure HBM time of all launches %.1f ms." %
               (tot[2] * 1e3, B / tot[2], B, tot[0] / tf * 1e3, tot[1] / bw * 1e3)]
+    lines += ["", "## Per launch shape (the 40 largest measured times; key as in `profiles/r01_step_breakdown_final.md` without the split factor)", "",
+              "| launch | n | GFLOP each | MB each | floor us each | measured us each | floor / measured | ms above the floor (all n) |",
+              "|---|---:|---:|---:|---:|---:|---:|---:|"]
+    rows = []
+    for k, (n, fl, by, fo) in shapes.items():
+        m = mshape.get(k)
+        if m:
+            rows.append((m - fo * 1e3, k, n, fl, by, fo, m))
+    for gap, k, n, fl, by, fo, m in sorted(rows, key=lambda r: -r[6])[:40]:
+        lines.append("| %s | %d | %.1f | %.1f | %.1f | %.1f | %.2f | %.2f |" % (k, n, fl / n / 1e9, by / n / 1e6, fo / n * 1e6, m / n * 1e3,
+                                                                        fo * 1e3 / m, gap))
+    unmatched = [k for k in shapes if k not in mshape]
+    lines += ["", "%d of %d launch shapes matched a measured row (%.1f of %.1f ms measured)." %
+              (len(rows), len(shapes), sum(r[6] for r in rows), sum(mshape.values()))]
     out = "\n".join(lines) + "\n"
     print(out)
     if args.md:
