@@ -136,5 +136,6 @@ def train_step(net, vq, perceptor, config=None, **kw):
                      tv_coef=_get(cfg, "tv_coef", 0.0) or 0.0, diversity_coef=_get(cfg, "diversity_coef", 0.0) or 0.0,
                      repeat=_get(cfg, "repeat", 1) or 1, clip_grad_norm=_get(cfg, "clip_grad_norm", None),
                      scheduler=_get(cfg, "scheduler", None), use_ema=bool(_get(cfg, "use_ema", False)),
+                     total_steps=kw.pop("total_steps", None) or _get(cfg, "max_steps", 0) or 0,      # main.py:704-705: T_max = config.max_steps
                      ema_decay=_get(cfg, "ema_decay", 0.995),
                      diversity_mode=_get(cfg, "diversity_mode", "between_same_prompts"), **kw)

@@ -479,3 +479,25 @@ def test_full_size_mappers_orchestration_vs_oracle(abi_on_cpu, which):
     (yr * w).sum().backward()
     worst = min(cos(p.grad, sd[n].grad) for n, p in net.named_parameters() if p.numel() >= 65536 and sd[n].grad is not None)
     assert worst > 0.97, worst
+
+
+def test_api_train_step_reads_the_reference_config_keys(abi_on_cpu, monkeypatch):
+    """api.train_step(net, vq, perceptor, config): the optimizer / loss keys of the reference's YAML (main.py:690-709) land in the
+    fused step — cutn, lr, l2 / tv coefficients, clip_grad_norm, scheduler: cosine with T_max = max_steps, use_ema / ema_decay"""
+    import oracle.vqgan as ovq
+    from feed_forward_vqgan_clip_b200 import api, cutouts, train_step, vqgan
+    for mod in (vqgan, cutouts, train_step):
+        monkeypatch.setattr(mod, "call", abi_model.call)
+    net = mixer.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=1)
+    vq = vqgan.VQModel(SMALL_VQ)
+    vq.load_state_dict(ovq.init_vqgan_state_dict(SMALL_VQ, seed=8))
+    clip = clip_vit.CLIP(SMALL_CLIP)
+    cfg = dict(cutn=3, lr=2e-4, l2_coef=0.1, tv_coef=0.2, clip_grad_norm=1.5, scheduler="cosine", max_steps=500, use_ema=True,
+               ema_decay=0.99, target_loss_coef=2.0, unknown_key="ignored")
+    ts = api.train_step(net, vq.eval().requires_grad_(False), clip.eval().requires_grad_(False), cfg, cut_size=64)
+    h = ts.opt.hyper
+    assert ts.cutn == 3 and ts.l2_coef == 0.1 and ts.tv_coef == 0.2 and ts.coef == 2.0
+    assert abs(float(h[0]) - 2e-4) < 1e-10 and float(h[9]) == 1.5 and float(h[13]) == 500.0 and abs(float(h[15]) - 0.99) < 1e-7
+    assert ts.opt.ema is not None
+    with pytest.raises(ValueError):                          # a cosine schedule without its horizon is a configuration error
+        api.train_step(net, vq, clip, dict(scheduler="cosine"), cut_size=64)
