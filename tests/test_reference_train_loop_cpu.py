@@ -274,3 +274,57 @@ def test_reference_train_loop_with_diversity_term_on_api_lpips(monkeypatch, tmp_
     assert len(loss_a) == len(loss_b) == 2
     for a, b in zip(loss_a, loss_b):
         assert abs(a - b) <= 3e-2 * abs(b) + 1e-3, (loss_a, loss_b)
+
+
+def test_fused_train_step_follows_the_reference_loop_step_for_step(monkeypatch, tmp_path):
+    """INTEGRATION.md's second mode: `TrainStep` replaces the BODY of the reference's loop (main.py:729-837).  The reference's own
+    train() runs 3 steps (autograd through this package's modules, torch.optim.Adam); the prompts it drew and the augmentation
+    parameters its MakeCutouts used are recorded and replayed through the fused step (explicit backward, FusedAdam) from the
+    same initial weights: the per-step losses coincide, i.e. three optimizer updates later the two trainings are still in step."""
+    import abi_model
+    import oracle.clip_vit as oclip
+    import oracle.vqgan as ovq
+    ref = _import_reference_main()
+    from feed_forward_vqgan_clip_b200 import api, clip_vit, cutouts, train_step, vqgan
+    monkeypatch.setattr(train_step, "call", abi_model.call)
+    steps, seen_inputs, seen_params = 3, [], []
+
+    class RecordingCutouts(api.MakeCutouts):
+        def forward(self, input):
+            prm = cutouts.sample_params(self.cutn * input.shape[0], self.cut_size, None, self.augs, self.noise_fac)
+            seen_params.append(prm)
+            self.next_params = prm
+            return super().forward(input)
+
+    def mapper(config):
+        net = api.build_model(config, vq_channels=64)
+        with torch.no_grad():
+            net.final_proj.weight.mul_(6.0)
+        # the progress block (main.py:920-945) runs one more forward on a fixed batch under no_grad: not a training step
+        net.register_forward_pre_hook(lambda mod, args: seen_inputs.append(args[0].detach().clone()) if torch.is_grad_enabled() else None)
+        mapper.initial = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        return net
+
+    orig_setattr = monkeypatch.setattr
+
+    class MP:                                                # _run installs api.MakeCutouts; put the recording subclass in its place
+        @staticmethod
+        def setattr(obj, name, value):
+            orig_setattr(obj, name, RecordingCutouts if (obj is ref and name == "MakeCutouts") else value)
+
+    _, ref_losses, _ = _run(ref, MP, tmp_path, "loop", mapper, steps, dict(model_type="mlp_mixer", dim=64))
+    assert len(ref_losses) == len(seen_inputs) == len(seen_params) == steps
+    # ---- the fused step on the recorded inputs, from the same initial weights
+    net = api.build_model(dict(model_type="mlp_mixer", dim=64, depth=1, clip_dim=64, vq_image_size=16, noise_dim=0), vq_channels=64)
+    net.load_state_dict(mapper.initial)
+    vq = vqgan.VQModel(SMALL_VQ)
+    vq.load_state_dict(ovq.init_vqgan_state_dict(SMALL_VQ, seed=8))
+    clip = clip_vit.CLIP(SMALL_CLIP)
+    clip.visual.load_state_dict(oclip.init_clip_state_dict(SMALL_CLIP, seed=9))
+    ts = api.train_step(net, vq.eval().requires_grad_(False), clip.eval().requires_grad_(False), dict(cutn=2, lr=1e-3), cut_size=64)
+    fused = [float(ts.step(x, None, prm)) for x, prm in zip(seen_inputs, seen_params)]
+    assert abs(fused[0] - ref_losses[0]) <= 1e-4 * abs(ref_losses[0])       # same weights, same forward: the first loss is the same number
+    # afterwards the two differ by bf16 rounding points (the loop normalises the cutouts in fp32 outside MakeCutouts, the fused
+    # step inside the cutout kernel before the bf16 store) amplified by Adam's sign-like first updates
+    for a, b in zip(fused, ref_losses):
+        assert abs(a - b) <= 2e-2 * abs(b), (fused, ref_losses)
