@@ -83,7 +83,9 @@ typedef struct {
   int two_cta;             /* 0 = auto, 1 = force the CTA-pair (cta_group::2) kernel, -1 = never */
   int epi_warps;           /* 0 = auto (16 for activation epilogues, compile-time epilogue where one exists),
                               8 = force the 8-warp epilogue, 16 = 16-warp epilogue with run-time flags only */
-  /* CONV3X3 (A is NHWC [conv_n][conv_h][conv_w][conv_c], pad 1, stride 1; M = n*h*w; K = 9*c) */
+  /* CONV3X3 (A is NHWC [conv_n][conv_h][conv_w][conv_c], pad 1, stride 1; M = n*h*w; K = 9*c).  Shape contract: c % 64 == 0, and a
+   * 128-pixel tile (one TMA box of whole rows) must tile one image: w % 128 == 0, or 128 % w == 0 and h % (128 / w) == 0 — i.e.
+   * images of at least 128 pixels (16 x 8 upwards); smaller ones are rejected with FFVC_ERR_ARG. */
   int conv_n, conv_h, conv_w, conv_c;
   /* epilogue */
   void* out;               /* bf16 or fp32 */

@@ -8,6 +8,9 @@ import torch
 import torch.nn.functional as F
 
 BF16, F32 = torch.bfloat16, torch.float32
+# shape contracts of the entry points are asserted like the library rejects them; a test that trades legal shapes for speed (tiny
+# images) must switch this off explicitly and say so
+STRICT_SHAPES = True
 
 
 def _dgelu(x):
@@ -36,6 +39,9 @@ def gemm_raw(a, b, out, M, N, K, *, a_mode=0, b_mode=0, a_ld=None, b_ld=None, a_
     if a_mode == 2:                                         # FFVC_OP_CONV3X3: implicit GEMM over an NHWC tensor, K = 9 * Cin
         n, h, w, c = conv
         assert M == n * h * w and K == 9 * c and batch == 1 and k_segs == 1 and not atomic
+        if STRICT_SHAPES:                                   # include/ffvc.h: a 128-pixel tile of whole rows must tile one image
+            assert c % 64 == 0, "conv: Cin must be a multiple of 64"
+            assert (w % 128 == 0) or (128 % w == 0 and h % (128 // w) == 0), "conv: H*W must tile by the pixel tile (%dx%d)" % (h, w)
         v = alpha * _conv3x3_packed(a, b, n, h, w, c, N)
         _epilogue(v, out, N if ldc is None else ldc, bias if bias_mode == 1 else None, res, aux, mul_mode, act)
         return out
@@ -45,6 +51,15 @@ def gemm_raw(a, b, out, M, N, K, *, a_mode=0, b_mode=0, a_ld=None, b_ld=None, a_
     if b_ld is None:
         b_ld = K if b_mode == 0 else N
     ldc = N if ldc is None else ldc
+    if STRICT_SHAPES:
+        # both operands travel by TMA (cuTensorMapEncodeTiled): 16-byte aligned base addresses and 16-byte multiples for every
+        # stride, i.e. multiples of 8 bf16 elements for row pitches, offsets and batch strides
+        for what, v in (("a_ld", a_ld), ("b_ld", b_ld), ("a_off", a_off), ("b_off", b_off), ("a_bs", a_bs), ("b_bs", b_bs),
+                        ("a_bs_in", a_bs_in), ("b_bs_in", b_bs_in)):
+            assert v % 8 == 0, "gemm: %s = %d is not a multiple of 8 elements (TMA 16-byte rule)" % (what, v)
+        assert (a.storage_offset() * a.element_size()) % 16 == 0 and (b.storage_offset() * b.element_size()) % 16 == 0, \
+            "gemm: operand base not 16-byte aligned"
+        assert splits == 1 or (out.dtype == F32 and atomic), "gemm: split-K needs fp32 atomic output"
     bi_n = max(1, batch_inner)
     for bidx in range(batch):
         bo, bi = bidx // bi_n, bidx % bi_n
@@ -197,6 +212,7 @@ def k_cast_f32_bf16_pitched(src, dst, rows, cols, ld):
 
 
 def k_vitgan_attn_fwd(qkv, out, probs, B, T, H, dh, ld_qkv, ld_out, scale):
+    assert not STRICT_SHAPES or (T <= 32 and dh <= 256), "vitgan_attn: T <= 32, dh <= 256 (include/ffvc.h)"
     x = qkv.view(B, T, ld_qkv)[:, :, :3 * H * dh].float().view(B, T, dh, 3, H).permute(3, 0, 4, 1, 2)
     q, k, v = x[0], x[1], x[2]
     P = torch.softmax(q @ k.transpose(-1, -2) * scale, -1)
@@ -247,6 +263,7 @@ def _heads(qkv, N, T, H, dh):
 
 
 def k_mha_small_fwd(qkv, out, N, T, H, dh, scale):
+    assert not STRICT_SHAPES or (T <= 64 and dh == 64), "mha_small: T <= 64, head_dim 64 (include/ffvc.h)"
     q, k, v = _heads(qkv, N, T, H, dh)
     o = torch.softmax(q @ k.transpose(-1, -2) * scale, -1) @ v
     out.view(-1)[:N * T * H * dh] = o.permute(0, 2, 1, 3).reshape(-1)

@@ -322,7 +322,7 @@ def test_lpips_diversity_engine_orchestration(abi_on_cpu, monkeypatch):
     net = lpips.LpipsVGG16()
     net.load_state_dict(sd)
     eng = net.engine()
-    R, bs, H = 2, 1, 128                      # 128 wide: slice 1 takes the halo conv entry point, the deeper slices the implicit GEMM
+    R, bs, H = 2, 1, 256                      # slices 1-2 take the halo conv entry point, the deeper ones the implicit GEMM (16 x 16 at relu5_3)
     g = torch.Generator().manual_seed(4)
     xr = torch.rand(R * bs, 3, H, H, generator=g)
     mean, std = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1), torch.tensor(CLIP_STD).view(1, 3, 1, 1)
@@ -350,6 +350,10 @@ def test_train_step_with_repeat_and_diversity_vs_reference_expression(abi_on_cpu
     from feed_forward_vqgan_clip_b200.cutouts import CLIP_MEAN, CLIP_STD
     for mod in (vqgan, cutouts, train_step, lpips):
         monkeypatch.setattr(mod, "call", abi_model.call)
+    # 32 x 32 images keep this test fast, but VGG16's deeper maps (8 x 8 and below) are smaller than the 128-pixel tile the conv
+    # entry point accepts: the shape contract is switched off here; legal sizes run in test_lpips_diversity_engine_orchestration
+    # (256 x 256) and on the GPU (test_ops_gpu.py, tools/run_configs.py config #5 at 512 x 512)
+    monkeypatch.setattr(abi_model, "STRICT_SHAPES", False)
     torch.manual_seed(11)
     net = mixer.Mixer(input_dim=64, image_size=16, channels=64, patch_size=1, dim=64, depth=1)
     with torch.no_grad():
@@ -397,7 +401,7 @@ def test_lpips_net_call_surface_vs_oracle_taps(abi_on_cpu, monkeypatch):
     model = api.LPIPS()
     model.net.load_state_dict(sd)
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(2, 3, 32, 32, generator=g)
+    x = torch.randn(1, 3, 256, 256, generator=g)            # the smallest image whose relu5_3 map (16 x 16) the conv entry point tiles
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     mine, ref = model.net(xa), ol.vgg_taps(sd, xb)
     assert len(mine) == 5

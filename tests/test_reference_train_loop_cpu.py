@@ -247,6 +247,9 @@ def test_reference_train_loop_with_diversity_term_on_api_lpips(monkeypatch, tmp_
     ref = _import_reference_main()
     from feed_forward_vqgan_clip_b200 import api, lpips
     monkeypatch.setattr(lpips, "call", abi_model.call)
+    # 32 x 32 images for speed: VGG16's deeper maps are then below the conv entry point's 128-pixel tile, so the model's shape
+    # contract is off here (legal sizes: test_engine_orchestration_cpu.py::test_lpips_*, 256 x 256)
+    monkeypatch.setattr(abi_model, "STRICT_SHAPES", False)
     sd_l = ol.init_vgg_state_dict(seed=3)
 
     def ours_lpips():

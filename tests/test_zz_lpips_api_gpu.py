@@ -17,7 +17,7 @@ def test_lpips_net_taps_and_input_gradient_vs_oracle():
     model.net.load_state_dict(sd)
     model = model.to("cuda")
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(2, 3, 128, 128, generator=g)
+    x = torch.randn(2, 3, 256, 256, generator=g)     # relu5_3 works on 16 x 16: the smallest map the implicit-GEMM conv tiles
     xa, xb = x.clone().cuda().requires_grad_(True), x.clone().requires_grad_(True)
     mine, ref = model.net(xa), ol.vgg_taps(sd, xb)
     assert len(mine) == 5
