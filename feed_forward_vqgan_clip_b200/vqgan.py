@@ -481,25 +481,34 @@ class _VQFn(torch.autograd.Function):
     """vector_quantize with the straight-through gradient of ReplaceGrad (main.py:105-116,134-138)."""
 
     @staticmethod
-    def forward(ctx, x, model):
-        eng = model.engine()
+    def forward(ctx, x, codebook, codeT, cnorm):
         shp = x.shape
         zf = x.reshape(-1, shp[-1]).contiguous().float()
         P, C = zf.shape
         idx = torch.empty(P, device=x.device, dtype=torch.int32)
         zq = torch.empty(P, C, device=x.device, dtype=F32)
-        call("vq_nearest", zf, eng.codebook, eng.codeT, eng.cnorm, idx, None, zq, None, P, C, eng.codebook.shape[0],
-             -3.0e38, 3.0e38)
+        call("vq_nearest", zf, codebook, codeT, cnorm, idx, None, zq, None, P, C, codebook.shape[0], -3.0e38, 3.0e38)
         ctx.mark_non_differentiable(idx)
         return zq.view(shp), idx.view(shp[:-1])
 
     @staticmethod
     def backward(ctx, g, _gi):
-        return g, None
+        return g, None, None, None
 
 
-def vector_quantize(x, model):
-    return _VQFn.apply(x, model)[0]
+def vector_quantize(x, codebook):
+    """main.py:134-138 `vector_quantize(x, codebook)`: x (..., C), codebook (ncodes, C) -> the nearest codes with the
+    straight-through gradient.  `codebook` may be the tensor the reference passes (`model.quantize.embedding.weight`) or the
+    VQModel itself, whose engine already holds the transposed copy and the code norms the search kernel wants."""
+    if hasattr(codebook, "engine"):
+        eng = codebook.engine()
+        cb, cbT, cn = eng.codebook, eng.codeT, eng.cnorm
+    else:
+        cb = codebook.detach().float().contiguous()
+        cbT = cb.t().contiguous()
+        cn = torch.empty(cb.shape[0], device=cb.device, dtype=F32)
+        call("rownorm2", cb, cn, cb.shape[0], cb.shape[1])
+    return _VQFn.apply(x, cb, cbT, cn)[0]
 
 
 def synth(model, z):

@@ -16,6 +16,20 @@
  *     thread-local message.  No exceptions cross the ABI.
  *   - activations are bf16 (NHWC / token-major), accumulation and normalisation statistics fp32,
  *     trainable parameters / gradients / Adam state fp32.
+ *
+ * Shape contracts (a call outside them returns FFVC_ERR_ARG / FFVC_ERR_UNSUPPORTED and launches nothing; tests/abi_model.py asserts
+ * the same conditions so that host code is checked against them without a GPU):
+ *   ffvc_gemm            operands travel by TMA: 16-byte aligned bases, every row pitch / offset / batch stride a multiple of 8
+ *                        elements; split-K needs the fp32 atomic output; block_n in {32, 64, 128, 256}, tile_m in {128, 256};
+ *                        CONV3X3: see ffvc_gemm_params
+ *   ffvc_conv3x3_halo*   w % 128 == 0, even h, cin % 64 == 0, cout <= 128 (the _gn / _gnbwd forms: cout == 128, bf16 out)
+ *   ffvc_layernorm_*     D % 8 == 0, D <= 2048; dgamma and dbeta both or neither; _bwd_sums: rows % rowsum_T == 0
+ *   ffvc_groupnorm_*     C % 8 == 0, C % G == 0, (C / 8) divides 256 (512 for the fused forms); backward: C / G in {1, 2, 4} or a
+ *                        multiple of 8
+ *   ffvc_vq_nearest      ncodes % 4 == 0, C in {64, 256};   ffvc_vq_nearest_tc: (3 * C) % 8 == 0, P < 2^31
+ *   ffvc_mha_small_*     head_dim == 64, 1 <= T <= 64;   ffvc_vitgan_attn_*: 1 <= T <= 32, dh <= 256
+ *   ffvc_upsample2x_*, ffvc_maxpool2x2_* (also even H, W), ffvc_conv3x3_cin3 (COUT <= 512): channels % 8 == 0
+ *   ffvc_softmax_*       ld >= n;   ffvc_cutout_final_*: P % patch == 0;   ffvc_diversity_tap: C <= 512;   ffvc_tv_loss: H, W >= 2
  */
 #ifndef FFVC_H_
 #define FFVC_H_

@@ -115,6 +115,7 @@ def k_add_bf16(a, b, y, n):
 
 
 def k_layernorm_fwd(x, g, b, y, mean, rstd, R, D, eps):
+    assert not STRICT_SHAPES or (D % 8 == 0 and D <= 2048), "layernorm: D must be a multiple of 8 and <= 2048"
     xf = x.reshape(-1)[:R * D].view(R, D).float()
     mu = xf.mean(1)
     var = xf.var(1, unbiased=False)
@@ -126,6 +127,7 @@ def k_layernorm_fwd(x, g, b, y, mean, rstd, R, D, eps):
 
 
 def k_layernorm_bwd(dy, x, g, mean, rstd, add, dx, dg, db, R, D):
+    assert not STRICT_SHAPES or (D % 8 == 0 and D <= 2048 and ((dg is None) == (db is None))), "layernorm_bwd: D % 8, D <= 2048, dgamma/dbeta both or none"
     xf = x.reshape(-1)[:R * D].view(R, D).float()
     dyf = dy.reshape(-1)[:R * D].view(R, D).float()
     mu, rs = mean.view(-1)[:R], rstd.view(-1)[:R]
@@ -154,6 +156,7 @@ def k_sln_mod_bwd(ds, n, w, gamma, beta, dn, dw_acc, dgamma, dbeta, total):
 
 
 def k_softmax_fwd(s, p, rows, n, ld):
+    assert ld >= n, "softmax: ld < n"
     S = s.reshape(-1)[:rows * ld].view(rows, ld)[:, :n]
     P = p.view(-1)[:rows * ld].view(rows, ld)
     P.zero_()
@@ -234,6 +237,7 @@ def k_vitgan_attn_bwd(qkv, probs, dout, dqkv, B, T, H, dh, ld_qkv, ld_out, scale
 
 
 def k_layernorm_bwd_sums(dy, x, g, mean, rstd, add, dx, dg, db, colsum_out, rowsum_out, rowsum_T, ws, R, D):
+    assert not STRICT_SHAPES or rowsum_out is None or R % rowsum_T == 0, "layernorm_bwd_sums: rows must be a multiple of rowsum_T"
     k_layernorm_bwd(dy, x, g, mean, rstd, add, dx, dg, db, R, D)
     d = dx.reshape(-1)[:R * D].view(R, D).float()
     if colsum_out is not None:
@@ -343,11 +347,18 @@ def k_groupnorm_finalize(ws, mean, rstd, N, HW, C, G, eps):
 
 
 def k_groupnorm_stats(x, ws, mean, rstd, N, HW, C, G, eps):
+    _gn_check(C, G)
     xf = x.reshape(-1)[:N * HW * C].view(N, HW, G, C // G).double()
     mu = xf.mean((1, 3))
     var = xf.var((1, 3), unbiased=False)
     mean.view(-1)[:N * G] = mu.reshape(-1).float()
     rstd.view(-1)[:N * G] = (var + eps).rsqrt().reshape(-1).float()
+
+
+def _gn_check(C, G, backward=False):
+    if STRICT_SHAPES:
+        assert C % 8 == 0 and C % G == 0 and 256 % (C // 8) == 0, "groupnorm: C % 8, C % G, (C / 8) | 256"
+        assert not backward or (C // G) in (1, 2, 4) or (C // G) % 8 == 0, "groupnorm_bwd: channels per group 1, 2, 4 or a multiple of 8"
 
 
 def _gn_parts(x, mean, rstd, gamma, beta, N, HW, C, G):
@@ -358,6 +369,7 @@ def _gn_parts(x, mean, rstd, gamma, beta, N, HW, C, G):
 
 
 def k_groupnorm_apply(x, mean, rstd, gamma, beta, y, N, HW, C, G, swish):
+    _gn_check(C, G)
     _, u = _gn_parts(x, mean, rstd, gamma, beta, N, HW, C, G)
     y.view(-1)[:N * HW * C] = (u * torch.sigmoid(u) if swish else u).reshape(-1)
 
@@ -381,6 +393,7 @@ def _gn_dx(g, xh, s0, s1, rstd, add, dx, N, HW, C, G):
 
 
 def k_groupnorm_bwd(dy, x, mean, rstd, gamma, beta, ws, add, dx, N, HW, C, G, swish):
+    _gn_check(C, G, backward=True)
     g, xh = _gn_g(dy, x, mean, rstd, gamma, beta, N, HW, C, G, swish)
     _gn_dx(g, xh, g.double().sum((1, 3)), (g * xh).double().sum((1, 3)), rstd, add, dx, N, HW, C, G)
 
@@ -393,17 +406,20 @@ def k_conv3x3_halo_gnbwd(x, w, out, n, h, wd, cin, cout, ldc, res, gn_x, gn_mean
 
 
 def k_groupnorm_bwd_apply(dy, x, mean, rstd, gamma, beta, sums, add, dx, N, HW, C, G, swish):
+    _gn_check(C, G, backward=True)
     g, xh = _gn_g(dy, x, mean, rstd, gamma, beta, N, HW, C, G, swish)
     s = sums.reshape(-1)[:N * G * 2].view(N, G, 2)
     _gn_dx(g, xh, s[..., 0], s[..., 1], rstd, add, dx, N, HW, C, G)
 
 
 def k_upsample2x_fwd(x, y, N, H, W, C):
+    assert not STRICT_SHAPES or C % 8 == 0, "upsample: C % 8 != 0"
     X = _nhwc(x, N, H, W, C)
     y.view(-1)[:N * 4 * H * W * C] = X.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(-1)
 
 
 def k_upsample2x_bwd(dy, dx, N, H, W, C):
+    assert not STRICT_SHAPES or C % 8 == 0, "upsample: C % 8 != 0"
     D = dy.reshape(-1)[:N * 4 * H * W * C].view(N, H, 2, W, 2, C).float()
     dx.view(-1)[:N * H * W * C] = D.sum((2, 4)).reshape(-1)
 
@@ -437,6 +453,7 @@ def k_rownorm2(x, out, rows, C):
 
 
 def k_vq_nearest(z, codebook, codeT, cnorm, idx, zq_bf16, zq_f32, zc, P, C, ncodes, lo, hi):
+    assert not STRICT_SHAPES or codeT is None or (ncodes % 4 == 0 and C in (64, 256)), "vq_nearest: ncodes % 4 == 0, embed dim 64 or 256"
     zz = z.reshape(-1)[:P * C].view(P, C).clamp(lo, hi)
     cb = codebook.reshape(-1)[:ncodes * C].view(ncodes, C)
     d = (zz.double() ** 2).sum(1, keepdim=True) + (cb.double() ** 2).sum(1)[None] - 2 * zz.double() @ cb.double().t()
@@ -458,6 +475,7 @@ def k_vq_prepare_codebook(codebook, csplit, cnorm, ncodes, C):
 
 
 def k_vq_nearest_tc(z, codebook, csplit, cnorm, zsplit, keys, idx, zq_bf16, zq_f32, zc, P, C, ncodes, lo, hi):
+    assert not STRICT_SHAPES or (3 * C) % 8 == 0, "vq_nearest_tc: 3*C must be a multiple of 8"
     k_vq_nearest(z, codebook, None, cnorm, idx, zq_bf16, zq_f32, zc, P, C, ncodes, lo, hi)
 
 
@@ -522,6 +540,7 @@ def _to_patches(img_nchw, N, P, patch):
 
 
 def k_cutout_final_fwd(cut1, hinv, sat, hue, noise, facs, erase, mean, std, patches, img_out, N, P, patch):
+    assert P % patch == 0, "cutout_final: cut size must be a multiple of the patch size"
     b = _final_stage(_nhwc(cut1, N, P, P, 3).permute(0, 3, 1, 2), hinv, sat, hue, erase, N, P)
     b = b + facs.reshape(-1)[:N].view(N, 1, 1, 1) * noise.reshape(-1)[:N * 3 * P * P].view(N, 3, P, P)       # main.py:223-225
     b = (b - _host3(mean).view(1, 3, 1, 1)) / _host3(std).view(1, 3, 1, 1)                                   # main.py:797
@@ -620,6 +639,7 @@ def k_normalize3_bwd(dy, dx_accum, n, std):
 
 
 def k_maxpool2x2_fwd(x, y, N, H, W, C):
+    assert not STRICT_SHAPES or (C % 8 == 0 and H % 2 == 0 and W % 2 == 0), "maxpool2x2: C % 8, H % 2, W % 2 must be 0"
     y.view(-1)[:N * (H // 2) * (W // 2) * C] = F.max_pool2d(_nhwc(x, N, H, W, C).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1)
 
 
@@ -635,6 +655,7 @@ def k_relu_mask(g, post, out, n):
 
 
 def k_diversity_tap(feats, loss_accum, dfeat, R, B, HW, C, scale):
+    assert not STRICT_SHAPES or C <= 512, "diversity_tap: C <= 512"
     """one VGG tap of main.py:778-782: normalize_tensor over channels, squared differences between the R samples of each prompt"""
     with torch.enable_grad():
         f = feats.reshape(-1)[:R * B * HW * C].view(R, B, HW, C).float().clone().requires_grad_(True)

@@ -155,6 +155,14 @@ def golden_glue():
     dists = 1.0 * ((H.sub(e).norm(dim=-1).div(2).arcsin().pow(2).mul(2)).mean())
     dists.backward()
     out["loss"] = dict(embed=embed.detach(), feats=feats, cutn=cutn, dists=dists.detach(), dembed=embed.grad.clone())
+    # (appended last so that the draws above keep their values) vector_quantize at a size the CUDA search accepts: 64-dim codes
+    cb64 = torch.randn(52, 64)
+    z64 = (torch.randn(2, 4, 4, 64) * 1.2).requires_grad_(True)
+    zq64 = ref.vector_quantize(z64, cb64)
+    w64 = torch.randn_like(zq64)
+    (zq64 * w64).sum().backward()
+    d64 = z64.detach().pow(2).sum(-1, keepdim=True) + cb64.pow(2).sum(1) - 2 * z64.detach() @ cb64.T
+    out["vq64"] = dict(cb=cb64, z=z64.detach(), zq=zq64.detach(), idx=d64.argmin(-1), w=w64, dz=z64.grad.clone())
     torch.save(out, os.path.join(OUT, "glue.pt"))
 
 

@@ -260,16 +260,17 @@ def test_reference_call_surface_glue_vs_reference_golden(abi_on_cpu, monkeypatch
     x = c["x"].clone().requires_grad_(True)
     api.clamp_with_grad(x, 0, 1).backward(c["g"])                       # main.py:118-132
     assert torch.equal(x.grad, c["gx"])
-    v = gold["vq"]
-    cfg = dict(SMALL_VQ, embed_dim=v["cb"].shape[1], n_embed=v["cb"].shape[0], z_channels=v["cb"].shape[1])
+    v = gold["vq64"]                                       # 52 codes of 64 dims: a size the search kernel accepts (C in {64, 256})
+    z = v["z"].clone().requires_grad_(True)
+    zq = api.vector_quantize(z, v["cb"])                   # main.py:134-138, the reference's own signature: (x, codebook)
+    assert torch.allclose(zq, v["zq"])
+    (zq * v["w"]).sum().backward()
+    assert torch.allclose(z.grad, v["dz"])                 # ReplaceGrad: straight-through
+    cfg = dict(SMALL_VQ, embed_dim=64, n_embed=52, z_channels=64)
     vq = vqgan.VQModel(cfg).eval().requires_grad_(False)
     with torch.no_grad():
         vq.quantize.embedding.weight.copy_(v["cb"])
-    z = v["z"].clone().requires_grad_(True)
-    zq = api.vector_quantize(z, vq)                                     # main.py:134-138
-    assert torch.allclose(zq, v["zq"])
-    (zq * v["w"]).sum().backward()
-    assert torch.allclose(z.grad, v["dz"])                              # ReplaceGrad: straight-through
+    assert torch.allclose(api.vector_quantize(v["z"], vq), v["zq"])      # ... or the model, whose engine caches the packed codebook
     # synth (main.py:140-143) on a real (small) decoder against the oracle, forward and gradient
     sd_v = ovq.init_vqgan_state_dict(SMALL_VQ, seed=4)
     vq = vqgan.VQModel(SMALL_VQ)
