@@ -109,6 +109,9 @@ def load_clip_model(model_type="ViT-B/32", path=None):
         model.visual.load_state_dict(vis)
         txt = {k: v.float() for k, v in sd.items() if k in model.text.state_dict()}
         model.text.load_state_dict(txt, strict=False)
+        if "logit_scale" in sd:                                       # used by the evaluation block (main.py:700,1192)
+            with torch.no_grad():
+                model.logit_scale.copy_(sd["logit_scale"].float())
     return model.eval().requires_grad_(False)
 
 

@@ -199,14 +199,14 @@ def test_load_clip_and_vqgan_checkpoints_in_the_published_formats(tmp_path):
     src = CLIP(VIT_B32, text_cfg=TEXT_B32)
     sd = {"visual." + k: v.half() for k, v in src.visual.state_dict().items()}
     sd.update({k: v.half() for k, v in src.text.state_dict().items()})
-    sd["logit_scale"] = torch.tensor(4.6)
+    sd["logit_scale"] = torch.tensor(3.25)
     torch.save(sd, tmp_path / "clip_sd.pt")
     m = api.load_clip_model("ViT-B/32", str(tmp_path / "clip_sd.pt"))
     k = "transformer.resblocks.3.mlp.c_fc.weight"
     assert m.visual.state_dict()[k].dtype == torch.float32
     assert torch.equal(m.visual.state_dict()[k], src.visual.state_dict()[k].half().float())
     assert torch.equal(m.text.state_dict()["text_projection"], src.text.state_dict()["text_projection"].half().float())
-    assert not any(p.requires_grad for p in m.parameters())
+    assert not any(p.requires_grad for p in m.parameters()) and abs(float(m.logit_scale) - 3.25) < 1e-6
 
     class Holder(torch.nn.Module):                       # a TorchScript archive only has to expose state_dict()
         def __init__(self):
