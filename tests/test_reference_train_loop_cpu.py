@@ -72,6 +72,9 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     extra_cfg = dict(extra_cfg)
     tokens = extra_cfg.pop("tokens", False)
     lpips_factory = extra_cfg.pop("lpips_factory", None)
+    if extra_cfg.pop("eval", False):                         # main.py:659-665,869-895: CLIP-score evaluation on held-out prompts
+        torch.save(torch.randn(3, 64, generator=g) * 0.45, folder / "eval.pkl")
+        extra_cfg["eval_path"] = str(folder / "eval.pkl")
     if tokens:                                               # token ids (dtype long): train() calls perceptor.encode_text (main.py:733)
         data = torch.randint(1, 90, (steps * 2, 77), generator=g)
         data[torch.arange(steps * 2), torch.randint(5, 77, (steps * 2,), generator=g)] = 99          # EOT = the largest id
@@ -109,7 +112,8 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     if lpips_factory is not None:                            # main.py:30-31,532-537: LPIPS / normalize_tensor come from taming
         monkeypatch.setattr(ref, "LPIPS", lpips_factory)
         monkeypatch.setattr(ref, "normalize_tensor", api.normalize_tensor)
-    losses = []
+    losses, scalars = [], {}
+    _run.last_scalars = scalars
 
     class Writer:                                            # SummaryWriter stand-in that records the logged scalars
         def __init__(self, folder):
@@ -118,6 +122,7 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
         def add_scalar(self, name, value, step):
             if name == "loss":
                 losses.append(float(value))
+            scalars.setdefault(name, []).append(float(value))
     monkeypatch.setattr(ref, "SummaryWriter", Writer)
     torch.manual_seed(123)                                   # mapper init, DataLoader shuffle and the augmentation draws
     ref.train(str(folder / "config.yaml"))
@@ -331,3 +336,21 @@ def test_fused_train_step_follows_the_reference_loop_step_for_step(monkeypatch, 
     # step inside the cutout kernel before the bf16 store) amplified by Adam's sign-like first updates
     for a, b in zip(fused, ref_losses):
         assert abs(a - b) <= 2e-2 * abs(b), (fused, ref_losses)
+
+
+def test_reference_train_loop_evaluation_block_on_this_package(monkeypatch, tmp_path):
+    """main.py:869-895 (run every log_interval steps when the config names an eval_path): no-grad mapper -> synth -> bilinear resize
+    -> perceptor.encode_image -> CLIP score with perceptor.logit_scale — the inference-side calls of the surface."""
+    ref = _import_reference_main()
+    from feed_forward_vqgan_clip_b200 import api
+
+    def mapper(config):
+        net = api.build_model(config, vq_channels=64)
+        with torch.no_grad():
+            net.final_proj.weight.mul_(6.0)
+        return net
+
+    _, losses, _ = _run(ref, monkeypatch, tmp_path, "eval", mapper, 2, dict(model_type="mlp_mixer", dim=64, eval=True))
+    sc = _run.last_scalars
+    assert len(losses) == 2 and len(sc["eval_dists"]) == 2 and len(sc["eval_clip_score"]) == 2
+    assert all(0 < d < 5 for d in sc["eval_dists"]) and all(abs(c) < 100.0 for c in sc["eval_clip_score"])
