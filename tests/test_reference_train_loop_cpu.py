@@ -129,12 +129,20 @@ def _run(ref, monkeypatch, tmp_path, tag, mapper_factory, steps, extra_cfg):
     return built[-1], losses, folder
 
 
-@pytest.mark.parametrize("model_type,tokens", [("mlp_mixer", False), ("vitgan", False), ("simple_vitgan", False), ("mlp_mixer", True)])
-def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_path, model_type, tokens):
+# main.py:690-693,758-773,831-834 (the reference's `scheduler: cosine` passes `verbose=` to CosineAnnealingLR, main.py:705, which
+# this image's torch 2.11 no longer accepts: its schedule is covered by the fused step's tests instead)
+LOSS_EXTRAS = dict(l2_coef=0.1, tv_coef=0.5, clip_grad_norm=1.0)
+
+
+@pytest.mark.parametrize("model_type,tokens,more", [("mlp_mixer", False, {}), ("vitgan", False, {}), ("simple_vitgan", False, {}),
+                                                    ("mlp_mixer", True, {}), ("mlp_mixer", False, LOSS_EXTRAS)])
+def test_reference_train_loop_runs_unmodified_on_this_package(monkeypatch, tmp_path, model_type, tokens, more):
     ref = _import_reference_main()
     from feed_forward_vqgan_clip_b200 import api
     steps = 3
-    extra = dict(model_type=model_type, dim=64 if model_type == "mlp_mixer" else 48, num_heads=3)
+    # `more`: the optional loss terms and optimizer extras — z feeds both the l2 term and the clamp, xr both the tv term and the
+    # cutouts, so autograd sums two gradient paths into each of this package's Functions
+    extra = dict(model_type=model_type, dim=64 if model_type == "mlp_mixer" else 48, num_heads=3, **more)
 
     def widen(net):                                          # spread z over the codebook range so VQ picks varied codes
         with torch.no_grad():
