@@ -37,7 +37,7 @@ def shard_cutout_params(prm, cutn, n_total, lo, hi):
     so a rank that owns prompts [lo, hi) needs rows {k * n_total + j : lo <= j < hi} of every per-cutout tensor, re-packed
     as k * (hi - lo) + (j - lo).  The erase rectangle is one per batch (RandomErasing(same_on_batch=True), main.py:189-190)
     and is shared.  With parameters sharded this way a data-parallel step over any world size reproduces the single-process
-    step on the global batch (tests/test_parallel_cpu.py, tests/test_zz_full_size_gpu.py)."""
+    step on the global batch (tests/test_parallel_cpu.py, tests/test_zz_d_full_size_gpu.py)."""
     out = {}
     for k, v in prm.items():
         if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == cutn * n_total:

@@ -185,7 +185,7 @@ def test_bucketed_allreduce_equals_single_allreduce_gloo():
 def test_sharded_step_reproduces_the_global_batch_step_oracle():
     """Size-independent property of the path: the train step is a mean over independent prompts, so the
     gradient of the global batch equals the average of the shard gradients when every shard gets ITS prompts' cutout
-    parameters (parallel.shard_cutout_params).  Checked here on the CPU oracle; tests/test_zz_full_size_gpu.py checks the
+    parameters (parallel.shard_cutout_params).  Checked here on the CPU oracle; tests/test_zz_d_full_size_gpu.py checks the
     same property on the CUDA path at BASELINE config #2's full size."""
     import oracle.clip_vit as oclip
     import oracle.mixer as omix
