@@ -358,8 +358,12 @@ class TrainStep:
         augmentation parameters of the NEXT call are drawn right after this step's graph launch, i.e. while the GPU works."""
         st = self.static
         B = st["inp"].shape[0]
+        if out_feats is None:
+            out_feats = inp
+        if self.repeat > 1 and inp.shape[0] * self.repeat == B:          # main.py:739-740: the prompt batch is repeated, as step() does
+            inp, out_feats = inp.repeat(self.repeat, 1), out_feats.repeat(self.repeat, 1)
         st["inp"].copy_(inp, non_blocking=True)
-        st["out"].copy_(inp if out_feats is None else out_feats, non_blocking=True)
+        st["out"].copy_(out_feats, non_blocking=True)
         presample = prm is None
         if presample:
             prm = self._next_prm if self._next_prm is not None else self.new_params(B)

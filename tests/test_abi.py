@@ -168,7 +168,7 @@ def test_replay_host_logic_draws_next_parameters_after_the_launch():
               sat=torch.zeros(N), hue=torch.zeros(N), erase=torch.zeros(4, dtype=torch.int32))
     events = []
     fake = SimpleNamespace(static=st, graph=SimpleNamespace(replay=lambda: events.append("launch")), loss=torch.zeros(1), cutn=cutn,
-                           cut_size=224, gen=torch.Generator().manual_seed(1), _next_prm=None)
+                           cut_size=224, gen=torch.Generator().manual_seed(1), _next_prm=None, repeat=1)
 
     def new_params(b):
         events.append("sample")
@@ -187,6 +187,11 @@ def test_replay_host_logic_draws_next_parameters_after_the_launch():
     kept = fake._next_prm
     TrainStep.replay(fake, x, None, explicit)
     assert events[-1] == "launch" and fake._next_prm is kept and torch.equal(st["persp_inv"], explicit["persp_inv"])
+    # repeat > 1 (main.py:739-740): a batch of B / repeat prompts is repeated into the static buffers like step() does
+    fake.repeat = 2
+    half = torch.randn(B // 2, 8)
+    TrainStep.replay(fake, half, None, explicit)
+    assert torch.equal(st["inp"], half.repeat(2, 1)) and torch.equal(st["out"], half.repeat(2, 1))
 
 
 def test_load_clip_and_vqgan_checkpoints_in_the_published_formats(tmp_path):
