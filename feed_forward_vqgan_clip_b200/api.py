@@ -2,6 +2,7 @@
 
     build_model(config)                      main.py:448-502   (model_type mlp_mixer, vitgan, simple_vitgan, xtransformer)
     load_vqgan_model(config_path, ckpt)      main.py:84-103
+    load_model(path)                         main.py:1273-1290 (checkpoint.th dictionaries and legacy pickled mappers)
     load_clip_model(name, path)              main.py:1308-1333 (OpenAI ViT-B/32 and OpenCLIP ViT-B-32 architectures)
     MakeCutouts / synth / clamp_with_grad / vector_quantize      main.py:105-229
     LPIPS / normalize_tensor                 main.py:30-31,532-537,776-787 (diversity term; `LPIPS().net(x)` -> the five VGG16 taps)
@@ -67,6 +68,25 @@ def build_model(config, vq_channels=256):
                             depth=_get(config, "depth"), heads=_get(config, "num_heads", 6),
                             initial_proj=_get(config, "initial_proj", True), add_input=_get(config, "add_input", False))
     raise ValueError("model_type should be 'vitgan' or  'mlp_mixer' or 'xtransformer'")      # main.py:501
+
+
+def load_model(model_path, vq_channels=256):
+    """main.py:1273-1290 (what `test`, `evaluate` and predict.py call): a `checkpoint.th` dictionary {"config", "state_dict", ...}
+    — the form train() writes (main.py:904) and the published models ship in — or, for backward compatibility, a pickled module
+    instance carrying `.config` (unpickling that needs the class it was saved from to be importable).  Returns this package's mapper
+    with those weights and `net.config` set."""
+    ckpt = torch.load(model_path, map_location="cpu", weights_only=False)
+    if isinstance(ckpt, dict):
+        config, sd = ckpt["config"], ckpt["state_dict"]
+    else:
+        config, sd = ckpt.config, ckpt.state_dict()
+    net = build_model(config, vq_channels=vq_channels)
+    net.load_state_dict(sd)
+    net.config = config
+    for k in ("step", "epoch"):
+        if isinstance(ckpt, dict) and k in ckpt:
+            setattr(net, k, ckpt[k])
+    return net
 
 
 def load_vqgan_model(config_path=None, checkpoint_path=None):

@@ -232,3 +232,33 @@ def test_load_clip_and_vqgan_checkpoints_in_the_published_formats(tmp_path):
     for k2, v in vq.state_dict().items():
         assert torch.equal(vq2.state_dict()[k2], v + 1.0), k2
     assert vq2.quantize.embedding.weight.shape == (16384, 256) and not vq2.training
+
+
+def test_load_model_reads_checkpoint_dictionaries_and_legacy_pickles(tmp_path):
+    """api.load_model (main.py:1273-1290): the {"config", "state_dict"} dictionary train() writes, and — where the reference tree is
+    present — a pickled instance of the REFERENCE's own Mixer (the legacy `model.th` form): both come back as this package's mapper
+    with the same weights."""
+    import sys
+    from feed_forward_vqgan_clip_b200 import api
+    cfg = dict(model_type="mlp_mixer", clip_model="ViT-B/32", clip_dim=32, vq_image_size=4, noise_dim=0, dim=32, depth=2, dropout=0)
+    torch.manual_seed(5)
+    src = api.build_model(cfg, vq_channels=16)
+    torch.save({"state_dict": src.state_dict(), "config": cfg, "step": 7, "epoch": 1}, tmp_path / "checkpoint.th")
+    net = api.load_model(str(tmp_path / "checkpoint.th"), vq_channels=16)
+    assert type(net) is type(src) and net.config == cfg and net.step == 7 and net.epoch == 1
+    for (k, a), b in zip(net.state_dict().items(), src.state_dict().values()):
+        assert torch.equal(a, b), k
+    if os.path.exists("/root/reference/mlp_mixer_pytorch.py"):
+        sys.path.insert(0, "/root/reference")
+        try:
+            from mlp_mixer_pytorch import Mixer as RefMixer
+            torch.manual_seed(6)
+            legacy = RefMixer(input_dim=32, image_size=4, channels=16, patch_size=1, dim=32, depth=2)
+            legacy.config = dict(cfg)                        # main.py:590 attaches the config to the module before pickling it
+            torch.save(legacy, tmp_path / "model.th")
+            net2 = api.load_model(str(tmp_path / "model.th"), vq_channels=16)
+            assert type(net2) is type(src)
+            for (k, a), b in zip(net2.state_dict().items(), legacy.state_dict().values()):
+                assert torch.equal(a, b), k
+        finally:
+            sys.path.remove("/root/reference")
