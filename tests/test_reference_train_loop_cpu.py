@@ -362,3 +362,33 @@ def test_reference_train_loop_evaluation_block_on_this_package(monkeypatch, tmp_
     sc = _run.last_scalars
     assert len(losses) == 2 and len(sc["eval_dists"]) == 2 and len(sc["eval_clip_score"]) == 2
     assert all(0 < d < 5 for d in sc["eval_dists"]) and all(abs(c) < 100.0 for c in sc["eval_clip_score"])
+
+
+def test_reference_test_command_generates_images_from_a_trained_checkpoint(monkeypatch, tmp_path):
+    """the reference's `test` command (main.py:975-1059) — load_model(checkpoint.th) -> tokenize -> encode_text ->
+    mapper -> clamp -> synth -> image grid — run unmodified on this package's load_model / load_clip_model / load_vqgan_model /
+    clamp_with_grad / synth, from the checkpoint the reference's train() wrote one test earlier in the same way."""
+    from PIL import Image
+    ref = _import_reference_main()
+    from feed_forward_vqgan_clip_b200 import api
+
+    def mapper(config):
+        net = api.build_model(config, vq_channels=64)
+        with torch.no_grad():
+            net.final_proj.weight.mul_(6.0)
+        return net
+
+    _, _, folder = _run(ref, monkeypatch, tmp_path, "train", mapper, 1, dict(model_type="mlp_mixer", dim=64, tokens=True))
+    monkeypatch.setattr(ref, "load_model", lambda path: api.load_model(path, vq_channels=64))
+    g = torch.Generator().manual_seed(4)
+
+    def tokenize(texts, truncate=True):                      # clip's BPE tokenizer is out of scope: ids with an EOT (largest id) each
+        t = torch.randint(1, 90, (len(texts), 77), generator=g)
+        t[:, 9] = 99
+        return t
+    monkeypatch.setattr(ref.clip, "tokenize", tokenize)
+    out = tmp_path / "grid.png"
+    ref.test(str(folder / "checkpoint.th"), "a red bus|a castle on a hill", nb_repeats=2, out_path=str(out), images_per_row=2, seed=1)
+    img = Image.open(out)
+    assert img.size == (2 * 32 + 3 * 2, 2 * 32 + 3 * 2)      # make_grid: 4 images of 32 x 32, 2 per row, 2-pixel padding
+    assert img.getextrema() != ((0, 0), (0, 0), (0, 0))
