@@ -392,3 +392,37 @@ def test_reference_test_command_generates_images_from_a_trained_checkpoint(monke
     img = Image.open(out)
     assert img.size == (2 * 32 + 3 * 2, 2 * 32 + 3 * 2)      # make_grid: 4 images of 32 x 32, 2 per row, 2-pixel padding
     assert img.getextrema() != ((0, 0), (0, 0), (0, 0))
+
+
+def test_reference_evaluate_command_scores_a_trained_checkpoint(monkeypatch, tmp_path):
+    """the reference's `evaluate` command (main.py:1062-1272) — for every batch of prompts: encoder.encode_text ->
+    mapper -> clamp -> synth -> bilinear resize to the perceptor's 224 x 224 -> encode_image -> CLIP score with logit_scale —
+    unmodified, on this package's objects, from a checkpoint the reference's train() wrote."""
+    import json
+    import oracle.clip_vit as oclip
+    ref = _import_reference_main()
+    from feed_forward_vqgan_clip_b200 import api, clip_vit
+
+    def mapper(config):
+        net = api.build_model(config, vq_channels=64)
+        with torch.no_grad():
+            net.final_proj.weight.mul_(6.0)
+        return net
+
+    _, _, folder = _run(ref, monkeypatch, tmp_path, "train", mapper, 1, dict(model_type="mlp_mixer", dim=64, tokens=True))
+    monkeypatch.setattr(ref, "load_model", lambda path: api.load_model(path, vq_channels=64))
+    cfg224 = dict(SMALL_CLIP, input_resolution=224)          # evaluate resizes to CLIP_SIZE["ViT-B/32"] = 224 (main.py:1146,1229)
+
+    def load_clip(model_type="ViT-B/32", path=None):
+        torch.manual_seed(77)
+        m = clip_vit.CLIP(cfg224, text_cfg=SMALL_TEXT)
+        m.visual.load_state_dict(oclip.init_clip_state_dict(cfg224, seed=9))
+        return m.eval().requires_grad_(False)
+    monkeypatch.setattr(ref, "load_clip_model", load_clip)
+    dump = ref.evaluate(str(folder / "checkpoint.th"), str(folder / "data.pkl"), batch_size=2, save_images=True, images_per_row=2)
+    name = "data.pkl_ViT-B_32"
+    scores = torch.load(folder / ("eval_%s.th" % name))
+    assert scores.shape == (2,) and torch.isfinite(scores).all()
+    assert abs(dump["clip_score_mean"] - float(scores.mean())) < 1e-6
+    assert json.load(open(folder / ("eval_%s.json" % name)))["clip_score_mean"] == dump["clip_score_mean"]
+    assert os.path.exists(folder / ("eval_%s_images" % name) / "batch_0000000000.png")
