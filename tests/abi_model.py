@@ -664,3 +664,28 @@ def k_diversity_tap(feats, loss_accum, dfeat, R, B, HW, C, scale):
         g, = torch.autograd.grad(div, f)
     loss_accum.view(-1)[0] += div.detach()
     dfeat.view(-1)[:R * B * HW * C] = g.reshape(-1)
+
+
+# ------------------------------------------------------------------------------------------------ alternates of the above
+def k_groupnorm_fused_fwd(x, gamma, beta, y, mean, rstd, ws, N, HW, C, G, swish, eps):
+    """single-kernel form: the same arithmetic as ffvc_groupnorm_stats + ffvc_groupnorm_apply"""
+    assert not STRICT_SHAPES or (C % 8 == 0 and C % G == 0 and 512 % (C // 8) == 0), "groupnorm_fused: C % 8, C % G, (C / 8) | 512"
+    xf = x.reshape(-1)[:N * HW * C].view(N, HW, G, C // G).double()
+    mean.view(-1)[:N * G] = xf.mean((1, 3)).reshape(-1).float()
+    rstd.view(-1)[:N * G] = (xf.var((1, 3), unbiased=False) + eps).rsqrt().reshape(-1).float()
+    _, u = _gn_parts(x, mean, rstd, gamma, beta, N, HW, C, G)
+    y.view(-1)[:N * HW * C] = (u * torch.sigmoid(u) if swish else u).reshape(-1)
+
+
+def k_groupnorm_fused_bwd(dy, x, mean, rstd, gamma, beta, ws, add, dx, N, HW, C, G, swish):
+    assert not STRICT_SHAPES or (C % 8 == 0 and C % G == 0 and 512 % (C // 8) == 0), "groupnorm_fused: C % 8, C % G, (C / 8) | 512"
+    g, xh = _gn_g(dy, x, mean, rstd, gamma, beta, N, HW, C, G, swish)
+    _gn_dx(g, xh, g.double().sum((1, 3)), (g * xh).double().sum((1, 3)), rstd, add, dx, N, HW, C, G)
+
+
+def k_conv3x3_cin3(x, w, y, N, H, W, COUT):
+    """3x3 conv with 3 input channels: fp32 NHWC in, fp32 weights [COUT][9][3] (tap-major), bf16 NHWC out"""
+    assert not STRICT_SHAPES or (COUT % 8 == 0 and COUT <= 512), "conv3x3_cin3: COUT % 8 != 0 or too large"
+    W4 = w.reshape(-1)[:COUT * 27].view(COUT, 3, 3, 3).float().permute(0, 3, 1, 2)
+    o = F.conv2d(_nhwc(x, N, H, W, 3).permute(0, 3, 1, 2), W4, padding=1)
+    y.view(-1)[:N * H * W * COUT] = o.permute(0, 2, 3, 1).reshape(-1)

@@ -262,3 +262,37 @@ def test_load_model_reads_checkpoint_dictionaries_and_legacy_pickles(tmp_path):
                 assert torch.equal(a, b), k
         finally:
             sys.path.remove("/root/reference")
+
+
+def test_every_compute_entry_point_has_a_cpu_statement_of_its_contract():
+    """tests/abi_model.py states the contract of every compute entry point of include/ffvc.h (the control / query functions —
+    options, launch counter, workspace sizes, error string — need none): a new kernel cannot be added to the ABI without its
+    host-checkable statement.  The single-kernel GroupNorm forms must agree with the two-pass model they alias."""
+    import abi_model
+    control = {"ffvc_arch", "ffvc_last_error", "ffvc_launch_count", "ffvc_reset_launch_count", "ffvc_set_option", "ffvc_get_option",
+               "ffvc_sizeof", "ffvc_gemm_set_stream_k", "ffvc_gemm_set_tma_store", "ffvc_groupnorm_set_pipeline",
+               "ffvc_groupnorm_ws_bytes", "ffvc_layernorm_bwd_ws_bytes"}
+    declared = set(_lib.header_declarations())
+    modelled = {"ffvc_" + n[2:] for n in dir(abi_model) if n.startswith("k_")} | {"ffvc_gemm"}
+    assert declared - modelled == control and not (modelled - declared)
+    g = torch.Generator().manual_seed(0)
+    N, HW, C = 2, 64, 64
+    x = torch.randn(N * HW, C, generator=g).to(torch.bfloat16)
+    dy = torch.randn(N * HW, C, generator=g).to(torch.bfloat16)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    m1, r1, m2, r2 = (torch.empty(N * 32) for _ in range(4))
+    y1, y2, d1, d2 = (torch.empty(N * HW, C, dtype=torch.bfloat16) for _ in range(4))
+    ws = torch.empty(4096, dtype=torch.float64)
+    abi_model.k_groupnorm_stats(x, ws, m1, r1, N, HW, C, 32, 1e-6)
+    abi_model.k_groupnorm_apply(x, m1, r1, gamma, beta, y1, N, HW, C, 32, 1)
+    abi_model.k_groupnorm_fused_fwd(x, gamma, beta, y2, m2, r2, ws, N, HW, C, 32, 1, 1e-6)
+    assert torch.equal(y1, y2) and torch.equal(m1, m2) and torch.equal(r1, r2)
+    abi_model.k_groupnorm_bwd(dy, x, m1, r1, gamma, beta, ws, None, d1, N, HW, C, 32, 1)
+    abi_model.k_groupnorm_fused_bwd(dy, x, m1, r1, gamma, beta, ws, None, d2, N, HW, C, 32, 1)
+    assert torch.equal(d1, d2)
+    img = torch.randn(1, 8, 8, 3, generator=g)
+    w = torch.randn(8, 27, generator=g)
+    out = torch.empty(64, 8, dtype=torch.bfloat16)
+    abi_model.k_conv3x3_cin3(img, w, out, 1, 8, 8, 8)
+    ref = torch.nn.functional.conv2d(img.permute(0, 3, 1, 2), w.view(8, 3, 3, 3).permute(0, 3, 1, 2), padding=1)
+    assert torch.allclose(out.float().view(1, 8, 8, 8), ref.permute(0, 2, 3, 1), atol=2e-2, rtol=1e-2)      # bf16 output
