@@ -351,6 +351,7 @@ def k_groupnorm_stats(x, ws, mean, rstd, N, HW, C, G, eps):
     xf = x.reshape(-1)[:N * HW * C].view(N, HW, G, C // G).double()
     mu = xf.mean((1, 3))
     var = xf.var((1, 3), unbiased=False)
+    ws.view(-1)[:N * G * 2] = torch.stack([xf.sum((1, 3)), (xf * xf).sum((1, 3))], -1).reshape(-1)    # (sum x, sum x^2) per (image, group)
     mean.view(-1)[:N * G] = mu.reshape(-1).float()
     rstd.view(-1)[:N * G] = (var + eps).rsqrt().reshape(-1).float()
 
@@ -395,7 +396,9 @@ def _gn_dx(g, xh, s0, s1, rstd, add, dx, N, HW, C, G):
 def k_groupnorm_bwd(dy, x, mean, rstd, gamma, beta, ws, add, dx, N, HW, C, G, swish):
     _gn_check(C, G, backward=True)
     g, xh = _gn_g(dy, x, mean, rstd, gamma, beta, N, HW, C, G, swish)
-    _gn_dx(g, xh, g.double().sum((1, 3)), (g * xh).double().sum((1, 3)), rstd, add, dx, N, HW, C, G)
+    s0, s1 = g.double().sum((1, 3)), (g * xh).double().sum((1, 3))
+    ws.view(-1)[:N * G * 2] = torch.stack([s0, s1], -1).reshape(-1)     # the first pass leaves (sum g, sum g * xhat) per (image, group)
+    _gn_dx(g, xh, s0, s1, rstd, add, dx, N, HW, C, G)
 
 
 def k_conv3x3_halo_gnbwd(x, w, out, n, h, wd, cin, cout, ldc, res, gn_x, gn_mean, gn_rstd, gn_gamma, gn_beta, gn_ws):
