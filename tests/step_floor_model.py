@@ -8,7 +8,7 @@ the per-prompt and the batch-independent (weights, optimizer) parts, extrapolate
 floor is max(FLOPs / tensor peak, bytes / HBM bandwidth) with the peaks of MEASURED_PEAKS.json; the sum over the step is the time
 below which no schedule of THESE launches can go — to be compared with the measured step (profiles/r01_step_breakdown_final.md).
 
-    python tools/step_floor_model.py [--md profiles/r01_step_floor_model.md]
+    python tests/step_floor_model.py [--md profiles/r01_step_floor_model.md]
 """
 import argparse
 import collections
@@ -140,7 +140,7 @@ def main():
                 nm = "tcgen05 GEMM / conv" if (nm == "gemm" or nm.startswith("conv3x3_halo")) else nm
                 measured[nm] = measured.get(nm, 0.0) + float(c[3])
     lines = ["# Roofline floor of the config #2 train step (B = %d) from a launch trace of the host path" % B, "",
-             "`python tools/step_floor_model.py` — engines on the CPU, every launch recorded in front of `tests/abi_model.py`; algorithmic",
+             "`python tests/step_floor_model.py` — engines on the CPU, every launch recorded in front of `tests/abi_model.py`; algorithmic",
              "FLOPs and bytes per launch from its arguments, traced at B = 1 and 2 and extended linearly to B = %d.  Peaks: HBM %.0f GB/s," % (B, peaks["hbm_gbs"]),
              "bf16 %.0f TFLOP/s sustained (`MEASURED_PEAKS.json`).  floor = sum over launches of max(FLOPs / peak, bytes / bandwidth)." % peaks["bf16_tflops_sustained"],
              "measured = CUDA-event time of the same launches in one eager step on a B200 (`profiles/r01_step_breakdown_final.md`).", "",
