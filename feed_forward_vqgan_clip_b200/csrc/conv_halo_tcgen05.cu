@@ -359,14 +359,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));           // the accumulator is free for the MMA warp before the fold below
       if (p.gn_ws) {
-        // fold the 8 warps' slots of this tile: thread (kind, group) -> one double atomic per (image, group, kind) and tile
+        // fold the 8 warps' slots of this tile (fixed order): thread (kind, group) -> one partial per (image, tile, kind, group)
         asm volatile("bar.sync 2, %0;" ::"n"(32 * kEW) : "memory");
         if (etid < 64) {
           const int kind = etid >> 5, g = etid & 31;
           float tot = 0.f;
 #pragma unroll
           for (int w8 = 0; w8 < 8; ++w8) tot += gn_part[(((acc * 8 + w8) * 2 + kind) << 5) + g];
-          atomicAdd(&p.gn_ws[((long long)img * 32 + g) * 2 + kind], (double)tot);
+          // this tile's slot of the partials [n][tile][kind][group] behind the [n][group][2] block: exactly one writer, no atomics —
+          // the fold over the tiles runs later in a fixed order (groupnorm_finalize / groupnorm_bwd_apply), so the statistics
+          // are reproducible bit for bit and independent of the batch the image is part of
+          const long long tile_in_img = (long long)ty * tiles_x + tx;
+          p.gn_ws[(long long)p.batch * 64 + (((long long)img * tiles_y * tiles_x + tile_in_img) * 2 + kind) * 32 + g] = (double)tot;
         }
       }
       if (++acc == 2) {
@@ -482,7 +486,6 @@ static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, i
     p.gn_gamma = gnb_gamma;
     p.gn_beta = gnb_beta;
   }
-  if (gn_ws) cudaMemsetAsync(gn_ws, 0, sizeof(double) * 2 * 32 * (size_t)n, reinterpret_cast<cudaStream_t>(stream));
   const long long tiles = (long long)n * (h / 2) * (wd / 128);
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   // 16 epilogue warps for the GroupNorm-statistics epilogues (option "halo_epi16": 1 = backward statistics, 2 = forward too)

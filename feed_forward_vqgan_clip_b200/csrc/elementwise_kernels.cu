@@ -649,10 +649,12 @@ __global__ void adam_tick_kernel(float* __restrict__ hyper) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     const float t = hyper[8] + 1.0f;
     hyper[8] = t;
-    hyper[4] = 1.0f - powf(hyper[1], t);
-    hyper[5] = sqrtf(1.0f - powf(hyper[2], t));
+    // one thread: double precision is free here and matches the Python-float arithmetic of torch.optim.Adam / CosineAnnealingLR
+    // (--use_fast_math powf left 3e-5 of relative error in the second bias correction)
+    hyper[4] = (float)(1.0 - pow((double)hyper[1], (double)t));
+    hyper[5] = (float)sqrt(1.0 - pow((double)hyper[2], (double)t));
     if (hyper[13] > 0.f)
-      hyper[0] = hyper[14] + (hyper[12] - hyper[14]) * 0.5f * (1.0f + cospif((t - 1.0f) / hyper[13]));
+      hyper[0] = (float)((double)hyper[14] + ((double)hyper[12] - (double)hyper[14]) * 0.5 * (1.0 + cospi(((double)t - 1.0) / (double)hyper[13])));
     if (hyper[9] > 0.f) {
       const float norm = sqrtf(hyper[10]) * hyper[6];         // norm of the averaged gradient (grad_scale = 1 / world)
       hyper[11] = fminf(1.0f, hyper[9] / (norm + 1e-6f));

@@ -510,6 +510,97 @@ __global__ void __launch_bounds__(256) ln_bwd_finalize_kernel(const float* __res
 }
 
 // ------------------------------------------------------------------------------------ GroupNorm
+// REPRODUCIBLE statistics (round 2): every reduction below runs in a FIXED order that depends on the sample's shape only —
+// warp shuffles, one shared-memory slot per warp, a fixed-order fold over the warps, one workspace slot per CTA
+// (ws partials [n][part][2][G]) and a fixed-order fold over the parts (gn_fold_parts) — so (mean, rstd) and the backward
+// sums are bit-identical from run to run and for any batch size or sharding of the batch.  Round 1 used float shared-memory
+// atomics inside the CTA and double atomics across CTAs: the last bit of mean / rstd flickered between identical runs, a
+// bf16 rounding flipped here and there, and 60 layers later the image differed by 0.85 % — which the reference's
+// discontinuous gradient (max-pool arg-max, HSV sectors) turned into a 16 % gradient difference (profiles/r02_parity_fullsize.md).
+//
+// Per-thread 8-channel partial sums (s, q) -> per-group sums of this WARP in sm[warp][0..G) / sm[warp][G..2G) (plain stores,
+// every (warp, group) slot has exactly one writer; slots of groups the warp does not cover must be zero beforehand).
+__device__ __forceinline__ void gn_fold_to_slots(float (&s)[8], float (&q)[8], float* sm, int G, int cpg, int vc,
+                                                 int vec_per_pix) {
+  const int lane = threadIdx.x & 31;
+  float* slot = sm + (threadIdx.x >> 5) * 2 * G;
+  if (vec_per_pix < 32) {      // lanes of the warp that own the same channel vector: butterfly (same tree every time)
+    for (int o = vec_per_pix; o < 32; o <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+      }
+    }
+  }
+  if (cpg >= 8) {
+    float ss = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+    float qq = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+    const int vpg = cpg >> 3;                     // channel vectors per group (power of two; neighbouring lanes)
+    for (int o = 1; o < vpg; o <<= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    }
+    if ((vec_per_pix >= 32 || lane < vec_per_pix) && (vc & (vpg - 1)) == 0) {
+      const int g = (vc * 8) / cpg;
+      slot[g] = ss;
+      slot[G + g] = qq;
+    }
+  } else {
+    if (vec_per_pix < 32 && lane >= vec_per_pix) return;
+    // cpg in {1, 2, 4}: fold neighbours with static register indices (no dynamic indexing -> no local memory)
+    if (cpg >= 2) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        s[j] += s[j + 1];
+        q[j] += q[j + 1];
+      }
+    }
+    if (cpg >= 4) {
+      s[0] += s[2];
+      q[0] += q[2];
+      s[4] += s[6];
+      q[4] += q[6];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j % cpg == 0) {
+        const int g = (vc * 8 + j) / cpg;
+        slot[g] = s[j];
+        slot[G + g] = q[j];
+      }
+    }
+  }
+}
+// after __syncthreads(): thread i < 2G folds the warps' slots in order and stores this CTA's partial (no atomics)
+__device__ __forceinline__ void gn_store_part(const float* sm, double* part, int G, int nwarps) {
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += sm[w * 2 * G + i];
+    part[i] = (double)t;
+  }
+}
+// 8 lanes per output fold `parts` partials (stride 2G doubles) in a fixed order: lane l takes parts l, l+8, ..., then a butterfly
+__device__ __forceinline__ double gn_fold_parts(const double* p, int parts, int stride, int l) {
+  double a = 0.0;
+  for (int k = l; k < parts; k += 8) a += p[(long long)k * stride];
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  a += __shfl_xor_sync(0xffffffffu, a, 4);
+  return a;
+}
+// ws = [N][G][2] folded sums (written here) followed by the partials [N][parts][2][G]
+__global__ void __launch_bounds__(256) gn_fold_kernel(double* __restrict__ ws, int N, int G, int parts) {
+  const int o = (blockIdx.x * 256 + threadIdx.x) >> 3, l = threadIdx.x & 7;
+  const int total = N * 2 * G;
+  const int oc = o < total ? o : total - 1;                // keep every lane in the shuffles
+  const int n = oc / (2 * G), kind = (oc / G) & 1, g = oc % G;
+  const double* part = ws + (long long)N * 2 * G + ((long long)n * parts * 2 + kind) * G + g;
+  const double a = gn_fold_parts(part, parts, 2 * G, l);
+  if (l == 0 && o < total) ws[((long long)n * G + g) * 2 + kind] = a;
+}
+
+// The single-kernel forms (off by default) keep round 1's atomic fold: their results are NOT reproducible bit for bit.
 // Per-thread 8-channel partial sums (s, q) -> per-group sums in shared memory sm[0..G) / sm[G..2G).
 // Channels are first combined per group in registers, then lanes of the warp that own the same channel vector
 // (vec_per_pix < 32) are folded with shuffles, so each warp issues one shared atomic per (vector, group).
@@ -563,18 +654,18 @@ __device__ __forceinline__ void gn_fold_to_smem(float (&s)[8], float (&q)[8], fl
 }
 
 // x: NHWC bf16, G groups of cpg = C/G consecutive channels.  Statistics per (n, g) over HW*cpg elements.
-// Pass 1: partial (sum, sumsq) per CTA -> double atomics into ws[N*G*2].  C % 8 == 0.
+// Pass 1: partial (sum, sumsq) per CTA -> its own slot of the partials in ws (see above).  C % 8 == 0.
 // Each thread owns one 8-channel vector column (fixed group set) and strides over pixels.
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ x,
-                                                              double* __restrict__ ws, int HW, int C, int G,
+                                                              double* __restrict__ ws_parts, int HW, int C, int G,
                                                               int pix_per_cta) {
-  extern __shared__ float sm[];  // [2][G]
+  extern __shared__ float sm[];  // [8 warps][2][G]
   const int n = blockIdx.y;
   const int cpg = C / G;
   const int vec_per_pix = C >> 3;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < 16 * G; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   // thread -> (vector column vc, pixel lane pl); blockDim.x is a multiple of vec_per_pix or vice versa handled by stride
   const int vc = threadIdx.x % vec_per_pix;
@@ -594,24 +685,31 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const __nv_bfloat1
         q[j] += v[j] * v[j];
       }
     }
-    gn_fold_to_smem(s, q, sm, G, cpg, vc, vec_per_pix);
+    gn_fold_to_slots(s, q, sm, G, cpg, vc, vec_per_pix);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < G; i += blockDim.x) {
-    atomicAdd(&ws[((long long)n * G + i) * 2 + 0], (double)sm[i]);
-    atomicAdd(&ws[((long long)n * G + i) * 2 + 1], (double)sm[G + i]);
-  }
+  gn_store_part(sm, ws_parts + ((long long)n * gridDim.x + blockIdx.x) * 2 * G, G, 8);
 }
 
-__global__ void groupnorm_finalize_kernel(const double* __restrict__ ws, float* __restrict__ mean,
-                                          float* __restrict__ rstd, int NG, double count, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= NG) return;
-  const double m = ws[2 * i] / count;
-  double var = ws[2 * i + 1] / count - m * m;
+// folds the partials (fixed order), leaves the sums in ws[n][g][2] and turns them into mean / rstd; 8 lanes per (n, g)
+__global__ void __launch_bounds__(256) groupnorm_finalize_kernel(double* __restrict__ ws, float* __restrict__ mean,
+                                                                 float* __restrict__ rstd, int N, int G, int parts, double count,
+                                                                 float eps) {
+  const int o = (blockIdx.x * 256 + threadIdx.x) >> 3, l = threadIdx.x & 7;
+  const int total = N * G;
+  const int oc = o < total ? o : total - 1;
+  const int n = oc / G, g = oc % G;
+  const double* part = ws + (long long)N * 2 * G + (long long)n * parts * 2 * G + g;
+  const double s1 = gn_fold_parts(part, parts, 2 * G, l);
+  const double s2 = gn_fold_parts(part + G, parts, 2 * G, l);
+  if (l != 0 || o >= total) return;
+  ws[2 * (long long)o] = s1;
+  ws[2 * (long long)o + 1] = s2;
+  const double m = s1 / count;
+  double var = s2 / count - m * m;
   if (var < 0) var = 0;
-  mean[i] = (float)m;
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  mean[o] = (float)m;
+  rstd[o] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // y = act((x - mean) * rstd * gamma + beta), act = swish or identity.
@@ -665,16 +763,16 @@ __global__ void __launch_bounds__(256, 4) groupnorm_bwd_stats_kernel(const __nv_
                                                                      const float* __restrict__ rstd,
                                                                      const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta,
-                                                                     double* __restrict__ ws, int HW, int C, int G,
+                                                                     double* __restrict__ ws_parts, int HW, int C, int G,
                                                                      int pix_per_cta, int swish) {
-  extern __shared__ float sm[];  // [2][G]
+  extern __shared__ float sm[];  // [8 warps][2][G]
   constexpr int CPV = 8 / GPV;   // channels of the vector that share a group
   const int n = blockIdx.y;
   const int cpg = C / G;
   const int vec_per_pix = C >> 3;
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < 16 * G; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const int vc = threadIdx.x % vec_per_pix;
   const int pl = threadIdx.x / vec_per_pix;
@@ -721,13 +819,10 @@ __global__ void __launch_bounds__(256, 4) groupnorm_bwd_stats_kernel(const __nv_
         }
       }
     }
-    gn_fold_to_smem(s, q, sm, G, cpg, vc, vec_per_pix);
+    gn_fold_to_slots(s, q, sm, G, cpg, vc, vec_per_pix);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < G; i += blockDim.x) {
-    atomicAdd(&ws[((long long)n * G + i) * 2 + 0], (double)sm[i]);
-    atomicAdd(&ws[((long long)n * G + i) * 2 + 1], (double)sm[G + i]);
-  }
+  gn_store_part(sm, ws_parts + ((long long)n * gridDim.x + blockIdx.x) * 2 * G, G, 8);
 }
 
 // backward pass 2: dx = rstd * (g - S1/cnt - xhat * S2/cnt) (+ add); same thread mapping as the apply kernel
@@ -1381,29 +1476,48 @@ static int gn_check(int C, int G) {
   return FFVC_OK;
 }
 
-// ws: N*G*2 doubles (zeroed here).  Produces mean/rstd [N*G].
+// Statistics passes: pixels per CTA depend on HW ONLY (never on N), so the partial sums of a sample — and with them mean / rstd —
+// are the same numbers whatever batch the sample is part of (4 .. 128 parts per sample).
+static int gn_stats_ppc(int HW) {
+  int ppc = HW / 128;
+  if (ppc < 64) ppc = 64;
+  if (ppc > 512) ppc = 512;
+  return ppc;
+}
+static int gn_stats_parts(int HW) { return (HW + gn_stats_ppc(HW) - 1) / gn_stats_ppc(HW); }
+// parts per sample the conv epilogues produce (one per 2-row x 128-pixel tile), 0 when the halo conv does not apply
+static int gn_epi_parts(int HW) { return HW % 256 == 0 ? HW / 256 : 0; }
+
+// doubles of statistics workspace for N samples of HW pixels: [N][G][2] folded sums + [N][parts][2][G] per-CTA partials
+extern "C" long long ffvc_groupnorm_ws_doubles(int N, int HW, int G) {
+  const int parts = gn_stats_parts(HW) > gn_epi_parts(HW) ? gn_stats_parts(HW) : gn_epi_parts(HW);
+  return (long long)N * 2 * G * (1 + parts);
+}
+
+// ws: ffvc_groupnorm_ws_doubles(N, HW, G) doubles.  Produces mean/rstd [N*G]; leaves (sum, sum of squares) in ws[n][g][2].
 extern "C" int ffvc_groupnorm_stats(const void* x, double* ws, float* mean, float* rstd, int N, int HW, int C, int G,
                                     float eps, void* stream) {
   int rc = gn_check(C, G);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st);
-  const int pix_per_cta = gn_pix_per_cta(N, HW);
-  dim3 grid((HW + pix_per_cta - 1) / pix_per_cta, N);
-  groupnorm_stats_kernel<<<grid, 256, 2 * G * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ws, HW, C, G,
-                                                                  pix_per_cta);
+  const int pix_per_cta = gn_stats_ppc(HW), parts = gn_stats_parts(HW);
+  dim3 grid(parts, N);
+  groupnorm_stats_kernel<<<grid, 256, 16 * G * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                                   ws + (long long)N * 2 * G, HW, C, G, pix_per_cta);
   FFVC_CHECK_LAUNCH();
-  groupnorm_finalize_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(ws, mean, rstd, N * G, (double)HW * (C / G), eps);
+  groupnorm_finalize_kernel<<<(N * G * 8 + 255) / 256, 256, 0, st>>>(ws, mean, rstd, N, G, parts, (double)HW * (C / G), eps);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
 
-// ws[N*G][2] = (sum, sum of squares) per (sample, group) -> mean / rstd.  For statistics produced elsewhere (the conv epilogue).
-extern "C" int ffvc_groupnorm_finalize(const double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps,
+// statistics produced by the conv epilogue (ffvc_conv3x3_halo_gn: one partial per 256-pixel tile behind the [N][G][2] block of
+// ws) -> mean / rstd; the folded sums are left in ws[n][g][2]
+extern "C" int ffvc_groupnorm_finalize(double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps,
                                        void* stream) {
   if (G <= 0 || C % G != 0) return set_error(FFVC_ERR_ARG, "groupnorm_finalize: C must be divisible by G");
-  groupnorm_finalize_kernel<<<(N * G + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ws, mean, rstd, N * G,
-                                                                                                       (double)HW * (C / G), eps);
+  if (gn_epi_parts(HW) == 0) return set_error(FFVC_ERR_ARG, "groupnorm_finalize: HW must be a multiple of 256 (conv epilogue tiles)");
+  groupnorm_finalize_kernel<<<(N * G * 8 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      ws, mean, rstd, N, G, gn_epi_parts(HW), (double)HW * (C / G), eps);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
@@ -1421,12 +1535,16 @@ extern "C" int ffvc_groupnorm_apply(const void* x, const float* mean, const floa
   return FFVC_OK;
 }
 
-// dx = d/dx [ act(GN(x)) ] . dy  (+ add).  ws: N*G*2 doubles scratch.
+// dx = d/dx [ act(GN(x)) ] . dy  (+ add).  ws: statistics workspace (ffvc_groupnorm_ws_doubles).
 template <int GPV>
 static void gn_bwd_launch(dim3 grid, cudaStream_t st, const __nv_bfloat16* dyb, const __nv_bfloat16* xb, const float* mean,
                           const float* rstd, const float* gamma, const float* beta, double* ws, const __nv_bfloat16* add,
-                          __nv_bfloat16* dx, int HW, int C, int G, int ppc, int swish) {
-  groupnorm_bwd_stats_kernel<GPV><<<grid, 256, 2 * G * sizeof(float), st>>>(dyb, xb, mean, rstd, gamma, beta, ws, HW, C, G, ppc, swish);
+                          __nv_bfloat16* dx, int N, int HW, int C, int G, int ppc, int swish) {
+  // pass 1 on the batch-invariant grid: per-CTA partials; fold (fixed order) into ws[n][g][2]; pass 2
+  const int ppc_s = gn_stats_ppc(HW), parts = gn_stats_parts(HW);
+  groupnorm_bwd_stats_kernel<GPV><<<dim3(parts, N), 256, 16 * G * sizeof(float), st>>>(dyb, xb, mean, rstd, gamma, beta,
+                                                                                         ws + (long long)N * 2 * G, HW, C, G, ppc_s, swish);
+  gn_fold_kernel<<<(N * 2 * G * 8 + 255) / 256, 256, 0, st>>>(ws, N, G, parts);
   groupnorm_bwd_apply_kernel<GPV><<<grid, 256, 0, st>>>(dyb, xb, mean, rstd, gamma, beta, ws, add, dx, HW, C, G, ppc,
                                                          1.0f / ((float)HW * (C / G)), swish);
 }
@@ -1442,11 +1560,13 @@ static void gn_bwd_apply_launch(dim3 grid, cudaStream_t st, const __nv_bfloat16*
 // second pass of ffvc_groupnorm_bwd alone: sums[N*G][2] = (sum g, sum g * xhat) were produced elsewhere (the dgrad conv's
 // epilogue, ffvc_conv3x3_halo_gnbwd).
 extern "C" int ffvc_groupnorm_bwd_apply(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                                        const float* beta, const double* sums, const void* add, void* dx, int N, int HW, int C,
+                                        const float* beta, double* sums, const void* add, void* dx, int N, int HW, int C,
                                         int G, int swish, void* stream) {
   int rc = gn_check(C, G);
   if (rc) return rc;
+  if (gn_epi_parts(HW) == 0) return set_error(FFVC_ERR_ARG, "groupnorm_bwd_apply: HW must be a multiple of 256 (conv epilogue tiles)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  gn_fold_kernel<<<(N * 2 * G * 8 + 255) / 256, 256, 0, st>>>(sums, N, G, gn_epi_parts(HW));   // per-tile partials -> sums[n][g][2]
   int ppc = 1024;
   while (ppc > 64 && (long long)N * ((HW + ppc - 1) / ppc) < 148 * 16) ppc >>= 1;
   dim3 grid((HW + ppc - 1) / ppc, N);
@@ -1464,15 +1584,14 @@ extern "C" int ffvc_groupnorm_bwd_apply(const void* dy, const void* x, const flo
   return FFVC_OK;
 }
 
-// dx = d/dx [ act(GN(x)) ] . dy  (+ add).  ws: N*G*2 doubles scratch.
+// dx = d/dx [ act(GN(x)) ] . dy  (+ add).  ws: statistics workspace (ffvc_groupnorm_ws_doubles); ends with (sum g, sum g xhat) in ws[n][g][2].
 extern "C" int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                                   const float* gamma, const float* beta, double* ws, const void* add, void* dx, int N,
                                   int HW, int C, int G, int swish, void* stream) {
   int rc = gn_check(C, G);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * N * G, st);
-  int ppc = 1024;   // pixels per CTA: aim for >= 16 CTAs per SM worth of work (4 resident), at least 64 pixels each
+  int ppc = 1024;   // pixels per CTA of the apply pass: aim for >= 16 CTAs per SM worth of work (4 resident), at least 64 pixels each
   while (ppc > 64 && (long long)N * ((HW + ppc - 1) / ppc) < 148 * 16) ppc >>= 1;
   dim3 grid((HW + ppc - 1) / ppc, N);
   auto dyb = reinterpret_cast<const __nv_bfloat16*>(dy);
@@ -1481,10 +1600,10 @@ extern "C" int ffvc_groupnorm_bwd(const void* dy, const void* x, const float* me
   auto dxb = reinterpret_cast<__nv_bfloat16*>(dx);
   const int cpg = C / G;
   // groups covered by one 8-channel vector: 8 / cpg when cpg divides 8, else (cpg a multiple of 8) exactly one
-  if (cpg >= 8 && cpg % 8 == 0) gn_bwd_launch<1>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, HW, C, G, ppc, swish);
-  else if (cpg == 4) gn_bwd_launch<2>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, HW, C, G, ppc, swish);
-  else if (cpg == 2) gn_bwd_launch<4>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, HW, C, G, ppc, swish);
-  else if (cpg == 1) gn_bwd_launch<8>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, HW, C, G, ppc, swish);
+  if (cpg >= 8 && cpg % 8 == 0) gn_bwd_launch<1>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, N, HW, C, G, ppc, swish);
+  else if (cpg == 4) gn_bwd_launch<2>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, N, HW, C, G, ppc, swish);
+  else if (cpg == 2) gn_bwd_launch<4>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, N, HW, C, G, ppc, swish);
+  else if (cpg == 1) gn_bwd_launch<8>(grid, st, dyb, xb, mean, rstd, gamma, beta, ws, ab, dxb, N, HW, C, G, ppc, swish);
   else return set_error(FFVC_ERR_UNSUPPORTED, "groupnorm_bwd: channels per group must be 1, 2, 4 or a multiple of 8");
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;

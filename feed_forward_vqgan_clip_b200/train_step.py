@@ -209,6 +209,8 @@ class TrainStep:
         self.static = None
         self._next_prm = None           # augmentation parameters drawn ahead of the next replay()
         self.last_indices = None
+        self.force_idx = None           # diagnostics: code indices to decode instead of the arg-min's
+        self.debug = None               # diagnostics: a dict here receives the step's intermediates
 
     # ------------------------------------------------------------------ one step on device-resident inputs
     def _device_step(self, inp, out_feats, prm):
@@ -218,6 +220,9 @@ class TrainStep:
         N = self.cutn * B
         z, sv_m = mix.forward(inp)                                       # [B*T, C] fp32
         zq, idx, zc = dec.quantize(z, self.z_lo, self.z_hi)
+        if self.force_idx is not None:                                   # diagnostics only (tools/diag_fullsize.py): decode these codes
+            idx = self.force_idx.to(idx.dtype).view(-1)
+            zq = dec.codebook[idx.long()].to(BF16)
         self.last_indices = idx
         img, tape = dec.forward(zq.view(B, S, S, C))                     # [B, H, W, 3] fp32 in [0, 1]
         patches, sv_c, _ = cut.forward(img, prm)
@@ -225,6 +230,8 @@ class TrainStep:
         demb = torch.empty(N, clip.E, device=self.dev, dtype=F32)
         call("spherical_loss", emb, out_feats, self.loss, demb, None, N, B, clip.E, self.coef)
         self.aux_loss.zero_()
+        if self.debug is not None:
+            self.debug.update(z=z.clone(), img=img.clone(), patches=patches.clone(), emb=emb.clone(), demb=demb.clone())
         # ---- backward
         dpatch = clip.backward(sv_e, demb)
         del sv_e
@@ -237,8 +244,12 @@ class TrainStep:
         if self.tv_coef > 0:                                             # tv_coef * tv_loss(xr), main.py:769-773,831
             H = img.shape[1]
             call("tv_loss", img, self.aux_loss[1:2], dimg, B, H, img.shape[2], 3, self.tv_coef)
+        if self.debug is not None:
+            self.debug.update(dimg=dimg.clone())
         dzq = dec.backward(tape, dimg)                                   # [B*T, C] bf16 (straight-through to z)
         del tape
+        if self.debug is not None:
+            self.debug.update(dzq=dzq.clone())
         dzq32 = torch.empty(B * S * S, C, device=self.dev, dtype=F32)
         call("cast_bf16_f32", dzq, dzq32, dzq.numel())
         dz = torch.empty_like(dzq32)

@@ -188,10 +188,16 @@ class DecoderEngine:
     def _new(self, *shape, dtype=BF16):
         return torch.empty(*shape, device=self.dev, dtype=dtype)
 
-    def _gn_ws(self, n):
-        if self._ws is None or self._ws.numel() < n:
-            self._ws = torch.empty(max(n, 4096), device=self.dev, dtype=torch.float64)
-        return self._ws
+    def _gn_ws(self, N, HW, tag=0):
+        """statistics workspace: folded sums + one partial per CTA / conv tile (include/ffvc.h: ffvc_groupnorm_ws_doubles).
+        tag 1: a second buffer for the backward sums that a dgrad conv leaves for the following groupnorm_bwd_apply."""
+        from . import _lib
+        n = int(_lib.load().ffvc_groupnorm_ws_doubles(N, HW, 32))
+        if self._ws is None:
+            self._ws = {}
+        if tag not in self._ws or self._ws[tag].numel() < n:
+            self._ws[tag] = torch.empty(max(n, 4096), device=self.dev, dtype=torch.float64)
+        return self._ws[tag]
 
     # ---------------------------------------------------------------- primitive ops (forward + backward closure)
     USE_HALO = True    # shared-memory halo reuse for the wide (W % 128 == 0), <= 128-output-channel 3x3 convs
@@ -210,7 +216,7 @@ class DecoderEngine:
         that is followed by Upsample, and conv_out)"""
         out = self._new(N * H * W, cout, dtype=F32 if out_f32 else BF16)
         if gn_next and self.GN_EPI_STATS and cout == 128 and not out_f32 and self._halo_ok(H, W, cin, cout):
-            ws = self._gn_ws(N * 65)
+            ws = self._gn_ws(N, H * W)
             mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
             call("conv3x3_halo_gn", x, self.pk[name + ".w"], out, N, H, W, cin, cout, cout, self.pk[name + ".b"], res, ws)
             call("groupnorm_finalize", ws, mean, rstd, N, H * W, cout, 32, 1e-6)
@@ -234,7 +240,7 @@ class DecoderEngine:
         if gnb is not None:
             if self.GN_EPI_BWD and cin == 128 and res is None and self._halo_ok(H, W, cout, cin):
                 x, st, nname = gnb
-                sums = self._new(N * 64, dtype=torch.float64)
+                sums = self._gn_ws(N, H * W, tag=1)
                 call("conv3x3_halo_gnbwd", dy, self.pk[name + ".wT"], dx, N, H, W, cout, cin, cin, None, x, st[0], st[1],
                      self.pk[nname + ".g"], self.pk[nname + ".be"], sums)
                 return dx, sums
@@ -267,14 +273,14 @@ class DecoderEngine:
         mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
         y = self._new(N * HW, C)
         if self._gn_fused(HW, C):
-            call("groupnorm_fused_fwd", x, self.pk[name + ".g"], self.pk[name + ".be"], y, mean, rstd, self._gn_ws(N * 65), N, HW, C,
+            call("groupnorm_fused_fwd", x, self.pk[name + ".g"], self.pk[name + ".be"], y, mean, rstd, self._gn_ws(N, HW), N, HW, C,
                  32, int(swish), 1e-6)
             return y, (mean, rstd)
         st = self._epi_stats.pop(x.data_ptr(), None)
         if st is not None and st[2] == N * HW * C:       # statistics came with the conv that wrote x
             mean, rstd = st[0], st[1]
         else:
-            call("groupnorm_stats", x, self._gn_ws(N * 65), mean, rstd, N, HW, C, 32, 1e-6)
+            call("groupnorm_stats", x, self._gn_ws(N, HW), mean, rstd, N, HW, C, 32, 1e-6)
         call("groupnorm_apply", x, mean, rstd, self.pk[name + ".g"], self.pk[name + ".be"], y, N, HW, C, 32, int(swish))
         return y, (mean, rstd)
 
@@ -285,7 +291,7 @@ class DecoderEngine:
                  N, HW, C, 32, int(swish))
             return dx
         call("groupnorm_fused_bwd" if self._gn_fused(HW, C) else "groupnorm_bwd", dy, x, stats[0], stats[1], self.pk[name + ".g"],
-             self.pk[name + ".be"], self._gn_ws(N * 65), add, dx, N, HW, C, 32, int(swish))
+             self.pk[name + ".be"], self._gn_ws(N, HW), add, dx, N, HW, C, 32, int(swish))
         return dx
 
     def resblock(self, x, name, N, H, W, cin, cout, tape, gn_next=True):

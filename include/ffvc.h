@@ -135,22 +135,29 @@ int ffvc_gemm_set_stream_k(int on);
  * Epilogue: + bias[cout] (fp32, optional), act, * act'(aux) (mul_mode), + res (bf16, optional), like ffvc_gemm. */
 int ffvc_conv3x3_halo(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
                       const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32, void* stream);
-/* same conv (bias, optional residual, bf16 out, Cout = 128); its epilogue also accumulates the GroupNorm(32) statistics of the
- * tensor it writes — sum and sum of squares per (image, group) of the bf16-rounded output — into gn_ws[n][32][2] doubles
- * (zeroed by the call).  ffvc_groupnorm_finalize(gn_ws, ...) gives the mean / rstd taming's next `Normalize` needs, so
- * ffvc_groupnorm_stats (one more read of the tensor) is skipped. */
+/* GroupNorm statistics workspace (round 2: REPRODUCIBLE statistics).  Every statistics producer below — ffvc_groupnorm_stats,
+ * the first pass of ffvc_groupnorm_bwd, the epilogues of ffvc_conv3x3_halo_gn / _gnbwd — writes one partial sum per CTA / conv
+ * tile into its own slot ([N][parts][2][G] doubles behind the [N][G][2] block of folded sums; parts depends on HW only) and a
+ * fixed-order fold finishes the job: no atomics, so mean / rstd and the backward sums are bit-identical from run to run and
+ * for any batch size or sharding of the batch.  Returns the doubles one workspace must hold for N samples of HW pixels. */
+long long ffvc_groupnorm_ws_doubles(int N, int HW, int G);
+/* same conv (bias, optional residual, bf16 out, Cout = 128); its epilogue also takes the GroupNorm(32) statistics of the
+ * tensor it writes — sum and sum of squares per (image, group) of the bf16-rounded output, one partial per 256-pixel tile in
+ * gn_ws (layout above).  ffvc_groupnorm_finalize(gn_ws, ...) folds them (leaving the sums in gn_ws[n][32][2]) and gives the
+ * mean / rstd taming's next `Normalize` needs, so ffvc_groupnorm_stats (one more read of the tensor) is skipped. */
 int ffvc_conv3x3_halo_gn(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
                          const float* bias, const void* res, double* gn_ws, void* stream);
-int ffvc_groupnorm_finalize(const double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps, void* stream);
+int ffvc_groupnorm_finalize(double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps, void* stream);
 /* dgrad form (no bias): `out` = dy of the Normalize + swish in front of the forward conv (Cout = 128 channels), stored as
- * usual; the epilogue also reads that layer's input gn_x at the same positions and accumulates the backward statistics
- * sum g, sum g * xhat per (image, group), g = dy * swish'(gamma * xhat + beta) * gamma, into gn_ws[n][32][2] doubles (zeroed by
- * the call) — the first pass of ffvc_groupnorm_bwd (two more reads of dy and x).  ffvc_groupnorm_bwd_apply is its second pass. */
+ * usual; the epilogue also reads that layer's input gn_x at the same positions and takes the backward statistics
+ * sum g, sum g * xhat per (image, group), g = dy * swish'(gamma * xhat + beta) * gamma (per-tile partials in gn_ws, layout
+ * above) — the first pass of ffvc_groupnorm_bwd (two more reads of dy and x).  ffvc_groupnorm_bwd_apply folds them (leaving
+ * the sums in sums[n][32][2]) and runs the second pass. */
 int ffvc_conv3x3_halo_gnbwd(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
                             const void* res, const void* gn_x, const float* gn_mean, const float* gn_rstd, const float* gn_gamma,
                             const float* gn_beta, double* gn_ws, void* stream);
 int ffvc_groupnorm_bwd_apply(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                             const float* beta, const double* sums, const void* add, void* dx, int N, int HW, int C, int G,
+                             const float* beta, double* sums, const void* add, void* dx, int N, int HW, int C, int G,
                              int swish, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -171,7 +178,8 @@ int ffvc_layernorm_bwd_sums(const void* dy, const void* x, const float* gamma, c
 long long ffvc_layernorm_bwd_ws_bytes(int D, int rowsum_T);
 
 /* GroupNorm(G groups, eps) [+ swish] on NHWC bf16 — taming Normalize + nonlinearity.
- * ws: N*G*2 doubles of scratch.  bwd gives dx only (frozen affine), optionally + add.                 */
+ * ws: ffvc_groupnorm_ws_doubles(N, HW, G) doubles of scratch; after the call ws[n][g][2] holds the folded sums
+ * ((sum x, sum x^2) / (sum g, sum g xhat)).  bwd gives dx only (frozen affine), optionally + add.                 */
 int ffvc_groupnorm_stats(const void* x, double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps,
                          void* stream);
 int ffvc_groupnorm_apply(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,

@@ -25,4 +25,4 @@ def encode_text(sd, text, heads, act="quick_gelu"):
         x = x + F.linear(u, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
         l += 1
     x = F.layer_norm(x, (W,), sd["ln_final.weight"], sd["ln_final.bias"])
-    return x[torch.arange(B), text.argmax(dim=-1)] @ sd["text_projection"]
+    return x[torch.arange(B, device=x.device), text.argmax(dim=-1)] @ sd["text_projection"]

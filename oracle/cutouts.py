@@ -24,7 +24,8 @@ TWO_PI = 2.0 * math.pi
 def warp(img, hinv, padding_mode):
     """img (N,3,H,W); hinv (N,3,3) maps output pixel (x,y,1) -> source pixel coords."""
     N, _, H, W = img.shape
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=img.dtype), torch.arange(W, dtype=img.dtype), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=img.dtype, device=img.device), torch.arange(W, dtype=img.dtype, device=img.device),
+                            indexing="ij")
     pts = torch.stack([xs, ys, torch.ones_like(xs)], dim=-1).reshape(1, H * W, 3)
     src = pts @ hinv.transpose(1, 2)
     sx = src[..., 0] / src[..., 2]
@@ -84,7 +85,7 @@ def make_cutouts(x, cutn, params, cut_size=224, normalize=True):
         batch = batch * mask
     batch = batch + params["noise"]
     if normalize:
-        mean = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1)
-        std = torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+        mean = torch.tensor(CLIP_MEAN, device=batch.device).view(1, 3, 1, 1)
+        std = torch.tensor(CLIP_STD, device=batch.device).view(1, 3, 1, 1)
         batch = (batch - mean) / std
     return batch

@@ -34,7 +34,7 @@ def xtransformer_forward(sd, x, image_size, channels, heads):
     h = F.linear(h, sd["transformer.project_in.weight"], sd["transformer.project_in.bias"])
     h = h + sd["transformer.pos_emb.emb.weight"][:T][None]
     dh = 64
-    mask = torch.ones(T, T, dtype=torch.bool).triu_(1)
+    mask = torch.ones(T, T, dtype=torch.bool, device=x.device).triu_(1)
     for j in range(xt_depth(sd)):
         p = "transformer.attn_layers.layers.%d." % (2 * j)
         n = F.layer_norm(h, (dim,), sd[p + "0.weight"], sd[p + "0.bias"])

@@ -85,7 +85,8 @@ def test_groupnorm_fwd_bwd(N, HW, C, swish):
     x, dy, add = rnd(N, HW, C, seed=1), rnd(N, HW, C, seed=2), rnd(N, HW, C, seed=3)
     gamma = 1 + 0.1 * torch.randn(C, device=DEV)
     beta = 0.1 * torch.randn(C, device=DEV)
-    ws = torch.empty(N * 64, device=DEV, dtype=torch.float64)
+    from feed_forward_vqgan_clip_b200 import _lib
+    ws = torch.full((int(_lib.load().ffvc_groupnorm_ws_doubles(N, HW, 32)),), float("nan"), device=DEV, dtype=torch.float64)
     mean, rstd = torch.empty(N * 32, device=DEV), torch.empty(N * 32, device=DEV)
     call("groupnorm_stats", x, ws, mean, rstd, N, HW, C, 32, 1e-6)
     y = torch.empty_like(x)
@@ -98,6 +99,16 @@ def test_groupnorm_fwd_bwd(N, HW, C, swish):
     dx = torch.empty_like(x)
     call("groupnorm_bwd", dy, x, mean, rstd, gamma, beta, ws, add, dx, N, HW, C, 32, swish)
     close(dx, xr.grad.permute(0, 2, 1) + add.float())
+    # reproducible and batch-invariant statistics (fixed-order reductions, partial sums per sample shaped by HW only): the
+    # same sample inside a batch of 2N samples gives bit-identical mean / rstd / dx, run after run
+    x2, dy2, add2 = torch.cat([x.flip(0), x]), torch.cat([dy.flip(0), dy]), torch.cat([add.flip(0), add])
+    ws2 = torch.full((int(_lib.load().ffvc_groupnorm_ws_doubles(2 * N, HW, 32)),), float("nan"), device=DEV, dtype=torch.float64)
+    m2, r2 = torch.empty(2 * N * 32, device=DEV), torch.empty(2 * N * 32, device=DEV)
+    call("groupnorm_stats", x2, ws2, m2, r2, 2 * N, HW, C, 32, 1e-6)
+    assert torch.equal(m2[N * 32:], mean) and torch.equal(r2[N * 32:], rstd)
+    dxx = torch.empty_like(x2)
+    call("groupnorm_bwd", dy2, x2, m2, r2, gamma, beta, ws2, add2, dxx, 2 * N, HW, C, 32, swish)
+    assert torch.equal(dxx[N:], dx)
 
 
 @pytest.mark.parametrize("ring", [0, 1])
@@ -125,7 +136,8 @@ def test_groupnorm_fused_single_kernel_forms(N, HW, C, swish, pipeline, ring, ff
     yr = u * torch.sigmoid(u) if swish else u
     close(y, yr.permute(0, 2, 1))
     mean2, rstd2, y2 = torch.empty_like(mean), torch.empty_like(rstd), torch.empty_like(x)
-    call("groupnorm_stats", x, ws, mean2, rstd2, N, HW, C, 32, 1e-6)
+    ws_two = torch.empty(int(_lib.load().ffvc_groupnorm_ws_doubles(N, HW, 32)), device=DEV, dtype=torch.float64)
+    call("groupnorm_stats", x, ws_two, mean2, rstd2, N, HW, C, 32, 1e-6)
     call("groupnorm_apply", x, mean2, rstd2, gamma, beta, y2, N, HW, C, 32, swish)
     assert torch.allclose(mean, mean2, atol=1e-5) and torch.allclose(rstd, rstd2, rtol=1e-4)
     assert (y.float() - y2.float()).abs().max().item() <= 2e-2 * y2.float().abs().max().item()

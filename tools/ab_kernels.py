@@ -123,7 +123,8 @@ def main():
         add = torch.randn(N, HW, C, device=DEV, generator=g).to(BF)
         y = torch.empty_like(x)
         gam, bet = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
-        gws = torch.empty((int(_lib.load().ffvc_groupnorm_ws_bytes(N, 32)) + 7) // 8, device=DEV, dtype=torch.float64)
+        gws = torch.empty(max((int(_lib.load().ffvc_groupnorm_ws_bytes(N, 32)) + 7) // 8, int(_lib.load().ffvc_groupnorm_ws_doubles(N, HW, 32))),
+                          device=DEV, dtype=torch.float64)
         mean, rstd = torch.empty(N * 32, device=DEV), torch.empty(N * 32, device=DEV)
         tb = N * HW * C * 2
 
