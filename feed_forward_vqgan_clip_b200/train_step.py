@@ -254,6 +254,8 @@ class TrainStep:
         call("cast_bf16_f32", dzq, dzq32, dzq.numel())
         dz = torch.empty_like(dzq32)
         call("clamp_bwd", dzq32, z, dz, dz.numel(), self.z_lo, self.z_hi)
+        if self.debug is not None:
+            self.debug.update(dz=dz.clone())
         if self.l2_coef > 0:                                             # l2_coef * mean(z**2) on the pre-clamp z, main.py:758-762
             call("sumsq", z, self.aux_loss[0:1], z.numel())
             self.aux_loss[0:1].mul_(self.l2_coef / z.numel())

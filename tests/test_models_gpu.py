@@ -312,12 +312,15 @@ def test_train_step_vs_oracle_step():
     for (n, p), gv in zip(net.named_parameters(), eng.grad_views):
         sims[n] = cos(gv, ref_grads[n])
     big = [n for n, p in net.named_parameters() if p.numel() >= 4096]
-    assert min(sims[n] for n in big) > 0.95, sims
+    print("step-vs-oracle: min gradient cosine over the big parameters %.5f" % min(sims[n] for n in big))
+    assert min(sims[n] for n in big) > 0.99, sims            # measured 0.994 (end to end, bf16 against fp32)
     # Adam moved every parameter by ~lr in the direction of -sign(grad): compare the update direction
     for n, p in net.named_parameters():
         if p.numel() >= 4096:
             du, dr = p.detach().cpu() - sd_m[n], ref_params[n] - sd_m[n]
-            assert cos(du, dr) > 0.8, (n, cos(du, dr))   # sign-like first Adam step: tiny gradients flip sign
+            print("adam update direction cosine", n, "%.4f" % cos(du, dr))
+            assert cos(du, dr) > 0.9, (n, cos(du, dr))   # sign-like first Adam step (update = -lr * g / (|g| + eps)): gradient
+            #                                              elements near zero flip sign at full weight; measured 0.933 - 0.944
 
 
 def test_train_step_vitgan_with_l2_and_tv_vs_oracle_step():
@@ -359,7 +362,10 @@ def test_train_step_vitgan_with_l2_and_tv_vs_oracle_step():
                         mapper="vitgan", num_heads=6)
     otr.step(x, x, prm, force_idx=ts.last_indices.cpu().long())   # same code indices as the CUDA step (argmin is discontinuous)
     sims = {n: cos(gv, otr.grads[n]) for (n, p), gv in zip(net.named_parameters(), eng.grad_views) if p.numel() >= 4096}
-    assert min(sims.values()) > 0.95, sims
+    print("vitgan step-vs-oracle: min gradient cosine %.5f" % min(sims.values()))
+    # measured 0.9894: end to end through the TV term, whose gradient is sign(difference of neighbouring pixels) — discontinuous
+    # wherever two neighbours are closer than the bf16 image error (the stage-wise checks of the engines hold 0.99)
+    assert min(sims.values()) > 0.98, sims
 
 
 def test_generate_inference_path_vs_oracle():
@@ -420,8 +426,11 @@ def test_cuda_graph_replay_matches_eager():
     a.capture(2, 64)                       # warm-up step + captured step ran once each during capture
     la = a.replay(x.pin_memory(), None, ident).item()
     assert la == la and 0 < la < 10
-    assert a.opt.t == 2 + 0 or True        # counters live on the device; just make sure replay advances parameters
+    # the optimizer's step counter lives on the device (hyper[8], include/ffvc.h): the warm-up step inside capture() ran once,
+    # the capture itself executes nothing, every replay advances it by one
+    assert int(a.opt.hyper[8].item()) == 2
     before = a.mix.arena.clone()
     a.replay(x.pin_memory(), None, ident)
     torch.cuda.synchronize()
+    assert int(a.opt.hyper[8].item()) == 3
     assert not torch.equal(before, a.mix.arena)

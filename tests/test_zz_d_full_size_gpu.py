@@ -81,20 +81,21 @@ def test_config2_full_size_step_is_invariant_to_batch_sharding():
         idx.append(ts.last_indices.clone().view(hi - lo, -1))
     acc /= world
     torch.cuda.synchronize()
-    # Rows of z that are bit-identical pick identical codes.  The GEMM tile configuration is chosen per problem size, so a row
-    # of z may differ in its last bf16 bit between the two batch sizes and flip a near-tie of the arg-min; a flipped code
-    # changes that sample's image locally and with it a slice of the gradient — hence "almost all" and a cosine bound that a
-    # mis-routed augmentation parameter or a wrong loss normalisation (cosine << 0.9) still fails by a wide margin.
-    same = (torch.cat(idx) == idx_full).float().mean().item()
-    assert same >= 0.995, same
+    # Every forward kernel is reproducible and batch-invariant (a GEMM output element is the same K-ordered sum whatever the tile
+    # configuration; GroupNorm statistics are fixed-order reductions whose partial sums depend on the sample's shape only — round 2),
+    # so each prompt's z, code indices, image and embedding are BIT-IDENTICAL however the batch is cut (asserted below on the
+    # indices and the loss; profiles/r02_diag_fullsize_after_fix.md for the tensors).  Round 1 failed here with cosine 0.9867:
+    # float atomics in the GroupNorm statistics made the image differ by 0.85 % from run to run, and the reference's discontinuous
+    # gradient (max-pool arg-max routing, HSV sectors) turned that into a 16 % gradient difference — of the step against ITSELF.
+    # What remains is backward-only: fp32 atomics in the cutout scatter and the wgrad split-K, re-rounded to bf16 by the decoder's
+    # and the mapper's activation-gradient chain (measured: d(z_q) cosine 0.99991, gradient cosine 0.99978, rel 0.021).
+    assert torch.equal(torch.cat(idx), idx_full)
     mean_loss = sum(losses) / world
-    assert abs(mean_loss - loss_full) <= 5e-3 * abs(loss_full), (mean_loss, loss_full)
+    assert abs(mean_loss - loss_full) <= 1e-5 * abs(loss_full), (mean_loss, loss_full)
     a, b = acc.double(), g_full.double()
     cosine = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300))
     rel = float((a - b).norm() / (b.norm() + 1e-300))
-    assert cosine >= 0.99 and rel <= 0.15, (cosine, rel)
-    if same == 1.0:                                   # no flipped code: only the order of the fp32 wgrad accumulation differs
-        assert cosine >= 0.9995 and rel <= 3e-2, (cosine, rel)
+    assert cosine >= 0.9995 and rel <= 3e-2, (cosine, rel)
 
 
 def test_full_size_vq_rows_are_nearest_codebook_rows():
@@ -124,44 +125,25 @@ def test_full_size_vq_rows_are_nearest_codebook_rows():
 
 def test_config2_full_architecture_step_vs_oracle():
     """Parity at BASELINE config #2's real architecture (not a scaled-down stand-in): Mixer 32 x 1024, the full VQGAN f16/16384
-    decoder, CLIP ViT-B/32, 256 x 256, 8 cutouts, 2 prompts — the CUDA step against the CPU oracle step on the same bf16-rounded
-    weights, embeddings and augmentation parameters.  The oracle needs a few seconds per prompt on the box's host cores.
-    Tolerances (bf16 compute, 32 + 12 layers deep, against fp32): loss 2 %, code indices 95 %, gradient cosine 0.95 — the CPU
-    statement of the ABI (tests/abi_model.py), which rounds to bf16 at the same places, gives 1e-4, 98.4 % and 0.987."""
-    import oracle.clip_vit as oclip
-    import oracle.mixer as omix
-    import oracle.vqgan as ovq
-    from oracle.train_step import OracleTrainer
+    decoder, CLIP ViT-B/32, 256 x 256, 8 cutouts, 8 prompts — the CUDA step against the fp32 oracle (plain torch on the GPU, TF32
+    off) on the same bf16-rounded weights, embeddings and augmentation parameters (tests/fullsize_parity.py).
 
-    def r16(sd):
-        return {k: (v.to(torch.bfloat16).float() if v.dim() >= 2 else v.clone()) for k, v in sd.items()}
-    sd_m = r16(omix.init_mixer_state_dict(512, 16, 256, 1024, 32, seed=0))
-    sd_v, sd_c = r16(ovq.init_vqgan_state_dict(seed=1)), r16(oclip.init_clip_state_dict(seed=2))
-    net = Mixer(**MIXER)
-    net.load_state_dict(sd_m)
-    vq = VQModel()
-    vq.load_state_dict(sd_v)
-    clip = CLIP()
-    clip.visual.load_state_dict(sd_c)
-    net, vq, clip = net.to(DEV), vq.to(DEV).eval().requires_grad_(False), clip.to(DEV).eval().requires_grad_(False)
-    nb = 2
-    g = torch.Generator().manual_seed(3)
-    x = (torch.randn(nb, 512, generator=g) * 0.45).to(torch.bfloat16).float()
-    prm = sample_params(CUTN * nb, CUT, g)
-    ts = TrainStep(net, vq, clip, cutn=CUTN, lr=1e-3)
-    loss = float(ts.step(x.to(DEV), None, prm).item())
-    idx = ts.last_indices.cpu().long()
-    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 256, cutn=CUTN)
-    ref = otr.step(x, x, prm, force_idx=idx)          # gradients on the codes the CUDA step picked (the arg-min is discontinuous)
-    assert abs(loss - ref) <= 2e-2 * abs(ref), (loss, ref)
-    cb = sd_v["quantize.embedding.weight"]
-    zt = otr.last_z.detach().reshape(nb, 256, 256).permute(0, 2, 1).reshape(nb * 256, 256).clamp(otr.z_lo, otr.z_hi)
-    own = torch.cat([(zt[i:i + 128, None, :] - cb[None]).pow(2).sum(-1).argmin(1) for i in range(0, zt.shape[0], 128)])
-    assert (own == idx.view(-1)).float().mean().item() >= 0.95
-    eng = net.engine()
-    worst = 1.0
-    for (n, p), gv in zip(net.named_parameters(), eng.grad_views):
-        if p.numel() >= 65536:
-            a, b = gv.detach().float().cpu().flatten().double(), otr.grads[n].flatten().double()
-            worst = min(worst, float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-300)))
-    assert worst >= 0.95, worst
+    The stated tolerance at this depth (bf16 compute, 32 + ~60 + 12 layers, against fp32):
+      forward   L2-relative error <= 2e-2 for z, the image and the embeddings; loss within 1e-3; >= 95 % of the code indices
+      backward  every stage's vector-Jacobian product, evaluated at the same inputs with the same cotangent: cosine >= 0.99
+                (measured 0.9999 cutouts + CLIP + loss, 0.9990 decoder, 0.9998 mapper — profiles/r02_parity_fullsize.md)
+      end to end  each path differentiates at ITS OWN image, and the reference's gradient is discontinuous in the image (max-pool
+                arg-max, HSV sectors, clamps; main.py:218,171-172,142): the fp32 oracle against ITSELF, with its image perturbed by
+                noise of the size of the CUDA path's image error (0.8 %), keeps only cosine ~0.93 of d(image).  The end-to-end
+                gradient must be at least as close to the oracle as the oracle is to its own perturbed evaluation, and >= 0.97."""
+    from fullsize_parity import report
+    r = report(nb=8)
+    assert abs(r["loss_cuda"] - r["loss_oracle"]) <= 1e-3 * abs(r["loss_oracle"]), r
+    assert r["idx_agreement"] >= 0.95, r["idx_agreement"]
+    for k in ("z", "img", "emb"):
+        assert r[k]["rel"] <= 2e-2 and r[k]["cos"] >= 0.9995, (k, r[k])
+    for k in ("stage_dimg", "stage_dzq", "stage_dparams"):
+        assert r[k]["cos"] >= 0.99, (k, r[k])
+    assert r["stage_dparams"]["worst_cos"] >= 0.99, r["stage_dparams"]
+    assert r["e2e_grad"]["cos"] >= max(0.97, r["sensitivity"]["cos"]), (r["e2e_grad"], r["sensitivity"])
+    assert r["e2e_grad"]["worst_cos"] >= 0.97, r["e2e_grad"]
