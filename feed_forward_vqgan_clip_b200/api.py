@@ -161,4 +161,8 @@ def train_step(net, vq, perceptor, config=None, **kw):
                      scheduler=_get(cfg, "scheduler", None), use_ema=bool(_get(cfg, "use_ema", False)),
                      total_steps=kw.pop("total_steps", None) or _get(cfg, "max_steps", 0) or 0,      # main.py:704-705: T_max = config.max_steps
                      ema_decay=_get(cfg, "ema_decay", 0.995),
-                     diversity_mode=_get(cfg, "diversity_mode", "between_same_prompts"), **kw)
+                     diversity_mode=_get(cfg, "diversity_mode", "between_same_prompts"),
+                     input_loss=bool(_get(cfg, "input_loss", False)), input_loss_coef=_get(cfg, "input_loss_coef", 1),   # main.py:690-691
+                     normalize_input=bool(_get(cfg, "normalize_input", False)),                                      # main.py:696
+                     noise_dim=_get(cfg, "noise_dim", 0) or 0, nb_noise=_get(cfg, "nb_noise", None), **kw)           # main.py:457,649
+    # (`tv_exponent`, main.py:699, is read by the reference and never used: tv_loss takes no exponent, main.py:423-428)

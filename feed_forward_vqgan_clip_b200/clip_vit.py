@@ -111,6 +111,7 @@ class ClipEngine:
         self.dev = vis.proj.device
         ops.require_cuda(self.dev, "the CLIP image encoder")
         self._ptr = vis.proj.data_ptr()
+        self._ver = tuple(p._version for p in vis.parameters())        # an in-place load_state_dict invalidates the packed weights
         self.W, self.L, self.Hh, self.E = cfg["width"], cfg["layers"], cfg["heads"], cfg["output_dim"]
         self.patch = cfg["patch_size"]
         self.G = cfg["input_resolution"] // self.patch
@@ -131,7 +132,7 @@ class ClipEngine:
             self.w[p + "pj"] = sd[p + "mlp.c_proj.weight"].contiguous().to(BF16)
 
     def valid(self):
-        return self.vis.proj.data_ptr() == self._ptr
+        return self.vis.proj.data_ptr() == self._ptr and tuple(p._version for p in self.vis.parameters()) == self._ver
 
     def _new(self, *shape, dtype=BF16):
         return torch.empty(*shape, device=self.dev, dtype=dtype)

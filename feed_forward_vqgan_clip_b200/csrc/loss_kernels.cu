@@ -12,52 +12,76 @@
 namespace ffvc {
 
 // embed: [N][D] fp32, target: [B][D] fp32 (row n uses target[n % B]).  loss_out: one float (accumulated, zeroed by caller).
+// target2 / coef2 (optional): the reference's `input_loss` term (main.py:812-824) — the same distance to a second target
+// (the source embeddings) added with its own coefficient; both terms share the normalised image embedding.
 __global__ void __launch_bounds__(256) spherical_loss_kernel(const float* __restrict__ embed, const float* __restrict__ target,
-                                                             float* __restrict__ loss_out, float* __restrict__ dembed,
-                                                             __nv_bfloat16* __restrict__ dembed_bf16, int N, int B, int D,
-                                                             float coef) {
+                                                             const float* __restrict__ target2, float* __restrict__ loss_out,
+                                                             float* __restrict__ dembed, __nv_bfloat16* __restrict__ dembed_bf16,
+                                                             int N, int B, int D, float coef, float coef2) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + warp;
   if (n >= N) return;
   const float* e = embed + (long long)n * D;
-  const float* t = target + (long long)(n % B) * D;
-  float se = 0.f, st = 0.f;
-  for (int i = lane; i < D; i += 32) {
-    se += e[i] * e[i];
-    st += t[i] * t[i];
-  }
+  float se = 0.f;
+  for (int i = lane; i < D; i += 32) se += e[i] * e[i];
   se = warp_sum(se);
-  st = warp_sum(st);
-  const float ne = fmaxf(sqrtf(se), 1e-12f), nt = fmaxf(sqrtf(st), 1e-12f);  // F.normalize eps
-  const float ie = 1.0f / ne, it = 1.0f / nt;
-  float d2 = 0.f, dot_eh_g = 0.f;
-  for (int i = lane; i < D; i += 32) {
-    const float diff = t[i] * it - e[i] * ie;
-    d2 += diff * diff;
+  const float ie = 1.0f / fmaxf(sqrtf(se), 1e-12f);   // F.normalize eps
+  // per target k: it[k] = 1 / |t|, s[k] = coef_k / N * dl/dd / d  (dl/dd = 2 * a / sqrt(1 - d^2/4), a = asin(d / 2))
+  float its[2] = {0.f, 0.f}, ss[2] = {0.f, 0.f}, lsum = 0.f;
+  const float* ts[2] = {target + (long long)(n % B) * D, target2 ? target2 + (long long)(n % B) * D : nullptr};
+  const float cs[2] = {coef, coef2};
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float* t = ts[k];
+    if (!t) continue;
+    float st = 0.f;
+    for (int i = lane; i < D; i += 32) st += t[i] * t[i];
+    st = warp_sum(st);
+    const float it = 1.0f / fmaxf(sqrtf(st), 1e-12f);
+    float d2 = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float diff = t[i] * it - e[i] * ie;
+      d2 += diff * diff;
+    }
+    d2 = warp_sum(d2);
+    const float d = sqrtf(d2);
+    const float half = fminf(0.5f * d, 1.0f);
+    const float a = asinf(half);
+    lsum += cs[k] * 2.0f * a * a;
+    const float dl_dd = (d > 0.f) ? 2.0f * a * rsqrtf(fmaxf(1.0f - half * half, 1e-12f)) : 0.f;
+    its[k] = it;
+    ss[k] = (d > 0.f) ? (cs[k] / N) * dl_dd / d : 0.f;
   }
-  d2 = warp_sum(d2);
-  const float d = sqrtf(d2);
-  const float half = fminf(0.5f * d, 1.0f);
-  const float a = asinf(half);
-  const float l = 2.0f * a * a;
-  if (lane == 0) atomicAdd(loss_out, coef * l / N);
-  // dl/dd = 2 * a / sqrt(1 - d^2/4);  dl/d(ehat) = dl/dd * (ehat - Hhat) / d
-  const float dl_dd = (d > 0.f) ? 2.0f * a * rsqrtf(fmaxf(1.0f - half * half, 1e-12f)) : 0.f;
-  const float s = (d > 0.f) ? (coef / N) * dl_dd / d : 0.f;
-  // g = s * (ehat - Hhat);  de = (g - ehat * <g, ehat>) / |e|
+  if (lane == 0) atomicAdd(loss_out, lsum / N);
+  // g = sum_k s_k * (ehat - Hhat_k);  de = (g - ehat * <g, ehat>) / |e|
+  float dot_eh_g = 0.f;
   for (int i = lane; i < D; i += 32) {
     const float eh = e[i] * ie;
-    const float g = s * (eh - t[i] * it);
+    float g = ss[0] * (eh - ts[0][i] * its[0]);
+    if (ts[1]) g += ss[1] * (eh - ts[1][i] * its[1]);
     dot_eh_g += g * eh;
   }
   dot_eh_g = warp_sum(dot_eh_g);
   for (int i = lane; i < D; i += 32) {
     const float eh = e[i] * ie;
-    const float g = s * (eh - t[i] * it);
+    float g = ss[0] * (eh - ts[0][i] * its[0]);
+    if (ts[1]) g += ss[1] * (eh - ts[1][i] * its[1]);
     const float de = (g - eh * dot_eh_g) * ie;
     if (dembed) dembed[(long long)n * D + i] = de;
     if (dembed_bf16) dembed_bf16[(long long)n * D + i] = __float2bfloat16(de);
   }
+}
+
+// y[r] = x[r] / max(|x[r]|, 1e-12): F.normalize(inp_feats, dim=1) of `normalize_input` (main.py:734-735); one warp per row
+__global__ void __launch_bounds__(256) normalize_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) s += x[(long long)r * D + i] * x[(long long)r * D + i];
+  s = warp_sum(s);
+  const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+  for (int i = lane; i < D; i += 32) y[(long long)r * D + i] = x[(long long)r * D + i] * inv;
 }
 
 // Total-variation loss of main.py:423-428 on an NHWC fp32 image, forward + backward fused:
@@ -108,8 +132,23 @@ extern "C" int ffvc_spherical_loss(const float* embed, const float* target, floa
                                    void* dembed_bf16, int N, int B, int D, float coef, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaMemsetAsync(loss_out, 0, sizeof(float), st);
-  spherical_loss_kernel<<<(N + 7) / 8, 256, 0, st>>>(embed, target, loss_out, dembed,
-                                                    reinterpret_cast<__nv_bfloat16*>(dembed_bf16), N, B, D, coef);
+  spherical_loss_kernel<<<(N + 7) / 8, 256, 0, st>>>(embed, target, nullptr, loss_out, dembed,
+                                                    reinterpret_cast<__nv_bfloat16*>(dembed_bf16), N, B, D, coef, 0.f);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_spherical_loss2(const float* embed, const float* target, const float* target2, float* loss_out, float* dembed,
+                                    void* dembed_bf16, int N, int B, int D, float coef, float coef2, void* stream) {
+  if (!target2) return set_error(FFVC_ERR_ARG, "spherical_loss2: null second target");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaMemsetAsync(loss_out, 0, sizeof(float), st);
+  spherical_loss_kernel<<<(N + 7) / 8, 256, 0, st>>>(embed, target, target2, loss_out, dembed,
+                                                    reinterpret_cast<__nv_bfloat16*>(dembed_bf16), N, B, D, coef, coef2);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_normalize_rows(const float* x, float* y, int rows, int D, void* stream) {
+  normalize_rows_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, y, rows, D);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

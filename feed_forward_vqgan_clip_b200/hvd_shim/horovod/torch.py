@@ -107,7 +107,8 @@ def broadcast(tensor, root_rank=0, name=None):
 
 
 def broadcast_(tensor, root_rank=0, name=None):
-    tensor.data.copy_(broadcast(tensor, root_rank))
+    with torch.no_grad():                      # not through .data: the version counter must move (engines key their caches on it)
+        tensor.copy_(broadcast(tensor, root_rank))
     return tensor
 
 

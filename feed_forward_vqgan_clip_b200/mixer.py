@@ -154,7 +154,7 @@ class MixerEngine:
 
     def refresh_shadow(self):
         ver = tuple(p._version for p in self.params)
-        if self.ext_shadow_fresh or ver == self._shadow_version:
+        if (self.ext_shadow_fresh and ver == getattr(self, "_adam_ver", ver)) or ver == self._shadow_version:
             self.ext_shadow_fresh = False
             self._shadow_version = ver
             return

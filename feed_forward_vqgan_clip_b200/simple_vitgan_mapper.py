@@ -127,7 +127,7 @@ class SimpleVitGANEngine:
 
     def refresh_shadow(self):
         ver = tuple(p._version for p in self.params)
-        if not (self.ext_shadow_fresh or ver == self._shadow_version):
+        if not ((self.ext_shadow_fresh and ver == getattr(self, "_adam_ver", ver)) or ver == self._shadow_version):
             call("cast_f32_bf16", self.arena, self.shadow, self.total)
         for i in range(self.L):     # 2 small re-packs per block from the fp32 masters (3.2 M + 1.1 M elements at dim 1024)
             p = "Transformer_Encoder.blocks.%d.attn." % i

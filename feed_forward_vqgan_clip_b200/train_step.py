@@ -84,7 +84,8 @@ class FusedAdam:
                  hi - lo, self.hyper)
         else:
             call("adam_step", e.arena[lo:hi], e.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], shadow, hi - lo, self.hyper)
-        e.ext_shadow_fresh = True
+        e.ext_shadow_fresh = True                      # the kernel refreshed the bf16 shadow ...
+        e._adam_ver = tuple(p._version for p in e.params)   # ... of the parameters as they are NOW (a later in-place write voids it)
 
     def apply(self):
         """tick the device-side step counter (bias corrections, lr, clip coefficient) and update parameters + bf16 shadow
@@ -164,7 +165,8 @@ class TrainStep:
     def __init__(self, net, vq, perceptor, cutn=8, lr=1e-3, cut_size=224, target_loss_coef=1.0, world_size=1,
                  process_group=None, seed=0, l2_coef=0.0, tv_coef=0.0, diversity_coef=0.0, repeat=1, lpips_net=None,
                  clip_grad_norm=None, scheduler=None, total_steps=0, use_ema=False, ema_decay=0.995,
-                 diversity_mode="between_same_prompts"):
+                 diversity_mode="between_same_prompts", input_loss=False, input_loss_coef=1.0, normalize_input=False,
+                 noise_dim=0, nb_noise=None):
         self.net, self.vq, self.perceptor = net, vq, perceptor
         self.mix = net.engine()
         self.dec = vq.engine()
@@ -180,6 +182,12 @@ class TrainStep:
         if diversity_mode not in ("between_same_prompts", "all"):       # main.py:695,788-789
             raise ValueError("diversity_mode should be 'between_same_prompts' lr 'all'")
         self.diversity_mode = diversity_mode
+        # main.py:690-691,812-824: + input_loss_coef * the same spherical distance to the SOURCE embeddings
+        self.input_loss_coef = float(input_loss_coef) if input_loss else 0.0
+        self.normalize_input = bool(normalize_input)                      # main.py:696,734-735
+        # main.py:457,649,680-684,741-750: a noise vector concatenated to the mapper's input — fresh N(0,1) per row, or one of
+        # `nb_noise` fixed vectors per repeat group
+        self.noise_dim, self.nb_noise = int(noise_dim or 0), int(nb_noise or 0)
         self.opt = FusedAdam(self.mix, lr=lr)
         self.world, self.pg = world_size, process_group
         self.opt.set_grad_scale(1.0 / world_size)
@@ -204,6 +212,9 @@ class TrainStep:
         cb = self.dec.codebook
         self.z_lo, self.z_hi = float(cb.min()), float(cb.max())          # main.py:645-646,763 (global scalars)
         self.gen = torch.Generator().manual_seed(seed)
+        self.noise_bank = torch.randn(self.nb_noise, self.noise_dim, generator=self.gen) if (self.noise_dim and self.nb_noise) else None
+        if world_size > 1:
+            self._sync_replicas()
         self.loss = torch.zeros(1, device=self.dev, dtype=F32)
         self.graph = None
         self.static = None
@@ -218,7 +229,20 @@ class TrainStep:
         B = inp.shape[0]
         S, C = mix.S, mix.C
         N = self.cutn * B
-        z, sv_m = mix.forward(inp)                                       # [B*T, C] fp32
+        if self.normalize_input:                                         # main.py:734-735 (before the repeat / the loss targets)
+            inp_n = torch.empty_like(inp)
+            call("normalize_rows", inp, inp_n, B, inp.shape[1])
+            inp = inp_n
+        inp_net = inp
+        if self.noise_dim:                                               # main.py:741-750: cat((inp_feats, noise), dim=1)
+            E = inp.shape[1]
+            inp_net = torch.empty(B, E + self.noise_dim, device=self.dev, dtype=F32)
+            inp_net[:, :E].copy_(inp)
+            if prm.get("mapper_noise") is not None:
+                inp_net[:, E:].copy_(prm["mapper_noise"])
+            else:
+                inp_net[:, E:].normal_()
+        z, sv_m = mix.forward(inp_net)                                   # [B*T, C] fp32
         zq, idx, zc = dec.quantize(z, self.z_lo, self.z_hi)
         if self.force_idx is not None:                                   # diagnostics only (tools/diag_fullsize.py): decode these codes
             idx = self.force_idx.to(idx.dtype).view(-1)
@@ -228,7 +252,10 @@ class TrainStep:
         patches, sv_c, _ = cut.forward(img, prm)
         emb, sv_e = clip.forward(patches)
         demb = torch.empty(N, clip.E, device=self.dev, dtype=F32)
-        call("spherical_loss", emb, out_feats, self.loss, demb, None, N, B, clip.E, self.coef)
+        if self.input_loss_coef != 0.0:                                  # main.py:812-824
+            call("spherical_loss2", emb, out_feats, inp, self.loss, demb, None, N, B, clip.E, self.coef, self.input_loss_coef)
+        else:
+            call("spherical_loss", emb, out_feats, self.loss, demb, None, N, B, clip.E, self.coef)
         self.aux_loss.zero_()
         if self.debug is not None:
             self.debug.update(z=z.clone(), img=img.clone(), patches=patches.clone(), emb=emb.clone(), demb=demb.clone())
@@ -307,8 +334,22 @@ class TrainStep:
         self.opt.apply()
         return self.loss
 
+    def _sync_replicas(self):
+        """main.py:628-629 (hvd.broadcast_parameters / broadcast_optimizer_state): every rank starts from rank 0's weights and
+        optimizer state, whatever each rank was built or resumed from; only gradients are averaged afterwards."""
+        import torch.distributed as dist
+        o = self.opt
+        for t in (self.mix.arena, o.m, o.v, o.hyper) + ((o.ema,) if o.ema is not None else ()):
+            dist.broadcast(t, src=0, group=self.pg)
+        self.mix.ext_shadow_fresh = False
+        self.mix._shadow_version = None
+
     def new_params(self, B):
         prm = sample_params(self.cutn * B, self.cut_size, self.gen, with_noise=False)
+        if self.noise_bank is not None:      # main.py:742-746: `repeat` of the nb_noise fixed vectors, one per repeat group
+            inds = torch.randperm(self.nb_noise, generator=self.gen)[:self.repeat]
+            bs = B // self.repeat
+            prm["mapper_noise"] = self.noise_bank[inds].repeat_interleave(bs, dim=0).contiguous()
         return prm
 
     def _stage_params(self, prm, B):
@@ -318,6 +359,7 @@ class TrainStep:
         for k in ("affine_inv", "persp_inv", "sat", "hue"):
             out[k] = prm[k].to(dev, non_blocking=True)
         out["erase"] = torch.tensor([int(t) for t in prm["erase"]], dtype=torch.int32).to(dev, non_blocking=True)
+        out["mapper_noise"] = prm["mapper_noise"].to(dev, non_blocking=True) if prm.get("mapper_noise") is not None else None
         if "noise_raw" in prm:
             out["noise_raw"] = prm["noise_raw"].to(dev)
             out["facs"] = prm["facs"].to(dev)
@@ -345,10 +387,12 @@ class TrainStep:
                   persp_inv=torch.eye(3, device=dev).repeat(N, 1, 1).contiguous(),
                   sat=torch.ones(N, device=dev), hue=torch.zeros(N, device=dev),
                   erase=torch.zeros(4, device=dev, dtype=torch.int32))
+        st["mapper_noise"] = torch.zeros(B, self.noise_dim, device=dev) if self.noise_bank is not None else None
         self.static = st
 
         def body():
             prm = dict(affine_inv=st["affine_inv"], persp_inv=st["persp_inv"], sat=st["sat"], hue=st["hue"], erase=st["erase"],
+                       mapper_noise=st["mapper_noise"],
                        facs=torch.rand(N, device=dev) * 0.1,
                        noise_raw=torch.randn(N, 3, self.cut_size, self.cut_size, device=dev))
             self._device_step(st["inp"], st["out"], prm)
@@ -366,6 +410,22 @@ class TrainStep:
             body()
         return self
 
+    def load_static(self, inp, out_feats, prm):
+        """copy one step's inputs (embeddings, augmentation parameters) into the captured graph's static device buffers"""
+        st = self.static
+        B = st["inp"].shape[0]
+        if out_feats is None:
+            out_feats = inp
+        if self.repeat > 1 and inp.shape[0] * self.repeat == B:
+            inp, out_feats = inp.repeat(self.repeat, 1), out_feats.repeat(self.repeat, 1)
+        st["inp"].copy_(inp, non_blocking=True)
+        st["out"].copy_(out_feats, non_blocking=True)
+        for k in ("affine_inv", "persp_inv", "sat", "hue"):
+            st[k].copy_(prm[k], non_blocking=True)
+        st["erase"].copy_(torch.tensor([int(t) for t in prm["erase"]], dtype=torch.int32), non_blocking=True)
+        if st.get("mapper_noise") is not None:
+            st["mapper_noise"].copy_(prm["mapper_noise"], non_blocking=True)
+
     def replay(self, inp, out_feats=None, prm=None):
         """inp may be a pinned host tensor (H2D copy on the current stream) or a device tensor.  With prm=None the
         augmentation parameters of the NEXT call are drawn right after this step's graph launch, i.e. while the GPU works."""
@@ -375,15 +435,11 @@ class TrainStep:
             out_feats = inp
         if self.repeat > 1 and inp.shape[0] * self.repeat == B:          # main.py:739-740: the prompt batch is repeated, as step() does
             inp, out_feats = inp.repeat(self.repeat, 1), out_feats.repeat(self.repeat, 1)
-        st["inp"].copy_(inp, non_blocking=True)
-        st["out"].copy_(out_feats, non_blocking=True)
         presample = prm is None
         if presample:
             prm = self._next_prm if self._next_prm is not None else self.new_params(B)
             self._next_prm = None
-        for k in ("affine_inv", "persp_inv", "sat", "hue"):
-            st[k].copy_(prm[k], non_blocking=True)
-        st["erase"].copy_(torch.tensor([int(t) for t in prm["erase"]], dtype=torch.int32), non_blocking=True)
+        self.load_static(inp, out_feats, prm)
         self.graph.replay()
         if presample:
             self._next_prm = self.new_params(B)

@@ -155,7 +155,7 @@ class VitGANEngine:
 
     def refresh_shadow(self):
         ver = tuple(p._version for p in self.params)
-        fresh = self.ext_shadow_fresh or ver == self._shadow_version
+        fresh = (self.ext_shadow_fresh and ver == getattr(self, "_adam_ver", ver)) or ver == self._shadow_version
         if not fresh:
             call("cast_f32_bf16", self.arena, self.shadow, self.total)
         for i in range(self.L):   # the padded copies are cheap (1 M elements per block): refresh every forward

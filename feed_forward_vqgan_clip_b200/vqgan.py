@@ -150,6 +150,7 @@ class DecoderEngine:
         self.dev = model.post_quant_conv.weight.device
         ops.require_cuda(self.dev, "the VQGAN decoder")
         self._ptr = model.post_quant_conv.weight.data_ptr()
+        self._ver = tuple(p._version for p in model.parameters())      # an in-place load_state_dict invalidates the packed weights
         self.layout = _decoder_layout(self.cfg)
         self.pk = {}
         sd = {k: v.detach() for k, v in model.state_dict().items()}
@@ -183,7 +184,8 @@ class DecoderEngine:
         self._epi_stats = {}            # data_ptr of a conv output -> (mean, rstd, numel) from that conv's epilogue
 
     def valid(self):
-        return self.model.post_quant_conv.weight.data_ptr() == self._ptr
+        return (self.model.post_quant_conv.weight.data_ptr() == self._ptr
+                and tuple(p._version for p in self.model.parameters()) == self._ver)
 
     def _new(self, *shape, dtype=BF16):
         return torch.empty(*shape, device=self.dev, dtype=dtype)

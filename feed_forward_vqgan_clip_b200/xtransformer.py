@@ -142,7 +142,7 @@ class XTEngine:
 
     def refresh_shadow(self):
         ver = tuple(p._version for p in self.params)
-        if not (self.ext_shadow_fresh or ver == self._shadow_version):
+        if not ((self.ext_shadow_fresh and ver == getattr(self, "_adam_ver", ver)) or ver == self._shadow_version):
             call("cast_f32_bf16", self.arena, self.shadow, self.total)
         self.ext_shadow_fresh = False
         self._shadow_version = ver

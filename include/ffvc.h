@@ -293,6 +293,12 @@ int ffvc_cutout_final_bwd(const float* cut1, const float* hinv, const float* sat
 /* spherical distance loss fwd+bwd (main.py:801-811): loss_out (1 float), dembed fp32 and/or bf16 [N][D]. */
 int ffvc_spherical_loss(const float* embed, const float* target, float* loss_out, float* dembed, void* dembed_bf16, int N,
                         int B, int D, float coef, void* stream);
+/* same with the reference's `input_loss` term (main.py:812-824): + coef2 * the same distance to a second target [B][D] (the
+ * source embeddings), one pass, one gradient */
+int ffvc_spherical_loss2(const float* embed, const float* target, const float* target2, float* loss_out, float* dembed,
+                         void* dembed_bf16, int N, int B, int D, float coef, float coef2, void* stream);
+/* y[r] = x[r] / max(|x[r]|, 1e-12) — F.normalize(inp_feats, dim=1) of `normalize_input` (main.py:734-735); fp32 [rows][D] */
+int ffvc_normalize_rows(const float* x, float* y, int rows, int D, void* stream);
 
 /* total-variation loss (main.py:423-428) on NHWC fp32, fwd+bwd: loss_accum += coef*tv, dimg_accum += coef*d(tv)/d(img);
  * axpy for the z-L2 term's gradient (main.py:758-762). */

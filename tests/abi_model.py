@@ -576,6 +576,27 @@ def k_spherical_loss(embed, target, loss_out, dembed, dembed_bf16, N, B, D, coef
         dembed_bf16.view(-1)[:N * D] = g.reshape(-1)
 
 
+def k_spherical_loss2(embed, target, target2, loss_out, dembed, dembed_bf16, N, B, D, coef, coef2):
+    """main.py:801-824: the target term plus `input_loss_coef` times the same distance to the source embeddings"""
+    with torch.enable_grad():
+        e = embed.reshape(-1)[:N * D].view(N, D).clone().requires_grad_(True)
+        en = F.normalize(e, dim=-1)
+        loss = 0
+        for t, c in ((target, coef), (target2, coef2)):
+            Hh = F.normalize(t.reshape(-1)[:B * D].view(B, D).repeat(N // B, 1), dim=-1)
+            loss = loss + ((en - Hh).norm(dim=-1).div(2).arcsin().pow(2).mul(2)).mean() * c
+        g, = torch.autograd.grad(loss, e)
+    loss_out.view(-1)[0] = loss.detach()
+    if dembed is not None:
+        dembed.view(-1)[:N * D] = g.reshape(-1)
+    if dembed_bf16 is not None:
+        dembed_bf16.view(-1)[:N * D] = g.reshape(-1)
+
+
+def k_normalize_rows(x, y, rows, D):
+    y.view(-1)[:rows * D] = F.normalize(x.reshape(-1)[:rows * D].view(rows, D), dim=1).reshape(-1)
+
+
 def k_tv_loss(img, loss_accum, dimg_accum, B, H, W, C, coef):
     """main.py:423-428 on NHWC; ACCUMULATES into loss_accum / dimg_accum"""
     with torch.enable_grad():

@@ -168,7 +168,8 @@ def test_replay_host_logic_draws_next_parameters_after_the_launch():
               sat=torch.zeros(N), hue=torch.zeros(N), erase=torch.zeros(4, dtype=torch.int32))
     events = []
     fake = SimpleNamespace(static=st, graph=SimpleNamespace(replay=lambda: events.append("launch")), loss=torch.zeros(1), cutn=cutn,
-                           cut_size=224, gen=torch.Generator().manual_seed(1), _next_prm=None, repeat=1)
+                           cut_size=224, gen=torch.Generator().manual_seed(1), _next_prm=None, repeat=1, noise_bank=None)
+    fake.load_static = lambda *a: TrainStep.load_static(fake, *a)
 
     def new_params(b):
         events.append("sample")

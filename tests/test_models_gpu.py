@@ -368,6 +368,47 @@ def test_train_step_vitgan_with_l2_and_tv_vs_oracle_step():
     assert min(sims.values()) > 0.98, sims
 
 
+def test_train_step_input_loss_normalize_input_and_noise_vs_oracle_step():
+    """the optional objective pieces of main.py:690-696,734-750,812-824 through the fused step: `input_loss` (second spherical term
+    on the source embeddings), `normalize_input`, and a noise vector concatenated to the mapper input (nb_noise bank, repeat 2)"""
+    noise_dim, nb_noise, repeat = 8, 4, 2
+    mcfg = dict(input_dim=64 + noise_dim, image_size=16, channels=64, patch_size=1, dim=128, depth=2)
+    torch.manual_seed(17)
+    net = Mixer(**mcfg)
+    with torch.no_grad():
+        net.final_proj.weight.mul_(6.0)
+        for p in net.parameters():
+            if p.dim() >= 2:
+                p.copy_(p.to(torch.bfloat16).float())
+    sd_m = {k: v.clone() for k, v in net.state_dict().items()}
+    vq, sd_v = _vq_pair(seed=8)
+    sd_c = bf16_round_sd(oclip.init_clip_state_dict(SMALL_CLIP, seed=9))
+    clip = CLIP(SMALL_CLIP)
+    clip.visual.load_state_dict(sd_c)
+    clip = clip.to(DEV).eval().requires_grad_(False)
+    net = net.to(DEV)
+    B, cutn, lr = 2, 4, 1e-3
+    g = torch.Generator().manual_seed(18)
+    x = (torch.randn(B, 64, generator=g) * 0.45).to(torch.bfloat16).float()
+    tgt = (torch.randn(B, 64, generator=g) * 0.45).to(torch.bfloat16).float()
+    ts = TrainStep(net, vq, clip, cutn=cutn, lr=lr, repeat=repeat, input_loss=True, input_loss_coef=0.5, normalize_input=True,
+                   noise_dim=noise_dim, nb_noise=nb_noise, seed=5)
+    prm = ts.new_params(B * repeat)                       # cutout parameters + the step's rows of the noise bank
+    assert prm["mapper_noise"].shape == (B * repeat, noise_dim)
+    assert torch.equal(prm["mapper_noise"][0], prm["mapper_noise"][1]) and not torch.equal(prm["mapper_noise"][0], prm["mapper_noise"][B])
+    prm["noise"] = torch.zeros(cutn * B * repeat, 3, 224, 224)
+    prm["noise_raw"], prm["facs"] = torch.zeros(cutn * B * repeat, 3, 224, 224), torch.zeros(cutn * B * repeat)
+    loss = ts.step(x.to(DEV), tgt.to(DEV), prm)
+    torch.cuda.synchronize()
+    otr = OracleTrainer(sd_m, sd_v, sd_c, 16, 64, SMALL_VQ, SMALL_CLIP, cutn=cutn, lr=lr, repeat=repeat, input_loss_coef=0.5,
+                        normalize_input=True)
+    ref = otr.step(x, tgt, prm, force_idx=ts.last_indices.cpu().long())
+    assert abs(loss.item() - ref) < 3e-2 * abs(ref), (loss.item(), ref)
+    eng = net.engine()
+    sims = {n: cos(gv, otr.grads[n]) for (n, p), gv in zip(net.named_parameters(), eng.grad_views) if p.numel() >= 4096}
+    assert min(sims.values()) > 0.98, sims
+
+
 def test_generate_inference_path_vs_oracle():
     """main.py:1056-1059 (test) / predict.py:113-117: forward-only mapper -> clamp -> synth"""
     from feed_forward_vqgan_clip_b200 import api

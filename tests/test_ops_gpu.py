@@ -583,3 +583,26 @@ def test_maxpool_and_relu_epilogue():
     out2 = torch.empty(256, 128, device=DEV, dtype=BF)
     ops.gemm(a, b, out2, 256, 128, 64, aux=aux, mul_mode=ops.ACT_RELU)
     close(out2, (a.float() @ b.float().t()) * (aux.float() > 0))
+
+
+def test_spherical_loss_with_input_loss_term_and_normalize_rows():
+    """ffvc_spherical_loss2 (main.py:801-824: target term + input_loss_coef * source term) and ffvc_normalize_rows (main.py:734-735)
+    against the reference's expressions"""
+    g = torch.Generator().manual_seed(4)
+    N, B, D = 24, 6, 512
+    e = torch.randn(N, D, generator=g).to(DEV)
+    t1, t2 = (torch.randn(B, D, generator=g) * 3).to(DEV), (torch.randn(B, D, generator=g) * 0.2).to(DEV)
+    loss, de = torch.zeros(1, device=DEV), torch.empty(N, D, device=DEV)
+    call("spherical_loss2", e, t1, t2, loss, de, None, N, B, D, 1.0, 0.37)
+    er = e.clone().requires_grad_(True)
+    en = F.normalize(er, dim=1)
+    ref = sum(c * (F.normalize(t.repeat(N // B, 1), dim=-1).sub(en).norm(dim=-1).div(2).arcsin().pow(2).mul(2)).mean()
+              for t, c in ((t1, 1.0), (t2, 0.37)))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert torch.allclose(de, er.grad, atol=1e-7, rtol=1e-3)
+    x = (torch.randn(37, 96, generator=g) * 5).to(DEV)
+    x[3] = 0                                             # F.normalize's eps path
+    y = torch.empty_like(x)
+    call("normalize_rows", x, y, 37, 96)
+    assert torch.allclose(y, F.normalize(x, dim=1), atol=1e-6, rtol=1e-5)
