@@ -273,6 +273,9 @@ def main():
                     help="N>1: mixer layers per gradient all-reduce bucket (overlapped with backward); 0 = one all-reduce after backward")
     ap.add_argument("--tail-overlap", action="store_true",
                     help="N>1: run Adam on the already-reduced slices while the last gradient bucket is in flight")
+    ap.add_argument("--comm-sms", type=int, default=0,
+                    help="N>1: SMs left to NCCL while gradient buckets are in flight — sets NCCL_MAX_CTAS and sizes the persistent GEMM grids "
+                         "to (SMs - this) during the overlapped part of backward; 0 = off")
     ap.add_argument("--nccl-max-ctas", type=int, default=0,
                     help="N>1: cap the CTAs NCCL may use (NCCL_MAX_CTAS) so its kernels take fewer SMs from the persistent GEMMs they overlap; 0 = NCCL's default")
     args = ap.parse_args()
@@ -316,8 +319,8 @@ def main():
     pg = None
     if world > 1:
         import torch.distributed as dist
-        if args.nccl_max_ctas > 0:
-            os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas)
+        if args.nccl_max_ctas > 0 or args.comm_sms > 0:
+            os.environ["NCCL_MAX_CTAS"] = str(args.nccl_max_ctas or args.comm_sms)
         dist.init_process_group("nccl", device_id=dev)
         pg = dist.group.WORLD
 
@@ -325,6 +328,10 @@ def main():
     if args.bucket_layers is not None:
         ts.bucket_layers = args.bucket_layers
     ts.tail_overlap = bool(args.tail_overlap)
+    ts.comm_sms = args.comm_sms if world > 1 else 0
+    if world > 1:
+        config.update(bucket_layers=ts.bucket_layers, tail_overlap=ts.tail_overlap, comm_sms=ts.comm_sms,
+                      nccl_max_ctas=os.environ.get("NCCL_MAX_CTAS"))
     x_host = [synthetic_embeddings(B, 1000 + 7919 * rank + i).pin_memory() for i in range(4)]
     Bimg = B * rep                                            # rows of the (repeated) batch = generated images per step
 

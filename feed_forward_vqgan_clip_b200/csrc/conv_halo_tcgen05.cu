@@ -487,7 +487,7 @@ static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, i
     p.gn_beta = gnb_beta;
   }
   const long long tiles = (long long)n * (h / 2) * (wd / 128);
-  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  const int grid = (int)(tiles < sm_budget(num_sms) ? tiles : sm_budget(num_sms));
   // 16 epilogue warps for the GroupNorm-statistics epilogues (option "halo_epi16": 1 = backward statistics, 2 = forward too)
   const int epi16 = gn_ws ? option(OPT_HALO_EPI16) : 0;
   if (block_n == 128 && ((epi16 >= 1 && p.gn_bwd) || epi16 >= 2))

@@ -740,7 +740,7 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   // stream-K for the fp32-atomic (wgrad) GEMMs whose tile count does not fill the machine evenly: replaces split-K
   {
     const long long tiles0 = (long long)((g->M + tile_m - 1) / tile_m) * ((g->N + block_n - 1) / block_n) * batch;
-    const long long workers = (two_cta == 1) ? g_num_sms / 2 : g_num_sms;
+    const long long workers = (two_cta == 1) ? sm_budget(g_num_sms) / 2 : sm_budget(g_num_sms);
     const long long total_kb_h = (long long)p.kb_per_seg * k_segs;
     const long long waves_x100 = tiles0 * splits * 100 / workers;            // work items per worker, in percent
     const bool uneven = (waves_x100 % 100) != 0 && waves_x100 < 800;         // a fractional last wave that matters
@@ -787,7 +787,8 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   cfg.stream = stream;
   if (two_cta == 1) {
     // one CTA pair (cluster of 2) per tile, persistent over min(tiles, SMs/2) pairs
-    const long long pairs = (p.stream_k || tiles >= g_num_sms / 2) ? g_num_sms / 2 : tiles;
+    const int sms = sm_budget(g_num_sms);     // tile shapes above are chosen for the whole GPU (same arithmetic); only the grid shrinks
+    const long long pairs = (p.stream_k || tiles >= sms / 2) ? sms / 2 : tiles;
     cfg.gridDim = dim3((unsigned)(2 * pairs));
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
@@ -796,7 +797,8 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   } else {
-    cfg.gridDim = dim3((unsigned)((p.stream_k || tiles >= g_num_sms) ? g_num_sms : tiles));
+    const int sms = sm_budget(g_num_sms);
+    cfg.gridDim = dim3((unsigned)((p.stream_k || tiles >= sms) ? sms : tiles));
   }
   // TMA-store epilogue: compile-time epilogue on the pair kernel, bf16 output(s) whose rows / batches start on 16-byte boundaries
   CUtensorMap tms[4];

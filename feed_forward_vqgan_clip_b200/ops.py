@@ -41,6 +41,16 @@ def call(name, *args):
     check(fn(*[_arg(a) for a in args], _stream()))
 
 
+_NUM_SMS = None
+
+
+def num_sms():
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        _NUM_SMS = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    return _NUM_SMS
+
+
 def launch_count():
     return int(_lib.load().ffvc_launch_count())
 

@@ -208,6 +208,10 @@ class TrainStep:
         # opt-in (not yet measured on a GPU): start Adam on the slices whose all-reduce has already been issued while the last
         # bucket (head of the arena + late ranges) is still in flight; needs the clip coefficient off (it wants the whole norm)
         self.tail_overlap = False
+        # SMs left to NCCL while gradient buckets are in flight: the persistent tcgen05 grids are sized to (SMs - comm_sms) from the
+        # first bucket to the end of backward (option "sm_limit"), so that NCCL's CTAs do not push a GEMM's last CTAs into a second
+        # wave; pair it with NCCL_MAX_CTAS = comm_sms (bench.py --comm-sms).  0 = off.
+        self.comm_sms = 0
         self.comm_stream = torch.cuda.Stream(device=self.dev) if world_size > 1 else None
         cb = self.dec.codebook
         self.z_lo, self.z_hi = float(cb.min()), float(cb.max())          # main.py:645-646,763 (global scalars)
@@ -298,7 +302,12 @@ class TrainStep:
             main, comm = torch.cuda.current_stream(), self.comm_stream
             first_layer_of_bucket = {mix.L - min(mix.L, (k + 1) * self.bucket_layers): k for k in range(len(buckets) - 1)}
 
+            from . import _lib
+            lib = _lib.load()
+
             def reduce_bucket(slices):
+                if self.comm_sms > 0:
+                    lib.ffvc_set_option(b"sm_limit", max(2, ops.num_sms() - self.comm_sms))
                 ev = torch.cuda.Event()
                 ev.record(main)                       # the gradients of these slices are complete at this point of the main stream
                 comm.wait_event(ev)
@@ -321,11 +330,13 @@ class TrainStep:
                 for lo, hi in sorted(s_ for b in buckets[:-1] for s_ in b):
                     self.opt.step_range(lo, hi)       # overlaps the last bucket's all-reduce
                 main.wait_stream(comm)
+                lib.ffvc_set_option(b"sm_limit", 0)
                 for lo, hi in buckets[-1]:
                     self.opt.step_range(lo, hi)
                 return self.loss
             reduce_bucket(buckets[-1])
             main.wait_stream(comm)
+            lib.ffvc_set_option(b"sm_limit", 0)
         else:
             mix.backward(sv_m, dz)
             if self.world > 1:

@@ -313,3 +313,27 @@ def test_abi_model_satisfies_the_expectations_of_the_kernel_tests():
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
     assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:] + r.stderr[-1000:]
     assert int(tail.split(" passed")[0].split()[-1]) >= 90, tail
+
+
+def test_documented_ctypes_stub_matches_the_header():
+    """INTEGRATION.md's ctypes mirror of ffvc_gemm_params (generated by tools/gen_ctypes_stub.py) is executed as written: its size
+    equals ffvc_sizeof("ffvc_gemm_params") and its fields are the package's own mirror's, in order (round 1 shipped a stale stub)."""
+    import ctypes
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"<!-- BEGIN GENERATED STRUCT -->\s*```python\n(.*?)```", doc, flags=re.S).group(1)
+    ns = {}
+    exec(block, ns)
+    stub = ns["ffvc_gemm_params"]
+    assert ctypes.sizeof(stub) == _lib.load().ffvc_sizeof(b"ffvc_gemm_params") == ctypes.sizeof(_lib.GemmParams)
+    assert [f[0] for f in stub._fields_] == [f[0] for f in _lib.GemmParams._fields_]
+    for (n1, t1), (n2, t2) in zip(stub._fields_, _lib.GemmParams._fields_):
+        assert ctypes.sizeof(t1) == ctypes.sizeof(t2), (n1, t1, t2)
+    # regenerating from the header changes nothing
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_ctypes_stub", os.path.join(root, "tools", "gen_ctypes_stub.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    assert gen.stub().strip() in block
