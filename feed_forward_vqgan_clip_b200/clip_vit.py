@@ -165,6 +165,11 @@ class ClipEngine:
             a = self._new(N * T, W)
             call("mha_small_fwd", qkv, a, N, T, Hh, 64, 0.125)
             return a, None
+        if self.FUSED_ATTN and self.W == 64 * self.Hh:      # more than 64 tokens: tiled attention, saves the row log-sum-exp
+            a = self._new(N * T, W)
+            lse = self._new(N, Hh, T, dtype=F32)
+            call("mha_flash_fwd", qkv, a, lse, N, T, Hh, 64, 0.125, 0)
+            return a, lse
         S = self._new(N, Hh, T, TP, dtype=F32)
         ops.gemm(qkv, qkv, S, T, T, 64, a_ld=3 * W, b_ld=3 * W, b_off=W, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT,
                  batch=N * Hh, batch_inner=Hh, a_bs=T * 3 * W, b_bs=T * 3 * W, a_bs_in=64, b_bs_in=64, ldc=TP,
@@ -178,11 +183,15 @@ class ClipEngine:
                  b_bs_in=64, ldc=W, out_bs=T * W, out_bs_in=64, block_n=64)
         return a, P
 
-    def _attn_bwd(self, qkv, P, da, N):
+    def _attn_bwd(self, qkv, P, da, N, a=None):
         W, T, Hh, TP = self.W, self.T, self.Hh, self.TP
         if P is None:
             dqkv = self._new(N * T, 3 * W)
             call("mha_small_bwd", qkv, da, dqkv, N, T, Hh, 64, 0.125)
+            return dqkv
+        if P.dtype == F32:                    # log-sum-exp of the tiled forward
+            dqkv = self._new(N * T, 3 * W)
+            call("mha_flash_bwd", qkv, a, da, P, torch.empty_like(P), dqkv, N, T, Hh, 64, 0.125, 0)
             return dqkv
         kw = dict(batch=N * Hh, batch_inner=Hh, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT, block_n=64)
         dP = self._new(N, Hh, T, TP, dtype=F32)            # dP[i,j] = sum_d dO[i,d] V[j,d]
@@ -226,6 +235,7 @@ class ClipEngine:
             a, P = self._attn_fwd(qkv, N)
             h2 = self._new(M, W)
             ops.gemm(a, self.w[p + "out"], h2, M, W, W, bias=self.sd32[p + "attn.out_proj.bias"], res=h)
+            a_keep = a if (P is not None and P.dtype == F32) else None       # the tiled backward wants O (delta = rowsum(dO * O))
             del a
             n2, st2 = self._ln(h2, p + "ln_2", M)
             u, gact = self._new(M, 4 * W), self._new(M, 4 * W)
@@ -234,7 +244,7 @@ class ClipEngine:
             h3 = self._new(M, W)
             ops.gemm(gact, self.w[p + "pj"], h3, M, W, 4 * W, bias=self.sd32[p + "mlp.c_proj.bias"], res=h2)
             del gact
-            saved["layers"].append(dict(h=h, st1=st1, qkv=qkv, P=P, h2=h2, st2=st2, u=u))
+            saved["layers"].append(dict(h=h, st1=st1, qkv=qkv, P=P, a=a_keep, h2=h2, st2=st2, u=u))
             h = h3
         xc = self._new(N, W)
         call("copy_rows", h, xc, N, W, T * W, W)                     # class-token rows
@@ -268,7 +278,7 @@ class ClipEngine:
             dh2 = self._ln_bwd(dn2, lv["h2"], lv["st2"], p + "ln_2", M, add=dh)
             da = self._new(M, W)
             ops.linear_dgrad(dh2, self.w[p + "out"], da, M, W, W)
-            dqkv = self._attn_bwd(lv["qkv"], lv["P"], da, N)
+            dqkv = self._attn_bwd(lv["qkv"], lv["P"], da, N, a=lv["a"])
             dn1 = self._new(M, W)
             ops.linear_dgrad(dqkv, self.w[p + "in"], dn1, M, 3 * W, W)
             del dqkv

@@ -280,6 +280,248 @@ __global__ void __launch_bounds__(128) mha_small_bwd_kernel(const __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------------------------------------------ long sequences (T > 64)
+// Tiled ("flash") attention on the same 64 x 64 building blocks: the x-transformer mapper's causal attention at T = 1024
+// (transformer.py:11-20 / x-transformers Attention, 6 heads x 64) and any ViT at more than 64 tokens.  Round 1 ran these as two
+// batched tcgen05 GEMMs around a row softmax with the T x T scores (fp32) and probabilities (bf16) materialised in HBM: at
+// config #4 that was 0.6 GB per layer and direction, 19 % of the step (profiles/r02_step_breakdown_c4.md).  Here scores and
+// probabilities never leave the SM:
+//   forward    CTA = (sequence, head, 64 query rows); key blocks of 64 stream through shared memory; online softmax in the log2
+//              domain (running max m, running sum l), O rescaled per block; saves lse2 = m + log2(l) per row for the backward
+//   backward   delta[i] = rowsum(dO_i * O_i) (one warp per row), then
+//              dQ kernel : CTA = (sequence, head, query block), loop over key blocks: P = 2^(s2 - lse2), dP = dO V^T,
+//                          dS = P (dP - delta) scale, dQ += dS K
+//              dKV kernel: CTA = (sequence, head, key block), loop over query blocks: P and dS of the block go to shared memory,
+//                          dV += P^T dO, dK += dS^T Q  (accumulators stay in registers over the loop)
+// causal: key j attends query i only if j <= i (blocks above the diagonal are skipped, the diagonal block is masked).
+__device__ __forceinline__ void stage_tile_rows(const __nv_bfloat16* __restrict__ base, long long row_stride, int row0, int T,
+                                                __nv_bfloat16* dst) {
+  for (int i = threadIdx.x; i < kTmax * 8; i += blockDim.x) {
+    const int t = i >> 3, v = i & 7;
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + t < T) pk = *reinterpret_cast<const uint4*>(base + (long long)(row0 + t) * row_stride + v * 8);
+    *reinterpret_cast<uint4*>(dst + t * kPitch + v * 8) = pk;
+  }
+}
+// scores of rows (q0 + m0 + g, + 8) against keys k0 .. k0 + 63 -> log2-domain logits, -FLT_MAX where masked
+__device__ __forceinline__ void mask_scale(float (&s)[8][4], float k2, int qrow0, int k0, int T, int causal, int lane) {
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = k0 + nt * 8 + t2 + (e & 1);
+      const int row = qrow0 + g + ((e & 2) ? 8 : 0);
+      const bool ok = col < T && (!causal || col <= row);
+      s[nt][e] = ok ? s[nt][e] * k2 : -FLT_MAX;
+    }
+}
+
+__global__ void __launch_bounds__(128) mha_flash_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                                                            float* __restrict__ lse, int T, int heads, float scale, int causal) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(sm_raw);
+  __nv_bfloat16* ks = qs + kTileElems;
+  __nv_bfloat16* vs = ks + kTileElems;
+  const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int W = heads * kDh;
+  const __nv_bfloat16* base = qkv + (long long)n * T * 3 * W + h * kDh;
+  const int q0 = qb * 64;
+  stage_tile_rows(base, 3 * W, q0, T, qs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = warp * 16, g = lane >> 2;
+  const float k2 = scale * 1.4426950408889634f;
+  float o[8][4];
+  zero_acc(o);
+  float mx0 = -FLT_MAX, mx1 = -FLT_MAX, l0 = 0.f, l1 = 0.f;
+  const int nkb = causal ? (qb + 1) : (T + 63) / 64;
+  for (int kb = 0; kb < nkb; ++kb) {
+    __syncthreads();                                   // previous block's K / V fully consumed (and Q staged, first time)
+    stage_tile_rows(base + W, 3 * W, kb * 64, T, ks);
+    stage_tile_rows(base + 2 * W, 3 * W, kb * 64, T, vs);
+    __syncthreads();
+    float s[8][4];
+    zero_acc(s);
+    mm_rows_x_rows(s, smem_u32(qs), smem_u32(ks), m0, lane);
+    mask_scale(s, k2, q0 + m0, kb * 64, T, causal, lane);
+    float bm0 = -FLT_MAX, bm1 = -FLT_MAX;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      bm0 = fmaxf(bm0, fmaxf(s[nt][0], s[nt][1]));
+      bm1 = fmaxf(bm1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(mx0, bm0), nm1 = fmaxf(mx1, bm1);
+    const float c0 = ex2_approx(mx0 - nm0), c1 = ex2_approx(mx1 - nm1);     // 0 on the first block (mx = -FLT_MAX)
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float m = (e & 2) ? nm1 : nm0;
+        const float pv = s[nt][e] > -1e37f ? ex2_approx(s[nt][e] - m) : 0.f;
+        s[nt][e] = pv;
+        if (e & 2) rs1 += pv; else rs0 += pv;
+      }
+      o[nt][0] *= c0;
+      o[nt][1] *= c0;
+      o[nt][2] *= c1;
+      o[nt][3] *= c1;
+    }
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1);
+    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1);
+    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+    mx0 = nm0;
+    mx1 = nm1;
+    uint32_t pf[4][4];
+    acc_to_afrag(s, pf);
+    mm_frag_x_cols(o, pf, smem_u32(vs), lane);
+  }
+  const float i0 = l0 > 0.f ? 1.0f / l0 : 0.f, i1 = l1 > 0.f ? 1.0f / l1 : 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    o[nt][0] *= i0;
+    o[nt][1] *= i0;
+    o[nt][2] *= i1;
+    o[nt][3] *= i1;
+  }
+  store_rows(o, out + (long long)n * T * W + h * kDh + (long long)q0 * W, W, m0, T - q0, lane);
+  if ((lane & 3) == 0) {
+    float* lr = lse + ((long long)n * heads + h) * T;
+    if (q0 + m0 + g < T) lr[q0 + m0 + g] = mx0 + log2f(l0);
+    if (q0 + m0 + g + 8 < T) lr[q0 + m0 + g + 8] = mx1 + log2f(l1);
+  }
+}
+
+// delta[n][h][t] = sum_d dO[n][t][h*64 + d] * O[n][t][h*64 + d]; one warp per (n, t, h)
+__global__ void __launch_bounds__(256) mha_flash_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                                              float* __restrict__ delta, long long rows, int T, int heads) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // over N * T * heads
+  if (item >= rows * heads) return;
+  const int h = (int)(item % heads);
+  const long long nt = item / heads;                 // n * T + t
+  const long long off = nt * heads * kDh + h * kDh + lane * 2;
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(o + off));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dout + off));
+  float d = warp_sum(a.x * b.x + a.y * b.y);
+  if (lane == 0) delta[((nt / T) * heads + h) * T + nt % T] = d;
+}
+
+// P (recomputed from lse2) and dS for rows (qrow0 + g, + 8) of this warp against the staged key block; rows >= T give zeros
+__device__ __forceinline__ void flash_p_ds(float (&p)[8][4], float (&dp)[8][4], uint32_t qs, uint32_t ks, uint32_t dos, uint32_t vs,
+                                           const float* __restrict__ lse, const float* __restrict__ delta, int m0, int q0, int k0, int T,
+                                           float scale, int causal, int lane) {
+  const int g = lane >> 2;
+  zero_acc(p);
+  mm_rows_x_rows(p, qs, ks, m0, lane);
+  mask_scale(p, scale * 1.4426950408889634f, q0 + m0, k0, T, causal, lane);
+  zero_acc(dp);
+  mm_rows_x_rows(dp, dos, vs, m0, lane);
+  const int r0 = q0 + m0 + g, r1 = r0 + 8;
+  const float ls0 = r0 < T ? lse[r0] : 0.f, ls1 = r1 < T ? lse[r1] : 0.f;
+  const float d0 = r0 < T ? delta[r0] : 0.f, d1 = r1 < T ? delta[r1] : 0.f;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool hi = (e & 2) != 0;
+      const bool ok = (hi ? r1 : r0) < T && p[nt][e] > -1e37f;
+      const float pv = ok ? ex2_approx(p[nt][e] - (hi ? ls1 : ls0)) : 0.f;
+      p[nt][e] = pv;
+      dp[nt][e] = pv * (dp[nt][e] - (hi ? d1 : d0)) * scale;
+    }
+}
+
+__global__ void __launch_bounds__(128) mha_flash_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                                                               const float* __restrict__ lse, const float* __restrict__ delta,
+                                                               __nv_bfloat16* __restrict__ dqkv, int T, int heads, float scale, int causal) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(sm_raw);
+  __nv_bfloat16* dos = qs + kTileElems;
+  __nv_bfloat16* ks = dos + kTileElems;
+  __nv_bfloat16* vs = ks + kTileElems;
+  const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int W = heads * kDh;
+  const __nv_bfloat16* base = qkv + (long long)n * T * 3 * W + h * kDh;
+  const int q0 = qb * 64;
+  stage_tile_rows(base, 3 * W, q0, T, qs);
+  stage_tile_rows(dout + (long long)n * T * W + h * kDh, W, q0, T, dos);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = warp * 16;
+  const float* lr = lse + ((long long)n * heads + h) * T;
+  const float* dr = delta + ((long long)n * heads + h) * T;
+  float dq[8][4];
+  zero_acc(dq);
+  const int nkb = causal ? (qb + 1) : (T + 63) / 64;
+  for (int kb = 0; kb < nkb; ++kb) {
+    __syncthreads();
+    stage_tile_rows(base + W, 3 * W, kb * 64, T, ks);
+    stage_tile_rows(base + 2 * W, 3 * W, kb * 64, T, vs);
+    __syncthreads();
+    float p[8][4], ds[8][4];
+    flash_p_ds(p, ds, smem_u32(qs), smem_u32(ks), smem_u32(dos), smem_u32(vs), lr, dr, m0, q0, kb * 64, T, scale, causal, lane);
+    uint32_t dsf[4][4];
+    acc_to_afrag(ds, dsf);
+    mm_frag_x_cols(dq, dsf, smem_u32(ks), lane);          // dQ += dS K
+  }
+  store_rows(dq, dqkv + (long long)n * T * 3 * W + h * kDh + (long long)q0 * 3 * W, 3 * W, m0, T - q0, lane);
+}
+
+__global__ void __launch_bounds__(128) mha_flash_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                                                                const float* __restrict__ lse, const float* __restrict__ delta,
+                                                                __nv_bfloat16* __restrict__ dqkv, int T, int heads, float scale, int causal) {
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(sm_raw);
+  __nv_bfloat16* vs = ks + kTileElems;
+  __nv_bfloat16* qs = vs + kTileElems;
+  __nv_bfloat16* dos = qs + kTileElems;
+  __nv_bfloat16* ps = dos + kTileElems;      // P  [i][j] of the current query block
+  __nv_bfloat16* dss = ps + kTileElems;      // dS [i][j]
+  const int kb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int W = heads * kDh;
+  const __nv_bfloat16* base = qkv + (long long)n * T * 3 * W + h * kDh;
+  const __nv_bfloat16* dob = dout + (long long)n * T * W + h * kDh;
+  const int k0 = kb * 64;
+  stage_tile_rows(base + W, 3 * W, k0, T, ks);
+  stage_tile_rows(base + 2 * W, 3 * W, k0, T, vs);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = warp * 16, g = lane >> 2, t2 = (lane & 3) * 2;
+  const float* lr = lse + ((long long)n * heads + h) * T;
+  const float* dr = delta + ((long long)n * heads + h) * T;
+  float dk[8][4], dv[8][4];
+  zero_acc(dk);
+  zero_acc(dv);
+  const int nqb = (T + 63) / 64;
+  for (int qb = causal ? kb : 0; qb < nqb; ++qb) {
+    __syncthreads();                          // the previous block's Q / dO / P / dS fully consumed
+    stage_tile_rows(base, 3 * W, qb * 64, T, qs);
+    stage_tile_rows(dob, W, qb * 64, T, dos);
+    __syncthreads();
+    float p[8][4], ds[8][4];
+    flash_p_ds(p, ds, smem_u32(qs), smem_u32(ks), smem_u32(dos), smem_u32(vs), lr, dr, m0, qb * 64, k0, T, scale, causal, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      *reinterpret_cast<uint32_t*>(ps + (m0 + g) * kPitch + nt * 8 + t2) = pack_bf16(p[nt][0], p[nt][1]);
+      *reinterpret_cast<uint32_t*>(ps + (m0 + g + 8) * kPitch + nt * 8 + t2) = pack_bf16(p[nt][2], p[nt][3]);
+      *reinterpret_cast<uint32_t*>(dss + (m0 + g) * kPitch + nt * 8 + t2) = pack_bf16(ds[nt][0], ds[nt][1]);
+      *reinterpret_cast<uint32_t*>(dss + (m0 + g + 8) * kPitch + nt * 8 + t2) = pack_bf16(ds[nt][2], ds[nt][3]);
+    }
+    __syncthreads();
+    mm_colsT_x_cols(dk, smem_u32(dss), smem_u32(qs), m0, lane);    // dK (keys m0..) += dS^T Q
+    mm_colsT_x_cols(dv, smem_u32(ps), smem_u32(dos), m0, lane);    // dV += P^T dO
+  }
+  __nv_bfloat16* ob = dqkv + (long long)n * T * 3 * W + h * kDh + (long long)k0 * 3 * W;
+  store_rows(dk, ob + W, 3 * W, m0, T - k0, lane);
+  store_rows(dv, ob + 2 * W, 3 * W, m0, T - k0, lane);
+}
+
 }  // namespace ffvc
 
 using namespace ffvc;
@@ -288,6 +530,8 @@ static int mha_setup() {
   static bool done = false;
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(mha_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kTileElems * 2);
+    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(mha_flash_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kTileElems * 2);
     if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
     done = true;
   }
@@ -314,6 +558,45 @@ extern "C" int ffvc_mha_small_bwd(const void* qkv, const void* dout, void* dqkv,
   mha_small_bwd_kernel<<<N * heads, 128, 6 * kTileElems * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(dout),
       reinterpret_cast<__nv_bfloat16*>(dqkv), T, heads, scale);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+// Tiled attention for any T (see above).  qkv [N][T][3*W] bf16 (q | k | v, head h = columns h*64..), out / dout [N][T][W] bf16,
+// lse [N][heads][T] fp32 (log2-domain log-sum-exp of the scaled scores, written by the forward, read by the backward),
+// delta_ws [N][heads][T] fp32 scratch.
+extern "C" int ffvc_mha_flash_fwd(const void* qkv, void* out, float* lse, int N, int T, int heads, int head_dim, float scale,
+                                  int causal, void* stream) {
+  if (head_dim != kDh || T < 1) return set_error(FFVC_ERR_UNSUPPORTED, "mha_flash: head_dim must be 64");
+  if (!qkv || !out || !lse) return set_error(FFVC_ERR_ARG, "mha_flash_fwd: null pointer");
+  int rc = mha_setup();
+  if (rc) return rc;
+  dim3 grid((T + 63) / 64, heads, N);
+  mha_flash_fwd_kernel<<<grid, 128, 3 * kTileElems * 2, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, T, heads, scale, causal);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+
+extern "C" int ffvc_mha_flash_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv,
+                                  int N, int T, int heads, int head_dim, float scale, int causal, void* stream) {
+  if (head_dim != kDh || T < 1) return set_error(FFVC_ERR_UNSUPPORTED, "mha_flash: head_dim must be 64");
+  if (!qkv || !out || !dout || !lse || !delta_ws || !dqkv) return set_error(FFVC_ERR_ARG, "mha_flash_bwd: null pointer");
+  int rc = mha_setup();
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long rows = (long long)N * T;
+  mha_flash_delta_kernel<<<(unsigned)((rows * heads + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                                            reinterpret_cast<const __nv_bfloat16*>(dout), delta_ws, rows, T, heads);
+  FFVC_CHECK_LAUNCH();
+  dim3 grid((T + 63) / 64, heads, N);
+  mha_flash_bwd_dq_kernel<<<grid, 128, 4 * kTileElems * 2, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta_ws,
+                                                                reinterpret_cast<__nv_bfloat16*>(dqkv), T, heads, scale, causal);
+  FFVC_CHECK_LAUNCH();
+  mha_flash_bwd_dkv_kernel<<<grid, 128, 6 * kTileElems * 2, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                 reinterpret_cast<const __nv_bfloat16*>(dout), lse, delta_ws,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), T, heads, scale, causal);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

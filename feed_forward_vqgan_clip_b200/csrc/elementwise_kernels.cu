@@ -477,6 +477,42 @@ __global__ void image_post_bwd_kernel(const float* __restrict__ g, const float* 
   }
 }
 
+// ---------------------------------------------------------------- 3x3 conv with tiny Cout as a 1x1 GEMM + tap gather (conv_out)
+// The decoder's last conv has 3 output channels.  As an implicit GEMM it reads every pixel nine times through the tensor core
+// for a 3-wide (padded to 32) N: the tcgen05 pipe was busy 60 % of 0.87 ms for 34 TFLOP/s (profiles/r02_ncu_conv_out.md) because
+// an MMA costs its A rows whatever N is.  Here the tensor core sees every pixel ONCE: v[p][tap*COUT + co] = sum_c a[p][c] w[co][tap][c]
+// (a plain GEMM, N = 9 * COUT <= 32, fp32 out), and this kernel adds the nine shifted taps:
+//   y[p][co] = bias[co] + sum_tap v[p + off(tap)][tap*COUT + co]   (zero outside the image = padding 1)
+// It also applies the image post-processing xr = clamp((y + 1) / 2, 0, 1) (main.py:142) when xr != nullptr.
+// CTA = 8 rows x 32 pixels: the 10 x 34 rows of v it touches (one 128-byte line each) stay in L1 across the taps.
+template <int COUT>
+__global__ void __launch_bounds__(256) conv_taps_gather_kernel(const float* __restrict__ v, const float* __restrict__ bias,
+                                                               float* __restrict__ y, float* __restrict__ xr, int H, int W) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int yy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int n = blockIdx.z;
+  if (x >= W || yy >= H) return;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = bias ? bias[c] : 0.f;
+  const float* vn = v + (long long)n * H * W * 32;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int sy = yy + tap / 3 - 1, sx = x + tap % 3 - 1;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+      const float* src = vn + ((long long)sy * W + sx) * 32 + tap * COUT;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] += src[c];
+    }
+  }
+  const long long o = (((long long)n * H + yy) * W + x) * COUT;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    y[o + c] = acc[c];
+    if (xr) xr[o + c] = fminf(fmaxf((acc[c] + 1.0f) * 0.5f, 0.f), 1.f);
+  }
+}
+
 // ---------------------------------------------------------------- 3x3 conv with tiny Cin (dgrad of conv_out: 3 -> 128 ch)
 // x: [N][H][W][CIN] fp32, w: [COUT][9][CIN] fp32 (already flipped/transposed for dgrad), y: NHWC bf16.  pad 1.
 template <int CIN>
@@ -883,6 +919,17 @@ extern "C" int ffvc_image_post_fwd(const float* d, float* xr, long long n, void*
 }
 extern "C" int ffvc_image_post_bwd(const float* g, const float* d, float* gd, long long n, void* stream) {
   image_post_bwd_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(g, d, gd, n);
+  FFVC_CHECK_LAUNCH();
+  return FFVC_OK;
+}
+extern "C" int ffvc_conv_taps_gather(const float* v, const float* bias, float* y, float* xr, int N, int H, int W, int COUT,
+                                     void* stream) {
+  if (!v || !y) return set_error(FFVC_ERR_ARG, "conv_taps_gather: null pointer");
+  dim3 grid((W + 31) / 32, (H + 7) / 8, N);
+  if (COUT == 3) conv_taps_gather_kernel<3><<<grid, 256, 0, ST(stream)>>>(v, bias, y, xr, H, W);
+  else if (COUT == 1) conv_taps_gather_kernel<1><<<grid, 256, 0, ST(stream)>>>(v, bias, y, xr, H, W);
+  else if (COUT == 2) conv_taps_gather_kernel<2><<<grid, 256, 0, ST(stream)>>>(v, bias, y, xr, H, W);
+  else return set_error(FFVC_ERR_ARG, "conv_taps_gather: COUT must be 1, 2 or 3 (9 * COUT tap columns in a 32-wide row)");
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

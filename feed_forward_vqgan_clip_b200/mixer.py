@@ -252,7 +252,8 @@ class MixerEngine:
         call("cast_f32_bf16", dz.contiguous(), dzb, R * C)
         # final_proj
         ops.linear_wgrad(dzb, sv["nf"], self.g("final_proj.weight"), R, C, D, splits=sp(C, D, R))
-        call("colsum", dzb, self.g("final_proj.bias"), R, C)
+        # bias-gradient sums do not feed the next GEMM: they run on a side stream next to it (ops.fork / ops.join)
+        ops.fork(lambda: call("colsum", dzb, self.g("final_proj.bias"), R, C))
         dnf = new(R, D)
         ops.linear_dgrad(dzb, self.w("final_proj.weight"), dnf, R, C, D)
         q = "mixer.%d." % (L + 2)
@@ -269,10 +270,11 @@ class MixerEngine:
             # (bias gradient of 1.fn.3 = colsum(dH): emitted by the LayerNorm backward that produced dH)
             dU2 = new(R, 4 * D)
             ops.linear_dgrad(dH, self.w(p + "1.fn.3.weight"), dU2, R, D, 4 * D, aux=lv["U2"], mul_mode=ops.ACT_GELU)
+            ops.fork(lambda t=dU2, q=p: call("colsum", t, self.g(q + "1.fn.0.bias"), R, 4 * D))
             ops.linear_wgrad(dU2, lv["n2"], self.g(p + "1.fn.0.weight"), R, 4 * D, D, splits=sp(4 * D, D, R))
-            call("colsum", dU2, self.g(p + "1.fn.0.bias"), R, 4 * D)
             dn2 = new(R, D)
             ops.linear_dgrad(dU2, self.w(p + "1.fn.0.weight"), dn2, R, 4 * D, D)
+            ops.join()                      # before dU2 (read by the forked column sum) goes back to the allocator
             del dU2
             dHb = new(R, D)
             call("layernorm_bwd_sums", dn2, lv["Hb"], self.wf(p + "1.norm.weight"), lv["mu2"], lv["rs2"], dH, dHb,
@@ -285,12 +287,13 @@ class MixerEngine:
             ops.gemm(self.w(p + "0.fn.3.weight"), dHb, dU1, 4 * T, D, T, a_mode=ops.MNMAJOR, a_ld=4 * T,
                      b_mode=ops.MNMAJOR, b_ld=D, b_role=ops.ROLE_OUT, b_bs=T * D, batch=B, out_bs=4 * T * D,
                      aux=lv["U1"], mul_mode=ops.ACT_GELU)
+            ops.fork(lambda t=dU1, q=p: call("rowsum", t, self.g(q + "0.fn.0.bias"), B, 4 * T, D))
             ops.gemm(dU1, lv["n1"], self.g(p + "0.fn.0.weight"), 4 * T, T, D, a_role=ops.ROLE_SEG, a_bs=4 * T * D,
                      b_role=ops.ROLE_SEG, b_bs=T * D, k_segs=B, splits=sp(4 * T, T, B * D), atomic=True)
-            call("rowsum", dU1, self.g(p + "0.fn.0.bias"), B, 4 * T, D)
             dn1 = new(R, D)
             ops.gemm(self.w(p + "0.fn.0.weight"), dU1, dn1, T, D, 4 * T, a_mode=ops.MNMAJOR, a_ld=T,
                      b_mode=ops.MNMAJOR, b_ld=D, b_role=ops.ROLE_OUT, b_bs=4 * T * D, batch=B, out_bs=T * D)
+            ops.join()
             del dU1
             dHa = new(R, D)
             nxt = "mixer.%d.1.fn.3.bias" % (i - 1) if i > 2 else "mixer.1.bias"     # the Linear whose output gradient dHa is
@@ -305,5 +308,6 @@ class MixerEngine:
         ops.linear_dgrad(dH, self.w("mixer.1.weight"), dtok, R, D, C)
         dP = new(B, C * T)
         call("transpose", dtok, dP, B, T, C, 0, 0)                    # [B][T][C] -> [B][C][T]
+        ops.fork(lambda: call("colsum", dP, self.g("proj.bias"), B, C * T))
         ops.linear_wgrad(dP, sv["xb"], self.g("proj.weight"), B, C * T, IN)
-        call("colsum", dP, self.g("proj.bias"), B, C * T)
+        ops.join()

@@ -51,6 +51,43 @@ def num_sms():
     return _NUM_SMS
 
 
+# ------------------------------------------------------------------ side streams: independent launches next to the critical path
+# The step's critical path is a chain of tensor-core GEMMs; several HBM-bound launches hang off it without feeding the next GEMM
+# (bias-gradient column / row sums, the optimizer update of a finished bucket, zeroing the gradient arena, drawing the cutout
+# noise).  fork() enqueues such work on a side stream ordered after everything issued so far on the current stream; join() makes
+# the current stream wait for it.  The caller joins BEFORE freeing any tensor the forked work reads (so the caching allocator
+# never hands its memory out again while the side stream is still reading) and before the step ends (so a CUDA-graph capture
+# closes with one stream).  FFVC_SIDE_STREAMS=0 runs everything inline.
+SIDE_STREAMS = os.environ.get("FFVC_SIDE_STREAMS", "1") == "1"
+_side = {}
+_pending = set()
+
+
+def fork(fn, key="aux"):
+    if not (SIDE_STREAMS and torch.cuda.is_available()):
+        return fn()
+    dev = torch.cuda.current_device()
+    s = _side.get((dev, key))
+    if s is None:
+        s = _side[(dev, key)] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(main)
+    s.wait_event(ev)
+    with torch.cuda.stream(s):
+        fn()
+    _pending.add((dev, key))
+
+
+def join(key="aux"):
+    if not _pending:
+        return
+    dev = torch.cuda.current_device()
+    if (dev, key) in _pending:
+        torch.cuda.current_stream().wait_stream(_side[(dev, key)])
+        _pending.discard((dev, key))
+
+
 def launch_count():
     return int(_lib.load().ffvc_launch_count())
 

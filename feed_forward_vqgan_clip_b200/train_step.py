@@ -212,6 +212,11 @@ class TrainStep:
         # first bucket to the end of backward (option "sm_limit"), so that NCCL's CTAs do not push a GEMM's last CTAs into a second
         # wave; pair it with NCCL_MAX_CTAS = comm_sms (bench.py --comm-sms).  0 = off.
         self.comm_sms = 0
+        # the optimizer update of a bucket of layers runs on a side stream as soon as backward (and, data parallel, the bucket's
+        # all-reduce) has finished it, next to the GEMMs of the remaining layers: only the last bucket's update is exposed.  Needs
+        # clip_grad_norm off (the clip coefficient wants the whole gradient).  The update is the same arithmetic on the same
+        # slices (FusedAdam.step_range); tests/test_dp_step_cpu.py compares it with the one-launch form.
+        self.adam_overlap = True
         self.comm_stream = torch.cuda.Stream(device=self.dev) if world_size > 1 else None
         cb = self.dec.codebook
         self.z_lo, self.z_hi = float(cb.min()), float(cb.max())          # main.py:645-646,763 (global scalars)
@@ -233,6 +238,7 @@ class TrainStep:
         B = inp.shape[0]
         S, C = mix.S, mix.C
         N = self.cutn * B
+        ops.fork(mix.zero_grad_arena, key="zero")      # 4 bytes per parameter of memset, off the critical path
         if self.normalize_input:                                         # main.py:734-735 (before the repeat / the loss targets)
             inp_n = torch.empty_like(inp)
             call("normalize_rows", inp, inp_n, B, inp.shape[1])
@@ -253,6 +259,7 @@ class TrainStep:
             zq = dec.codebook[idx.long()].to(BF16)
         self.last_indices = idx
         img, tape = dec.forward(zq.view(B, S, S, C))                     # [B, H, W, 3] fp32 in [0, 1]
+        ops.join("noise")
         patches, sv_c, _ = cut.forward(img, prm)
         emb, sv_e = clip.forward(patches)
         demb = torch.empty(N, clip.E, device=self.dev, dtype=F32)
@@ -291,7 +298,7 @@ class TrainStep:
             call("sumsq", z, self.aux_loss[0:1], z.numel())
             self.aux_loss[0:1].mul_(self.l2_coef / z.numel())
             call("axpy_f32", z, dz, 2.0 * self.l2_coef / z.numel(), z.numel())
-        mix.zero_grad_arena()
+        ops.join("zero")                      # the gradient arena was zeroed on a side stream while the forward ran (below)
         if self.world > 1 and self.bucket_layers > 0 and hasattr(mix, "layer_starts"):
             from .parallel import bucket_slices
             # bucket k (k < last): the gradients of mixer layers [L - (k+1)*n, L - k*n) (+ the final norm / output projection for
@@ -305,7 +312,11 @@ class TrainStep:
             from . import _lib
             lib = _lib.load()
 
-            def reduce_bucket(slices):
+            early_adam = self.adam_overlap and self.opt.clip == 0 and len(buckets) > 1 and not self.tail_overlap
+            if early_adam:
+                self.opt.tick()                       # before the first bucket: step counter, bias corrections, lr (no clip coefficient)
+
+            def reduce_bucket(slices, last=False):
                 if self.comm_sms > 0:
                     lib.ffvc_set_option(b"sm_limit", max(2, ops.num_sms() - self.comm_sms))
                 ev = torch.cuda.Event()
@@ -314,6 +325,9 @@ class TrainStep:
                 with torch.cuda.stream(comm):
                     for lo, hi in slices:
                         torch.distributed.all_reduce(mix.grad[lo:hi], group=self.pg)
+                    if early_adam and not last:       # the bucket's update right behind its all-reduce, next to the remaining backward
+                        for lo, hi in slices:
+                            self.opt.step_range(lo, hi)
 
             def on_layer_done(k):
                 if k in first_layer_of_bucket:
@@ -334,9 +348,32 @@ class TrainStep:
                 for lo, hi in buckets[-1]:
                     self.opt.step_range(lo, hi)
                 return self.loss
-            reduce_bucket(buckets[-1])
+            reduce_bucket(buckets[-1], last=True)
             main.wait_stream(comm)
             lib.ffvc_set_option(b"sm_limit", 0)
+            if early_adam:
+                del sv_m
+                for lo, hi in buckets[-1]:
+                    self.opt.step_range(lo, hi)
+                return self.loss
+        elif (self.world == 1 and self.adam_overlap and self.opt.clip == 0 and self.bucket_layers > 0 and hasattr(mix, "layer_starts")
+              and ops.SIDE_STREAMS and mix.dev.type == "cuda"):
+            from .parallel import bucket_slices
+            buckets = bucket_slices(mix.layer_starts(), mix.total, self.bucket_layers, late=mix.late_ranges())
+            first_layer_of_bucket = {mix.L - min(mix.L, (k + 1) * self.bucket_layers): k for k in range(len(buckets) - 1)}
+            self.opt.tick()
+
+            def on_layer_done(k):
+                if k in first_layer_of_bucket:
+                    sl = buckets[first_layer_of_bucket[k]]
+                    ops.fork(lambda: [self.opt.step_range(lo, hi) for lo, hi in sl], key="adam")
+
+            mix.backward(sv_m, dz, on_layer_done=on_layer_done)
+            del sv_m
+            ops.join("adam")
+            for lo, hi in buckets[-1]:
+                self.opt.step_range(lo, hi)
+            return self.loss
         else:
             mix.backward(sv_m, dz)
             if self.world > 1:
@@ -401,11 +438,17 @@ class TrainStep:
         st["mapper_noise"] = torch.zeros(B, self.noise_dim, device=dev) if self.noise_bank is not None else None
         self.static = st
 
+        st["facs"] = torch.empty(N, device=dev)
+        st["noise_raw"] = torch.empty(N, 3, self.cut_size, self.cut_size, device=dev)
+
+        def draw_noise():          # main.py:223-225: facs ~ U(0, noise_fac), noise ~ N(0, 1); 2.4 KB per cutout of RNG output per step
+            st["facs"].uniform_(0.0, 0.1)
+            st["noise_raw"].normal_()
+
         def body():
+            ops.fork(draw_noise, key="noise")       # next to the mapper / decoder forward; joined in front of the cutouts
             prm = dict(affine_inv=st["affine_inv"], persp_inv=st["persp_inv"], sat=st["sat"], hue=st["hue"], erase=st["erase"],
-                       mapper_noise=st["mapper_noise"],
-                       facs=torch.rand(N, device=dev) * 0.1,
-                       noise_raw=torch.randn(N, 3, self.cut_size, self.cut_size, device=dev))
+                       mapper_noise=st["mapper_noise"], facs=st["facs"], noise_raw=st["noise_raw"])
             self._device_step(st["inp"], st["out"], prm)
 
         # warm-up on a side stream (allocator + lazy init), then capture

@@ -162,7 +162,12 @@ class DecoderEngine:
                     self.pk[name + ".w"] = v.permute(0, 2, 3, 1).reshape(co, 9 * ci).contiguous().to(BF16)
                     if co % 64 == 0:   # dgrad pack: [ci][flipped tap][co]
                         self.pk[name + ".wT"] = v.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous().to(BF16)
-                    else:              # conv_out: dgrad runs on the tiny-Cin SIMT kernel, fp32 [ci][flipped tap][co]
+                    else:              # conv_out: forward as a 1x1 GEMM into 9 * co tap columns (+ ffvc_conv_taps_gather) ...
+                        if 9 * co <= 32:
+                            wv = torch.zeros(32, ci, device=v.device, dtype=F32)      # row tap * co_n + co = w[co][:, kh, kw]
+                            wv[:9 * co] = v.permute(2, 3, 0, 1).reshape(9 * co, ci)
+                            self.pk[name + ".wv"] = wv.to(BF16)
+                        # ... dgrad runs on the tiny-Cin SIMT kernel, fp32 [ci][flipped tap][co]
                         wt = v.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).contiguous().float()
                         self.pk[name + ".wT32"] = wt
                         wp = torch.zeros(ci, 32, device=wt.device, dtype=F32)      # K padded 27 -> 32 for the GEMM form
@@ -202,6 +207,7 @@ class DecoderEngine:
         return self._ws[tag]
 
     # ---------------------------------------------------------------- primitive ops (forward + backward closure)
+    CONV_OUT_TAPS = os.environ.get("FFVC_CONV_OUT_TAPS", "1") == "1"   # conv_out as 1x1 GEMM + tap gather (0: implicit-GEMM conv)
     USE_HALO = True    # shared-memory halo reuse for the wide (W % 128 == 0), <= 128-output-channel 3x3 convs
 
     def _halo_ok(self, H, W, cin, cout, out_f32=False):
@@ -408,13 +414,24 @@ class DecoderEngine:
         HW = H * W
         x_last = h
         a, st = self.gn(h, "decoder.norm_out", N, HW, c, True)
-        dimg = self.conv3(a, "decoder.conv_out", N, H, W, c, cfg["out_ch"], out_f32=True)   # [N*HW, 3] fp32
-        del a
-        if post:
-            img = self._new(N * HW, 3, dtype=F32)
-            call("image_post_fwd", dimg, img, N * HW * 3)
+        co = cfg["out_ch"]
+        if self.CONV_OUT_TAPS and ("decoder.conv_out.wv" in self.pk):
+            # every pixel through the tensor core once (N = 9 * co tap columns), then the nine shifted taps + bias (+ post) in one pass
+            taps = self._new(N * HW, 32, dtype=F32)
+            ops.gemm(a, self.pk["decoder.conv_out.wv"], taps, N * HW, 32, c)
+            del a
+            dimg = self._new(N * HW, co, dtype=F32)
+            img = self._new(N * HW, co, dtype=F32) if post else dimg
+            call("conv_taps_gather", taps, self.pk["decoder.conv_out.b"], dimg, img if post else None, N, H, W, co)
+            del taps
         else:
-            img = dimg
+            dimg = self.conv3(a, "decoder.conv_out", N, H, W, c, co, out_f32=True)   # [N*HW, 3] fp32
+            del a
+            if post:
+                img = self._new(N * HW, 3, dtype=F32)
+                call("image_post_fwd", dimg, img, N * HW * 3)
+            else:
+                img = dimg
 
         def out_bwd(g, H=H, W=W, c=c):
             # g: [N*HW, 3] fp32 gradient w.r.t. the returned image

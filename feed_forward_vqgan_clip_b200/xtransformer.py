@@ -154,8 +154,17 @@ class XTEngine:
         return torch.empty(*shape, device=self.dev, dtype=dtype)
 
     # attention over the fused [B][T][3*Wi] q|k|v activation; per-(sample, head) GEMMs, causal
+    # tiled attention (ffvc_mha_flash_*): scores / probabilities never reach HBM, the forward saves the row log-sum-exp only.
+    # False selects round 1's batched tcgen05 GEMMs around a materialised T x T softmax (kept for A/B and as a cross-check).
+    FLASH_ATTN = True
+
     def _attn_fwd(self, qkv, B):
         T, H, Wi = self.T, self.H, self.Wi
+        if self.FLASH_ATTN:
+            a = self._new(B * T, Wi)
+            lse = self._new(B, H, T, dtype=F32)
+            call("mha_flash_fwd", qkv, a, lse, B, T, H, DIM_HEAD, DIM_HEAD ** -0.5, 1)
+            return a, lse
         S = self._new(B, H, T, T, dtype=F32)
         ops.gemm(qkv, qkv, S, T, T, DIM_HEAD, a_ld=3 * Wi, b_ld=3 * Wi, b_off=Wi, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT,
                  batch=B * H, batch_inner=H, a_bs=T * 3 * Wi, b_bs=T * 3 * Wi, a_bs_in=DIM_HEAD, b_bs_in=DIM_HEAD, ldc=T,
@@ -169,8 +178,12 @@ class XTEngine:
                  b_bs_in=DIM_HEAD, ldc=Wi, out_bs=T * Wi, out_bs_in=DIM_HEAD, block_n=64)
         return a, P
 
-    def _attn_bwd(self, qkv, P, da, B):
+    def _attn_bwd(self, qkv, P, da, B, a=None):
         T, H, Wi = self.T, self.H, self.Wi
+        if P.dtype == F32:                    # the flash forward's log-sum-exp: recompute the probabilities block by block
+            dqkv = self._new(B * T, 3 * Wi)
+            call("mha_flash_bwd", qkv, a, da, P, torch.empty_like(P), dqkv, B, T, H, DIM_HEAD, DIM_HEAD ** -0.5, 1)
+            return dqkv
         kw = dict(batch=B * H, batch_inner=H, a_role=ops.ROLE_OUT, b_role=ops.ROLE_OUT)
         dP = self._new(B, H, T, T, dtype=F32)
         ops.gemm(da, qkv, dP, T, T, DIM_HEAD, a_ld=Wi, b_ld=3 * Wi, b_off=2 * Wi, a_bs=T * Wi, a_bs_in=DIM_HEAD, b_bs=T * 3 * Wi,
@@ -275,7 +288,7 @@ class XTEngine:
             call("colsum", dh2, self.g(pa + "1.to_out.bias"), R, D)
             da = self._new(R, Wi)
             ops.linear_dgrad(dh2, self.w(pa + "1.to_out.weight"), da, R, D, Wi)
-            dqkv = self._attn_bwd(lv["qkv"], lv["P"], da, B)
+            dqkv = self._attn_bwd(lv["qkv"], lv["P"], da, B, a=lv["a"])
             dn1 = None
             for i, nm in enumerate(("to_q", "to_k", "to_v")):
                 # wgrad: dW[n,k] += sum_m dqkv[m, i*Wi + n] n1[m,k]

@@ -246,6 +246,12 @@ int ffvc_clamp_bwd(const float* g, const float* x, float* gx, long long n, float
 /* xr = clamp_with_grad((d + 1) / 2, 0, 1) and its backward (main.py:142). */
 int ffvc_image_post_fwd(const float* d, float* xr, long long n, void* stream);
 int ffvc_image_post_bwd(const float* g, const float* d, float* gd, long long n, void* stream);
+/* 3x3 / pad-1 conv with COUT <= 3 output channels (the decoder's conv_out, taming Decoder; call site main.py:142) in two steps:
+ * ffvc_gemm computes v[p][tap * COUT + co] = sum_c a[p][c] * w[co][tap][c] for every pixel ONCE (M = N*H*W, N = 32 columns of which
+ * 9 * COUT are used, K = Cin, fp32 out, ldc = 32); this entry point adds the nine shifted taps, y[p][co] = bias[co] +
+ * sum_tap v[p + off(tap)][tap * COUT + co] (fp32 [N*H*W][COUT]), and, when xr is given, also writes clamp((y + 1) / 2, 0, 1)
+ * (ffvc_image_post_fwd).  The implicit-GEMM form read every pixel nine times through the tensor core for a 3-wide N. */
+int ffvc_conv_taps_gather(const float* v, const float* bias, float* y, float* xr, int N, int H, int W, int COUT, void* stream);
 /* 3x3 conv, Cin = 3 (fp32 NHWC in, [COUT][9][3] fp32 weights, bf16 NHWC out): dgrad of the decoder's conv_out. */
 int ffvc_conv3x3_cin3(const float* x, const float* w, void* y, int N, int H, int W, int COUT, void* stream);
 
@@ -272,6 +278,15 @@ int ffvc_adam_step_ema(float* p, const float* g, float* m, float* v, void* shado
 int ffvc_mha_small_fwd(const void* qkv, void* out, int N, int T, int heads, int head_dim, float scale, void* stream);
 int ffvc_mha_small_bwd(const void* qkv, const void* dout, void* dqkv, int N, int T, int heads, int head_dim, float scale,
                        void* stream);
+/* Tiled ("flash") attention for any sequence length, head_dim 64: the x-transformer mapper's causal attention at 1024 tokens
+ * (transformer.py:11-20; x-transformers Attention) and ViTs beyond 64 tokens.  Same layouts as ffvc_mha_small_*; scores and
+ * probabilities stay on the SM.  lse [N][heads][T] fp32: log2-domain log-sum-exp of the scaled (and masked) scores, written by
+ * the forward, read by the backward (which recomputes the probabilities); delta_ws: [N][heads][T] fp32 scratch;
+ * out (the forward's result) is read by the backward.  causal != 0: token i attends tokens j <= i. */
+int ffvc_mha_flash_fwd(const void* qkv, void* out, float* lse, int N, int T, int heads, int head_dim, float scale, int causal,
+                       void* stream);
+int ffvc_mha_flash_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta_ws, void* dqkv, int N,
+                       int T, int heads, int head_dim, float scale, int causal, void* stream);
 
 /* CLIP ViT token assembly: x[n][0] = cls + pos[0], x[n][1+p] = pe[n][p] + pos[1+p] (cloob.py:240-243); strided row copy. */
 int ffvc_clip_assemble(const void* pe, const float* cls, const float* pos, void* x, int N, int T, int W, void* stream);

@@ -576,6 +576,51 @@ def k_spherical_loss(embed, target, loss_out, dembed, dembed_bf16, N, B, D, coef
         dembed_bf16.view(-1)[:N * D] = g.reshape(-1)
 
 
+def _flash_ref(qkv, N, T, heads, scale, causal):
+    W = heads * 64
+    x = qkv.reshape(-1)[:N * T * 3 * W].view(N, T, 3, heads, 64).float()
+    q, k, v = x[:, :, 0].transpose(1, 2), x[:, :, 1].transpose(1, 2), x[:, :, 2].transpose(1, 2)      # (N, heads, T, 64)
+    s = (q @ k.transpose(-1, -2)) * scale
+    if causal:
+        s = s.masked_fill(torch.ones(T, T, dtype=torch.bool).triu_(1), float("-inf"))
+    return q, k, v, s
+
+
+def k_mha_flash_fwd(qkv, out, lse, N, T, heads, head_dim, scale, causal):
+    """softmax(q k^T * scale [causal]) v per (sequence, head); lse = log2-domain log-sum-exp of the masked scaled scores"""
+    assert head_dim == 64
+    q, k, v, s = _flash_ref(qkv, N, T, heads, scale, causal)
+    p = torch.softmax(s, dim=-1).to(torch.bfloat16).float()          # the kernel rounds P to bf16 in front of P V
+    o = (p @ v).transpose(1, 2).reshape(N * T * heads * 64)
+    out.view(-1)[:o.numel()] = o
+    lse.view(-1)[:N * heads * T] = (torch.logsumexp(s, dim=-1) * 1.4426950408889634).reshape(-1)
+
+
+def k_mha_flash_bwd(qkv, out, dout, lse, delta_ws, dqkv, N, T, heads, head_dim, scale, causal):
+    W = heads * 64
+    with torch.enable_grad():
+        x = qkv.reshape(-1)[:N * T * 3 * W].view(N, T, 3 * W).float().clone().requires_grad_(True)
+        q, k, v, s = _flash_ref(x, N, T, heads, scale, causal)
+        o = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(N, T, W)
+        g, = torch.autograd.grad(o, x, dout.reshape(-1)[:N * T * W].view(N, T, W).float())
+    dqkv.view(-1)[:N * T * 3 * W] = g.reshape(-1)
+
+
+def k_conv_taps_gather(v, bias, y, xr, N, H, W, COUT):
+    """y[p][co] = bias[co] + sum_tap v[p + off(tap)][tap * COUT + co] (zero outside the image); xr = clamp((y + 1) / 2, 0, 1)"""
+    V = v.reshape(-1)[:N * H * W * 32].view(N, H, W, 32).float()
+    out = torch.zeros(N, H, W, COUT)
+    for tap in range(9):
+        dy, dx = tap // 3 - 1, tap % 3 - 1
+        ys0, ys1, xs0, xs1 = max(0, -dy), min(H, H - dy), max(0, -dx), min(W, W - dx)
+        out[:, ys0:ys1, xs0:xs1] += V[:, ys0 + dy:ys1 + dy, xs0 + dx:xs1 + dx, tap * COUT:(tap + 1) * COUT]
+    if bias is not None:
+        out = out + bias.reshape(-1)[:COUT].float()
+    y.view(-1)[:N * H * W * COUT] = out.reshape(-1)
+    if xr is not None:
+        xr.view(-1)[:N * H * W * COUT] = ((out + 1) / 2).clamp(0, 1).reshape(-1)
+
+
 def k_spherical_loss2(embed, target, target2, loss_out, dembed, dembed_bf16, N, B, D, coef, coef2):
     """main.py:801-824: the target term plus `input_loss_coef` times the same distance to the source embeddings"""
     with torch.enable_grad():

@@ -162,7 +162,9 @@ def test_decoder_engine_orchestration(abi_on_cpu, monkeypatch, epilogue_stats):
     assert float((y - yr).detach().abs().max()) <= 3e-2 * float(yr.detach().abs().max())
     assert cos(zc.grad, zr.grad) > 0.99
     assert ("conv3x3_halo_gn" in seen) == epilogue_stats and ("conv3x3_halo_gnbwd" in seen) == epilogue_stats
-    assert "conv3x3_halo" in seen and "groupnorm_bwd" in seen and "im2col3x3_cin3" in seen
+    # conv_out: one GEMM into the tap columns + the gather (round 2; the implicit-GEMM halo form was its only plain conv3x3_halo here)
+    assert "conv_taps_gather" in seen and "groupnorm_bwd" in seen and "im2col3x3_cin3" in seen
+    assert ("conv3x3_halo" in seen) == (not epilogue_stats)      # without epilogue statistics the wide layers take the plain halo conv
 
 
 SMALL_VQ = dict(ch=64, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(16,), resolution=32, z_channels=64, out_ch=3,

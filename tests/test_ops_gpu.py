@@ -515,7 +515,8 @@ def test_sln_and_vitgan_attention_kernels():
     assert torch.equal(dst[:, :126], src.to(BF)) and float(dst[:, 126:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("R,C,HW", [(2, 64, 50), (4, 512, 9), (5, 128, 33), (16, 512, 7), (7, 40, 21)])
+@pytest.mark.parametrize("R,C,HW", [(2, 64, 50), (4, 512, 9), (5, 128, 33), (16, 512, 7), (7, 40, 21), (2, 128, 41), (3, 256, 12),
+                                    (2, 512, 10), (4, 64, 33), (3, 128, 2500)])
 def test_diversity_tap_kernels_vs_reference_expression(R, C, HW):
     """main.py:779-787 on one tap: R <= 4 takes the in-register kernel, R > 4 (mode 'all': R = batch, B = 1; or repeat > 4)
     the streaming kernel; value and gradient w.r.t. the features"""
@@ -606,3 +607,54 @@ def test_spherical_loss_with_input_loss_term_and_normalize_rows():
     y = torch.empty_like(x)
     call("normalize_rows", x, y, 37, 96)
     assert torch.allclose(y, F.normalize(x, dim=1), atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("n,h,w,c,co", [(2, 32, 32, 64, 3), (1, 24, 40, 128, 3), (3, 8, 16, 64, 1)])
+def test_conv_out_as_one_gemm_plus_tap_gather(n, h, w, c, co):
+    """the decoder's conv_out (3x3, pad 1, <= 3 output channels): ffvc_gemm into 9 * co tap columns + ffvc_conv_taps_gather against
+    F.conv2d, and the fused image post-processing against clamp((y + 1) / 2, 0, 1) (main.py:142)"""
+    g = torch.Generator().manual_seed(6)
+    a = torch.randn(n, h, w, c, generator=g).to(BF)
+    wt = (torch.randn(co, c, 3, 3, generator=g) * (9 * c) ** -0.5).to(BF)
+    bias = torch.randn(co, generator=g)
+    wv = torch.zeros(32, c)
+    wv[:9 * co] = wt.float().permute(2, 3, 0, 1).reshape(9 * co, c)
+    taps = torch.empty(n * h * w, 32, device=DEV, dtype=torch.float32)
+    ops.gemm(a.to(DEV), wv.to(BF).to(DEV), taps, n * h * w, 32, c)
+    y = torch.full((n * h * w, co), float("nan"), device=DEV)
+    xr = torch.full((n * h * w, co), float("nan"), device=DEV)
+    call("conv_taps_gather", taps, bias.to(DEV), y, xr, n, h, w, co)
+    ref = F.conv2d(a.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(n * h * w, co)
+    assert torch.allclose(y.cpu(), ref, atol=2e-4, rtol=2e-4), (y.cpu() - ref).abs().max()
+    assert torch.equal(xr, ((y + 1) / 2).clamp(0, 1))
+    y2 = torch.empty_like(y)
+    call("conv_taps_gather", taps, None, y2, None, n, h, w, co)
+    assert torch.allclose(y2.cpu() + bias, y.cpu(), atol=1e-6)
+
+
+@pytest.mark.parametrize("N,T,heads,causal", [(2, 1024, 6, 1), (3, 200, 2, 0), (1, 130, 3, 1), (2, 64, 2, 1), (1, 257, 12, 0)])
+def test_mha_flash_fwd_bwd(N, T, heads, causal):
+    """tiled attention (ffvc_mha_flash_*) against torch: x-transformer shape (1024 tokens, 6 heads, causal), ragged lengths, and
+    agreement with the small-sequence kernel at T = 64"""
+    W = heads * 64
+    qkv = rnd(N, T, 3 * W, seed=1)
+    dout = rnd(N, T, W, seed=2)
+    out = torch.full((N, T, W), float("nan"), device=DEV, dtype=BF)
+    lse = torch.full((N, heads, T), float("nan"), device=DEV)
+    call("mha_flash_fwd", qkv, out, lse, N, T, heads, 64, 0.125, causal)
+    x = qkv.float().clone().requires_grad_(True)
+    q, k, v = (x.view(N, T, 3, heads, 64)[:, :, i].transpose(1, 2) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s.masked_fill(torch.ones(T, T, dtype=torch.bool, device=DEV).triu_(1), float("-inf"))
+    ref = (torch.softmax(s, dim=-1) @ v).transpose(1, 2).reshape(N, T, W)
+    close(out, ref, 2e-2)
+    assert torch.allclose(lse, torch.logsumexp(s, dim=-1) * 1.4426950408889634, atol=2e-3, rtol=1e-4)
+    ref.backward(dout.float())
+    dqkv = torch.full((N, T, 3 * W), float("nan"), device=DEV, dtype=BF)
+    call("mha_flash_bwd", qkv, out, dout, lse, torch.empty_like(lse), dqkv, N, T, heads, 64, 0.125, causal)
+    close(dqkv, x.grad, 2e-2)
+    if T <= 64 and not causal:
+        o2 = torch.empty_like(out)
+        call("mha_small_fwd", qkv, o2, N, T, heads, 64, 0.125)
+        close(out, o2.float(), 1e-2)

@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""Per-launch breakdown of one eager train step (config #2) with CUDA events around EVERY ffvc_* launch, aggregated by
-(kernel, shape).  Runs on the GPU box:  python tools/prof_step.py [--batch 64] [--out gpurun_out/step_breakdown.md]
+"""Per-launch breakdown of one eager train step (bench.py --config C) with CUDA events around EVERY ffvc_* launch, aggregated by
+(kernel, shape).  Runs on the GPU box:  python tools/prof_step.py [--config 2] [--batch 0] [--out gpurun_out/step_breakdown.md]
 The numbers are warm-cache, in-step timings (unlike the serialised cold-cache ncu launch list)."""
 import argparse
 import collections
 import os
 import sys
+
+os.environ.setdefault("FFVC_SIDE_STREAMS", "0")     # every launch on the timed stream
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,7 +20,8 @@ from feed_forward_vqgan_clip_b200 import ops  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--out", default="gpurun_out/step_breakdown.md")
     ap.add_argument("--gn-pipeline", type=int, default=1)
     args = ap.parse_args()
@@ -28,7 +31,9 @@ def main():
         _lib.load().ffvc_gemm_set_stream_k(int(os.environ["FFVC_STREAM_K"]))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
-    ts = bench.build_b200(dev, args.batch, 1, None)
+    conf = bench.CONFIGS[args.config]
+    args.batch = args.batch or conf["batch"]
+    ts = bench.build_b200(dev, conf, 1, None)
     x = bench.synthetic_embeddings(args.batch, 1000).to(dev)
     ts.step(x)
     ts.step(x)
@@ -83,8 +88,8 @@ def main():
         a[1] += t
         a[2] += fl
     tot = sum(a[1] for a in agg.values())
-    lines = ["# eager step breakdown (CUDA events per launch), batch %d: step %.2f ms, sum of launches %.2f ms, %d launches"
-             % (args.batch, s_all.elapsed_time(e_all), tot, len(recs)), "", "| launch | n | ms total | us each | TFLOP/s |", "|---|---:|---:|---:|---:|"]
+    lines = ["# eager step breakdown (CUDA events per launch), config #%d, batch %d: step %.2f ms, sum of launches %.2f ms, %d launches"
+             % (args.config, args.batch, s_all.elapsed_time(e_all), tot, len(recs)), "", "| launch | n | ms total | us each | TFLOP/s |", "|---|---:|---:|---:|---:|"]
     for key, (n, t, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append("| %s | %d | %.3f | %.1f | %s |" % (key, n, t, 1e3 * t / n, ("%.0f" % (fl / t / 1e9)) if fl else ""))
     os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
