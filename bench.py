@@ -273,6 +273,8 @@ def main():
                     help="N>1: mixer layers per gradient all-reduce bucket (overlapped with backward); 0 = one all-reduce after backward")
     ap.add_argument("--tail-overlap", action="store_true",
                     help="N>1: run Adam on the already-reduced slices while the last gradient bucket is in flight")
+    ap.add_argument("--no-adam-overlap", action="store_true",
+                    help="N>1: one Adam launch after the last all-reduce instead of per-bucket updates behind each bucket's all-reduce")
     ap.add_argument("--comm-sms", type=int, default=0,
                     help="N>1: SMs left to NCCL while gradient buckets are in flight — sets NCCL_MAX_CTAS and sizes the persistent GEMM grids "
                          "to (SMs - this) during the overlapped part of backward; 0 = off")
@@ -329,8 +331,9 @@ def main():
         ts.bucket_layers = args.bucket_layers
     ts.tail_overlap = bool(args.tail_overlap)
     ts.comm_sms = args.comm_sms if world > 1 else 0
+    ts.adam_overlap = not args.no_adam_overlap
     if world > 1:
-        config.update(bucket_layers=ts.bucket_layers, tail_overlap=ts.tail_overlap, comm_sms=ts.comm_sms,
+        config.update(bucket_layers=ts.bucket_layers, tail_overlap=ts.tail_overlap, comm_sms=ts.comm_sms, adam_overlap=ts.adam_overlap,
                       nccl_max_ctas=os.environ.get("NCCL_MAX_CTAS"))
     x_host = [synthetic_embeddings(B, 1000 + 7919 * rank + i).pin_memory() for i in range(4)]
     Bimg = B * rep                                            # rows of the (repeated) batch = generated images per step

@@ -57,8 +57,11 @@ def num_sms():
 # noise).  fork() enqueues such work on a side stream ordered after everything issued so far on the current stream; join() makes
 # the current stream wait for it.  The caller joins BEFORE freeing any tensor the forked work reads (so the caching allocator
 # never hands its memory out again while the side stream is still reading) and before the step ends (so a CUDA-graph capture
-# closes with one stream).  FFVC_SIDE_STREAMS=0 runs everything inline.
-SIDE_STREAMS = os.environ.get("FFVC_SIDE_STREAMS", "1") == "1"
+# closes with one stream).
+# Measured on the B200 (profiles/r02_ab_side_streams.md): NEUTRAL — the persistent tcgen05 kernels fill every SM's registers and
+# shared memory, so forked launches cannot co-reside with them, and the GPU runs at its power cap, where step time follows the
+# energy spent rather than the critical path.  Hence off by default (FFVC_SIDE_STREAMS=1 enables it).
+SIDE_STREAMS = os.environ.get("FFVC_SIDE_STREAMS", "0") == "1"
 _side = {}
 _pending = set()
 
