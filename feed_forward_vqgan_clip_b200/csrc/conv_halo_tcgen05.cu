@@ -43,8 +43,18 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128_off(uint32_t saddr) {
   return umma_smem_desc_sw128(saddr, 16u, 1024u);
 }
 
-template <int kEW>
-__global__ void __launch_bounds__(64 + 32 * kEW, 1)
+// kXf: kXfWarps TRANSFORM warps (the last threads of the CTA) sit between the TMA producer and the MMA issuer: when a halo tile has landed
+// they rewrite it in place, y = swish(gamma * (x - mean) * rstd + beta) per (image, channel) — taming's Normalize + nonlinearity
+// in front of this conv — skip the zero-filled padding pixels (the conv pads the ACTIVATED tensor), fence the
+// generic-proxy writes for the tensor core and release the tile to the MMA warp (hready barrier).  A thread owns physical 16-byte
+// chunk (t & 7) of lines (t >> 3) + 4 kXfWarps k: because the line step is a multiple of 8, the 128B-swizzle phase (line & 7) — hence the
+// LOGICAL chunk, hence the 8 channels and their scale / shift — is fixed per thread.  swish(t) = h + h tanh(h), h = t / 2: two FFMA
+// and one MUFU.TANH per element; 33 K elements per tile chunk = 2080 clk of MUFU against ~4700 clk of MMAs on that chunk.
+static constexpr int kXfWarps = 4;   // transform warps.  8 (two per scheduler) measured the same: the transform is not issue-bound, it
+                                     // competes with the tensor core for the shared-memory port (profiles/r02_gn_apply_fusion.md)
+
+template <int kEW, bool kXf>
+__global__ void __launch_bounds__(64 + 32 * kEW + (kXf ? 32 * kXfWarps : 0), 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const GemmDev p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -57,6 +67,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   auto bempty_bar = [&](int s) { return bar_base + 8u * (8 + s); };   // 4
   auto tfull_bar = [&](int a) { return bar_base + 8u * (12 + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (14 + a); };
+  auto hready_bar = [&](int i) { return bar_base + 8u * (18 + i); };  // 2: halo tile transformed (kXf)
   const uint32_t tmem_slot = bar_base + 8u * 16;
   const uint32_t bias_smem = bar_base + 256u;
   const uint32_t gn_smem = bias_smem + 2048u;
@@ -70,6 +81,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(hfull_bar(i), 1);
       mbar_init(hempty_bar(i), 1);
+      mbar_init(hready_bar(i), kXfWarps);       // one arrival per transform warp
     }
     for (int s = 0; s < kBStages; ++s) {
       mbar_init(bfull_bar(s), 1);
@@ -138,7 +150,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * 256u;
         for (int c = 0; c < cblocks; ++c) {
-          mbar_wait(hfull_bar(hb), hphase);
+          mbar_wait(kXf ? hready_bar(hb) : hfull_bar(hb), hphase);
           tc_fence_after();
           const uint32_t halo = halo_base + hb * kHaloStride;
           for (int tap = 0; tap < 9; ++tap) {
@@ -176,6 +188,75 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         }
       }
     }
+  } else if (kXf && warp >= 2 + kEW) {
+    // ------------------------------------------------------------------ transform warps: GroupNorm + swish on the halo tile, in place
+    const int xt = threadIdx.x - (64 + 32 * kEW);        // 0 .. 32 * kXfWarps - 1
+    const int pch = xt & 7, lrow = xt >> 3;              // physical 16-byte chunk, first line
+    const int j = pch ^ (lrow & 7);                      // logical chunk: channels 8 j .. 8 j + 7 of the 64-channel block
+    int hb = 0;
+    uint32_t hphase = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int tx = (int)(t % tiles_x);
+      const int ty = (int)((t / tiles_x) % tiles_y);
+      const int img = (int)(t / ((long long)tiles_x * tiles_y));
+      const int y0 = ty * 2 - 1, x0 = tx * 128 - 1;
+      for (int c = 0; c < cblocks; ++c) {
+        // half-scale / half-shift of this thread's 8 channels (fetched while the tile is still in flight)
+        float sc[8], sh[8];
+        const int ch0 = c * 64 + j * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int ch = ch0 + k;
+          const int g = img * p.xf_groups + ch / p.xf_cpg;
+          const float rs = p.xf_rstd[g], ga = p.xf_gamma[ch];
+          sc[k] = 0.5f * rs * ga;
+          sh[k] = 0.5f * (p.xf_beta[ch] - p.xf_mean[g] * rs * ga);
+        }
+        mbar_wait(hfull_bar(hb), hphase);
+        const uint32_t tile = halo_base + hb * kHaloStride + (uint32_t)pch * 16u;
+        // four lines per trip (loads first, then the arithmetic, then the stores): a thread's 33 lines are a dependent
+        // LDS -> FFMA -> MUFU -> FFMA -> STS chain each, and with one transform warp per scheduler nothing else hides its latency
+        constexpr int kLineStep = 4 * kXfWarps;            // lines between a thread's consecutive lines (a multiple of 8)
+        for (int line0 = lrow; line0 < kHaloRows * kHaloPix; line0 += 4 * kLineStep) {
+          uint4 v[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int line = line0 + kLineStep * u;
+            const int r = line / kHaloPix, px = line - r * kHaloPix;
+            const int yy = y0 + r, xx = x0 + px;
+            ok[u] = line < kHaloRows * kHaloPix && yy >= 0 && yy < H && xx >= 0 && xx < W;      // padding pixels stay zero
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[u]) {
+              const uint32_t a = tile + (uint32_t)line * 128u;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "r"(a));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[k]));
+              const float h0 = fmaf(f.x, sc[2 * k], sh[2 * k]), h1 = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
+              const __nv_bfloat162 o = __floats2bfloat162_rn(fmaf(h0, tanh_approx(h0), h0), fmaf(h1, tanh_approx(h1), h1));
+              w4[k] = *reinterpret_cast<const uint32_t*>(&o);
+            }
+            v[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (ok[u]) st_shared_v4(tile + (uint32_t)(line0 + kLineStep * u) * 128u, v[u]);
+        }
+        fence_proxy_async_smem();                          // generic-proxy writes -> visible to tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hready_bar(hb));
+        if (++hb == 2) {
+          hb = 0;
+          hphase ^= 1u;
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9): sub-tile = output row
     const int q = warp & 3;
@@ -193,7 +274,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // 32-byte (256-bit) row accesses when every row starts on a 32-byte boundary (bf16 output): half the L1 requests
     const bool vec32_ok = vec_ok && !p.out_fp32 && (p.ldc % 16 == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.aux) | reinterpret_cast<uintptr_t>(p.res)) & 31) == 0;
-    const bool gnb = p.gn_ws && p.gn_bwd;
+    const bool gnb = !kXf && p.gn_ws && p.gn_bwd;          // (the forward-only transform variant never takes backward statistics)
     const bool want_aux = p.mul_mode != FFVC_ACT_NONE || gnb, want_res = p.res != nullptr;
     if (gnb && etid < 128) {                  // gamma / beta of the Normalize, once per CTA (the bias staging area is free: dgrad)
       sbias_all[etid] = p.gn_gamma[etid];
@@ -423,7 +504,9 @@ using namespace ffvc;
 static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
                                const float* bias, const void* res, const void* aux, int mul_mode, int act, int out_fp32,
                                double* gn_ws, void* stream, const float* gnb_mean = nullptr, const float* gnb_rstd = nullptr,
-                               const float* gnb_gamma = nullptr, const float* gnb_beta = nullptr) {
+                               const float* gnb_gamma = nullptr, const float* gnb_beta = nullptr, const float* xf_mean = nullptr,
+                               const float* xf_rstd = nullptr, const float* xf_gamma = nullptr, const float* xf_beta = nullptr,
+                               int xf_groups = 0) {
   if (!x || !w || !out) return set_error(FFVC_ERR_ARG, "conv_halo: null pointer");
   if (gn_ws && (cout != 128 || out_fp32 || ldc % 16 != 0))
     return set_error(FFVC_ERR_UNSUPPORTED, "conv_halo: epilogue GroupNorm statistics need Cout = 128 (32 groups of 4), bf16 output");
@@ -432,9 +515,11 @@ static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, i
   static bool attr_done = false;
   static int num_sms = 0;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
     if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
-    e = cudaFuncSetAttribute(conv3x3_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
+    if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(conv3x3_halo_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem);
     if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
@@ -486,14 +571,26 @@ static int conv3x3_halo_launch(const void* x, const void* w, void* out, int n, i
     p.gn_gamma = gnb_gamma;
     p.gn_beta = gnb_beta;
   }
+  if (xf_mean) {
+    if (!xf_rstd || !xf_gamma || !xf_beta || xf_groups <= 0 || cin % xf_groups != 0)
+      return set_error(FFVC_ERR_ARG, "conv_halo_xf: statistics / affine pointers and a group count dividing Cin are required");
+    p.xf_mean = xf_mean;
+    p.xf_rstd = xf_rstd;
+    p.xf_gamma = xf_gamma;
+    p.xf_beta = xf_beta;
+    p.xf_groups = xf_groups;
+    p.xf_cpg = cin / xf_groups;
+  }
   const long long tiles = (long long)n * (h / 2) * (wd / 128);
   const int grid = (int)(tiles < sm_budget(num_sms) ? tiles : sm_budget(num_sms));
   // 16 epilogue warps for the GroupNorm-statistics epilogues (option "halo_epi16": 1 = backward statistics, 2 = forward too)
   const int epi16 = gn_ws ? option(OPT_HALO_EPI16) : 0;
-  if (block_n == 128 && ((epi16 >= 1 && p.gn_bwd) || epi16 >= 2))
-    conv3x3_halo_kernel<16><<<grid, 64 + 32 * 16, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+  if (xf_mean)
+    conv3x3_halo_kernel<8, true><<<grid, 64 + 32 * 8 + 32 * kXfWarps, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+  else if (block_n == 128 && ((epi16 >= 1 && p.gn_bwd) || epi16 >= 2))
+    conv3x3_halo_kernel<16, false><<<grid, 64 + 32 * 16, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
   else
-    conv3x3_halo_kernel<8><<<grid, 64 + 32 * 8, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+    conv3x3_halo_kernel<8, false><<<grid, 64 + 32 * 8, kHaloSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   count_launch();
@@ -526,4 +623,16 @@ extern "C" int ffvc_conv3x3_halo_gnbwd(const void* x, const void* w, void* out, 
   if (!gn_ws || !gn_x || !gn_mean || !gn_rstd || !gn_gamma || !gn_beta) return set_error(FFVC_ERR_ARG, "conv_halo_gnbwd: null pointer");
   return conv3x3_halo_launch(x, w, out, n, h, wd, cin, cout, ldc, nullptr, res, gn_x, 0, 0, 0, gn_ws, stream, gn_mean, gn_rstd,
                              gn_gamma, gn_beta);
+}
+
+// The conv applied to swish(GroupNorm(x)) without that tensor ever existing: x is the RAW input of taming's Normalize + nonlinearity
+// in front of this conv; four transform warps normalise every halo tile in shared memory between the TMA load and the MMAs (see
+// conv3x3_halo_kernel).  xf_mean / xf_rstd: [n][xf_groups] statistics of x (ffvc_groupnorm_stats / _finalize), xf_gamma / xf_beta:
+// [cin].  gn_ws (optional, Cout = 128): also take the GroupNorm(32) statistics of the OUTPUT in the epilogue, as ffvc_conv3x3_halo_gn.
+extern "C" int ffvc_conv3x3_halo_xf(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                                    const float* bias, const void* res, const float* xf_mean, const float* xf_rstd,
+                                    const float* xf_gamma, const float* xf_beta, int xf_groups, double* gn_ws, void* stream) {
+  if (!xf_mean) return set_error(FFVC_ERR_ARG, "conv_halo_xf: null statistics");
+  return conv3x3_halo_launch(x, w, out, n, h, wd, cin, cout, ldc, bias, res, nullptr, 0, 0, 0, gn_ws, stream, nullptr, nullptr, nullptr,
+                             nullptr, xf_mean, xf_rstd, xf_gamma, xf_beta, xf_groups);
 }

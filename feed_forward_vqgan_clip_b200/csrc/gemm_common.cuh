@@ -47,6 +47,14 @@ struct GemmDev {
   const float* gn_rstd;
   const float* gn_gamma;        // [128]
   const float* gn_beta;
+  // conv3x3_halo only, xf_mean != nullptr: the INPUT tensor is the raw input x of a Normalize (GroupNorm(xf_groups) + swish); four
+  // transform warps apply it to every halo tile in shared memory between the TMA load and the MMAs (the normalised tensor never
+  // exists in HBM).  xf_mean / xf_rstd: [images][xf_groups]; xf_gamma / xf_beta: [Cin].
+  const float* xf_mean;
+  const float* xf_rstd;
+  const float* xf_gamma;
+  const float* xf_beta;
+  int xf_groups, xf_cpg;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

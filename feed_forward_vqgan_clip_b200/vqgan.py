@@ -219,6 +219,36 @@ class DecoderEngine:
     # (mean, rstd) are produced on the fly and `gn` skips the statistics pass.  FFVC_GN_EPI_STATS=0 selects the separate pass.
     GN_EPI_STATS = os.environ.get("FFVC_GN_EPI_STATS", "1") == "1"    # measured +0.9 % prompts/s (profiles/r01_ab_kernels.md)
 
+    # GroupNorm apply + swish fused into the consuming conv (ffvc_conv3x3_halo_xf): the wide layers never materialise the normalised
+    # tensor (-17 GB of HBM traffic per step at config #2).  Built, parity-tested — and measured SLOWER on the B200: the halo conv is
+    # bound by the shared-memory port (128 x 128 x 16 MMAs), and the in-place transform of the halo tile takes its share of that
+    # port: 1465 us per 256 x 256 layer against 982 us conv + 395 us apply pass; step 114.1 ms against 111.5 ms
+    # (profiles/r02_gn_apply_fusion.md).  Off by default; FFVC_GN_FUSE_APPLY=1 selects it.
+    GN_FUSE_APPLY = os.environ.get("FFVC_GN_FUSE_APPLY", "0") == "1"
+
+    def gn_stats(self, x, N, HW, C):
+        """(mean, rstd) of a Normalize's input: from the epilogue of the conv that wrote x when it left them, else one statistics pass"""
+        st = self._epi_stats.pop(x.data_ptr(), None)
+        if st is not None and st[2] == N * HW * C:
+            return st[0], st[1]
+        mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
+        call("groupnorm_stats", x, self._gn_ws(N, HW), mean, rstd, N, HW, C, 32, 1e-6)
+        return mean, rstd
+
+    def conv3_of_gn(self, x, st, nname, name, N, H, W, cin, cout, res=None, gn_next=True):
+        """conv(swish(GroupNorm(x))) with the apply fused into the conv's operand path; st = (mean, rstd) of x"""
+        out = self._new(N * H * W, cout)
+        ws = None
+        if gn_next and self.GN_EPI_STATS and cout == 128:
+            ws = self._gn_ws(N, H * W)
+        call("conv3x3_halo_xf", x, self.pk[name + ".w"], out, N, H, W, cin, cout, cout, self.pk[name + ".b"], res, st[0], st[1],
+             self.pk[nname + ".g"], self.pk[nname + ".be"], 32, ws)
+        if ws is not None:
+            mean, rstd = self._new(N * 32, dtype=F32), self._new(N * 32, dtype=F32)
+            call("groupnorm_finalize", ws, mean, rstd, N, H * W, cout, 32, 1e-6)
+            self._epi_stats[out.data_ptr()] = (mean, rstd, N * H * W * cout)
+        return out
+
     def conv3(self, x, name, N, H, W, cin, cout, res=None, out_f32=False, gn_next=True):
         """gn_next: the output goes straight into a Normalize (true for every decoder conv but the last one of a level
         that is followed by Upsample, and conv_out)"""
@@ -304,13 +334,22 @@ class DecoderEngine:
 
     def resblock(self, x, name, N, H, W, cin, cout, tape, gn_next=True):
         HW = H * W
-        a1, st1 = self.gn(x, name + ".norm1", N, HW, cin, True)
-        h1 = self.conv3(a1, name + ".conv1", N, H, W, cin, cout)
-        del a1
-        a2, st2 = self.gn(h1, name + ".norm2", N, HW, cout, True)
+        if self.GN_FUSE_APPLY and self._halo_ok(H, W, cin, cout) and not self._gn_fused(HW, cin):
+            st1 = self.gn_stats(x, N, HW, cin)
+            h1 = self.conv3_of_gn(x, st1, name + ".norm1", name + ".conv1", N, H, W, cin, cout)
+        else:
+            a1, st1 = self.gn(x, name + ".norm1", N, HW, cin, True)
+            h1 = self.conv3(a1, name + ".conv1", N, H, W, cin, cout)
+            del a1
         short = x if cin == cout else self.conv1(x, name + ".nin_shortcut", N * HW, cin, cout)
-        out = self.conv3(a2, name + ".conv2", N, H, W, cout, cout, res=short, gn_next=gn_next)
-        del a2, short
+        if self.GN_FUSE_APPLY and self._halo_ok(H, W, cout, cout) and not self._gn_fused(HW, cout):
+            st2 = self.gn_stats(h1, N, HW, cout)
+            out = self.conv3_of_gn(h1, st2, name + ".norm2", name + ".conv2", N, H, W, cout, cout, res=short, gn_next=gn_next)
+        else:
+            a2, st2 = self.gn(h1, name + ".norm2", N, HW, cout, True)
+            out = self.conv3(a2, name + ".conv2", N, H, W, cout, cout, res=short, gn_next=gn_next)
+            del a2
+        del short
 
         def bwd(d):
             d2, s2 = self.conv3_dgrad(d, name + ".conv2", N, H, W, cout, cout, gnb=(h1, st2, name + ".norm2"))

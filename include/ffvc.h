@@ -148,6 +148,15 @@ long long ffvc_groupnorm_ws_doubles(int N, int HW, int G);
 int ffvc_conv3x3_halo_gn(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
                          const float* bias, const void* res, double* gn_ws, void* stream);
 int ffvc_groupnorm_finalize(double* ws, float* mean, float* rstd, int N, int HW, int C, int G, float eps, void* stream);
+/* The same conv applied to swish(GroupNorm(x)) WITHOUT that tensor ever existing in HBM: x is the raw input of taming's
+ * Normalize + nonlinearity in front of the conv (K6 of SURVEY 2.4).  Four transform warps normalise every halo
+ * tile in shared memory between the TMA load and the MMAs — y = swish(gamma * (x - mean) * rstd + beta), padding pixels stay
+ * zero — so the separate ffvc_groupnorm_apply pass (one read + one write of the tensor) and the re-read by the conv disappear.
+ * xf_mean / xf_rstd: [n][xf_groups] statistics of x; xf_gamma / xf_beta: [cin].  gn_ws (optional, Cout = 128): the epilogue
+ * also takes the GroupNorm(32) statistics of the output, as ffvc_conv3x3_halo_gn. */
+int ffvc_conv3x3_halo_xf(const void* x, const void* w, void* out, int n, int h, int wd, int cin, int cout, long long ldc,
+                         const float* bias, const void* res, const float* xf_mean, const float* xf_rstd, const float* xf_gamma,
+                         const float* xf_beta, int xf_groups, double* gn_ws, void* stream);
 /* dgrad form (no bias): `out` = dy of the Normalize + swish in front of the forward conv (Cout = 128 channels), stored as
  * usual; the epilogue also reads that layer's input gn_x at the same positions and takes the backward statistics
  * sum g, sum g * xhat per (image, group), g = dy * swish'(gamma * xhat + beta) * gamma (per-tile partials in gn_ws, layout

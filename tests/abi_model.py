@@ -337,6 +337,16 @@ def k_conv3x3_halo_gn(x, w, out, n, h, wd, cin, cout, ldc, bias, res, gn_ws):
     gn_ws.view(-1)[:n * 64] = _group_sums(o, o, n, h * wd, cout).reshape(-1)
 
 
+def k_conv3x3_halo_xf(x, w, out, n, h, wd, cin, cout, ldc, bias, res, xf_mean, xf_rstd, xf_gamma, xf_beta, xf_groups, gn_ws):
+    """the conv of swish(GroupNorm(x)) (statistics given), the normalised tensor rounded to bf16 like the kernel's shared-memory tile"""
+    a = torch.empty(n * h * wd, cin, dtype=torch.bfloat16)
+    k_groupnorm_apply(x, xf_mean, xf_rstd, xf_gamma, xf_beta, a, n, h * wd, cin, xf_groups, 1)
+    if gn_ws is not None:
+        k_conv3x3_halo_gn(a, w, out, n, h, wd, cin, cout, ldc, bias, res, gn_ws)
+    else:
+        k_conv3x3_halo(a, w, out, n, h, wd, cin, cout, ldc, bias, res, None, 0, 0, 0)
+
+
 def k_groupnorm_finalize(ws, mean, rstd, N, HW, C, G, eps):
     s = ws.reshape(-1)[:N * G * 2].view(N, G, 2)
     cnt = HW * (C // G)

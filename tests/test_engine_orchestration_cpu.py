@@ -133,8 +133,9 @@ MID_VQ = dict(ch=128, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(64,), 
               embed_dim=64, n_embed=512)      # 128 channels at 128 x 128: the halo-reuse conv entry points and their GroupNorm epilogues
 
 
+@pytest.mark.parametrize("fuse_apply", [True, False])
 @pytest.mark.parametrize("epilogue_stats", [True, False])
-def test_decoder_engine_orchestration(abi_on_cpu, monkeypatch, epilogue_stats):
+def test_decoder_engine_orchestration(abi_on_cpu, monkeypatch, epilogue_stats, fuse_apply):
     """DecoderEngine (VQModel.decode, main.py:142) forward + gradient w.r.t. z_q: implicit-GEMM convs, the halo-reuse conv
     entry points with GroupNorm statistics handed from the conv epilogues to the Normalize that follows (forward) / precedes
     (backward), or the separate statistics passes; attention block; upsample; conv_out and its im2col dgrad."""
@@ -143,6 +144,7 @@ def test_decoder_engine_orchestration(abi_on_cpu, monkeypatch, epilogue_stats):
     monkeypatch.setattr(vqgan, "call", abi_model.call)
     monkeypatch.setattr(vqgan.DecoderEngine, "GN_EPI_STATS", epilogue_stats)
     monkeypatch.setattr(vqgan.DecoderEngine, "GN_EPI_BWD", epilogue_stats)
+    monkeypatch.setattr(vqgan.DecoderEngine, "GN_FUSE_APPLY", fuse_apply)
     seen = []
     monkeypatch.setattr(abi_model, "call", lambda name, *a: (seen.append(name), getattr(abi_model, "k_" + name)(*a))[1])
     monkeypatch.setattr(vqgan, "call", abi_model.call)
@@ -161,10 +163,12 @@ def test_decoder_engine_orchestration(abi_on_cpu, monkeypatch, epilogue_stats):
     (yr * w).sum().backward()
     assert float((y - yr).detach().abs().max()) <= 3e-2 * float(yr.detach().abs().max())
     assert cos(zc.grad, zr.grad) > 0.99
-    assert ("conv3x3_halo_gn" in seen) == epilogue_stats and ("conv3x3_halo_gnbwd" in seen) == epilogue_stats
+    # forward: the wide convs either take the normalised tensor (conv3x3_halo[_gn]) or normalise the raw one on load (conv3x3_halo_xf)
+    assert ("conv3x3_halo_xf" in seen) == fuse_apply and ("conv3x3_halo_gnbwd" in seen) == epilogue_stats
+    assert ("conv3x3_halo_gn" in seen) == (epilogue_stats and not fuse_apply)
     # conv_out: one GEMM into the tap columns + the gather (round 2; the implicit-GEMM halo form was its only plain conv3x3_halo here)
     assert "conv_taps_gather" in seen and "groupnorm_bwd" in seen and "im2col3x3_cin3" in seen
-    assert ("conv3x3_halo" in seen) == (not epilogue_stats)      # without epilogue statistics the wide layers take the plain halo conv
+    assert ("conv3x3_halo" in seen) == (not epilogue_stats)      # without epilogue statistics the wide layers' dgrads (and, unfused, their forwards) take the plain halo conv
 
 
 SMALL_VQ = dict(ch=64, ch_mult=(1, 2), num_res_blocks=1, attn_resolutions=(16,), resolution=32, z_channels=64, out_ch=3,

@@ -463,3 +463,51 @@ def test_conv3x3_halo_epilogue_groupnorm_backward_statistics(n, h, w, cin, epi16
     call("groupnorm_bwd_apply", dy2, x, mean, rstd, gamma, beta, sums2, add, dx2, n, h * w, cout, 32, 1)
     assert torch.equal(sums[:n * 64], sums2[:n * 64]) and torch.equal(dx1, dx2)
     assert (dx1.float() - dx0.float()).abs().max().item() <= 2e-2 * dx0.float().abs().max().item()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,with_res,with_stats", [(2, 128, 128, 128, 128, True, True), (3, 4, 256, 64, 128, False, True),
+                                                               (1, 256, 256, 128, 128, True, False), (2, 6, 128, 256, 128, False, True),
+                                                               (5, 2, 128, 128, 64, False, False)])
+def test_conv3x3_halo_with_fused_groupnorm_apply(n, h, w, cin, cout, with_res, with_stats):
+    """ffvc_conv3x3_halo_xf — the conv of swish(GroupNorm(x)) with the apply done by transform warps on the halo tile in shared
+    memory — against ffvc_groupnorm_apply followed by the plain halo conv (taming Normalize + nonlinearity + Conv2d): same output up
+    to the bf16 rounding of the normalised tensor (the fused form computes swish as h + h tanh(h)), borders (zero padding of the
+    ACTIVATED tensor) included, and the same epilogue statistics of the output; twice the same bits."""
+    from feed_forward_vqgan_clip_b200 import _lib
+    from feed_forward_vqgan_clip_b200.ops import call
+    BF = torch.bfloat16
+    g = torch.Generator().manual_seed(11)
+    x = (0.3 + 1.7 * torch.randn(n, h, w, cin, generator=g)).to(DEV).to(BF)
+    wt = (torch.randn(cout, 9, cin, generator=g) * (9 * cin) ** -0.5).to(DEV).to(BF)
+    bias = torch.randn(cout, generator=g).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(cin, generator=g)).to(DEV)
+    beta = (0.5 * torch.randn(cin, generator=g)).to(DEV)            # a large shift: a wrong padding value would show at the borders
+    res = torch.randn(n * h * w, cout, generator=g).to(DEV).to(BF) if with_res else None
+    nws = int(_lib.load().ffvc_groupnorm_ws_doubles(n, h * w, 32))
+    ws = torch.empty(nws, device=DEV, dtype=torch.float64)
+    mean, rstd = torch.empty(n * 32, device=DEV), torch.empty(n * 32, device=DEV)
+    call("groupnorm_stats", x, ws, mean, rstd, n, h * w, cin, 32, 1e-6)
+    a = torch.empty_like(x)
+    call("groupnorm_apply", x, mean, rstd, gamma, beta, a, n, h * w, cin, 32, 1)
+    out0 = torch.empty(n * h * w, cout, device=DEV, dtype=BF)
+    call("conv3x3_halo", a, wt, out0, n, h, w, cin, cout, cout, bias, res, None, 0, 0, 0)
+    outs = []
+    for _ in range(2):
+        out1 = torch.full((n * h * w, cout), float("nan"), device=DEV, dtype=BF)
+        ws1 = torch.full((nws,), float("nan"), device=DEV, dtype=torch.float64) if with_stats else None
+        call("conv3x3_halo_xf", x, wt, out1, n, h, w, cin, cout, cout, bias, res, mean, rstd, gamma, beta, 32, ws1)
+        outs.append(out1)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    err = (outs[0].float() - out0.float()).abs().max().item()
+    assert err <= 2e-2 * out0.float().abs().max().item(), err
+    o4 = outs[0].float().view(n, h, w, cout)
+    r4 = out0.float().view(n, h, w, cout)
+    for sl in ((slice(None), 0), (slice(None), h - 1), (slice(None), slice(None), 0), (slice(None), slice(None), w - 1)):
+        assert (o4[sl] - r4[sl]).abs().max().item() <= 2e-2 * r4.abs().max().item()          # image borders
+    if with_stats:
+        m1, r1 = torch.empty(n * 32, device=DEV), torch.empty(n * 32, device=DEV)
+        call("groupnorm_finalize", ws1, m1, r1, n, h * w, cout, 32, 1e-6)
+        m2, r2 = torch.empty_like(m1), torch.empty_like(r1)
+        call("groupnorm_stats", outs[1], ws, m2, r2, n, h * w, cout, 32, 1e-6)
+        assert torch.allclose(m1, m2, atol=1e-5, rtol=1e-5) and torch.allclose(r1, r2, rtol=1e-4)

@@ -52,7 +52,10 @@ def case_halo(kind, n=64, h=256, w=256, cin=128, cout=128):
     gx = rnd(n * h * w, 128, seed=5) if "gnbwd" in kind else None
 
     def fn(i):
-        if kind.startswith("gnbwd"):
+        if kind.startswith("xf"):
+            call("conv3x3_halo_xf", xs[i], wt, outs[i], n, h, w, cin, cout, cout, bias, res, mean, rstd, gamma, beta, 32,
+                 ws if "gn" in kind else None)
+        elif kind.startswith("gnbwd"):
             call("conv3x3_halo_gnbwd", xs[i], wt, outs[i], n, h, w, cin, cout, cout, res, gx, mean, rstd, gamma, beta, ws)
         elif kind.startswith("gn"):
             call("conv3x3_halo_gn", xs[i], wt, outs[i], n, h, w, cin, cout, cout, bias, res, ws)
@@ -125,6 +128,9 @@ CASES = {
     "halo_gn_res": lambda: case_halo("gn_res"),
     "halo_gnbwd": lambda: case_halo("gnbwd"),
     "halo_plain_res": lambda: case_halo("plain_res"),
+    "halo_xf": lambda: case_halo("xf"),
+    "halo_xf_gn": lambda: case_halo("xf_gn"),
+    "halo_xf_gn_res": lambda: case_halo("xf_gn_res"),
     "gemm_mul1": lambda: case_gemm("mul1"),
     "gemm_act1pre": lambda: case_gemm("act1pre"),
     "gemm_plain4096": lambda: case_gemm("plain4096"),
