@@ -108,7 +108,17 @@ class CheckpointWriter:
         sizes = [self.hi - self.lo] * len(self.names) + [self.opt.hyper.numel()]      # + Adam's device-side scalar block
         self.snap = (snapshot_cls or _CudaSnapshot)(sizes, self.eng.arena.device) if self.active else None
         self.thread, self.error = None, None
+        self._steps = []
         os.makedirs(folder, exist_ok=True)
+        import atexit
+        atexit.register(self._finish_at_exit)
+
+    def _finish_at_exit(self):
+        try:
+            self.wait()
+        except Exception as e:                                        # nobody is left to call wait(): say it
+            import sys
+            sys.stderr.write("CheckpointWriter: the last save failed: %r\n" % (e,))
 
     def _arenas(self):
         a = {"arena": self.eng.arena, "m": self.opt.m, "v": self.opt.v}
@@ -138,19 +148,31 @@ class CheckpointWriter:
                 bufs = dict(zip(self.names, host))
                 adam_step, group = _adam_group(self.opt, host[len(self.names)])
                 if self.sharded:
+                    # shards carry their step in the file name and the previous generation is kept: ranks write independently (no
+                    # barrier), so after a crash the newest index may point at a step some rank never finished — load_sharded then
+                    # falls back to the previous index, whose shards are all still there
                     _atomic_save({"lo": self.lo, "hi": self.hi, "total": self.eng.arena.numel(), "step": step, "epoch": epoch,
                                   **{k: bufs[k] for k in self.names}},
-                                 os.path.join(self.folder, "checkpoint.shard-%02d-of-%02d.th" % (self.rank, self.world)))
+                                 os.path.join(self.folder, _shard_name(self.rank, self.world, step)))
                     if self.rank == 0:
+                        idx = os.path.join(self.folder, "checkpoint.index.th")
+                        if os.path.exists(idx):
+                            os.replace(idx, os.path.join(self.folder, "checkpoint.index.prev.th"))
                         _atomic_save({"layout": self.layout, "config": self.config, "step": step, "epoch": epoch, "world": self.world,
-                                      "adam_step": adam_step, "adam_group": group, "names": self.names, "extra": extra},
-                                     os.path.join(self.folder, "checkpoint.index.th"))
+                                      "adam_step": adam_step, "adam_group": group, "names": self.names, "extra": extra}, idx)
+                    self._steps.append(step)
+                    for old in self._steps[:-2]:                      # keep this generation and the previous one
+                        try:
+                            os.remove(os.path.join(self.folder, _shard_name(self.rank, self.world, old)))
+                        except OSError:
+                            pass
+                    del self._steps[:-2]
                     return
                 write_reference_files(self.folder, self.layout, bufs, self.config, step, epoch, adam_step, group, extra)
             except Exception as e:                                     # surfaced by the next wait() / save()
                 self.error = e
 
-        self.thread = threading.Thread(target=work, daemon=True)
+        self.thread = threading.Thread(target=work, daemon=False)    # a process that exits right after save() still finishes the write
         self.thread.start()
         if blocking:
             self.wait()
@@ -177,14 +199,29 @@ def write_reference_files(folder, layout, bufs, config, step, epoch, adam_step, 
     _atomic_save(adam_state_from_arenas(layout, bufs["m"], bufs["v"], adam_step, group), os.path.join(folder, "opt.th"))
 
 
+def _shard_name(rank, world, step):
+    return "checkpoint.shard-%02d-of-%02d.step-%d.th" % (rank, world, step)
+
+
 def load_sharded(folder):
     """Reassemble a sharded checkpoint: returns (checkpoint dict, ema checkpoint dict or None, Adam state_dict) in the
-    reference's formats — what `write_reference_files` would have written from one rank."""
-    index = torch.load(os.path.join(folder, "checkpoint.index.th"), map_location="cpu", weights_only=False)
+    reference's formats — what `write_reference_files` would have written from one rank.  Uses the newest index whose shards
+    are all present (a crash between the ranks' writes leaves the previous generation complete)."""
+    index = None
+    for name in ("checkpoint.index.th", "checkpoint.index.prev.th"):
+        path = os.path.join(folder, name)
+        if not os.path.exists(path):
+            continue
+        cand = torch.load(path, map_location="cpu", weights_only=False)
+        if all(os.path.exists(os.path.join(folder, _shard_name(r, cand["world"], cand["step"]))) for r in range(cand["world"])):
+            index = cand
+            break
+    if index is None:
+        raise RuntimeError("no complete sharded checkpoint in %s" % folder)
     world, names = index["world"], index["names"]
     flat = None
     for r in range(world):
-        sh = torch.load(os.path.join(folder, "checkpoint.shard-%02d-of-%02d.th" % (r, world)), map_location="cpu", weights_only=False)
+        sh = torch.load(os.path.join(folder, _shard_name(r, world, index["step"])), map_location="cpu", weights_only=False)
         if sh["step"] != index["step"]:
             raise RuntimeError("shard %d is from step %d, the index from step %d" % (r, sh["step"], index["step"]))
         if flat is None:

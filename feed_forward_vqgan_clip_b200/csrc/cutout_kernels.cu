@@ -21,32 +21,55 @@ static inline unsigned grid_for_c(long long n, int threads, int cap = 148 * 16) 
   return (unsigned)(g < cap ? g : cap);
 }
 
+// fixed-point accumulators of the backward's scatter stages (see scatter3 below)
+#define FFVC_FX_SCALE 1099511627776.0f            /* 2^40 */
+#define FFVC_FX_INV 9.094947017729282e-13f        /* 2^-40 */
+__device__ __forceinline__ void fx_add(long long* p, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * FFVC_FX_SCALE));
+}
+__device__ __forceinline__ float fx_get(const long long* p) { return (float)(*p) * FFVC_FX_INV; }
+
 // ------------------------------------------------------------------------------ adaptive (avg+max)/2 pooling
 __device__ __forceinline__ int win_start(int i, int in, int out) { return (int)(((long long)i * in) / out); }
 __device__ __forceinline__ int win_end(int i, int in, int out) { return (int)((((long long)(i + 1)) * in + out - 1) / out); }
 
+// Index math: every kernel of this file maps blockIdx.y to an output row and blockIdx.z to an image, threads run along x — the
+// flat 64-bit index of round 1 cost ~10 emulated 64-bit div / mod per element and made these kernels issue-bound (69 - 82 % issue
+// active at 0.4 - 2 TB/s, profiles/r02_ncu_hbm_kernels.md).
 __global__ void pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int P) {
-  const long long total = (long long)B * P * P * 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % 3);
-    long long p = i / 3;
-    const int ox = (int)(p % P);
-    p /= P;
-    const int oy = (int)(p % P);
-    const int b = (int)(p / P);
-    const int y0 = win_start(oy, H, P), y1 = win_end(oy, H, P), x0 = win_start(ox, W, P), x1 = win_end(ox, W, P);
-    float s = 0.f, m = -FLT_MAX;
-    for (int yy = y0; yy < y1; ++yy)
-      for (int xx = x0; xx < x1; ++xx) {
-        const float v = x[(((long long)b * H + yy) * W + xx) * 3 + c];
-        s += v;
-        m = fmaxf(m, v);
-      }
-    y[i] = 0.5f * (s / ((y1 - y0) * (x1 - x0)) + m);
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= P) return;
+  const int oy = blockIdx.y, b = blockIdx.z;
+  const int y0 = (oy * H) / P, y1 = ((oy + 1) * H + P - 1) / P, x0 = (ox * W) / P, x1 = ((ox + 1) * W + P - 1) / P;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, m0 = -FLT_MAX, m1 = -FLT_MAX, m2 = -FLT_MAX;
+  for (int yy = y0; yy < y1; ++yy) {
+    const float* row = x + (((long long)b * H + yy) * W + x0) * 3;
+    for (int xx = 0; xx < x1 - x0; ++xx) {
+      const float v0 = row[3 * xx], v1 = row[3 * xx + 1], v2 = row[3 * xx + 2];
+      s0 += v0;
+      s1 += v1;
+      s2 += v2;
+      m0 = fmaxf(m0, v0);
+      m1 = fmaxf(m1, v1);
+      m2 = fmaxf(m2, v2);
+    }
   }
+  const float inv = 1.0f / (float)((y1 - y0) * (x1 - x0));
+  float* o = y + (((long long)b * P + oy) * P + ox) * 3;
+  o[0] = 0.5f * (s0 * inv + m0);
+  o[1] = 0.5f * (s1 * inv + m1);
+  o[2] = 0.5f * (s2 * inv + m2);
 }
 // gather form: each input pixel collects from every pooled output whose window contains it
-__global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx, int B, int H,
+template <typename TG>
+__device__ __forceinline__ float grad_get(const TG* p);
+template <>
+__device__ __forceinline__ float grad_get<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float grad_get<long long>(const long long* p) { return fx_get(p); }
+
+template <typename TG>
+__global__ void pool_bwd_kernel(const float* __restrict__ x, const TG* __restrict__ dy, float* __restrict__ dx, int B, int H,
                                 int W, int P) {
   const long long total = (long long)B * H * W * 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -65,7 +88,7 @@ __global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __rest
       for (int ox = ox_lo; ox <= ox_hi; ++ox) {
         const int x0 = win_start(ox, W, P), x1 = win_end(ox, W, P);
         if (ix < x0 || ix >= x1) continue;
-        const float g = dy[(((long long)b * P + oy) * P + ox) * 3 + c];
+        const float g = grad_get(dy + (((long long)b * P + oy) * P + ox) * 3 + c);
         acc += 0.5f * g / ((y1 - y0) * (x1 - x0));
         // arg max of the window (first maximum in row-major order, like ATen's adaptive_max_pool2d)
         float m = -FLT_MAX;
@@ -89,7 +112,8 @@ __global__ void pool_bwd_kernel(const float* __restrict__ x, const float* __rest
 // Same gather, laid out so that no 64-bit division is needed and the window geometry is shared by the 3 channels:
 // blockIdx.y = (image, input row), threads run along x.  (The flat form above spends most of its time in emulated
 // 64-bit div/mod: ~10 of them per element.)  Identical arithmetic per element.
-__global__ void __launch_bounds__(128) pool_bwd_rows_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+template <typename TG>
+__global__ void __launch_bounds__(128) pool_bwd_rows_kernel(const float* __restrict__ x, const TG* __restrict__ dy,
                                                             float* __restrict__ dx, int H, int W, int P) {
   const int ix = blockIdx.x * 128 + threadIdx.x;
   if (ix >= W) return;
@@ -105,8 +129,8 @@ __global__ void __launch_bounds__(128) pool_bwd_rows_kernel(const float* __restr
     for (int ox = ox_lo; ox <= ox_hi; ++ox) {
       const int x0 = (ox * W) / P, x1 = ((ox + 1) * W + P - 1) / P;
       if (ix < x0 || ix >= x1) continue;
-      const float* gp = dy + (((long long)b * P + oy) * P + ox) * 3;
-      const float g0 = gp[0], g1 = gp[1], g2 = gp[2];
+      const TG* gp = dy + (((long long)b * P + oy) * P + ox) * 3;
+      const float g0 = grad_get(gp), g1 = grad_get(gp + 1), g2 = grad_get(gp + 2);
       const int area = (y1 - y0) * (x1 - x0);
       acc0 += 0.5f * g0 / area;
       acc1 += 0.5f * g1 / area;
@@ -181,48 +205,49 @@ __device__ __forceinline__ void sample3(const float* __restrict__ img, const Tap
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) o[ch] = t.w00 * a[ch] + t.w01 * b[ch] + t.w10 * c[ch] + t.w11 * d[ch];
 }
-__device__ __forceinline__ void scatter3(float* __restrict__ img, const Taps& t, int P, const float (&g)[3]) {
-  float* a = img + ((long long)t.y0 * P + t.x0) * 3;
-  float* b = img + ((long long)t.y0 * P + t.x1) * 3;
-  float* c = img + ((long long)t.y1 * P + t.x0) * 3;
-  float* d = img + ((long long)t.y1 * P + t.x1) * 3;
+// The two bilinear stages scatter in the backward (several output pixels sample one source pixel).  Float atomics would make
+// d(image) depend on the order of arrival — and one flipped bf16 rounding downstream grows to the bf16 noise floor within a few
+// layers (profiles/r02_parity_fullsize.md).  The scatter targets are therefore 64-bit FIXED-POINT accumulators (value x 2^40:
+// integer addition commutes, so the sums are bit-identical from run to run and for any sharding of the batch; resolution 9e-13,
+// range +-8e6, against gradient elements of 1e-8 .. 1e-2); the consumer of each buffer converts back while reading.
+__device__ __forceinline__ void scatter3(long long* __restrict__ img, const Taps& t, int P, const float (&g)[3]) {
+  long long* a = img + ((long long)t.y0 * P + t.x0) * 3;
+  long long* b = img + ((long long)t.y0 * P + t.x1) * 3;
+  long long* c = img + ((long long)t.y1 * P + t.x0) * 3;
+  long long* d = img + ((long long)t.y1 * P + t.x1) * 3;
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
-    if (t.w00 != 0.f) atomicAdd(a + ch, t.w00 * g[ch]);
-    if (t.w01 != 0.f) atomicAdd(b + ch, t.w01 * g[ch]);
-    if (t.w10 != 0.f) atomicAdd(c + ch, t.w10 * g[ch]);
-    if (t.w11 != 0.f) atomicAdd(d + ch, t.w11 * g[ch]);
+    if (t.w00 != 0.f) fx_add(a + ch, t.w00 * g[ch]);
+    if (t.w01 != 0.f) fx_add(b + ch, t.w01 * g[ch]);
+    if (t.w10 != 0.f) fx_add(c + ch, t.w10 * g[ch]);
+    if (t.w11 != 0.f) fx_add(d + ch, t.w11 * g[ch]);
   }
 }
 
 // out[n] = warp(in[n % n_src], hinv[n])
 __global__ void warp_fwd_kernel(const float* __restrict__ in, const float* __restrict__ hinv, float* __restrict__ out, int N,
                                 int n_src, int P, int border) {
-  const long long total = (long long)N * P * P;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % P);
-    const int oy = (int)((i / P) % P);
-    const int n = (int)(i / ((long long)P * P));
-    const Taps t = make_taps(hinv + n * 9, ox, oy, P, border);
-    float o[3];
-    sample3(in + (long long)(n % n_src) * P * P * 3, t, P, o);
-    out[i * 3 + 0] = o[0];
-    out[i * 3 + 1] = o[1];
-    out[i * 3 + 2] = o[2];
-  }
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= P) return;
+  const int oy = blockIdx.y, n = blockIdx.z;
+  const long long i = ((long long)n * P + oy) * P + ox;
+  const Taps t = make_taps(hinv + n * 9, ox, oy, P, border);
+  float o[3];
+  sample3(in + (long long)(n % n_src) * P * P * 3, t, P, o);
+  out[i * 3 + 0] = o[0];
+  out[i * 3 + 1] = o[1];
+  out[i * 3 + 2] = o[2];
 }
-// din[n % n_src] += warp^T(dout[n])   (din must be zeroed by the caller)
-__global__ void warp_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ hinv, float* __restrict__ din, int N,
+// din[n % n_src] += warp^T(dout[n])   (both fixed-point, din zeroed by the caller)
+__global__ void warp_bwd_kernel(const long long* __restrict__ dout, const float* __restrict__ hinv, long long* __restrict__ din, int N,
                                 int n_src, int P, int border) {
-  const long long total = (long long)N * P * P;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % P);
-    const int oy = (int)((i / P) % P);
-    const int n = (int)(i / ((long long)P * P));
-    const Taps t = make_taps(hinv + n * 9, ox, oy, P, border);
-    const float g[3] = {dout[i * 3], dout[i * 3 + 1], dout[i * 3 + 2]};
-    scatter3(din + (long long)(n % n_src) * P * P * 3, t, P, g);
-  }
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= P) return;
+  const int oy = blockIdx.y, n = blockIdx.z;
+  const long long i = ((long long)n * P + oy) * P + ox;
+  const Taps t = make_taps(hinv + n * 9, ox, oy, P, border);
+  const float g[3] = {fx_get(dout + i * 3), fx_get(dout + i * 3 + 1), fx_get(dout + i * 3 + 2)};
+  scatter3(din + (long long)(n % n_src) * P * P * 3, t, P, g);
 }
 
 // ------------------------------------------------------------------------------ hue / saturation jitter with forward-mode
@@ -314,11 +339,10 @@ struct FinalParams {
 // forward: -> patches [N][grid*grid][3*patch*patch] bf16   (k = c*patch^2 + py*patch + px)
 __global__ void cutout_final_fwd_kernel(FinalParams fp, __nv_bfloat16* __restrict__ patches, float* __restrict__ img_out) {
   const int P = fp.P;
-  const long long total = (long long)fp.N * P * P;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % P);
-    const int oy = (int)((i / P) % P);
-    const int n = (int)(i / ((long long)P * P));
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= P) return;
+  {
+    const int oy = blockIdx.y, n = blockIdx.z;
     const Taps t = make_taps(fp.hinv + n * 9, ox, oy, P, 0);
     float c[3];
     sample3(fp.cut1 + (long long)n * P * P * 3, t, P, c);
@@ -340,16 +364,15 @@ __global__ void cutout_final_fwd_kernel(FinalParams fp, __nv_bfloat16* __restric
     }
   }
 }
-// backward: dpatches (bf16, same layout) -> dcut1 (atomics, zeroed by caller)
-__global__ void cutout_final_bwd_kernel(FinalParams fp, const __nv_bfloat16* __restrict__ dpatches, float* __restrict__ dcut1) {
+// backward: dpatches (bf16, same layout) -> dcut1 (fixed-point accumulators, zeroed by caller)
+__global__ void cutout_final_bwd_kernel(FinalParams fp, const __nv_bfloat16* __restrict__ dpatches, long long* __restrict__ dcut1) {
   const int P = fp.P;
-  const long long total = (long long)fp.N * P * P;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % P);
-    const int oy = (int)((i / P) % P);
-    const int n = (int)(i / ((long long)P * P));
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ox >= P) return;
+  {
+    const int oy = blockIdx.y, n = blockIdx.z;
     const bool erased = ox >= fp.erase[0] && ox < fp.erase[2] && oy >= fp.erase[1] && oy < fp.erase[3];
-    if (erased) continue;
+    if (erased) return;
     const Taps t = make_taps(fp.hinv + n * 9, ox, oy, P, 0);
     float c[3];
     sample3(fp.cut1 + (long long)n * P * P * 3, t, P, c);
@@ -374,30 +397,42 @@ __global__ void cutout_final_bwd_kernel(FinalParams fp, const __nv_bfloat16* __r
 
 using namespace ffvc;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
+// one block (of whole warps, at most 256 threads) per stretch of an output row; grid = (stretches, rows, images)
+static inline unsigned row_block(int P) { return (unsigned)(P >= 256 ? 256 : (P + 31) / 32 * 32); }
+static inline dim3 row_grid(int P, int n) { return dim3((unsigned)((P + (int)row_block(P) - 1) / (int)row_block(P)), (unsigned)P, (unsigned)n); }
 
 extern "C" int ffvc_cutout_pool_fwd(const float* x, float* y, int B, int H, int W, int P, void* stream) {
-  pool_fwd_kernel<<<grid_for_c((long long)B * P * P * 3, 256), 256, 0, ST(stream)>>>(x, y, B, H, W, P);
+  if (B > 65535 || P > 65535) return set_error(FFVC_ERR_ARG, "cutout_pool_fwd: more than 65535 images or rows");
+  pool_fwd_kernel<<<row_grid(P, B), row_block(P), 0, ST(stream)>>>(x, y, B, H, W, P);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
-extern "C" int ffvc_cutout_pool_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int P, void* stream) {
+template <typename TG>
+static void pool_bwd_launch(const float* x, const TG* dy, float* dx, int B, int H, int W, int P, cudaStream_t st) {
   if (option(OPT_POOL_V2) && (long long)B * H <= 65535 && (long long)(H > W ? H : W) * (P + 1) < (1LL << 30))
-    pool_bwd_rows_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)(B * H)), 128, 0, ST(stream)>>>(x, dy, dx, H, W, P);
+    pool_bwd_rows_kernel<TG><<<dim3((unsigned)((W + 127) / 128), (unsigned)(B * H)), 128, 0, st>>>(x, dy, dx, H, W, P);
   else
-    pool_bwd_kernel<<<grid_for_c((long long)B * H * W * 3, 256), 256, 0, ST(stream)>>>(x, dy, dx, B, H, W, P);
+    pool_bwd_kernel<TG><<<grid_for_c((long long)B * H * W * 3, 256), 256, 0, st>>>(x, dy, dx, B, H, W, P);
+}
+// dy_fixed != 0: dy is the fixed-point (x 2^40, int64) buffer ffvc_cutout_warp_bwd leaves; 0: plain fp32
+extern "C" int ffvc_cutout_pool_bwd(const float* x, const void* dy, float* dx, int B, int H, int W, int P, int dy_fixed, void* stream) {
+  if (dy_fixed) pool_bwd_launch(x, reinterpret_cast<const long long*>(dy), dx, B, H, W, P, ST(stream));
+  else pool_bwd_launch(x, reinterpret_cast<const float*>(dy), dx, B, H, W, P, ST(stream));
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
 extern "C" int ffvc_cutout_warp_fwd(const float* in, const float* hinv, float* out, int N, int n_src, int P, int border,
                                     void* stream) {
-  warp_fwd_kernel<<<grid_for_c((long long)N * P * P, 256), 256, 0, ST(stream)>>>(in, hinv, out, N, n_src, P, border);
+  if (N > 65535 || P > 65535) return set_error(FFVC_ERR_ARG, "cutout_warp: more than 65535 cutouts or rows");
+  warp_fwd_kernel<<<row_grid(P, N), row_block(P), 0, ST(stream)>>>(in, hinv, out, N, n_src, P, border);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
-extern "C" int ffvc_cutout_warp_bwd(const float* dout, const float* hinv, float* din, int N, int n_src, int P, int border,
+extern "C" int ffvc_cutout_warp_bwd(const long long* dout, const float* hinv, long long* din, int N, int n_src, int P, int border,
                                     void* stream) {
-  cudaMemsetAsync(din, 0, sizeof(float) * (size_t)n_src * P * P * 3, ST(stream));
-  warp_bwd_kernel<<<grid_for_c((long long)N * P * P, 256), 256, 0, ST(stream)>>>(dout, hinv, din, N, n_src, P, border);
+  cudaMemsetAsync(din, 0, sizeof(long long) * (size_t)n_src * P * P * 3, ST(stream));
+  if (N > 65535 || P > 65535) return set_error(FFVC_ERR_ARG, "cutout_warp: more than 65535 cutouts or rows");
+  warp_bwd_kernel<<<row_grid(P, N), row_block(P), 0, ST(stream)>>>(dout, hinv, din, N, n_src, P, border);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
@@ -431,20 +466,20 @@ extern "C" int ffvc_cutout_final_fwd(const float* cut1, const float* hinv, const
   FinalParams fp;
   int rc = fill_final(fp, cut1, hinv, sat, hue, noise, facs, erase, mean, std_, N, P, patch);
   if (rc) return rc;
-  cutout_final_fwd_kernel<<<grid_for_c((long long)N * P * P, 256), 256, 0, ST(stream)>>>(
-      fp, reinterpret_cast<__nv_bfloat16*>(patches), img_out);
+  if (N > 65535 || P > 65535) return set_error(FFVC_ERR_ARG, "cutout_final: more than 65535 cutouts or rows");
+  cutout_final_fwd_kernel<<<row_grid(P, N), row_block(P), 0, ST(stream)>>>(fp, reinterpret_cast<__nv_bfloat16*>(patches), img_out);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }
 extern "C" int ffvc_cutout_final_bwd(const float* cut1, const float* hinv, const float* sat, const float* hue,
                                      const int* erase, const float* mean, const float* std_, const void* dpatches,
-                                     float* dcut1, int N, int P, int patch, void* stream) {
+                                     long long* dcut1, int N, int P, int patch, void* stream) {
   FinalParams fp;
   int rc = fill_final(fp, cut1, hinv, sat, hue, nullptr, nullptr, erase, mean, std_, N, P, patch);
   if (rc) return rc;
-  cudaMemsetAsync(dcut1, 0, sizeof(float) * (size_t)N * P * P * 3, ST(stream));
-  cutout_final_bwd_kernel<<<grid_for_c((long long)N * P * P, 256), 256, 0, ST(stream)>>>(
-      fp, reinterpret_cast<const __nv_bfloat16*>(dpatches), dcut1);
+  cudaMemsetAsync(dcut1, 0, sizeof(long long) * (size_t)N * P * P * 3, ST(stream));
+  if (N > 65535 || P > 65535) return set_error(FFVC_ERR_ARG, "cutout_final: more than 65535 cutouts or rows");
+  cutout_final_bwd_kernel<<<row_grid(P, N), row_block(P), 0, ST(stream)>>>(fp, reinterpret_cast<const __nv_bfloat16*>(dpatches), dcut1);
   FFVC_CHECK_LAUNCH();
   return FFVC_OK;
 }

@@ -485,25 +485,41 @@ __global__ void image_post_bwd_kernel(const float* __restrict__ g, const float* 
 //   y[p][co] = bias[co] + sum_tap v[p + off(tap)][tap*COUT + co]   (zero outside the image = padding 1)
 // It also applies the image post-processing xr = clamp((y + 1) / 2, 0, 1) (main.py:142) when xr != nullptr.
 // CTA = 8 rows x 32 pixels: the 10 x 34 rows of v it touches (one 128-byte line each) stay in L1 across the taps.
+// CTA = 8 rows x 32 pixels.  The 10 x 34 source rows of v it needs (one 128-byte line each) are staged in shared memory with
+// coalesced 16-byte loads (8 lanes per line; row pitch 33 floats so that the per-pixel reads below are bank-conflict free) —
+// reading them straight from global memory, one 4-byte load per lane at a 128-byte stride, kept L1 at 97 % for 408 us against
+// ~95 us of HBM time (profiles/r02_ncu_hbm_kernels.md).
 template <int COUT>
 __global__ void __launch_bounds__(256) conv_taps_gather_kernel(const float* __restrict__ v, const float* __restrict__ bias,
                                                                float* __restrict__ y, float* __restrict__ xr, int H, int W) {
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int yy = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int n = blockIdx.z;
+  constexpr int TW = 34, TH = 10, PITCH = 33;
+  __shared__ float sv[TH * TW * PITCH];                  // 44,880 B
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8, n = blockIdx.z;
+  const float* vn = v + (long long)n * H * W * 32;
+  for (int i = threadIdx.x; i < TH * TW * 8; i += 256) {
+    const int piece = i & 7, line = i >> 3;
+    const int ly = line / TW, lx = line - ly * TW;
+    const int sy = y0 + ly - 1, sx = x0 + lx - 1;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);          // outside the image: zero (padding 1)
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) q = *reinterpret_cast<const float4*>(vn + ((long long)sy * W + sx) * 32 + piece * 4);
+    float* d = sv + line * PITCH + piece * 4;
+    d[0] = q.x;
+    d[1] = q.y;
+    d[2] = q.z;
+    d[3] = q.w;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int x = x0 + lx, yy = y0 + ly;
   if (x >= W || yy >= H) return;
   float acc[COUT];
 #pragma unroll
   for (int c = 0; c < COUT; ++c) acc[c] = bias ? bias[c] : 0.f;
-  const float* vn = v + (long long)n * H * W * 32;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    const int sy = yy + tap / 3 - 1, sx = x + tap % 3 - 1;
-    if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-      const float* src = vn + ((long long)sy * W + sx) * 32 + tap * COUT;
+    const float* src = sv + ((ly + tap / 3) * TW + lx + tap % 3) * PITCH + tap * COUT;
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] += src[c];
-    }
+    for (int c = 0; c < COUT; ++c) acc[c] += src[c];
   }
   const long long o = (((long long)n * H + yy) * W + x) * COUT;
 #pragma unroll

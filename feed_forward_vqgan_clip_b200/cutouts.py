@@ -163,13 +163,14 @@ class CutoutEngine:
         P, N = self.P, self.cutn * B
         prm = saved["prm"]
         dev = self.dev
-        dcut1 = torch.empty(N, P, P, 3, device=dev, dtype=F32)
+        # the two scatter stages accumulate in 64-bit fixed point (x 2^40): reproducible d(image), see include/ffvc.h
+        dcut1 = torch.empty(N, P, P, 3, device=dev, dtype=torch.int64)
         call("cutout_final_bwd", saved["cut1"], prm["persp_inv"], prm["sat"], prm["hue"], saved["erase"],
              self._C.addressof(self._mean), self._C.addressof(self._std), dpatches, dcut1, N, P, self.patch)
-        dpooled = torch.empty(B, P, P, 3, device=dev, dtype=F32)
+        dpooled = torch.empty(B, P, P, 3, device=dev, dtype=torch.int64)
         call("cutout_warp_bwd", dcut1, prm["affine_inv"], dpooled, N, B, P, 1)
         dimg = torch.empty(B, H, W, 3, device=dev, dtype=F32)
-        call("cutout_pool_bwd", saved["img"], dpooled, dimg, B, H, W, P)
+        call("cutout_pool_bwd", saved["img"], dpooled, dimg, B, H, W, P, 1)
         return dimg
 
 

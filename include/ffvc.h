@@ -303,15 +303,18 @@ int ffvc_copy_rows(const void* src, void* dst, long long rows, int D, long long 
 
 /* MakeCutouts (main.py:212-229) on NHWC fp32 3-channel images, explicit augmentation parameters. */
 int ffvc_cutout_pool_fwd(const float* x, float* y, int B, int H, int W, int P, void* stream);
-int ffvc_cutout_pool_bwd(const float* x, const float* dy, float* dx, int B, int H, int W, int P, void* stream);
+/* Backward buffers between the three stages (dcut1 of ffvc_cutout_final_bwd, dout / din of ffvc_cutout_warp_bwd, dy of
+ * ffvc_cutout_pool_bwd with dy_fixed != 0) are 64-bit FIXED-POINT accumulators, value x 2^40: the bilinear stages scatter, and
+ * integer addition commutes, so d(image) is reproducible bit for bit (float atomics are not; resolution 9e-13, range +-8e6). */
+int ffvc_cutout_pool_bwd(const float* x, const void* dy, float* dx, int B, int H, int W, int P, int dy_fixed, void* stream);
 int ffvc_cutout_warp_fwd(const float* in, const float* hinv, float* out, int N, int n_src, int P, int border, void* stream);
-int ffvc_cutout_warp_bwd(const float* dout, const float* hinv, float* din, int N, int n_src, int P, int border, void* stream);
+int ffvc_cutout_warp_bwd(const long long* dout, const float* hinv, long long* din, int N, int n_src, int P, int border, void* stream);
 /* erase: DEVICE int[4] (x0,y0,x1,y1); mean, std (3 floats each) are HOST pointers. patches: [N][(P/patch)^2][3*patch^2] bf16. */
 int ffvc_cutout_final_fwd(const float* cut1, const float* hinv, const float* sat, const float* hue, const float* noise,
                           const float* facs, const int* erase, const float* mean, const float* std_, void* patches,
                           float* img_out, int N, int P, int patch, void* stream);
 int ffvc_cutout_final_bwd(const float* cut1, const float* hinv, const float* sat, const float* hue, const int* erase,
-                          const float* mean, const float* std_, const void* dpatches, float* dcut1, int N, int P, int patch,
+                          const float* mean, const float* std_, const void* dpatches, long long* dcut1, int N, int P, int patch,
                           void* stream);
 
 /* spherical distance loss fwd+bwd (main.py:801-811): loss_out (1 float), dembed fp32 and/or bf16 [N][D]. */

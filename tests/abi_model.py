@@ -513,10 +513,27 @@ def k_cutout_pool_fwd(x, y, B, H, W, P):
     y.view(-1)[:B * P * P * 3] = _pool(_nhwc(x, B, H, W, 3).permute(0, 3, 1, 2), P).permute(0, 2, 3, 1).reshape(-1)
 
 
-def k_cutout_pool_bwd(x, dy, dx, B, H, W, P):
+_FX = float(2 ** 40)       # fixed-point scale of the cutout backward's scatter buffers (include/ffvc.h)
+
+
+def _fx_load(t, n):
+    v = t.reshape(-1)[:n]
+    return v.double().div(_FX).float() if v.dtype == torch.int64 else v.float()
+
+
+def _fx_store(t, vals):
+    n = vals.numel()
+    if t.dtype == torch.int64:
+        t.view(-1)[:n] = (vals.double().reshape(-1) * _FX).round().to(torch.int64)
+    else:
+        t.view(-1)[:n] = vals.reshape(-1)
+
+
+def k_cutout_pool_bwd(x, dy, dx, B, H, W, P, dy_fixed=0):
+    assert bool(dy_fixed) == (dy.dtype == torch.int64)
     with torch.enable_grad():
         xi = _nhwc(x, B, H, W, 3).permute(0, 3, 1, 2).clone().requires_grad_(True)
-        g, = torch.autograd.grad(_pool(xi, P), xi, _nhwc(dy, B, P, P, 3).permute(0, 3, 1, 2))
+        g, = torch.autograd.grad(_pool(xi, P), xi, _fx_load(dy, B * P * P * 3).view(B, P, P, 3).permute(0, 3, 1, 2))
     dx.view(-1)[:B * H * W * 3] = g.permute(0, 2, 3, 1).reshape(-1)
 
 
@@ -532,8 +549,10 @@ def k_cutout_warp_fwd(inp, hinv, out, N, n_src, P, border):
 def k_cutout_warp_bwd(dout, hinv, din, N, n_src, P, border):
     with torch.enable_grad():
         xi = torch.zeros(n_src, 3, P, P, requires_grad=True)
-        g, = torch.autograd.grad(_warp_stage(xi, hinv, N, n_src, border), xi, _nhwc(dout, N, P, P, 3).permute(0, 3, 1, 2))
-    din.view(-1)[:n_src * P * P * 3] = g.permute(0, 2, 3, 1).reshape(-1)
+        g, = torch.autograd.grad(_warp_stage(xi, hinv, N, n_src, border), xi,
+                                 _fx_load(dout, N * P * P * 3).view(N, P, P, 3).permute(0, 3, 1, 2))
+    assert din.dtype == torch.int64 and dout.dtype == torch.int64, "fixed-point scatter buffers (include/ffvc.h)"
+    _fx_store(din, g.permute(0, 2, 3, 1))
 
 
 def _final_stage(c_nchw, hinv, sat, hue, erase, N, P):
@@ -569,7 +588,8 @@ def k_cutout_final_bwd(cut1, hinv, sat, hue, erase, mean, std, dpatches, dcut1, 
     with torch.enable_grad():
         ci = _nhwc(cut1, N, P, P, 3).permute(0, 3, 1, 2).clone().requires_grad_(True)
         gr, = torch.autograd.grad(_final_stage(ci, hinv, sat, hue, erase, N, P), ci, dp)
-    dcut1.view(-1)[:N * P * P * 3] = gr.permute(0, 2, 3, 1).reshape(-1)
+    assert dcut1.dtype == torch.int64, "fixed-point scatter buffer (include/ffvc.h)"
+    _fx_store(dcut1, gr.permute(0, 2, 3, 1))
 
 
 def k_spherical_loss(embed, target, loss_out, dembed, dembed_bf16, N, B, D, coef):

@@ -79,7 +79,7 @@ def test_sharded_writers_reassemble_to_the_single_writer_files(tmp_path):
         w = ck.CheckpointWriter(ts, str(many), config="cfg", rank=r, world=world, sharded=True, snapshot_cls=HostSnapshot)
         assert (w.hi - w.lo) <= (ts.mix.arena.numel() + world - 1) // world
         w.save(7, 1, blocking=True)
-    assert sorted(os.listdir(many)) == ["checkpoint.index.th"] + ["checkpoint.shard-%02d-of-03.th" % r for r in range(3)]
+    assert sorted(os.listdir(many)) == ["checkpoint.index.th"] + ["checkpoint.shard-%02d-of-03.step-7.th" % r for r in range(3)]
     c, e, o = ck.load_sharded(str(many))
     c1 = torch.load(one / "checkpoint.th", weights_only=False)
     e1 = torch.load(one / "checkpoint_ema.th", weights_only=False)
@@ -90,6 +90,15 @@ def test_sharded_writers_reassemble_to_the_single_writer_files(tmp_path):
     assert o["param_groups"] == o1["param_groups"]
     for i in o1["state"]:
         assert torch.equal(o["state"][i]["exp_avg_sq"], o1["state"][i]["exp_avg_sq"])
+    # a later generation whose shards are incomplete (a rank died before writing): the previous complete one is loaded
+    writers = [ck.CheckpointWriter(ts, str(many), config="cfg", rank=r, world=world, sharded=True, snapshot_cls=HostSnapshot) for r in range(2)]
+    for w in writers:                                    # rank 2 never writes step 9
+        w.save(9, 1, blocking=True)
+    assert os.path.exists(many / "checkpoint.index.prev.th")
+    c2, _, _ = ck.load_sharded(str(many))
+    assert c2["step"] == 7
+    ck.CheckpointWriter(ts, str(many), config="cfg", rank=2, world=world, sharded=True, snapshot_cls=HostSnapshot).save(9, 1, blocking=True)
+    assert ck.load_sharded(str(many))[0]["step"] == 9
     # replicas other than rank 0 stay silent in the reference's (unsharded) mode
     w = ck.CheckpointWriter(ts, str(tmp_path / "none"), rank=1, world=2, sharded=False, snapshot_cls=HostSnapshot)
     w.save(1, 0, blocking=True)

@@ -439,7 +439,7 @@ def test_cutout_pool_bwd_row_kernel_matches_flat_kernel_and_autograd(B, H, P, ff
     for v2 in (0, 1):
         ffvc_options(pool_v2=v2)
         dx = torch.full((B, H, H, 3), 7.0, device=DEV)
-        call("cutout_pool_bwd", x, dy, dx, B, H, H, P)
+        call("cutout_pool_bwd", x, dy, dx, B, H, H, P, 0)
         outs.append(dx)
     assert torch.allclose(outs[0], outs[1], rtol=1e-6, atol=1e-7)       # same arithmetic per element
     xr = x.permute(0, 3, 1, 2).clone().requires_grad_(True)          # main.py:218 on NCHW

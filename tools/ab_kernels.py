@@ -161,7 +161,7 @@ def main():
 
     def pool(i):
         s = ps[i]
-        call("cutout_pool_bwd", s["x"], s["dy"], s["dx"], B, H, H, P)
+        call("cutout_pool_bwd", s["x"], s["dy"], s["dx"], B, H, H, P, 0)
 
     for v2 in (0, 1):
         setopt(pool_v2=v2)
