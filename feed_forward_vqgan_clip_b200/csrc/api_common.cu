@@ -18,7 +18,7 @@ int set_error(int code, const char* msg) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- kernel-selection switches.  Defaults are the variants measured faster on B200 (profiles/); FFVC_OPTS overrides.
-static const char* const kOptNames[OPT_COUNT] = {"ln_fwd_v2", "ln_bwd_v2", "pool_v2", "gn_ring", "halo_epi16", "sm_limit"};
+static const char* const kOptNames[OPT_COUNT] = {"ln_fwd_v2", "ln_bwd_v2", "pool_v2", "gn_ring", "halo_epi16", "sm_limit", "gemm_quad"};
 static std::atomic<int> g_opts[OPT_COUNT];
 static std::once_flag g_opts_once;
 static int opt_index(const char* name) {
@@ -28,7 +28,7 @@ static int opt_index(const char* name) {
   return -1;
 }
 static void opts_init() {
-  static const int defaults[OPT_COUNT] = {2, 1, 1, 1, 0, 0}   /* measured: profiles/r01_ab_kernels.md */;
+  static const int defaults[OPT_COUNT] = {2, 1, 1, 1, 0, 0, 0}   /* measured: profiles/r01_ab_kernels.md */;
   for (int i = 0; i < OPT_COUNT; ++i) g_opts[i].store(defaults[i]);
   const char* env = getenv("FFVC_OPTS");
   if (!env) return;

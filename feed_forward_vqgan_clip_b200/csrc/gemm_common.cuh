@@ -37,6 +37,7 @@ struct GemmDev {
   int mul_mode;   // multiply by act'(aux): FFVC_ACT_*
   float alpha;
   unsigned long long* argmin;   // optional: per-row arg-min epilogue (see ffvc_gemm_params.argmin_out)
+  int quad;                     // CTA-pair kernel in clusters of 4: two M-adjacent pair tiles share the B tile through TMA multicast
   int stream_k;                 // 1: contiguous (tile, k-block) ranges per worker instead of whole tiles (atomic fp32 output)
   int tma_store;                // 1: the epilogue warps stage their results in shared memory and TMA-store them
   double* gn_ws;                // conv3x3_halo only: per-(image, group) sum / sum of squares of the stored output (GroupNorm(32) statistics)

@@ -110,14 +110,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = kTwoCta ? cluster_ctarank() : 0u;
+  // CTA pair: rank = 0 (leader, issues the MMAs) / 1.  Quad (p.quad, cluster of 4): pair_id = 0 / 1 are two pair tiles adjacent in M
+  // that share one B tile: every CTA fetches only HALF of its B rows and TMA-multicasts them to its counterpart in the other pair
+  // (24 KB instead of 32 KB of L2 -> SM traffic per CTA and k-block; the large GEMMs run at the chip's L2 -> SM limit, ~6300 B/clk:
+  // tensor pipe 65 % active with every other unit below 40 %, profiles/r02_ncu_gemm_family.md)
+  const uint32_t rank4 = kTwoCta ? cluster_ctarank() : 0u;
+  const uint32_t rank = rank4 & 1u;
+  const bool quad = kTwoCta && p.quad != 0;
+  const uint32_t pair_id = rank4 >> 1;
+  const uint32_t leader_cta = rank4 & ~1u;
+  const uint16_t pair_mask = (uint16_t)(3u << (2u * pair_id));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < kStagesT; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), quad ? 2 : 1);     // quad: a stage is free once BOTH pairs' MMAs have retired (multicast destinations)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -142,11 +151,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int tiles_m = (p.M + p.tile_m - 1) / p.tile_m;
   const int tiles_n = (p.N + p.block_n - 1) / p.block_n;
-  const int tiles_per_batch = tiles_m * tiles_n;
+  const int tiles_m_it = quad ? (tiles_m >> 1) : tiles_m;     // quad: one work item = two M-adjacent pair tiles
+  const int tiles_per_batch = tiles_m_it * tiles_n;
   const int total_kb = p.kb_per_seg * p.k_segs;
   const long long tiles_all_batches = (long long)tiles_per_batch * p.batch;
-  const long long tile_first = kTwoCta ? (blockIdx.x >> 1) : blockIdx.x;
-  const long long tile_step = kTwoCta ? (gridDim.x >> 1) : gridDim.x;
+  const int wshift = kTwoCta ? (quad ? 2 : 1) : 0;
+  const long long tile_first = blockIdx.x >> wshift;
+  const long long tile_step = gridDim.x >> wshift;
   const int rows_cta = kTwoCta ? 128 : p.tile_m;             // rows of A this CTA stages
   const int bn_cta = kTwoCta ? (p.block_n >> 1) : p.block_n;  // rows of B this CTA stages
   const uint32_t a_bytes = (uint32_t)rows_cta * kBlockK * 2;
@@ -166,7 +177,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int rem, kb_begin, kb_end;
       while (it.next(rem, kb_begin, kb_end)) {
         const int bi = rem / tiles_per_batch;
-        const int tm = (rem % tiles_per_batch) / tiles_n;
+        int tm = (rem % tiles_per_batch) / tiles_n;
+        if (quad) tm = 2 * tm + (int)pair_id;
         const int tn = rem % tiles_n;
         const int m0 = tm * p.tile_m + (kTwoCta ? (int)rank * 128 : 0);
         const int n0 = tn * p.block_n + (kTwoCta ? (int)rank * bn_cta : 0);
@@ -208,7 +220,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           {
             const int c2 = (p.b_role == FFVC_ROLE_OUT_BATCH) ? bi_in : 0;
             const int c3 = (p.b_role == FFVC_ROLE_OUT_BATCH) ? bi_out : (p.b_role == FFVC_ROLE_K_SEGMENT ? seg : 0);
-            if (p.b_mode == FFVC_OP_KMAJOR) {
+            if (quad) {
+              // this CTA's half of the B rows it shares with CTA (rank4 ^ 2): rows [n0 + pair_id * bn_cta / 2, + bn_cta / 2)
+              const uint16_t mc = (uint16_t)((1u << rank) | (1u << (2u + rank)));
+              const int hrows = bn_cta >> 1;
+              if (p.b_mode == FFVC_OP_KMAJOR) {
+                tma_load_4d_2sm_mc(sb + pair_id * (uint32_t)hrows * 128u, &tmap_b, fb, k0, n0 + (int)pair_id * hrows, c2, c3, mc);
+              } else {
+                const int nch = hrows / 64;                       // 64-row chunks in this CTA's share
+                for (int j = 0; j < nch; ++j) {
+                  const int jj = (int)pair_id * nch + j;
+                  tma_load_4d_2sm_mc(sb + jj * 8192, &tmap_b, fb, n0 + 64 * jj, k0, c2, c3, mc);
+                }
+              }
+            } else if (p.b_mode == FFVC_OP_KMAJOR) {
               tma4(sb, &tmap_b, fb, k0, n0, c2, c3);
             } else {
               for (int j = 0; j < bn_cta / 64; ++j) tma4(sb + j * 8192, &tmap_b, fb, n0 + 64 * j, k0, c2, c3);
@@ -262,14 +287,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
-          if (kTwoCta) umma_commit_2sm(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+          if (kTwoCta) umma_commit_2sm(empty_bar(stage), quad ? (uint16_t)0xF : pair_mask); else umma_commit(empty_bar(stage));
           if (++stage == kStagesT) {
             stage = 0;
             phase ^= 1u;
           }
         }
         // accumulator ready for the epilogue warps (of both CTAs)
-        if (kTwoCta) umma_commit_2sm(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
+        if (kTwoCta) umma_commit_2sm(tfull_bar(acc), pair_mask); else umma_commit(tfull_bar(acc));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -319,7 +344,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int rem, kb_begin_unused, kb_end_unused;
     while (it.next(rem, kb_begin_unused, kb_end_unused)) {
       const int bi = rem / tiles_per_batch;
-      const int tm = (rem % tiles_per_batch) / tiles_n;
+      int tm = (rem % tiles_per_batch) / tiles_n;
+      if (quad) tm = 2 * tm + (int)pair_id;
       const int tn = rem % tiles_n;
       const int gm = tm * p.tile_m + row_in_tile;
       const int n0 = tn * p.block_n;
@@ -433,7 +459,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (kTwoCta) mbar_arrive_cluster(tempty_bar(acc), 0); else mbar_arrive(tempty_bar(acc));
+        if (kTwoCta) mbar_arrive_cluster(tempty_bar(acc), leader_cta); else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == 2) {
         acc = 0;
@@ -502,6 +528,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t*
 }
 
 static int g_num_sms = 0;
+static int g_max_quads = -1;          // co-resident clusters of 4 CTAs (GPC sizes are not all multiples of 4): queried once
 static bool g_attr_set = false;
 static int g_stream_k_enabled = 0;    // ffvc_gemm_set_stream_k(1): measured no better than split-K on this workload (the wgrad
                                       // GEMMs are L2-operand-bandwidth bound, not tail bound), so it is opt-in
@@ -570,6 +597,9 @@ static int set_gemm_attrs() {
 }  // namespace ffvc
 
 using namespace ffvc;
+
+/* co-resident clusters of 4 CTAs of the CTA-pair GEMM kernel (-1 until the first quad launch queried it) */
+extern "C" int ffvc_gemm_max_quads(void) { return g_max_quads; }
 
 extern "C" int ffvc_gemm_set_stream_k(int on) {
   g_stream_k_enabled = on ? 1 : 0;
@@ -646,6 +676,29 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   if (two_cta != 1 && tile_m == 256 && block_n > 128) return set_error(FFVC_ERR_ARG, "gemm: tile_m 256 needs block_n <= 128");
   const int rows_cta = (two_cta == 1) ? 128 : tile_m;          // A rows staged per CTA
   const int bn_cta = (two_cta == 1) ? block_n / 2 : block_n;   // B rows staged per CTA
+  // quad: clusters of 4 = two M-adjacent pair tiles sharing the B tile by TMA multicast (option "gemm_quad")
+  const int tiles_m_host = (g->M + tile_m - 1) / tile_m;
+  bool quad = two_cta == 1 && option(OPT_GEMM_QUAD) != 0 && tiles_m_host % 2 == 0 && bn_cta >= 128 && !g->argmin_out;
+  if (quad && g_max_quads < 0) {
+    // how many clusters of 4 fit the GPU at once (a persistent grid must not exceed it: the excess clusters would run as a second wave)
+    cudaLaunchConfig_t qc;
+    memset(&qc, 0, sizeof(qc));
+    cudaLaunchAttribute qa[1];
+    qc.gridDim = dim3((unsigned)(g_num_sms / 4 * 4));
+    qc.blockDim = dim3(64 + 32 * 16);
+    qc.dynamicSmemBytes = kSmemBytes;
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = 4;
+    qa[0].val.clusterDim.y = 1;
+    qa[0].val.clusterDim.z = 1;
+    qc.attrs = qa;
+    qc.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<true, 16, -1, false>, &qc) != cudaSuccess) n = 0;
+    cudaGetLastError();
+    g_max_quads = n;
+  }
+  if (quad && g_max_quads < 8) quad = false;       // no room for clusters of 4: stay on pairs
 
   GemmDev p;
   memset(&p, 0, sizeof(p));
@@ -727,7 +780,7 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     if (g->b_mode == FFVC_OP_KMAJOR) {
       uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->N, n_in, n_out};
       uint64_t str[4] = {1, (uint64_t)g->b_ld, s_in, s_out};
-      uint32_t box[4] = {64, (uint32_t)bn_cta, 1, 1};
+      uint32_t box[4] = {64, (uint32_t)(quad ? bn_cta / 2 : bn_cta), 1, 1};      // quad: every CTA fetches half of its rows
       if ((rc = make_tmap(&tb, g->b, 4, dims, str, box)) != FFVC_OK) return rc;
     } else {
       uint64_t dims[4] = {(uint64_t)g->N, (uint64_t)g->K, n_in, n_out};
@@ -744,7 +797,8 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     const long long total_kb_h = (long long)p.kb_per_seg * k_segs;
     const long long waves_x100 = tiles0 * splits * 100 / workers;            // work items per worker, in percent
     const bool uneven = (waves_x100 % 100) != 0 && waves_x100 < 800;         // a fractional last wave that matters
-    p.stream_k = (g_stream_k_enabled && g->out_fp32 && g->atomic && !g->argmin_out && !g->bias && !g->res && !g->aux && !g->pre_out &&
+    p.quad = quad ? 1 : 0;
+    p.stream_k = (!quad && g_stream_k_enabled && g->out_fp32 && g->atomic && !g->argmin_out && !g->bias && !g->res && !g->aux && !g->pre_out &&
                   g->act == FFVC_ACT_NONE && uneven && tiles0 * total_kb_h >= 4 * workers) ? 1 : 0;
     if (p.stream_k) splits = p.splits = 1;
   }
@@ -785,7 +839,21 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
   cfg.blockDim = dim3(nthreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
-  if (two_cta == 1) {
+  if (two_cta == 1 && quad) {
+    // one cluster of 4 (two pairs) per two M-adjacent tiles, persistent over min(items, SMs/4) clusters
+    const int sms = sm_budget(g_num_sms);
+    const long long items = tiles / 2;
+    int cap = sms / 4 < g_max_quads ? sms / 4 : g_max_quads;
+    if (cap < 1) cap = 1;
+    const long long quads = items >= cap ? cap : items;
+    cfg.gridDim = dim3((unsigned)(4 * quads));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else if (two_cta == 1) {
     // one CTA pair (cluster of 2) per tile, persistent over min(tiles, SMs/2) pairs
     const int sms = sm_budget(g_num_sms);     // tile shapes above are chosen for the whole GPU (same arithmetic); only the grid shrinks
     const long long pairs = (p.stream_k || tiles >= sms / 2) ? sms / 2 : tiles;

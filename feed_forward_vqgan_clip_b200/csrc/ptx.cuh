@@ -179,6 +179,16 @@ __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const void* desc, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// Same, multicast: the box lands at the same shared-memory offset in every CTA of `mask` (cluster ranks), and the transaction
+// bytes are credited, per destination CTA, to the mbarrier at `bar`'s offset in that CTA's PAIR LEADER (peer bit cleared).
+__device__ __forceinline__ void tma_load_4d_2sm_mc(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2, int c3,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
 }

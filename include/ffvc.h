@@ -128,6 +128,11 @@ int ffvc_gemm_set_tma_store(int on);
  * k-blocks of the linearised (tile, k-block) space); 0 (default): split-K as requested by the caller.  Measured equal or
  * slightly slower than split-K on config #2 (those GEMMs are bound by L2 -> SM operand traffic), hence opt-in. */
 int ffvc_gemm_set_stream_k(int on);
+/* option "gemm_quad" (ffvc_set_option, default 0): the CTA-pair kernel in clusters of 4 — two M-adjacent pair tiles share their B
+ * tile through TMA multicast (every CTA fetches half of its B rows and multicasts them to its counterpart in the other pair: 24 KB
+ * instead of 32 KB of L2 -> SM traffic per CTA and k-block).  Same results bit for bit.  ffvc_gemm_max_quads: how many such
+ * clusters the GPU holds at once (-1 before the first quad launch). */
+int ffvc_gemm_max_quads(void);
 
 /* 3x3 conv (pad 1, stride 1) with shared-memory halo reuse: NHWC bf16 x [n][h][w][cin], packed weights [cout][9][cin]
  * (tap-major, as for FFVC_OP_CONV3X3), bf16 out [n*h*w][ldc].  Requires w % 128 == 0, even h, cin % 64 == 0, cout <= 128:

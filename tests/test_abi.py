@@ -271,7 +271,7 @@ def test_every_compute_entry_point_has_a_cpu_statement_of_its_contract():
     host-checkable statement.  The single-kernel GroupNorm forms must agree with the two-pass model they alias."""
     import abi_model
     control = {"ffvc_arch", "ffvc_last_error", "ffvc_launch_count", "ffvc_reset_launch_count", "ffvc_set_option", "ffvc_get_option",
-               "ffvc_sizeof", "ffvc_gemm_set_stream_k", "ffvc_gemm_set_tma_store", "ffvc_groupnorm_set_pipeline",
+               "ffvc_sizeof", "ffvc_gemm_set_stream_k", "ffvc_gemm_max_quads", "ffvc_gemm_set_tma_store", "ffvc_groupnorm_set_pipeline",
                "ffvc_groupnorm_ws_bytes", "ffvc_groupnorm_ws_doubles", "ffvc_layernorm_bwd_ws_bytes"}
     declared = set(_lib.header_declarations())
     modelled = {"ffvc_" + n[2:] for n in dir(abi_model) if n.startswith("k_")} | {"ffvc_gemm"}

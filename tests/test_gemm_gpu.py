@@ -511,3 +511,50 @@ def test_conv3x3_halo_with_fused_groupnorm_apply(n, h, w, cin, cout, with_res, w
         m2, r2 = torch.empty_like(m1), torch.empty_like(r1)
         call("groupnorm_stats", outs[1], ws, m2, r2, n, h * w, cout, 32, 1e-6)
         assert torch.allclose(m1, m2, atol=1e-5, rtol=1e-5) and torch.allclose(r1, r2, rtol=1e-4)
+
+
+@pytest.mark.parametrize("M,N,K,kind", [(1024, 512, 256, "kk"), (2048, 1024, 1024, "kk"), (2048, 768, 640, "km"), (1024, 512, 4096, "mm"),
+                                        (1536, 256, 320, "kk")])
+def test_gemm_cluster_of_four_multicast_matches_the_pair_kernel(M, N, K, kind, ffvc_options):
+    """option gemm_quad: clusters of 4 CTAs, two M-adjacent pair tiles share their B tile through TMA multicast (each CTA fetches half
+    of its B rows, UTMALDG.MULTICAST.2CTA) — bit-identical to the pair kernel for K-major / MN-major operands, fused epilogues and the
+    fp32-atomic wgrad form (same K order per element); shapes whose tile rows are odd (1536 / 256 = 6 is even, 1280 would not be) or
+    narrower than 256 columns fall back to pairs"""
+    from feed_forward_vqgan_clip_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    BFD = torch.bfloat16
+
+    def run(out):
+        if kind == "mm":
+            ops.gemm(a, b, out, M, N, K, a_mode=ops.MNMAJOR, b_mode=ops.MNMAJOR, a_ld=M, b_ld=N, atomic=True, two_cta=1)
+        elif kind == "km":
+            ops.gemm(a, b, out, M, N, K, b_mode=ops.MNMAJOR, b_ld=N, res=res, two_cta=1)
+        else:
+            ops.gemm(a, b, out, M, N, K, bias=bias, act=ops.ACT_GELU, pre_out=pre, two_cta=1)
+
+    if kind == "mm":
+        a, b = torch.randn(K, M, generator=g).to(DEV).to(BFD), torch.randn(K, N, generator=g).to(DEV).to(BFD)
+        outs = [torch.zeros(M, N, device=DEV) for _ in range(2)]
+    elif kind == "km":
+        a, b = torch.randn(M, K, generator=g).to(DEV).to(BFD), torch.randn(K, N, generator=g).to(DEV).to(BFD)
+        res = torch.randn(M, N, generator=g).to(DEV).to(BFD)
+        outs = [torch.empty(M, N, device=DEV, dtype=BFD) for _ in range(2)]
+    else:
+        a, b = torch.randn(M, K, generator=g).to(DEV).to(BFD), torch.randn(N, K, generator=g).to(DEV).to(BFD)
+        bias = torch.randn(N, generator=g).to(DEV)
+        pre = torch.empty(M, N, device=DEV, dtype=BFD)
+        outs = [torch.empty(M, N, device=DEV, dtype=BFD) for _ in range(2)]
+    ffvc_options(gemm_quad=0)
+    run(outs[0])
+    pre0 = pre.clone() if kind == "kk" else None
+    ffvc_options(gemm_quad=1)
+    run(outs[1])
+    torch.cuda.synchronize()
+    if kind == "mm":                       # fp32 atomics: the order of the k-block partial sums may differ
+        assert torch.allclose(outs[0], outs[1], rtol=1e-5, atol=1e-3)
+        ref = a.float().t() @ b.float()
+        assert torch.allclose(outs[1], ref, rtol=2e-2, atol=2e-1)
+    else:
+        assert torch.equal(outs[0], outs[1])
+        if kind == "kk":
+            assert torch.equal(pre0, pre)
