@@ -5,7 +5,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libffvc_sm100.so")
+LIB_PATH = os.environ.get("FFVC_LIB") or os.path.join(_HERE, "libffvc_sm100.so")     # FFVC_LIB: another build of the same ABI (A/B runs)
 HEADER_PATH = os.path.join(_HERE, "..", "include", "ffvc.h")
 _lib = None
 _decls = None
@@ -81,6 +81,8 @@ def load():
             "(or __graft_entry__.build()).  There is no fallback path." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (ret, argtypes) in header_declarations().items():
+        if os.environ.get("FFVC_LIB") and not hasattr(lib, name):
+            continue                     # an older build under A/B: symbols added since are simply absent
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.restype = ret
         fn.argtypes = argtypes

@@ -85,7 +85,7 @@ struct WorkIter {
 //   HALF of the B tile; the leader CTA issues tcgen05.mma M=256 that reads both CTAs' shared memory, so every SM
 //   reads / is written only (A + B/2) per k-step instead of (A + B): the 1-CTA kernel is shared-memory-bandwidth
 //   bound (128 B/clk/SM) at ~55-65 % of the tensor pipe, the pair removes a third of that traffic.  6-stage ring.
-template <bool kTwoCta, int kEpiWarps, int kEpi, bool kTma>
+template <bool kTwoCta, int kEpiWarps, int kEpi, bool kTma, bool kQuad = false>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_pre, const GemmDev p) {
@@ -110,16 +110,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // CTA pair: rank = 0 (leader, issues the MMAs) / 1.  Quad (p.quad, cluster of 4): pair_id = 0 / 1 are two pair tiles adjacent in M
+  // CTA pair: rank = 0 (leader, issues the MMAs) / 1.  Quad (kQuad, launched in clusters of 4 when p.quad): pair_id = 0 / 1 are two pair tiles adjacent in M
   // that share one B tile: every CTA fetches only HALF of its B rows and TMA-multicasts them to its counterpart in the other pair
   // (24 KB instead of 32 KB of L2 -> SM traffic per CTA and k-block; the large GEMMs run at the chip's L2 -> SM limit, ~6300 B/clk:
   // tensor pipe 65 % active with every other unit below 40 %, profiles/r02_ncu_gemm_family.md)
   const uint32_t rank4 = kTwoCta ? cluster_ctarank() : 0u;
-  const uint32_t rank = rank4 & 1u;
-  const bool quad = kTwoCta && p.quad != 0;
-  const uint32_t pair_id = rank4 >> 1;
-  const uint32_t leader_cta = rank4 & ~1u;
-  const uint16_t pair_mask = (uint16_t)(3u << (2u * pair_id));
+  const uint32_t rank = kQuad ? (rank4 & 1u) : rank4;
+  // kQuad is a compile-time variant (generic epilogue only): as a run-time flag it cost the default pair kernels 1 % of the step
+  constexpr bool quad = kTwoCta && kQuad;
+  const uint32_t pair_id = quad ? (rank4 >> 1) : 0u;
+  const uint32_t leader_cta = quad ? (rank4 & ~1u) : 0u;
+  const uint16_t pair_mask = quad ? (uint16_t)(3u << (2u * pair_id)) : (uint16_t)3;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -564,6 +565,10 @@ static cudaError_t launch_wide(const cudaLaunchConfig_t& cfg, int epi, const CUt
 }
 static cudaError_t launch_gemm(const cudaLaunchConfig_t& cfg, bool two_cta, bool wide_epi, int epi, const CUtensorMap* tm,
                                const GemmDev& p) {
+  if (two_cta && p.quad) {
+    if (wide_epi) return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 16, -1, false, true>, tm[0], tm[1], tm[2], tm[3], p);
+    return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true, 8, -1, false, true>, tm[0], tm[1], tm[2], tm[3], p);
+  }
   if (wide_epi) return two_cta ? launch_wide<true>(cfg, epi, tm, p) : launch_wide<false>(cfg, epi, tm, p);
   return two_cta ? launch_one<true, 8, -1>(cfg, tm, p) : launch_one<false, 8, -1>(cfg, tm, p);
 }
@@ -590,6 +595,10 @@ static cudaError_t set_attr_all() {
 static int set_gemm_attrs() {
   cudaError_t e = set_attr_all<false>();
   if (e == cudaSuccess) e = set_attr_all<true>();
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true, 8, -1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true, 16, -1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
   if (e != cudaSuccess) return set_error(FFVC_ERR_CUDA, cudaGetErrorString(e));
   return FFVC_OK;
 }
@@ -694,7 +703,7 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     qc.attrs = qa;
     qc.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<true, 16, -1, false>, &qc) != cudaSuccess) n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<true, 16, -1, false, true>, &qc) != cudaSuccess) n = 0;
     cudaGetLastError();
     g_max_quads = n;
   }
@@ -833,6 +842,7 @@ extern "C" int ffvc_gemm(const ffvc_gemm_params* g, void* stream_v) {
     for (int i = 0; i < kNumEpiCodes; ++i)
       if (kEpiCodes[i] == code) epi = code;
   }
+  if (quad) epi = -1;        // the cluster-of-4 variant is instantiated with the run-time epilogue only
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cudaLaunchAttribute attr[1];

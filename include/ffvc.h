@@ -130,7 +130,8 @@ int ffvc_gemm_set_tma_store(int on);
 int ffvc_gemm_set_stream_k(int on);
 /* option "gemm_quad" (ffvc_set_option, default 0): the CTA-pair kernel in clusters of 4 — two M-adjacent pair tiles share their B
  * tile through TMA multicast (every CTA fetches half of its B rows and multicasts them to its counterpart in the other pair: 24 KB
- * instead of 32 KB of L2 -> SM traffic per CTA and k-block).  Same results bit for bit.  ffvc_gemm_max_quads: how many such
+ * instead of 32 KB of L2 -> SM traffic per CTA and k-block; a separate kernel instantiation with the run-time epilogue).  Same
+ * results bit for bit.  ffvc_gemm_max_quads: how many such
  * clusters the GPU holds at once (-1 before the first quad launch). */
 int ffvc_gemm_max_quads(void);
 
